@@ -1,0 +1,208 @@
+/*
+ * phi_gpu_index.h — C ABI of the B200-native PHI front end (ILP_index stage).
+ *
+ * The reference has no plugin/FFI interface; the seam this library replaces is
+ * INSIDE ILP_index::ILP_function, between /root/reference/src/ILP_index.cpp:543
+ * (first statement after the "Graph has ..." log line) and :752 (end of the
+ * in_nodes loop is :745-752 and stays on the caller's side; the replaced range
+ * is :543-743).  Caller before the seam: main() (/root/reference/src/main.cpp:140).
+ * Consumer after the seam: the Gurobi model construction reading
+ * Anchor_hits[i][j][k] and count_sp_r (/root/reference/src/ILP_index.cpp:786-833,
+ * :838-879).  INTEGRATION.md shows the adapter a PHI maintainer would add.
+ *
+ * Plain pointers and sizes only: no C++ types, no exceptions, no torch types
+ * cross this boundary.  There is NO CPU fallback: every entry point that
+ * computes fails with PHI_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Ownership: the caller owns every input buffer for the duration of a call;
+ * the library owns a phi_index_result until phi_gpu_index_result_free().
+ * A ctx is single-threaded (one ctx per host thread / per GPU), re-entrant
+ * across ctxs.
+ */
+#ifndef PHI_GPU_INDEX_H
+#define PHI_GPU_INDEX_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHI_GPU_INDEX_ABI_VERSION 1
+
+/* status codes (0 == ok); text via phi_gpu_last_error() */
+enum {
+    PHI_OK = 0,
+    PHI_ERR_ARG = 1,          /* bad argument / inconsistent view */
+    PHI_ERR_UNSUPPORTED = 2,  /* legal for the reference but not implemented here (e.g. k > 32): hard error, never a silent divergence */
+    PHI_ERR_CUDA = 3,         /* CUDA runtime / no device */
+    PHI_ERR_NOMEM = 4,
+    PHI_ERR_COMM = 5          /* NCCL / multi-GPU exchange */
+};
+
+/*
+ * Graph, flat view of what ILP_index::read_gfa() builds
+ * (/root/reference/src/ILP_index.cpp:20-155):
+ *   seg_off/seg_bases  <- node_seq[v]   (:35)  original case, ASCII, concatenated
+ *   walk_off/walk_vtx  <- paths[h]      (:110) forward-strand vertex ids, W-line order
+ *   top_order_map      <- top_order_map (:150-154) Kahn order index per vertex
+ * Vertex id = segment index by first appearance (/root/reference/src/gfa-base.cpp:75-96).
+ */
+typedef struct {
+    uint32_t n_vtx;
+    const uint64_t *seg_off;        /* [n_vtx + 1] */
+    const uint8_t *seg_bases;       /* [seg_off[n_vtx]] */
+    uint32_t n_walks;
+    const uint64_t *walk_off;       /* [n_walks + 1] */
+    const uint32_t *walk_vtx;       /* [walk_off[n_walks]] */
+    const int32_t *top_order_map;   /* [n_vtx] */
+} phi_graph_view;
+
+/* Reads, flat view of ip_reads[r].second (/root/reference/src/ILP_index.cpp:313-328, :620). */
+typedef struct {
+    uint64_t n_reads;
+    const uint64_t *read_off;       /* [n_reads + 1] */
+    const uint8_t *read_bases;      /* [read_off[n_reads]] ASCII, any case */
+} phi_reads_view;
+
+/*
+ * Parameters = the ILP_index members the replaced range reads
+ * (/root/reference/src/ILP_index.h:72-81; set in /root/reference/src/main.cpp:118-131):
+ * k_mer (-k, 31), window (-w, 25), threshold (-T, 1.0f), debug (-d).
+ */
+typedef struct {
+    int32_t k;
+    int32_t w;
+    float threshold;
+    int32_t debug;
+} phi_index_params;
+
+/*
+ * Result = everything that crosses the seam.
+ *
+ * count_sp_r / spectrum : ILP_index.cpp:631-636 — number of distinct read
+ *     minimizer hashes and the hashes themselves in ascending unsigned order;
+ *     rank r <-> spectrum[r].
+ * anchors (CSR, FINAL post-filter order) : ILP_index.cpp:643-716.  Anchor a is
+ *     Anchor_hits[anchor_rank[a]][anchor_walk[a]][j] with j = its index among
+ *     the anchors of the same (rank, walk), and its vertex list is
+ *     anchor_vtx[anchor_off[a] .. anchor_off[a+1]).  Anchors are sorted by
+ *     (rank, walk, j), so a single forward pass with push_back rebuilds the
+ *     reference's nested vectors exactly.
+ * minimizers_per_walk : kmer_index[h].size(), log line ILP_index.cpp:563.
+ * anchors_per_walk    : log lines ILP_index.cpp:725-735.
+ * n_filtered          : filtered_kmers, ILP_index.cpp:719-721 (log :738-743).
+ */
+typedef struct {
+    int32_t count_sp_r;
+    uint32_t n_walks;
+    int64_t n_filtered;
+    uint64_t n_anchors;
+    uint64_t n_anchor_vtx;
+    const uint64_t *spectrum;            /* [count_sp_r] */
+    const int32_t *anchor_rank;          /* [n_anchors] */
+    const int32_t *anchor_walk;          /* [n_anchors] */
+    const uint64_t *anchor_off;          /* [n_anchors + 1] */
+    const int32_t *anchor_vtx;           /* [n_anchor_vtx] */
+    const uint64_t *minimizers_per_walk; /* [n_walks] */
+    const uint64_t *anchors_per_walk;    /* [n_walks] */
+    /* work counters of this run (for throughput / roofline arithmetic) */
+    uint64_t read_kmer_positions;        /* sum_r max(0, len_r - k + 1) over reads with len_r >= w + k - 1 */
+    uint64_t path_kmer_positions;        /* same over walks */
+    uint64_t read_minimizers_emitted;    /* table inserts attempted */
+    uint64_t path_minimizers_emitted;    /* sum of minimizers_per_walk (== probes) */
+    uint64_t path_hits;                  /* probes that found a rank (pre-filter anchors) */
+} phi_index_result;
+
+/* Per-stage device times of the last run, CUDA events on the ctx's stream (ms). */
+typedef struct {
+    float h2d_ms;            /* host -> device copies of graph + reads (0 for a resident run) */
+    float graph_prep_ms;     /* step base offsets, tile directory */
+    float read_sketch_ms;    /* read minimizers -> HBM hash table */
+    float spectrum_ms;       /* compact + sort + bucket directory */
+    float walk_sketch_ms;    /* walk minimizers + probe + anchor emit (dominant kernel) */
+    float filter_ms;         /* group count, threshold, ordering, CSR */
+    float d2h_ms;            /* device -> host copies of the result */
+    float total_ms;          /* first event to last event */
+    float walk_kernel_ms;    /* the walk sketch kernel alone (roofline numerator's denominator) */
+    float read_kernel_ms;    /* the read sketch kernel alone */
+    uint64_t kernel_launches;/* kernels launched by this library during the run */
+} phi_stage_times;
+
+typedef struct phi_gpu_index_ctx phi_gpu_index_ctx;
+
+/* device < 0 selects the current device.  Fails (PHI_ERR_CUDA) without a GPU. */
+int phi_gpu_index_create(int device, phi_gpu_index_ctx **out);
+void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx);
+/* Last error text of this ctx (or of create() when ctx == NULL). Never NULL. */
+const char *phi_gpu_last_error(const phi_gpu_index_ctx *ctx);
+int phi_gpu_index_abi_version(void);
+
+/*
+ * The drop-in call: replaces ILP_index.cpp:543-743.  Host buffers in, host
+ * result out; H2D and D2H copies happen inside.
+ */
+int phi_gpu_index_run(phi_gpu_index_ctx *ctx, const phi_graph_view *graph, const phi_reads_view *reads,
+                      const phi_index_params *params, phi_index_result **out);
+
+/*
+ * Resident variant (used to time the device path alone): upload once, then run
+ * any number of times on the HBM-resident inputs.  `download` != 0 copies the
+ * result to the host (then *out is set); with download == 0 *out receives a
+ * result whose array pointers are NULL but whose scalar counters are valid.
+ */
+int phi_gpu_index_upload(phi_gpu_index_ctx *ctx, const phi_graph_view *graph, const phi_reads_view *reads);
+int phi_gpu_index_run_resident(phi_gpu_index_ctx *ctx, const phi_index_params *params, int download,
+                               phi_index_result **out);
+
+void phi_gpu_index_result_free(phi_index_result *res);
+int phi_gpu_index_last_times(const phi_gpu_index_ctx *ctx, phi_stage_times *out);
+
+/*
+ * Walk sketch alone == ILP_index::index_kmers for every walk
+ * (/root/reference/src/ILP_index.cpp:359-445): every emitted minimizer of every
+ * walk, in path order, with its hash and its vertex list.  Returned through a
+ * phi_index_result in which  spectrum == NULL,  anchor_rank[a] is unused (0),
+ * anchors are in (walk, path position) order and  *hashes_out[a]  is the
+ * minimizer hash.  Free *hashes_out with phi_gpu_index_free_u64.
+ */
+int phi_gpu_index_sketch_walks(phi_gpu_index_ctx *ctx, const phi_graph_view *graph, const phi_index_params *params,
+                               phi_index_result **out, uint64_t **hashes_out);
+void phi_gpu_index_free_u64(uint64_t *p);
+
+/*
+ * Device MurmurHash3_x64_128(key, len, seed 0) -> out[0]^out[1], i.e. the
+ * reference's hash128_to_64 (/root/reference/src/ILP_index.cpp:10-18;
+ * /root/reference/src/MurmurHash3.cpp:255-332), over n keys of `len` bytes
+ * each, packed back to back.  Known-answer-test hook.
+ */
+int phi_gpu_hash128_to_64(phi_gpu_index_ctx *ctx, const uint8_t *keys, uint64_t n, int32_t len, uint64_t *out);
+
+/*
+ * Multi-GPU (one ctx per GPU, one process or thread per ctx).  The 128-byte
+ * id comes from phi_gpu_index_comm_unique_id() on rank 0 and is distributed by
+ * the caller (torch.distributed store, MPI, a file ...).  After comm_init,
+ * phi_gpu_index_run / _run_resident treat `reads` and the walks of `graph` as
+ * THIS RANK'S SHARD (segments and top_order_map replicated), exchange read
+ * minimizer hashes by hash range (all-to-all), all-gather the spectrum, route
+ * hits to the owner of their rank, and return on every rank the anchors whose
+ * rank it owns; phi_shard_* below describe the partition.  walk ids in the
+ * result are global: walk_id_base + local index.
+ */
+#define PHI_COMM_ID_BYTES 128
+int phi_gpu_index_comm_unique_id(uint8_t id[PHI_COMM_ID_BYTES]);
+int phi_gpu_index_comm_init(phi_gpu_index_ctx *ctx, int rank, int world, const uint8_t id[PHI_COMM_ID_BYTES],
+                            uint32_t walk_id_base, uint32_t n_walks_global);
+
+/* Host-only partition helpers (no GPU needed). */
+/* owner rank of a hash under the range partition on the high bits */
+int phi_shard_owner_of_hash(uint64_t hash, int world);
+/* contiguous, size-balanced split of n items with per-item weights off[i+1]-off[i] into `world` parts:
+ * writes world+1 boundaries into bounds[] */
+int phi_shard_split_by_weight(const uint64_t *off, uint64_t n, int world, uint64_t *bounds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHI_GPU_INDEX_H */

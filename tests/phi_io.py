@@ -1,0 +1,165 @@
+"""Test helpers: .phiarr reader (written by oracle/ref_build/ref_probe.cpp), model-dump parser
+(written by oracle/ref_build/stub/gurobi_c++.h), oracle ctypes binding.  Test infrastructure only."""
+import ctypes as C
+import hashlib
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+
+from phi_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+_DT = {"B": np.uint8, "i": np.int32, "I": np.uint32, "Q": np.uint64, "q": np.int64}
+
+
+def read_phiarr(path):
+    out = {}
+    with open(path, "rb") as f:
+        data = f.read()
+    p = 0
+    while p < len(data):
+        (nl,) = struct.unpack_from("<I", data, p); p += 4
+        name = data[p:p + nl].decode(); p += nl
+        dt = chr(data[p]); p += 1
+        (n,) = struct.unpack_from("<Q", data, p); p += 8
+        dtype = np.dtype(_DT[dt])
+        out[name] = np.frombuffer(data, dtype=dtype, count=n, offset=p).copy()
+        p += n * dtype.itemsize
+    return out
+
+
+def graph_from_arrays(d):
+    names = bytes(d["walk_names"]).decode().split("\n")[:-1] if "walk_names" in d else []
+    return _abi.Graph(d["seg_off"], d["seg_bases"], d["walk_off"], d["walk_vtx"], d["top_order_map"], names)
+
+
+def reads_from_arrays(d):
+    return _abi.Reads(d["read_off"], d["read_bases"])
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ---------------------------------------------------------------- model dump
+_EDGE = re.compile(r"^(\d+)_(\d+)_(\d+)_(\d+)$")
+
+
+def parse_model_dump(path):
+    """Recover what the dump pins about Anchor_hits: for every z_i_j_k (creation order) the vertex list
+    implied by its edge variables (None for single-vertex anchors, which create no constraint terms).
+    Works for both -q1 (Q records) and -q0 (C Kmer_constraints_i_j_k records)."""
+    z_order = []          # (i, j, k) in creation order
+    lists = {}            # (i, j, k) -> [v0, v1, ...]
+    n = {"V": 0, "C": 0, "Q": 0}
+    with open(path) as f:
+        for line in f:
+            t = line[0]
+            if t in n:
+                n[t] += 1
+            if t == "V" and line.startswith("V z_"):
+                parts = line.split()[1].split("_")
+                if len(parts) == 4:
+                    z_order.append((int(parts[1]), int(parts[2]), int(parts[3])))
+            elif t == "Q" and line.startswith("Q Kmer_constraints_"):
+                quad = line.split("|")[1].split(";")[1].split()
+                cur = {}
+                for term in quad:               # coeff*u_j_v_j*z_i_j_k, in walk order
+                    _, e, z = term.split("*")
+                    m = _EDGE.match(e)
+                    zi = tuple(int(x) for x in z.split("_")[1:])
+                    lst = cur.setdefault(zi, [])
+                    if not lst:
+                        lst.append(int(m.group(1)))
+                    lst.append(int(m.group(3)))
+                lists.update(cur)
+            elif t == "C" and line.startswith("C Kmer_constraints_"):
+                name = line.split()[1]
+                idx = name[len("Kmer_constraints_"):].split("_")
+                if len(idx) == 3:
+                    lhs = line.split("|")[1].split()
+                    lst = []
+                    for term in lhs:
+                        _, e = term.split("*")
+                        m = _EDGE.match(e)
+                        if not lst:
+                            lst.append(int(m.group(1)))
+                        lst.append(int(m.group(3)))
+                    lists[tuple(int(x) for x in idx)] = lst
+    return z_order, lists, n
+
+
+# -------------------------------------------------------------------- oracle
+_oracle = None
+
+
+def oracle_lib():
+    """ctypes handle on oracle/libphi_oracle.so, building it with gcc if needed (test infra only)."""
+    global _oracle
+    if _oracle is None:
+        so = os.path.join(ROOT, "oracle", "libphi_oracle.so")
+        src = os.path.join(ROOT, "oracle", "phi_oracle.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libphi_oracle.so"],
+                                  stdout=subprocess.DEVNULL)
+        lib = C.CDLL(so)
+        lib.phi_oracle_hash128_to_64.restype = C.c_uint64
+        lib.phi_oracle_hash128_to_64.argtypes = [C.c_char_p, C.c_int32]
+        lib.phi_oracle_index_run.restype = C.c_int
+        lib.phi_oracle_index_run.argtypes = [C.POINTER(_abi.GraphView), C.POINTER(_abi.ReadsView),
+                                             C.POINTER(_abi.IndexParams), C.c_int,
+                                             C.POINTER(C.POINTER(_abi.IndexResult))]
+        lib.phi_oracle_sketch_walks.restype = C.c_int
+        lib.phi_oracle_sketch_walks.argtypes = [C.POINTER(_abi.GraphView), C.POINTER(_abi.IndexParams), C.c_int,
+                                                C.POINTER(C.POINTER(_abi.IndexResult)), C.POINTER(_abi.u64p)]
+        lib.phi_oracle_read_hashes.restype = C.c_int64
+        lib.phi_oracle_read_hashes.argtypes = [C.c_char_p, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(_abi.u64p)]
+        lib.phi_oracle_result_free.argtypes = [C.POINTER(_abi.IndexResult)]
+        lib.phi_oracle_free.argtypes = [C.c_void_p]
+        _oracle = lib
+    return _oracle
+
+
+def oracle_hash(key: bytes) -> int:
+    return oracle_lib().phi_oracle_hash128_to_64(key, len(key))
+
+
+def oracle_index(graph, reads, k=31, w=25, threshold=1.0, threads=0):
+    lib = oracle_lib()
+    gv, rv = graph.view(), reads.view()
+    prm = _abi.IndexParams(k, w, threshold, 0)
+    out = C.POINTER(_abi.IndexResult)()
+    rc = lib.phi_oracle_index_run(C.byref(gv), C.byref(rv), C.byref(prm), threads, C.byref(out))
+    assert rc == 0, rc
+    res = _abi.result_to_py(out.contents)
+    lib.phi_oracle_result_free(out)
+    return res
+
+
+def oracle_sketch_walks(graph, k=31, w=25, threads=0):
+    lib = oracle_lib()
+    gv = graph.view()
+    prm = _abi.IndexParams(k, w, 1.0, 0)
+    out = C.POINTER(_abi.IndexResult)()
+    hp = _abi.u64p()
+    rc = lib.phi_oracle_sketch_walks(C.byref(gv), C.byref(prm), threads, C.byref(out), C.byref(hp))
+    assert rc == 0, rc
+    res = _abi.result_to_py(out.contents)
+    hashes = _abi._np_from(hp, res.n_anchors, np.uint64)
+    lib.phi_oracle_result_free(out)
+    lib.phi_oracle_free(hp)
+    return res, hashes
+
+
+def oracle_read_hashes(seq: bytes, k=31, w=25):
+    lib = oracle_lib()
+    hp = _abi.u64p()
+    n = lib.phi_oracle_read_hashes(seq, len(seq), k, w, C.byref(hp))
+    a = _abi._np_from(hp, n, np.uint64)
+    lib.phi_oracle_free(hp)
+    return a
