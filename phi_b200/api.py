@@ -1,0 +1,140 @@
+"""ctypes binding of include/phi_gpu_index.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class PhiGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"phi_gpu_index error {code}: {msg}")
+        self.code = code
+
+
+def library_path():
+    return os.path.join(_HERE, "libphi_gpu_index.so")
+
+
+def load_library():
+    """Load libphi_gpu_index.so.  Raises if it has not been built (no fallback of any kind)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise PhiGpuError(-1, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    ctxp = C.c_void_p
+    resp = C.POINTER(_abi.IndexResult)
+    lib.phi_gpu_index_abi_version.restype = C.c_int
+    lib.phi_gpu_index_create.restype = C.c_int
+    lib.phi_gpu_index_create.argtypes = [C.c_int, C.POINTER(ctxp)]
+    lib.phi_gpu_index_destroy.argtypes = [ctxp]
+    lib.phi_gpu_last_error.restype = C.c_char_p
+    lib.phi_gpu_last_error.argtypes = [ctxp]
+    lib.phi_gpu_index_run.restype = C.c_int
+    lib.phi_gpu_index_run.argtypes = [ctxp, C.POINTER(_abi.GraphView), C.POINTER(_abi.ReadsView),
+                                      C.POINTER(_abi.IndexParams), C.POINTER(resp)]
+    lib.phi_gpu_index_upload.restype = C.c_int
+    lib.phi_gpu_index_upload.argtypes = [ctxp, C.POINTER(_abi.GraphView), C.POINTER(_abi.ReadsView)]
+    lib.phi_gpu_index_run_resident.restype = C.c_int
+    lib.phi_gpu_index_run_resident.argtypes = [ctxp, C.POINTER(_abi.IndexParams), C.c_int, C.POINTER(resp)]
+    lib.phi_gpu_index_result_free.argtypes = [resp]
+    lib.phi_gpu_index_last_times.restype = C.c_int
+    lib.phi_gpu_index_last_times.argtypes = [ctxp, C.POINTER(_abi.StageTimes)]
+    lib.phi_gpu_index_sketch_walks.restype = C.c_int
+    lib.phi_gpu_index_sketch_walks.argtypes = [ctxp, C.POINTER(_abi.GraphView), C.POINTER(_abi.IndexParams),
+                                               C.POINTER(resp), C.POINTER(_abi.u64p)]
+    lib.phi_gpu_index_free_u64.argtypes = [_abi.u64p]
+    lib.phi_gpu_hash128_to_64.restype = C.c_int
+    lib.phi_gpu_hash128_to_64.argtypes = [ctxp, C.c_char_p, C.c_uint64, C.c_int32, _abi.u64p]
+    lib.phi_shard_owner_of_hash.restype = C.c_int
+    lib.phi_shard_owner_of_hash.argtypes = [C.c_uint64, C.c_int]
+    lib.phi_shard_split_by_weight.restype = C.c_int
+    lib.phi_shard_split_by_weight.argtypes = [_abi.u64p, C.c_uint64, C.c_int, _abi.u64p]
+    _LIB = lib
+    return lib
+
+
+class PhiGpuIndex:
+    """One ctx == one GPU == one CUDA stream.  Mirrors the C ABI one to one."""
+
+    def __init__(self, device=-1):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.lib.phi_gpu_index_create(device, C.byref(self.ctx))
+        if rc != _abi.PHI_OK:
+            raise PhiGpuError(rc, self.lib.phi_gpu_last_error(None).decode())
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.phi_gpu_index_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != _abi.PHI_OK:
+            raise PhiGpuError(rc, self.lib.phi_gpu_last_error(self.ctx).decode())
+
+    @staticmethod
+    def _params(k, w, threshold, debug=0):
+        return _abi.IndexParams(int(k), int(w), float(threshold), int(debug))
+
+    def _take(self, resp, free=True):
+        res = _abi.result_to_py(resp.contents)
+        if free:
+            self.lib.phi_gpu_index_result_free(resp)
+        return res
+
+    def run(self, graph, reads, k=31, w=25, threshold=1.0):
+        """Host buffers in, host result out (H2D + kernels + D2H): the drop-in call."""
+        gv, rv, prm = graph.view(), reads.view(), self._params(k, w, threshold)
+        out = C.POINTER(_abi.IndexResult)()
+        self._check(self.lib.phi_gpu_index_run(self.ctx, C.byref(gv), C.byref(rv), C.byref(prm), C.byref(out)))
+        return self._take(out)
+
+    def upload(self, graph, reads):
+        gv, rv = graph.view(), reads.view()
+        self._check(self.lib.phi_gpu_index_upload(self.ctx, C.byref(gv), C.byref(rv)))
+
+    def run_resident(self, k=31, w=25, threshold=1.0, download=True):
+        prm = self._params(k, w, threshold)
+        out = C.POINTER(_abi.IndexResult)()
+        self._check(self.lib.phi_gpu_index_run_resident(self.ctx, C.byref(prm), 1 if download else 0, C.byref(out)))
+        return self._take(out)
+
+    def times(self):
+        t = _abi.StageTimes()
+        self._check(self.lib.phi_gpu_index_last_times(self.ctx, C.byref(t)))
+        return t.as_dict()
+
+    def sketch_walks(self, graph, k=31, w=25):
+        """ILP_index::index_kmers for every walk: (result in (walk, path) order, hashes)."""
+        gv, prm = graph.view(), self._params(k, w, 1.0)
+        out = C.POINTER(_abi.IndexResult)()
+        hp = _abi.u64p()
+        self._check(self.lib.phi_gpu_index_sketch_walks(self.ctx, C.byref(gv), C.byref(prm), C.byref(out), C.byref(hp)))
+        res = _abi.result_to_py(out.contents)
+        hashes = _abi._np_from(hp, res.n_anchors, np.uint64)
+        self.lib.phi_gpu_index_result_free(out)
+        self.lib.phi_gpu_index_free_u64(hp)
+        return res, hashes
+
+    def hash128_to_64(self, keys, length):
+        """Device MurmurHash3_x64_128 -> h0^h1 over len(keys)//length packed keys."""
+        n = len(keys) // length
+        out = np.zeros(n, dtype=np.uint64)
+        self._check(self.lib.phi_gpu_hash128_to_64(self.ctx, bytes(keys), n, length, out.ctypes.data_as(_abi.u64p)))
+        return out

@@ -1,0 +1,286 @@
+// Threshold filter + final ordering of the walk hits
+// (/root/reference/src/ILP_index.cpp:670-722), on the device.
+//
+// Reference semantics (SURVEY.md §9 rule 10): per rank r, hits are grouped by their vertex list; if
+// ANY group has count >= threshold * num_walks (float compare) the whole rank is dropped; otherwise
+// the hits are re-emitted in std::map<std::string> order of the key "v0_v1_..._" and, inside a
+// group, in insertion order (walk asc, path position asc).  The final index j inside
+// Anchor_hits[r][h] is therefore (key order, position) among the hits of (r, h).
+//
+// Device formulation:
+//   1. group table  : open addressing over (rank, vertex list) -> count, exact (lists are compared,
+//                     the hash only picks the start slot).
+//   2. mark         : a slot whose count reaches the threshold drops its rank.
+//   3. survivors    : compaction + stable radix sort on (rank, global path coordinate).
+//   4. multi-hit fix: only (rank, walk) groups with >= 2 hits need the decimal-string key order;
+//                     small groups by insertion sort in one thread, big ones by a block rank sort.
+//   5. CSR          : scan of list lengths + gather.
+#include "kernels.h"
+#include "device_common.cuh"
+
+namespace phi {
+
+#define PHI_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; if (launches) ++*launches; } while (0)
+
+constexpr uint32_t G_EMPTY = 0xFFFFFFFFu;
+constexpr int SMALL_GROUP = 48;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+__device__ __forceinline__ bool same_list(const FilterArgs &A, uint32_t a, uint32_t b)
+{
+    if (A.hit_rank[a] != A.hit_rank[b]) return false;
+    uint32_t n = A.hit_nv[a];
+    if (n != A.hit_nv[b]) return false;
+    const int32_t *pa = A.vtx_pool + A.hit_voff[a], *pb = A.vtx_pool + A.hit_voff[b];
+    for (uint32_t i = 0; i < n; ++i) if (pa[i] != pb[i]) return false;
+    return true;
+}
+
+__global__ void group_count_kernel(FilterArgs A, FilterWork W)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= A.n_hits) return;
+    const int32_t *p = A.vtx_pool + A.hit_voff[i];
+    uint32_t n = A.hit_nv[i];
+    uint64_t hsh = mix64(A.hit_rank[i] + 0x9E3779B97F4A7C15ull);
+    for (uint32_t q = 0; q < n; ++q) hsh = mix64(hsh ^ (uint64_t)(uint32_t)p[q]);
+    const uint64_t mask = W.g_cap - 1;
+    uint64_t slot = hsh & mask;
+    for (;;) {
+        uint32_t rep = W.g_rep[slot];
+        if (rep == G_EMPTY) {
+            uint32_t old = atomicCAS(&W.g_rep[slot], G_EMPTY, (uint32_t)i);
+            rep = old == G_EMPTY ? (uint32_t)i : old;
+        }
+        if (rep == (uint32_t)i || same_list(A, (uint32_t)i, rep)) { atomicAdd(&W.g_cnt[slot], 1u); return; }
+        slot = (slot + 1) & mask;
+    }
+}
+
+__global__ void mark_drop_kernel(FilterArgs A, FilterWork W)
+{
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= W.g_cap) return;
+    uint32_t rep = W.g_rep[s];
+    if (rep == G_EMPTY) return;
+    // anchor.second.first >= threshold * num_walks  — int32 promoted to float (:698)
+    if ((float)(int32_t)W.g_cnt[s] >= A.thr) W.rank_drop[A.hit_rank[rep]] = 1;
+}
+
+__global__ void count_drops_kernel(const uint8_t *rank_drop, uint32_t n, unsigned long long *ctr)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = i < n ? rank_drop[i] : 0;
+    uint32_t b = __ballot_sync(0xFFFFFFFFu, v != 0);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&ctr[CTR_FILTERED], (unsigned long long)__popc(b));
+}
+
+__global__ void flag_survivors_kernel(FilterArgs A, FilterWork W)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= A.n_hits) return;
+    W.flags[i] = W.rank_drop[A.hit_rank[i]] ? 0u : 1u;
+}
+
+// flags[] has been exclusive-scanned in place; a hit survives iff its rank is not dropped
+__global__ void emit_keys_kernel(FilterArgs A, FilterWork W, int combined)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= A.n_hits) return;
+    uint32_t r = A.hit_rank[i];
+    if (W.rank_drop[r]) return;
+    uint32_t j = W.flags[i];
+    uint64_t gpos = A.walk_gbase[A.hit_walk[i]] + A.hit_pos[i];
+    W.keys_a[j] = combined ? (((uint64_t)r << A.gpos_bits) | gpos) : gpos;
+    W.vals_a[j] = (uint32_t)i;
+}
+
+// second-stage key when (rank, gpos) does not fit one u64: key = rank of vals[j]
+__global__ void rank_keys_kernel(FilterArgs A, const uint32_t *vals, uint64_t *keys, uint64_t n)
+{
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j < n) keys[j] = A.hit_rank[vals[j]];
+}
+
+cudaError_t filter_count_groups(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches)
+{
+    if (!A.n_hits) return cudaSuccess;
+    group_count_kernel<<<(unsigned)((A.n_hits + 255) / 256), 256, 0, st>>>(A, W);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t filter_mark_drops(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches)
+{
+    if (A.n_hits) {
+        mark_drop_kernel<<<(unsigned)((W.g_cap + 255) / 256), 256, 0, st>>>(A, W);
+        PHI_LAUNCH_CHECK();
+    }
+    if (A.n_ranks) {
+        count_drops_kernel<<<(A.n_ranks + 255) / 256, 256, 0, st>>>(W.rank_drop, A.n_ranks, W.ctr);
+        PHI_LAUNCH_CHECK();
+    }
+    return cudaSuccess;
+}
+cudaError_t filter_flag_survivors(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches)
+{
+    if (!A.n_hits) return cudaSuccess;
+    flag_survivors_kernel<<<(unsigned)((A.n_hits + 255) / 256), 256, 0, st>>>(A, W);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t filter_emit_keys(const FilterArgs &A, const FilterWork &W, uint64_t n_surv, bool combined, cudaStream_t st, uint64_t *launches)
+{
+    if (!A.n_hits || !n_surv) return cudaSuccess;
+    emit_keys_kernel<<<(unsigned)((A.n_hits + 255) / 256), 256, 0, st>>>(A, W, combined ? 1 : 0);
+    PHI_LAUNCH_CHECK();
+    if (combined) return radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n_surv, 0, A.gpos_bits + A.rank_bits, W.sort_scratch, st, launches);
+    cudaError_t e = radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n_surv, 0, A.gpos_bits, W.sort_scratch, st, launches);
+    if (e != cudaSuccess) return e;
+    rank_keys_kernel<<<(unsigned)((n_surv + 255) / 256), 256, 0, st>>>(A, W.vals_a, W.keys_a, n_surv);
+    PHI_LAUNCH_CHECK();
+    return radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n_surv, 0, A.rank_bits, W.sort_scratch, st, launches);
+}
+
+// ---- decimal-string order of "v0_v1_..._" keys ('_' sorts after every digit)
+__device__ __forceinline__ int ndigits(uint32_t v)
+{
+    int d = 1;
+    while (v >= 10) { v /= 10; ++d; }
+    return d;
+}
+__device__ __forceinline__ int cmp_dec(uint32_t a, uint32_t b)        // order of to_string(a)+"_" vs to_string(b)+"_"
+{
+    if (a == b) return 0;
+    int da = ndigits(a), db = ndigits(b);
+    if (da == db) return a < b ? -1 : 1;
+    if (da < db) {                                                    // a shorter: compare a with the first da digits of b
+        uint32_t bp = b; for (int i = 0; i < db - da; ++i) bp /= 10;
+        if (a != bp) return a < bp ? -1 : 1;
+        return 1;                                                     // a is a proper prefix: a's '_' meets a digit of b -> a sorts after
+    }
+    uint32_t ap = a; for (int i = 0; i < da - db; ++i) ap /= 10;
+    if (ap != b) return ap < b ? -1 : 1;
+    return -1;
+}
+__device__ int cmp_list(const FilterArgs &A, uint32_t x, uint32_t y)
+{
+    uint32_t nx = A.hit_nv[x], ny = A.hit_nv[y];
+    const int32_t *px = A.vtx_pool + A.hit_voff[x], *py = A.vtx_pool + A.hit_voff[y];
+    uint32_t n = nx < ny ? nx : ny;
+    for (uint32_t i = 0; i < n; ++i) { int c = cmp_dec((uint32_t)px[i], (uint32_t)py[i]); if (c) return c; }
+    return nx == ny ? 0 : nx < ny ? -1 : 1;                           // proper prefix string sorts first
+}
+
+__device__ __forceinline__ bool same_rw(const FilterArgs &A, uint32_t x, uint32_t y)
+{
+    return A.hit_rank[x] == A.hit_rank[y] && A.hit_walk[x] == A.hit_walk[y];
+}
+
+// order[] = hit ids sorted by (rank, walk, position).  Each thread owning the head of a (rank, walk) group with >= 2 members
+// re-orders it by (key string, position): stable insertion sort for small groups, deferral for big ones.
+__global__ void fix_multi_kernel(FilterArgs A, uint32_t *order, uint64_t n, uint32_t *big_list, uint32_t big_cap, unsigned long long *ctr)
+{
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t me = order[j];
+    if (j > 0 && same_rw(A, order[j - 1], me)) return;               // not a head
+    if (j + 1 >= n || !same_rw(A, order[j + 1], me)) return;         // singleton
+    uint64_t e = j + 2;
+    while (e < n && same_rw(A, order[e], me)) ++e;
+    uint64_t len = e - j;
+    if (len > SMALL_GROUP) {
+        unsigned long long slot = atomicAdd(&ctr[CTR_BIG_GROUPS], 1ull);
+        if (slot < big_cap) { big_list[2 * slot] = (uint32_t)j; big_list[2 * slot + 1] = (uint32_t)len; }
+        return;
+    }
+    for (uint64_t a = j + 1; a < e; ++a) {
+        uint32_t x = order[a]; uint64_t b = a;
+        while (b > j && cmp_list(A, order[b - 1], x) > 0) { order[b] = order[b - 1]; --b; }
+        order[b] = x;
+    }
+}
+
+// one block per big group: rank sort (stable: ties keep the incoming position order)
+__global__ void fix_big_kernel(FilterArgs A, uint32_t *order, uint32_t *tmp, const uint32_t *big_list)
+{
+    const uint32_t j0 = big_list[2 * blockIdx.x], len = big_list[2 * blockIdx.x + 1];
+    for (uint32_t a = threadIdx.x; a < len; a += blockDim.x) {
+        uint32_t x = order[j0 + a], pos = 0;
+        for (uint32_t b = 0; b < len; ++b) {
+            if (b == a) continue;
+            int c = cmp_list(A, order[j0 + b], x);
+            pos += (c < 0) || (c == 0 && b < a);
+        }
+        tmp[j0 + pos] = x;
+    }
+    __syncthreads();
+    for (uint32_t a = threadIdx.x; a < len; a += blockDim.x) order[j0 + a] = tmp[j0 + a];
+}
+
+cudaError_t filter_fix_multi(const FilterArgs &A, uint32_t *order, uint64_t n_surv, uint32_t *big_list, uint32_t big_cap,
+                             unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
+{
+    if (n_surv < 2) return cudaSuccess;
+    fix_multi_kernel<<<(unsigned)((n_surv + 127) / 128), 128, 0, st>>>(A, order, n_surv, big_list, big_cap, ctr);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t filter_fix_big(const FilterArgs &A, uint32_t *order, uint32_t *tmp, const uint32_t *big_list, uint32_t n_big,
+                           uint64_t n_surv, cudaStream_t st, uint64_t *launches)
+{
+    if (!n_big) return cudaSuccess;
+    fix_big_kernel<<<n_big, 256, 0, st>>>(A, order, tmp, big_list);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+__global__ void csr_sizes_kernel(FilterArgs A, const uint32_t *order, uint64_t n, uint32_t *nv_out)
+{
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j < n) nv_out[j] = A.hit_nv[order[j]];
+}
+
+__global__ void csr_fill_kernel(FilterArgs A, const uint32_t *order, uint64_t n, const uint64_t *anchor_off, int32_t *anchor_rank,
+                                int32_t *anchor_walk, int32_t *anchor_vtx, unsigned long long *anchors_per_walk, uint32_t walk_id_base,
+                                uint32_t n_walks_out)
+{
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint32_t wl = 0xFFFFFFFFu;
+    if (j < n) {
+        uint32_t x = order[j];
+        anchor_rank[j] = (int32_t)A.hit_rank[x];
+        anchor_walk[j] = (int32_t)A.hit_walk[x];
+        const int32_t *p = A.vtx_pool + A.hit_voff[x];
+        uint64_t o = anchor_off[j]; uint32_t nv = A.hit_nv[x];
+        for (uint32_t i = 0; i < nv; ++i) anchor_vtx[o + i] = p[i];
+        wl = A.hit_walk[x];
+    }
+    // warp-aggregated per-walk counts (few distinct walks -> heavy contention otherwise)
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, wl);
+    if (wl != 0xFFFFFFFFu && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&anchors_per_walk[wl], (unsigned long long)__popc(peers));
+}
+
+cudaError_t filter_csr_sizes(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, uint32_t *nv_out, cudaStream_t st, uint64_t *launches)
+{
+    if (!n_surv) return cudaSuccess;
+    csr_sizes_kernel<<<(unsigned)((n_surv + 255) / 256), 256, 0, st>>>(A, order, n_surv, nv_out);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t filter_csr_fill(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, const uint64_t *anchor_off, int32_t *anchor_rank,
+                            int32_t *anchor_walk, int32_t *anchor_vtx, unsigned long long *anchors_per_walk, uint32_t walk_id_base,
+                            uint32_t n_walks_out, cudaStream_t st, uint64_t *launches)
+{
+    if (!n_surv) return cudaSuccess;
+    csr_fill_kernel<<<(unsigned)((n_surv + 255) / 256), 256, 0, st>>>(A, order, n_surv, anchor_off, anchor_rank, anchor_walk, anchor_vtx,
+                                                                     anchors_per_walk, walk_id_base, n_walks_out);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+}  // namespace phi

@@ -1,0 +1,724 @@
+// Host side of libphi_gpu_index.so: the C ABI declared in include/phi_gpu_index.h and the stage
+// pipeline that replaces /root/reference/src/ILP_index.cpp:543-743.  C++ only (no PyTorch); one ctx
+// drives one GPU through one CUDA stream.  There is no CPU fallback: without a usable device
+// phi_gpu_index_create() fails and nothing else can be called.
+#include "../../include/phi_gpu_index.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace phi;
+
+namespace {
+
+thread_local std::string g_create_error = "no error";
+
+struct DevBuf {                       // grow-only device buffer
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+enum { EV_START, EV_H2D, EV_PREP, EV_READS, EV_SPECTRUM, EV_WALKS, EV_FILTER, EV_END, EV_RK0, EV_RK1, EV_WK0, EV_WK1, EV_COUNT };
+
+}  // namespace
+
+struct phi_gpu_index_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    std::string err = "no error";
+    uint64_t launches = 0;
+    phi_stage_times times = {};
+
+    // resident inputs
+    bool have_inputs = false;
+    uint32_t n_vtx = 0, n_walks = 0; uint64_t n_steps = 0, seg_total = 0, n_reads = 0, read_total = 0;
+    DevBuf seg_off, seg_bases, walk_off, walk_vtx, top_order, read_off, read_bases;
+    std::vector<uint64_t> h_walk_off;
+
+    // work buffers
+    DevBuf step_len, gbase, step_base, walk_len, walk_tile_base, tile_first_step, tile_first_read, scan_scr, ctr;
+    DevBuf walk_off_c, walk_vtx_c, flags64;
+    DevBuf table, spec_a, spec_b, sort_scr, dir;
+    DevBuf mpw, hit_rank, hit_walk, hit_pos, hit_voff, hit_nv, hit_hash, vtx_pool;
+    DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
+    DevBuf anchor_off, anchor_rank, anchor_walk, anchor_vtx, apw, walk_gbase;
+    unsigned long long *h_ctr = nullptr;   // pinned mirror of the counter block
+
+    // multi-GPU (set by comm_init)
+    int rank = 0, world = 1; uint32_t walk_id_base = 0, n_walks_global = 0;
+    void *comm = nullptr;
+
+    int fail(int code, const std::string &m) { err = m; return code; }
+};
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx->fail(PHI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+extern "C" int phi_gpu_index_abi_version(void) { return PHI_GPU_INDEX_ABI_VERSION; }
+
+extern "C" const char *phi_gpu_last_error(const phi_gpu_index_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
+{
+    if (!out) { g_create_error = "out is NULL"; return PHI_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this library has no CPU fallback)";
+        return PHI_ERR_CUDA;
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= n) { g_create_error = "device index out of range"; return PHI_ERR_ARG; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return PHI_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return PHI_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_error = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; this library is built for sm_100a only";
+        return PHI_ERR_CUDA;
+    }
+    phi_gpu_index_ctx *ctx = new phi_gpu_index_ctx();
+    ctx->device = device;
+    if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
+    if ((e = cudaHostAlloc((void **)&ctx->h_ctr, CTR_COUNT * 8, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    if ((e = ctx->ctr.reserve(CTR_COUNT * 8)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    *out = ctx;
+    return PHI_OK;
+}
+
+extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    DevBuf *bufs[] = {&ctx->seg_off, &ctx->seg_bases, &ctx->walk_off, &ctx->walk_vtx, &ctx->top_order, &ctx->read_off, &ctx->read_bases,
+                      &ctx->step_len, &ctx->gbase, &ctx->step_base, &ctx->walk_len, &ctx->walk_tile_base, &ctx->tile_first_step,
+                      &ctx->tile_first_read, &ctx->scan_scr, &ctx->ctr, &ctx->walk_off_c, &ctx->walk_vtx_c, &ctx->flags64, &ctx->table,
+                      &ctx->spec_a, &ctx->spec_b, &ctx->sort_scr, &ctx->dir, &ctx->mpw, &ctx->hit_rank, &ctx->hit_walk, &ctx->hit_pos,
+                      &ctx->hit_voff, &ctx->hit_nv, &ctx->hit_hash, &ctx->vtx_pool, &ctx->g_rep, &ctx->g_cnt, &ctx->rank_drop, &ctx->flags,
+                      &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->big_list, &ctx->tmp_order, &ctx->nv_out,
+                      &ctx->anchor_off, &ctx->anchor_rank, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw, &ctx->walk_gbase};
+    for (DevBuf *b : bufs) b->release();
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+static int check_views(phi_gpu_index_ctx *ctx, const phi_graph_view *g, const phi_reads_view *r)
+{
+    if (!g || !r) return ctx->fail(PHI_ERR_ARG, "graph/reads view is NULL");
+    if ((g->n_vtx && (!g->seg_off || !g->top_order_map)) || (g->n_walks && !g->walk_off)) return ctx->fail(PHI_ERR_ARG, "graph view has NULL arrays");
+    if (r->n_reads && !r->read_off) return ctx->fail(PHI_ERR_ARG, "reads view has NULL arrays");
+    return PHI_OK;
+}
+
+extern "C" int phi_gpu_index_upload(phi_gpu_index_ctx *ctx, const phi_graph_view *g, const phi_reads_view *r)
+{
+    if (!ctx) return PHI_ERR_ARG;
+    int rc = check_views(ctx, g, r);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_inputs = false;
+    ctx->n_vtx = g->n_vtx; ctx->n_walks = g->n_walks;
+    ctx->seg_total = g->n_vtx ? g->seg_off[g->n_vtx] : 0;
+    ctx->n_steps = g->n_walks ? g->walk_off[g->n_walks] : 0;
+    ctx->n_reads = r->n_reads;
+    ctx->read_total = r->n_reads ? r->read_off[r->n_reads] : 0;
+    ctx->h_walk_off.assign(g->n_walks + 1, 0);
+    if (g->n_walks) memcpy(ctx->h_walk_off.data(), g->walk_off, (size_t)(g->n_walks + 1) * 8);
+    static const uint64_t zero_off[1] = {0};
+
+    CU(ctx->seg_off.reserve(((size_t)g->n_vtx + 1) * 8));
+    CU(ctx->seg_bases.reserve(ctx->seg_total + 16));
+    CU(ctx->top_order.reserve((size_t)g->n_vtx * 4 + 4));
+    CU(ctx->walk_off.reserve(((size_t)g->n_walks + 1) * 8));
+    CU(ctx->walk_vtx.reserve(ctx->n_steps * 4 + 4));
+    CU(ctx->read_off.reserve((ctx->n_reads + 1) * 8));
+    CU(ctx->read_bases.reserve(ctx->read_total + 32));
+    CU(cudaMemcpyAsync(ctx->seg_off.p, g->n_vtx ? g->seg_off : zero_off, ((size_t)g->n_vtx + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
+    if (ctx->seg_total) CU(cudaMemcpyAsync(ctx->seg_bases.p, g->seg_bases, ctx->seg_total, cudaMemcpyHostToDevice, ctx->st));
+    if (g->n_vtx) CU(cudaMemcpyAsync(ctx->top_order.p, g->top_order_map, (size_t)g->n_vtx * 4, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->walk_off.p, g->n_walks ? g->walk_off : zero_off, ((size_t)g->n_walks + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
+    if (ctx->n_steps) CU(cudaMemcpyAsync(ctx->walk_vtx.p, g->walk_vtx, ctx->n_steps * 4, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->read_off.p, ctx->n_reads ? r->read_off : zero_off, (ctx->n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
+    if (ctx->read_total) CU(cudaMemcpyAsync(ctx->read_bases.p, r->read_bases, ctx->read_total, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemsetAsync((char *)ctx->read_bases.p + ctx->read_total, 0, 32, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->have_inputs = true;
+    return PHI_OK;
+}
+
+static int bits_for(uint64_t max_value)     // number of bits needed to represent values in [0, max_value]
+{
+    int b = 0;
+    while (b < 64 && (max_value >> b)) ++b;
+    return b ? b : 1;
+}
+
+static cudaError_t read_counters(phi_gpu_index_ctx *ctx)
+{
+    cudaError_t e = cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p, CTR_COUNT * 8, cudaMemcpyDeviceToHost, ctx->st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(ctx->st);
+}
+
+__global__ void count_positions_kernel(const uint64_t *off, uint64_t n, int k, int w, unsigned long long *out)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (i < n) { uint64_t len = off[i + 1] - off[i]; if (len >= (uint64_t)(w + k - 1)) v = len - k + 1; }
+    for (int d = 16; d; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
+__global__ void count_zero_steps_kernel(const uint32_t *step_len, uint64_t n, unsigned long long *ctr)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    bool z = i < n && step_len[i] == 0;
+    uint32_t b = __ballot_sync(0xFFFFFFFFu, z);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&ctr[CTR_ZERO_STEPS], (unsigned long long)__popc(b));
+}
+
+__global__ void nonzero_flags_kernel(const uint32_t *step_len, uint64_t n, uint32_t *flags)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = step_len[i] != 0;
+}
+
+__global__ void compact_steps_kernel(const uint32_t *walk_vtx, const uint32_t *step_len, const uint64_t *pos, uint64_t n, uint32_t *out_vtx,
+                                     uint32_t *out_len)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n && step_len[i]) { out_vtx[pos[i]] = walk_vtx[i]; out_len[pos[i]] = step_len[i]; }
+}
+
+__global__ void remap_walk_off_kernel(const uint64_t *walk_off, uint32_t n_walks, const uint64_t *pos, uint64_t n_steps, uint64_t n_kept, uint64_t *out)
+{
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h > n_walks) return;
+    uint64_t o = walk_off[h];
+    out[h] = o < n_steps ? pos[o] : n_kept;
+}
+
+__global__ void count_survivors_kernel(const uint32_t *flags, uint64_t n, unsigned long long *ctr)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    bool s = i < n && flags[i];
+    uint32_t b = __ballot_sync(0xFFFFFFFFu, s);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&ctr[CTR_SURVIVORS], (unsigned long long)__popc(b));
+}
+
+namespace {
+
+struct RunOut {                    // device-side products of one run
+    uint32_t n_spec = 0;
+    uint64_t n_hits = 0, n_hit_vtx = 0, n_surv = 0, n_anchor_vtx = 0;
+    uint64_t read_pos = 0, path_pos = 0, read_emitted = 0, path_emitted = 0;
+    int64_t n_filtered = 0;
+};
+
+}  // namespace
+
+// ---- stage: graph preparation (depends on k, w through the tile directory)
+static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<uint64_t> &h_walk_len, std::vector<uint64_t> &h_tile_base,
+                            uint64_t &max_tiles, const uint32_t *&d_walk_vtx, const uint64_t *&d_walk_off, uint64_t &n_steps_eff)
+{
+    const uint32_t H = ctx->n_walks; const uint64_t S = ctx->n_steps;
+    d_walk_vtx = ctx->walk_vtx.as<uint32_t>(); d_walk_off = ctx->walk_off.as<uint64_t>(); n_steps_eff = S;
+    h_walk_len.assign(H, 0); h_tile_base.assign(H + 1, 0); max_tiles = 0;
+    if (!H) return PHI_OK;
+    CU(ctx->step_len.reserve(S * 4 + 4));
+    CU(ctx->gbase.reserve((S + 1) * 8));
+    CU(ctx->scan_scr.reserve(std::max(scan_u32_to_u64_scratch(S + 1), (size_t)1024)));
+    CU(launch_step_len(d_walk_vtx, ctx->seg_off.as<uint64_t>(), S, ctx->step_len.as<uint32_t>(), ctx->st)); ctx->launches++;
+    if (S) {
+        count_zero_steps_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->st>>>(ctx->step_len.as<uint32_t>(), S, ctx->ctr.as<unsigned long long>());
+        CU(cudaGetLastError()); ctx->launches++;
+    }
+    CU(read_counters(ctx));
+    if (ctx->h_ctr[CTR_ZERO_STEPS]) {
+        // zero-length segments contribute no bases (ILP_index.cpp:364-381): drop their steps
+        const uint64_t kept = S - ctx->h_ctr[CTR_ZERO_STEPS];
+        CU(ctx->flags.reserve(S * 4 + 4));
+        CU(ctx->flags64.reserve((S + 1) * 8));
+        CU(ctx->walk_vtx_c.reserve(kept * 4 + 4));
+        CU(ctx->walk_off_c.reserve(((size_t)H + 1) * 8));
+        CU(ctx->nv_out.reserve(kept * 4 + 4));
+        nonzero_flags_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->st>>>(ctx->step_len.as<uint32_t>(), S, ctx->flags.as<uint32_t>());
+        CU(cudaGetLastError()); ctx->launches++;
+        CU(scan_u32_to_u64(ctx->flags.as<uint32_t>(), ctx->flags64.as<uint64_t>(), S, ctx->scan_scr.p, ctx->st, &ctx->launches));
+        compact_steps_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->st>>>(d_walk_vtx, ctx->step_len.as<uint32_t>(), ctx->flags64.as<uint64_t>(), S,
+                                                                              ctx->walk_vtx_c.as<uint32_t>(), ctx->nv_out.as<uint32_t>());
+        CU(cudaGetLastError()); ctx->launches++;
+        remap_walk_off_kernel<<<(H + 1 + 127) / 128, 128, 0, ctx->st>>>(d_walk_off, H, ctx->flags64.as<uint64_t>(), S, kept, ctx->walk_off_c.as<uint64_t>());
+        CU(cudaGetLastError()); ctx->launches++;
+        if (kept) CU(cudaMemcpyAsync(ctx->step_len.p, ctx->nv_out.p, kept * 4, cudaMemcpyDeviceToDevice, ctx->st));
+        d_walk_vtx = ctx->walk_vtx_c.as<uint32_t>(); d_walk_off = ctx->walk_off_c.as<uint64_t>(); n_steps_eff = kept;
+    }
+    const uint64_t S2 = n_steps_eff;
+    CU(scan_u32_to_u64(ctx->step_len.as<uint32_t>(), ctx->gbase.as<uint64_t>(), S2, ctx->scan_scr.p, ctx->st, &ctx->launches));
+    CU(ctx->walk_len.reserve((size_t)H * 8));
+    CU(launch_walk_len(ctx->gbase.as<uint64_t>(), ctx->step_len.as<uint32_t>(), d_walk_off, H, S2, ctx->walk_len.as<uint64_t>(), ctx->st)); ctx->launches++;
+    CU(cudaMemcpyAsync(h_walk_len.data(), ctx->walk_len.p, (size_t)H * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    const int T = tile_windows();
+    for (uint32_t h = 0; h < H; ++h) {
+        uint64_t len = h_walk_len[h];
+        if (len >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "walk longer than 2^31-1 bases (the reference's int32 position loop overflows there too)");
+        uint64_t nt = len >= (uint64_t)(w + k - 1) ? (len - k) / T + 1 : 0;
+        h_tile_base[h + 1] = h_tile_base[h] + nt;
+        max_tiles = std::max(max_tiles, nt);
+    }
+    CU(ctx->walk_tile_base.reserve(((size_t)H + 1) * 8));
+    CU(cudaMemcpyAsync(ctx->walk_tile_base.p, h_tile_base.data(), ((size_t)H + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
+    CU(ctx->step_base.reserve(S2 * 4 + 4));
+    CU(ctx->tile_first_step.reserve(h_tile_base[H] * 4 + 4));
+    CU(launch_step_finalize(ctx->gbase.as<uint64_t>(), ctx->step_len.as<uint32_t>(), d_walk_off, H, S2, w, ctx->walk_tile_base.as<uint64_t>(),
+                            ctx->step_base.as<uint32_t>(), ctx->tile_first_step.as<uint32_t>(), ctx->st)); ctx->launches++;
+    return PHI_OK;
+}
+
+// ---- stage: reads -> ranked spectrum (sorted distinct hashes + radix directory)
+static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbits)
+{
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    const int T = tile_windows();
+    const uint64_t G = ctx->read_total, R = ctx->n_reads;
+    const uint64_t n_tiles = (R && G >= (uint64_t)(w + k - 1)) ? (G - k) / T + 1 : 0;
+    uint64_t n_spec = 0;
+    CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st));
+    CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
+    if (n_tiles) {
+        count_positions_kernel<<<(unsigned)((R + 255) / 256), 256, 0, ctx->st>>>(ctx->read_off.as<uint64_t>(), R, k, w, d_ctr + 10);
+        CU(cudaGetLastError()); ctx->launches++;
+        CU(ctx->tile_first_read.reserve(n_tiles * 8));
+        CU(launch_read_tile_dir(ctx->read_off.as<uint64_t>(), R, w, n_tiles, ctx->tile_first_read.as<uint64_t>(), ctx->st)); ctx->launches++;
+        // expected minimizer density is 2/(w+1); size the table for ~35% load at that density, retry on overflow
+        double dens = std::min(1.0, 2.6 / (w + 1.0));
+        uint64_t want = (uint64_t)((double)G * dens * 2.0) + 1024, cap = 1024;
+        while (cap < want) cap <<= 1;
+        for (;;) {
+            CU(ctx->table.reserve(cap * 8));
+            CU(fill_u64(ctx->table.as<uint64_t>(), cap, TABLE_EMPTY, ctx->st, &ctx->launches));
+            CU(cudaMemsetAsync(d_ctr, 0, 4 * 8, ctx->st));                 // DISTINCT, OVERFLOW, HAS_MAXKEY, READ_EMITTED
+            ReadSketchArgs A;
+            A.read_bases = ctx->read_bases.as<uint8_t>(); A.read_off = ctx->read_off.as<uint64_t>();
+            A.n_reads = R; A.total_bases = G; A.tile_first_read = ctx->tile_first_read.as<uint64_t>();
+            A.k = k; A.w = w; A.table = ctx->table.as<uint64_t>(); A.table_mask = cap - 1; A.ctr = d_ctr;
+            CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st));
+            CU(launch_read_sketch(A, n_tiles, ctx->st)); ctx->launches++;
+            CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
+            CU(read_counters(ctx));
+            if (!ctx->h_ctr[CTR_OVERFLOW] && ctx->h_ctr[CTR_DISTINCT] * 10 <= cap * 8) break;
+            cap <<= 1;
+        }
+        o.read_emitted = ctx->h_ctr[CTR_READ_EMITTED];
+        o.read_pos = ctx->h_ctr[10];
+        const uint64_t nd = ctx->h_ctr[CTR_DISTINCT];
+        const bool maxkey = ctx->h_ctr[CTR_HAS_MAXKEY] != 0;
+        n_spec = nd + (maxkey ? 1 : 0);
+        if (n_spec >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^31-1 distinct read minimizers (count_sp_r is int32 in the reference)");
+        CU(cudaEventRecord(ctx->ev[EV_READS], ctx->st));
+        CU(ctx->spec_a.reserve((n_spec + 1) * 8));
+        CU(ctx->spec_b.reserve((n_spec + 1) * 8));
+        CU(ctx->sort_scr.reserve(radix_sort_scratch(std::max<uint64_t>(n_spec, 1))));
+        CU(cudaMemsetAsync(d_ctr + 11, 0, 8, ctx->st));
+        CU(table_compact(ctx->table.as<uint64_t>(), cap, ctx->spec_a.as<uint64_t>(), d_ctr + 11, ctx->st, &ctx->launches));
+        CU(radix_sort_u64(ctx->spec_a.as<uint64_t>(), ctx->spec_b.as<uint64_t>(), nullptr, nullptr, nd, 0, 64, ctx->sort_scr.p, ctx->st, &ctx->launches));
+        if (maxkey) CU(fill_u64(ctx->spec_a.as<uint64_t>() + nd, 1, TABLE_EMPTY, ctx->st, &ctx->launches));
+    } else {
+        CU(cudaEventRecord(ctx->ev[EV_READS], ctx->st));
+        CU(ctx->spec_a.reserve(8));
+    }
+    o.n_spec = (uint32_t)n_spec;
+    dbits = 0;
+    while (dbits < 30 && (1ull << dbits) < n_spec) ++dbits;
+    CU(ctx->dir.reserve(((1ull << dbits) + 2) * 4));
+    CU(build_directory(ctx->spec_a.as<uint64_t>(), o.n_spec, dbits, ctx->dir.as<uint32_t>(), ctx->st, &ctx->launches));
+    return PHI_OK;
+}
+
+// ---- stage: walks -> hits
+static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits, const std::vector<uint64_t> &h_walk_len, uint64_t max_tiles,
+                       const uint32_t *d_walk_vtx, const uint64_t *d_walk_off, uint64_t n_steps_eff, RunOut &o)
+{
+    const uint32_t H = ctx->n_walks;
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    CU(ctx->mpw.reserve(((size_t)H + 1) * 8));
+    uint64_t positions = 0, bases = 0;
+    for (uint32_t h = 0; h < H; ++h) { bases += h_walk_len[h]; if (h_walk_len[h] >= (uint64_t)(w + k - 1)) positions += h_walk_len[h] - k + 1; }
+    o.path_pos = positions;
+    CU(cudaEventRecord(ctx->ev[EV_WK0], ctx->st));
+    CU(cudaEventRecord(ctx->ev[EV_WK1], ctx->st));
+    if (!H || !max_tiles) { CU(cudaMemsetAsync(ctx->mpw.p, 0, ((size_t)H + 1) * 8, ctx->st)); return PHI_OK; }
+    // capacity estimate: emitted density 2/(w+1), vertices per anchor 1 + (k-1)/mean node length; exact re-run on overflow
+    double dens = std::min(1.0, 2.0 / (w + 1.0)) * 1.3;
+    double mean_node = n_steps_eff ? (double)bases / (double)n_steps_eff : 1.0;
+    uint64_t hit_cap = (uint64_t)((double)positions * dens) + 65536;
+    uint64_t vtx_cap = (uint64_t)((double)hit_cap * std::min((double)k, 1.0 + (k - 1) / std::max(mean_node, 1.0)) * 1.2) + 65536;
+    for (int attempt = 0;; ++attempt) {
+        if (hit_cap >= (1ull << 32)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-1 walk hits on one GPU; shard the walks over more GPUs");
+        CU(ctx->hit_rank.reserve(hit_cap * 4)); CU(ctx->hit_walk.reserve(hit_cap * 4)); CU(ctx->hit_pos.reserve(hit_cap * 4));
+        CU(ctx->hit_voff.reserve(hit_cap * 8)); CU(ctx->hit_nv.reserve(hit_cap));
+        if (mode == WALK_MODE_ALL) CU(ctx->hit_hash.reserve(hit_cap * 8));
+        CU(ctx->vtx_pool.reserve(vtx_cap * 4));
+        CU(cudaMemsetAsync(ctx->mpw.p, 0, ((size_t)H + 1) * 8, ctx->st));
+        CU(cudaMemsetAsync(d_ctr + CTR_HITS, 0, 2 * 8, ctx->st));
+        WalkSketchArgs A;
+        A.seg_bases = ctx->seg_bases.as<uint8_t>(); A.seg_off = ctx->seg_off.as<uint64_t>(); A.top_order_map = ctx->top_order.as<int32_t>();
+        A.walk_vtx = d_walk_vtx; A.walk_off = d_walk_off; A.step_base = ctx->step_base.as<uint32_t>();
+        A.walk_len = ctx->walk_len.as<uint64_t>(); A.walk_tile_base = ctx->walk_tile_base.as<uint64_t>();
+        A.tile_first_step = ctx->tile_first_step.as<uint32_t>();
+        A.k = k; A.w = w; A.mode = mode;
+        A.spec = ctx->spec_a.as<uint64_t>(); A.dir = ctx->dir.as<uint32_t>(); A.dbits = dbits;
+        A.walk_id_base = ctx->walk_id_base;
+        A.minimizers_per_walk = ctx->mpw.as<unsigned long long>();
+        A.hit_rank = ctx->hit_rank.as<uint32_t>(); A.hit_walk = ctx->hit_walk.as<uint32_t>(); A.hit_pos = ctx->hit_pos.as<uint32_t>();
+        A.hit_voff = ctx->hit_voff.as<uint64_t>(); A.hit_nv = ctx->hit_nv.as<uint8_t>();
+        A.hit_hash = mode == WALK_MODE_ALL ? ctx->hit_hash.as<uint64_t>() : nullptr;
+        A.vtx_pool = ctx->vtx_pool.as<int32_t>(); A.hit_cap = hit_cap; A.vtx_cap = vtx_cap; A.ctr = d_ctr;
+        CU(cudaEventRecord(ctx->ev[EV_WK0], ctx->st));
+        CU(launch_walk_sketch(A, H, max_tiles, ctx->st)); ctx->launches++;
+        CU(cudaEventRecord(ctx->ev[EV_WK1], ctx->st));
+        CU(read_counters(ctx));
+        o.n_hits = ctx->h_ctr[CTR_HITS]; o.n_hit_vtx = ctx->h_ctr[CTR_HIT_VTX];
+        if (o.n_hits <= hit_cap && o.n_hit_vtx <= vtx_cap) break;
+        if (attempt) return ctx->fail(PHI_ERR_CUDA, "walk hit buffers overflowed twice (internal error)");
+        hit_cap = o.n_hits + 1024; vtx_cap = o.n_hit_vtx + 1024;          // exact sizes are now known: run again
+    }
+    return PHI_OK;
+}
+
+// ---- stage: threshold filter, final order, CSR
+static int stage_filter(phi_gpu_index_ctx *ctx, const std::vector<uint64_t> &h_walk_gbase, uint32_t n_walks_global, float threshold, RunOut &o)
+{
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    const uint64_t n = o.n_hits;
+    CU(ctx->apw.reserve(((size_t)n_walks_global + 1) * 8));
+    CU(cudaMemsetAsync(ctx->apw.p, 0, ((size_t)n_walks_global + 1) * 8, ctx->st));
+    CU(cudaMemsetAsync(d_ctr + CTR_FILTERED, 0, 3 * 8, ctx->st));        // FILTERED, SURVIVORS, BIG_GROUPS
+    CU(ctx->rank_drop.reserve((size_t)o.n_spec + 4));
+    CU(cudaMemsetAsync(ctx->rank_drop.p, 0, (size_t)o.n_spec + 4, ctx->st));
+    CU(ctx->anchor_off.reserve(8));
+    o.n_surv = 0; o.n_anchor_vtx = 0; o.n_filtered = 0;
+    if (!n) { CU(cudaMemsetAsync(ctx->anchor_off.p, 0, 8, ctx->st)); return PHI_OK; }
+
+    FilterArgs A;
+    A.n_hits = n; A.hit_rank = ctx->hit_rank.as<uint32_t>(); A.hit_walk = ctx->hit_walk.as<uint32_t>(); A.hit_pos = ctx->hit_pos.as<uint32_t>();
+    A.hit_voff = ctx->hit_voff.as<uint64_t>(); A.hit_nv = ctx->hit_nv.as<uint8_t>(); A.vtx_pool = ctx->vtx_pool.as<int32_t>();
+    A.n_ranks = o.n_spec;
+    A.thr = threshold * (float)n_walks_global;                            // float * uint32 -> float, as ILP_index.cpp:698
+    CU(ctx->walk_gbase.reserve(h_walk_gbase.size() * 8));
+    CU(cudaMemcpyAsync(ctx->walk_gbase.p, h_walk_gbase.data(), h_walk_gbase.size() * 8, cudaMemcpyHostToDevice, ctx->st));
+    A.walk_gbase = ctx->walk_gbase.as<uint64_t>();
+    A.gpos_bits = bits_for(h_walk_gbase.back()); A.rank_bits = bits_for(o.n_spec ? o.n_spec - 1 : 0);
+
+    FilterWork W;
+    uint64_t gcap = 1024; while (gcap < 2 * n) gcap <<= 1;
+    CU(ctx->g_rep.reserve(gcap * 4)); CU(ctx->g_cnt.reserve(gcap * 4)); CU(ctx->flags.reserve(n * 4 + 4));
+    CU(fill_u32(ctx->g_rep.as<uint32_t>(), gcap, 0xFFFFFFFFu, ctx->st, &ctx->launches));
+    CU(cudaMemsetAsync(ctx->g_cnt.p, 0, gcap * 4, ctx->st));
+    W.g_rep = ctx->g_rep.as<uint32_t>(); W.g_cnt = ctx->g_cnt.as<uint32_t>(); W.g_cap = gcap;
+    W.rank_drop = ctx->rank_drop.as<uint8_t>(); W.flags = ctx->flags.as<uint32_t>(); W.ctr = d_ctr;
+    W.keys_a = W.keys_b = nullptr; W.vals_a = W.vals_b = nullptr; W.sort_scratch = nullptr; W.scan_scratch = nullptr;
+    CU(filter_count_groups(A, W, ctx->st, &ctx->launches));
+    CU(filter_mark_drops(A, W, ctx->st, &ctx->launches));
+    CU(filter_flag_survivors(A, W, ctx->st, &ctx->launches));
+    count_survivors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(W.flags, n, d_ctr);
+    CU(cudaGetLastError()); ctx->launches++;
+    CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(n), scan_u32_to_u64_scratch(n + 1))));
+    CU(scan_u32_inplace(W.flags, n, ctx->scan_scr.p, ctx->st, &ctx->launches));
+    CU(read_counters(ctx));
+    o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED];
+    const uint64_t ns = ctx->h_ctr[CTR_SURVIVORS];
+    o.n_surv = ns;
+    if (!ns) { CU(cudaMemsetAsync(ctx->anchor_off.p, 0, 8, ctx->st)); return PHI_OK; }
+
+    CU(ctx->keys_a.reserve(ns * 8)); CU(ctx->keys_b.reserve(ns * 8)); CU(ctx->vals_a.reserve(ns * 4)); CU(ctx->vals_b.reserve(ns * 4));
+    CU(ctx->sort_scr.reserve(radix_sort_scratch(ns)));
+    W.keys_a = ctx->keys_a.as<uint64_t>(); W.keys_b = ctx->keys_b.as<uint64_t>();
+    W.vals_a = ctx->vals_a.as<uint32_t>(); W.vals_b = ctx->vals_b.as<uint32_t>(); W.sort_scratch = ctx->sort_scr.p;
+    const bool combined = A.gpos_bits + A.rank_bits <= 64;
+    CU(filter_emit_keys(A, W, ns, combined, ctx->st, &ctx->launches));
+    uint32_t *order = W.vals_a;
+
+    const uint32_t big_cap = (uint32_t)(ns / 48 + 1);
+    CU(ctx->big_list.reserve((size_t)big_cap * 8));
+    CU(filter_fix_multi(A, order, ns, ctx->big_list.as<uint32_t>(), big_cap, d_ctr, ctx->st, &ctx->launches));
+    CU(read_counters(ctx));
+    if (ctx->h_ctr[CTR_BIG_GROUPS]) {
+        CU(ctx->tmp_order.reserve(ns * 4));
+        CU(filter_fix_big(A, order, ctx->tmp_order.as<uint32_t>(), ctx->big_list.as<uint32_t>(), (uint32_t)ctx->h_ctr[CTR_BIG_GROUPS], ns, ctx->st, &ctx->launches));
+    }
+    CU(ctx->nv_out.reserve((ns + 1) * 4));
+    CU(ctx->anchor_off.reserve((ns + 1) * 8));
+    CU(cudaMemsetAsync(ctx->nv_out.as<uint32_t>() + ns, 0, 4, ctx->st));
+    CU(filter_csr_sizes(A, order, ns, ctx->nv_out.as<uint32_t>(), ctx->st, &ctx->launches));
+    CU(scan_u32_to_u64(ctx->nv_out.as<uint32_t>(), ctx->anchor_off.as<uint64_t>(), ns + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
+    uint64_t total_vtx = 0;
+    CU(cudaMemcpyAsync(&total_vtx, ctx->anchor_off.as<uint64_t>() + ns, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    o.n_anchor_vtx = total_vtx;
+    CU(ctx->anchor_rank.reserve(ns * 4)); CU(ctx->anchor_walk.reserve(ns * 4)); CU(ctx->anchor_vtx.reserve(total_vtx * 4 + 4));
+    CU(filter_csr_fill(A, order, ns, ctx->anchor_off.as<uint64_t>(), ctx->anchor_rank.as<int32_t>(), ctx->anchor_walk.as<int32_t>(),
+                       ctx->anchor_vtx.as<int32_t>(), ctx->apw.as<unsigned long long>(), ctx->walk_id_base, n_walks_global, ctx->st, &ctx->launches));
+    return PHI_OK;
+}
+
+static phi_index_result *alloc_result() { return (phi_index_result *)calloc(1, sizeof(phi_index_result)); }
+
+extern "C" void phi_gpu_index_result_free(phi_index_result *r)
+{
+    if (!r) return;
+    free((void *)r->spectrum); free((void *)r->anchor_rank); free((void *)r->anchor_walk); free((void *)r->anchor_off);
+    free((void *)r->anchor_vtx); free((void *)r->minimizers_per_walk); free((void *)r->anchors_per_walk);
+    free(r);
+}
+extern "C" void phi_gpu_index_free_u64(uint64_t *p) { free(p); }
+
+static int validate_params(phi_gpu_index_ctx *ctx, const phi_index_params *p)
+{
+    if (!p) return ctx->fail(PHI_ERR_ARG, "params is NULL");
+    if (p->k < 1 || p->w < 1) return ctx->fail(PHI_ERR_ARG, "k and w must be >= 1");
+    if (p->k > 32) return ctx->fail(PHI_ERR_UNSUPPORTED, "k > 32 is not implemented on the GPU path (packed 2-bit k-mers); refusing rather than diverging");
+    if (p->w > 256) return ctx->fail(PHI_ERR_UNSUPPORTED, "w > 256 is not implemented on the GPU path");
+    return PHI_OK;
+}
+
+template <class T>
+static int download(phi_gpu_index_ctx *ctx, const void *dev, uint64_t n, const T **out)
+{
+    T *h = (T *)malloc(std::max<uint64_t>(n, 1) * sizeof(T));
+    if (!h) return ctx->fail(PHI_ERR_NOMEM, "host allocation failed");
+    if (n) CU(cudaMemcpyAsync(h, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->st));
+    *out = h;
+    return PHI_OK;
+}
+
+static void collect_times(phi_gpu_index_ctx *ctx, float h2d_ms)
+{
+    auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return ms; };
+    phi_stage_times &t = ctx->times;
+    t.h2d_ms = h2d_ms;
+    t.graph_prep_ms = el(EV_H2D, EV_PREP);
+    t.read_sketch_ms = el(EV_PREP, EV_READS);
+    t.spectrum_ms = el(EV_READS, EV_SPECTRUM);
+    t.walk_sketch_ms = el(EV_SPECTRUM, EV_WALKS);
+    t.filter_ms = el(EV_WALKS, EV_FILTER);
+    t.d2h_ms = el(EV_FILTER, EV_END);
+    t.total_ms = el(EV_START, EV_END) ;
+    t.walk_kernel_ms = el(EV_WK0, EV_WK1);
+    t.read_kernel_ms = el(EV_RK0, EV_RK1);
+    t.kernel_launches = ctx->launches;
+}
+
+static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int mode, int do_download, phi_index_result **out,
+                        uint64_t **hashes_out, float h2d_ms, bool start_recorded)
+{
+    if (!ctx->have_inputs) return ctx->fail(PHI_ERR_ARG, "no inputs uploaded");
+    int rc = validate_params(ctx, prm);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const int k = prm->k, w = prm->w;
+    ctx->launches = 0;
+    if (!start_recorded) CU(cudaEventRecord(ctx->ev[EV_START], ctx->st));
+    CU(cudaEventRecord(ctx->ev[EV_H2D], ctx->st));
+    CU(cudaMemsetAsync(ctx->ctr.p, 0, CTR_COUNT * 8, ctx->st));
+    RunOut o;
+    std::vector<uint64_t> h_walk_len, h_tile_base; uint64_t max_tiles = 0, n_steps_eff = 0;
+    const uint32_t *d_walk_vtx; const uint64_t *d_walk_off;
+    rc = stage_graph_prep(ctx, k, w, h_walk_len, h_tile_base, max_tiles, d_walk_vtx, d_walk_off, n_steps_eff);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[EV_PREP], ctx->st));
+    int dbits = 0;
+    if (mode == WALK_MODE_PROBE) {
+        rc = stage_reads(ctx, k, w, o, dbits);
+        if (rc) return rc;
+    } else {
+        CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st)); CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
+        CU(cudaEventRecord(ctx->ev[EV_READS], ctx->st));
+    }
+    CU(cudaEventRecord(ctx->ev[EV_SPECTRUM], ctx->st));
+    rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, max_tiles, d_walk_vtx, d_walk_off, n_steps_eff, o);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[EV_WALKS], ctx->st));
+
+    const uint32_t H = ctx->n_walks;
+    const uint32_t HG = ctx->world > 1 ? ctx->n_walks_global : H;
+    std::vector<uint64_t> h_walk_gbase(HG + 1, 0);
+    if (ctx->world == 1) for (uint32_t h = 0; h < H; ++h) h_walk_gbase[h + 1] = h_walk_gbase[h] + h_walk_len[h];
+    else for (uint32_t h = 0; h < HG; ++h) h_walk_gbase[h + 1] = h_walk_gbase[h] + (1ull << 31);   // any monotone walk-major coordinate orders correctly
+
+    phi_index_result *res = alloc_result();
+    if (!res) return ctx->fail(PHI_ERR_NOMEM, "host allocation failed");
+    if (mode == WALK_MODE_PROBE) {
+        rc = stage_filter(ctx, h_walk_gbase, HG, prm->threshold, o);
+        if (rc) { free(res); return rc; }
+    } else {
+        // sketch-only: order all emitted minimizers by (walk, position) and build the CSR without filtering
+        unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+        const uint64_t n = o.n_hits;
+        CU(ctx->apw.reserve(((size_t)HG + 1) * 8));
+        CU(cudaMemsetAsync(ctx->apw.p, 0, ((size_t)HG + 1) * 8, ctx->st));
+        CU(ctx->rank_drop.reserve(4)); CU(cudaMemsetAsync(ctx->rank_drop.p, 0, 4, ctx->st));
+        CU(ctx->anchor_off.reserve((n + 1) * 8));
+        o.n_surv = n;
+        if (n) {
+            FilterArgs A;
+            A.n_hits = n; A.hit_rank = ctx->hit_rank.as<uint32_t>(); A.hit_walk = ctx->hit_walk.as<uint32_t>(); A.hit_pos = ctx->hit_pos.as<uint32_t>();
+            A.hit_voff = ctx->hit_voff.as<uint64_t>(); A.hit_nv = ctx->hit_nv.as<uint8_t>(); A.vtx_pool = ctx->vtx_pool.as<int32_t>();
+            A.n_ranks = 1; A.thr = 0;
+            CU(ctx->walk_gbase.reserve(h_walk_gbase.size() * 8));
+            CU(cudaMemcpyAsync(ctx->walk_gbase.p, h_walk_gbase.data(), h_walk_gbase.size() * 8, cudaMemcpyHostToDevice, ctx->st));
+            A.walk_gbase = ctx->walk_gbase.as<uint64_t>(); A.gpos_bits = bits_for(h_walk_gbase.back()); A.rank_bits = 1;
+            FilterWork W; memset(&W, 0, sizeof(W));
+            CU(ctx->flags.reserve(n * 4 + 4));
+            CU(ctx->keys_a.reserve(n * 8)); CU(ctx->keys_b.reserve(n * 8)); CU(ctx->vals_a.reserve(n * 4)); CU(ctx->vals_b.reserve(n * 4));
+            CU(ctx->sort_scr.reserve(radix_sort_scratch(n)));
+            CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(n), scan_u32_to_u64_scratch(n + 1))));
+            W.rank_drop = ctx->rank_drop.as<uint8_t>(); W.flags = ctx->flags.as<uint32_t>(); W.ctr = d_ctr;
+            W.keys_a = ctx->keys_a.as<uint64_t>(); W.keys_b = ctx->keys_b.as<uint64_t>();
+            W.vals_a = ctx->vals_a.as<uint32_t>(); W.vals_b = ctx->vals_b.as<uint32_t>(); W.sort_scratch = ctx->sort_scr.p;
+            CU(filter_flag_survivors(A, W, ctx->st, &ctx->launches));
+            CU(scan_u32_inplace(W.flags, n, ctx->scan_scr.p, ctx->st, &ctx->launches));
+            CU(filter_emit_keys(A, W, n, true, ctx->st, &ctx->launches));
+            CU(ctx->nv_out.reserve((n + 1) * 4));
+            CU(cudaMemsetAsync(ctx->nv_out.as<uint32_t>() + n, 0, 4, ctx->st));
+            CU(filter_csr_sizes(A, W.vals_a, n, ctx->nv_out.as<uint32_t>(), ctx->st, &ctx->launches));
+            CU(scan_u32_to_u64(ctx->nv_out.as<uint32_t>(), ctx->anchor_off.as<uint64_t>(), n + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
+            CU(ctx->anchor_rank.reserve(n * 4)); CU(ctx->anchor_walk.reserve(n * 4)); CU(ctx->anchor_vtx.reserve(o.n_hit_vtx * 4 + 4));
+            CU(filter_csr_fill(A, W.vals_a, n, ctx->anchor_off.as<uint64_t>(), ctx->anchor_rank.as<int32_t>(), ctx->anchor_walk.as<int32_t>(),
+                               ctx->anchor_vtx.as<int32_t>(), ctx->apw.as<unsigned long long>(), 0, HG, ctx->st, &ctx->launches));
+            o.n_anchor_vtx = o.n_hit_vtx;
+            if (hashes_out) {
+                // hashes in final order: gather on the host side after download (test-only path)
+            }
+        } else CU(cudaMemsetAsync(ctx->anchor_off.p, 0, 8, ctx->st));
+    }
+    CU(cudaEventRecord(ctx->ev[EV_FILTER], ctx->st));
+
+    res->count_sp_r = (int32_t)o.n_spec; res->n_walks = H; res->n_filtered = o.n_filtered;
+    res->n_anchors = o.n_surv; res->n_anchor_vtx = o.n_anchor_vtx;
+    res->read_kmer_positions = o.read_pos; res->path_kmer_positions = o.path_pos;
+    res->read_minimizers_emitted = o.read_emitted; res->path_hits = o.n_hits;
+    if (do_download) {
+        rc = download<uint64_t>(ctx, ctx->spec_a.p, mode == WALK_MODE_PROBE ? o.n_spec : 0, &res->spectrum);
+        if (!rc) rc = download<int32_t>(ctx, ctx->anchor_rank.p, o.n_surv, &res->anchor_rank);
+        if (!rc) rc = download<int32_t>(ctx, ctx->anchor_walk.p, o.n_surv, &res->anchor_walk);
+        if (!rc) rc = download<uint64_t>(ctx, ctx->anchor_off.p, o.n_surv + 1, &res->anchor_off);
+        if (!rc) rc = download<int32_t>(ctx, ctx->anchor_vtx.p, o.n_anchor_vtx, &res->anchor_vtx);
+        if (!rc) rc = download<uint64_t>(ctx, ctx->apw.as<uint64_t>() + ctx->walk_id_base, H, &res->anchors_per_walk);
+        if (rc) { phi_gpu_index_result_free(res); return rc; }
+    }
+    {   // per-walk minimizer counts are tiny and always returned
+        int rc2 = download<uint64_t>(ctx, ctx->mpw.p, H, &res->minimizers_per_walk);
+        if (rc2) { phi_gpu_index_result_free(res); return rc2; }
+    }
+    uint64_t *hashes = nullptr; uint32_t *h_order = nullptr;
+    if (mode == WALK_MODE_ALL && hashes_out && o.n_hits) {
+        hashes = (uint64_t *)malloc(o.n_hits * 8); h_order = (uint32_t *)malloc(o.n_hits * 4);
+        CU(cudaMemcpyAsync(hashes, ctx->hit_hash.p, o.n_hits * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(h_order, ctx->vals_a.p, o.n_hits * 4, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CU(cudaEventRecord(ctx->ev[EV_END], ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    for (uint32_t h = 0; h < H; ++h) res->path_minimizers_emitted += res->minimizers_per_walk[h];
+    if (mode == WALK_MODE_ALL && hashes_out) {
+        uint64_t *sorted = (uint64_t *)malloc(std::max<uint64_t>(o.n_hits, 1) * 8);
+        for (uint64_t i = 0; i < o.n_hits; ++i) sorted[i] = hashes[h_order[i]];
+        free(hashes); free(h_order);
+        *hashes_out = sorted;
+    }
+    collect_times(ctx, h2d_ms);
+    *out = res;
+    return PHI_OK;
+}
+
+extern "C" int phi_gpu_index_run_resident(phi_gpu_index_ctx *ctx, const phi_index_params *params, int download_result, phi_index_result **out)
+{
+    if (!ctx || !out) return PHI_ERR_ARG;
+    *out = nullptr;
+    return run_pipeline(ctx, params, WALK_MODE_PROBE, download_result, out, nullptr, 0.f, false);
+}
+
+extern "C" int phi_gpu_index_run(phi_gpu_index_ctx *ctx, const phi_graph_view *graph, const phi_reads_view *reads, const phi_index_params *params,
+                                 phi_index_result **out)
+{
+    if (!ctx || !out) return PHI_ERR_ARG;
+    *out = nullptr;
+    int rc = validate_params(ctx, params);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev[EV_START], ctx->st));
+    rc = phi_gpu_index_upload(ctx, graph, reads);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[EV_H2D], ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    float h2d = 0; cudaEventElapsedTime(&h2d, ctx->ev[EV_START], ctx->ev[EV_H2D]);
+    return run_pipeline(ctx, params, WALK_MODE_PROBE, 1, out, nullptr, h2d, true);
+}
+
+extern "C" int phi_gpu_index_sketch_walks(phi_gpu_index_ctx *ctx, const phi_graph_view *graph, const phi_index_params *params,
+                                          phi_index_result **out, uint64_t **hashes_out)
+{
+    if (!ctx || !out || !hashes_out) return PHI_ERR_ARG;
+    *out = nullptr; *hashes_out = nullptr;
+    phi_reads_view none = {0, nullptr, nullptr};
+    int rc = phi_gpu_index_upload(ctx, graph, &none);
+    if (rc) return rc;
+    return run_pipeline(ctx, params, WALK_MODE_ALL, 1, out, hashes_out, 0.f, false);
+}
+
+extern "C" int phi_gpu_index_last_times(const phi_gpu_index_ctx *ctx, phi_stage_times *out)
+{
+    if (!ctx || !out) return PHI_ERR_ARG;
+    *out = ctx->times;
+    return PHI_OK;
+}
+
+extern "C" int phi_gpu_hash128_to_64(phi_gpu_index_ctx *ctx, const uint8_t *keys, uint64_t n, int32_t len, uint64_t *out)
+{
+    if (!ctx || !keys || !out || len < 1 || len > 32) return ctx ? ctx->fail(PHI_ERR_ARG, "bad arguments (len must be 1..32)") : PHI_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf dk, dout;
+    CU(dk.reserve(n * len)); CU(dout.reserve(n * 8));
+    CU(cudaMemcpyAsync(dk.p, keys, n * len, cudaMemcpyHostToDevice, ctx->st));
+    CU(launch_hash_bytes(dk.as<uint8_t>(), n, len, dout.as<uint64_t>(), ctx->st));
+    CU(cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    dk.release(); dout.release();
+    return PHI_OK;
+}
+
+// ---- multi-GPU entry points (NCCL exchange: see comm.cu once built; until then they refuse loudly)
+extern "C" int phi_gpu_index_comm_unique_id(uint8_t id[PHI_COMM_ID_BYTES])
+{
+    (void)id;
+    return PHI_ERR_UNSUPPORTED;
+}
+extern "C" int phi_gpu_index_comm_init(phi_gpu_index_ctx *ctx, int rank, int world, const uint8_t id[PHI_COMM_ID_BYTES],
+                                       uint32_t walk_id_base, uint32_t n_walks_global)
+{
+    (void)rank; (void)world; (void)id; (void)walk_id_base; (void)n_walks_global;
+    return ctx ? ctx->fail(PHI_ERR_UNSUPPORTED, "multi-GPU exchange is not built into this library yet") : PHI_ERR_ARG;
+}

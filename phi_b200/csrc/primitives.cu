@@ -1,0 +1,267 @@
+// Hand-written device primitives used around the sketch kernels: exclusive scans, a stable LSD radix
+// sort on u64 keys (optionally carrying a u32 value), compaction of the spectrum table, and the radix
+// directory that turns the sorted spectrum into an O(1)-expected rank lookup.
+// All of this is HBM-bound integer work: coalesced streaming loads/stores, shared-memory histograms,
+// warp match/ballot ranking; no tensor cores (nothing here is a contraction).
+#include "kernels.h"
+#include "device_common.cuh"
+
+namespace phi {
+
+#define PHI_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; if (launches) ++*launches; } while (0)
+
+// ------------------------------------------------------------------ scan
+constexpr int SCAN_T = 256, SCAN_I = 8, SCAN_B = SCAN_T * SCAN_I;
+
+template <class T>
+__device__ __forceinline__ T block_exclusive(T v, T *total, T *scratch /* 32 */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    T inc = v;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { T t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) scratch[wid] = inc;
+    __syncthreads();
+    T off = 0, tot = 0;
+    for (int i = 0; i < SCAN_T / 32; ++i) { T c = scratch[i]; if (i < wid) off += c; tot += c; }
+    __syncthreads();
+    *total = tot;
+    return off + inc - v;
+}
+
+template <class Tin, class Tout>
+__global__ void __launch_bounds__(SCAN_T) scan_reduce_kernel(const Tin *in, uint64_t n, Tout *sums)
+{
+    __shared__ Tout scratch[32];
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_B + threadIdx.x * SCAN_I;
+    Tout s = 0;
+    #pragma unroll
+    for (int i = 0; i < SCAN_I; ++i) if (base + i < n) s += (Tout)in[base + i];
+    Tout tot;
+    block_exclusive<Tout>(s, &tot, scratch);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+template <class Tin, class Tout>
+__global__ void __launch_bounds__(SCAN_T) scan_apply_kernel(const Tin *in, Tout *out, uint64_t n, const Tout *sums_scanned)
+{
+    __shared__ Tout scratch[32];
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_B + threadIdx.x * SCAN_I;
+    Tout v[SCAN_I]; Tout s = 0;
+    #pragma unroll
+    for (int i = 0; i < SCAN_I; ++i) { v[i] = base + i < n ? (Tout)in[base + i] : 0; s += v[i]; }
+    Tout tot;
+    Tout ex = block_exclusive<Tout>(s, &tot, scratch) + (sums_scanned ? sums_scanned[blockIdx.x] : 0);
+    #pragma unroll
+    for (int i = 0; i < SCAN_I; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+}
+
+template <class Tout>
+static size_t scan_scratch_elems(uint64_t n)
+{
+    size_t tot = 0;
+    while (n > SCAN_B) { n = (n + SCAN_B - 1) / SCAN_B; tot += n; }
+    return tot + 1;
+}
+
+template <class Tin, class Tout>
+static cudaError_t scan_rec(const Tin *in, Tout *out, uint64_t n, Tout *scratch, cudaStream_t st, uint64_t *launches)
+{
+    if (n == 0) return cudaSuccess;
+    uint64_t nb = (n + SCAN_B - 1) / SCAN_B;
+    if (nb == 1) {
+        scan_apply_kernel<Tin, Tout><<<1, SCAN_T, 0, st>>>(in, out, n, nullptr);
+        PHI_LAUNCH_CHECK();
+        return cudaSuccess;
+    }
+    Tout *sums = scratch;
+    scan_reduce_kernel<Tin, Tout><<<(unsigned)nb, SCAN_T, 0, st>>>(in, n, sums);
+    PHI_LAUNCH_CHECK();
+    cudaError_t e = scan_rec<Tout, Tout>(sums, sums, nb, scratch + nb, st, launches);
+    if (e != cudaSuccess) return e;
+    scan_apply_kernel<Tin, Tout><<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, n, sums);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+size_t scan_u32_to_u64_scratch(uint64_t n) { return scan_scratch_elems<uint64_t>(n) * 8; }
+cudaError_t scan_u32_to_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *scratch, cudaStream_t st, uint64_t *launches)
+{
+    return scan_rec<uint32_t, uint64_t>(in, out, n, (uint64_t *)scratch, st, launches);
+}
+size_t scan_u32_scratch(uint64_t n) { return scan_scratch_elems<uint32_t>(n) * 4; }
+cudaError_t scan_u32_inplace(uint32_t *data, uint64_t n, void *scratch, cudaStream_t st, uint64_t *launches)
+{
+    return scan_rec<uint32_t, uint32_t>(data, data, n, (uint32_t *)scratch, st, launches);
+}
+
+// ------------------------------------------------------------------ radix sort
+constexpr int RS_T = 256, RS_I = 16, RS_B = RS_T * RS_I, RS_WARPS = RS_T / 32;
+
+__global__ void __launch_bounds__(RS_T) radix_hist_kernel(const uint64_t *keys, uint64_t n, int shift, uint32_t *hist, uint32_t nb)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t base = (uint64_t)blockIdx.x * RS_B;
+    #pragma unroll 4
+    for (int i = 0; i < RS_I; ++i) {
+        uint64_t idx = base + (uint64_t)i * RS_T + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255], 1u);
+    }
+    __syncthreads();
+    hist[(uint64_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
+                                                           uint32_t *vals_out, uint64_t n, int shift, const uint32_t *hist, uint32_t nb)
+{
+    __shared__ uint32_t wcount[RS_WARPS][257];
+    __shared__ uint32_t gbase[256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_T) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * RS_B + (uint64_t)wid * (RS_I * 32);
+    uint64_t key[RS_I]; uint16_t rk[RS_I];
+    #pragma unroll
+    for (int r = 0; r < RS_I; ++r) {
+        uint64_t idx = base + r * 32 + lane;
+        bool valid = idx < n;
+        key[r] = valid ? keys_in[idx] : 0;
+        uint32_t d = valid ? (uint32_t)((key[r] >> shift) & 255) : 256u;
+        uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader) { old = wcount[wid][d]; wcount[wid][d] = old + __popc(peers); }
+        old = __shfl_sync(0xFFFFFFFFu, old, leader);
+        rk[r] = (uint16_t)(old + __popc(peers & lanemask_lt()));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        uint32_t d = threadIdx.x, run = 0;
+        #pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
+        gbase[d] = hist[(uint64_t)d * nb + blockIdx.x];
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int r = 0; r < RS_I; ++r) {
+        uint64_t idx = base + r * 32 + lane;
+        if (idx < n) {
+            uint32_t d = (uint32_t)((key[r] >> shift) & 255);
+            uint32_t dst = gbase[d] + wcount[wid][d] + rk[r];
+            keys_out[dst] = key[r];
+            if (vals_in) vals_out[dst] = vals_in[idx];
+        }
+    }
+}
+
+size_t radix_sort_scratch(uint64_t n)
+{
+    uint64_t nb = (n + RS_B - 1) / RS_B;
+    return (size_t)(256 * nb) * 4 + scan_u32_scratch(256 * nb) + 64;
+}
+
+cudaError_t radix_sort_u64(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, uint64_t n, int bit_lo, int bit_hi,
+                           void *scratch, cudaStream_t st, uint64_t *launches)
+{
+    if (n <= 1 || bit_hi <= bit_lo) return cudaSuccess;
+    if (n >= (1ull << 32)) return cudaErrorInvalidValue;
+    const uint32_t nb = (uint32_t)((n + RS_B - 1) / RS_B);
+    uint32_t *hist = (uint32_t *)scratch;
+    void *scan_scr = (void *)(hist + (size_t)256 * nb);
+    uint64_t *kin = keys_a, *kout = keys_b; uint32_t *vin = vals_a, *vout = vals_b;
+    int passes = 0;
+    for (int shift = bit_lo; shift < bit_hi; shift += 8, ++passes) {
+        radix_hist_kernel<<<nb, RS_T, 0, st>>>(kin, n, shift, hist, nb);
+        PHI_LAUNCH_CHECK();
+        cudaError_t e = scan_u32_inplace(hist, (uint64_t)256 * nb, scan_scr, st, launches);
+        if (e != cudaSuccess) return e;
+        radix_scatter_kernel<<<nb, RS_T, 0, st>>>(kin, vin, kout, vout, n, shift, hist, nb);
+        PHI_LAUNCH_CHECK();
+        uint64_t *tk = kin; kin = kout; kout = tk;
+        uint32_t *tv = vin; vin = vout; vout = tv;
+    }
+    if (passes & 1) {                                   // result currently in keys_b: bring it home
+        cudaError_t e = cudaMemcpyAsync(keys_a, keys_b, n * 8, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+        if (vals_a) { e = cudaMemcpyAsync(vals_a, vals_b, n * 4, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; }
+    }
+    return cudaSuccess;
+}
+
+// ------------------------------------------------------------------ table compaction
+__global__ void __launch_bounds__(256) table_compact_kernel(const uint64_t *table, uint64_t cap, uint64_t *out, unsigned long long *count)
+{
+    __shared__ uint32_t scratch[32];
+    __shared__ unsigned long long s_base;
+    constexpr int I = 8;
+    uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * I;
+    uint64_t v[I]; uint32_t c = 0;
+    #pragma unroll
+    for (int i = 0; i < I; ++i) { v[i] = base + i < cap ? table[base + i] : TABLE_EMPTY; c += v[i] != TABLE_EMPTY; }
+    uint32_t tot;
+    uint32_t ex = block_exclusive<uint32_t>(c, &tot, scratch);
+    if (threadIdx.x == 0) s_base = tot ? atomicAdd(count, (unsigned long long)tot) : 0ull;
+    __syncthreads();
+    uint64_t o = s_base + ex;
+    #pragma unroll
+    for (int i = 0; i < I; ++i) if (v[i] != TABLE_EMPTY) out[o++] = v[i];
+}
+
+cudaError_t table_compact(const uint64_t *table, uint64_t cap, uint64_t *out, unsigned long long *d_count, cudaStream_t st, uint64_t *launches)
+{
+    if (!cap) return cudaSuccess;
+    uint64_t nb = (cap + 2047) / 2048;
+    table_compact_kernel<<<(unsigned)nb, 256, 0, st>>>(table, cap, out, d_count);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+// ------------------------------------------------------------------ radix directory
+__global__ void directory_kernel(const uint64_t *sorted, uint32_t n, int dbits, uint32_t *dir)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t nbuckets = 1ull << dbits;
+    uint64_t pb = dbits ? sorted[i] >> (64 - dbits) : 0;
+    long long pprev = i ? (long long)(dbits ? sorted[i - 1] >> (64 - dbits) : 0) : -1;
+    for (long long b = pprev + 1; b <= (long long)pb; ++b) dir[b] = i;
+    if (i == n - 1) for (uint64_t b = pb + 1; b <= nbuckets; ++b) dir[b] = n;
+}
+
+cudaError_t build_directory(const uint64_t *sorted, uint32_t n, int dbits, uint32_t *dir, cudaStream_t st, uint64_t *launches)
+{
+    if (n == 0) return fill_u32(dir, (1ull << dbits) + 1, 0, st, launches);
+    directory_kernel<<<(n + 255) / 256, 256, 0, st>>>(sorted, n, dbits, dir);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+// ------------------------------------------------------------------ fills
+template <class T>
+__global__ void fill_kernel(T *p, uint64_t n, T v)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+cudaError_t fill_u64(uint64_t *p, uint64_t n, uint64_t v, cudaStream_t st, uint64_t *launches)
+{
+    if (!n) return cudaSuccess;
+    unsigned nb = (unsigned)((n + 1023) / 1024 < 148 * 16 ? (n + 1023) / 1024 : 148 * 16);
+    fill_kernel<uint64_t><<<nb, 256, 0, st>>>(p, n, v);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t fill_u32(uint32_t *p, uint64_t n, uint32_t v, cudaStream_t st, uint64_t *launches)
+{
+    if (!n) return cudaSuccess;
+    unsigned nb = (unsigned)((n + 1023) / 1024 < 148 * 16 ? (n + 1023) / 1024 : 148 * 16);
+    fill_kernel<uint32_t><<<nb, 256, 0, st>>>(p, n, v);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+}  // namespace phi

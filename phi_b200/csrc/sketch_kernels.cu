@@ -1,0 +1,480 @@
+// Read-sketch and walk-sketch kernels (hand-written sm_100a CUDA).
+//
+//   read_sketch_kernel : ILP_index::compute_hashes for every read + the Sp_R union
+//                        (/root/reference/src/ILP_index.cpp:447-493, :615-629), fused:
+//                        minimizer hashes go straight into an open-addressing HBM table.
+//   walk_sketch_kernel : ILP_index::index_kmers for every walk + compute_anchors
+//                        (/root/reference/src/ILP_index.cpp:359-445, :495-526, :643-655), fused:
+//                        node-spanning windows are gathered into shared memory from the segment
+//                        store, minimizers are probed against the ranked read spectrum as they are
+//                        found, and only hits (rank, walk, position, vertex list) are written.
+#include "kernels.h"
+#include "sketch_tile.cuh"
+
+namespace phi {
+
+// ------------------------------------------------------------------ block scan of two ints
+struct Scan2 { int ex_a, ex_b, tot_a, tot_b; };
+__device__ __forceinline__ Scan2 block_scan2(uint32_t *scratch /* >= 32 words */, int a, int b)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int ia = a, ib = b;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int ta = __shfl_up_sync(0xFFFFFFFFu, ia, d), tb = __shfl_up_sync(0xFFFFFFFFu, ib, d);
+        if (lane >= d) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) { scratch[2 * wid] = ia; scratch[2 * wid + 1] = ib; }
+    __syncthreads();
+    Scan2 s; s.ex_a = ia - a; s.ex_b = ib - b; s.tot_a = 0; s.tot_b = 0;
+    #pragma unroll
+    for (int i = 0; i < NT / 32; ++i) {
+        int ca = scratch[2 * i], cb = scratch[2 * i + 1];
+        if (i < wid) { s.ex_a += ca; s.ex_b += cb; }
+        s.tot_a += ca; s.tot_b += cb;
+    }
+    __syncthreads();
+    return s;
+}
+
+// ================================================================== reads
+// Insert into the open-addressing spectrum table (linear probing, u64 keys, EMPTY = ~0).
+// The key ~0 itself is recorded in flags[FLAG_HAS_MAXKEY] instead of the table.
+__device__ __forceinline__ void table_insert(uint64_t *table, uint64_t mask, uint64_t key, unsigned long long *ctr)
+{
+    if (key == TABLE_EMPTY) { ctr[CTR_HAS_MAXKEY] = 1; return; }
+    uint64_t slot = key & mask;
+    for (uint64_t tries = 0; tries <= mask; ++tries) {
+        uint64_t cur = table[slot];
+        if (cur == key) return;
+        if (cur == TABLE_EMPTY) {
+            uint64_t old = atomicCAS((unsigned long long *)&table[slot], (unsigned long long)TABLE_EMPTY, (unsigned long long)key);
+            if (old == TABLE_EMPTY) { atomicAdd(&ctr[CTR_DISTINCT], 1ull); return; }
+            if (old == key) return;
+        }
+        slot = (slot + 1) & mask;
+    }
+    ctr[CTR_OVERFLOW] = 1;
+}
+
+__global__ void __launch_bounds__(NT, 3)
+read_sketch_kernel(ReadSketchArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const TileLayout L = make_layout(A.k, A.w, false);
+    Tile t = carve(smem, L, A.k, A.w);
+    const long long tile = blockIdx.x;
+    t.g0 = tile * TILE_W - A.w;
+    t.seq_len = (long long)A.total_bases;
+    const int tid = threadIdx.x;
+
+    // ---- read boundaries -> bit mask (bit p set iff a read starts at g0 + p)
+    const int nwords = (L.NB + 31) / 32 + 1;
+    for (int i = tid; i < nwords; i += NT) t.bnd[i] = 0;
+    __syncthreads();
+    {
+        const long long hi = t.g0 + L.NB;
+        uint64_t r0 = A.tile_first_read[tile];
+        for (;;) {
+            uint64_t r = r0 + tid;
+            int past = 1;
+            if (r <= A.n_reads) {
+                long long off = (long long)A.read_off[r];
+                if (off < hi) { past = 0; atomicOr(&t.bnd[(off - t.g0) >> 5], 1u << ((off - t.g0) & 31)); }
+            }
+            if (__syncthreads_or(past)) break;
+            r0 += NT;
+        }
+    }
+    // ---- stage bases: aligned 8-byte loads, funnel to the chunk, mask outside [0, total)
+    {
+        const int nchunks = (L.NB + 7) / 8;
+        const uint64_t *words = (const uint64_t *)A.read_bases;      // 8-aligned, padded with >= 16 zero bytes
+        for (int c = tid; c < nchunks; c += NT) {
+            long long g = t.g0 + 8ll * c;
+            uint64_t v = 0;
+            if (g + 8 > 0 && g < t.seq_len) {
+                long long ga = g < 0 ? 0 : g;                        // first real byte
+                long long wi = ga >> 3; int m = (int)(ga & 7);
+                uint64_t w0 = words[wi], w1 = m ? words[wi + 1] : 0;
+                v = m ? (w0 >> (8 * m)) | (w1 << (64 - 8 * m)) : w0; // bytes ga .. ga+7
+                int lead = (int)(ga - g);                            // bytes before the sequence start
+                if (lead) v <<= 8 * lead;
+                long long nvalid = t.seq_len - g;                    // bytes [0, nvalid) of the chunk are real
+                if (nvalid < 8) v &= (1ull << (8 * nvalid)) - 1;
+            }
+            uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32), lo2 = 0, hi2 = 0;
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                lo2 |= upcase((lo >> (8 * i)) & 0xFF) << (8 * i);
+                hi2 |= upcase((hi >> (8 * i)) & 0xFF) << (8 * i);
+            }
+            stage_chunk(t, c, lo2, hi2);
+        }
+    }
+    __syncthreads();
+    phase_canon(t);
+    __syncthreads();
+    phase_block_minima(t);
+    __syncthreads();
+    phase_window_argmin(t);
+    __syncthreads();
+    uint16_t *runs = t.pre;                                          // pre+suf are contiguous and dead: >= TILE_W+1 entries
+    const int n_runs = phase_runs<true>(t, runs);
+    if (n_runs == 0) return;
+
+    if (tid == 0) t.hash[0] = halo_prev_hash<true>(t);
+    int emitted = 0;
+    for (int b0 = 0; b0 < n_runs; b0 += NT) {
+        const int j = b0 + tid; const bool have = j < n_runs;
+        const int cnt = min(NT, n_runs - b0);
+        uint32_t ent = have ? runs[j] : 0;
+        uint64_t h = have ? hash_at(t, ent & 0x7FFF) : 0;
+        t.hash[tid + 1] = h;
+        __syncthreads();
+        uint64_t prev = (ent & 0x8000) ? 0xFFFFFFFFFFFFFFFFull : t.hash[tid];
+        uint64_t carry = t.hash[cnt];
+        bool emit = have && h != prev;
+        if (emit) table_insert(A.table, A.table_mask, h, A.ctr);
+        emitted += __syncthreads_count(emit);
+        if (tid == 0) t.hash[0] = carry;
+    }
+    if (tid == 0 && emitted) atomicAdd(&A.ctr[CTR_READ_EMITTED], (unsigned long long)emitted);
+}
+
+// per tile: first read r with read_off[r] >= tile*TILE_W - w
+__global__ void read_tile_dir_kernel(const uint64_t *read_off, uint64_t n_reads, int w, uint64_t n_tiles, uint64_t *tile_first_read)
+{
+    uint64_t tile = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (tile >= n_tiles) return;
+    long long g0 = (long long)tile * TILE_W - w;
+    uint64_t lo = 0, hi = n_reads + 1;                               // search over read_off[0 .. n_reads]
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if ((long long)read_off[mid] < g0) lo = mid + 1; else hi = mid;
+    }
+    tile_first_read[tile] = lo;
+}
+
+// ================================================================== walks
+// rank of `key` in the sorted spectrum via the radix directory over the top dbits bits; -1 if absent
+__device__ __forceinline__ int64_t spectrum_probe(const uint64_t *spec, const uint32_t *dir, int dbits, uint64_t key)
+{
+    uint32_t b = dbits ? (uint32_t)(key >> (64 - dbits)) : 0u;
+    uint32_t lo = dir[b], hi = dir[b + 1];
+    for (uint32_t i = lo; i < hi; ++i) {
+        uint64_t s = spec[i];
+        if (s == key) return (int64_t)i;
+        if (s > key) break;
+    }
+    return -1;
+}
+
+// Slow anchor path: distinct vertices in first-seen order, then sorted by top_order_map
+// (/root/reference/src/ILP_index.cpp:424-435).  Returns the count; writes the list if out != nullptr.
+__device__ __noinline__ int anchor_slow(const Tile &t, int j0, int n_raw, const int32_t *top_order_map, int32_t *out)
+{
+    int32_t u[MAX_K]; int nu = 0;
+    for (int i = 0; i < n_raw; ++i) {
+        int32_t v = (int32_t)t.stepv[j0 + i];
+        bool seen = false;
+        for (int q = 0; q < nu; ++q) seen |= (u[q] == v);
+        if (!seen) u[nu++] = v;
+    }
+    for (int a = 1; a < nu; ++a) {
+        int32_t x = u[a]; int32_t tx = top_order_map[x]; int b = a - 1;
+        while (b >= 0 && top_order_map[u[b]] > tx) { u[b + 1] = u[b]; --b; }
+        u[b + 1] = x;
+    }
+    if (out) for (int i = 0; i < nu; ++i) out[i] = u[i];
+    return nu;
+}
+
+__global__ void __launch_bounds__(NT, 3)
+walk_sketch_kernel(WalkSketchArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t h = blockIdx.y;
+    const long long len = A.walk_len[h];
+    const long long tile = blockIdx.x;
+    if (len < (long long)A.w + A.k - 1) return;
+    if (tile * TILE_W > len - A.k) return;                           // no window ends in this tile
+    const TileLayout L = make_layout(A.k, A.w, true);
+    Tile t = carve(smem, L, A.k, A.w);
+    t.g0 = tile * TILE_W - A.w;
+    t.seq_len = len;
+    const int tid = threadIdx.x;
+
+    // ---- steps overlapping the tile's bases [base_lo, base_hi)
+    const long long base_lo = t.g0 < 0 ? 0 : t.g0;
+    const long long base_hi = min(len, t.g0 + (long long)L.NB);
+    const uint64_t wbeg = A.walk_off[h], wend = A.walk_off[h + 1];
+    const uint64_t s0 = wbeg + A.tile_first_step[A.walk_tile_base[h] + tile];
+    int n_steps = 0;
+    for (uint64_t c0 = s0;; c0 += NT) {
+        uint64_t s = c0 + tid; int ok = 0;
+        if (s < wend) {
+            long long sb = A.step_base[s];
+            if (sb < base_hi) {
+                ok = 1;
+                int j = (int)(s - s0);
+                t.stepv[j] = A.walk_vtx[s];
+                t.steps[j] = (uint16_t)(sb <= base_lo ? 0 : sb - base_lo);
+            }
+        }
+        int c = __syncthreads_count(ok);
+        n_steps += c;
+        if (c < NT) break;
+    }
+    if (tid == 0) t.steps[n_steps] = (uint16_t)(base_hi - base_lo);
+    const long long first_true = A.step_base[s0];                    // true start of step 0 (may precede base_lo)
+    __syncthreads();
+
+    // ---- gather bases through the step table, 8 per thread
+    {
+        const int nchunks = (L.NB + 7) / 8;
+        for (int c = tid; c < nchunks; c += NT) {
+            const long long g = t.g0 + 8ll * c;
+            uint32_t lo4 = 0, hi4 = 0;
+            if (g + 8 > base_lo && g < base_hi) {
+                long long gq = g < base_lo ? base_lo : g;
+                int q = (int)(gq - base_lo);
+                int a = 0, b = n_steps;                              // last j with steps[j] <= q
+                while (b - a > 1) { int m = (a + b) >> 1; if (t.steps[m] <= q) a = m; else b = m; }
+                int j = a;
+                long long jstart = j == 0 ? first_true : base_lo + t.steps[j];
+                const uint8_t *src = A.seg_bases + A.seg_off[t.stepv[j]] - jstart;   // src[g] is the base at walk coordinate g
+                int nxt = t.steps[j + 1];
+                #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    long long gi = g + i;
+                    uint32_t ch = 0;
+                    if (gi >= base_lo && gi < base_hi) {
+                        int qi = (int)(gi - base_lo);
+                        while (qi >= nxt) {
+                            ++j; nxt = t.steps[j + 1];
+                            src = A.seg_bases + A.seg_off[t.stepv[j]] - (base_lo + t.steps[j]);
+                        }
+                        ch = upcase(src[gi]);
+                    }
+                    if (i < 4) lo4 |= ch << (8 * i); else hi4 |= ch << (8 * (i - 4));
+                }
+            }
+            stage_chunk(t, c, lo4, hi4);
+        }
+    }
+    __syncthreads();
+    phase_canon(t);
+    __syncthreads();
+    phase_block_minima(t);
+    __syncthreads();
+    phase_window_argmin(t);
+    __syncthreads();
+    uint16_t *runs = t.pre;
+    const int n_runs = phase_runs<false>(t, runs);
+    if (n_runs == 0) return;
+
+    if (tid == 0) t.hash[0] = halo_prev_hash<false>(t);
+    int emitted = 0;
+    for (int b0 = 0; b0 < n_runs; b0 += NT) {
+        const int jr = b0 + tid; const bool have = jr < n_runs;
+        const int cnt = min(NT, n_runs - b0);
+        uint32_t ent = have ? runs[jr] : 0;
+        const int a = ent & 0x7FFF;
+        uint64_t hv = have ? hash_at(t, a) : 0;
+        t.hash[tid + 1] = hv;
+        __syncthreads();
+        uint64_t prev = (ent & 0x8000) ? 0xFFFFFFFFFFFFFFFFull : t.hash[tid];
+        uint64_t carry = t.hash[cnt];
+        bool emit = have && hv != prev;
+        emitted += __syncthreads_count(emit);
+        if (tid == 0) t.hash[0] = carry;
+
+        // ---- probe + anchor
+        int64_t rank = -1;
+        if (emit) rank = A.mode == WALK_MODE_ALL ? 0 : spectrum_probe(A.spec, A.dir, A.dbits, hv);
+        const bool hit = rank >= 0;
+        int j0 = 0, nv = 0; bool slow = false;
+        if (hit) {
+            int q = (int)(t.g0 + a - base_lo);                       // k-mer start relative to base_lo
+            int lo = 0, hi = n_steps;
+            while (hi - lo > 1) { int m = (lo + hi) >> 1; if (t.steps[m] <= q) lo = m; else hi = m; }
+            j0 = lo;
+            int j1 = j0;
+            while (t.steps[j1 + 1] < q + A.k) ++j1;                  // last step starting before the k-mer's end
+            nv = j1 - j0 + 1;
+            int32_t prev_top = -0x7FFFFFFF - 1;
+            for (int i = 0; i < nv; ++i) {                           // walk order == topological order for a valid walk
+                int32_t tp = A.top_order_map[t.stepv[j0 + i]];
+                if (i && tp <= prev_top) slow = true;
+                prev_top = tp;
+            }
+            if (slow) nv = anchor_slow(t, j0, nv, A.top_order_map, nullptr);
+        }
+        Scan2 sc = block_scan2(t.scan, hit ? 1 : 0, nv);
+        __shared__ unsigned long long s_base_hit, s_base_vtx;
+        if (tid == 0 && sc.tot_a) {
+            s_base_hit = atomicAdd(&A.ctr[CTR_HITS], (unsigned long long)sc.tot_a);
+            s_base_vtx = atomicAdd(&A.ctr[CTR_HIT_VTX], (unsigned long long)sc.tot_b);
+        }
+        __syncthreads();
+        if (hit) {
+            unsigned long long hi_idx = s_base_hit + sc.ex_a, vo = s_base_vtx + sc.ex_b;
+            if (hi_idx < A.hit_cap && vo + nv <= A.vtx_cap) {
+                A.hit_rank[hi_idx] = (uint32_t)rank;
+                A.hit_walk[hi_idx] = A.walk_id_base + h;
+                A.hit_pos[hi_idx] = (uint32_t)(t.g0 + a);
+                A.hit_voff[hi_idx] = vo;
+                A.hit_nv[hi_idx] = (uint8_t)nv;
+                if (A.hit_hash) A.hit_hash[hi_idx] = hv;
+                if (!slow) for (int i = 0; i < nv; ++i) A.vtx_pool[vo + i] = (int32_t)t.stepv[j0 + i];
+                else {
+                    int j1 = j0; int q = (int)(t.g0 + a - base_lo);
+                    while (t.steps[j1 + 1] < q + A.k) ++j1;
+                    anchor_slow(t, j0, j1 - j0 + 1, A.top_order_map, A.vtx_pool + vo);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && emitted) atomicAdd(&A.minimizers_per_walk[h], (unsigned long long)emitted);
+}
+
+// ================================================================== graph preparation
+// step_len[s] = number of bases of the segment under walk step s
+__global__ void step_len_kernel(const uint32_t *walk_vtx, const uint64_t *seg_off, uint64_t n_steps, uint32_t *step_len)
+{
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= n_steps) return;
+    uint32_t v = walk_vtx[s];
+    step_len[s] = (uint32_t)(seg_off[v + 1] - seg_off[v]);
+}
+
+__device__ __forceinline__ uint32_t walk_of_step(const uint64_t *walk_off, uint32_t n_walks, uint64_t s)
+{
+    uint32_t lo = 0, hi = n_walks;                                   // last h with walk_off[h] <= s
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
+    return lo;
+}
+
+// gbase = exclusive scan of step_len over ALL steps (u64).  Produces walk-relative step_base (u32) and, for every
+// tile of every walk, the index (relative to the walk's first step) of the step containing the tile's first base.
+__global__ void step_finalize_kernel(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
+                                     uint64_t n_steps, int w, const uint64_t *walk_tile_base, uint32_t *step_base,
+                                     uint32_t *tile_first_step)
+{
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= n_steps) return;
+    uint32_t h = walk_of_step(walk_off, n_walks, s);
+    uint64_t b = gbase[s] - gbase[walk_off[h]];
+    uint32_t len = step_len[s];
+    step_base[s] = (uint32_t)b;
+    if (len == 0) return;
+    uint64_t ntile = walk_tile_base[h + 1] - walk_tile_base[h];
+    // tile t's first base is max(0, t*TILE_W - w); it lies in [b, b+len)
+    uint64_t t_lo = b == 0 ? 0 : (b + w + TILE_W - 1) / TILE_W;      // smallest t >= 1 with t*TILE_W - w >= b (t = 0 handled by b == 0)
+    if (b != 0 && t_lo == 0) t_lo = 1;
+    for (uint64_t t = t_lo; t < ntile; ++t) {
+        long long first = (long long)t * TILE_W - w; if (first < 0) first = 0;
+        if ((uint64_t)first >= b + len) break;
+        if ((uint64_t)first >= b) tile_first_step[walk_tile_base[h] + t] = (uint32_t)(s - walk_off[h]);
+    }
+}
+
+// walk_len[h] (bases) from the global scan
+__global__ void walk_len_kernel(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
+                                uint64_t n_steps, uint64_t *walk_len)
+{
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_walks) return;
+    uint64_t a = walk_off[h], b = walk_off[h + 1];
+    uint64_t ga = a < n_steps ? gbase[a] : (n_steps ? gbase[n_steps - 1] + step_len[n_steps - 1] : 0);
+    uint64_t gb = b < n_steps ? gbase[b] : (n_steps ? gbase[n_steps - 1] + step_len[n_steps - 1] : 0);
+    walk_len[h] = gb - ga;
+}
+
+// ================================================================== hash KAT hook
+__global__ void hash_bytes_kernel(const uint8_t *keys, uint64_t n, int len, uint64_t *out)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *p = keys + i * (uint64_t)len;
+    uint64_t W[4] = {0, 0, 0, 0};
+    bool clean = true;
+    for (int j = 0; j < len; ++j) { W[j >> 3] |= (uint64_t)p[j] << (8 * (j & 7)); clean &= is_acgt(p[j]); }
+    uint64_t h = murmur3_x64_128_xor(W, len);
+    if (clean) {                                                      // cross-check the packed path used by the sketch kernels
+        uint64_t km = 0;
+        for (int j = 0; j < len; ++j) km = (km << 2) | code2(p[j]);
+        uint64_t h2 = hash_packed_kmer(km, len);
+        if (h2 != h) h = ~h;                                          // make any divergence visible to the test
+    }
+    out[i] = h;
+}
+
+// ------------------------------------------------------------------ launchers
+static size_t tile_smem_bytes(int k, int w, bool walk) { return (size_t)make_layout(k, w, walk).bytes; }
+
+cudaError_t launch_read_tile_dir(const uint64_t *read_off, uint64_t n_reads, int w, uint64_t n_tiles, uint64_t *out, cudaStream_t st)
+{
+    if (!n_tiles) return cudaSuccess;
+    read_tile_dir_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(read_off, n_reads, w, n_tiles, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_read_sketch(const ReadSketchArgs &A, uint64_t n_tiles, cudaStream_t st)
+{
+    if (!n_tiles) return cudaSuccess;
+    size_t smem = tile_smem_bytes(A.k, A.w, false);
+    cudaError_t e = cudaFuncSetAttribute(read_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    read_sketch_kernel<<<(unsigned)n_tiles, NT, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_walk_sketch(const WalkSketchArgs &A, uint32_t n_walks, uint64_t max_tiles, cudaStream_t st)
+{
+    if (!n_walks || !max_tiles) return cudaSuccess;
+    size_t smem = tile_smem_bytes(A.k, A.w, true);
+    cudaError_t e = cudaFuncSetAttribute(walk_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)max_tiles, n_walks);
+    walk_sketch_kernel<<<grid, NT, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step_len(const uint32_t *walk_vtx, const uint64_t *seg_off, uint64_t n_steps, uint32_t *step_len, cudaStream_t st)
+{
+    if (!n_steps) return cudaSuccess;
+    step_len_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, seg_off, n_steps, step_len);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_walk_len(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
+                            uint64_t n_steps, uint64_t *walk_len, cudaStream_t st)
+{
+    if (!n_walks) return cudaSuccess;
+    walk_len_kernel<<<(n_walks + 127) / 128, 128, 0, st>>>(gbase, step_len, walk_off, n_walks, n_steps, walk_len);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step_finalize(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
+                                 uint64_t n_steps, int w, const uint64_t *walk_tile_base, uint32_t *step_base,
+                                 uint32_t *tile_first_step, cudaStream_t st)
+{
+    if (!n_steps) return cudaSuccess;
+    step_finalize_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(gbase, step_len, walk_off, n_walks, n_steps, w,
+                                                                           walk_tile_base, step_base, tile_first_step);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hash_bytes(const uint8_t *keys, uint64_t n, int len, uint64_t *out, cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    hash_bytes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(keys, n, len, out);
+    return cudaGetLastError();
+}
+
+int tile_windows() { return TILE_W; }
+
+}  // namespace phi

