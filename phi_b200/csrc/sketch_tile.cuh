@@ -45,19 +45,20 @@ __host__ __device__ inline TileLayout make_layout(int k, int w, bool walk)
     L.NB = L.M + k - 1;
     const int nb8 = align_up(L.NB, 8) + 8;               // bases, padded so chunked stores stay in bounds
     int o = 0;
-    L.o_canon = o; o += 8 * L.M;
-    L.o_hash = o;  o += 8 * (NT + 1);
-    L.o_pack = o;  o += 4 * (nb8 / 16 + 4);
-    L.o_dirty = o; o += 4 * (nb8 / 32 + 4);
-    L.o_bnd = o;   o += 4 * (nb8 / 32 + 4);
-    L.o_scan = o;  o += 4 * 64;
-    L.o_pre = o;   o += 2 * align_up(L.M, 2);
-    L.o_suf = o;   o += 2 * align_up(L.M, 2);
-    L.o_arg = o;   o += 2 * align_up(L.M, 2);
-    L.o_stepv = o; o += walk ? 4 * (L.NB + 2) : 0;
-    L.o_steps = o; o += walk ? 2 * align_up(L.NB + 2, 2) : 0;
-    L.o_flag = o;  o += align_up(L.M, 8);
-    L.o_base = o;  o += nb8;
+    auto take = [&o](int bytes) { int at = o; o += align_up(bytes, 16); return at; };   // every section 16-byte aligned
+    L.o_canon = take(8 * L.M);
+    L.o_hash = take(8 * (NT + 1));
+    L.o_pack = take(4 * (nb8 / 16 + 4));
+    L.o_dirty = take(4 * (nb8 / 32 + 4));
+    L.o_bnd = take(4 * (nb8 / 32 + 4));
+    L.o_scan = take(4 * 64);
+    L.o_pre = take(2 * align_up(L.M, 2));            // pre and suf stay adjacent: runs[] aliases both
+    L.o_suf = take(2 * align_up(L.M, 2));
+    L.o_arg = take(2 * align_up(L.M, 2));
+    L.o_stepv = take(walk ? 4 * (L.NB + 2) : 0);
+    L.o_steps = take(walk ? 2 * (L.NB + 2) : 0);
+    L.o_flag = take(L.M);
+    L.o_base = take(nb8);
     L.bytes = align_up(o, 16);
     return L;
 }
