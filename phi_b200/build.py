@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
             raise RuntimeError(f"nvcc failed on {s}")
     if procs or force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "static"]
         subprocess.check_call(cmd)
     if log:
         with open(os.path.join(objdir, "ptxas.log"), "w") as f:
