@@ -156,7 +156,13 @@ int phi_gpu_index_upload(phi_gpu_index_ctx *ctx, const phi_graph_view *graph, co
 int phi_gpu_index_run_resident(phi_gpu_index_ctx *ctx, const phi_index_params *params, int download,
                                phi_index_result **out);
 
+/* Result arrays live in pinned host memory borrowed from the ctx; _result_free hands it back for reuse by the next
+ * run (free a result before the next run on the same ctx and no new pinning happens).  Safe after ctx destroy. */
 void phi_gpu_index_result_free(phi_index_result *res);
+/* Pinned (page-locked) host memory for INPUT buffers: views that point into it are copied to the device at full
+ * PCIe speed; ordinary pageable memory works too, only slower. */
+void *phi_gpu_host_alloc(size_t bytes);
+void phi_gpu_host_free(void *p);
 int phi_gpu_index_last_times(const phi_gpu_index_ctx *ctx, phi_stage_times *out);
 
 /*

@@ -54,6 +54,9 @@ def load_library():
     lib.phi_gpu_index_free_u64.argtypes = [_abi.u64p]
     lib.phi_gpu_hash128_to_64.restype = C.c_int
     lib.phi_gpu_hash128_to_64.argtypes = [ctxp, C.c_char_p, C.c_uint64, C.c_int32, _abi.u64p]
+    lib.phi_gpu_host_alloc.restype = C.c_void_p
+    lib.phi_gpu_host_alloc.argtypes = [C.c_size_t]
+    lib.phi_gpu_host_free.argtypes = [C.c_void_p]
     lib.phi_shard_owner_of_hash.restype = C.c_int
     lib.phi_shard_owner_of_hash.argtypes = [C.c_uint64, C.c_int]
     lib.phi_shard_split_by_weight.restype = C.c_int
@@ -77,6 +80,9 @@ class PhiGpuIndex:
         if getattr(self, "ctx", None):
             self.lib.phi_gpu_index_destroy(self.ctx)
             self.ctx = None
+            for p in getattr(self, "_pinned", []):
+                self.lib.phi_gpu_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -99,11 +105,39 @@ class PhiGpuIndex:
         return res
 
     def run(self, graph, reads, k=31, w=25, threshold=1.0):
-        """Host buffers in, host result out (H2D + kernels + D2H): the drop-in call."""
+        """Host buffers in, host result out (H2D + kernels + D2H): the drop-in call.  Returns numpy copies."""
+        return self._take(self.run_raw(graph, reads, k, w, threshold))
+
+    def run_raw(self, graph, reads, k=31, w=25, threshold=1.0):
+        """The same call, returning the C result pointer untouched (no numpy copies); free it with free_raw()."""
         gv, rv, prm = graph.view(), reads.view(), self._params(k, w, threshold)
         out = C.POINTER(_abi.IndexResult)()
         self._check(self.lib.phi_gpu_index_run(self.ctx, C.byref(gv), C.byref(rv), C.byref(prm), C.byref(out)))
-        return self._take(out)
+        return out
+
+    def free_raw(self, out):
+        self.lib.phi_gpu_index_result_free(out)
+
+    def pinned_copy(self, arr):
+        """Copy a numpy array into pinned host memory (phi_gpu_host_alloc) and return a numpy view on it."""
+        arr = np.ascontiguousarray(arr)
+        nbytes = max(arr.nbytes, 1)
+        p = self.lib.phi_gpu_host_alloc(nbytes)
+        if not p:
+            raise PhiGpuError(_abi.PHI_ERR_NOMEM, "phi_gpu_host_alloc failed")
+        buf = (C.c_uint8 * nbytes).from_address(p)
+        out = np.frombuffer(buf, dtype=arr.dtype, count=arr.size).reshape(arr.shape)
+        out[...] = arr
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        return out
+
+    def pinned_inputs(self, graph, reads):
+        """Graph / Reads whose arrays live in pinned host memory."""
+        g = _abi.Graph(self.pinned_copy(graph.seg_off), self.pinned_copy(graph.seg_bases), self.pinned_copy(graph.walk_off),
+                       self.pinned_copy(graph.walk_vtx), self.pinned_copy(graph.top_order_map), graph.walk_names)
+        r = _abi.Reads(self.pinned_copy(reads.read_off), self.pinned_copy(reads.read_bases))
+        return g, r
 
     def upload(self, graph, reads):
         gv, rv = graph.view(), reads.view()

@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -34,6 +36,9 @@ struct DevBuf {                       // grow-only device buffer
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T *as() const { return (T *)p; }
 };
+
+// pinned host buffer recycled through the ctx's pool (result arrays land here: D2H at full PCIe speed, no staging copy)
+struct PinnedBuf { void *p = nullptr; size_t cap = 0; };
 
 enum { EV_START, EV_H2D, EV_PREP, EV_READS, EV_SPECTRUM, EV_WALKS, EV_FILTER, EV_END, EV_RK0, EV_RK1, EV_WK0, EV_WK1, EV_COUNT };
 
@@ -61,6 +66,7 @@ struct phi_gpu_index_ctx {
     DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
     DevBuf anchor_off, anchor_rank, anchor_walk, anchor_vtx, apw, walk_gbase;
     unsigned long long *h_ctr = nullptr;   // pinned mirror of the counter block
+    std::vector<PinnedBuf> pinned_pool;    // free pinned buffers (returned by phi_gpu_index_result_free)
 
     // multi-GPU (set by comm_init)
     int rank = 0, world = 1; uint32_t walk_id_base = 0, n_walks_global = 0;
@@ -68,6 +74,9 @@ struct phi_gpu_index_ctx {
 
     int fail(int code, const std::string &m) { err = m; return code; }
 };
+
+static std::mutex g_live_mu;                       // live ctxs: a result freed after its ctx releases its pinned buffers itself
+static std::set<phi_gpu_index_ctx *> g_live_ctx;
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx->fail(PHI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
@@ -101,6 +110,7 @@ extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
     if ((e = cudaHostAlloc((void **)&ctx->h_ctr, CTR_COUNT * 8, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     if ((e = ctx->ctr.reserve(CTR_COUNT * 8)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    { std::lock_guard<std::mutex> lk(g_live_mu); g_live_ctx.insert(ctx); }
     *out = ctx;
     return PHI_OK;
 }
@@ -118,6 +128,12 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
                       &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->big_list, &ctx->tmp_order, &ctx->nv_out,
                       &ctx->anchor_off, &ctx->anchor_rank, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw, &ctx->walk_gbase};
     for (DevBuf *b : bufs) b->release();
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        g_live_ctx.erase(ctx);
+        for (PinnedBuf &pb : ctx->pinned_pool) cudaFreeHost(pb.p);
+        ctx->pinned_pool.clear();
+    }
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->st) cudaStreamDestroy(ctx->st);
@@ -485,15 +501,49 @@ static int stage_filter(phi_gpu_index_ctx *ctx, const std::vector<uint64_t> &h_w
     return PHI_OK;
 }
 
-static phi_index_result *alloc_result() { return (phi_index_result *)calloc(1, sizeof(phi_index_result)); }
+// A result owns pinned buffers borrowed from its ctx's pool; freeing it hands them back (or releases them if the ctx is gone).
+struct ResultBox {
+    phi_index_result pub;              // must stay the first member: the public pointer is &box->pub
+    phi_gpu_index_ctx *owner;
+    PinnedBuf bufs[8]; int nbufs;
+};
+static PinnedBuf pinned_acquire(phi_gpu_index_ctx *ctx, size_t bytes)
+{
+    PinnedBuf best; int bi = -1;
+    for (size_t i = 0; i < ctx->pinned_pool.size(); ++i)
+        if (ctx->pinned_pool[i].cap >= bytes && (bi < 0 || ctx->pinned_pool[i].cap < best.cap)) { best = ctx->pinned_pool[i]; bi = (int)i; }
+    if (bi >= 0) { ctx->pinned_pool.erase(ctx->pinned_pool.begin() + bi); return best; }
+    PinnedBuf b; size_t want = bytes + bytes / 4 + 4096;
+    if (cudaHostAlloc(&b.p, want, cudaHostAllocDefault) == cudaSuccess) b.cap = want; else b.p = nullptr;
+    return b;
+}
+
+static phi_index_result *alloc_result(phi_gpu_index_ctx *ctx)
+{
+    ResultBox *b = (ResultBox *)calloc(1, sizeof(ResultBox));
+    if (b) b->owner = ctx;
+    return b ? &b->pub : nullptr;
+}
 
 extern "C" void phi_gpu_index_result_free(phi_index_result *r)
 {
     if (!r) return;
-    free((void *)r->spectrum); free((void *)r->anchor_rank); free((void *)r->anchor_walk); free((void *)r->anchor_off);
-    free((void *)r->anchor_vtx); free((void *)r->minimizers_per_walk); free((void *)r->anchors_per_walk);
-    free(r);
+    ResultBox *b = (ResultBox *)r;
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    const bool alive = g_live_ctx.count(b->owner) != 0;
+    for (int i = 0; i < b->nbufs; ++i) {
+        if (!b->bufs[i].p) continue;
+        if (alive) b->owner->pinned_pool.push_back(b->bufs[i]); else cudaFreeHost(b->bufs[i].p);
+    }
+    free(b);
 }
+
+extern "C" void *phi_gpu_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+extern "C" void phi_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" void phi_gpu_index_free_u64(uint64_t *p) { free(p); }
 
 static int validate_params(phi_gpu_index_ctx *ctx, const phi_index_params *p)
@@ -506,12 +556,14 @@ static int validate_params(phi_gpu_index_ctx *ctx, const phi_index_params *p)
 }
 
 template <class T>
-static int download(phi_gpu_index_ctx *ctx, const void *dev, uint64_t n, const T **out)
+static int download(phi_gpu_index_ctx *ctx, phi_index_result *res, const void *dev, uint64_t n, const T **out)
 {
-    T *h = (T *)malloc(std::max<uint64_t>(n, 1) * sizeof(T));
-    if (!h) return ctx->fail(PHI_ERR_NOMEM, "host allocation failed");
-    if (n) CU(cudaMemcpyAsync(h, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->st));
-    *out = h;
+    ResultBox *b = (ResultBox *)res;
+    PinnedBuf pb = pinned_acquire(ctx, std::max<uint64_t>(n, 1) * sizeof(T));
+    if (!pb.p) return ctx->fail(PHI_ERR_NOMEM, "pinned host allocation failed");
+    b->bufs[b->nbufs++] = pb;
+    if (n) CU(cudaMemcpyAsync(pb.p, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->st));
+    *out = (const T *)pb.p;
     return PHI_OK;
 }
 
@@ -569,11 +621,11 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     if (ctx->world == 1) for (uint32_t h = 0; h < H; ++h) h_walk_gbase[h + 1] = h_walk_gbase[h] + h_walk_len[h];
     else for (uint32_t h = 0; h < HG; ++h) h_walk_gbase[h + 1] = h_walk_gbase[h] + (1ull << 31);   // any monotone walk-major coordinate orders correctly
 
-    phi_index_result *res = alloc_result();
+    phi_index_result *res = alloc_result(ctx);
     if (!res) return ctx->fail(PHI_ERR_NOMEM, "host allocation failed");
     if (mode == WALK_MODE_PROBE) {
         rc = stage_filter(ctx, h_walk_gbase, HG, prm->threshold, o);
-        if (rc) { free(res); return rc; }
+        if (rc) { phi_gpu_index_result_free(res); return rc; }
     } else {
         // sketch-only: order all emitted minimizers by (walk, position) and build the CSR without filtering
         unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
@@ -622,16 +674,16 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     res->read_kmer_positions = o.read_pos; res->path_kmer_positions = o.path_pos;
     res->read_minimizers_emitted = o.read_emitted; res->path_hits = o.n_hits;
     if (do_download) {
-        rc = download<uint64_t>(ctx, ctx->spec_a.p, mode == WALK_MODE_PROBE ? o.n_spec : 0, &res->spectrum);
-        if (!rc) rc = download<int32_t>(ctx, ctx->anchor_rank.p, o.n_surv, &res->anchor_rank);
-        if (!rc) rc = download<int32_t>(ctx, ctx->anchor_walk.p, o.n_surv, &res->anchor_walk);
-        if (!rc) rc = download<uint64_t>(ctx, ctx->anchor_off.p, o.n_surv + 1, &res->anchor_off);
-        if (!rc) rc = download<int32_t>(ctx, ctx->anchor_vtx.p, o.n_anchor_vtx, &res->anchor_vtx);
-        if (!rc) rc = download<uint64_t>(ctx, ctx->apw.as<uint64_t>() + ctx->walk_id_base, H, &res->anchors_per_walk);
+        rc = download<uint64_t>(ctx, res, ctx->spec_a.p, mode == WALK_MODE_PROBE ? o.n_spec : 0, &res->spectrum);
+        if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_rank.p, o.n_surv, &res->anchor_rank);
+        if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_walk.p, o.n_surv, &res->anchor_walk);
+        if (!rc) rc = download<uint64_t>(ctx, res, ctx->anchor_off.p, o.n_surv + 1, &res->anchor_off);
+        if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_vtx.p, o.n_anchor_vtx, &res->anchor_vtx);
+        if (!rc) rc = download<uint64_t>(ctx, res, ctx->apw.as<uint64_t>() + ctx->walk_id_base, H, &res->anchors_per_walk);
         if (rc) { phi_gpu_index_result_free(res); return rc; }
     }
     {   // per-walk minimizer counts are tiny and always returned
-        int rc2 = download<uint64_t>(ctx, ctx->mpw.p, H, &res->minimizers_per_walk);
+        int rc2 = download<uint64_t>(ctx, res, ctx->mpw.p, H, &res->minimizers_per_walk);
         if (rc2) { phi_gpu_index_result_free(res); return rc2; }
     }
     uint64_t *hashes = nullptr; uint32_t *h_order = nullptr;
