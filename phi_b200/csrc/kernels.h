@@ -19,13 +19,25 @@ enum {
     CTR_SURVIVORS = 7,
     CTR_BIG_GROUPS = 8,
     CTR_ZERO_STEPS = 9,
+    CTR_READ_POS = 10,
+    CTR_COMPACT = 11,
+    CTR_NONMONO = 12,      // some walk is not strictly increasing in top_order_map
     CTR_COUNT = 16
 };
 
 enum { WALK_MODE_PROBE = 0, WALK_MODE_ALL = 1 };
 
+// shared-memory carve-up of a sketch tile (computed on the host: sketch_tile.cuh make_layout)
+struct TileLayout {
+    int M, M8, NB, nchunks;
+    int o_canon, o_hash, o_pack, o_dirty, o_bnd, o_scan, o_pre, o_suf, o_flag, o_base, o_stepv, o_steps, o_cfirst, o_cmask;
+    int bytes;
+};
+TileLayout tile_layout(int k, int w, bool walk);
+
 struct ReadSketchArgs {
-    const uint8_t *read_bases;        // 8-aligned, >= 16 zero bytes of padding after total_bases
+    TileLayout layout;
+    const uint8_t *read_bases;        // 16 readable bytes in front, >= 16 zero bytes after total_bases
     const uint64_t *read_off;         // [n_reads + 1]
     uint64_t n_reads, total_bases;
     const uint64_t *tile_first_read;  // [n_tiles]
@@ -35,7 +47,10 @@ struct ReadSketchArgs {
 };
 
 struct WalkSketchArgs {
-    const uint8_t *seg_bases; const uint64_t *seg_off; const int32_t *top_order_map;
+    TileLayout layout;
+    int walks_monotone;                                       // every walk strictly increasing in top_order_map: anchors need no per-hit check
+    const uint8_t *seg_bases;                                 // 16 readable bytes in front, >= 16 after
+    const uint64_t *seg_off; const int32_t *top_order_map;
     const uint32_t *walk_vtx; const uint64_t *walk_off;      // zero-length steps removed
     const uint32_t *step_base;                                // walk-relative first base of each step
     const uint64_t *walk_len;                                 // [n_walks] bases
@@ -63,6 +78,8 @@ cudaError_t launch_walk_len(const uint64_t *gbase, const uint32_t *step_len, con
 cudaError_t launch_step_finalize(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
                                  uint64_t n_steps, int w, const uint64_t *walk_tile_base, uint32_t *step_base,
                                  uint32_t *tile_first_step, cudaStream_t st);
+cudaError_t launch_walk_monotone(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
+                                 const int32_t *top_order_map, unsigned long long *ctr, cudaStream_t st);
 cudaError_t launch_hash_bytes(const uint8_t *keys, uint64_t n, int len, uint64_t *out, cudaStream_t st);
 
 // primitives.cu — all on `st`, scratch supplied by the caller

@@ -165,20 +165,24 @@ extern "C" int phi_gpu_index_upload(phi_gpu_index_ctx *ctx, const phi_graph_view
     static const uint64_t zero_off[1] = {0};
 
     CU(ctx->seg_off.reserve(((size_t)g->n_vtx + 1) * 8));
-    CU(ctx->seg_bases.reserve(ctx->seg_total + 16));
+    CU(ctx->seg_bases.reserve(ctx->seg_total + 64));
     CU(ctx->top_order.reserve((size_t)g->n_vtx * 4 + 4));
     CU(ctx->walk_off.reserve(((size_t)g->n_walks + 1) * 8));
     CU(ctx->walk_vtx.reserve(ctx->n_steps * 4 + 4));
     CU(ctx->read_off.reserve((ctx->n_reads + 1) * 8));
-    CU(ctx->read_bases.reserve(ctx->read_total + 32));
+    CU(ctx->read_bases.reserve(ctx->read_total + 64));
     CU(cudaMemcpyAsync(ctx->seg_off.p, g->n_vtx ? g->seg_off : zero_off, ((size_t)g->n_vtx + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
-    if (ctx->seg_total) CU(cudaMemcpyAsync(ctx->seg_bases.p, g->seg_bases, ctx->seg_total, cudaMemcpyHostToDevice, ctx->st));
+    // sequence buffers carry 16 readable bytes in front and zero padding behind: the sketch kernels use unaligned 8-byte loads
+    CU(cudaMemsetAsync(ctx->seg_bases.p, 0, 16, ctx->st));
+    CU(cudaMemsetAsync((char *)ctx->seg_bases.p + 16 + ctx->seg_total, 0, 32, ctx->st));
+    if (ctx->seg_total) CU(cudaMemcpyAsync((char *)ctx->seg_bases.p + 16, g->seg_bases, ctx->seg_total, cudaMemcpyHostToDevice, ctx->st));
     if (g->n_vtx) CU(cudaMemcpyAsync(ctx->top_order.p, g->top_order_map, (size_t)g->n_vtx * 4, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->walk_off.p, g->n_walks ? g->walk_off : zero_off, ((size_t)g->n_walks + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
     if (ctx->n_steps) CU(cudaMemcpyAsync(ctx->walk_vtx.p, g->walk_vtx, ctx->n_steps * 4, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->read_off.p, ctx->n_reads ? r->read_off : zero_off, (ctx->n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
-    if (ctx->read_total) CU(cudaMemcpyAsync(ctx->read_bases.p, r->read_bases, ctx->read_total, cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaMemsetAsync((char *)ctx->read_bases.p + ctx->read_total, 0, 32, ctx->st));
+    CU(cudaMemsetAsync(ctx->read_bases.p, 0, 16, ctx->st));
+    if (ctx->read_total) CU(cudaMemcpyAsync((char *)ctx->read_bases.p + 16, r->read_bases, ctx->read_total, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemsetAsync((char *)ctx->read_bases.p + 16 + ctx->read_total, 0, 32, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     ctx->have_inputs = true;
     return PHI_OK;
@@ -257,8 +261,10 @@ struct RunOut {                    // device-side products of one run
 
 // ---- stage: graph preparation (depends on k, w through the tile directory)
 static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<uint64_t> &h_walk_len, std::vector<uint64_t> &h_tile_base,
-                            uint64_t &max_tiles, const uint32_t *&d_walk_vtx, const uint64_t *&d_walk_off, uint64_t &n_steps_eff)
+                            uint64_t &max_tiles, const uint32_t *&d_walk_vtx, const uint64_t *&d_walk_off, uint64_t &n_steps_eff,
+                            int &walks_monotone)
 {
+    walks_monotone = 1;
     const uint32_t H = ctx->n_walks; const uint64_t S = ctx->n_steps;
     d_walk_vtx = ctx->walk_vtx.as<uint32_t>(); d_walk_off = ctx->walk_off.as<uint64_t>(); n_steps_eff = S;
     h_walk_len.assign(H, 0); h_tile_base.assign(H + 1, 0); max_tiles = 0;
@@ -293,10 +299,12 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     }
     const uint64_t S2 = n_steps_eff;
     CU(scan_u32_to_u64(ctx->step_len.as<uint32_t>(), ctx->gbase.as<uint64_t>(), S2, ctx->scan_scr.p, ctx->st, &ctx->launches));
+    CU(launch_walk_monotone(d_walk_vtx, d_walk_off, H, S2, ctx->top_order.as<int32_t>(), ctx->ctr.as<unsigned long long>(), ctx->st)); ctx->launches++;
     CU(ctx->walk_len.reserve((size_t)H * 8));
     CU(launch_walk_len(ctx->gbase.as<uint64_t>(), ctx->step_len.as<uint32_t>(), d_walk_off, H, S2, ctx->walk_len.as<uint64_t>(), ctx->st)); ctx->launches++;
     CU(cudaMemcpyAsync(h_walk_len.data(), ctx->walk_len.p, (size_t)H * 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(read_counters(ctx));                                             // also syncs: walk lengths + the monotonicity flag
+    walks_monotone = ctx->h_ctr[CTR_NONMONO] ? 0 : 1;
     const int T = tile_windows();
     for (uint32_t h = 0; h < H; ++h) {
         uint64_t len = h_walk_len[h];
@@ -325,7 +333,7 @@ static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbi
     CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st));
     CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
     if (n_tiles) {
-        count_positions_kernel<<<(unsigned)((R + 255) / 256), 256, 0, ctx->st>>>(ctx->read_off.as<uint64_t>(), R, k, w, d_ctr + 10);
+        count_positions_kernel<<<(unsigned)((R + 255) / 256), 256, 0, ctx->st>>>(ctx->read_off.as<uint64_t>(), R, k, w, d_ctr + CTR_READ_POS);
         CU(cudaGetLastError()); ctx->launches++;
         CU(ctx->tile_first_read.reserve(n_tiles * 8));
         CU(launch_read_tile_dir(ctx->read_off.as<uint64_t>(), R, w, n_tiles, ctx->tile_first_read.as<uint64_t>(), ctx->st)); ctx->launches++;
@@ -338,7 +346,8 @@ static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbi
             CU(fill_u64(ctx->table.as<uint64_t>(), cap, TABLE_EMPTY, ctx->st, &ctx->launches));
             CU(cudaMemsetAsync(d_ctr, 0, 4 * 8, ctx->st));                 // DISTINCT, OVERFLOW, HAS_MAXKEY, READ_EMITTED
             ReadSketchArgs A;
-            A.read_bases = ctx->read_bases.as<uint8_t>(); A.read_off = ctx->read_off.as<uint64_t>();
+            A.layout = tile_layout(k, w, false);
+            A.read_bases = ctx->read_bases.as<uint8_t>() + 16; A.read_off = ctx->read_off.as<uint64_t>();
             A.n_reads = R; A.total_bases = G; A.tile_first_read = ctx->tile_first_read.as<uint64_t>();
             A.k = k; A.w = w; A.table = ctx->table.as<uint64_t>(); A.table_mask = cap - 1; A.ctr = d_ctr;
             CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st));
@@ -349,7 +358,7 @@ static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbi
             cap <<= 1;
         }
         o.read_emitted = ctx->h_ctr[CTR_READ_EMITTED];
-        o.read_pos = ctx->h_ctr[10];
+        o.read_pos = ctx->h_ctr[CTR_READ_POS];
         const uint64_t nd = ctx->h_ctr[CTR_DISTINCT];
         const bool maxkey = ctx->h_ctr[CTR_HAS_MAXKEY] != 0;
         n_spec = nd + (maxkey ? 1 : 0);
@@ -358,8 +367,8 @@ static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbi
         CU(ctx->spec_a.reserve((n_spec + 1) * 8));
         CU(ctx->spec_b.reserve((n_spec + 1) * 8));
         CU(ctx->sort_scr.reserve(radix_sort_scratch(std::max<uint64_t>(n_spec, 1))));
-        CU(cudaMemsetAsync(d_ctr + 11, 0, 8, ctx->st));
-        CU(table_compact(ctx->table.as<uint64_t>(), cap, ctx->spec_a.as<uint64_t>(), d_ctr + 11, ctx->st, &ctx->launches));
+        CU(cudaMemsetAsync(d_ctr + CTR_COMPACT, 0, 8, ctx->st));
+        CU(table_compact(ctx->table.as<uint64_t>(), cap, ctx->spec_a.as<uint64_t>(), d_ctr + CTR_COMPACT, ctx->st, &ctx->launches));
         CU(radix_sort_u64(ctx->spec_a.as<uint64_t>(), ctx->spec_b.as<uint64_t>(), nullptr, nullptr, nd, 0, 64, ctx->sort_scr.p, ctx->st, &ctx->launches));
         if (maxkey) CU(fill_u64(ctx->spec_a.as<uint64_t>() + nd, 1, TABLE_EMPTY, ctx->st, &ctx->launches));
     } else {
@@ -376,7 +385,7 @@ static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbi
 
 // ---- stage: walks -> hits
 static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits, const std::vector<uint64_t> &h_walk_len, uint64_t max_tiles,
-                       const uint32_t *d_walk_vtx, const uint64_t *d_walk_off, uint64_t n_steps_eff, RunOut &o)
+                       const uint32_t *d_walk_vtx, const uint64_t *d_walk_off, uint64_t n_steps_eff, int walks_monotone, RunOut &o)
 {
     const uint32_t H = ctx->n_walks;
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
@@ -401,7 +410,8 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
         CU(cudaMemsetAsync(ctx->mpw.p, 0, ((size_t)H + 1) * 8, ctx->st));
         CU(cudaMemsetAsync(d_ctr + CTR_HITS, 0, 2 * 8, ctx->st));
         WalkSketchArgs A;
-        A.seg_bases = ctx->seg_bases.as<uint8_t>(); A.seg_off = ctx->seg_off.as<uint64_t>(); A.top_order_map = ctx->top_order.as<int32_t>();
+        A.layout = tile_layout(k, w, true); A.walks_monotone = walks_monotone;
+        A.seg_bases = ctx->seg_bases.as<uint8_t>() + 16; A.seg_off = ctx->seg_off.as<uint64_t>(); A.top_order_map = ctx->top_order.as<int32_t>();
         A.walk_vtx = d_walk_vtx; A.walk_off = d_walk_off; A.step_base = ctx->step_base.as<uint32_t>();
         A.walk_len = ctx->walk_len.as<uint64_t>(); A.walk_tile_base = ctx->walk_tile_base.as<uint64_t>();
         A.tile_first_step = ctx->tile_first_step.as<uint32_t>();
@@ -599,7 +609,8 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     RunOut o;
     std::vector<uint64_t> h_walk_len, h_tile_base; uint64_t max_tiles = 0, n_steps_eff = 0;
     const uint32_t *d_walk_vtx; const uint64_t *d_walk_off;
-    rc = stage_graph_prep(ctx, k, w, h_walk_len, h_tile_base, max_tiles, d_walk_vtx, d_walk_off, n_steps_eff);
+    int walks_monotone = 1;
+    rc = stage_graph_prep(ctx, k, w, h_walk_len, h_tile_base, max_tiles, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[EV_PREP], ctx->st));
     int dbits = 0;
@@ -611,7 +622,7 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
         CU(cudaEventRecord(ctx->ev[EV_READS], ctx->st));
     }
     CU(cudaEventRecord(ctx->ev[EV_SPECTRUM], ctx->st));
-    rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, max_tiles, d_walk_vtx, d_walk_off, n_steps_eff, o);
+    rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, max_tiles, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, o);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[EV_WALKS], ctx->st));
 

@@ -57,15 +57,59 @@ __device__ __forceinline__ void table_insert(uint64_t *table, uint64_t mask, uin
     ctr[CTR_OVERFLOW] = 1;
 }
 
-__global__ void __launch_bounds__(NT, 3)
+// unaligned 8-byte load (two aligned loads + funnel); the buffers are padded so that p-7 .. p+15 is always readable
+__device__ __forceinline__ uint64_t load8_unaligned(const uint8_t *p)
+{
+    const unsigned long long a = (unsigned long long)p;
+    const uint64_t *w = (const uint64_t *)(a & ~7ull);
+    const int s = (int)(a & 7) * 8;
+    uint64_t w0 = w[0];
+    if (!s) return w0;
+    return (w0 >> s) | (w[1] << (64 - s));
+}
+
+template <bool CLEAN>
+__device__ __forceinline__ void read_tile_body(Tile &t, const ReadSketchArgs &A)
+{
+    const int tid = threadIdx.x;
+    phase_canon<CLEAN>(t);
+    __syncthreads();
+    phase_block_minima<CLEAN>(t);
+    __syncthreads();
+    uint16_t *runs = t.pre;                                          // safe: phase_runs syncs before writing runs[]
+    int halo = -1;
+    const int n_runs = phase_runs<true, CLEAN>(t, runs, &halo);
+    if (n_runs == 0) return;
+
+    if (tid == 0) t.hash[0] = halo >= 0 ? hash_at<CLEAN>(t, halo) : 0xFFFFFFFFFFFFFFFFull;
+    int emitted = 0;
+    for (int b0 = 0; b0 < n_runs; b0 += NT) {
+        const int j = b0 + tid; const bool have = j < n_runs;
+        const int cnt = min(NT, n_runs - b0);
+        uint32_t ent = have ? runs[j] : 0;
+        uint64_t h = have ? hash_at<CLEAN>(t, ent & 0x7FFF) : 0;
+        t.hash[tid + 1] = h;
+        __syncthreads();
+        uint64_t prev = (ent & 0x8000) ? 0xFFFFFFFFFFFFFFFFull : t.hash[tid];
+        uint64_t carry = t.hash[cnt];
+        bool emit = have && h != prev;
+        if (emit) table_insert(A.table, A.table_mask, h, A.ctr);
+        emitted += __syncthreads_count(emit);
+        if (tid == 0) t.hash[0] = carry;
+    }
+    if (tid == 0 && emitted) atomicAdd(&A.ctr[CTR_READ_EMITTED], (unsigned long long)emitted);
+}
+
+__global__ void __launch_bounds__(NT, 4)
 read_sketch_kernel(ReadSketchArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const TileLayout L = make_layout(A.k, A.w, false);
+    const TileLayout &L = A.layout;
     Tile t = carve(smem, L, A.k, A.w);
     const long long tile = blockIdx.x;
     t.g0 = tile * TILE_W - A.w;
     t.seq_len = (long long)A.total_bases;
+    set_window_bounds(t);
     const int tid = threadIdx.x;
 
     // ---- read boundaries -> bit mask (bit p set iff a read starts at g0 + p)
@@ -86,60 +130,23 @@ read_sketch_kernel(ReadSketchArgs A)
             r0 += NT;
         }
     }
-    // ---- stage bases: aligned 8-byte loads, funnel to the chunk, mask outside [0, total)
-    {
-        const int nchunks = (L.NB + 7) / 8;
-        const uint64_t *words = (const uint64_t *)A.read_bases;      // 8-aligned, padded with >= 16 zero bytes
-        for (int c = tid; c < nchunks; c += NT) {
-            long long g = t.g0 + 8ll * c;
-            uint64_t v = 0;
-            if (g + 8 > 0 && g < t.seq_len) {
-                long long ga = g < 0 ? 0 : g;                        // first real byte
-                long long wi = ga >> 3; int m = (int)(ga & 7);
-                uint64_t w0 = words[wi], w1 = m ? words[wi + 1] : 0;
-                v = m ? (w0 >> (8 * m)) | (w1 << (64 - 8 * m)) : w0; // bytes ga .. ga+7
-                int lead = (int)(ga - g);                            // bytes before the sequence start
-                if (lead) v <<= 8 * lead;
-                long long nvalid = t.seq_len - g;                    // bytes [0, nvalid) of the chunk are real
-                if (nvalid < 8) v &= (1ull << (8 * nvalid)) - 1;
-            }
-            uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32), lo2 = 0, hi2 = 0;
-            #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                lo2 |= upcase((lo >> (8 * i)) & 0xFF) << (8 * i);
-                hi2 |= upcase((hi >> (8 * i)) & 0xFF) << (8 * i);
-            }
-            stage_chunk(t, c, lo2, hi2);
+    // ---- stage bases: unaligned 8-byte loads, mask outside [0, total)
+    uint32_t dirty_any = 0;
+    for (int c = tid; c < L.nchunks; c += NT) {
+        long long g = t.g0 + 8ll * c;
+        uint64_t v = 0;
+        if (g + 8 > 0 && g < t.seq_len) {
+            v = load8_unaligned(A.read_bases + g);                   // front padding covers g in [-7, -1]
+            if (g < 0) v &= ~0ull << (8 * (int)(-g));
+            long long nvalid = t.seq_len - g;                        // bytes [0, nvalid) of the chunk are real
+            if (nvalid < 8) v &= (1ull << (8 * nvalid)) - 1;
+            v = upcase8(v);
         }
+        dirty_any |= stage_chunk(t, c, v);
     }
-    __syncthreads();
-    phase_canon(t);
-    __syncthreads();
-    phase_block_minima(t);
-    __syncthreads();
-    phase_window_argmin(t);
-    __syncthreads();
-    uint16_t *runs = t.pre;                                          // pre+suf are contiguous and dead: >= TILE_W+1 entries
-    const int n_runs = phase_runs<true>(t, runs);
-    if (n_runs == 0) return;
-
-    if (tid == 0) t.hash[0] = halo_prev_hash<true>(t);
-    int emitted = 0;
-    for (int b0 = 0; b0 < n_runs; b0 += NT) {
-        const int j = b0 + tid; const bool have = j < n_runs;
-        const int cnt = min(NT, n_runs - b0);
-        uint32_t ent = have ? runs[j] : 0;
-        uint64_t h = have ? hash_at(t, ent & 0x7FFF) : 0;
-        t.hash[tid + 1] = h;
-        __syncthreads();
-        uint64_t prev = (ent & 0x8000) ? 0xFFFFFFFFFFFFFFFFull : t.hash[tid];
-        uint64_t carry = t.hash[cnt];
-        bool emit = have && h != prev;
-        if (emit) table_insert(A.table, A.table_mask, h, A.ctr);
-        emitted += __syncthreads_count(emit);
-        if (tid == 0) t.hash[0] = carry;
-    }
-    if (tid == 0 && emitted) atomicAdd(&A.ctr[CTR_READ_EMITTED], (unsigned long long)emitted);
+    // a tile is CLEAN when every staged byte that a valid window can touch is A/C/G/T; padding at either end of
+    // the data counts as dirty and sends the (few) boundary tiles through the general path
+    if (__syncthreads_or(dirty_any != 0)) read_tile_body<false>(t, A); else read_tile_body<true>(t, A);
 }
 
 // per tile: first read r with read_off[r] >= tile*TILE_W - w
@@ -190,7 +197,86 @@ __device__ __noinline__ int anchor_slow(const Tile &t, int j0, int n_raw, const 
     return nu;
 }
 
-__global__ void __launch_bounds__(NT, 3)
+// step index of local base position p (chunk directory filled while gathering)
+__device__ __forceinline__ int step_of(const Tile &t, int p)
+{
+    const int c = p >> 3;
+    return t.cfirst[c] + __popc((uint32_t)t.cmask[c] & ((2u << (p & 7)) - 1u));
+}
+
+template <bool CLEAN>
+__device__ __forceinline__ void walk_tile_body(Tile &t, const WalkSketchArgs &A, uint32_t h)
+{
+    const int tid = threadIdx.x;
+    phase_canon<CLEAN>(t);
+    __syncthreads();
+    phase_block_minima<CLEAN>(t);
+    __syncthreads();
+    uint16_t *runs = t.pre;
+    int halo = -1;
+    const int n_runs = phase_runs<false, CLEAN>(t, runs, &halo);
+    if (n_runs == 0) return;
+
+    if (tid == 0) t.hash[0] = halo >= 0 ? hash_at<CLEAN>(t, halo) : 0xFFFFFFFFFFFFFFFFull;
+    int emitted = 0;
+    for (int b0 = 0; b0 < n_runs; b0 += NT) {
+        const int jr = b0 + tid; const bool have = jr < n_runs;
+        const int cnt = min(NT, n_runs - b0);
+        uint32_t ent = have ? runs[jr] : 0;
+        const int a = ent & 0x7FFF;
+        uint64_t hv = have ? hash_at<CLEAN>(t, a) : 0;
+        t.hash[tid + 1] = hv;
+        __syncthreads();
+        uint64_t prev = (ent & 0x8000) ? 0xFFFFFFFFFFFFFFFFull : t.hash[tid];
+        uint64_t carry = t.hash[cnt];
+        bool emit = have && hv != prev;
+        emitted += __syncthreads_count(emit);
+        if (tid == 0) t.hash[0] = carry;
+
+        // ---- probe + anchor
+        int64_t rank = -1;
+        if (emit) rank = A.mode == WALK_MODE_ALL ? 0 : spectrum_probe(A.spec, A.dir, A.dbits, hv);
+        const bool hit = rank >= 0;
+        int j0 = 0, nv = 0, n_raw = 0; bool slow = false;
+        if (hit) {
+            j0 = step_of(t, a);
+            n_raw = nv = step_of(t, a + A.k - 1) - j0 + 1;           // steps under bases [a, a+k)
+            if (!A.walks_monotone) {                                 // walk order == topological order for a valid walk; verify otherwise
+                int32_t prev_top = -0x7FFFFFFF - 1;
+                for (int i = 0; i < nv; ++i) {
+                    int32_t tp = A.top_order_map[t.stepv[j0 + i]];
+                    if (i && tp <= prev_top) slow = true;
+                    prev_top = tp;
+                }
+                if (slow) nv = anchor_slow(t, j0, n_raw, A.top_order_map, nullptr);
+            }
+        }
+        Scan2 sc = block_scan2(t.scan, hit ? 1 : 0, nv);
+        __shared__ unsigned long long s_base_hit, s_base_vtx;
+        if (tid == 0 && sc.tot_a) {
+            s_base_hit = atomicAdd(&A.ctr[CTR_HITS], (unsigned long long)sc.tot_a);
+            s_base_vtx = atomicAdd(&A.ctr[CTR_HIT_VTX], (unsigned long long)sc.tot_b);
+        }
+        __syncthreads();
+        if (hit) {
+            unsigned long long hi_idx = s_base_hit + sc.ex_a, vo = s_base_vtx + sc.ex_b;
+            if (hi_idx < A.hit_cap && vo + nv <= A.vtx_cap) {
+                A.hit_rank[hi_idx] = (uint32_t)rank;
+                A.hit_walk[hi_idx] = A.walk_id_base + h;
+                A.hit_pos[hi_idx] = (uint32_t)(t.g0 + a);
+                A.hit_voff[hi_idx] = vo;
+                A.hit_nv[hi_idx] = (uint8_t)nv;
+                if (A.hit_hash) A.hit_hash[hi_idx] = hv;
+                if (!slow) for (int i = 0; i < nv; ++i) A.vtx_pool[vo + i] = (int32_t)t.stepv[j0 + i];
+                else anchor_slow(t, j0, n_raw, A.top_order_map, A.vtx_pool + vo);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && emitted) atomicAdd(&A.minimizers_per_walk[h], (unsigned long long)emitted);
+}
+
+__global__ void __launch_bounds__(NT, 4)
 walk_sketch_kernel(WalkSketchArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -199,10 +285,11 @@ walk_sketch_kernel(WalkSketchArgs A)
     const long long tile = blockIdx.x;
     if (len < (long long)A.w + A.k - 1) return;
     if (tile * TILE_W > len - A.k) return;                           // no window ends in this tile
-    const TileLayout L = make_layout(A.k, A.w, true);
+    const TileLayout &L = A.layout;
     Tile t = carve(smem, L, A.k, A.w);
     t.g0 = tile * TILE_W - A.w;
     t.seq_len = len;
+    set_window_bounds(t);
     const int tid = threadIdx.x;
 
     // ---- steps overlapping the tile's bases [base_lo, base_hi)
@@ -230,114 +317,38 @@ walk_sketch_kernel(WalkSketchArgs A)
     const long long first_true = A.step_base[s0];                    // true start of step 0 (may precede base_lo)
     __syncthreads();
 
-    // ---- gather bases through the step table, 8 per thread
-    {
-        const int nchunks = (L.NB + 7) / 8;
-        for (int c = tid; c < nchunks; c += NT) {
-            const long long g = t.g0 + 8ll * c;
-            uint32_t lo4 = 0, hi4 = 0;
-            if (g + 8 > base_lo && g < base_hi) {
-                long long gq = g < base_lo ? base_lo : g;
-                int q = (int)(gq - base_lo);
-                int a = 0, b = n_steps;                              // last j with steps[j] <= q
-                while (b - a > 1) { int m = (a + b) >> 1; if (t.steps[m] <= q) a = m; else b = m; }
-                int j = a;
-                long long jstart = j == 0 ? first_true : base_lo + t.steps[j];
-                const uint8_t *src = A.seg_bases + A.seg_off[t.stepv[j]] - jstart;   // src[g] is the base at walk coordinate g
-                int nxt = t.steps[j + 1];
-                #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    long long gi = g + i;
-                    uint32_t ch = 0;
-                    if (gi >= base_lo && gi < base_hi) {
-                        int qi = (int)(gi - base_lo);
-                        while (qi >= nxt) {
-                            ++j; nxt = t.steps[j + 1];
-                            src = A.seg_bases + A.seg_off[t.stepv[j]] - (base_lo + t.steps[j]);
-                        }
-                        ch = upcase(src[gi]);
-                    }
-                    if (i < 4) lo4 |= ch << (8 * i); else hi4 |= ch << (8 * (i - 4));
-                }
+    // ---- gather bases through the step table: per 8-base chunk, one unaligned 8-byte load per overlapping step
+    uint32_t dirty_any = 0;
+    const int rel0 = (int)(base_lo - t.g0);                          // local index of base_lo (0, or w for tile 0)
+    const int nb = (int)(base_hi - base_lo);                         // real bases staged
+    for (int c = tid; c < L.nchunks; c += NT) {
+        const int q0 = 8 * c - rel0;                                 // chunk start relative to base_lo (may be < 0)
+        uint64_t v = 0; int first = 0; uint32_t smask = 0;
+        if (q0 + 8 > 0 && q0 < nb) {
+            int cur = q0 < 0 ? 0 : q0;
+            const int qend = min(q0 + 8, nb);
+            int a = 0, b = n_steps;                                  // last j with steps[j] <= cur
+            while (b - a > 1) { int m = (a + b) >> 1; if (t.steps[m] <= cur) a = m; else b = m; }
+            int j = first = a;
+            while (cur < qend) {
+                const int jend = t.steps[j + 1];
+                const int hi = min(jend, qend);
+                const long long jstart = j == 0 ? first_true - base_lo : (long long)t.steps[j];   // relative to base_lo, may be < 0 for j == 0
+                const uint8_t *src = A.seg_bases + A.seg_off[t.stepv[j]] + ((long long)q0 - jstart);  // chunk byte 0 in this segment's coordinates
+                uint64_t x = load8_unaligned(src);
+                const int lo_b = cur - q0, hi_b = hi - q0;           // bytes [lo_b, hi_b) of the chunk come from step j
+                uint64_t m = (hi_b == 8 ? ~0ull : ((1ull << (8 * hi_b)) - 1)) & (~0ull << (8 * lo_b));
+                v |= x & m;
+                if (j != first) smask |= 1u << lo_b;
+                cur = hi;
+                if (cur == jend) ++j;
             }
-            stage_chunk(t, c, lo4, hi4);
+            v = upcase8(v);
         }
+        t.cfirst[c] = (uint16_t)first; t.cmask[c] = (uint8_t)smask;
+        dirty_any |= stage_chunk(t, c, v);
     }
-    __syncthreads();
-    phase_canon(t);
-    __syncthreads();
-    phase_block_minima(t);
-    __syncthreads();
-    phase_window_argmin(t);
-    __syncthreads();
-    uint16_t *runs = t.pre;
-    const int n_runs = phase_runs<false>(t, runs);
-    if (n_runs == 0) return;
-
-    if (tid == 0) t.hash[0] = halo_prev_hash<false>(t);
-    int emitted = 0;
-    for (int b0 = 0; b0 < n_runs; b0 += NT) {
-        const int jr = b0 + tid; const bool have = jr < n_runs;
-        const int cnt = min(NT, n_runs - b0);
-        uint32_t ent = have ? runs[jr] : 0;
-        const int a = ent & 0x7FFF;
-        uint64_t hv = have ? hash_at(t, a) : 0;
-        t.hash[tid + 1] = hv;
-        __syncthreads();
-        uint64_t prev = (ent & 0x8000) ? 0xFFFFFFFFFFFFFFFFull : t.hash[tid];
-        uint64_t carry = t.hash[cnt];
-        bool emit = have && hv != prev;
-        emitted += __syncthreads_count(emit);
-        if (tid == 0) t.hash[0] = carry;
-
-        // ---- probe + anchor
-        int64_t rank = -1;
-        if (emit) rank = A.mode == WALK_MODE_ALL ? 0 : spectrum_probe(A.spec, A.dir, A.dbits, hv);
-        const bool hit = rank >= 0;
-        int j0 = 0, nv = 0; bool slow = false;
-        if (hit) {
-            int q = (int)(t.g0 + a - base_lo);                       // k-mer start relative to base_lo
-            int lo = 0, hi = n_steps;
-            while (hi - lo > 1) { int m = (lo + hi) >> 1; if (t.steps[m] <= q) lo = m; else hi = m; }
-            j0 = lo;
-            int j1 = j0;
-            while (t.steps[j1 + 1] < q + A.k) ++j1;                  // last step starting before the k-mer's end
-            nv = j1 - j0 + 1;
-            int32_t prev_top = -0x7FFFFFFF - 1;
-            for (int i = 0; i < nv; ++i) {                           // walk order == topological order for a valid walk
-                int32_t tp = A.top_order_map[t.stepv[j0 + i]];
-                if (i && tp <= prev_top) slow = true;
-                prev_top = tp;
-            }
-            if (slow) nv = anchor_slow(t, j0, nv, A.top_order_map, nullptr);
-        }
-        Scan2 sc = block_scan2(t.scan, hit ? 1 : 0, nv);
-        __shared__ unsigned long long s_base_hit, s_base_vtx;
-        if (tid == 0 && sc.tot_a) {
-            s_base_hit = atomicAdd(&A.ctr[CTR_HITS], (unsigned long long)sc.tot_a);
-            s_base_vtx = atomicAdd(&A.ctr[CTR_HIT_VTX], (unsigned long long)sc.tot_b);
-        }
-        __syncthreads();
-        if (hit) {
-            unsigned long long hi_idx = s_base_hit + sc.ex_a, vo = s_base_vtx + sc.ex_b;
-            if (hi_idx < A.hit_cap && vo + nv <= A.vtx_cap) {
-                A.hit_rank[hi_idx] = (uint32_t)rank;
-                A.hit_walk[hi_idx] = A.walk_id_base + h;
-                A.hit_pos[hi_idx] = (uint32_t)(t.g0 + a);
-                A.hit_voff[hi_idx] = vo;
-                A.hit_nv[hi_idx] = (uint8_t)nv;
-                if (A.hit_hash) A.hit_hash[hi_idx] = hv;
-                if (!slow) for (int i = 0; i < nv; ++i) A.vtx_pool[vo + i] = (int32_t)t.stepv[j0 + i];
-                else {
-                    int j1 = j0; int q = (int)(t.g0 + a - base_lo);
-                    while (t.steps[j1 + 1] < q + A.k) ++j1;
-                    anchor_slow(t, j0, j1 - j0 + 1, A.top_order_map, A.vtx_pool + vo);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (tid == 0 && emitted) atomicAdd(&A.minimizers_per_walk[h], (unsigned long long)emitted);
+    if (__syncthreads_or(dirty_any != 0)) walk_tile_body<false>(t, A, h); else walk_tile_body<true>(t, A, h);
 }
 
 // ================================================================== graph preparation
@@ -393,6 +404,17 @@ __global__ void walk_len_kernel(const uint64_t *gbase, const uint32_t *step_len,
     walk_len[h] = gb - ga;
 }
 
+// flags CTR_NONMONO if some walk visits vertices out of topological order (then anchors are verified per hit)
+__global__ void walk_monotone_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
+                                     const int32_t *top_order_map, unsigned long long *ctr)
+{
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s + 1 >= n_steps) return;
+    uint32_t h = walk_of_step(walk_off, n_walks, s);
+    if (s + 1 >= walk_off[h + 1]) return;                             // last step of its walk
+    if (top_order_map[walk_vtx[s]] >= top_order_map[walk_vtx[s + 1]]) ctr[CTR_NONMONO] = 1;
+}
+
 // ================================================================== hash KAT hook
 __global__ void hash_bytes_kernel(const uint8_t *keys, uint64_t n, int len, uint64_t *out)
 {
@@ -413,7 +435,6 @@ __global__ void hash_bytes_kernel(const uint8_t *keys, uint64_t n, int len, uint
 }
 
 // ------------------------------------------------------------------ launchers
-static size_t tile_smem_bytes(int k, int w, bool walk) { return (size_t)make_layout(k, w, walk).bytes; }
 
 cudaError_t launch_read_tile_dir(const uint64_t *read_off, uint64_t n_reads, int w, uint64_t n_tiles, uint64_t *out, cudaStream_t st)
 {
@@ -425,7 +446,7 @@ cudaError_t launch_read_tile_dir(const uint64_t *read_off, uint64_t n_reads, int
 cudaError_t launch_read_sketch(const ReadSketchArgs &A, uint64_t n_tiles, cudaStream_t st)
 {
     if (!n_tiles) return cudaSuccess;
-    size_t smem = tile_smem_bytes(A.k, A.w, false);
+    size_t smem = (size_t)A.layout.bytes;
     cudaError_t e = cudaFuncSetAttribute(read_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     read_sketch_kernel<<<(unsigned)n_tiles, NT, smem, st>>>(A);
@@ -435,7 +456,7 @@ cudaError_t launch_read_sketch(const ReadSketchArgs &A, uint64_t n_tiles, cudaSt
 cudaError_t launch_walk_sketch(const WalkSketchArgs &A, uint32_t n_walks, uint64_t max_tiles, cudaStream_t st)
 {
     if (!n_walks || !max_tiles) return cudaSuccess;
-    size_t smem = tile_smem_bytes(A.k, A.w, true);
+    size_t smem = (size_t)A.layout.bytes;
     cudaError_t e = cudaFuncSetAttribute(walk_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)max_tiles, n_walks);
@@ -468,6 +489,14 @@ cudaError_t launch_step_finalize(const uint64_t *gbase, const uint32_t *step_len
     return cudaGetLastError();
 }
 
+cudaError_t launch_walk_monotone(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
+                                 const int32_t *top_order_map, unsigned long long *ctr, cudaStream_t st)
+{
+    if (n_steps < 2) return cudaSuccess;
+    walk_monotone_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, top_order_map, ctr);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_hash_bytes(const uint8_t *keys, uint64_t n, int len, uint64_t *out, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
@@ -476,5 +505,6 @@ cudaError_t launch_hash_bytes(const uint8_t *keys, uint64_t n, int len, uint64_t
 }
 
 int tile_windows() { return TILE_W; }
+TileLayout tile_layout(int k, int w, bool walk) { return make_layout(k, w, walk); }
 
 }  // namespace phi

@@ -1,4 +1,4 @@
-// Minimizer tile core shared by the read-sketch and walk-sketch kernels (sm_100a).
+// Minimizer tile core shared by the read-sketch and walk-sketch kernels (sm_100a) — v2.
 //
 // A tile owns TILE_W consecutive window end positions e (global k-mer start index of the
 // LAST k-mer of the window) of one sequence coordinate system:
@@ -16,8 +16,14 @@
 //     compares against UINT64_MAX (:383, :413).  prev_hash always equals the hash of the
 //     previous window's minimum, so "runs" of equal arg-min position are the unit of work.
 //   * non-ACGT bytes take part verbatim ("dirty" k-mers: byte-wise compare + byte-wise hash).
+//
+// v2 (instruction diet, see profiles/r1_walk_kernel_phases_v1.txt): the layout comes from the
+// host; tiles without any non-ACGT byte run a CLEAN specialisation with no flag traffic; canonical
+// k-mers are rolled 8 per thread and stored with 4 STS.128 into a padded, conflict-free array;
+// window arg-min and run detection are fused (warp shuffles instead of an arg[] array).
 #pragma once
 #include "device_common.cuh"
+#include "kernels.h"
 
 namespace phi {
 
@@ -29,80 +35,98 @@ constexpr int MAX_K = 32;
 constexpr uint8_t F_STRAND = 1;  // canonical == reverse complement
 constexpr uint8_t F_DIRTY = 2;   // k-mer contains a non-ACGT byte (or padding)
 
-// Dynamic shared memory carve-up.  All offsets in bytes from the (16-aligned) base.
-struct TileLayout {
-    int M, NB;
-    int o_canon, o_pack, o_dirty, o_bnd, o_pre, o_suf, o_arg, o_flag, o_base, o_hash, o_scan, o_stepv, o_steps;
-    int bytes;
-};
+// Dynamic shared memory carve-up: struct TileLayout lives in kernels.h (computed once on the host, passed by value).
+inline int align_up_h(int x, int a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
-
-__host__ __device__ inline TileLayout make_layout(int k, int w, bool walk)
+inline TileLayout make_layout(int k, int w, bool walk)
 {
     TileLayout L;
     L.M = TILE_W + w;
+    L.M8 = align_up_h(L.M, 8);
     L.NB = L.M + k - 1;
-    const int nb8 = align_up(L.NB, 8) + 8;               // bases, padded so chunked stores stay in bounds
+    L.nchunks = (L.NB + 7) / 8;
+    const int nb8 = 8 * L.nchunks + 8;                   // bases, padded so chunked stores stay in bounds
     int o = 0;
-    auto take = [&o](int bytes) { int at = o; o += align_up(bytes, 16); return at; };   // every section 16-byte aligned
-    L.o_canon = take(8 * L.M);
+    auto take = [&o](int bytes) { int at = o; o += align_up_h(bytes, 16); return at; };   // every section 16-byte aligned
+    L.o_canon = take(8 * (L.M8 + 2 * (L.M8 / 8)));       // padded: idx(p) = p + 2*(p>>3)
     L.o_hash = take(8 * (NT + 1));
     L.o_pack = take(4 * (nb8 / 16 + 4));
     L.o_dirty = take(4 * (nb8 / 32 + 4));
     L.o_bnd = take(4 * (nb8 / 32 + 4));
     L.o_scan = take(4 * 64);
-    L.o_pre = take(2 * align_up(L.M, 2));            // pre and suf stay adjacent: runs[] aliases both
-    L.o_suf = take(2 * align_up(L.M, 2));
-    L.o_arg = take(2 * align_up(L.M, 2));
+    L.o_pre = take(2 * (L.M8 + 8));                      // runs[] aliases pre (TILE_W + 1 entries <= M)
+    L.o_suf = take(2 * (L.M8 + 8));
+    L.o_flag = take(L.M8 + 8);
+    L.o_base = take(nb8);
     L.o_stepv = take(walk ? 4 * (L.NB + 2) : 0);
     L.o_steps = take(walk ? 2 * (L.NB + 2) : 0);
-    L.o_flag = take(L.M);
-    L.o_base = take(nb8);
-    L.bytes = align_up(o, 16);
+    L.o_cfirst = take(walk ? 2 * (L.nchunks + 2) : 0);
+    L.o_cmask = take(walk ? (L.nchunks + 2) : 0);
+    L.bytes = align_up_h(o, 16);
     return L;
 }
 
 struct Tile {
     // geometry
-    int k, w, M, NB;
+    int k, w, M, M8, NB;
     long long g0;            // global coordinate of local 0
     long long seq_len;       // WALK: walk length in bases; MULTI: total bases of all reads
+    int e_lo, e_hi;          // WALK: local window ends e with a valid window are [e_lo, e_hi); e_first: the sequence's first window
+    int e_first;
     // shared arrays
     uint64_t *canon; uint64_t *hash;
     uint32_t *pack, *dirty, *bnd, *scan;
-    uint16_t *pre, *suf, *arg, *steps;
+    uint16_t *pre, *suf, *steps, *cfirst;
     uint32_t *stepv;
-    uint8_t *flag, *base;
+    uint8_t *flag, *base, *cmask;
 };
 
 __device__ __forceinline__ Tile carve(unsigned char *smem, const TileLayout &L, int k, int w)
 {
     Tile t;
-    t.k = k; t.w = w; t.M = L.M; t.NB = L.NB;
+    t.k = k; t.w = w; t.M = L.M; t.M8 = L.M8; t.NB = L.NB;
     t.canon = (uint64_t *)(smem + L.o_canon); t.hash = (uint64_t *)(smem + L.o_hash);
     t.pack = (uint32_t *)(smem + L.o_pack); t.dirty = (uint32_t *)(smem + L.o_dirty);
     t.bnd = (uint32_t *)(smem + L.o_bnd); t.scan = (uint32_t *)(smem + L.o_scan);
-    t.pre = (uint16_t *)(smem + L.o_pre); t.suf = (uint16_t *)(smem + L.o_suf); t.arg = (uint16_t *)(smem + L.o_arg);
+    t.pre = (uint16_t *)(smem + L.o_pre); t.suf = (uint16_t *)(smem + L.o_suf);
     t.stepv = (uint32_t *)(smem + L.o_stepv); t.steps = (uint16_t *)(smem + L.o_steps);
+    t.cfirst = (uint16_t *)(smem + L.o_cfirst); t.cmask = smem + L.o_cmask;
     t.flag = smem + L.o_flag; t.base = smem + L.o_base;
     return t;
 }
 
-// ---- staging helper: 8 upper-cased bytes (as two u32, byte i of the chunk in byte i) for chunk c
-// (local bases 8c..8c+7) -> base[], 2-bit pack[], dirty mask.  Padding bytes must be passed as 0.
-__device__ __forceinline__ void stage_chunk(const Tile &t, int c, uint32_t lo4, uint32_t hi4)
+// padded canon index: 10 slots per 8 positions -> 80-byte thread stride, conflict-free STS.128 / LDS.64
+__device__ __forceinline__ int cidx(int p) { return p + 2 * (p >> 3); }
+
+// upper-case 8 packed bytes (SWAR; bytes >= 0x80 untouched, like ::toupper in the C locale)
+__device__ __forceinline__ uint64_t upcase8(uint64_t x)
 {
-    uint32_t bits = 0, dm = 0;
+    const uint64_t lo7 = 0x7F7F7F7F7F7F7F7Full;
+    uint64_t t = x & lo7;
+    uint64_t ge_a = t + 0x1F1F1F1F1F1F1F1Full;          // bit7 set iff byte >= 'a' (0x61)
+    uint64_t gt_z = t + 0x0505050505050505ull;          // bit7 set iff byte >  'z' (0x7A)
+    uint64_t lower = ge_a & ~gt_z & ~x & 0x8080808080808080ull;
+    return x ^ (lower >> 2);                            // clear 0x20
+}
+
+// ---- staging helper: 8 upper-cased bytes for chunk c (local bases 8c..8c+7, byte i of v = base i)
+// -> base[], 2-bit pack[], dirty mask.  Padding bytes must be passed as 0.  Returns the chunk's dirty mask.
+__device__ __forceinline__ uint32_t stage_chunk(const Tile &t, int c, uint64_t v)
+{
+    const uint32_t lo4 = (uint32_t)v, hi4 = (uint32_t)(v >> 32);
+    // codes: ((c>>1)^(c>>2))&3 per byte, then gather 4 codes into one byte with a multiply (no carries: 2-bit fields)
+    uint32_t cl = ((lo4 >> 1) ^ (lo4 >> 2)) & 0x03030303u, ch = ((hi4 >> 1) ^ (hi4 >> 2)) & 0x03030303u;
+    uint32_t bits = (((cl * 0x40100401u) >> 24) << 8) | ((ch * 0x40100401u) >> 24);
+    uint32_t dm = 0;
     #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        uint32_t ch = ((i < 4 ? lo4 : hi4) >> (8 * (i & 3))) & 0xFFu;
-        bits = (bits << 2) | code2(ch);
-        dm |= (is_acgt(ch) ? 0u : 1u) << i;
+        uint32_t b = ((i < 4 ? lo4 : hi4) >> (8 * (i & 3))) & 0xFFu;
+        dm |= (is_acgt(b) ? 0u : 1u) << i;
     }
     ((uint2 *)t.base)[c] = make_uint2(lo4, hi4);
     ((uint16_t *)t.pack)[c ^ 1] = (uint16_t)bits;       // big-endian base order inside each u32
     ((uint8_t *)t.dirty)[c] = (uint8_t)dm;
+    return dm;
 }
 
 // 2k bits of the packed stream starting at base p, right-aligned
@@ -112,6 +136,12 @@ __device__ __forceinline__ uint64_t extract_kmer(const uint32_t *pack, int p, in
     uint32_t w0 = pack[i], w1 = pack[i + 1], w2 = pack[i + 2];
     uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
     return (((uint64_t)hi << 32) | lo) >> (64 - 2 * k);
+}
+// the 8 bases p..p+7 as 16 bits (base p on top)
+__device__ __forceinline__ uint32_t extract8(const uint32_t *pack, int p)
+{
+    int i = p >> 4, sh = (p & 15) * 2;
+    return __funnelshift_l(pack[i + 1], pack[i], sh) >> 16;
 }
 
 // any bit set in mask[lo .. hi] (bit positions, inclusive)?
@@ -138,14 +168,16 @@ __device__ __noinline__ int cmp_canon_bytes(const Tile &t, int a, int sa, int b,
 }
 
 // canon[a] <= canon[b] ?   (va/vb, fa/fb: canon value and flag of a and b)
+template <bool CLEAN>
 __device__ __forceinline__ bool canon_le(const Tile &t, int a, uint64_t va, uint32_t fa, int b, uint64_t vb, uint32_t fb)
 {
-    if (((fa | fb) & F_DIRTY) == 0) return va <= vb;
+    if (CLEAN || ((fa | fb) & F_DIRTY) == 0) return va <= vb;
     return cmp_canon_bytes(t, a, fa & F_STRAND, b, fb & F_STRAND) <= 0;
 }
+template <bool CLEAN>
 __device__ __forceinline__ bool canon_lt(const Tile &t, int a, uint64_t va, uint32_t fa, int b, uint64_t vb, uint32_t fb)
 {
-    if (((fa | fb) & F_DIRTY) == 0) return va < vb;
+    if (CLEAN || ((fa | fb) & F_DIRTY) == 0) return va < vb;
     return cmp_canon_bytes(t, a, fa & F_STRAND, b, fb & F_STRAND) < 0;
 }
 
@@ -159,71 +191,99 @@ __device__ __noinline__ uint64_t hash_dirty(const Tile &t, int a, int strand)
     }
     return murmur3_x64_128_xor(W, t.k);
 }
+template <bool CLEAN>
 __device__ __forceinline__ uint64_t hash_at(const Tile &t, int a)
 {
-    uint32_t f = t.flag[a];
-    if (f & F_DIRTY) return hash_dirty(t, a, f & F_STRAND);
-    return hash_packed_kmer(t.canon[a], t.k);
+    if (!CLEAN) {
+        uint32_t f = t.flag[a];
+        if (f & F_DIRTY) return hash_dirty(t, a, f & F_STRAND);
+    }
+    return hash_packed_kmer(t.canon[cidx(a)], t.k);
 }
 
-// ---- phase 3: canonical k-mers for p in [0, M)
+// ---- phase: canonical k-mers for p in [0, M8), 8 consecutive positions per thread, rolled
+template <bool CLEAN>
 __device__ __forceinline__ void phase_canon(const Tile &t)
 {
-    for (int p = threadIdx.x; p < t.M; p += NT) {
-        uint64_t fwd = extract_kmer(t.pack, p, t.k);
-        uint32_t d = __funnelshift_r(t.dirty[p >> 5], t.dirty[(p >> 5) + 1], p & 31);
-        if (t.k < 32) d &= (1u << t.k) - 1;
-        uint64_t cv; uint32_t f;
-        if (d == 0) {
-            uint64_t rc = revcomp2(fwd, t.k);
-            f = rc < fwd ? F_STRAND : 0;
-            cv = rc < fwd ? rc : fwd;
-        } else {
-            // std::min(fwd, rev): rev only if strictly smaller (:394)
-            int c = cmp_canon_bytes(t, p, 1, p, 0);
-            f = F_DIRTY | (c < 0 ? F_STRAND : 0);
-            cv = 0;
+    const int k = t.k;
+    const uint64_t kmask = k == 32 ? ~0ull : (1ull << (2 * k)) - 1;
+    const int top = 2 * (k - 1);
+    for (int g8 = threadIdx.x; g8 < t.M8 / 8; g8 += NT) {
+        const int p0 = 8 * g8;
+        uint64_t fwd = extract_kmer(t.pack, p0, k);
+        uint64_t rc = revcomp2(fwd, k);
+        const uint32_t nxt = extract8(t.pack, p0 + k);                 // bases entering at steps 1..7 (+1 spare)
+        uint64_t cv[8];
+        cv[0] = rc < fwd ? rc : fwd;
+        uint32_t strand = rc < fwd ? 1u : 0u;
+        #pragma unroll
+        for (int i = 1; i < 8; ++i) {
+            uint64_t code = (nxt >> (16 - 2 * i)) & 3u;
+            fwd = ((fwd << 2) | code) & kmask;
+            rc = (rc >> 2) | ((3ull - code) << top);
+            cv[i] = rc < fwd ? rc : fwd;
+            strand |= (rc < fwd ? 1u : 0u) << i;
         }
-        t.canon[p] = cv; t.flag[p] = (uint8_t)f;
+        if (!CLEAN) {
+            // non-ACGT bytes: k-mer i is dirty iff any of dirty bits [p0+i, p0+i+k) is set
+            const int wi = p0 >> 5, sh = p0 & 31;
+            uint64_t d64 = ((uint64_t)__funnelshift_r(t.dirty[wi + 1], t.dirty[wi + 2], sh) << 32) | __funnelshift_r(t.dirty[wi], t.dirty[wi + 1], sh);
+            const uint64_t km = k == 32 ? 0xFFFFFFFFull : (1ull << k) - 1;
+            uint64_t fl = 0;
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t f = (strand >> i) & 1u;
+                if ((d64 >> i) & km) {
+                    int c = cmp_canon_bytes(t, p0 + i, 1, p0 + i, 0);  // std::min(fwd, rev): rev only if strictly smaller (:394)
+                    f = F_DIRTY | (c < 0 ? F_STRAND : 0);
+                    cv[i] = 0;
+                }
+                fl |= (uint64_t)f << (8 * i);
+            }
+            *(uint64_t *)(t.flag + p0) = fl;
+        }
+        ulonglong2 *dst = (ulonglong2 *)(t.canon + cidx(p0));
+        dst[0] = make_ulonglong2(cv[0], cv[1]); dst[1] = make_ulonglong2(cv[2], cv[3]);
+        dst[2] = make_ulonglong2(cv[4], cv[5]); dst[3] = make_ulonglong2(cv[6], cv[7]);
     }
 }
 
-// ---- phase 4: van Herk / Gil-Werman block prefix (rightmost-min) and suffix (rightmost-min) arg-minima
+// ---- phase: van Herk / Gil-Werman block prefix (rightmost-min) and suffix (rightmost-min) arg-minima
+template <bool CLEAN>
 __device__ __forceinline__ void phase_block_minima(const Tile &t)
 {
     const int nblk = (t.M + t.w - 1) / t.w;
     for (int id = threadIdx.x; id < 2 * nblk; id += NT) {
         if (id < nblk) {                                     // prefix: later position wins ties
             int b0 = id * t.w, b1 = min(b0 + t.w, t.M);
-            int cur = b0; uint64_t cv = t.canon[b0]; uint32_t cf = t.flag[b0];
+            int cur = b0; uint64_t cv = t.canon[cidx(b0)]; uint32_t cf = CLEAN ? 0 : t.flag[b0];
             t.pre[b0] = (uint16_t)b0;
             for (int p = b0 + 1; p < b1; ++p) {
-                uint64_t v = t.canon[p]; uint32_t f = t.flag[p];
-                if (canon_le(t, p, v, f, cur, cv, cf)) { cur = p; cv = v; cf = f; }
+                uint64_t v = t.canon[cidx(p)]; uint32_t f = CLEAN ? 0 : t.flag[p];
+                if (canon_le<CLEAN>(t, p, v, f, cur, cv, cf)) { cur = p; cv = v; cf = f; }
                 t.pre[p] = (uint16_t)cur;
             }
         } else {                                             // suffix: earlier position wins only if strictly smaller
             int b0 = (id - nblk) * t.w, b1 = min(b0 + t.w, t.M);
-            int cur = b1 - 1; uint64_t cv = t.canon[cur]; uint32_t cf = t.flag[cur];
+            int cur = b1 - 1; uint64_t cv = t.canon[cidx(cur)]; uint32_t cf = CLEAN ? 0 : t.flag[cur];
             t.suf[cur] = (uint16_t)cur;
             for (int p = b1 - 2; p >= b0; --p) {
-                uint64_t v = t.canon[p]; uint32_t f = t.flag[p];
-                if (canon_lt(t, p, v, f, cur, cv, cf)) { cur = p; cv = v; cf = f; }
+                uint64_t v = t.canon[cidx(p)]; uint32_t f = CLEAN ? 0 : t.flag[p];
+                if (canon_lt<CLEAN>(t, p, v, f, cur, cv, cf)) { cur = p; cv = v; cf = f; }
                 t.suf[p] = (uint16_t)cur;
             }
         }
     }
 }
 
-// ---- phase 5: arg-min (rightmost) of every window end p_e in [w-1, M)
-__device__ __forceinline__ void phase_window_argmin(const Tile &t)
+// arg-min (rightmost) of the window ending at e
+template <bool CLEAN>
+__device__ __forceinline__ int window_argmin(const Tile &t, int e)
 {
-    for (int e = t.w - 1 + threadIdx.x; e < t.M; e += NT) {
-        int a = t.suf[e - t.w + 1], b = t.pre[e];
-        int r = b;
-        if (a != b) r = canon_le(t, b, t.canon[b], t.flag[b], a, t.canon[a], t.flag[a]) ? b : a;
-        t.arg[e] = (uint16_t)r;
-    }
+    int a = t.suf[e - t.w + 1], b = t.pre[e];
+    if (a == b) return b;
+    uint32_t fa = CLEAN ? 0 : t.flag[a], fb = CLEAN ? 0 : t.flag[b];
+    return canon_le<CLEAN>(t, b, t.canon[cidx(b)], fb, a, t.canon[cidx(a)], fa) ? b : a;
 }
 
 // Sequence model: which windows exist, and which is the first of its sequence.
@@ -232,23 +292,33 @@ struct SeqModel {
     // k-mer positions of window e are [e-w+1, e]; bases [e-w+1, e+k-1]
     __device__ static __forceinline__ bool window_valid(const Tile &t, int e)
     {
-        long long gs = t.g0 + e - t.w + 1, ge = t.g0 + e + t.k;           // [gs, ge) bases
-        if (gs < 0 || ge > t.seq_len) return false;
+        if (e < t.e_lo || e >= t.e_hi) return false;
         if (MULTI) return !any_bits(t.bnd, e - t.w + 2, e + t.k - 1);     // no read starts strictly inside
         return true;
     }
     __device__ static __forceinline__ bool window_first(const Tile &t, int e)
     {
         if (MULTI) { int s = e - t.w + 1; return (t.bnd[s >> 5] >> (s & 31)) & 1u; }
-        return t.g0 + e == t.w - 1;
+        return e == t.e_first;
     }
 };
 
-// ---- phase 6: run starts among the tile's own windows e in [w, M), compacted in position order.
+// window-validity bounds in local coordinates from g0 / seq_len (call once per tile)
+__device__ __forceinline__ void set_window_bounds(Tile &t)
+{
+    // valid: g0 + e - w + 1 >= 0  and  g0 + e + k <= seq_len
+    long long lo = (long long)t.w - 1 - t.g0, hi = t.seq_len - t.k - t.g0 + 1;
+    t.e_lo = (int)max(lo, (long long)(t.w - 1));
+    t.e_hi = (int)min(hi, (long long)t.M);
+    t.e_first = (int)min(max(lo, -1ll), (long long)t.M + 1);               // only meaningful for the walk model
+}
+
+// ---- phase: window arg-minima + run starts among the tile's own windows e in [w, M), compacted in position order.
 // Run entry: arg-min position | 0x8000 if the run starts at the first window of its sequence.
-// Returns the number of runs (block-uniform).  runs[] aliases pre[]/suf[] (dead by now).
-template <bool MULTI>
-__device__ __forceinline__ int phase_runs(const Tile &t, uint16_t *runs)
+// Returns the number of runs (block-uniform).  runs[] aliases pre[]: the caller passes a separate array.
+// *halo_arg receives the arg-min of the halo window (e = w-1) if that window is valid, else -1 (thread 0 only).
+template <bool MULTI, bool CLEAN>
+__device__ __forceinline__ int phase_runs(const Tile &t, uint16_t *runs, int *halo_arg)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     constexpr int PER_WARP = TILE_W / (NT / 32);                          // 256 windows per warp
@@ -256,21 +326,31 @@ __device__ __forceinline__ int phase_runs(const Tile &t, uint16_t *runs)
     uint32_t ballots[ROUNDS];
     uint16_t mine[ROUNDS];
     int total = 0;
+    int carry = -1;                                                       // arg-min of the window before this lane-0's window
+    {
+        int e0 = t.w + wid * PER_WARP - 1;                                // window preceding the warp's first
+        if (lane == 0 && SeqModel<MULTI>::window_valid(t, e0)) carry = window_argmin<CLEAN>(t, e0);
+        if (threadIdx.x == 0) *halo_arg = carry;
+    }
     #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
-        int e = t.w + wid * PER_WARP + r * 32 + lane;
+        const int e = t.w + wid * PER_WARP + r * 32 + lane;
+        const bool valid = SeqModel<MULTI>::window_valid(t, e);
+        int a = valid ? window_argmin<CLEAN>(t, e) : -1;
+        int prev = __shfl_up_sync(0xFFFFFFFFu, a, 1);
+        if (lane == 0) prev = carry;
+        carry = __shfl_sync(0xFFFFFFFFu, a, 31);
         bool start = false; uint16_t ent = 0;
-        if (SeqModel<MULTI>::window_valid(t, e)) {
-            int a = t.arg[e];
+        if (valid) {
             if (SeqModel<MULTI>::window_first(t, e)) { start = true; ent = (uint16_t)(a | 0x8000); }
-            else if (a != t.arg[e - 1]) { start = true; ent = (uint16_t)a; }
+            else if (a != prev) { start = true; ent = (uint16_t)a; }
         }
         ballots[r] = __ballot_sync(0xFFFFFFFFu, start);
         mine[r] = ent;
         total += __popc(ballots[r]);
     }
     if (lane == 0) t.scan[wid] = total;
-    __syncthreads();                                                      // also: arg[] reads done before runs[] (aliasing pre/suf only)
+    __syncthreads();                                                      // all pre[]/suf[] reads are done: runs[] may alias pre[]
     int off = 0, all = 0;
     #pragma unroll
     for (int i = 0; i < NT / 32; ++i) { int c = t.scan[i]; if (i < wid) off += c; all += c; }
@@ -281,17 +361,6 @@ __device__ __forceinline__ int phase_runs(const Tile &t, uint16_t *runs)
     }
     __syncthreads();
     return all;
-}
-
-// Hash of the run preceding the tile's first window (the halo window's minimum), or UINT64_MAX when the
-// tile starts its sequence coordinate (no previous window exists).  Only meaningful if the first run of the
-// tile is not flagged "first of sequence" — flagged runs ignore it.
-template <bool MULTI>
-__device__ __forceinline__ uint64_t halo_prev_hash(const Tile &t)
-{
-    int e = t.w - 1;
-    if (!SeqModel<MULTI>::window_valid(t, e)) return 0xFFFFFFFFFFFFFFFFull;
-    return hash_at(t, t.arg[e]);
 }
 
 }  // namespace phi
