@@ -24,6 +24,7 @@ namespace phi {
 
 constexpr uint32_t G_EMPTY = 0xFFFFFFFFu;
 constexpr int SMALL_GROUP = 48;
+constexpr uint32_t CSR_HIST_MAX = 8192;   // walks whose counters fit a per-block shared histogram
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x)
 {
@@ -51,25 +52,25 @@ __global__ void group_count_kernel(FilterArgs A, FilterWork W)
     for (uint32_t q = 0; q < n; ++q) hsh = mix64(hsh ^ (uint64_t)(uint32_t)p[q]);
     const uint64_t mask = W.g_cap - 1;
     uint64_t slot = hsh & mask;
-    for (;;) {
+    for (uint64_t tries = 0; tries <= mask; ++tries) {
         uint32_t rep = W.g_rep[slot];
         if (rep == G_EMPTY) {
+            if (W.ctr[CTR_GROUPS] * 10 > W.g_cap * 8) break;             // table too full: the host retries with a larger one
             uint32_t old = atomicCAS(&W.g_rep[slot], G_EMPTY, (uint32_t)i);
-            rep = old == G_EMPTY ? (uint32_t)i : old;
+            if (old == G_EMPTY) { rep = (uint32_t)i; atomicAdd(&W.ctr[CTR_GROUPS], 1ull); } else rep = old;
         }
-        if (rep == (uint32_t)i || same_list(A, (uint32_t)i, rep)) { atomicAdd(&W.g_cnt[slot], 1u); return; }
+        if (rep == (uint32_t)i || same_list(A, (uint32_t)i, rep)) { atomicAdd(&W.g_cnt[slot], 1u); W.hit_slot[i] = (uint32_t)slot; return; }
         slot = (slot + 1) & mask;
     }
+    W.ctr[CTR_GROUP_OVERFLOW] = 1;
 }
 
 __global__ void mark_drop_kernel(FilterArgs A, FilterWork W)
 {
-    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (s >= W.g_cap) return;
-    uint32_t rep = W.g_rep[s];
-    if (rep == G_EMPTY) return;
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= A.n_hits) return;
     // anchor.second.first >= threshold * num_walks  — int32 promoted to float (:698)
-    if ((float)(int32_t)W.g_cnt[s] >= A.thr) W.rank_drop[A.hit_rank[rep]] = 1;
+    if ((float)(int32_t)W.g_cnt[W.hit_slot[i]] >= A.thr) W.rank_drop[A.hit_rank[i]] = 1;
 }
 
 __global__ void count_drops_kernel(const uint8_t *rank_drop, uint32_t n, unsigned long long *ctr)
@@ -83,8 +84,10 @@ __global__ void count_drops_kernel(const uint8_t *rank_drop, uint32_t n, unsigne
 __global__ void flag_survivors_kernel(FilterArgs A, FilterWork W)
 {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= A.n_hits) return;
-    W.flags[i] = W.rank_drop[A.hit_rank[i]] ? 0u : 1u;
+    uint32_t f = 0;
+    if (i < A.n_hits) { f = W.rank_drop[A.hit_rank[i]] ? 0u : 1u; W.flags[i] = f; }
+    int c = __syncthreads_count(f);
+    if (threadIdx.x == 0 && c) atomicAdd(&W.ctr[CTR_SURVIVORS], (unsigned long long)c);
 }
 
 // flags[] has been exclusive-scanned in place; a hit survives iff its rank is not dropped
@@ -117,7 +120,7 @@ cudaError_t filter_count_groups(const FilterArgs &A, const FilterWork &W, cudaSt
 cudaError_t filter_mark_drops(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches)
 {
     if (A.n_hits) {
-        mark_drop_kernel<<<(unsigned)((W.g_cap + 255) / 256), 256, 0, st>>>(A, W);
+        mark_drop_kernel<<<(unsigned)((A.n_hits + 255) / 256), 256, 0, st>>>(A, W);
         PHI_LAUNCH_CHECK();
     }
     if (A.n_ranks) {
@@ -260,9 +263,19 @@ __global__ void csr_fill_kernel(FilterArgs A, const uint32_t *order, uint64_t n,
         for (uint32_t i = 0; i < nv; ++i) anchor_vtx[o + i] = p[i];
         wl = A.hit_walk[x];
     }
-    // warp-aggregated per-walk counts (few distinct walks -> heavy contention otherwise)
-    uint32_t peers = __match_any_sync(0xFFFFFFFFu, wl);
-    if (wl != 0xFFFFFFFFu && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&anchors_per_walk[wl], (unsigned long long)__popc(peers));
+    // per-walk counts: block-local shared histogram (few distinct walks -> heavy global contention otherwise)
+    extern __shared__ uint32_t s_hist[];
+    if (n_walks_out <= CSR_HIST_MAX) {
+        for (uint32_t i = threadIdx.x; i < n_walks_out; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        if (wl != 0xFFFFFFFFu) atomicAdd(&s_hist[wl], 1u);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_walks_out; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(&anchors_per_walk[i], (unsigned long long)s_hist[i]);
+    } else {
+        uint32_t peers = __match_any_sync(0xFFFFFFFFu, wl);
+        if (wl != 0xFFFFFFFFu && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&anchors_per_walk[wl], (unsigned long long)__popc(peers));
+    }
 }
 
 cudaError_t filter_csr_sizes(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, uint32_t *nv_out, cudaStream_t st, uint64_t *launches)
@@ -277,7 +290,8 @@ cudaError_t filter_csr_fill(const FilterArgs &A, const uint32_t *order, uint64_t
                             uint32_t n_walks_out, cudaStream_t st, uint64_t *launches)
 {
     if (!n_surv) return cudaSuccess;
-    csr_fill_kernel<<<(unsigned)((n_surv + 255) / 256), 256, 0, st>>>(A, order, n_surv, anchor_off, anchor_rank, anchor_walk, anchor_vtx,
+    const size_t hist_bytes = n_walks_out <= CSR_HIST_MAX ? (size_t)n_walks_out * 4 : 0;
+    csr_fill_kernel<<<(unsigned)((n_surv + 1023) / 1024), 1024, hist_bytes, st>>>(A, order, n_surv, anchor_off, anchor_rank, anchor_walk, anchor_vtx,
                                                                      anchors_per_walk, walk_id_base, n_walks_out);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;

@@ -21,7 +21,9 @@ enum {
     CTR_ZERO_STEPS = 9,
     CTR_READ_POS = 10,
     CTR_COMPACT = 11,
-    CTR_NONMONO = 12,      // some walk is not strictly increasing in top_order_map
+    CTR_NONMONO = 12,
+    CTR_GROUPS = 13,       // distinct (rank, vertex list) groups in the filter table
+    CTR_GROUP_OVERFLOW = 14,      // some walk is not strictly increasing in top_order_map
     CTR_COUNT = 16
 };
 
@@ -111,6 +113,7 @@ struct FilterArgs {
 };
 struct FilterWork {                  // device scratch, sized by the host
     uint32_t *g_rep, *g_cnt; uint64_t g_cap;      // group table
+    uint32_t *hit_slot;                            // [n_hits] slot of each hit's group
     uint8_t *rank_drop;                            // [n_ranks]
     uint32_t *flags;                               // [n_hits] survivor flags -> scanned
     uint64_t *keys_a, *keys_b; uint32_t *vals_a, *vals_b;   // [n_survivors]

@@ -71,6 +71,7 @@ struct phi_gpu_index_ctx {
     // multi-GPU (set by comm_init)
     int rank = 0, world = 1; uint32_t walk_id_base = 0, n_walks_global = 0;
     void *comm = nullptr;
+    uint64_t gcap_hint = 0;              // group-table size that worked last time
 
     int fail(int code, const std::string &m) { err = m; return code; }
 };
@@ -460,18 +461,28 @@ static int stage_filter(phi_gpu_index_ctx *ctx, const std::vector<uint64_t> &h_w
     A.gpos_bits = bits_for(h_walk_gbase.back()); A.rank_bits = bits_for(o.n_spec ? o.n_spec - 1 : 0);
 
     FilterWork W;
-    uint64_t gcap = 1024; while (gcap < 2 * n) gcap <<= 1;
-    CU(ctx->g_rep.reserve(gcap * 4)); CU(ctx->g_cnt.reserve(gcap * 4)); CU(ctx->flags.reserve(n * 4 + 4));
-    CU(fill_u32(ctx->g_rep.as<uint32_t>(), gcap, 0xFFFFFFFFu, ctx->st, &ctx->launches));
-    CU(cudaMemsetAsync(ctx->g_cnt.p, 0, gcap * 4, ctx->st));
-    W.g_rep = ctx->g_rep.as<uint32_t>(); W.g_cnt = ctx->g_cnt.as<uint32_t>(); W.g_cap = gcap;
+    // group table: distinct (rank, vertex list) groups are usually far fewer than hits (one group per locus shared by many
+    // walks), so start small and grow on overflow instead of paying for a 2n-slot table every run
+    uint64_t gcap = 1024; while (gcap < n / 4) gcap <<= 1;
+    if (ctx->gcap_hint > gcap) gcap = ctx->gcap_hint;
+    CU(ctx->flags.reserve(n * 4 + 4)); CU(ctx->vals_b.reserve(n * 4 + 4));
+    W.hit_slot = ctx->vals_b.as<uint32_t>();                              // free until the survivor sort
     W.rank_drop = ctx->rank_drop.as<uint8_t>(); W.flags = ctx->flags.as<uint32_t>(); W.ctr = d_ctr;
     W.keys_a = W.keys_b = nullptr; W.vals_a = W.vals_b = nullptr; W.sort_scratch = nullptr; W.scan_scratch = nullptr;
-    CU(filter_count_groups(A, W, ctx->st, &ctx->launches));
+    for (;;) {
+        CU(ctx->g_rep.reserve(gcap * 4)); CU(ctx->g_cnt.reserve(gcap * 4));
+        CU(fill_u32(ctx->g_rep.as<uint32_t>(), gcap, 0xFFFFFFFFu, ctx->st, &ctx->launches));
+        CU(cudaMemsetAsync(ctx->g_cnt.p, 0, gcap * 4, ctx->st));
+        CU(cudaMemsetAsync(d_ctr + CTR_GROUPS, 0, 2 * 8, ctx->st));
+        W.g_rep = ctx->g_rep.as<uint32_t>(); W.g_cnt = ctx->g_cnt.as<uint32_t>(); W.g_cap = gcap;
+        CU(filter_count_groups(A, W, ctx->st, &ctx->launches));
+        CU(read_counters(ctx));
+        if (!ctx->h_ctr[CTR_GROUP_OVERFLOW]) break;
+        gcap <<= 2;
+        ctx->gcap_hint = gcap;
+    }
     CU(filter_mark_drops(A, W, ctx->st, &ctx->launches));
     CU(filter_flag_survivors(A, W, ctx->st, &ctx->launches));
-    count_survivors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(W.flags, n, d_ctr);
-    CU(cudaGetLastError()); ctx->launches++;
     CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(n), scan_u32_to_u64_scratch(n + 1))));
     CU(scan_u32_inplace(W.flags, n, ctx->scan_scr.p, ctx->st, &ctx->launches));
     CU(read_counters(ctx));

@@ -126,7 +126,9 @@ __device__ __forceinline__ uint32_t stage_chunk(const Tile &t, int c, uint64_t v
     ((uint2 *)t.base)[c] = make_uint2(lo4, hi4);
     ((uint16_t *)t.pack)[c ^ 1] = (uint16_t)bits;       // big-endian base order inside each u32
     ((uint8_t *)t.dirty)[c] = (uint8_t)dm;
-    return dm;
+    // bytes at or beyond NB are slack of the last chunk: no k-mer of the tile can touch them, so they must not make the tile dirty
+    const int live = t.NB - 8 * c;
+    return live >= 8 ? dm : (dm & ((1u << (live > 0 ? live : 0)) - 1u));
 }
 
 // 2k bits of the packed stream starting at base p, right-aligned
