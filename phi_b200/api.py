@@ -57,6 +57,10 @@ def load_library():
     lib.phi_gpu_host_alloc.restype = C.c_void_p
     lib.phi_gpu_host_alloc.argtypes = [C.c_size_t]
     lib.phi_gpu_host_free.argtypes = [C.c_void_p]
+    lib.phi_gpu_index_comm_unique_id.restype = C.c_int
+    lib.phi_gpu_index_comm_unique_id.argtypes = [C.c_char_p]
+    lib.phi_gpu_index_comm_init.restype = C.c_int
+    lib.phi_gpu_index_comm_init.argtypes = [ctxp, C.c_int, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32]
     lib.phi_shard_owner_of_hash.restype = C.c_int
     lib.phi_shard_owner_of_hash.argtypes = [C.c_uint64, C.c_int]
     lib.phi_shard_split_by_weight.restype = C.c_int
@@ -165,6 +169,19 @@ class PhiGpuIndex:
         self.lib.phi_gpu_index_result_free(out)
         self.lib.phi_gpu_index_free_u64(hp)
         return res, hashes
+
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id (rank 0 creates it, the caller distributes it)."""
+        lib = load_library()
+        buf = C.create_string_buffer(_abi.PHI_COMM_ID_BYTES)
+        rc = lib.phi_gpu_index_comm_unique_id(buf)
+        if rc != _abi.PHI_OK:
+            raise PhiGpuError(rc, lib.phi_gpu_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, rank, world, unique_id, walk_id_base, n_walks_global):
+        self._check(self.lib.phi_gpu_index_comm_init(self.ctx, rank, world, unique_id, walk_id_base, n_walks_global))
 
     def hash128_to_64(self, keys, length):
         """Device MurmurHash3_x64_128 -> h0^h1 over len(keys)//length packed keys."""

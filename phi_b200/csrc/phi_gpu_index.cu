@@ -6,6 +6,8 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <dlfcn.h>
+#include <nccl.h>          // types and prototypes only: the functions are resolved with dlopen at comm_init
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -72,6 +74,8 @@ struct phi_gpu_index_ctx {
     int rank = 0, world = 1; uint32_t walk_id_base = 0, n_walks_global = 0;
     void *comm = nullptr;
     uint64_t gcap_hint = 0;              // group-table size that worked last time
+    DevBuf xk_a, xk_b, xcnt, xoff, ag_send, ag_recv, r_rank, r_walk, r_pos, r_voff, r_nv, r_vtx, s_rank, s_walk, s_pos, s_voff, s_nv, s_vtx;
+    std::vector<uint64_t> own_off;       // [world + 1] first global rank owned by each GPU (multi-GPU runs)
 
     int fail(int code, const std::string &m) { err = m; return code; }
 };
@@ -323,6 +327,318 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     return PHI_OK;
 }
 
+
+// =====================================================================================================
+// Multi-GPU: one ctx per GPU, NCCL for the two exchange steps of the path.
+//   (1) distinct read-minimizer hashes -> owner GPU by hash range (all-to-all), owners dedup + sort, the sorted
+//       slices are broadcast so every GPU holds the whole ranked spectrum (concatenation of range slices is sorted);
+//   (2) walk hits -> owner of their rank (all-to-all), where the threshold filter and the final ordering run.
+// The reference has no counterpart (single process, OpenMP); see DESIGN.md §6.
+// =====================================================================================================
+namespace {
+
+struct NcclApi {
+    void *handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+};
+
+NcclApi *nccl_api(std::string &err)
+{
+    static NcclApi api; static std::mutex mu; static bool tried = false;
+    std::lock_guard<std::mutex> lk(mu);
+    if (api.handle) return &api;
+    if (tried) { err = "NCCL could not be loaded"; return nullptr; }
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+    if (!api.handle) { err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return nullptr; }
+#define PHI_NCCL_SYM(field, name) api.field = (decltype(api.field))dlsym(api.handle, name); if (!api.field) { err = std::string("NCCL symbol missing: ") + name; api.handle = nullptr; return nullptr; }
+    PHI_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") PHI_NCCL_SYM(CommInitRank, "ncclCommInitRank") PHI_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    PHI_NCCL_SYM(GetErrorString, "ncclGetErrorString") PHI_NCCL_SYM(GroupStart, "ncclGroupStart") PHI_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    PHI_NCCL_SYM(Send, "ncclSend") PHI_NCCL_SYM(Recv, "ncclRecv") PHI_NCCL_SYM(AllGather, "ncclAllGather") PHI_NCCL_SYM(Broadcast, "ncclBroadcast")
+#undef PHI_NCCL_SYM
+    return &api;
+}
+
+}  // namespace
+
+#define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return ctx->fail(PHI_ERR_COMM, std::string(#call) + ": " + nc->GetErrorString(r_)); } while (0)
+
+extern "C" int phi_gpu_index_comm_unique_id(uint8_t id[PHI_COMM_ID_BYTES])
+{
+    std::string err;
+    NcclApi *nc = nccl_api(err);
+    if (!nc || !id) { g_create_error = err; return PHI_ERR_COMM; }
+    static_assert(PHI_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "id size");
+    ncclUniqueId u;
+    if (nc->GetUniqueId(&u) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return PHI_ERR_COMM; }
+    memcpy(id, u.internal, PHI_COMM_ID_BYTES);
+    return PHI_OK;
+}
+
+extern "C" int phi_gpu_index_comm_init(phi_gpu_index_ctx *ctx, int rank, int world, const uint8_t id[PHI_COMM_ID_BYTES],
+                                       uint32_t walk_id_base, uint32_t n_walks_global)
+{
+    if (!ctx) return PHI_ERR_ARG;
+    if (world < 1 || rank < 0 || rank >= world || !id) return ctx->fail(PHI_ERR_ARG, "bad rank/world/id");
+    if (world > 64) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 64 ranks");
+    ctx->rank = rank; ctx->world = world; ctx->walk_id_base = walk_id_base; ctx->n_walks_global = n_walks_global;
+    if (world == 1) return PHI_OK;
+    std::string err;
+    NcclApi *nc = nccl_api(err);
+    if (!nc) return ctx->fail(PHI_ERR_COMM, err);
+    CU(cudaSetDevice(ctx->device));
+    ncclUniqueId u; memcpy(u.internal, id, PHI_COMM_ID_BYTES);
+    ncclComm_t comm;
+    NC(nc->CommInitRank(&comm, world, u, rank));
+    ctx->comm = comm;
+    return PHI_OK;
+}
+
+// byte-wise all-to-all with per-peer counts and offsets (in elements of `esz` bytes)
+static int alltoallv(phi_gpu_index_ctx *ctx, NcclApi *nc, const void *send, const std::vector<uint64_t> &scnt, const std::vector<uint64_t> &soff,
+                     void *recv, const std::vector<uint64_t> &rcnt, const std::vector<uint64_t> &roff, size_t esz)
+{
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    for (int p = 0; p < ctx->world; ++p) {
+        if (scnt[p]) NC(nc->Send((const char *)send + soff[p] * esz, scnt[p] * esz, ncclUint8, p, comm, ctx->st));
+        if (rcnt[p]) NC(nc->Recv((char *)recv + roff[p] * esz, rcnt[p] * esz, ncclUint8, p, comm, ctx->st));
+    }
+    return PHI_OK;
+}
+
+// every rank contributes `n` u64 values (host), receives world*n (host)
+static int allgather_host_u64(phi_gpu_index_ctx *ctx, NcclApi *nc, const std::vector<uint64_t> &mine, std::vector<uint64_t> &all)
+{
+    const size_t n = mine.size(), W = ctx->world;
+    CU(ctx->ag_send.reserve(n * 8 + 8)); CU(ctx->ag_recv.reserve(n * W * 8 + 8));
+    CU(cudaMemcpyAsync(ctx->ag_send.p, mine.data(), n * 8, cudaMemcpyHostToDevice, ctx->st));
+    NC(nc->AllGather(ctx->ag_send.p, ctx->ag_recv.p, n, ncclUint64, (ncclComm_t)ctx->comm, ctx->st));
+    all.resize(n * W);
+    CU(cudaMemcpyAsync(all.data(), ctx->ag_recv.p, n * W * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return PHI_OK;
+}
+
+__global__ void owner_split_kernel(const uint64_t *sorted, uint64_t n, const uint64_t *bounds, int world, uint64_t *split)
+{
+    int o = threadIdx.x;
+    if (o > world) return;
+    if (o == world) { split[o] = n; return; }
+    uint64_t key = bounds[o], lo = 0, hi = n;                        // first index with sorted[i] >= bounds[o]
+    while (lo < hi) { uint64_t m = (lo + hi) >> 1; if (sorted[m] < key) lo = m + 1; else hi = m; }
+    split[o] = lo;
+}
+__global__ void unique_flags_kernel(const uint64_t *sorted, uint64_t n, uint32_t *flags)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (i == 0 || sorted[i] != sorted[i - 1]) ? 1u : 0u;
+}
+__global__ void unique_compact_kernel(const uint64_t *sorted, uint64_t n, const uint64_t *pos, uint64_t *out)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n && (i == 0 || sorted[i] != sorted[i - 1])) out[pos[i]] = sorted[i];
+}
+
+// Exchange of the locally distinct, locally sorted hashes (n_local of them in ctx->spec_a) -> ctx->spec_a = global sorted spectrum.
+static int exchange_spectrum(phi_gpu_index_ctx *ctx, uint64_t n_local, uint64_t &n_spec)
+{
+    std::string err; NcclApi *nc = nccl_api(err);
+    if (!nc || !ctx->comm) return ctx->fail(PHI_ERR_COMM, "communicator not initialised");
+    const int W = ctx->world, me = ctx->rank;
+    // owner boundaries: smallest hash owned by o is ceil(o * 2^64 / W)   (phi_shard_owner_of_hash)
+    std::vector<uint64_t> bounds(W + 1, 0), split(W + 1, 0);
+    for (int o = 0; o < W; ++o) bounds[o] = (uint64_t)((((unsigned __int128)o << 64) + W - 1) / W);
+    CU(ctx->xcnt.reserve((W + 1) * 16));
+    uint64_t *d_bounds = ctx->xcnt.as<uint64_t>(), *d_split = d_bounds + (W + 1);
+    CU(cudaMemcpyAsync(d_bounds, bounds.data(), (W + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
+    owner_split_kernel<<<1, 128, 0, ctx->st>>>(ctx->spec_a.as<uint64_t>(), n_local, d_bounds, W, d_split);
+    CU(cudaGetLastError()); ctx->launches++;
+    CU(cudaMemcpyAsync(split.data(), d_split, (W + 1) * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    std::vector<uint64_t> scnt(W), soff(W), all;
+    for (int o = 0; o < W; ++o) { scnt[o] = split[o + 1] - split[o]; soff[o] = split[o]; }
+    int rc = allgather_host_u64(ctx, nc, scnt, all);                   // all[src * W + dst]
+    if (rc) return rc;
+    std::vector<uint64_t> rcnt(W), roff(W);
+    uint64_t rtot = 0;
+    for (int p = 0; p < W; ++p) { rcnt[p] = all[(size_t)p * W + me]; roff[p] = rtot; rtot += rcnt[p]; }
+    CU(ctx->xk_a.reserve((rtot + 1) * 8)); CU(ctx->xk_b.reserve((rtot + 1) * 8));
+    NC(nc->GroupStart());
+    rc = alltoallv(ctx, nc, ctx->spec_a.p, scnt, soff, ctx->xk_a.p, rcnt, roff, 8);
+    if (rc) return rc;
+    NC(nc->GroupEnd());
+    // owner: sort what arrived, drop duplicates
+    CU(ctx->sort_scr.reserve(radix_sort_scratch(std::max<uint64_t>(rtot, 1))));
+    CU(radix_sort_u64(ctx->xk_a.as<uint64_t>(), ctx->xk_b.as<uint64_t>(), nullptr, nullptr, rtot, 0, 64, ctx->sort_scr.p, ctx->st, &ctx->launches));
+    uint64_t n_own = 0;
+    if (rtot) {
+        CU(ctx->flags.reserve(rtot * 4 + 4)); CU(ctx->flags64.reserve((rtot + 1) * 8));
+        CU(ctx->scan_scr.reserve(scan_u32_to_u64_scratch(rtot + 1)));
+        unique_flags_kernel<<<(unsigned)((rtot + 255) / 256), 256, 0, ctx->st>>>(ctx->xk_a.as<uint64_t>(), rtot, ctx->flags.as<uint32_t>());
+        CU(cudaGetLastError()); ctx->launches++;
+        CU(scan_u32_to_u64(ctx->flags.as<uint32_t>(), ctx->flags64.as<uint64_t>(), rtot, ctx->scan_scr.p, ctx->st, &ctx->launches));
+        unique_compact_kernel<<<(unsigned)((rtot + 255) / 256), 256, 0, ctx->st>>>(ctx->xk_a.as<uint64_t>(), rtot, ctx->flags64.as<uint64_t>(), ctx->xk_b.as<uint64_t>());
+        CU(cudaGetLastError()); ctx->launches++;
+        uint64_t last_pos = 0; uint32_t last_flag = 0;
+        CU(cudaMemcpyAsync(&last_pos, ctx->flags64.as<uint64_t>() + rtot - 1, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(&last_flag, ctx->flags.as<uint32_t>() + rtot - 1, 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        n_own = last_pos + last_flag;
+    }
+    std::vector<uint64_t> mine(1, n_own), owns;
+    rc = allgather_host_u64(ctx, nc, mine, owns);
+    if (rc) return rc;
+    ctx->own_off.assign(W + 1, 0);
+    for (int o = 0; o < W; ++o) ctx->own_off[o + 1] = ctx->own_off[o] + owns[o];
+    n_spec = ctx->own_off[W];
+    CU(ctx->spec_a.reserve((n_spec + 1) * 8));
+    NC(nc->GroupStart());
+    for (int o = 0; o < W; ++o) {
+        if (!owns[o]) continue;
+        uint64_t *dst = ctx->spec_a.as<uint64_t>() + ctx->own_off[o];
+        NC(nc->Broadcast(o == me ? (const void *)ctx->xk_b.p : (const void *)dst, dst, owns[o], ncclUint64, o, (ncclComm_t)ctx->comm, ctx->st));
+    }
+    NC(nc->GroupEnd());
+    return PHI_OK;
+}
+
+// ---- hit routing
+__global__ void route_count_kernel(const uint32_t *hit_rank, const uint8_t *hit_nv, uint64_t n, const uint64_t *own_off, int world,
+                                   unsigned long long *cnt /* [2*world]: hits, vertices */)
+{
+    __shared__ unsigned long long sh[128];
+    for (int i = threadIdx.x; i < 2 * world; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint64_t r = hit_rank[i]; int o = 0;
+        while (o + 1 < world && own_off[o + 1] <= r) ++o;
+        atomicAdd(&sh[o], 1ull); atomicAdd(&sh[world + o], (unsigned long long)hit_nv[i]);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 2 * world; j += blockDim.x) if (sh[j]) atomicAdd(&cnt[j], sh[j]);
+}
+
+struct RouteArgs {
+    const uint32_t *hit_rank, *hit_walk, *hit_pos; const uint64_t *hit_voff; const uint8_t *hit_nv; const int32_t *vtx;
+    uint64_t n; const uint64_t *own_off; int world;
+    unsigned long long *cursor;                   // [2*world] running (hits, vertices) per owner, initialised with the segment starts
+    const uint64_t *vtx_seg_start;                // [world] start of each owner's vertex segment in s_vtx
+    uint32_t *s_rank, *s_walk, *s_pos; uint64_t *s_voff; uint8_t *s_nv; int32_t *s_vtx;
+};
+__global__ void route_scatter_kernel(RouteArgs A)
+{
+    __shared__ unsigned long long sh_cnt[128], sh_base[128];
+    for (int i = threadIdx.x; i < 2 * A.world; i += blockDim.x) sh_cnt[i] = 0;
+    __syncthreads();
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    int o = 0; unsigned long long lh = 0, lv = 0; uint32_t nv = 0;
+    if (i < A.n) {
+        uint64_t r = A.hit_rank[i];
+        while (o + 1 < A.world && A.own_off[o + 1] <= r) ++o;
+        nv = A.hit_nv[i];
+        lh = atomicAdd(&sh_cnt[o], 1ull); lv = atomicAdd(&sh_cnt[A.world + o], (unsigned long long)nv);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 2 * A.world; j += blockDim.x) sh_base[j] = sh_cnt[j] ? atomicAdd(&A.cursor[j], sh_cnt[j]) : 0ull;
+    __syncthreads();
+    if (i < A.n) {
+        unsigned long long dh = sh_base[o] + lh, dv = sh_base[A.world + o] + lv;
+        A.s_rank[dh] = A.hit_rank[i]; A.s_walk[dh] = A.hit_walk[i]; A.s_pos[dh] = A.hit_pos[i]; A.s_nv[dh] = (uint8_t)nv;
+        A.s_voff[dh] = dv - A.vtx_seg_start[o];                       // relative to the (src -> owner) vertex segment
+        const int32_t *src = A.vtx + A.hit_voff[i];
+        for (uint32_t q = 0; q < nv; ++q) A.s_vtx[dv + q] = src[q];
+    }
+}
+__global__ void rebase_voff_kernel(uint64_t *voff, uint64_t n, const uint64_t *hit_seg_off, const uint64_t *vtx_seg_off, int world)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = 0;
+    while (p + 1 < world && hit_seg_off[p + 1] <= i) ++p;
+    voff[i] += vtx_seg_off[p];
+}
+
+// hits (ctx->hit_*) -> owner of their rank; afterwards ctx->hit_* hold the hits this GPU owns
+static int exchange_hits(phi_gpu_index_ctx *ctx, RunOut &o)
+{
+    std::string err; NcclApi *nc = nccl_api(err);
+    if (!nc || !ctx->comm) return ctx->fail(PHI_ERR_COMM, "communicator not initialised");
+    const int W = ctx->world, me = ctx->rank;
+    const uint64_t n = o.n_hits;
+    CU(ctx->xcnt.reserve(8192));
+    uint64_t *d_own = ctx->xcnt.as<uint64_t>();                        // [W+1] own_off | [2W] counts | [2W] cursors | [W] vtx seg start | recv seg offs
+    unsigned long long *d_cnt = (unsigned long long *)(d_own + 65), *d_cur = d_cnt + 128;
+    uint64_t *d_vseg = (uint64_t *)(d_cur + 128), *d_rh = d_vseg + 64, *d_rv = d_rh + 65;
+    CU(cudaMemcpyAsync(d_own, ctx->own_off.data(), (W + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemsetAsync(d_cnt, 0, 2 * W * 8, ctx->st));
+    if (n) {
+        route_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(ctx->hit_rank.as<uint32_t>(), ctx->hit_nv.as<uint8_t>(), n, d_own, W, d_cnt);
+        CU(cudaGetLastError()); ctx->launches++;
+    }
+    std::vector<uint64_t> cnt(2 * W, 0), all;
+    CU(cudaMemcpyAsync(cnt.data(), d_cnt, 2 * W * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    std::vector<uint64_t> sh_cnt(W), sh_off(W), sv_cnt(W), sv_off(W), cur(2 * W);
+    uint64_t th = 0, tv = 0;
+    for (int p = 0; p < W; ++p) { sh_cnt[p] = cnt[p]; sv_cnt[p] = cnt[W + p]; sh_off[p] = th; sv_off[p] = tv; th += cnt[p]; tv += cnt[W + p]; cur[p] = sh_off[p]; cur[W + p] = sv_off[p]; }
+    CU(ctx->s_rank.reserve(th * 4 + 4)); CU(ctx->s_walk.reserve(th * 4 + 4)); CU(ctx->s_pos.reserve(th * 4 + 4));
+    CU(ctx->s_voff.reserve(th * 8 + 8)); CU(ctx->s_nv.reserve(th + 4)); CU(ctx->s_vtx.reserve(tv * 4 + 4));
+    CU(cudaMemcpyAsync(d_cur, cur.data(), 2 * W * 8, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(d_vseg, sv_off.data(), W * 8, cudaMemcpyHostToDevice, ctx->st));
+    if (n) {
+        RouteArgs A;
+        A.hit_rank = ctx->hit_rank.as<uint32_t>(); A.hit_walk = ctx->hit_walk.as<uint32_t>(); A.hit_pos = ctx->hit_pos.as<uint32_t>();
+        A.hit_voff = ctx->hit_voff.as<uint64_t>(); A.hit_nv = ctx->hit_nv.as<uint8_t>(); A.vtx = ctx->vtx_pool.as<int32_t>();
+        A.n = n; A.own_off = d_own; A.world = W; A.cursor = d_cur; A.vtx_seg_start = d_vseg;
+        A.s_rank = ctx->s_rank.as<uint32_t>(); A.s_walk = ctx->s_walk.as<uint32_t>(); A.s_pos = ctx->s_pos.as<uint32_t>();
+        A.s_voff = ctx->s_voff.as<uint64_t>(); A.s_nv = ctx->s_nv.as<uint8_t>(); A.s_vtx = ctx->s_vtx.as<int32_t>();
+        route_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(A);
+        CU(cudaGetLastError()); ctx->launches++;
+    }
+    int rc = allgather_host_u64(ctx, nc, cnt, all);                     // all[src * 2W + {dst, W + dst}]
+    if (rc) return rc;
+    std::vector<uint64_t> rh_cnt(W), rh_off(W + 1, 0), rv_cnt(W), rv_off(W + 1, 0);
+    for (int p = 0; p < W; ++p) {
+        rh_cnt[p] = all[(size_t)p * 2 * W + me]; rv_cnt[p] = all[(size_t)p * 2 * W + W + me];
+        rh_off[p + 1] = rh_off[p] + rh_cnt[p]; rv_off[p + 1] = rv_off[p] + rv_cnt[p];
+    }
+    const uint64_t rh = rh_off[W], rv = rv_off[W];
+    if (rh >= (1ull << 32)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-1 hits routed to one GPU");
+    CU(ctx->r_rank.reserve(rh * 4 + 4)); CU(ctx->r_walk.reserve(rh * 4 + 4)); CU(ctx->r_pos.reserve(rh * 4 + 4));
+    CU(ctx->r_voff.reserve(rh * 8 + 8)); CU(ctx->r_nv.reserve(rh + 4)); CU(ctx->r_vtx.reserve(rv * 4 + 4));
+    NC(nc->GroupStart());
+    rc = alltoallv(ctx, nc, ctx->s_rank.p, sh_cnt, sh_off, ctx->r_rank.p, rh_cnt, rh_off, 4);
+    if (!rc) rc = alltoallv(ctx, nc, ctx->s_walk.p, sh_cnt, sh_off, ctx->r_walk.p, rh_cnt, rh_off, 4);
+    if (!rc) rc = alltoallv(ctx, nc, ctx->s_pos.p, sh_cnt, sh_off, ctx->r_pos.p, rh_cnt, rh_off, 4);
+    if (!rc) rc = alltoallv(ctx, nc, ctx->s_voff.p, sh_cnt, sh_off, ctx->r_voff.p, rh_cnt, rh_off, 8);
+    if (!rc) rc = alltoallv(ctx, nc, ctx->s_nv.p, sh_cnt, sh_off, ctx->r_nv.p, rh_cnt, rh_off, 1);
+    if (!rc) rc = alltoallv(ctx, nc, ctx->s_vtx.p, sv_cnt, sv_off, ctx->r_vtx.p, rv_cnt, rv_off, 4);
+    if (rc) return rc;
+    NC(nc->GroupEnd());
+    if (rh) {
+        CU(cudaMemcpyAsync(d_rh, rh_off.data(), (W + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaMemcpyAsync(d_rv, rv_off.data(), (W + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
+        rebase_voff_kernel<<<(unsigned)((rh + 255) / 256), 256, 0, ctx->st>>>(ctx->r_voff.as<uint64_t>(), rh, d_rh, d_rv, W);
+        CU(cudaGetLastError()); ctx->launches++;
+    }
+    CU(cudaStreamSynchronize(ctx->st));                                  // host vectors above were the source of async copies
+    std::swap(ctx->hit_rank, ctx->r_rank); std::swap(ctx->hit_walk, ctx->r_walk); std::swap(ctx->hit_pos, ctx->r_pos);
+    std::swap(ctx->hit_voff, ctx->r_voff); std::swap(ctx->hit_nv, ctx->r_nv); std::swap(ctx->vtx_pool, ctx->r_vtx);
+    o.n_hits = rh; o.n_hit_vtx = rv;
+    return PHI_OK;
+}
+
 // ---- stage: reads -> ranked spectrum (sorted distinct hashes + radix directory)
 static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbits)
 {
@@ -376,6 +692,11 @@ static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbi
         CU(cudaEventRecord(ctx->ev[EV_READS], ctx->st));
         CU(ctx->spec_a.reserve(8));
     }
+    if (ctx->world > 1) {                                                 // every rank takes part, also with zero local reads
+        int rc = exchange_spectrum(ctx, n_spec, n_spec);
+        if (rc) return rc;
+        if (n_spec >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^31-1 distinct read minimizers (count_sp_r is int32 in the reference)");
+    }
     o.n_spec = (uint32_t)n_spec;
     dbits = 0;
     while (dbits < 30 && (1ull << dbits) < n_spec) ++dbits;
@@ -389,14 +710,16 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
                        const uint32_t *d_walk_vtx, const uint64_t *d_walk_off, uint64_t n_steps_eff, int walks_monotone, RunOut &o)
 {
     const uint32_t H = ctx->n_walks;
+    const uint32_t HM = ctx->world > 1 ? ctx->n_walks_global : H;         // per-walk counters are indexed by global walk id
+    const uint32_t wbase = ctx->world > 1 ? ctx->walk_id_base : 0;
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
-    CU(ctx->mpw.reserve(((size_t)H + 1) * 8));
+    CU(ctx->mpw.reserve(((size_t)HM + 1) * 8));
     uint64_t positions = 0, bases = 0;
     for (uint32_t h = 0; h < H; ++h) { bases += h_walk_len[h]; if (h_walk_len[h] >= (uint64_t)(w + k - 1)) positions += h_walk_len[h] - k + 1; }
     o.path_pos = positions;
     CU(cudaEventRecord(ctx->ev[EV_WK0], ctx->st));
     CU(cudaEventRecord(ctx->ev[EV_WK1], ctx->st));
-    if (!H || !max_tiles) { CU(cudaMemsetAsync(ctx->mpw.p, 0, ((size_t)H + 1) * 8, ctx->st)); return PHI_OK; }
+    if (!H || !max_tiles) { CU(cudaMemsetAsync(ctx->mpw.p, 0, ((size_t)HM + 1) * 8, ctx->st)); o.n_hits = o.n_hit_vtx = 0; return PHI_OK; }
     // capacity estimate: emitted density 2/(w+1), vertices per anchor 1 + (k-1)/mean node length; exact re-run on overflow
     double dens = std::min(1.0, 2.0 / (w + 1.0)) * 1.3;
     double mean_node = n_steps_eff ? (double)bases / (double)n_steps_eff : 1.0;
@@ -408,7 +731,7 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
         CU(ctx->hit_voff.reserve(hit_cap * 8)); CU(ctx->hit_nv.reserve(hit_cap));
         if (mode == WALK_MODE_ALL) CU(ctx->hit_hash.reserve(hit_cap * 8));
         CU(ctx->vtx_pool.reserve(vtx_cap * 4));
-        CU(cudaMemsetAsync(ctx->mpw.p, 0, ((size_t)H + 1) * 8, ctx->st));
+        CU(cudaMemsetAsync(ctx->mpw.p, 0, ((size_t)HM + 1) * 8, ctx->st));
         CU(cudaMemsetAsync(d_ctr + CTR_HITS, 0, 2 * 8, ctx->st));
         WalkSketchArgs A;
         A.layout = tile_layout(k, w, true); A.walks_monotone = walks_monotone;
@@ -418,8 +741,8 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
         A.tile_first_step = ctx->tile_first_step.as<uint32_t>();
         A.k = k; A.w = w; A.mode = mode;
         A.spec = ctx->spec_a.as<uint64_t>(); A.dir = ctx->dir.as<uint32_t>(); A.dbits = dbits;
-        A.walk_id_base = ctx->walk_id_base;
-        A.minimizers_per_walk = ctx->mpw.as<unsigned long long>();
+        A.walk_id_base = wbase;
+        A.minimizers_per_walk = ctx->mpw.as<unsigned long long>() + wbase;
         A.hit_rank = ctx->hit_rank.as<uint32_t>(); A.hit_walk = ctx->hit_walk.as<uint32_t>(); A.hit_pos = ctx->hit_pos.as<uint32_t>();
         A.hit_voff = ctx->hit_voff.as<uint64_t>(); A.hit_nv = ctx->hit_nv.as<uint8_t>();
         A.hit_hash = mode == WALK_MODE_ALL ? ctx->hit_hash.as<uint64_t>() : nullptr;
@@ -635,6 +958,10 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     CU(cudaEventRecord(ctx->ev[EV_SPECTRUM], ctx->st));
     rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, max_tiles, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, o);
     if (rc) return rc;
+    if (ctx->world > 1 && mode == WALK_MODE_PROBE) {
+        rc = exchange_hits(ctx, o);
+        if (rc) return rc;
+    }
     CU(cudaEventRecord(ctx->ev[EV_WALKS], ctx->st));
 
     const uint32_t H = ctx->n_walks;
@@ -691,7 +1018,7 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     }
     CU(cudaEventRecord(ctx->ev[EV_FILTER], ctx->st));
 
-    res->count_sp_r = (int32_t)o.n_spec; res->n_walks = H; res->n_filtered = o.n_filtered;
+    res->count_sp_r = (int32_t)o.n_spec; res->n_walks = HG; res->n_filtered = o.n_filtered;
     res->n_anchors = o.n_surv; res->n_anchor_vtx = o.n_anchor_vtx;
     res->read_kmer_positions = o.read_pos; res->path_kmer_positions = o.path_pos;
     res->read_minimizers_emitted = o.read_emitted; res->path_hits = o.n_hits;
@@ -701,11 +1028,11 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
         if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_walk.p, o.n_surv, &res->anchor_walk);
         if (!rc) rc = download<uint64_t>(ctx, res, ctx->anchor_off.p, o.n_surv + 1, &res->anchor_off);
         if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_vtx.p, o.n_anchor_vtx, &res->anchor_vtx);
-        if (!rc) rc = download<uint64_t>(ctx, res, ctx->apw.as<uint64_t>() + ctx->walk_id_base, H, &res->anchors_per_walk);
+        if (!rc) rc = download<uint64_t>(ctx, res, ctx->apw.as<uint64_t>(), HG, &res->anchors_per_walk);
         if (rc) { phi_gpu_index_result_free(res); return rc; }
     }
     {   // per-walk minimizer counts are tiny and always returned
-        int rc2 = download<uint64_t>(ctx, res, ctx->mpw.p, H, &res->minimizers_per_walk);
+        int rc2 = download<uint64_t>(ctx, res, ctx->mpw.p, HG, &res->minimizers_per_walk);
         if (rc2) { phi_gpu_index_result_free(res); return rc2; }
     }
     uint64_t *hashes = nullptr; uint32_t *h_order = nullptr;
@@ -716,7 +1043,7 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     }
     CU(cudaEventRecord(ctx->ev[EV_END], ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
-    for (uint32_t h = 0; h < H; ++h) res->path_minimizers_emitted += res->minimizers_per_walk[h];
+    for (uint32_t h = 0; h < HG; ++h) res->path_minimizers_emitted += res->minimizers_per_walk[h];
     if (mode == WALK_MODE_ALL && hashes_out) {
         uint64_t *sorted = (uint64_t *)malloc(std::max<uint64_t>(o.n_hits, 1) * 8);
         for (uint64_t i = 0; i < o.n_hits; ++i) sorted[i] = hashes[h_order[i]];
@@ -784,15 +1111,3 @@ extern "C" int phi_gpu_hash128_to_64(phi_gpu_index_ctx *ctx, const uint8_t *keys
     return PHI_OK;
 }
 
-// ---- multi-GPU entry points (NCCL exchange: see comm.cu once built; until then they refuse loudly)
-extern "C" int phi_gpu_index_comm_unique_id(uint8_t id[PHI_COMM_ID_BYTES])
-{
-    (void)id;
-    return PHI_ERR_UNSUPPORTED;
-}
-extern "C" int phi_gpu_index_comm_init(phi_gpu_index_ctx *ctx, int rank, int world, const uint8_t id[PHI_COMM_ID_BYTES],
-                                       uint32_t walk_id_base, uint32_t n_walks_global)
-{
-    (void)rank; (void)world; (void)id; (void)walk_id_base; (void)n_walks_global;
-    return ctx ? ctx->fail(PHI_ERR_UNSUPPORTED, "multi-GPU exchange is not built into this library yet") : PHI_ERR_ARG;
-}

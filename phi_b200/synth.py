@@ -56,7 +56,7 @@ class SynthGraph:
 
 def make_graph(seed, backbone_len, n_haps, var_spacing=50, chop=30, founders=8, block_sites=400,
                indel_frac=0.10, sv_frac=0.05, max_indel=50, max_sv=10000, snv_only=False,
-               lower_frac=0.0, n_frac=0.0):
+               lower_frac=0.0, n_frac=0.0, walk_range=None):
     rng = np.random.Generator(np.random.PCG64(seed))
     L = int(backbone_len)
     backbone = _ACGT[rng.integers(0, 4, L)]
@@ -130,15 +130,16 @@ def make_graph(seed, backbone_len, n_haps, var_spacing=50, chop=30, founders=8, 
     g = Graph(seg_off, seg_bases, np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint32),
               np.arange(n_vtx, dtype=np.int32), [])
     sg = SynthGraph(g, piece_first_node, piece_n_nodes, piece_off, piece_len, n_sites, alleles)
-    walks = [sg.walk_of(alleles[h]) for h in range(n_haps)]
+    lo, hi = walk_range if walk_range is not None else (0, n_haps)      # only these walks are spelled out (multi-GPU shards)
+    walks = [sg.walk_of(alleles[h]) for h in range(lo, hi)]
     g.walk_off = np.concatenate([[0], np.cumsum([len(x) for x in walks])]).astype(np.uint64)
     g.walk_vtx = np.concatenate(walks).astype(np.uint32) if walks else np.zeros(0, dtype=np.uint32)
-    g.walk_names = [f"hap{h}.{h}" for h in range(n_haps)]
+    g.walk_names = [f"hap{h}.{h}" for h in range(lo, hi)]
     return sg
 
 
 def make_reads(seed, sg, coverage, read_len=150, sub_err=0.005, len_sigma=0.0, mosaic_block=2000,
-               lower_frac=0.0, n_frac=0.0):
+               lower_frac=0.0, n_frac=0.0, sample_seed=0):
     """Reads sampled from a held-out mosaic of the graph's haplotypes, both strands, substitution errors."""
     rng = np.random.Generator(np.random.PCG64(seed ^ 0x5EED))
     n_haps = sg.alleles.shape[0]
@@ -147,6 +148,8 @@ def make_reads(seed, sg, coverage, read_len=150, sub_err=0.005, len_sigma=0.0, m
     mosaic = sg.alleles[src[np.arange(sg.n_sites) // mosaic_block], np.arange(sg.n_sites)]
     seq = sg.sequence_of(mosaic)
     n = len(seq)
+    if sample_seed:                                               # same sample (mosaic), independent read draw
+        rng = np.random.Generator(np.random.PCG64((seed ^ 0x5EED) + 7919 * sample_seed))
     n_reads = max(1, int(round(coverage * n / read_len)))
     if len_sigma > 0:
         lens = np.clip(rng.lognormal(np.log(read_len), len_sigma, n_reads).astype(np.int64), 50, n)

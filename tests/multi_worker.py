@@ -1,0 +1,136 @@
+"""Worker launched by the multi-rank tests:  python -m torch.distributed.run ... tests/multi_worker.py {gpu|cpu} <case>
+
+gpu : every rank drives one B200 through the C ABI (NCCL exchange inside the library), rank 0 merges and checks
+      against the oracle on the unsharded input.
+cpu : gloo, no GPU — the same partition functions (phi_shard_*) and merge code, with the per-rank compute done by the
+      oracle and the exchanges done with torch.distributed object collectives: a check of the sharded ALGORITHM
+      (hash-range ownership, rank offsets, hit routing, owner-side filter, merge), not of the kernels.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch.distributed as dist  # noqa: E402
+
+import phi_io  # noqa: E402
+from golden_cases import Case, assert_same_result  # noqa: E402
+from phi_b200 import _abi, multi  # noqa: E402
+
+
+def load(name):
+    if name.startswith("synth:"):
+        from phi_b200 import synth
+        _, seed, backbone, haps, cov = name.split(":")
+        sg = synth.make_graph(int(seed), int(backbone), int(haps))
+        rd = synth.make_reads(int(seed), sg, float(cov))
+        return sg.graph, rd, 31, 25, 1.0
+    c = Case(name)
+    return c.graph, c.reads, c.k, c.w, c.T
+
+
+def main_gpu(name):
+    import torch
+    import phi_b200
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    g, rd, k, w, T = load(name)
+    gs, rs, base = multi.shard_inputs(g, rd, rank, world)
+    ix = phi_b200.PhiGpuIndex(local)
+    multi.init_comm(ix, rank, world, base, g.n_walks, dist)
+    part = ix.run(gs, rs, k, w, T)
+    part2 = ix.run(gs, rs, k, w, T)                      # repeatable
+    assert_same_result(part, part2)
+    parts = [None] * world
+    dist.gather_object(part, parts if rank == 0 else None, dst=0)
+    if rank == 0:
+        got = multi.merge_results(parts)
+        want = phi_io.oracle_index(g, rd, k, w, T)
+        got.path_hits = want.path_hits                   # pre-filter hit count is per-GPU bookkeeping
+        assert_same_result(want, got)
+        print(f"MULTI_OK gpu world={world} case={name} spectrum={got.count_sp_r} anchors={got.n_anchors}")
+    ix.close()
+    dist.barrier()
+
+
+def py_filter(hits, n_walks_global, T):
+    """hits: list of (rank, walk, seq, vertices).  Reference filter + order (ILP_index.cpp:670-716) for the ranks present."""
+    by_rank = {}
+    for h in hits:
+        by_rank.setdefault(h[0], []).append(h)
+    out, filtered = [], 0
+    thr = np.float32(T) * np.float32(n_walks_global)
+    for r in sorted(by_rank):
+        hs = sorted(by_rank[r], key=lambda x: (x[1], x[2]))            # insertion order: walk asc, path order
+        groups = {}
+        for h in hs:
+            groups.setdefault("".join(f"{v}_" for v in h[3]), []).append(h)
+        if any(np.float32(len(m)) >= thr for m in groups.values()):
+            filtered += 1
+            continue
+        per_walk = {}
+        for key in sorted(groups):                                      # std::map<std::string> order
+            for h in groups[key]:
+                per_walk.setdefault(h[1], []).append(h)
+        for wk in sorted(per_walk):
+            out.extend(per_walk[wk])
+    return out, filtered
+
+
+def main_cpu(name):
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo")
+    g, rd, k, w, T = load(name)
+    gs, rs, base = multi.shard_inputs(g, rd, rank, world)
+    empty = _abi.Graph(g.seg_off, g.seg_bases, np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint32), g.top_order_map)
+    local = phi_io.oracle_index(empty, rs, k, w, T).spectrum            # this rank's distinct read-minimizer hashes
+    owner = np.array([multi.owner_of_hash(h, world) for h in local], dtype=np.int64)
+    assert np.all(np.diff(owner) >= 0)                                  # range partition: owners ascend with the hash
+    send = [local[owner == o] for o in range(world)]
+    allsend = [None] * world
+    dist.all_gather_object(allsend, send)
+    mine = np.unique(np.concatenate([allsend[src][rank] for src in range(world)]))
+    slices = [None] * world
+    dist.all_gather_object(slices, mine)
+    spectrum = np.concatenate(slices)                                   # concatenation of range slices is globally sorted
+    own_off = np.concatenate([[0], np.cumsum([len(s) for s in slices])])
+    assert np.all(spectrum[1:] > spectrum[:-1])
+    sk, hashes = phi_io.oracle_sketch_walks(gs, k, w)
+    idx = np.searchsorted(spectrum, hashes)
+    idx[idx == len(spectrum)] = 0
+    hit = spectrum[idx] == hashes if len(spectrum) else np.zeros(len(hashes), dtype=bool)
+    off = sk.anchor_off.astype(np.int64)
+    hits = [(int(idx[a]), int(sk.anchor_walk[a]) + base, int(a), sk.anchor_vtx[off[a]:off[a + 1]].tolist()) for a in np.nonzero(hit)[0]]
+    route = [[h for h in hits if own_off[o] <= h[0] < own_off[o + 1]] for o in range(world)]
+    allroute = [None] * world
+    dist.all_gather_object(allroute, route)
+    owned = [h for src in range(world) for h in allroute[src][rank]]
+    kept, filtered = py_filter(owned, g.n_walks, T)
+    mpw = np.zeros(g.n_walks, dtype=np.uint64)
+    mpw[base:base + gs.n_walks] = sk.minimizers_per_walk
+    apw = np.bincount([h[1] for h in kept], minlength=g.n_walks).astype(np.uint64)
+    voff = np.concatenate([[0], np.cumsum([len(h[3]) for h in kept])]).astype(np.uint64)
+    part = _abi.IndexResultPy(
+        count_sp_r=len(spectrum), n_walks=g.n_walks, n_filtered=filtered, spectrum=spectrum,
+        anchor_rank=np.array([h[0] for h in kept], dtype=np.int32), anchor_walk=np.array([h[1] for h in kept], dtype=np.int32),
+        anchor_off=voff, anchor_vtx=np.array([v for h in kept for v in h[3]], dtype=np.int32),
+        minimizers_per_walk=mpw, anchors_per_walk=apw)
+    parts = [None] * world
+    dist.gather_object(part, parts if rank == 0 else None, dst=0)
+    if rank == 0:
+        got = multi.merge_results(parts)
+        want = phi_io.oracle_index(g, rd, k, w, T)
+        for f in ("spectrum", "anchor_rank", "anchor_walk", "anchor_off", "anchor_vtx", "minimizers_per_walk", "anchors_per_walk"):
+            assert np.array_equal(getattr(got, f), getattr(want, f)), f
+        assert got.n_filtered == want.n_filtered and got.count_sp_r == want.count_sp_r
+        print(f"MULTI_OK cpu world={world} case={name} spectrum={got.count_sp_r} anchors={got.n_anchors}")
+    dist.barrier()
+
+
+if __name__ == "__main__":
+    (main_gpu if sys.argv[1] == "gpu" else main_cpu)(sys.argv[2])
