@@ -128,6 +128,10 @@ typedef struct {
     float walk_kernel_ms;    /* the walk sketch kernel alone (roofline numerator's denominator) */
     float read_kernel_ms;    /* the read sketch kernel alone */
     uint64_t kernel_launches;/* kernels launched by this library during the run */
+    /* multi-GPU runs only (0 otherwise): parts of read_sketch.. and walk_sketch_ms spent in the NCCL exchanges */
+    float exchange_spectrum_ms; /* hash-range all-to-all + owner dedup/sort + slice broadcast */
+    float route_hits_ms;        /* bucketing hits by owner (count + scatter kernels) */
+    float exchange_hits_ms;     /* counts all-gather + all-to-all of the hit records + rebase */
 } phi_stage_times;
 
 typedef struct phi_gpu_index_ctx phi_gpu_index_ctx;

@@ -42,7 +42,8 @@ class StageTimes(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("graph_prep_ms", C.c_float), ("read_sketch_ms", C.c_float),
                 ("spectrum_ms", C.c_float), ("walk_sketch_ms", C.c_float), ("filter_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("walk_kernel_ms", C.c_float),
-                ("read_kernel_ms", C.c_float), ("kernel_launches", C.c_uint64)]
+                ("read_kernel_ms", C.c_float), ("kernel_launches", C.c_uint64),
+                ("exchange_spectrum_ms", C.c_float), ("route_hits_ms", C.c_float), ("exchange_hits_ms", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

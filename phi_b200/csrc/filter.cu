@@ -59,7 +59,7 @@ __global__ void group_count_kernel(FilterArgs A, FilterWork W)
             uint32_t old = atomicCAS(&W.g_rep[slot], G_EMPTY, (uint32_t)i);
             if (old == G_EMPTY) { rep = (uint32_t)i; atomicAdd(&W.ctr[CTR_GROUPS], 1ull); } else rep = old;
         }
-        if (rep == (uint32_t)i || same_list(A, (uint32_t)i, rep)) { atomicAdd(&W.g_cnt[slot], 1u); W.hit_slot[i] = (uint32_t)slot; return; }
+        if (rep == (uint32_t)i || same_list(A, (uint32_t)i, rep)) { atomicAdd(&W.g_cnt[slot], W.weight ? W.weight[i] : 1u); W.hit_slot[i] = (uint32_t)slot; return; }
         slot = (slot + 1) & mask;
     }
     W.ctr[CTR_GROUP_OVERFLOW] = 1;

@@ -114,6 +114,7 @@ struct FilterArgs {
 struct FilterWork {                  // device scratch, sized by the host
     uint32_t *g_rep, *g_cnt; uint64_t g_cap;      // group table
     uint32_t *hit_slot;                            // [n_hits] slot of each hit's group
+    const uint32_t *weight;                        // optional [n_hits]: occurrences a record stands for (multi-GPU summaries)
     uint8_t *rank_drop;                            // [n_ranks]
     uint32_t *flags;                               // [n_hits] survivor flags -> scanned
     uint64_t *keys_a, *keys_b; uint32_t *vals_a, *vals_b;   // [n_survivors]

@@ -42,7 +42,7 @@ struct DevBuf {                       // grow-only device buffer
 // pinned host buffer recycled through the ctx's pool (result arrays land here: D2H at full PCIe speed, no staging copy)
 struct PinnedBuf { void *p = nullptr; size_t cap = 0; };
 
-enum { EV_START, EV_H2D, EV_PREP, EV_READS, EV_SPECTRUM, EV_WALKS, EV_FILTER, EV_END, EV_RK0, EV_RK1, EV_WK0, EV_WK1, EV_COUNT };
+enum { EV_START, EV_H2D, EV_PREP, EV_READS, EV_SPECTRUM, EV_WALKS, EV_FILTER, EV_END, EV_RK0, EV_RK1, EV_WK0, EV_WK1, EV_XS0, EV_XS1, EV_XH0, EV_XH1, EV_XH2, EV_COUNT };
 
 }  // namespace
 
@@ -74,7 +74,7 @@ struct phi_gpu_index_ctx {
     int rank = 0, world = 1; uint32_t walk_id_base = 0, n_walks_global = 0;
     void *comm = nullptr;
     uint64_t gcap_hint = 0;              // group-table size that worked last time
-    DevBuf xk_a, xk_b, xcnt, xoff, ag_send, ag_recv, r_rank, r_walk, r_pos, r_voff, r_nv, r_vtx, s_rank, s_walk, s_pos, s_voff, s_nv, s_vtx;
+    DevBuf xk_a, xk_b, xcnt, xoff, ag_send, ag_recv, m_rank, m_cnt, m_voff, m_nv, r_rank, r_walk, r_pos, r_voff, r_nv, r_vtx, s_rank, s_walk, s_pos, s_voff, s_nv, s_vtx;
     std::vector<uint64_t> own_off;       // [world + 1] first global rank owned by each GPU (multi-GPU runs)
 
     int fail(int code, const std::string &m) { err = m; return code; }
@@ -512,52 +512,76 @@ static int exchange_spectrum(phi_gpu_index_ctx *ctx, uint64_t n_local, uint64_t 
     return PHI_OK;
 }
 
-// ---- hit routing
-__global__ void route_count_kernel(const uint32_t *hit_rank, const uint8_t *hit_nv, uint64_t n, const uint64_t *own_off, int world,
-                                   unsigned long long *cnt /* [2*world]: hits, vertices */)
+// ---- record routing (hits or group summaries) to the owner of their rank
+constexpr int ROUTE_ITEMS = 8;                      // records per thread: 2048 per block -> few global atomics
+struct RouteIn {
+    const uint32_t *rank, *walk, *pos; const uint64_t *voff; const uint8_t *nv; const int32_t *vtx;
+    uint64_t n;
+    const uint8_t *drop;                            // optional: records whose rank is flagged are not routed
+};
+__device__ __forceinline__ int owner_of_rank(const uint64_t *own_off, int world, uint64_t r)
+{
+    int o = 0;
+    while (o + 1 < world && own_off[o + 1] <= r) ++o;
+    return o;
+}
+__global__ void __launch_bounds__(256) route_count_kernel(RouteIn I, const uint64_t *own_off, int world, unsigned long long *cnt /* [2*world] */)
 {
     __shared__ unsigned long long sh[128];
     for (int i = threadIdx.x; i < 2 * world; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n) {
-        uint64_t r = hit_rank[i]; int o = 0;
-        while (o + 1 < world && own_off[o + 1] <= r) ++o;
-        atomicAdd(&sh[o], 1ull); atomicAdd(&sh[world + o], (unsigned long long)hit_nv[i]);
+    const uint64_t base = (uint64_t)blockIdx.x * (256 * ROUTE_ITEMS);
+    #pragma unroll
+    for (int it = 0; it < ROUTE_ITEMS; ++it) {
+        uint64_t i = base + it * 256 + threadIdx.x;
+        int o = -1; uint32_t nv = 0;
+        if (i < I.n) { uint32_t r = I.rank[i]; if (!I.drop || !I.drop[r]) { o = owner_of_rank(own_off, world, r); nv = I.nv[i]; } }
+        // warp-aggregated: one shared-memory atomic per distinct owner per warp
+        uint32_t peers = __match_any_sync(0xFFFFFFFFu, o);
+        if (o >= 0) { atomicAdd(&sh[world + o], (unsigned long long)nv); if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[o], (unsigned long long)__popc(peers)); }
     }
     __syncthreads();
     for (int j = threadIdx.x; j < 2 * world; j += blockDim.x) if (sh[j]) atomicAdd(&cnt[j], sh[j]);
 }
 
-struct RouteArgs {
-    const uint32_t *hit_rank, *hit_walk, *hit_pos; const uint64_t *hit_voff; const uint8_t *hit_nv; const int32_t *vtx;
-    uint64_t n; const uint64_t *own_off; int world;
-    unsigned long long *cursor;                   // [2*world] running (hits, vertices) per owner, initialised with the segment starts
+struct RouteOut {
+    unsigned long long *cursor;                   // [2*world] running (records, vertices) per owner, initialised with the segment starts
     const uint64_t *vtx_seg_start;                // [world] start of each owner's vertex segment in s_vtx
     uint32_t *s_rank, *s_walk, *s_pos; uint64_t *s_voff; uint8_t *s_nv; int32_t *s_vtx;
 };
-__global__ void route_scatter_kernel(RouteArgs A)
+__global__ void __launch_bounds__(256) route_scatter_kernel(RouteIn I, RouteOut O, const uint64_t *own_off, int world)
 {
     __shared__ unsigned long long sh_cnt[128], sh_base[128];
-    for (int i = threadIdx.x; i < 2 * A.world; i += blockDim.x) sh_cnt[i] = 0;
+    for (int i = threadIdx.x; i < 2 * world; i += blockDim.x) sh_cnt[i] = 0;
     __syncthreads();
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    int o = 0; unsigned long long lh = 0, lv = 0; uint32_t nv = 0;
-    if (i < A.n) {
-        uint64_t r = A.hit_rank[i];
-        while (o + 1 < A.world && A.own_off[o + 1] <= r) ++o;
-        nv = A.hit_nv[i];
-        lh = atomicAdd(&sh_cnt[o], 1ull); lv = atomicAdd(&sh_cnt[A.world + o], (unsigned long long)nv);
+    const uint64_t base = (uint64_t)blockIdx.x * (256 * ROUTE_ITEMS);
+    int own[ROUTE_ITEMS]; uint32_t lh[ROUTE_ITEMS], lv[ROUTE_ITEMS];
+    #pragma unroll
+    for (int it = 0; it < ROUTE_ITEMS; ++it) {
+        uint64_t i = base + it * 256 + threadIdx.x;
+        own[it] = -1; lh[it] = lv[it] = 0;
+        if (i < I.n) {
+            uint32_t r = I.rank[i];
+            if (!I.drop || !I.drop[r]) {
+                int o = own[it] = owner_of_rank(own_off, world, r);
+                lh[it] = (uint32_t)atomicAdd(&sh_cnt[o], 1ull); lv[it] = (uint32_t)atomicAdd(&sh_cnt[world + o], (unsigned long long)I.nv[i]);
+            }
+        }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < 2 * A.world; j += blockDim.x) sh_base[j] = sh_cnt[j] ? atomicAdd(&A.cursor[j], sh_cnt[j]) : 0ull;
+    for (int j = threadIdx.x; j < 2 * world; j += blockDim.x) sh_base[j] = sh_cnt[j] ? atomicAdd(&O.cursor[j], sh_cnt[j]) : 0ull;
     __syncthreads();
-    if (i < A.n) {
-        unsigned long long dh = sh_base[o] + lh, dv = sh_base[A.world + o] + lv;
-        A.s_rank[dh] = A.hit_rank[i]; A.s_walk[dh] = A.hit_walk[i]; A.s_pos[dh] = A.hit_pos[i]; A.s_nv[dh] = (uint8_t)nv;
-        A.s_voff[dh] = dv - A.vtx_seg_start[o];                       // relative to the (src -> owner) vertex segment
-        const int32_t *src = A.vtx + A.hit_voff[i];
-        for (uint32_t q = 0; q < nv; ++q) A.s_vtx[dv + q] = src[q];
+    #pragma unroll
+    for (int it = 0; it < ROUTE_ITEMS; ++it) {
+        if (own[it] < 0) continue;
+        const uint64_t i = base + it * 256 + threadIdx.x;
+        const int o = own[it];
+        const unsigned long long dh = sh_base[o] + lh[it], dv = sh_base[world + o] + lv[it];
+        const uint32_t nv = I.nv[i];
+        O.s_rank[dh] = I.rank[i]; O.s_walk[dh] = I.walk[i]; O.s_pos[dh] = I.pos[i]; O.s_nv[dh] = (uint8_t)nv;
+        O.s_voff[dh] = dv - O.vtx_seg_start[o];                       // relative to the (src -> owner) vertex segment
+        const int32_t *src = I.vtx + I.voff[i];
+        for (uint32_t q = 0; q < nv; ++q) O.s_vtx[dv + q] = src[q];
     }
 }
 __global__ void rebase_voff_kernel(uint64_t *voff, uint64_t n, const uint64_t *hit_seg_off, const uint64_t *vtx_seg_off, int world)
@@ -569,13 +593,14 @@ __global__ void rebase_voff_kernel(uint64_t *voff, uint64_t n, const uint64_t *h
     voff[i] += vtx_seg_off[p];
 }
 
-// hits (ctx->hit_*) -> owner of their rank; afterwards ctx->hit_* hold the hits this GPU owns
-static int exchange_hits(phi_gpu_index_ctx *ctx, RunOut &o)
+// Route the records of `I` to the owners of their ranks.  Received records land in ctx->r_* (rh records, rv vertices).
+static int exchange_records(phi_gpu_index_ctx *ctx, const RouteIn &I, uint64_t &rh, uint64_t &rv)
 {
     std::string err; NcclApi *nc = nccl_api(err);
     if (!nc || !ctx->comm) return ctx->fail(PHI_ERR_COMM, "communicator not initialised");
     const int W = ctx->world, me = ctx->rank;
-    const uint64_t n = o.n_hits;
+    const uint64_t n = I.n;
+    const unsigned nblk = (unsigned)((n + 256 * ROUTE_ITEMS - 1) / (256 * ROUTE_ITEMS));
     CU(ctx->xcnt.reserve(8192));
     uint64_t *d_own = ctx->xcnt.as<uint64_t>();                        // [W+1] own_off | [2W] counts | [2W] cursors | [W] vtx seg start | recv seg offs
     unsigned long long *d_cnt = (unsigned long long *)(d_own + 65), *d_cur = d_cnt + 128;
@@ -583,7 +608,7 @@ static int exchange_hits(phi_gpu_index_ctx *ctx, RunOut &o)
     CU(cudaMemcpyAsync(d_own, ctx->own_off.data(), (W + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemsetAsync(d_cnt, 0, 2 * W * 8, ctx->st));
     if (n) {
-        route_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(ctx->hit_rank.as<uint32_t>(), ctx->hit_nv.as<uint8_t>(), n, d_own, W, d_cnt);
+        route_count_kernel<<<nblk, 256, 0, ctx->st>>>(I, d_own, W, d_cnt);
         CU(cudaGetLastError()); ctx->launches++;
     }
     std::vector<uint64_t> cnt(2 * W, 0), all;
@@ -597,13 +622,11 @@ static int exchange_hits(phi_gpu_index_ctx *ctx, RunOut &o)
     CU(cudaMemcpyAsync(d_cur, cur.data(), 2 * W * 8, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(d_vseg, sv_off.data(), W * 8, cudaMemcpyHostToDevice, ctx->st));
     if (n) {
-        RouteArgs A;
-        A.hit_rank = ctx->hit_rank.as<uint32_t>(); A.hit_walk = ctx->hit_walk.as<uint32_t>(); A.hit_pos = ctx->hit_pos.as<uint32_t>();
-        A.hit_voff = ctx->hit_voff.as<uint64_t>(); A.hit_nv = ctx->hit_nv.as<uint8_t>(); A.vtx = ctx->vtx_pool.as<int32_t>();
-        A.n = n; A.own_off = d_own; A.world = W; A.cursor = d_cur; A.vtx_seg_start = d_vseg;
-        A.s_rank = ctx->s_rank.as<uint32_t>(); A.s_walk = ctx->s_walk.as<uint32_t>(); A.s_pos = ctx->s_pos.as<uint32_t>();
-        A.s_voff = ctx->s_voff.as<uint64_t>(); A.s_nv = ctx->s_nv.as<uint8_t>(); A.s_vtx = ctx->s_vtx.as<int32_t>();
-        route_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(A);
+        RouteOut O;
+        O.cursor = d_cur; O.vtx_seg_start = d_vseg;
+        O.s_rank = ctx->s_rank.as<uint32_t>(); O.s_walk = ctx->s_walk.as<uint32_t>(); O.s_pos = ctx->s_pos.as<uint32_t>();
+        O.s_voff = ctx->s_voff.as<uint64_t>(); O.s_nv = ctx->s_nv.as<uint8_t>(); O.s_vtx = ctx->s_vtx.as<int32_t>();
+        route_scatter_kernel<<<nblk, 256, 0, ctx->st>>>(I, O, d_own, W);
         CU(cudaGetLastError()); ctx->launches++;
     }
     int rc = allgather_host_u64(ctx, nc, cnt, all);                     // all[src * 2W + {dst, W + dst}]
@@ -613,8 +636,8 @@ static int exchange_hits(phi_gpu_index_ctx *ctx, RunOut &o)
         rh_cnt[p] = all[(size_t)p * 2 * W + me]; rv_cnt[p] = all[(size_t)p * 2 * W + W + me];
         rh_off[p + 1] = rh_off[p] + rh_cnt[p]; rv_off[p + 1] = rv_off[p] + rv_cnt[p];
     }
-    const uint64_t rh = rh_off[W], rv = rv_off[W];
-    if (rh >= (1ull << 32)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-1 hits routed to one GPU");
+    rh = rh_off[W]; rv = rv_off[W];
+    if (rh >= (1ull << 32)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-1 records routed to one GPU");
     CU(ctx->r_rank.reserve(rh * 4 + 4)); CU(ctx->r_walk.reserve(rh * 4 + 4)); CU(ctx->r_pos.reserve(rh * 4 + 4));
     CU(ctx->r_voff.reserve(rh * 8 + 8)); CU(ctx->r_nv.reserve(rh + 4)); CU(ctx->r_vtx.reserve(rv * 4 + 4));
     NC(nc->GroupStart());
@@ -633,9 +656,6 @@ static int exchange_hits(phi_gpu_index_ctx *ctx, RunOut &o)
         CU(cudaGetLastError()); ctx->launches++;
     }
     CU(cudaStreamSynchronize(ctx->st));                                  // host vectors above were the source of async copies
-    std::swap(ctx->hit_rank, ctx->r_rank); std::swap(ctx->hit_walk, ctx->r_walk); std::swap(ctx->hit_pos, ctx->r_pos);
-    std::swap(ctx->hit_voff, ctx->r_voff); std::swap(ctx->hit_nv, ctx->r_nv); std::swap(ctx->vtx_pool, ctx->r_vtx);
-    o.n_hits = rh; o.n_hit_vtx = rv;
     return PHI_OK;
 }
 
@@ -693,8 +713,10 @@ static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbi
         CU(ctx->spec_a.reserve(8));
     }
     if (ctx->world > 1) {                                                 // every rank takes part, also with zero local reads
+        CU(cudaEventRecord(ctx->ev[EV_XS0], ctx->st));
         int rc = exchange_spectrum(ctx, n_spec, n_spec);
         if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev[EV_XS1], ctx->st));
         if (n_spec >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^31-1 distinct read minimizers (count_sp_r is int32 in the reference)");
     }
     o.n_spec = (uint32_t)n_spec;
@@ -760,38 +782,29 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
 }
 
 // ---- stage: threshold filter, final order, CSR
-static int stage_filter(phi_gpu_index_ctx *ctx, const std::vector<uint64_t> &h_walk_gbase, uint32_t n_walks_global, float threshold, RunOut &o)
+static void filter_args(phi_gpu_index_ctx *ctx, FilterArgs &A, uint64_t n, uint32_t n_spec, float threshold, uint32_t n_walks_global,
+                        const std::vector<uint64_t> &h_walk_gbase)
 {
-    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
-    const uint64_t n = o.n_hits;
-    CU(ctx->apw.reserve(((size_t)n_walks_global + 1) * 8));
-    CU(cudaMemsetAsync(ctx->apw.p, 0, ((size_t)n_walks_global + 1) * 8, ctx->st));
-    CU(cudaMemsetAsync(d_ctr + CTR_FILTERED, 0, 3 * 8, ctx->st));        // FILTERED, SURVIVORS, BIG_GROUPS
-    CU(ctx->rank_drop.reserve((size_t)o.n_spec + 4));
-    CU(cudaMemsetAsync(ctx->rank_drop.p, 0, (size_t)o.n_spec + 4, ctx->st));
-    CU(ctx->anchor_off.reserve(8));
-    o.n_surv = 0; o.n_anchor_vtx = 0; o.n_filtered = 0;
-    if (!n) { CU(cudaMemsetAsync(ctx->anchor_off.p, 0, 8, ctx->st)); return PHI_OK; }
-
-    FilterArgs A;
     A.n_hits = n; A.hit_rank = ctx->hit_rank.as<uint32_t>(); A.hit_walk = ctx->hit_walk.as<uint32_t>(); A.hit_pos = ctx->hit_pos.as<uint32_t>();
     A.hit_voff = ctx->hit_voff.as<uint64_t>(); A.hit_nv = ctx->hit_nv.as<uint8_t>(); A.vtx_pool = ctx->vtx_pool.as<int32_t>();
-    A.n_ranks = o.n_spec;
+    A.n_ranks = n_spec;
     A.thr = threshold * (float)n_walks_global;                            // float * uint32 -> float, as ILP_index.cpp:698
-    CU(ctx->walk_gbase.reserve(h_walk_gbase.size() * 8));
-    CU(cudaMemcpyAsync(ctx->walk_gbase.p, h_walk_gbase.data(), h_walk_gbase.size() * 8, cudaMemcpyHostToDevice, ctx->st));
     A.walk_gbase = ctx->walk_gbase.as<uint64_t>();
-    A.gpos_bits = bits_for(h_walk_gbase.back()); A.rank_bits = bits_for(o.n_spec ? o.n_spec - 1 : 0);
+    A.gpos_bits = bits_for(h_walk_gbase.back()); A.rank_bits = bits_for(n_spec ? n_spec - 1 : 0);
+}
 
-    FilterWork W;
-    // group table: distinct (rank, vertex list) groups are usually far fewer than hits (one group per locus shared by many
-    // walks), so start small and grow on overflow instead of paying for a 2n-slot table every run
+// group table over the records of A (weight[i] occurrences each, 1 if weight == nullptr); fills W.hit_slot / g_rep / g_cnt
+static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, FilterWork &W, const uint32_t *weight)
+{
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    const uint64_t n = A.n_hits;
+    // distinct (rank, vertex list) groups are usually far fewer than hits (one group per locus shared by many walks),
+    // so start small and grow on overflow instead of paying for a 2n-slot table every run
     uint64_t gcap = 1024; while (gcap < n / 4) gcap <<= 1;
     if (ctx->gcap_hint > gcap) gcap = ctx->gcap_hint;
-    CU(ctx->flags.reserve(n * 4 + 4)); CU(ctx->vals_b.reserve(n * 4 + 4));
+    CU(ctx->vals_b.reserve(n * 4 + 4));
     W.hit_slot = ctx->vals_b.as<uint32_t>();                              // free until the survivor sort
-    W.rank_drop = ctx->rank_drop.as<uint8_t>(); W.flags = ctx->flags.as<uint32_t>(); W.ctr = d_ctr;
-    W.keys_a = W.keys_b = nullptr; W.vals_a = W.vals_b = nullptr; W.sort_scratch = nullptr; W.scan_scratch = nullptr;
+    W.weight = weight;
     for (;;) {
         CU(ctx->g_rep.reserve(gcap * 4)); CU(ctx->g_cnt.reserve(gcap * 4));
         CU(fill_u32(ctx->g_rep.as<uint32_t>(), gcap, 0xFFFFFFFFu, ctx->st, &ctx->launches));
@@ -804,12 +817,21 @@ static int stage_filter(phi_gpu_index_ctx *ctx, const std::vector<uint64_t> &h_w
         gcap <<= 2;
         ctx->gcap_hint = gcap;
     }
-    CU(filter_mark_drops(A, W, ctx->st, &ctx->launches));
+    return PHI_OK;
+}
+
+// survivors (records of A whose rank is not flagged in rank_drop) -> final (rank, walk, j) order -> CSR in ctx->anchor_*
+static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, FilterWork &W, uint32_t n_walks_global, RunOut &o)
+{
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    const uint64_t n = A.n_hits;
+    CU(cudaMemsetAsync(d_ctr + CTR_SURVIVORS, 0, 2 * 8, ctx->st));        // SURVIVORS, BIG_GROUPS
+    CU(ctx->flags.reserve(n * 4 + 4));
+    W.flags = ctx->flags.as<uint32_t>();
     CU(filter_flag_survivors(A, W, ctx->st, &ctx->launches));
     CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(n), scan_u32_to_u64_scratch(n + 1))));
     CU(scan_u32_inplace(W.flags, n, ctx->scan_scr.p, ctx->st, &ctx->launches));
     CU(read_counters(ctx));
-    o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED];
     const uint64_t ns = ctx->h_ctr[CTR_SURVIVORS];
     o.n_surv = ns;
     if (!ns) { CU(cudaMemsetAsync(ctx->anchor_off.p, 0, 8, ctx->st)); return PHI_OK; }
@@ -843,6 +865,118 @@ static int stage_filter(phi_gpu_index_ctx *ctx, const std::vector<uint64_t> &h_w
     CU(filter_csr_fill(A, order, ns, ctx->anchor_off.as<uint64_t>(), ctx->anchor_rank.as<int32_t>(), ctx->anchor_walk.as<int32_t>(),
                        ctx->anchor_vtx.as<int32_t>(), ctx->apw.as<unsigned long long>(), ctx->walk_id_base, n_walks_global, ctx->st, &ctx->launches));
     return PHI_OK;
+}
+
+__global__ void summary_flags_kernel(const uint32_t *g_rep, const uint32_t *hit_slot, uint64_t n, uint32_t *flags)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = g_rep[hit_slot[i]] == (uint32_t)i ? 1u : 0u;
+}
+// one summary per local group: (rank, count, vertex list of the representative)
+__global__ void summary_emit_kernel(FilterArgs A, const uint32_t *g_rep, const uint32_t *g_cnt, const uint32_t *hit_slot, const uint64_t *pos,
+                                    uint32_t *m_rank, uint32_t *m_cnt, uint64_t *m_voff, uint8_t *m_nv)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= A.n_hits) return;
+    uint32_t slot = hit_slot[i];
+    if (g_rep[slot] != (uint32_t)i) return;
+    uint64_t j = pos[i];
+    m_rank[j] = A.hit_rank[i]; m_cnt[j] = g_cnt[slot]; m_voff[j] = A.hit_voff[i]; m_nv[j] = A.hit_nv[i];
+}
+
+static int stage_filter(phi_gpu_index_ctx *ctx, const std::vector<uint64_t> &h_walk_gbase, uint32_t n_walks_global, float threshold, RunOut &o)
+{
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    CU(ctx->apw.reserve(((size_t)n_walks_global + 1) * 8));
+    CU(cudaMemsetAsync(ctx->apw.p, 0, ((size_t)n_walks_global + 1) * 8, ctx->st));
+    CU(cudaMemsetAsync(d_ctr + CTR_FILTERED, 0, 3 * 8, ctx->st));        // FILTERED, SURVIVORS, BIG_GROUPS
+    CU(ctx->rank_drop.reserve((size_t)o.n_spec + 4));
+    CU(cudaMemsetAsync(ctx->rank_drop.p, 0, (size_t)o.n_spec + 4, ctx->st));
+    CU(ctx->anchor_off.reserve(8));
+    CU(cudaMemsetAsync(ctx->anchor_off.p, 0, 8, ctx->st));
+    CU(ctx->walk_gbase.reserve(h_walk_gbase.size() * 8));
+    CU(cudaMemcpyAsync(ctx->walk_gbase.p, h_walk_gbase.data(), h_walk_gbase.size() * 8, cudaMemcpyHostToDevice, ctx->st));
+    o.n_surv = 0; o.n_anchor_vtx = 0; o.n_filtered = 0;
+    FilterArgs A; FilterWork W; memset(&W, 0, sizeof(W));
+    W.rank_drop = ctx->rank_drop.as<uint8_t>(); W.ctr = d_ctr;
+
+    if (ctx->world == 1) {
+        const uint64_t n = o.n_hits;
+        if (!n) return PHI_OK;
+        filter_args(ctx, A, n, o.n_spec, threshold, n_walks_global, h_walk_gbase);
+        int rc = count_groups_adaptive(ctx, A, W, nullptr);
+        if (rc) return rc;
+        CU(filter_mark_drops(A, W, ctx->st, &ctx->launches));
+        rc = order_and_csr(ctx, A, W, n_walks_global, o);
+        o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED];
+        return rc;
+    }
+
+    // ---- multi-GPU, two phases (every rank takes part in every collective, also with zero hits):
+    //  A. local groups -> one (rank, count, list) summary per group -> owner of the rank adds the counts up, applies the
+    //     threshold, and the drop flags of all owners are shared;
+    //  B. only surviving hits travel to the owner of their rank, which orders them and builds its slice of the CSR.
+    std::string err; NcclApi *nc = nccl_api(err);
+    if (!nc || !ctx->comm) return ctx->fail(PHI_ERR_COMM, "communicator not initialised");
+    const int Wn = ctx->world, me = ctx->rank;
+    const uint64_t n = o.n_hits;
+    CU(cudaEventRecord(ctx->ev[EV_XH0], ctx->st));
+    filter_args(ctx, A, n, o.n_spec, threshold, n_walks_global, h_walk_gbase);
+    uint64_t n_sum = 0;
+    if (n) {
+        int rc = count_groups_adaptive(ctx, A, W, nullptr);
+        if (rc) return rc;
+        CU(ctx->flags.reserve(n * 4 + 4)); CU(ctx->flags64.reserve((n + 1) * 8));
+        CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(n), scan_u32_to_u64_scratch(n + 1))));
+        summary_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(W.g_rep, W.hit_slot, n, ctx->flags.as<uint32_t>());
+        CU(cudaGetLastError()); ctx->launches++;
+        CU(scan_u32_to_u64(ctx->flags.as<uint32_t>(), ctx->flags64.as<uint64_t>(), n, ctx->scan_scr.p, ctx->st, &ctx->launches));
+        n_sum = ctx->h_ctr[CTR_GROUPS];                                   // distinct local groups (read by count_groups_adaptive)
+        CU(ctx->m_rank.reserve(n_sum * 4 + 4)); CU(ctx->m_cnt.reserve(n_sum * 4 + 4)); CU(ctx->m_voff.reserve(n_sum * 8 + 8)); CU(ctx->m_nv.reserve(n_sum + 4));
+        summary_emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(A, W.g_rep, W.g_cnt, W.hit_slot, ctx->flags64.as<uint64_t>(),
+                                                                             ctx->m_rank.as<uint32_t>(), ctx->m_cnt.as<uint32_t>(), ctx->m_voff.as<uint64_t>(), ctx->m_nv.as<uint8_t>());
+        CU(cudaGetLastError()); ctx->launches++;
+    }
+    RouteIn I;
+    I.rank = ctx->m_rank.as<uint32_t>(); I.walk = ctx->m_cnt.as<uint32_t>(); I.pos = ctx->m_cnt.as<uint32_t>(); I.voff = ctx->m_voff.as<uint64_t>();
+    I.nv = ctx->m_nv.as<uint8_t>(); I.vtx = ctx->vtx_pool.as<int32_t>(); I.n = n_sum; I.drop = nullptr;
+    uint64_t rs = 0, rsv = 0;
+    int rc = exchange_records(ctx, I, rs, rsv);
+    if (rc) return rc;
+    if (rs) {                                                             // owner: add the partial counts up, apply the threshold
+        FilterArgs B = A;
+        B.n_hits = rs; B.hit_rank = ctx->r_rank.as<uint32_t>(); B.hit_walk = ctx->r_walk.as<uint32_t>(); B.hit_pos = ctx->r_pos.as<uint32_t>();
+        B.hit_voff = ctx->r_voff.as<uint64_t>(); B.hit_nv = ctx->r_nv.as<uint8_t>(); B.vtx_pool = ctx->r_vtx.as<int32_t>();
+        FilterWork WB; memset(&WB, 0, sizeof(WB));
+        WB.rank_drop = ctx->rank_drop.as<uint8_t>(); WB.ctr = d_ctr;
+        rc = count_groups_adaptive(ctx, B, WB, ctx->r_walk.as<uint32_t>());
+        if (rc) return rc;
+        CU(filter_mark_drops(B, WB, ctx->st, &ctx->launches));             // also counts the flags (all in this rank's owned range)
+    }
+    CU(read_counters(ctx));
+    o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED];
+    NC(nc->GroupStart());                                                   // share the drop flags: owner o holds the truth for its rank range
+    for (int q = 0; q < Wn; ++q) {
+        const uint64_t lo = ctx->own_off[q], cnt = ctx->own_off[q + 1] - lo;
+        if (cnt) NC(nc->Broadcast(ctx->rank_drop.as<uint8_t>() + lo, ctx->rank_drop.as<uint8_t>() + lo, cnt, ncclUint8, q, (ncclComm_t)ctx->comm, ctx->st));
+    }
+    NC(nc->GroupEnd());
+    CU(cudaEventRecord(ctx->ev[EV_XH1], ctx->st));
+    (void)me;
+    // B: surviving hits -> owners
+    RouteIn J;
+    J.rank = A.hit_rank; J.walk = A.hit_walk; J.pos = A.hit_pos; J.voff = A.hit_voff; J.nv = A.hit_nv; J.vtx = A.vtx_pool; J.n = n;
+    J.drop = ctx->rank_drop.as<uint8_t>();
+    uint64_t rh = 0, rv = 0;
+    rc = exchange_records(ctx, J, rh, rv);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[EV_XH2], ctx->st));
+    std::swap(ctx->hit_rank, ctx->r_rank); std::swap(ctx->hit_walk, ctx->r_walk); std::swap(ctx->hit_pos, ctx->r_pos);
+    std::swap(ctx->hit_voff, ctx->r_voff); std::swap(ctx->hit_nv, ctx->r_nv); std::swap(ctx->vtx_pool, ctx->r_vtx);
+    o.n_hit_vtx = rv;
+    if (!rh) return PHI_OK;
+    filter_args(ctx, A, rh, o.n_spec, threshold, n_walks_global, h_walk_gbase);
+    return order_and_csr(ctx, A, W, n_walks_global, o);
 }
 
 // A result owns pinned buffers borrowed from its ctx's pool; freeing it hands them back (or releases them if the ctx is gone).
@@ -926,6 +1060,12 @@ static void collect_times(phi_gpu_index_ctx *ctx, float h2d_ms)
     t.walk_kernel_ms = el(EV_WK0, EV_WK1);
     t.read_kernel_ms = el(EV_RK0, EV_RK1);
     t.kernel_launches = ctx->launches;
+    t.exchange_spectrum_ms = t.route_hits_ms = t.exchange_hits_ms = 0.f;
+    if (ctx->world > 1) {
+        t.exchange_spectrum_ms = el(EV_XS0, EV_XS1);
+        t.route_hits_ms = el(EV_XH0, EV_XH1);
+        t.exchange_hits_ms = el(EV_XH1, EV_XH2);
+    }
 }
 
 static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int mode, int do_download, phi_index_result **out,
@@ -958,10 +1098,6 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     CU(cudaEventRecord(ctx->ev[EV_SPECTRUM], ctx->st));
     rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, max_tiles, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, o);
     if (rc) return rc;
-    if (ctx->world > 1 && mode == WALK_MODE_PROBE) {
-        rc = exchange_hits(ctx, o);
-        if (rc) return rc;
-    }
     CU(cudaEventRecord(ctx->ev[EV_WALKS], ctx->st));
 
     const uint32_t H = ctx->n_walks;
