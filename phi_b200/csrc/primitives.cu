@@ -97,6 +97,7 @@ cudaError_t scan_u32_inplace(uint32_t *data, uint64_t n, void *scratch, cudaStre
 
 // ------------------------------------------------------------------ radix sort
 constexpr int RS_T = 256, RS_I = 16, RS_B = RS_T * RS_I, RS_WARPS = RS_T / 32;
+constexpr size_t RS_SMEM = (size_t)RS_B * 12;          // staged keys (8 B) + values (4 B)
 
 __global__ void __launch_bounds__(RS_T) radix_hist_kernel(const uint64_t *keys, uint64_t n, int shift, uint32_t *hist, uint32_t nb)
 {
@@ -113,15 +114,24 @@ __global__ void __launch_bounds__(RS_T) radix_hist_kernel(const uint64_t *keys, 
     hist[(uint64_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
 }
 
+// One pass of the stable LSD sort.  Ranking: every warp owns a contiguous 512-key slice of the block's 4096 keys and ranks
+// it round by round with __match_any_sync (equal digits -> one leader bumps the warp's counter); a 256-thread pass turns
+// the per-warp counters into block-wide exclusive offsets.  Scatter: keys (and values) are first placed at their
+// block-local sorted position in shared memory, then written out so that consecutive threads write consecutive
+// addresses of one digit run (coalesced), instead of 32 scattered 8-byte stores per warp.
 __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
                                                            uint32_t *vals_out, uint64_t n, int shift, const uint32_t *hist, uint32_t nb)
 {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint64_t *skey = (uint64_t *)rs_smem;                                  // [RS_B]
+    uint32_t *sval = (uint32_t *)(rs_smem + (size_t)RS_B * 8);             // [RS_B] (only touched when vals_in != nullptr)
     __shared__ uint32_t wcount[RS_WARPS][257];
-    __shared__ uint32_t gbase[256];
+    __shared__ uint32_t gbase[256], dstart[257];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_T) (&wcount[0][0])[i] = 0;
     __syncthreads();
-    const uint64_t base = (uint64_t)blockIdx.x * RS_B + (uint64_t)wid * (RS_I * 32);
+    const uint64_t blk0 = (uint64_t)blockIdx.x * RS_B;
+    const uint64_t base = blk0 + (uint64_t)wid * (RS_I * 32);
     uint64_t key[RS_I]; uint16_t rk[RS_I];
     #pragma unroll
     for (int r = 0; r < RS_I; ++r) {
@@ -138,11 +148,25 @@ __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const uint64_t *key
         __syncwarp();
     }
     __syncthreads();
-    {
+    {   // per digit: exclusive offsets of the warps inside the block, block total -> dstart (scanned below)
         uint32_t d = threadIdx.x, run = 0;
         #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
         gbase[d] = hist[(uint64_t)d * nb + blockIdx.x];
+        dstart[d] = run;
+    }
+    __syncthreads();
+    if (wid == 0) {                                                        // exclusive scan of the 256 digit totals (8 per lane)
+        uint32_t v[8], sum = 0;
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] = dstart[lane * 8 + i]; sum += v[i]; }
+        uint32_t inc = sum;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+        uint32_t ex = inc - sum;
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) { dstart[lane * 8 + i] = ex; ex += v[i]; }
+        if (lane == 31) dstart[256] = inc;
     }
     __syncthreads();
     #pragma unroll
@@ -150,10 +174,19 @@ __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const uint64_t *key
         uint64_t idx = base + r * 32 + lane;
         if (idx < n) {
             uint32_t d = (uint32_t)((key[r] >> shift) & 255);
-            uint32_t dst = gbase[d] + wcount[wid][d] + rk[r];
-            keys_out[dst] = key[r];
-            if (vals_in) vals_out[dst] = vals_in[idx];
+            uint32_t loc = dstart[d] + wcount[wid][d] + rk[r];             // block-local sorted position
+            skey[loc] = key[r];
+            if (vals_in) sval[loc] = vals_in[idx];
         }
+    }
+    __syncthreads();
+    const uint32_t cnt = dstart[256];
+    for (uint32_t i = threadIdx.x; i < cnt; i += RS_T) {
+        uint64_t k = skey[i];
+        uint32_t d = (uint32_t)((k >> shift) & 255);
+        uint32_t dst = gbase[d] + (i - dstart[d]);
+        keys_out[dst] = k;
+        if (vals_in) vals_out[dst] = sval[i];
     }
 }
 
@@ -168,6 +201,14 @@ cudaError_t radix_sort_u64(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a,
 {
     if (n <= 1 || bit_hi <= bit_lo) return cudaSuccess;
     if (n >= (1ull << 32)) return cudaErrorInvalidValue;
+    {
+        static bool attr_set = false;                                      // 48 KB staging + 9 KB static shared memory > the 48 KB default
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+    }
     const uint32_t nb = (uint32_t)((n + RS_B - 1) / RS_B);
     uint32_t *hist = (uint32_t *)scratch;
     void *scan_scr = (void *)(hist + (size_t)256 * nb);
@@ -178,7 +219,7 @@ cudaError_t radix_sort_u64(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a,
         PHI_LAUNCH_CHECK();
         cudaError_t e = scan_u32_inplace(hist, (uint64_t)256 * nb, scan_scr, st, launches);
         if (e != cudaSuccess) return e;
-        radix_scatter_kernel<<<nb, RS_T, 0, st>>>(kin, vin, kout, vout, n, shift, hist, nb);
+        radix_scatter_kernel<<<nb, RS_T, RS_SMEM, st>>>(kin, vin, kout, vout, n, shift, hist, nb);
         PHI_LAUNCH_CHECK();
         uint64_t *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;
