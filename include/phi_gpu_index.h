@@ -170,6 +170,24 @@ void phi_gpu_host_free(void *p);
 int phi_gpu_index_last_times(const phi_gpu_index_ctx *ctx, phi_stage_times *out);
 
 /*
+ * Walk sharing (no counterpart in the reference, which sketches every walk on its own,
+ * /root/reference/src/ILP_index.cpp:556-573): walks are cut into chunks at content-defined boundaries, chunks with the
+ * same vertex sequence and context are sketched ONCE, and the hits are instantiated for every walk that contains the
+ * chunk.  The result is bit-identical with or without sharing; these knobs only change how much work is done.
+ *   chunk_shift : log2 of the chunk bucket size in bases of the topological coordinate (default 11; 4..24)
+ *   share       : 0 = sketch every chunk of every walk on its own, 1 = share identical chunks (default)
+ */
+int phi_gpu_index_set_walk_sharing(phi_gpu_index_ctx *ctx, int chunk_shift, int share);
+typedef struct {
+    uint64_t chunks;            /* chunks over all walks of this ctx */
+    uint64_t active_chunks;     /* chunks that own at least one window */
+    uint64_t tiles;             /* sketch tiles launched (tiles of the representative chunks) */
+    uint64_t unique_windows;    /* window end positions actually sketched (<= path_kmer_positions) */
+    uint64_t unique_hits;       /* hits found by the representatives (<= path_hits) */
+} phi_walk_sharing_stats;
+int phi_gpu_index_last_sharing(const phi_gpu_index_ctx *ctx, phi_walk_sharing_stats *out);
+
+/*
  * Walk sketch alone == ILP_index::index_kmers for every walk
  * (/root/reference/src/ILP_index.cpp:359-445): every emitted minimizer of every
  * walk, in path order, with its hash and its vertex list.  Returned through a

@@ -49,6 +49,14 @@ class StageTimes(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class SharingStats(C.Structure):
+    _fields_ = [("chunks", C.c_uint64), ("active_chunks", C.c_uint64), ("tiles", C.c_uint64),
+                ("unique_windows", C.c_uint64), ("unique_hits", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
 def _arr(a, dtype):
     a = np.ascontiguousarray(a, dtype=dtype)
     return a

@@ -48,6 +48,10 @@ def load_library():
     lib.phi_gpu_index_result_free.argtypes = [resp]
     lib.phi_gpu_index_last_times.restype = C.c_int
     lib.phi_gpu_index_last_times.argtypes = [ctxp, C.POINTER(_abi.StageTimes)]
+    lib.phi_gpu_index_set_walk_sharing.restype = C.c_int
+    lib.phi_gpu_index_set_walk_sharing.argtypes = [ctxp, C.c_int, C.c_int]
+    lib.phi_gpu_index_last_sharing.restype = C.c_int
+    lib.phi_gpu_index_last_sharing.argtypes = [ctxp, C.POINTER(_abi.SharingStats)]
     lib.phi_gpu_index_sketch_walks.restype = C.c_int
     lib.phi_gpu_index_sketch_walks.argtypes = [ctxp, C.POINTER(_abi.GraphView), C.POINTER(_abi.IndexParams),
                                                C.POINTER(resp), C.POINTER(_abi.u64p)]
@@ -156,6 +160,14 @@ class PhiGpuIndex:
     def times(self):
         t = _abi.StageTimes()
         self._check(self.lib.phi_gpu_index_last_times(self.ctx, C.byref(t)))
+        return t.as_dict()
+
+    def set_walk_sharing(self, chunk_shift=11, share=True):
+        self._check(self.lib.phi_gpu_index_set_walk_sharing(self.ctx, int(chunk_shift), 1 if share else 0))
+
+    def sharing(self):
+        t = _abi.SharingStats()
+        self._check(self.lib.phi_gpu_index_last_sharing(self.ctx, C.byref(t)))
         return t.as_dict()
 
     def sketch_walks(self, graph, k=31, w=25):

@@ -1,0 +1,369 @@
+// Walk chunking and de-duplication (hand-written sm_100a CUDA).
+//
+// The reference sketches every haplotype walk independently (/root/reference/src/ILP_index.cpp:556-573,
+// one index_kmers(h) per walk), although the walks of a pangenome graph share most of their vertex
+// sequences.  What index_kmers emits for the windows ending inside a stretch of a walk is a pure function
+// of the vertex sequence under that stretch plus w bases of left and k-1 bases of right context
+// (:388-442: the k-mers of the windows, the previous window's minimum for the prev_hash chain, and the
+// vertices under the chosen k-mer).  So walks are cut into CHUNKS at content-defined boundaries (a step
+// starts a chunk when its vertex falls into a new bucket of the topological base coordinate — the same
+// vertex starts a chunk in every walk that reaches it the same way), chunks with identical context are
+// grouped, ONE representative per group is sketched and probed, and its hits are instantiated for every
+// member with the member's walk id and base offset.  Bit-exactness does not depend on where the
+// boundaries fall or on how much sharing there is; only the amount of work does.
+//
+// Pipeline (all on the ctx stream):
+//   topo coordinate -> boundary flags -> chunk table -> geometry + 128-bit fingerprint (warp per chunk)
+//   -> open-addressing grouping (smallest chunk id represents) -> exact verification of every member
+//   against its representative -> tile records of the representatives.
+#include "kernels.h"
+#include "device_common.cuh"
+
+namespace phi {
+
+#define PHI_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; if (launches) ++*launches; } while (0)
+
+constexpr uint32_t C_NONE = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint64_t cmix(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+// ---- topological base coordinate of every vertex: bases of all vertices that precede it in top_order_map
+__global__ void topo_len_kernel(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, uint32_t *tlen, unsigned long long *ctr)
+{
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_vtx) return;
+    int32_t t = top_order_map[v];
+    if (t < 0 || (uint32_t)t >= n_vtx) { ctr[CTR_BAD_TOPO] = 1; return; }
+    tlen[t] = (uint32_t)(seg_off[v + 1] - seg_off[v]);
+}
+// coord[v] = prefix[top_order_map[v]]; with an unusable top_order_map the segment-store offset serves (any function of v is correct)
+__global__ void topo_coord_kernel(const int32_t *top_order_map, const uint64_t *seg_off, const uint64_t *prefix, uint32_t n_vtx,
+                                  const unsigned long long *ctr, uint64_t *coord)
+{
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_vtx) return;
+    coord[v] = ctr[CTR_BAD_TOPO] ? seg_off[v] : prefix[top_order_map[v]];
+}
+
+// ---- boundaries: step s starts a chunk when its vertex lies in another coordinate bucket than the previous step's
+__global__ void chunk_flag_kernel(const uint32_t *walk_vtx, uint64_t n_steps, const uint64_t *coord, int shift, uint32_t *flags)
+{
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= n_steps) return;
+    uint32_t f = 1;
+    if (s) f = (coord[walk_vtx[s]] >> shift) != (coord[walk_vtx[s - 1]] >> shift);
+    flags[s] = f;
+}
+__global__ void walk_start_flag_kernel(const uint64_t *walk_off, uint32_t n_walks, uint32_t *flags)
+{
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < n_walks && walk_off[h] < walk_off[h + 1]) flags[walk_off[h]] = 1;
+}
+__global__ void chunk_fill_kernel(const uint32_t *flags, const uint32_t *pos, uint64_t n_steps, const uint64_t *walk_off, uint32_t n_walks,
+                                  uint32_t n_chunks, uint32_t *chunk_step, uint32_t *c_walk)
+{
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s == 0) chunk_step[n_chunks] = (uint32_t)n_steps;
+    if (s >= n_steps || !flags[s]) return;
+    uint32_t c = pos[s];
+    chunk_step[c] = (uint32_t)s;
+    uint32_t lo = 0, hi = n_walks;                                    // last h with walk_off[h] <= s
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
+    c_walk[c] = lo;
+}
+
+// ---- geometry + fingerprint, one warp per chunk
+// Owned windows: end positions e (start of the window's last k-mer) in [lo, hi), lo = first base of the chunk, hi = first base of
+// the next chunk clipped to the walk's last k-mer.  Context steps [L, R]: from the step under base lo - w (halo window) to the
+// step under base (next chunk start) + k - 2.
+__global__ void __launch_bounds__(256) chunk_key_kernel(ChunkTable C, const uint32_t *walk_vtx, const uint64_t *walk_off, const uint32_t *step_base,
+                                                        const uint64_t *walk_len, int k, int w, unsigned long long *ctr)
+{
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= C.n_chunks) return;
+    const uint32_t h = C.c_walk[c];
+    const uint64_t ws = walk_off[h], we = walk_off[h + 1];
+    const long long len = (long long)walk_len[h];
+    const uint64_t s0 = C.chunk_step[c], s1 = C.chunk_step[c + 1];
+    uint32_t L = 0, R = 0; long long lo = 0, hi = 0;
+    if (lane == 0) {
+        lo = step_base[s0];
+        const long long b1 = s1 < we ? (long long)step_base[s1] : len;
+        hi = min(b1, len - k + 1);
+        if (len < (long long)w + k - 1 || hi <= max(lo, (long long)w - 1)) hi = lo;     // no valid window ends here
+        uint64_t l = s0; const long long need = lo - w;
+        while (l > ws && (long long)step_base[l] > need) --l;
+        uint64_t r = s1 - 1; const long long last = min(b1 + k - 2, len - 1);
+        while (r + 1 < we && (long long)step_base[r + 1] <= last) ++r;
+        L = (uint32_t)l; R = (uint32_t)r;
+    }
+    L = __shfl_sync(0xFFFFFFFFu, L, 0); R = __shfl_sync(0xFFFFFFFFu, R, 0);
+    lo = __shfl_sync(0xFFFFFFFFu, lo, 0); hi = __shfl_sync(0xFFFFFFFFu, hi, 0);
+    uint64_t h1 = 0, h2 = 0;
+    if (hi > lo) {
+        for (uint32_t i = L + lane; i <= R; i += 32) {
+            const uint64_t x = walk_vtx[i], idx = i - L;
+            h1 += cmix(x * 0x9E3779B97F4A7C15ull + idx * 0xD6E8FEB86659FD93ull + 0x2545F4914F6CDD1Dull);
+            h2 += cmix((x + 0x632BE59BD9B4E019ull) * 0xBF58476D1CE4E5B9ull ^ (idx + 1) * 0x94D049BB133111EBull);
+        }
+        #pragma unroll
+        for (int d = 16; d; d >>= 1) { h1 += __shfl_xor_sync(0xFFFFFFFFu, h1, d); h2 += __shfl_xor_sync(0xFFFFFFFFu, h2, d); }
+        const uint64_t meta = ((uint64_t)(s0 - L) << 40) ^ ((uint64_t)(s1 - L) << 20) ^ (uint64_t)(R - L);
+        const uint64_t span = (uint64_t)(hi - lo);
+        h1 = cmix(h1 ^ cmix(meta + 0x1234567ull) ^ (span << 32)); h2 = cmix(h2 + cmix(meta ^ 0xABCDEF01ull) + span);
+    }
+    if (lane == 0) {
+        C.c_L[c] = L; C.c_R[c] = R; C.c_lo[c] = (uint32_t)lo; C.c_hi[c] = (uint32_t)hi; C.c_h1[c] = h1; C.c_h2[c] = h2;
+        if (hi > lo) atomicAdd(&ctr[CTR_ACTIVE_CHUNKS], 1ull);
+    }
+}
+
+// ---- grouping by fingerprint: the slot ends up holding the smallest chunk id of its group
+__global__ void chunk_group_kernel(ChunkTable C, uint32_t *table, uint32_t mask, int dedupe)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C.n_chunks) return;
+    if (C.c_hi[c] <= C.c_lo[c]) { C.c_slot[c] = C_NONE; return; }
+    if (!dedupe) { C.c_slot[c] = C_NONE; return; }
+    const uint64_t h1 = C.c_h1[c], h2 = C.c_h2[c];
+    uint32_t slot = (uint32_t)h1 & mask;
+    for (;;) {
+        uint32_t cur = table[slot];
+        if (cur == C_NONE) {
+            uint32_t old = atomicCAS(&table[slot], C_NONE, c);
+            if (old == C_NONE) break;
+            cur = old;
+        }
+        if (C.c_h1[cur] == h1 && C.c_h2[cur] == h2) { atomicMin(&table[slot], c); break; }
+        slot = (slot + 1) & mask;
+    }
+    C.c_slot[c] = slot;
+}
+
+// ---- representative of every chunk, member counts, exact verification (warp per chunk)
+__global__ void __launch_bounds__(256) chunk_rep_kernel(ChunkTable C, const uint32_t *table, const uint32_t *walk_vtx, int dedupe, unsigned long long *ctr)
+{
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= C.n_chunks) return;
+    const bool active = C.c_hi[c] > C.c_lo[c];
+    uint32_t rep = C_NONE;
+    if (active) rep = dedupe ? table[C.c_slot[c]] : c;
+    if (active && rep != c) {
+        // a member must match its representative exactly: same shape, same vertex sequence (the fingerprint only proposes)
+        const uint32_t L = C.c_L[c], R = C.c_R[c], Lr = C.c_L[rep], Rr = C.c_R[rep];
+        bool same = (R - L) == (Rr - Lr) && (C.chunk_step[c] - L) == (C.chunk_step[rep] - Lr) && (C.chunk_step[c + 1] - L) == (C.chunk_step[rep + 1] - Lr)
+                    && (C.c_hi[c] - C.c_lo[c]) == (C.c_hi[rep] - C.c_lo[rep]);
+        if (same) for (uint32_t i = lane; i <= R - L; i += 32) same &= walk_vtx[L + i] == walk_vtx[Lr + i];
+        same = __all_sync(0xFFFFFFFFu, same);
+        if (!same && lane == 0) ctr[CTR_DEDUPE_MISMATCH] = 1;
+    }
+    if (lane == 0) {
+        C.c_rep[c] = rep;
+        if (active) atomicAdd(&C.c_ninst[rep], 1u);
+        const uint32_t T = TILE_WINDOWS;
+        const uint32_t nt = (active && rep == c) ? (C.c_hi[c] - C.c_lo[c] + T - 1) / T : 0u;
+        C.c_ntile[c] = nt;
+        if (nt) atomicAdd(&ctr[CTR_UNIQUE_WINDOWS], (unsigned long long)(C.c_hi[c] - C.c_lo[c]));
+    }
+}
+
+// ---- tile records of the representatives (c_tile_base = exclusive scan of c_ntile)
+__global__ void tile_fill_kernel(ChunkTable C, const uint64_t *walk_off, const uint32_t *step_base, int w, TileRec *tiles)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C.n_chunks) return;
+    const uint32_t nt = C.c_ntile[c];
+    if (!nt) return;
+    const uint32_t h = C.c_walk[c], lo = C.c_lo[c], hi = C.c_hi[c], L = C.c_L[c], R = C.c_R[c];
+    const uint64_t ws = walk_off[h];
+    const uint32_t tb = C.c_tile_base[c];
+    for (uint32_t t = 0; t < nt; ++t) {
+        TileRec r;
+        r.walk = h; r.e0 = lo + t * TILE_WINDOWS; r.e1 = min(r.e0 + TILE_WINDOWS, hi); r.chunk = c; r.cbase = lo; r._r0 = r._r1 = 0;
+        const long long first = max((long long)r.e0 - w, 0ll);         // first base the tile stages
+        uint32_t a = L, b = R + 1;                                      // last step in [L, R] with step_base <= first
+        while (b - a > 1) { uint32_t m = (a + b) >> 1; if ((long long)step_base[m] <= first) a = m; else b = m; }
+        r.first_step = (uint32_t)(a - ws);
+        tiles[tb + t] = r;
+    }
+}
+
+// ---- per-walk minimizer counts: every member adds what its representative emitted
+__global__ void chunk_emitted_kernel(ChunkTable C, const uint32_t *c_emitted, const uint32_t *c_hits, uint32_t walk_id_base,
+                                     unsigned long long *minimizers_per_walk, unsigned long long *ctr)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t h = C_NONE; unsigned long long v = 0, nh = 0;
+    if (c < C.n_chunks) { uint32_t rep = C.c_rep[c]; if (rep != C_NONE) { h = C.c_walk[c]; v = c_emitted[rep]; nh = c_hits[rep]; } }
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) nh += __shfl_xor_sync(0xFFFFFFFFu, nh, d);
+    if ((threadIdx.x & 31) == 0 && nh) atomicAdd(&ctr[CTR_PATH_HITS], nh);
+    // chunks are ordered by walk: lanes of one warp mostly share the walk -> one atomic per distinct walk per warp
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
+    unsigned long long sum = 0;
+    for (uint32_t m = peers; m; m &= m - 1) sum += __shfl_sync(peers, v, __ffs(m) - 1);
+    if (h != C_NONE && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1) && sum) atomicAdd(&minimizers_per_walk[walk_id_base + h], sum);
+}
+
+// ---- survivors per representative chunk: hits of its tiles whose rank is not dropped (one warp per tile)
+__global__ void __launch_bounds__(256) tile_survivors_kernel(const TileRec *tiles, uint32_t n_tiles, const uint32_t *seg_off, const uint32_t *seg_cnt,
+                                                             const uint32_t *hit_rank, const uint8_t *rank_drop, uint32_t *c_surv)
+{
+    const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (tile >= n_tiles) return;
+    uint32_t n = 0;
+    for (int sg = 0; sg < SEG_PER_TILE; ++sg) {
+        const uint32_t cnt = seg_cnt[(size_t)tile * SEG_PER_TILE + sg], off = seg_off[(size_t)tile * SEG_PER_TILE + sg];
+        for (uint32_t i = lane; i < cnt; i += 32) n += rank_drop[hit_rank[off + i]] ? 0u : 1u;
+    }
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, d);
+    if (lane == 0 && n) atomicAdd(&c_surv[tiles[tile].chunk], n);
+}
+__global__ void member_counts_kernel(ChunkTable C, const uint32_t *c_surv, uint32_t *member_cnt)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C.n_chunks) return;
+    uint32_t rep = C.c_rep[c];
+    member_cnt[c] = rep == C_NONE ? 0u : c_surv[rep];
+}
+
+// ---- instantiate the surviving hits of every member chunk (one warp per member), in (walk, position) order:
+// members are numbered along their walks, tiles along the chunk, hits along the tile
+__global__ void __launch_bounds__(256) expand_kernel(ChunkTable C, ExpandArgs X)
+{
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= C.n_chunks) return;
+    const uint32_t rep = C.c_rep[c];
+    if (rep == C_NONE) return;
+    uint64_t out = X.member_off[c];
+    if (X.member_off[c + 1] == out) return;
+    const uint32_t walk = X.walk_id_base + C.c_walk[c];
+    const int32_t shift = (int32_t)C.c_lo[c] - X.w;                          // rel = p + w - lo(rep)  ->  p' = rel - w + lo(member)
+    const uint32_t t0 = C.c_tile_base[rep], nt = C.c_ntile[rep];
+    for (uint32_t t = t0; t < t0 + nt; ++t) {
+        for (int sg = 0; sg < SEG_PER_TILE; ++sg) {
+            const uint32_t cnt = X.hseg_cnt[(size_t)t * SEG_PER_TILE + sg], off = X.hseg_off[(size_t)t * SEG_PER_TILE + sg];
+            for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+                const uint32_t i = off + i0 + lane;
+                const bool have = i0 + lane < cnt;
+                uint32_t r = have ? X.hit_rank[i] : 0u;
+                const bool keep = have && !X.rank_drop[r];
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) {
+                    const uint64_t j = out + __popc(b & lanemask_lt());
+                    X.x_rank[j] = r; X.x_walk[j] = walk; X.x_pos[j] = (uint32_t)((int32_t)X.hit_pos[i] + shift);
+                    X.x_voff[j] = X.hit_voff[i]; X.x_nv[j] = X.hit_nv[i];
+                    if (X.x_hash) X.x_hash[j] = X.hit_hash[i];
+                }
+                out += __popc(b);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, uint32_t *tlen, uint64_t *prefix, uint64_t *coord,
+                             void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
+{
+    if (!n_vtx) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(tlen, 0, (size_t)n_vtx * 4, st);
+    if (e != cudaSuccess) return e;
+    topo_len_kernel<<<(n_vtx + 255) / 256, 256, 0, st>>>(top_order_map, seg_off, n_vtx, tlen, ctr);
+    PHI_LAUNCH_CHECK();
+    e = scan_u32_to_u64(tlen, prefix, n_vtx, scan_scratch, st, launches);
+    if (e != cudaSuccess) return e;
+    topo_coord_kernel<<<(n_vtx + 255) / 256, 256, 0, st>>>(top_order_map, seg_off, prefix, n_vtx, ctr, coord);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t chunk_flags(const uint32_t *walk_vtx, uint64_t n_steps, const uint64_t *walk_off, uint32_t n_walks, const uint64_t *coord, int shift,
+                        uint32_t *flags, cudaStream_t st, uint64_t *launches)
+{
+    if (!n_steps) return cudaSuccess;
+    chunk_flag_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, n_steps, coord, shift, flags);
+    PHI_LAUNCH_CHECK();
+    walk_start_flag_kernel<<<(n_walks + 255) / 256, 256, 0, st>>>(walk_off, n_walks, flags);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t chunk_build(const ChunkTable &C, const uint32_t *flags, const uint32_t *pos, const uint32_t *walk_vtx, uint64_t n_steps, const uint64_t *walk_off,
+                        uint32_t n_walks, const uint32_t *step_base, const uint64_t *walk_len, int k, int w, unsigned long long *ctr,
+                        cudaStream_t st, uint64_t *launches)
+{
+    if (!n_steps || !C.n_chunks) return cudaSuccess;
+    chunk_fill_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(flags, pos, n_steps, walk_off, n_walks, C.n_chunks, C.chunk_step, C.c_walk);
+    PHI_LAUNCH_CHECK();
+    chunk_key_kernel<<<(unsigned)(((uint64_t)C.n_chunks * 32 + 255) / 256), 256, 0, st>>>(C, walk_vtx, walk_off, step_base, walk_len, k, w, ctr);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t chunk_group(const ChunkTable &C, uint32_t *table, uint32_t table_cap, const uint32_t *walk_vtx, int dedupe, unsigned long long *ctr,
+                        cudaStream_t st, uint64_t *launches)
+{
+    if (!C.n_chunks) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(C.c_ninst, 0, (size_t)C.n_chunks * 4, st);
+    if (e != cudaSuccess) return e;
+    if (dedupe) {
+        e = fill_u32(table, table_cap, C_NONE, st, launches);
+        if (e != cudaSuccess) return e;
+    }
+    chunk_group_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>(C, table, table_cap - 1, dedupe);
+    PHI_LAUNCH_CHECK();
+    chunk_rep_kernel<<<(unsigned)(((uint64_t)C.n_chunks * 32 + 255) / 256), 256, 0, st>>>(C, table, walk_vtx, dedupe, ctr);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t chunk_tiles(const ChunkTable &C, const uint64_t *walk_off, const uint32_t *step_base, int w, TileRec *tiles, cudaStream_t st, uint64_t *launches)
+{
+    if (!C.n_chunks) return cudaSuccess;
+    tile_fill_kernel<<<(C.n_chunks + 127) / 128, 128, 0, st>>>(C, walk_off, step_base, w, tiles);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t chunk_emitted(const ChunkTable &C, const uint32_t *c_emitted, const uint32_t *c_hits, uint32_t walk_id_base,
+                          unsigned long long *minimizers_per_walk, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
+{
+    if (!C.n_chunks) return cudaSuccess;
+    chunk_emitted_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>(C, c_emitted, c_hits, walk_id_base, minimizers_per_walk, ctr);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t chunk_survivors(const ChunkTable &C, const TileRec *tiles, uint32_t n_tiles, const uint32_t *seg_off, const uint32_t *seg_cnt,
+                            const uint32_t *hit_rank, const uint8_t *rank_drop, uint32_t *c_surv, uint32_t *member_cnt, cudaStream_t st, uint64_t *launches)
+{
+    if (!C.n_chunks) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(c_surv, 0, (size_t)C.n_chunks * 4, st);
+    if (e != cudaSuccess) return e;
+    if (n_tiles) {
+        tile_survivors_kernel<<<(unsigned)(((uint64_t)n_tiles * 32 + 255) / 256), 256, 0, st>>>(tiles, n_tiles, seg_off, seg_cnt, hit_rank, rank_drop, c_surv);
+        PHI_LAUNCH_CHECK();
+    }
+    member_counts_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>(C, c_surv, member_cnt);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t chunk_expand(const ChunkTable &C, const ExpandArgs &X, cudaStream_t st, uint64_t *launches)
+{
+    if (!C.n_chunks) return cudaSuccess;
+    expand_kernel<<<(unsigned)(((uint64_t)C.n_chunks * 32 + 255) / 256), 256, 0, st>>>(C, X);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+}  // namespace phi

@@ -11,7 +11,9 @@
 //   1. group table  : open addressing over (rank, vertex list) -> count, exact (lists are compared,
 //                     the hash only picks the start slot).
 //   2. mark         : a slot whose count reaches the threshold drops its rank.
-//   3. survivors    : compaction + stable radix sort on (rank, global path coordinate).
+//   3. survivors    : the hits of the representative chunks are instantiated for every member chunk (chunks.cu) in
+//                     (walk, position) order, then a stable radix sort on the rank alone gives (rank, walk, position);
+//                     records that arrive from other GPUs are sorted on (rank, global path coordinate).
 //   4. multi-hit fix: only (rank, walk) groups with >= 2 hits need the decimal-string key order;
 //                     small groups by insertion sort in one thread, big ones by a block rank sort.
 //   5. CSR          : scan of list lengths + gather.
@@ -59,7 +61,10 @@ __global__ void group_count_kernel(FilterArgs A, FilterWork W)
             uint32_t old = atomicCAS(&W.g_rep[slot], G_EMPTY, (uint32_t)i);
             if (old == G_EMPTY) { rep = (uint32_t)i; atomicAdd(&W.ctr[CTR_GROUPS], 1ull); } else rep = old;
         }
-        if (rep == (uint32_t)i || same_list(A, (uint32_t)i, rep)) { atomicAdd(&W.g_cnt[slot], W.weight ? W.weight[i] : 1u); W.hit_slot[i] = (uint32_t)slot; return; }
+        if (rep == (uint32_t)i || same_list(A, (uint32_t)i, rep)) {
+            const uint32_t wt = W.weight ? W.weight[i] : W.chunk_weight ? W.chunk_weight[A.hit_walk[i]] : 1u;
+            atomicAdd(&W.g_cnt[slot], wt); W.hit_slot[i] = (uint32_t)slot; return;
+        }
         slot = (slot + 1) & mask;
     }
     W.ctr[CTR_GROUP_OVERFLOW] = 1;
@@ -81,26 +86,18 @@ __global__ void count_drops_kernel(const uint8_t *rank_drop, uint32_t n, unsigne
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(&ctr[CTR_FILTERED], (unsigned long long)__popc(b));
 }
 
-__global__ void flag_survivors_kernel(FilterArgs A, FilterWork W)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    uint32_t f = 0;
-    if (i < A.n_hits) { f = W.rank_drop[A.hit_rank[i]] ? 0u : 1u; W.flags[i] = f; }
-    int c = __syncthreads_count(f);
-    if (threadIdx.x == 0 && c) atomicAdd(&W.ctr[CTR_SURVIVORS], (unsigned long long)c);
-}
-
-// flags[] has been exclusive-scanned in place; a hit survives iff its rank is not dropped
-__global__ void emit_keys_kernel(FilterArgs A, FilterWork W, int combined)
+// every record survives; key = rank when the records already are in (walk, position) order, else (rank, global path coordinate)
+__global__ void emit_keys_kernel(FilterArgs A, FilterWork W, int mode /* 0: rank, 1: (rank, gpos), 2: gpos */)
 {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= A.n_hits) return;
-    uint32_t r = A.hit_rank[i];
-    if (W.rank_drop[r]) return;
-    uint32_t j = W.flags[i];
-    uint64_t gpos = A.walk_gbase[A.hit_walk[i]] + A.hit_pos[i];
-    W.keys_a[j] = combined ? (((uint64_t)r << A.gpos_bits) | gpos) : gpos;
-    W.vals_a[j] = (uint32_t)i;
+    uint64_t key = A.hit_rank[i];
+    if (mode) {
+        uint64_t gpos = A.walk_gbase[A.hit_walk[i]] + A.hit_pos[i];
+        key = mode == 1 ? ((key << A.gpos_bits) | gpos) : gpos;
+    }
+    W.keys_a[i] = key;
+    W.vals_a[i] = (uint32_t)i;
 }
 
 // second-stage key when (rank, gpos) does not fit one u64: key = rank of vals[j]
@@ -129,24 +126,20 @@ cudaError_t filter_mark_drops(const FilterArgs &A, const FilterWork &W, cudaStre
     }
     return cudaSuccess;
 }
-cudaError_t filter_flag_survivors(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches)
+cudaError_t filter_sort_records(const FilterArgs &A, const FilterWork &W, bool presorted, cudaStream_t st, uint64_t *launches)
 {
-    if (!A.n_hits) return cudaSuccess;
-    flag_survivors_kernel<<<(unsigned)((A.n_hits + 255) / 256), 256, 0, st>>>(A, W);
+    const uint64_t n = A.n_hits;
+    if (!n) return cudaSuccess;
+    const bool combined = A.gpos_bits + A.rank_bits <= 64;
+    emit_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, W, presorted ? 0 : combined ? 1 : 2);
     PHI_LAUNCH_CHECK();
-    return cudaSuccess;
-}
-cudaError_t filter_emit_keys(const FilterArgs &A, const FilterWork &W, uint64_t n_surv, bool combined, cudaStream_t st, uint64_t *launches)
-{
-    if (!A.n_hits || !n_surv) return cudaSuccess;
-    emit_keys_kernel<<<(unsigned)((A.n_hits + 255) / 256), 256, 0, st>>>(A, W, combined ? 1 : 0);
-    PHI_LAUNCH_CHECK();
-    if (combined) return radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n_surv, 0, A.gpos_bits + A.rank_bits, W.sort_scratch, st, launches);
-    cudaError_t e = radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n_surv, 0, A.gpos_bits, W.sort_scratch, st, launches);
+    if (presorted) return radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n, 0, A.rank_bits, W.sort_scratch, st, launches);
+    if (combined) return radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n, 0, A.gpos_bits + A.rank_bits, W.sort_scratch, st, launches);
+    cudaError_t e = radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n, 0, A.gpos_bits, W.sort_scratch, st, launches);
     if (e != cudaSuccess) return e;
-    rank_keys_kernel<<<(unsigned)((n_surv + 255) / 256), 256, 0, st>>>(A, W.vals_a, W.keys_a, n_surv);
+    rank_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, W.vals_a, W.keys_a, n);
     PHI_LAUNCH_CHECK();
-    return radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n_surv, 0, A.rank_bits, W.sort_scratch, st, launches);
+    return radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n, 0, A.rank_bits, W.sort_scratch, st, launches);
 }
 
 // ---- decimal-string order of "v0_v1_..._" keys ('_' sorts after every digit)

@@ -21,13 +21,48 @@ enum {
     CTR_ZERO_STEPS = 9,
     CTR_READ_POS = 10,
     CTR_COMPACT = 11,
-    CTR_NONMONO = 12,
+    CTR_NONMONO = 12,      // some walk is not strictly increasing in top_order_map
     CTR_GROUPS = 13,       // distinct (rank, vertex list) groups in the filter table
-    CTR_GROUP_OVERFLOW = 14,      // some walk is not strictly increasing in top_order_map
-    CTR_COUNT = 16
+    CTR_GROUP_OVERFLOW = 14,
+    CTR_BAD_TOPO = 15,            // top_order_map is not an index into [0, n_vtx): chunk coordinates fall back to segment offsets
+    CTR_ACTIVE_CHUNKS = 16,       // chunks that own at least one valid window
+    CTR_UNIQUE_WINDOWS = 17,      // window end positions owned by representative chunks (what the walk kernel really sketches)
+    CTR_DEDUPE_MISMATCH = 18,
+    CTR_PATH_HITS = 19,           // hits of all walks (every member chunk counts what its representative found)     // a chunk differs from its fingerprint representative (128-bit collision): rerun without sharing
+    CTR_COUNT = 24
 };
 
 enum { WALK_MODE_PROBE = 0, WALK_MODE_ALL = 1 };
+
+constexpr int TILE_WINDOWS = 2048;   // window end positions per sketch tile
+constexpr int SEG_PER_TILE = 8;      // a tile emits its hits in batches of 256 runs: at most TILE_WINDOWS / 256 contiguous hit segments
+
+// One walk-sketch tile: window end positions [e0, e1) of walk `walk` (the representative of chunk `chunk`).
+struct TileRec {
+    uint32_t walk, e0, e1, first_step;   // first_step: step under the tile's first staged base, relative to walk_off[walk]
+    uint32_t chunk, cbase, _r0, _r1;     // cbase: first base of the chunk; hit positions are stored as p + w - cbase
+};
+
+// Chunk table (chunks.cu): chunks are numbered along the walks, walk after walk.
+struct ChunkTable {
+    uint32_t n_chunks;
+    uint32_t *chunk_step;                // [n_chunks + 1] first step (global index) of each chunk
+    uint32_t *c_walk, *c_L, *c_R;        // walk; context steps [L, R] (global indices)
+    uint32_t *c_lo, *c_hi;               // owned window end positions [lo, hi) in walk coordinates (lo == hi: nothing to sketch)
+    uint64_t *c_h1, *c_h2;               // fingerprint of the context
+    uint32_t *c_slot, *c_rep;            // grouping table slot; representative chunk (0xFFFFFFFF: inactive)
+    uint32_t *c_ninst;                   // members of the group (at the representative)
+    uint32_t *c_ntile, *c_tile_base;     // tiles of a representative and their first index
+};
+
+struct ExpandArgs {
+    int w; uint32_t walk_id_base;
+    const uint64_t *member_off;          // [n_chunks + 1] first expanded record of each member chunk
+    const uint32_t *hseg_off, *hseg_cnt; // [n_tiles * SEG_PER_TILE]
+    const uint8_t *rank_drop;
+    const uint32_t *hit_rank, *hit_pos; const uint64_t *hit_voff; const uint8_t *hit_nv; const uint64_t *hit_hash;
+    uint32_t *x_rank, *x_walk, *x_pos; uint64_t *x_voff; uint8_t *x_nv; uint64_t *x_hash;
+};
 
 // shared-memory carve-up of a sketch tile (computed on the host: sketch_tile.cuh make_layout)
 struct TileLayout {
@@ -56,13 +91,13 @@ struct WalkSketchArgs {
     const uint32_t *walk_vtx; const uint64_t *walk_off;      // zero-length steps removed
     const uint32_t *step_base;                                // walk-relative first base of each step
     const uint64_t *walk_len;                                 // [n_walks] bases
-    const uint64_t *walk_tile_base;                           // [n_walks + 1]
-    const uint32_t *tile_first_step;                          // [total tiles] relative to walk_off[h]
+    const TileRec *tiles;                                     // [n_tiles] tiles of the representative chunks
     int k, w, mode;
     const uint64_t *spec; const uint32_t *dir; int dbits;     // ranked spectrum + radix directory
-    uint32_t walk_id_base;
-    unsigned long long *minimizers_per_walk;                  // [n_walks]
-    uint32_t *hit_rank, *hit_walk, *hit_pos; uint64_t *hit_voff; uint8_t *hit_nv; uint64_t *hit_hash;
+    uint32_t *chunk_emitted, *chunk_hits;                     // [n_chunks] minimizers emitted / hits found by a representative chunk
+    uint32_t *hseg_off, *hseg_cnt;                            // [n_tiles * SEG_PER_TILE] hit segments of each tile, in position order
+    // hits of the representative chunks: hit_chunk = chunk id, hit_pos = p + w - (first base of the chunk)
+    uint32_t *hit_rank, *hit_chunk, *hit_pos; uint64_t *hit_voff; uint8_t *hit_nv; uint64_t *hit_hash;
     int32_t *vtx_pool;
     uint64_t hit_cap, vtx_cap;
     unsigned long long *ctr;
@@ -73,24 +108,41 @@ int tile_windows();
 // sketch_kernels.cu
 cudaError_t launch_read_tile_dir(const uint64_t *read_off, uint64_t n_reads, int w, uint64_t n_tiles, uint64_t *out, cudaStream_t st);
 cudaError_t launch_read_sketch(const ReadSketchArgs &A, uint64_t n_tiles, cudaStream_t st);
-cudaError_t launch_walk_sketch(const WalkSketchArgs &A, uint32_t n_walks, uint64_t max_tiles, cudaStream_t st);
+cudaError_t launch_walk_sketch(const WalkSketchArgs &A, uint32_t n_tiles, cudaStream_t st);
 cudaError_t launch_step_len(const uint32_t *walk_vtx, const uint64_t *seg_off, uint64_t n_steps, uint32_t *step_len, cudaStream_t st);
 cudaError_t launch_walk_len(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
                             uint64_t n_steps, uint64_t *walk_len, cudaStream_t st);
-cudaError_t launch_step_finalize(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
-                                 uint64_t n_steps, int w, const uint64_t *walk_tile_base, uint32_t *step_base,
-                                 uint32_t *tile_first_step, cudaStream_t st);
+cudaError_t launch_step_finalize(const uint64_t *gbase, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, uint32_t *step_base,
+                                 cudaStream_t st);
 cudaError_t launch_walk_monotone(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
                                  const int32_t *top_order_map, unsigned long long *ctr, cudaStream_t st);
 cudaError_t launch_hash_bytes(const uint8_t *keys, uint64_t n, int len, uint64_t *out, cudaStream_t st);
+
+// chunks.cu — walk chunking, grouping of identical chunks, instantiation of the representatives' hits
+cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, uint32_t *tlen, uint64_t *prefix, uint64_t *coord,
+                             void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
+cudaError_t chunk_flags(const uint32_t *walk_vtx, uint64_t n_steps, const uint64_t *walk_off, uint32_t n_walks, const uint64_t *coord, int shift,
+                        uint32_t *flags, cudaStream_t st, uint64_t *launches);
+cudaError_t chunk_build(const ChunkTable &C, const uint32_t *flags, const uint32_t *pos, const uint32_t *walk_vtx, uint64_t n_steps, const uint64_t *walk_off,
+                        uint32_t n_walks, const uint32_t *step_base, const uint64_t *walk_len, int k, int w, unsigned long long *ctr,
+                        cudaStream_t st, uint64_t *launches);
+cudaError_t chunk_group(const ChunkTable &C, uint32_t *table, uint32_t table_cap, const uint32_t *walk_vtx, int dedupe, unsigned long long *ctr,
+                        cudaStream_t st, uint64_t *launches);
+cudaError_t chunk_tiles(const ChunkTable &C, const uint64_t *walk_off, const uint32_t *step_base, int w, TileRec *tiles, cudaStream_t st, uint64_t *launches);
+cudaError_t chunk_emitted(const ChunkTable &C, const uint32_t *c_emitted, const uint32_t *c_hits, uint32_t walk_id_base,
+                          unsigned long long *minimizers_per_walk, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
+cudaError_t chunk_survivors(const ChunkTable &C, const TileRec *tiles, uint32_t n_tiles, const uint32_t *hseg_off, const uint32_t *hseg_cnt,
+                            const uint32_t *hit_rank, const uint8_t *rank_drop, uint32_t *c_surv, uint32_t *member_cnt, cudaStream_t st, uint64_t *launches);
+cudaError_t chunk_expand(const ChunkTable &C, const ExpandArgs &X, cudaStream_t st, uint64_t *launches);
 
 // primitives.cu — all on `st`, scratch supplied by the caller
 // exclusive scan of u32 -> u64 (out may not alias in); returns bytes of scratch needed when scratch == nullptr
 size_t scan_u32_to_u64_scratch(uint64_t n);
 cudaError_t scan_u32_to_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *scratch, cudaStream_t st, uint64_t *launches);
-// in-place exclusive scan of u32 (n < 2^32 total)
+// exclusive scan of u32 (n < 2^32 total), in place or out of place
 size_t scan_u32_scratch(uint64_t n);
 cudaError_t scan_u32_inplace(uint32_t *data, uint64_t n, void *scratch, cudaStream_t st, uint64_t *launches);
+cudaError_t scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, void *scratch, cudaStream_t st, uint64_t *launches);
 // stable LSD radix sort of u64 keys (optional u32 values) on bits [bit_lo, bit_hi); result ends in keys_a/vals_a
 size_t radix_sort_scratch(uint64_t n);
 cudaError_t radix_sort_u64(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, uint64_t n, int bit_lo, int bit_hi,
@@ -115,6 +167,7 @@ struct FilterWork {                  // device scratch, sized by the host
     uint32_t *g_rep, *g_cnt; uint64_t g_cap;      // group table
     uint32_t *hit_slot;                            // [n_hits] slot of each hit's group
     const uint32_t *weight;                        // optional [n_hits]: occurrences a record stands for (multi-GPU summaries)
+    const uint32_t *chunk_weight;                  // optional [n_chunks]: members of the chunk hit_walk[i] names (hits of representatives)
     uint8_t *rank_drop;                            // [n_ranks]
     uint32_t *flags;                               // [n_hits] survivor flags -> scanned
     uint64_t *keys_a, *keys_b; uint32_t *vals_a, *vals_b;   // [n_survivors]
@@ -123,8 +176,9 @@ struct FilterWork {                  // device scratch, sized by the host
 };
 cudaError_t filter_count_groups(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_mark_drops(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
-cudaError_t filter_flag_survivors(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
-cudaError_t filter_emit_keys(const FilterArgs &A, const FilterWork &W, uint64_t n_surv, bool combined, cudaStream_t st, uint64_t *launches);
+// sort keys of records that ALL survive.  presorted: the records already are in (walk, position) order and only a stable
+// sort on the rank is needed; otherwise the key is (rank, global path coordinate), in one or two sorts.
+cudaError_t filter_sort_records(const FilterArgs &A, const FilterWork &W, bool presorted, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_fix_multi(const FilterArgs &A, uint32_t *order, uint64_t n_surv, uint32_t *big_list, uint32_t big_cap,
                              unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_fix_big(const FilterArgs &A, uint32_t *order, uint32_t *tmp, const uint32_t *big_list, uint32_t n_big,

@@ -61,10 +61,14 @@ struct phi_gpu_index_ctx {
     std::vector<uint64_t> h_walk_off;
 
     // work buffers
-    DevBuf step_len, gbase, step_base, walk_len, walk_tile_base, tile_first_step, tile_first_read, scan_scr, ctr;
+    DevBuf step_len, gbase, step_base, walk_len, tile_first_read, scan_scr, ctr;
     DevBuf walk_off_c, walk_vtx_c, flags64;
     DevBuf table, spec_a, spec_b, sort_scr, dir;
-    DevBuf mpw, hit_rank, hit_walk, hit_pos, hit_voff, hit_nv, hit_hash, vtx_pool;
+    DevBuf mpw, hit_rank, hit_chunk, hit_pos, hit_voff, hit_nv, hit_hash, vtx_pool;
+    // walk chunks (chunks.cu): boundaries, fingerprints, representatives, tiles, hit segments, expanded survivors
+    DevBuf tlen, tprefix, coord, cflags, cpos, chunk_step, c_walk, c_L, c_R, c_lo, c_hi, c_h1, c_h2, c_slot, c_rep, c_ninst, c_ntile, c_tile_base, ctable, tiles;
+    DevBuf hseg_off, hseg_cnt, c_emitted, c_hits, c_surv, member_cnt, member_off, x_rank, x_walk, x_pos, x_voff, x_nv, x_hash;
+    uint32_t n_chunks = 0, n_tiles = 0; uint64_t unique_windows = 0, active_chunks = 0, rep_chunks = 0, unique_hits = 0; int dedupe = 1, chunk_shift = 11;
     DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
     DevBuf anchor_off, anchor_rank, anchor_walk, anchor_vtx, apw, walk_gbase;
     unsigned long long *h_ctr = nullptr;   // pinned mirror of the counter block
@@ -126,9 +130,16 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     DevBuf *bufs[] = {&ctx->seg_off, &ctx->seg_bases, &ctx->walk_off, &ctx->walk_vtx, &ctx->top_order, &ctx->read_off, &ctx->read_bases,
-                      &ctx->step_len, &ctx->gbase, &ctx->step_base, &ctx->walk_len, &ctx->walk_tile_base, &ctx->tile_first_step,
+                      &ctx->step_len, &ctx->gbase, &ctx->step_base, &ctx->walk_len,
                       &ctx->tile_first_read, &ctx->scan_scr, &ctx->ctr, &ctx->walk_off_c, &ctx->walk_vtx_c, &ctx->flags64, &ctx->table,
-                      &ctx->spec_a, &ctx->spec_b, &ctx->sort_scr, &ctx->dir, &ctx->mpw, &ctx->hit_rank, &ctx->hit_walk, &ctx->hit_pos,
+                      &ctx->spec_a, &ctx->spec_b, &ctx->sort_scr, &ctx->dir, &ctx->mpw, &ctx->hit_rank, &ctx->hit_chunk, &ctx->hit_pos,
+                      &ctx->tlen, &ctx->tprefix, &ctx->coord, &ctx->cflags, &ctx->cpos, &ctx->chunk_step, &ctx->c_walk, &ctx->c_L, &ctx->c_R, &ctx->c_lo,
+                      &ctx->c_hi, &ctx->c_h1, &ctx->c_h2, &ctx->c_slot, &ctx->c_rep, &ctx->c_ninst, &ctx->c_ntile, &ctx->c_tile_base, &ctx->ctable,
+                      &ctx->tiles, &ctx->hseg_off, &ctx->hseg_cnt, &ctx->c_emitted, &ctx->c_hits, &ctx->c_surv, &ctx->member_cnt, &ctx->member_off,
+                      &ctx->x_rank, &ctx->x_walk, &ctx->x_pos, &ctx->x_voff, &ctx->x_nv, &ctx->x_hash,
+                      &ctx->xk_a, &ctx->xk_b, &ctx->xcnt, &ctx->xoff, &ctx->ag_send, &ctx->ag_recv, &ctx->m_rank, &ctx->m_cnt, &ctx->m_voff, &ctx->m_nv,
+                      &ctx->r_rank, &ctx->r_walk, &ctx->r_pos, &ctx->r_voff, &ctx->r_nv, &ctx->r_vtx, &ctx->s_rank, &ctx->s_walk, &ctx->s_pos,
+                      &ctx->s_voff, &ctx->s_nv, &ctx->s_vtx,
                       &ctx->hit_voff, &ctx->hit_nv, &ctx->hit_hash, &ctx->vtx_pool, &ctx->g_rep, &ctx->g_cnt, &ctx->rank_drop, &ctx->flags,
                       &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->big_list, &ctx->tmp_order, &ctx->nv_out,
                       &ctx->anchor_off, &ctx->anchor_rank, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw, &ctx->walk_gbase};
@@ -257,22 +268,85 @@ namespace {
 
 struct RunOut {                    // device-side products of one run
     uint32_t n_spec = 0;
-    uint64_t n_hits = 0, n_hit_vtx = 0, n_surv = 0, n_anchor_vtx = 0;
+    uint64_t n_hits = 0, n_hit_vtx = 0, n_surv = 0, n_anchor_vtx = 0;   // n_hits: hits of the representative chunks
+    uint64_t path_hits = 0;                                             // hits of all walks
     uint64_t read_pos = 0, path_pos = 0, read_emitted = 0, path_emitted = 0;
     int64_t n_filtered = 0;
 };
 
 }  // namespace
 
-// ---- stage: graph preparation (depends on k, w through the tile directory)
-static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<uint64_t> &h_walk_len, std::vector<uint64_t> &h_tile_base,
-                            uint64_t &max_tiles, const uint32_t *&d_walk_vtx, const uint64_t *&d_walk_off, uint64_t &n_steps_eff,
-                            int &walks_monotone)
+// ---- stage: graph preparation: step base offsets, walk lengths, then the chunk table and the tiles of the representative
+// chunks (depends on k and w through the chunk context)
+static ChunkTable chunk_table(phi_gpu_index_ctx *ctx)
+{
+    ChunkTable C;
+    C.n_chunks = ctx->n_chunks; C.chunk_step = ctx->chunk_step.as<uint32_t>();
+    C.c_walk = ctx->c_walk.as<uint32_t>(); C.c_L = ctx->c_L.as<uint32_t>(); C.c_R = ctx->c_R.as<uint32_t>();
+    C.c_lo = ctx->c_lo.as<uint32_t>(); C.c_hi = ctx->c_hi.as<uint32_t>(); C.c_h1 = ctx->c_h1.as<uint64_t>(); C.c_h2 = ctx->c_h2.as<uint64_t>();
+    C.c_slot = ctx->c_slot.as<uint32_t>(); C.c_rep = ctx->c_rep.as<uint32_t>(); C.c_ninst = ctx->c_ninst.as<uint32_t>();
+    C.c_ntile = ctx->c_ntile.as<uint32_t>(); C.c_tile_base = ctx->c_tile_base.as<uint32_t>();
+    return C;
+}
+
+static int stage_chunks(phi_gpu_index_ctx *ctx, int k, int w, const uint32_t *d_walk_vtx, const uint64_t *d_walk_off, uint64_t S)
+{
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    const uint32_t H = ctx->n_walks, V = ctx->n_vtx;
+    ctx->n_chunks = ctx->n_tiles = 0; ctx->unique_windows = ctx->active_chunks = ctx->rep_chunks = 0;
+    if (!H || !S) return PHI_OK;
+    if (S >= 0xFFFFFFFFull) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-2 walk steps on one GPU; shard the walks over more GPUs");
+    // topological base coordinate of every vertex
+    CU(ctx->tlen.reserve((size_t)V * 4 + 4)); CU(ctx->tprefix.reserve(((size_t)V + 1) * 8)); CU(ctx->coord.reserve((size_t)V * 8 + 8));
+    CU(ctx->scan_scr.reserve(std::max({scan_u32_to_u64_scratch((uint64_t)V + 1), scan_u32_scratch(S + 1), (size_t)1024})));
+    CU(chunk_topo_coord(ctx->top_order.as<int32_t>(), ctx->seg_off.as<uint64_t>(), V, ctx->tlen.as<uint32_t>(), ctx->tprefix.as<uint64_t>(),
+                        ctx->coord.as<uint64_t>(), ctx->scan_scr.p, d_ctr, ctx->st, &ctx->launches));
+    // boundaries -> chunk ids
+    CU(ctx->cflags.reserve(S * 4 + 4)); CU(ctx->cpos.reserve(S * 4 + 4));
+    CU(chunk_flags(d_walk_vtx, S, d_walk_off, H, ctx->coord.as<uint64_t>(), ctx->chunk_shift, ctx->cflags.as<uint32_t>(), ctx->st, &ctx->launches));
+    CU(scan_u32(ctx->cflags.as<uint32_t>(), ctx->cpos.as<uint32_t>(), S, ctx->scan_scr.p, ctx->st, &ctx->launches));
+    uint32_t last_pos = 0, last_flag = 0;
+    CU(cudaMemcpyAsync(&last_pos, ctx->cpos.as<uint32_t>() + (S - 1), 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&last_flag, ctx->cflags.as<uint32_t>() + (S - 1), 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    const uint32_t NC = last_pos + last_flag;
+    ctx->n_chunks = NC;
+    DevBuf *u32s[] = {&ctx->chunk_step, &ctx->c_walk, &ctx->c_L, &ctx->c_R, &ctx->c_lo, &ctx->c_hi, &ctx->c_slot, &ctx->c_rep, &ctx->c_ninst,
+                      &ctx->c_ntile, &ctx->c_tile_base, &ctx->c_emitted, &ctx->c_hits, &ctx->c_surv};
+    for (DevBuf *b : u32s) CU(b->reserve(((size_t)NC + 2) * 4));
+    CU(ctx->c_h1.reserve(((size_t)NC + 1) * 8)); CU(ctx->c_h2.reserve(((size_t)NC + 1) * 8));
+    CU(ctx->member_cnt.reserve(((size_t)NC + 2) * 4)); CU(ctx->member_off.reserve(((size_t)NC + 2) * 8));
+    ChunkTable C = chunk_table(ctx);
+    CU(chunk_build(C, ctx->cflags.as<uint32_t>(), ctx->cpos.as<uint32_t>(), d_walk_vtx, S, d_walk_off, H, ctx->step_base.as<uint32_t>(),
+                   ctx->walk_len.as<uint64_t>(), k, w, d_ctr, ctx->st, &ctx->launches));
+    uint32_t tcap = 1024; while (tcap < 2 * (uint64_t)NC) tcap <<= 1;
+    CU(ctx->ctable.reserve((size_t)tcap * 4));
+    CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch((uint64_t)NC + 2), scan_u32_to_u64_scratch((uint64_t)NC + 2))));
+    for (int dedupe = ctx->dedupe ? 1 : 0;; dedupe = 0) {
+        CU(cudaMemsetAsync(d_ctr + CTR_UNIQUE_WINDOWS, 0, 2 * 8, ctx->st));               // UNIQUE_WINDOWS, DEDUPE_MISMATCH
+        CU(chunk_group(C, ctx->ctable.as<uint32_t>(), tcap, d_walk_vtx, dedupe, d_ctr, ctx->st, &ctx->launches));
+        CU(cudaMemsetAsync(ctx->c_ntile.as<uint32_t>() + NC, 0, 4, ctx->st));
+        CU(scan_u32(ctx->c_ntile.as<uint32_t>(), ctx->c_tile_base.as<uint32_t>(), (uint64_t)NC + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
+        uint32_t n_tiles = 0;
+        CU(cudaMemcpyAsync(&n_tiles, ctx->c_tile_base.as<uint32_t>() + NC, 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(read_counters(ctx));
+        ctx->n_tiles = n_tiles;
+        if (!dedupe || !ctx->h_ctr[CTR_DEDUPE_MISMATCH]) break;                          // a fingerprint collision: sketch every chunk on its own
+    }
+    ctx->unique_windows = ctx->h_ctr[CTR_UNIQUE_WINDOWS]; ctx->active_chunks = ctx->h_ctr[CTR_ACTIVE_CHUNKS];
+    CU(ctx->tiles.reserve((size_t)ctx->n_tiles * sizeof(TileRec) + 32));
+    CU(chunk_tiles(C, d_walk_off, ctx->step_base.as<uint32_t>(), w, ctx->tiles.as<TileRec>(), ctx->st, &ctx->launches));
+    return PHI_OK;
+}
+
+static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<uint64_t> &h_walk_len, const uint32_t *&d_walk_vtx,
+                            const uint64_t *&d_walk_off, uint64_t &n_steps_eff, int &walks_monotone)
 {
     walks_monotone = 1;
     const uint32_t H = ctx->n_walks; const uint64_t S = ctx->n_steps;
     d_walk_vtx = ctx->walk_vtx.as<uint32_t>(); d_walk_off = ctx->walk_off.as<uint64_t>(); n_steps_eff = S;
-    h_walk_len.assign(H, 0); h_tile_base.assign(H + 1, 0); max_tiles = 0;
+    h_walk_len.assign(H, 0);
+    ctx->n_chunks = ctx->n_tiles = 0; ctx->unique_windows = 0;
     if (!H) return PHI_OK;
     CU(ctx->step_len.reserve(S * 4 + 4));
     CU(ctx->gbase.reserve((S + 1) * 8));
@@ -308,23 +382,13 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     CU(ctx->walk_len.reserve((size_t)H * 8));
     CU(launch_walk_len(ctx->gbase.as<uint64_t>(), ctx->step_len.as<uint32_t>(), d_walk_off, H, S2, ctx->walk_len.as<uint64_t>(), ctx->st)); ctx->launches++;
     CU(cudaMemcpyAsync(h_walk_len.data(), ctx->walk_len.p, (size_t)H * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(ctx->step_base.reserve(S2 * 4 + 4));
+    CU(launch_step_finalize(ctx->gbase.as<uint64_t>(), d_walk_off, H, S2, ctx->step_base.as<uint32_t>(), ctx->st)); ctx->launches++;
     CU(read_counters(ctx));                                             // also syncs: walk lengths + the monotonicity flag
     walks_monotone = ctx->h_ctr[CTR_NONMONO] ? 0 : 1;
-    const int T = tile_windows();
-    for (uint32_t h = 0; h < H; ++h) {
-        uint64_t len = h_walk_len[h];
-        if (len >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "walk longer than 2^31-1 bases (the reference's int32 position loop overflows there too)");
-        uint64_t nt = len >= (uint64_t)(w + k - 1) ? (len - k) / T + 1 : 0;
-        h_tile_base[h + 1] = h_tile_base[h] + nt;
-        max_tiles = std::max(max_tiles, nt);
-    }
-    CU(ctx->walk_tile_base.reserve(((size_t)H + 1) * 8));
-    CU(cudaMemcpyAsync(ctx->walk_tile_base.p, h_tile_base.data(), ((size_t)H + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
-    CU(ctx->step_base.reserve(S2 * 4 + 4));
-    CU(ctx->tile_first_step.reserve(h_tile_base[H] * 4 + 4));
-    CU(launch_step_finalize(ctx->gbase.as<uint64_t>(), ctx->step_len.as<uint32_t>(), d_walk_off, H, S2, w, ctx->walk_tile_base.as<uint64_t>(),
-                            ctx->step_base.as<uint32_t>(), ctx->tile_first_step.as<uint32_t>(), ctx->st)); ctx->launches++;
-    return PHI_OK;
+    for (uint32_t h = 0; h < H; ++h)
+        if (h_walk_len[h] >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "walk longer than 2^31-1 bases (the reference's int32 position loop overflows there too)");
+    return stage_chunks(ctx, k, w, d_walk_vtx, d_walk_off, S2);
 }
 
 
@@ -727,8 +791,8 @@ static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbi
     return PHI_OK;
 }
 
-// ---- stage: walks -> hits
-static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits, const std::vector<uint64_t> &h_walk_len, uint64_t max_tiles,
+// ---- stage: representative chunks -> hits
+static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits, const std::vector<uint64_t> &h_walk_len,
                        const uint32_t *d_walk_vtx, const uint64_t *d_walk_off, uint64_t n_steps_eff, int walks_monotone, RunOut &o)
 {
     const uint32_t H = ctx->n_walks;
@@ -741,36 +805,41 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
     o.path_pos = positions;
     CU(cudaEventRecord(ctx->ev[EV_WK0], ctx->st));
     CU(cudaEventRecord(ctx->ev[EV_WK1], ctx->st));
-    if (!H || !max_tiles) { CU(cudaMemsetAsync(ctx->mpw.p, 0, ((size_t)HM + 1) * 8, ctx->st)); o.n_hits = o.n_hit_vtx = 0; return PHI_OK; }
+    CU(cudaMemsetAsync(ctx->mpw.p, 0, ((size_t)HM + 1) * 8, ctx->st));
+    o.n_hits = o.n_hit_vtx = 0; o.path_hits = 0;
+    const uint32_t NT_ = ctx->n_tiles, NC = ctx->n_chunks;
+    if (!H || !NT_) return PHI_OK;
     // capacity estimate: emitted density 2/(w+1), vertices per anchor 1 + (k-1)/mean node length; exact re-run on overflow
     double dens = std::min(1.0, 2.0 / (w + 1.0)) * 1.3;
     double mean_node = n_steps_eff ? (double)bases / (double)n_steps_eff : 1.0;
-    uint64_t hit_cap = (uint64_t)((double)positions * dens) + 65536;
+    uint64_t hit_cap = (uint64_t)((double)ctx->unique_windows * dens) + 65536;
     uint64_t vtx_cap = (uint64_t)((double)hit_cap * std::min((double)k, 1.0 + (k - 1) / std::max(mean_node, 1.0)) * 1.2) + 65536;
+    CU(ctx->hseg_off.reserve((size_t)NT_ * SEG_PER_TILE * 4)); CU(ctx->hseg_cnt.reserve((size_t)NT_ * SEG_PER_TILE * 4));
     for (int attempt = 0;; ++attempt) {
         if (hit_cap >= (1ull << 32)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-1 walk hits on one GPU; shard the walks over more GPUs");
-        CU(ctx->hit_rank.reserve(hit_cap * 4)); CU(ctx->hit_walk.reserve(hit_cap * 4)); CU(ctx->hit_pos.reserve(hit_cap * 4));
+        CU(ctx->hit_rank.reserve(hit_cap * 4)); CU(ctx->hit_chunk.reserve(hit_cap * 4)); CU(ctx->hit_pos.reserve(hit_cap * 4));
         CU(ctx->hit_voff.reserve(hit_cap * 8)); CU(ctx->hit_nv.reserve(hit_cap));
         if (mode == WALK_MODE_ALL) CU(ctx->hit_hash.reserve(hit_cap * 8));
         CU(ctx->vtx_pool.reserve(vtx_cap * 4));
-        CU(cudaMemsetAsync(ctx->mpw.p, 0, ((size_t)HM + 1) * 8, ctx->st));
         CU(cudaMemsetAsync(d_ctr + CTR_HITS, 0, 2 * 8, ctx->st));
+        CU(cudaMemsetAsync(ctx->hseg_cnt.p, 0, (size_t)NT_ * SEG_PER_TILE * 4, ctx->st));
+        CU(cudaMemsetAsync(ctx->c_emitted.p, 0, (size_t)NC * 4, ctx->st));
+        CU(cudaMemsetAsync(ctx->c_hits.p, 0, (size_t)NC * 4, ctx->st));
         WalkSketchArgs A;
         A.layout = tile_layout(k, w, true); A.walks_monotone = walks_monotone;
         A.seg_bases = ctx->seg_bases.as<uint8_t>() + 16; A.seg_off = ctx->seg_off.as<uint64_t>(); A.top_order_map = ctx->top_order.as<int32_t>();
         A.walk_vtx = d_walk_vtx; A.walk_off = d_walk_off; A.step_base = ctx->step_base.as<uint32_t>();
-        A.walk_len = ctx->walk_len.as<uint64_t>(); A.walk_tile_base = ctx->walk_tile_base.as<uint64_t>();
-        A.tile_first_step = ctx->tile_first_step.as<uint32_t>();
+        A.walk_len = ctx->walk_len.as<uint64_t>(); A.tiles = ctx->tiles.as<TileRec>();
         A.k = k; A.w = w; A.mode = mode;
         A.spec = ctx->spec_a.as<uint64_t>(); A.dir = ctx->dir.as<uint32_t>(); A.dbits = dbits;
-        A.walk_id_base = wbase;
-        A.minimizers_per_walk = ctx->mpw.as<unsigned long long>() + wbase;
-        A.hit_rank = ctx->hit_rank.as<uint32_t>(); A.hit_walk = ctx->hit_walk.as<uint32_t>(); A.hit_pos = ctx->hit_pos.as<uint32_t>();
+        A.chunk_emitted = ctx->c_emitted.as<uint32_t>(); A.chunk_hits = ctx->c_hits.as<uint32_t>();
+        A.hseg_off = ctx->hseg_off.as<uint32_t>(); A.hseg_cnt = ctx->hseg_cnt.as<uint32_t>();
+        A.hit_rank = ctx->hit_rank.as<uint32_t>(); A.hit_chunk = ctx->hit_chunk.as<uint32_t>(); A.hit_pos = ctx->hit_pos.as<uint32_t>();
         A.hit_voff = ctx->hit_voff.as<uint64_t>(); A.hit_nv = ctx->hit_nv.as<uint8_t>();
         A.hit_hash = mode == WALK_MODE_ALL ? ctx->hit_hash.as<uint64_t>() : nullptr;
         A.vtx_pool = ctx->vtx_pool.as<int32_t>(); A.hit_cap = hit_cap; A.vtx_cap = vtx_cap; A.ctr = d_ctr;
         CU(cudaEventRecord(ctx->ev[EV_WK0], ctx->st));
-        CU(launch_walk_sketch(A, H, max_tiles, ctx->st)); ctx->launches++;
+        CU(launch_walk_sketch(A, NT_, ctx->st)); ctx->launches++;
         CU(cudaEventRecord(ctx->ev[EV_WK1], ctx->st));
         CU(read_counters(ctx));
         o.n_hits = ctx->h_ctr[CTR_HITS]; o.n_hit_vtx = ctx->h_ctr[CTR_HIT_VTX];
@@ -778,33 +847,40 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
         if (attempt) return ctx->fail(PHI_ERR_CUDA, "walk hit buffers overflowed twice (internal error)");
         hit_cap = o.n_hits + 1024; vtx_cap = o.n_hit_vtx + 1024;          // exact sizes are now known: run again
     }
+    // every member chunk emits what its representative emitted: per-walk minimizer counts, total hits
+    CU(cudaMemsetAsync(d_ctr + CTR_PATH_HITS, 0, 8, ctx->st));
+    CU(chunk_emitted(chunk_table(ctx), ctx->c_emitted.as<uint32_t>(), ctx->c_hits.as<uint32_t>(), wbase, ctx->mpw.as<unsigned long long>(), d_ctr,
+                     ctx->st, &ctx->launches));
     return PHI_OK;
 }
 
 // ---- stage: threshold filter, final order, CSR
-static void filter_args(phi_gpu_index_ctx *ctx, FilterArgs &A, uint64_t n, uint32_t n_spec, float threshold, uint32_t n_walks_global,
-                        const std::vector<uint64_t> &h_walk_gbase)
+static FilterArgs filter_args(phi_gpu_index_ctx *ctx, uint64_t n, const DevBuf &rank, const DevBuf &walk, const DevBuf &pos, const DevBuf &voff,
+                              const DevBuf &nv, const DevBuf &vtx, uint32_t n_spec, float threshold, uint32_t n_walks_global,
+                              const std::vector<uint64_t> &h_walk_gbase)
 {
-    A.n_hits = n; A.hit_rank = ctx->hit_rank.as<uint32_t>(); A.hit_walk = ctx->hit_walk.as<uint32_t>(); A.hit_pos = ctx->hit_pos.as<uint32_t>();
-    A.hit_voff = ctx->hit_voff.as<uint64_t>(); A.hit_nv = ctx->hit_nv.as<uint8_t>(); A.vtx_pool = ctx->vtx_pool.as<int32_t>();
+    FilterArgs A;
+    A.n_hits = n; A.hit_rank = rank.as<uint32_t>(); A.hit_walk = walk.as<uint32_t>(); A.hit_pos = pos.as<uint32_t>();
+    A.hit_voff = voff.as<uint64_t>(); A.hit_nv = nv.as<uint8_t>(); A.vtx_pool = vtx.as<int32_t>();
     A.n_ranks = n_spec;
     A.thr = threshold * (float)n_walks_global;                            // float * uint32 -> float, as ILP_index.cpp:698
     A.walk_gbase = ctx->walk_gbase.as<uint64_t>();
     A.gpos_bits = bits_for(h_walk_gbase.back()); A.rank_bits = bits_for(n_spec ? n_spec - 1 : 0);
+    return A;
 }
 
-// group table over the records of A (weight[i] occurrences each, 1 if weight == nullptr); fills W.hit_slot / g_rep / g_cnt
-static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, FilterWork &W, const uint32_t *weight)
+// group table over the records of A; a record stands for weight[i] occurrences, or for as many as its chunk has members
+// (chunk_weight), or for one.  Fills W.hit_slot / g_rep / g_cnt.
+static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, FilterWork &W, const uint32_t *weight, const uint32_t *chunk_weight)
 {
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
     const uint64_t n = A.n_hits;
-    // distinct (rank, vertex list) groups are usually far fewer than hits (one group per locus shared by many walks),
-    // so start small and grow on overflow instead of paying for a 2n-slot table every run
-    uint64_t gcap = 1024; while (gcap < n / 4) gcap <<= 1;
+    // distinct (rank, vertex list) groups are usually fewer than records, so start small and grow on overflow
+    uint64_t gcap = 1024; while (gcap < n / 2) gcap <<= 1;
     if (ctx->gcap_hint > gcap) gcap = ctx->gcap_hint;
     CU(ctx->vals_b.reserve(n * 4 + 4));
     W.hit_slot = ctx->vals_b.as<uint32_t>();                              // free until the survivor sort
-    W.weight = weight;
+    W.weight = weight; W.chunk_weight = chunk_weight;
     for (;;) {
         CU(ctx->g_rep.reserve(gcap * 4)); CU(ctx->g_cnt.reserve(gcap * 4));
         CU(fill_u32(ctx->g_rep.as<uint32_t>(), gcap, 0xFFFFFFFFu, ctx->st, &ctx->launches));
@@ -820,40 +896,67 @@ static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, Fi
     return PHI_OK;
 }
 
-// survivors (records of A whose rank is not flagged in rank_drop) -> final (rank, walk, j) order -> CSR in ctx->anchor_*
-static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, FilterWork &W, uint32_t n_walks_global, RunOut &o)
+// Instantiate the hits of the representative chunks whose rank survived for every member chunk -> ctx->x_* in
+// (walk, position) order; ns = number of records.
+static int expand_survivors(phi_gpu_index_ctx *ctx, int w, bool with_hash, uint64_t &ns)
+{
+    ns = 0;
+    const uint32_t NC = ctx->n_chunks;
+    if (!NC) return PHI_OK;
+    ChunkTable C = chunk_table(ctx);
+    CU(chunk_survivors(C, ctx->tiles.as<TileRec>(), ctx->n_tiles, ctx->hseg_off.as<uint32_t>(), ctx->hseg_cnt.as<uint32_t>(), ctx->hit_rank.as<uint32_t>(),
+                       ctx->rank_drop.as<uint8_t>(), ctx->c_surv.as<uint32_t>(), ctx->member_cnt.as<uint32_t>(), ctx->st, &ctx->launches));
+    CU(cudaMemsetAsync(ctx->member_cnt.as<uint32_t>() + NC, 0, 4, ctx->st));
+    CU(ctx->scan_scr.reserve(scan_u32_to_u64_scratch((uint64_t)NC + 2)));
+    CU(scan_u32_to_u64(ctx->member_cnt.as<uint32_t>(), ctx->member_off.as<uint64_t>(), (uint64_t)NC + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
+    CU(cudaMemcpyAsync(&ns, ctx->member_off.as<uint64_t>() + NC, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (ns >= (1ull << 32)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-1 anchors on one GPU; shard the walks over more GPUs");
+    if (!ns) return PHI_OK;
+    CU(ctx->x_rank.reserve(ns * 4)); CU(ctx->x_walk.reserve(ns * 4)); CU(ctx->x_pos.reserve(ns * 4)); CU(ctx->x_voff.reserve(ns * 8)); CU(ctx->x_nv.reserve(ns));
+    if (with_hash) CU(ctx->x_hash.reserve(ns * 8));
+    ExpandArgs X;
+    X.w = w; X.walk_id_base = ctx->world > 1 ? ctx->walk_id_base : 0;
+    X.member_off = ctx->member_off.as<uint64_t>(); X.hseg_off = ctx->hseg_off.as<uint32_t>(); X.hseg_cnt = ctx->hseg_cnt.as<uint32_t>();
+    X.rank_drop = ctx->rank_drop.as<uint8_t>();
+    X.hit_rank = ctx->hit_rank.as<uint32_t>(); X.hit_pos = ctx->hit_pos.as<uint32_t>(); X.hit_voff = ctx->hit_voff.as<uint64_t>();
+    X.hit_nv = ctx->hit_nv.as<uint8_t>(); X.hit_hash = with_hash ? ctx->hit_hash.as<uint64_t>() : nullptr;
+    X.x_rank = ctx->x_rank.as<uint32_t>(); X.x_walk = ctx->x_walk.as<uint32_t>(); X.x_pos = ctx->x_pos.as<uint32_t>();
+    X.x_voff = ctx->x_voff.as<uint64_t>(); X.x_nv = ctx->x_nv.as<uint8_t>(); X.x_hash = with_hash ? ctx->x_hash.as<uint64_t>() : nullptr;
+    CU(chunk_expand(C, X, ctx->st, &ctx->launches));
+    return PHI_OK;
+}
+
+// records of A (all of them survive) -> final (rank, walk, j) order -> CSR in ctx->anchor_*
+static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, bool presorted, bool key_order, uint32_t n_walks_global, RunOut &o)
 {
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
-    const uint64_t n = A.n_hits;
-    CU(cudaMemsetAsync(d_ctr + CTR_SURVIVORS, 0, 2 * 8, ctx->st));        // SURVIVORS, BIG_GROUPS
-    CU(ctx->flags.reserve(n * 4 + 4));
-    W.flags = ctx->flags.as<uint32_t>();
-    CU(filter_flag_survivors(A, W, ctx->st, &ctx->launches));
-    CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(n), scan_u32_to_u64_scratch(n + 1))));
-    CU(scan_u32_inplace(W.flags, n, ctx->scan_scr.p, ctx->st, &ctx->launches));
-    CU(read_counters(ctx));
-    const uint64_t ns = ctx->h_ctr[CTR_SURVIVORS];
+    const uint64_t ns = A.n_hits;
     o.n_surv = ns;
+    CU(ctx->anchor_off.reserve((ns + 1) * 8));
     if (!ns) { CU(cudaMemsetAsync(ctx->anchor_off.p, 0, 8, ctx->st)); return PHI_OK; }
-
+    FilterWork W; memset(&W, 0, sizeof(W));
+    W.rank_drop = ctx->rank_drop.as<uint8_t>(); W.ctr = d_ctr;
+    CU(cudaMemsetAsync(d_ctr + CTR_BIG_GROUPS, 0, 8, ctx->st));
     CU(ctx->keys_a.reserve(ns * 8)); CU(ctx->keys_b.reserve(ns * 8)); CU(ctx->vals_a.reserve(ns * 4)); CU(ctx->vals_b.reserve(ns * 4));
     CU(ctx->sort_scr.reserve(radix_sort_scratch(ns)));
+    CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(ns), scan_u32_to_u64_scratch(ns + 1))));
     W.keys_a = ctx->keys_a.as<uint64_t>(); W.keys_b = ctx->keys_b.as<uint64_t>();
     W.vals_a = ctx->vals_a.as<uint32_t>(); W.vals_b = ctx->vals_b.as<uint32_t>(); W.sort_scratch = ctx->sort_scr.p;
-    const bool combined = A.gpos_bits + A.rank_bits <= 64;
-    CU(filter_emit_keys(A, W, ns, combined, ctx->st, &ctx->launches));
+    CU(filter_sort_records(A, W, presorted, ctx->st, &ctx->launches));
     uint32_t *order = W.vals_a;
 
-    const uint32_t big_cap = (uint32_t)(ns / 48 + 1);
-    CU(ctx->big_list.reserve((size_t)big_cap * 8));
-    CU(filter_fix_multi(A, order, ns, ctx->big_list.as<uint32_t>(), big_cap, d_ctr, ctx->st, &ctx->launches));
-    CU(read_counters(ctx));
-    if (ctx->h_ctr[CTR_BIG_GROUPS]) {
-        CU(ctx->tmp_order.reserve(ns * 4));
-        CU(filter_fix_big(A, order, ctx->tmp_order.as<uint32_t>(), ctx->big_list.as<uint32_t>(), (uint32_t)ctx->h_ctr[CTR_BIG_GROUPS], ns, ctx->st, &ctx->launches));
+    if (key_order) {                                                      // (rank, walk) groups with several hits: std::map<std::string> order (:680-709)
+        const uint32_t big_cap = (uint32_t)(ns / 48 + 1);
+        CU(ctx->big_list.reserve((size_t)big_cap * 8));
+        CU(filter_fix_multi(A, order, ns, ctx->big_list.as<uint32_t>(), big_cap, d_ctr, ctx->st, &ctx->launches));
+        CU(read_counters(ctx));
+        if (ctx->h_ctr[CTR_BIG_GROUPS]) {
+            CU(ctx->tmp_order.reserve(ns * 4));
+            CU(filter_fix_big(A, order, ctx->tmp_order.as<uint32_t>(), ctx->big_list.as<uint32_t>(), (uint32_t)ctx->h_ctr[CTR_BIG_GROUPS], ns, ctx->st, &ctx->launches));
+        }
     }
     CU(ctx->nv_out.reserve((ns + 1) * 4));
-    CU(ctx->anchor_off.reserve((ns + 1) * 8));
     CU(cudaMemsetAsync(ctx->nv_out.as<uint32_t>() + ns, 0, 4, ctx->st));
     CU(filter_csr_sizes(A, order, ns, ctx->nv_out.as<uint32_t>(), ctx->st, &ctx->launches));
     CU(scan_u32_to_u64(ctx->nv_out.as<uint32_t>(), ctx->anchor_off.as<uint64_t>(), ns + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
@@ -884,7 +987,7 @@ __global__ void summary_emit_kernel(FilterArgs A, const uint32_t *g_rep, const u
     m_rank[j] = A.hit_rank[i]; m_cnt[j] = g_cnt[slot]; m_voff[j] = A.hit_voff[i]; m_nv[j] = A.hit_nv[i];
 }
 
-static int stage_filter(phi_gpu_index_ctx *ctx, const std::vector<uint64_t> &h_walk_gbase, uint32_t n_walks_global, float threshold, RunOut &o)
+static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, const std::vector<uint64_t> &h_walk_gbase, uint32_t n_walks_global, float threshold, RunOut &o)
 {
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
     CU(ctx->apw.reserve(((size_t)n_walks_global + 1) * 8));
@@ -897,34 +1000,51 @@ static int stage_filter(phi_gpu_index_ctx *ctx, const std::vector<uint64_t> &h_w
     CU(ctx->walk_gbase.reserve(h_walk_gbase.size() * 8));
     CU(cudaMemcpyAsync(ctx->walk_gbase.p, h_walk_gbase.data(), h_walk_gbase.size() * 8, cudaMemcpyHostToDevice, ctx->st));
     o.n_surv = 0; o.n_anchor_vtx = 0; o.n_filtered = 0;
-    FilterArgs A; FilterWork W; memset(&W, 0, sizeof(W));
+    FilterWork W; memset(&W, 0, sizeof(W));
     W.rank_drop = ctx->rank_drop.as<uint8_t>(); W.ctr = d_ctr;
+    const uint64_t n = o.n_hits;                                          // hits of the representative chunks
+    // the representatives' hits: hit_chunk takes the place of the walk id (its member count is the record's weight)
+    FilterArgs A = filter_args(ctx, n, ctx->hit_rank, ctx->hit_chunk, ctx->hit_pos, ctx->hit_voff, ctx->hit_nv, ctx->vtx_pool, o.n_spec, threshold,
+                               n_walks_global, h_walk_gbase);
+
+    if (mode == WALK_MODE_ALL) {
+        // sketch-only: every emitted minimizer of every walk, in (walk, position) order, no filter
+        uint64_t ns = 0;
+        int rc = expand_survivors(ctx, w, true, ns);
+        if (rc) return rc;
+        FilterArgs X = filter_args(ctx, ns, ctx->x_rank, ctx->x_walk, ctx->x_pos, ctx->x_voff, ctx->x_nv, ctx->vtx_pool, 1, 0.f, n_walks_global, h_walk_gbase);
+        X.rank_bits = 0;                                                  // already in final order
+        return order_and_csr(ctx, X, true, false, n_walks_global, o);
+    }
 
     if (ctx->world == 1) {
-        const uint64_t n = o.n_hits;
         if (!n) return PHI_OK;
-        filter_args(ctx, A, n, o.n_spec, threshold, n_walks_global, h_walk_gbase);
-        int rc = count_groups_adaptive(ctx, A, W, nullptr);
+        int rc = count_groups_adaptive(ctx, A, W, nullptr, ctx->c_ninst.as<uint32_t>());
         if (rc) return rc;
         CU(filter_mark_drops(A, W, ctx->st, &ctx->launches));
-        rc = order_and_csr(ctx, A, W, n_walks_global, o);
+        uint64_t ns = 0;
+        rc = expand_survivors(ctx, w, false, ns);
+        if (rc) return rc;
+        FilterArgs X = filter_args(ctx, ns, ctx->x_rank, ctx->x_walk, ctx->x_pos, ctx->x_voff, ctx->x_nv, ctx->vtx_pool, o.n_spec, threshold, n_walks_global, h_walk_gbase);
+        rc = order_and_csr(ctx, X, true, true, n_walks_global, o);
+        if (rc) return rc;
+        CU(read_counters(ctx));
         o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED];
-        return rc;
+        return PHI_OK;
     }
 
     // ---- multi-GPU, two phases (every rank takes part in every collective, also with zero hits):
     //  A. local groups -> one (rank, count, list) summary per group -> owner of the rank adds the counts up, applies the
     //     threshold, and the drop flags of all owners are shared;
-    //  B. only surviving hits travel to the owner of their rank, which orders them and builds its slice of the CSR.
+    //  B. the surviving hits are instantiated for the local walks and travel to the owner of their rank, which orders
+    //     them and builds its slice of the CSR.
     std::string err; NcclApi *nc = nccl_api(err);
     if (!nc || !ctx->comm) return ctx->fail(PHI_ERR_COMM, "communicator not initialised");
-    const int Wn = ctx->world, me = ctx->rank;
-    const uint64_t n = o.n_hits;
+    const int Wn = ctx->world;
     CU(cudaEventRecord(ctx->ev[EV_XH0], ctx->st));
-    filter_args(ctx, A, n, o.n_spec, threshold, n_walks_global, h_walk_gbase);
     uint64_t n_sum = 0;
     if (n) {
-        int rc = count_groups_adaptive(ctx, A, W, nullptr);
+        int rc = count_groups_adaptive(ctx, A, W, nullptr, ctx->c_ninst.as<uint32_t>());
         if (rc) return rc;
         CU(ctx->flags.reserve(n * 4 + 4)); CU(ctx->flags64.reserve((n + 1) * 8));
         CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(n), scan_u32_to_u64_scratch(n + 1))));
@@ -944,12 +1064,10 @@ static int stage_filter(phi_gpu_index_ctx *ctx, const std::vector<uint64_t> &h_w
     int rc = exchange_records(ctx, I, rs, rsv);
     if (rc) return rc;
     if (rs) {                                                             // owner: add the partial counts up, apply the threshold
-        FilterArgs B = A;
-        B.n_hits = rs; B.hit_rank = ctx->r_rank.as<uint32_t>(); B.hit_walk = ctx->r_walk.as<uint32_t>(); B.hit_pos = ctx->r_pos.as<uint32_t>();
-        B.hit_voff = ctx->r_voff.as<uint64_t>(); B.hit_nv = ctx->r_nv.as<uint8_t>(); B.vtx_pool = ctx->r_vtx.as<int32_t>();
+        FilterArgs B = filter_args(ctx, rs, ctx->r_rank, ctx->r_walk, ctx->r_pos, ctx->r_voff, ctx->r_nv, ctx->r_vtx, o.n_spec, threshold, n_walks_global, h_walk_gbase);
         FilterWork WB; memset(&WB, 0, sizeof(WB));
         WB.rank_drop = ctx->rank_drop.as<uint8_t>(); WB.ctr = d_ctr;
-        rc = count_groups_adaptive(ctx, B, WB, ctx->r_walk.as<uint32_t>());
+        rc = count_groups_adaptive(ctx, B, WB, ctx->r_walk.as<uint32_t>(), nullptr);
         if (rc) return rc;
         CU(filter_mark_drops(B, WB, ctx->st, &ctx->launches));             // also counts the flags (all in this rank's owned range)
     }
@@ -962,21 +1080,21 @@ static int stage_filter(phi_gpu_index_ctx *ctx, const std::vector<uint64_t> &h_w
     }
     NC(nc->GroupEnd());
     CU(cudaEventRecord(ctx->ev[EV_XH1], ctx->st));
-    (void)me;
-    // B: surviving hits -> owners
+    // B: surviving hits of the local walks -> owners
+    uint64_t ns_local = 0;
+    rc = expand_survivors(ctx, w, false, ns_local);
+    if (rc) return rc;
     RouteIn J;
-    J.rank = A.hit_rank; J.walk = A.hit_walk; J.pos = A.hit_pos; J.voff = A.hit_voff; J.nv = A.hit_nv; J.vtx = A.vtx_pool; J.n = n;
-    J.drop = ctx->rank_drop.as<uint8_t>();
+    J.rank = ctx->x_rank.as<uint32_t>(); J.walk = ctx->x_walk.as<uint32_t>(); J.pos = ctx->x_pos.as<uint32_t>(); J.voff = ctx->x_voff.as<uint64_t>();
+    J.nv = ctx->x_nv.as<uint8_t>(); J.vtx = ctx->vtx_pool.as<int32_t>(); J.n = ns_local; J.drop = nullptr;
     uint64_t rh = 0, rv = 0;
     rc = exchange_records(ctx, J, rh, rv);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[EV_XH2], ctx->st));
-    std::swap(ctx->hit_rank, ctx->r_rank); std::swap(ctx->hit_walk, ctx->r_walk); std::swap(ctx->hit_pos, ctx->r_pos);
-    std::swap(ctx->hit_voff, ctx->r_voff); std::swap(ctx->hit_nv, ctx->r_nv); std::swap(ctx->vtx_pool, ctx->r_vtx);
     o.n_hit_vtx = rv;
     if (!rh) return PHI_OK;
-    filter_args(ctx, A, rh, o.n_spec, threshold, n_walks_global, h_walk_gbase);
-    return order_and_csr(ctx, A, W, n_walks_global, o);
+    FilterArgs R = filter_args(ctx, rh, ctx->r_rank, ctx->r_walk, ctx->r_pos, ctx->r_voff, ctx->r_nv, ctx->r_vtx, o.n_spec, threshold, n_walks_global, h_walk_gbase);
+    return order_and_csr(ctx, R, false, true, n_walks_global, o);
 }
 
 // A result owns pinned buffers borrowed from its ctx's pool; freeing it hands them back (or releases them if the ctx is gone).
@@ -1081,10 +1199,10 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     CU(cudaEventRecord(ctx->ev[EV_H2D], ctx->st));
     CU(cudaMemsetAsync(ctx->ctr.p, 0, CTR_COUNT * 8, ctx->st));
     RunOut o;
-    std::vector<uint64_t> h_walk_len, h_tile_base; uint64_t max_tiles = 0, n_steps_eff = 0;
+    std::vector<uint64_t> h_walk_len; uint64_t n_steps_eff = 0;
     const uint32_t *d_walk_vtx; const uint64_t *d_walk_off;
     int walks_monotone = 1;
-    rc = stage_graph_prep(ctx, k, w, h_walk_len, h_tile_base, max_tiles, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone);
+    rc = stage_graph_prep(ctx, k, w, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[EV_PREP], ctx->st));
     int dbits = 0;
@@ -1096,7 +1214,7 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
         CU(cudaEventRecord(ctx->ev[EV_READS], ctx->st));
     }
     CU(cudaEventRecord(ctx->ev[EV_SPECTRUM], ctx->st));
-    rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, max_tiles, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, o);
+    rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, o);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[EV_WALKS], ctx->st));
 
@@ -1108,56 +1226,16 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
 
     phi_index_result *res = alloc_result(ctx);
     if (!res) return ctx->fail(PHI_ERR_NOMEM, "host allocation failed");
-    if (mode == WALK_MODE_PROBE) {
-        rc = stage_filter(ctx, h_walk_gbase, HG, prm->threshold, o);
-        if (rc) { phi_gpu_index_result_free(res); return rc; }
-    } else {
-        // sketch-only: order all emitted minimizers by (walk, position) and build the CSR without filtering
-        unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
-        const uint64_t n = o.n_hits;
-        CU(ctx->apw.reserve(((size_t)HG + 1) * 8));
-        CU(cudaMemsetAsync(ctx->apw.p, 0, ((size_t)HG + 1) * 8, ctx->st));
-        CU(ctx->rank_drop.reserve(4)); CU(cudaMemsetAsync(ctx->rank_drop.p, 0, 4, ctx->st));
-        CU(ctx->anchor_off.reserve((n + 1) * 8));
-        o.n_surv = n;
-        if (n) {
-            FilterArgs A;
-            A.n_hits = n; A.hit_rank = ctx->hit_rank.as<uint32_t>(); A.hit_walk = ctx->hit_walk.as<uint32_t>(); A.hit_pos = ctx->hit_pos.as<uint32_t>();
-            A.hit_voff = ctx->hit_voff.as<uint64_t>(); A.hit_nv = ctx->hit_nv.as<uint8_t>(); A.vtx_pool = ctx->vtx_pool.as<int32_t>();
-            A.n_ranks = 1; A.thr = 0;
-            CU(ctx->walk_gbase.reserve(h_walk_gbase.size() * 8));
-            CU(cudaMemcpyAsync(ctx->walk_gbase.p, h_walk_gbase.data(), h_walk_gbase.size() * 8, cudaMemcpyHostToDevice, ctx->st));
-            A.walk_gbase = ctx->walk_gbase.as<uint64_t>(); A.gpos_bits = bits_for(h_walk_gbase.back()); A.rank_bits = 1;
-            FilterWork W; memset(&W, 0, sizeof(W));
-            CU(ctx->flags.reserve(n * 4 + 4));
-            CU(ctx->keys_a.reserve(n * 8)); CU(ctx->keys_b.reserve(n * 8)); CU(ctx->vals_a.reserve(n * 4)); CU(ctx->vals_b.reserve(n * 4));
-            CU(ctx->sort_scr.reserve(radix_sort_scratch(n)));
-            CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(n), scan_u32_to_u64_scratch(n + 1))));
-            W.rank_drop = ctx->rank_drop.as<uint8_t>(); W.flags = ctx->flags.as<uint32_t>(); W.ctr = d_ctr;
-            W.keys_a = ctx->keys_a.as<uint64_t>(); W.keys_b = ctx->keys_b.as<uint64_t>();
-            W.vals_a = ctx->vals_a.as<uint32_t>(); W.vals_b = ctx->vals_b.as<uint32_t>(); W.sort_scratch = ctx->sort_scr.p;
-            CU(filter_flag_survivors(A, W, ctx->st, &ctx->launches));
-            CU(scan_u32_inplace(W.flags, n, ctx->scan_scr.p, ctx->st, &ctx->launches));
-            CU(filter_emit_keys(A, W, n, true, ctx->st, &ctx->launches));
-            CU(ctx->nv_out.reserve((n + 1) * 4));
-            CU(cudaMemsetAsync(ctx->nv_out.as<uint32_t>() + n, 0, 4, ctx->st));
-            CU(filter_csr_sizes(A, W.vals_a, n, ctx->nv_out.as<uint32_t>(), ctx->st, &ctx->launches));
-            CU(scan_u32_to_u64(ctx->nv_out.as<uint32_t>(), ctx->anchor_off.as<uint64_t>(), n + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
-            CU(ctx->anchor_rank.reserve(n * 4)); CU(ctx->anchor_walk.reserve(n * 4)); CU(ctx->anchor_vtx.reserve(o.n_hit_vtx * 4 + 4));
-            CU(filter_csr_fill(A, W.vals_a, n, ctx->anchor_off.as<uint64_t>(), ctx->anchor_rank.as<int32_t>(), ctx->anchor_walk.as<int32_t>(),
-                               ctx->anchor_vtx.as<int32_t>(), ctx->apw.as<unsigned long long>(), 0, HG, ctx->st, &ctx->launches));
-            o.n_anchor_vtx = o.n_hit_vtx;
-            if (hashes_out) {
-                // hashes in final order: gather on the host side after download (test-only path)
-            }
-        } else CU(cudaMemsetAsync(ctx->anchor_off.p, 0, 8, ctx->st));
-    }
+    rc = stage_filter(ctx, w, mode, h_walk_gbase, HG, prm->threshold, o);
+    if (rc) { phi_gpu_index_result_free(res); return rc; }
+    o.path_hits = ctx->h_ctr[CTR_PATH_HITS];                               // read back by the syncs of the filter stage
+    ctx->unique_hits = o.n_hits;
     CU(cudaEventRecord(ctx->ev[EV_FILTER], ctx->st));
 
     res->count_sp_r = (int32_t)o.n_spec; res->n_walks = HG; res->n_filtered = o.n_filtered;
     res->n_anchors = o.n_surv; res->n_anchor_vtx = o.n_anchor_vtx;
     res->read_kmer_positions = o.read_pos; res->path_kmer_positions = o.path_pos;
-    res->read_minimizers_emitted = o.read_emitted; res->path_hits = o.n_hits;
+    res->read_minimizers_emitted = o.read_emitted; res->path_hits = o.path_hits;
     if (do_download) {
         rc = download<uint64_t>(ctx, res, ctx->spec_a.p, mode == WALK_MODE_PROBE ? o.n_spec : 0, &res->spectrum);
         if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_rank.p, o.n_surv, &res->anchor_rank);
@@ -1172,17 +1250,17 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
         if (rc2) { phi_gpu_index_result_free(res); return rc2; }
     }
     uint64_t *hashes = nullptr; uint32_t *h_order = nullptr;
-    if (mode == WALK_MODE_ALL && hashes_out && o.n_hits) {
-        hashes = (uint64_t *)malloc(o.n_hits * 8); h_order = (uint32_t *)malloc(o.n_hits * 4);
-        CU(cudaMemcpyAsync(hashes, ctx->hit_hash.p, o.n_hits * 8, cudaMemcpyDeviceToHost, ctx->st));
-        CU(cudaMemcpyAsync(h_order, ctx->vals_a.p, o.n_hits * 4, cudaMemcpyDeviceToHost, ctx->st));
+    if (mode == WALK_MODE_ALL && hashes_out && o.n_surv) {
+        hashes = (uint64_t *)malloc(o.n_surv * 8); h_order = (uint32_t *)malloc(o.n_surv * 4);
+        CU(cudaMemcpyAsync(hashes, ctx->x_hash.p, o.n_surv * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(h_order, ctx->vals_a.p, o.n_surv * 4, cudaMemcpyDeviceToHost, ctx->st));
     }
     CU(cudaEventRecord(ctx->ev[EV_END], ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     for (uint32_t h = 0; h < HG; ++h) res->path_minimizers_emitted += res->minimizers_per_walk[h];
     if (mode == WALK_MODE_ALL && hashes_out) {
-        uint64_t *sorted = (uint64_t *)malloc(std::max<uint64_t>(o.n_hits, 1) * 8);
-        for (uint64_t i = 0; i < o.n_hits; ++i) sorted[i] = hashes[h_order[i]];
+        uint64_t *sorted = (uint64_t *)malloc(std::max<uint64_t>(o.n_surv, 1) * 8);
+        for (uint64_t i = 0; i < o.n_surv; ++i) sorted[i] = hashes[h_order[i]];
         free(hashes); free(h_order);
         *hashes_out = sorted;
     }
@@ -1224,6 +1302,22 @@ extern "C" int phi_gpu_index_sketch_walks(phi_gpu_index_ctx *ctx, const phi_grap
     int rc = phi_gpu_index_upload(ctx, graph, &none);
     if (rc) return rc;
     return run_pipeline(ctx, params, WALK_MODE_ALL, 1, out, hashes_out, 0.f, false);
+}
+
+extern "C" int phi_gpu_index_set_walk_sharing(phi_gpu_index_ctx *ctx, int chunk_shift, int share)
+{
+    if (!ctx) return PHI_ERR_ARG;
+    if (chunk_shift < 4 || chunk_shift > 24) return ctx->fail(PHI_ERR_ARG, "chunk_shift must be in [4, 24]");
+    ctx->chunk_shift = chunk_shift; ctx->dedupe = share ? 1 : 0;
+    return PHI_OK;
+}
+
+extern "C" int phi_gpu_index_last_sharing(const phi_gpu_index_ctx *ctx, phi_walk_sharing_stats *out)
+{
+    if (!ctx || !out) return PHI_ERR_ARG;
+    out->chunks = ctx->n_chunks; out->active_chunks = ctx->active_chunks; out->tiles = ctx->n_tiles;
+    out->unique_windows = ctx->unique_windows; out->unique_hits = ctx->unique_hits;
+    return PHI_OK;
 }
 
 extern "C" int phi_gpu_index_last_times(const phi_gpu_index_ctx *ctx, phi_stage_times *out)

@@ -205,7 +205,7 @@ __device__ __forceinline__ int step_of(const Tile &t, int p)
 }
 
 template <bool CLEAN>
-__device__ __forceinline__ void walk_tile_body(Tile &t, const WalkSketchArgs &A, uint32_t h)
+__device__ __forceinline__ void walk_tile_body(Tile &t, const WalkSketchArgs &A, const TileRec &tr, uint32_t tile)
 {
     const int tid = threadIdx.x;
     phase_canon<CLEAN>(t);
@@ -256,14 +256,19 @@ __device__ __forceinline__ void walk_tile_body(Tile &t, const WalkSketchArgs &A,
         if (tid == 0 && sc.tot_a) {
             s_base_hit = atomicAdd(&A.ctr[CTR_HITS], (unsigned long long)sc.tot_a);
             s_base_vtx = atomicAdd(&A.ctr[CTR_HIT_VTX], (unsigned long long)sc.tot_b);
+            if (s_base_hit + sc.tot_a <= A.hit_cap) {                // this batch's hits: one contiguous segment, in position order
+                A.hseg_off[(size_t)tile * SEG_PER_TILE + b0 / NT] = (uint32_t)s_base_hit;
+                A.hseg_cnt[(size_t)tile * SEG_PER_TILE + b0 / NT] = (uint32_t)sc.tot_a;
+            }
+            atomicAdd(&A.chunk_hits[tr.chunk], (uint32_t)sc.tot_a);
         }
         __syncthreads();
         if (hit) {
             unsigned long long hi_idx = s_base_hit + sc.ex_a, vo = s_base_vtx + sc.ex_b;
             if (hi_idx < A.hit_cap && vo + nv <= A.vtx_cap) {
                 A.hit_rank[hi_idx] = (uint32_t)rank;
-                A.hit_walk[hi_idx] = A.walk_id_base + h;
-                A.hit_pos[hi_idx] = (uint32_t)(t.g0 + a);
+                A.hit_chunk[hi_idx] = tr.chunk;
+                A.hit_pos[hi_idx] = (uint32_t)(t.g0 + a + A.w - (long long)tr.cbase);
                 A.hit_voff[hi_idx] = vo;
                 A.hit_nv[hi_idx] = (uint8_t)nv;
                 if (A.hit_hash) A.hit_hash[hi_idx] = hv;
@@ -273,30 +278,32 @@ __device__ __forceinline__ void walk_tile_body(Tile &t, const WalkSketchArgs &A,
         }
         __syncthreads();
     }
-    if (tid == 0 && emitted) atomicAdd(&A.minimizers_per_walk[h], (unsigned long long)emitted);
+    if (tid == 0 && emitted) atomicAdd(&A.chunk_emitted[tr.chunk], (uint32_t)emitted);
 }
 
 __global__ void __launch_bounds__(NT, 4)
 walk_sketch_kernel(WalkSketchArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t h = blockIdx.y;
+    const uint32_t tile = blockIdx.x;
+    const TileRec tr = A.tiles[tile];
+    const uint32_t h = tr.walk;
     const long long len = A.walk_len[h];
-    const long long tile = blockIdx.x;
-    if (len < (long long)A.w + A.k - 1) return;
-    if (tile * TILE_W > len - A.k) return;                           // no window ends in this tile
     const TileLayout &L = A.layout;
     Tile t = carve(smem, L, A.k, A.w);
-    t.g0 = tile * TILE_W - A.w;
+    // the tile owns the window end positions [e0, e1) of walk h (at most TILE_W); everything below is sized by what it really holds
+    t.M = (int)(tr.e1 - tr.e0) + A.w; t.M8 = (t.M + 7) & ~7; t.NB = t.M + A.k - 1;
+    const int nchunks = (t.NB + 7) >> 3;
+    t.g0 = (long long)tr.e0 - A.w;
     t.seq_len = len;
     set_window_bounds(t);
     const int tid = threadIdx.x;
 
     // ---- steps overlapping the tile's bases [base_lo, base_hi)
     const long long base_lo = t.g0 < 0 ? 0 : t.g0;
-    const long long base_hi = min(len, t.g0 + (long long)L.NB);
+    const long long base_hi = min(len, t.g0 + (long long)t.NB);
     const uint64_t wbeg = A.walk_off[h], wend = A.walk_off[h + 1];
-    const uint64_t s0 = wbeg + A.tile_first_step[A.walk_tile_base[h] + tile];
+    const uint64_t s0 = wbeg + tr.first_step;
     int n_steps = 0;
     for (uint64_t c0 = s0;; c0 += NT) {
         uint64_t s = c0 + tid; int ok = 0;
@@ -321,7 +328,7 @@ walk_sketch_kernel(WalkSketchArgs A)
     uint32_t dirty_any = 0;
     const int rel0 = (int)(base_lo - t.g0);                          // local index of base_lo (0, or w for tile 0)
     const int nb = (int)(base_hi - base_lo);                         // real bases staged
-    for (int c = tid; c < L.nchunks; c += NT) {
+    for (int c = tid; c < nchunks; c += NT) {
         const int q0 = 8 * c - rel0;                                 // chunk start relative to base_lo (may be < 0)
         uint64_t v = 0; int first = 0; uint32_t smask = 0;
         if (q0 + 8 > 0 && q0 < nb) {
@@ -348,7 +355,7 @@ walk_sketch_kernel(WalkSketchArgs A)
         t.cfirst[c] = (uint16_t)first; t.cmask[c] = (uint8_t)smask;
         dirty_any |= stage_chunk(t, c, v);
     }
-    if (__syncthreads_or(dirty_any != 0)) walk_tile_body<false>(t, A, h); else walk_tile_body<true>(t, A, h);
+    if (__syncthreads_or(dirty_any != 0)) walk_tile_body<false>(t, A, tr, tile); else walk_tile_body<true>(t, A, tr, tile);
 }
 
 // ================================================================== graph preparation
@@ -368,28 +375,13 @@ __device__ __forceinline__ uint32_t walk_of_step(const uint64_t *walk_off, uint3
     return lo;
 }
 
-// gbase = exclusive scan of step_len over ALL steps (u64).  Produces walk-relative step_base (u32) and, for every
-// tile of every walk, the index (relative to the walk's first step) of the step containing the tile's first base.
-__global__ void step_finalize_kernel(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
-                                     uint64_t n_steps, int w, const uint64_t *walk_tile_base, uint32_t *step_base,
-                                     uint32_t *tile_first_step)
+// gbase = exclusive scan of step_len over ALL steps (u64) -> walk-relative step_base (u32)
+__global__ void step_finalize_kernel(const uint64_t *gbase, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, uint32_t *step_base)
 {
     uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (s >= n_steps) return;
     uint32_t h = walk_of_step(walk_off, n_walks, s);
-    uint64_t b = gbase[s] - gbase[walk_off[h]];
-    uint32_t len = step_len[s];
-    step_base[s] = (uint32_t)b;
-    if (len == 0) return;
-    uint64_t ntile = walk_tile_base[h + 1] - walk_tile_base[h];
-    // tile t's first base is max(0, t*TILE_W - w); it lies in [b, b+len)
-    uint64_t t_lo = b == 0 ? 0 : (b + w + TILE_W - 1) / TILE_W;      // smallest t >= 1 with t*TILE_W - w >= b (t = 0 handled by b == 0)
-    if (b != 0 && t_lo == 0) t_lo = 1;
-    for (uint64_t t = t_lo; t < ntile; ++t) {
-        long long first = (long long)t * TILE_W - w; if (first < 0) first = 0;
-        if ((uint64_t)first >= b + len) break;
-        if ((uint64_t)first >= b) tile_first_step[walk_tile_base[h] + t] = (uint32_t)(s - walk_off[h]);
-    }
+    step_base[s] = (uint32_t)(gbase[s] - gbase[walk_off[h]]);
 }
 
 // walk_len[h] (bases) from the global scan
@@ -453,14 +445,13 @@ cudaError_t launch_read_sketch(const ReadSketchArgs &A, uint64_t n_tiles, cudaSt
     return cudaGetLastError();
 }
 
-cudaError_t launch_walk_sketch(const WalkSketchArgs &A, uint32_t n_walks, uint64_t max_tiles, cudaStream_t st)
+cudaError_t launch_walk_sketch(const WalkSketchArgs &A, uint32_t n_tiles, cudaStream_t st)
 {
-    if (!n_walks || !max_tiles) return cudaSuccess;
+    if (!n_tiles) return cudaSuccess;
     size_t smem = (size_t)A.layout.bytes;
     cudaError_t e = cudaFuncSetAttribute(walk_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)max_tiles, n_walks);
-    walk_sketch_kernel<<<grid, NT, smem, st>>>(A);
+    walk_sketch_kernel<<<n_tiles, NT, smem, st>>>(A);
     return cudaGetLastError();
 }
 
@@ -479,13 +470,11 @@ cudaError_t launch_walk_len(const uint64_t *gbase, const uint32_t *step_len, con
     return cudaGetLastError();
 }
 
-cudaError_t launch_step_finalize(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
-                                 uint64_t n_steps, int w, const uint64_t *walk_tile_base, uint32_t *step_base,
-                                 uint32_t *tile_first_step, cudaStream_t st)
+cudaError_t launch_step_finalize(const uint64_t *gbase, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, uint32_t *step_base,
+                                 cudaStream_t st)
 {
     if (!n_steps) return cudaSuccess;
-    step_finalize_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(gbase, step_len, walk_off, n_walks, n_steps, w,
-                                                                           walk_tile_base, step_base, tile_first_step);
+    step_finalize_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(gbase, walk_off, n_walks, n_steps, step_base);
     return cudaGetLastError();
 }
 

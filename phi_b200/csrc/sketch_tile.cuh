@@ -27,7 +27,7 @@
 
 namespace phi {
 
-constexpr int TILE_W = 2048;     // windows per tile
+constexpr int TILE_W = TILE_WINDOWS;   // windows per tile (kernels.h)
 constexpr int NT = 256;          // threads per tile CTA
 constexpr int MAX_W = 256;
 constexpr int MAX_K = 32;
@@ -337,6 +337,7 @@ __device__ __forceinline__ int phase_runs(const Tile &t, uint16_t *runs, int *ha
     #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
         const int e = t.w + wid * PER_WARP + r * 32 + lane;
+        if (e - lane >= t.e_hi) { ballots[r] = 0; mine[r] = 0; continue; }  // warp-uniform: a short tile has no windows here (nor further on)
         const bool valid = SeqModel<MULTI>::window_valid(t, e);
         int a = valid ? window_argmin<CLEAN>(t, e) : -1;
         int prev = __shfl_up_sync(0xFFFFFFFFu, a, 1);

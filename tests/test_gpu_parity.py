@@ -157,3 +157,38 @@ def test_full_size_properties(gpu):
     assert_same_result(got, gpu.run(sg.graph, rd2)) if False else None
     got3 = gpu.run(sg.graph, rd2)
     assert np.array_equal(got3.spectrum, got.spectrum) and np.array_equal(got3.anchor_vtx, got.anchor_vtx)
+
+
+@pytest.mark.parametrize("shift,share", [(4, True), (7, True), (11, False), (16, True), (24, True)])
+def test_walk_sharing_does_not_change_results(gpu, shift, share):
+    """Chunk boundaries and sharing only change the amount of work: tiny chunks (shorter than the w / k-1 context),
+    no sharing at all, chunks longer than a tile, one chunk per walk — all bit-identical to the oracle."""
+    sg = synth.make_graph(211, 120000, 9, lower_frac=0.01, n_frac=0.002)
+    g = sg.graph
+    # walk 3 is repeated verbatim (fully shared), walk 5 is cut short (shares a prefix only, ends inside a chunk)
+    wo = g.walk_off.astype(np.int64)
+    walks = [g.walk_vtx[wo[h]:wo[h + 1]] for h in range(g.n_walks)]
+    walks.append(walks[3].copy())
+    walks.append(walks[5][:len(walks[5]) // 3])
+    walks.append(walks[5][len(walks[5]) // 2:])
+    g2 = phi_b200.Graph(g.seg_off, g.seg_bases, np.concatenate([[0], np.cumsum([len(x) for x in walks])]),
+                        np.concatenate(walks), g.top_order_map)
+    rd = synth.make_reads(211, sg, 3.0, lower_frac=0.01, n_frac=0.002)
+    want = phi_io.oracle_index(g2, rd, 31, 25, 0.7)
+    try:
+        gpu.set_walk_sharing(shift, share)
+        got = gpu.run(g2, rd, 31, 25, 0.7)
+        st = gpu.sharing()
+        res, hashes = gpu.sketch_walks(g2, 21, 11)
+    finally:
+        gpu.set_walk_sharing()
+    assert_same_result(want, got)
+    assert st["unique_windows"] <= got.path_kmer_positions and st["unique_hits"] <= got.path_hits
+    if share and shift <= 11:
+        assert st["unique_windows"] < 0.7 * got.path_kmer_positions      # 9 walks from 8 founders + a verbatim copy: real sharing
+    if not share:
+        assert st["unique_windows"] == got.path_kmer_positions and st["unique_hits"] == got.path_hits
+    ref, ref_hashes = gpu.sketch_walks(g2, 21, 11)
+    assert np.array_equal(hashes, ref_hashes) and np.array_equal(res.anchor_vtx, ref.anchor_vtx)
+    assert np.array_equal(res.anchor_off, ref.anchor_off) and np.array_equal(res.anchor_walk, ref.anchor_walk)
+    assert res.minimizers_per_walk.tolist() == ref.minimizers_per_walk.tolist()
