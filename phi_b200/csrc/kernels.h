@@ -79,7 +79,7 @@ struct ReadSketchArgs {
     uint64_t n_reads, total_bases;
     const uint64_t *tile_first_read;  // [n_tiles]
     int k, w;
-    uint64_t *table; uint64_t table_mask;
+    uint64_t *table; uint64_t table_mult, table_limit;   // home slot = umulhi(key, table_mult); slots [0, table_limit), table[table_limit] stays EMPTY
     unsigned long long *ctr;
 };
 
@@ -147,8 +147,14 @@ cudaError_t scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, void *scratc
 size_t radix_sort_scratch(uint64_t n);
 cudaError_t radix_sort_u64(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, uint64_t n, int bit_lo, int bit_hi,
                            void *scratch, cudaStream_t st, uint64_t *launches);
-// compact the non-empty slots of the spectrum table into out (order arbitrary); count written to *d_count
-cudaError_t table_compact(const uint64_t *table, uint64_t cap, uint64_t *out, unsigned long long *d_count, cudaStream_t st, uint64_t *launches);
+// Order-preserving spectrum table (sketch_kernels.cu: table_insert): slots [0, limit) + one EMPTY sentinel at table[limit].
+constexpr uint64_t TABLE_PAD = 4096;      // probe room behind the last home slot (no wrap-around)
+constexpr uint64_t TABLE_BLOCK = 2048;    // slots per block of the count / write kernels
+// sort every probe cluster in place -> the occupied slots are in ascending order; then count per block
+size_t table_blocks(uint64_t limit);
+cudaError_t table_sort_and_count(uint64_t *table, uint64_t limit, uint32_t *block_cnt, cudaStream_t st, uint64_t *launches);
+// block_off = exclusive scan of block_cnt: write the occupied slots in slot order to out
+cudaError_t table_write_ordered(const uint64_t *table, uint64_t limit, const uint32_t *block_off, uint64_t *out, cudaStream_t st, uint64_t *launches);
 // radix directory over the top dbits bits of a sorted key array: dir[b] = lower_bound(prefix b), dir[2^dbits] = n
 cudaError_t build_directory(const uint64_t *sorted, uint32_t n, int dbits, uint32_t *dir, cudaStream_t st, uint64_t *launches);
 cudaError_t fill_u64(uint64_t *p, uint64_t n, uint64_t v, cudaStream_t st, uint64_t *launches);

@@ -42,14 +42,16 @@ struct DevBuf {                       // grow-only device buffer
 // pinned host buffer recycled through the ctx's pool (result arrays land here: D2H at full PCIe speed, no staging copy)
 struct PinnedBuf { void *p = nullptr; size_t cap = 0; };
 
-enum { EV_START, EV_H2D, EV_PREP, EV_READS, EV_SPECTRUM, EV_WALKS, EV_FILTER, EV_END, EV_RK0, EV_RK1, EV_WK0, EV_WK1, EV_XS0, EV_XS1, EV_XH0, EV_XH1, EV_XH2, EV_COUNT };
+enum { EV_START, EV_H2D, EV_PREP0, EV_PREP, EV_RD0, EV_READS, EV_SPECTRUM, EV_WALKS, EV_FILTER, EV_END, EV_RK0, EV_RK1, EV_WK0, EV_WK1, EV_XS0, EV_XS1, EV_XH0, EV_XH1, EV_XH2, EV_COUNT };
 
 }  // namespace
 
 struct phi_gpu_index_ctx {
     int device = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;             // main stream: reads, spectrum, walk sketch, filter, result copies
+    cudaStream_t st2 = nullptr;            // second stream: graph upload + graph preparation / chunking, concurrent with the read stage
     cudaEvent_t ev[EV_COUNT] = {};
+    cudaEvent_t ev_sync = nullptr;         // cross-stream ordering (no timing)
     std::string err = "no error";
     uint64_t launches = 0;
     phi_stage_times times = {};
@@ -63,7 +65,8 @@ struct phi_gpu_index_ctx {
     // work buffers
     DevBuf step_len, gbase, step_base, walk_len, tile_first_read, scan_scr, ctr;
     DevBuf walk_off_c, walk_vtx_c, flags64;
-    DevBuf table, spec_a, spec_b, sort_scr, dir;
+    DevBuf table, tblk, spec_a, spec_b, sort_scr, dir;
+    uint32_t *h_tot = nullptr;             // pinned: occupied slots of the spectrum table
     DevBuf mpw, hit_rank, hit_chunk, hit_pos, hit_voff, hit_nv, hit_hash, vtx_pool;
     // walk chunks (chunks.cu): boundaries, fingerprints, representatives, tiles, hit segments, expanded survivors
     DevBuf tlen, tprefix, coord, cflags, cpos, chunk_step, c_walk, c_L, c_R, c_lo, c_hi, c_h1, c_h2, c_slot, c_rep, c_ninst, c_ntile, c_tile_base, ctable, tiles;
@@ -72,6 +75,8 @@ struct phi_gpu_index_ctx {
     DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
     DevBuf anchor_off, anchor_rank, anchor_walk, anchor_vtx, apw, walk_gbase;
     unsigned long long *h_ctr = nullptr;   // pinned mirror of the counter block
+    // what the second stream uses instead of ctr / h_ctr / scan_scr / flags / flags64 / nv_out (swapped in by PrepScope)
+    DevBuf ctr2, scan_scr2, flags2, flags64_2, nv_out2; unsigned long long *h_ctr2 = nullptr;
     std::vector<PinnedBuf> pinned_pool;    // free pinned buffers (returned by phi_gpu_index_result_free)
 
     // multi-GPU (set by comm_init)
@@ -116,9 +121,14 @@ extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
     phi_gpu_index_ctx *ctx = new phi_gpu_index_ctx();
     ctx->device = device;
     if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    if ((e = cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
+    cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming);
     if ((e = cudaHostAlloc((void **)&ctx->h_ctr, CTR_COUNT * 8, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    if ((e = cudaHostAlloc((void **)&ctx->h_tot, 64, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    if ((e = cudaHostAlloc((void **)&ctx->h_ctr2, CTR_COUNT * 8, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     if ((e = ctx->ctr.reserve(CTR_COUNT * 8)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    if ((e = ctx->ctr2.reserve(CTR_COUNT * 8)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     { std::lock_guard<std::mutex> lk(g_live_mu); g_live_ctx.insert(ctx); }
     *out = ctx;
     return PHI_OK;
@@ -129,9 +139,11 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
-    DevBuf *bufs[] = {&ctx->seg_off, &ctx->seg_bases, &ctx->walk_off, &ctx->walk_vtx, &ctx->top_order, &ctx->read_off, &ctx->read_bases,
+    if (ctx->st2) cudaStreamSynchronize(ctx->st2);
+    DevBuf *bufs[] = {&ctx->ctr2, &ctx->scan_scr2, &ctx->flags2, &ctx->flags64_2, &ctx->nv_out2,
+                      &ctx->seg_off, &ctx->seg_bases, &ctx->walk_off, &ctx->walk_vtx, &ctx->top_order, &ctx->read_off, &ctx->read_bases,
                       &ctx->step_len, &ctx->gbase, &ctx->step_base, &ctx->walk_len,
-                      &ctx->tile_first_read, &ctx->scan_scr, &ctx->ctr, &ctx->walk_off_c, &ctx->walk_vtx_c, &ctx->flags64, &ctx->table,
+                      &ctx->tile_first_read, &ctx->scan_scr, &ctx->ctr, &ctx->walk_off_c, &ctx->walk_vtx_c, &ctx->flags64, &ctx->table, &ctx->tblk,
                       &ctx->spec_a, &ctx->spec_b, &ctx->sort_scr, &ctx->dir, &ctx->mpw, &ctx->hit_rank, &ctx->hit_chunk, &ctx->hit_pos,
                       &ctx->tlen, &ctx->tprefix, &ctx->coord, &ctx->cflags, &ctx->cpos, &ctx->chunk_step, &ctx->c_walk, &ctx->c_L, &ctx->c_R, &ctx->c_lo,
                       &ctx->c_hi, &ctx->c_h1, &ctx->c_h2, &ctx->c_slot, &ctx->c_rep, &ctx->c_ninst, &ctx->c_ntile, &ctx->c_tile_base, &ctx->ctable,
@@ -151,8 +163,12 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
         ctx->pinned_pool.clear();
     }
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->h_ctr2) cudaFreeHost(ctx->h_ctr2);
+    if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->st) cudaStreamDestroy(ctx->st);
+    if (ctx->st2) cudaStreamDestroy(ctx->st2);
     delete ctx;
 }
 
@@ -164,9 +180,11 @@ static int check_views(phi_gpu_index_ctx *ctx, const phi_graph_view *g, const ph
     return PHI_OK;
 }
 
-extern "C" int phi_gpu_index_upload(phi_gpu_index_ctx *ctx, const phi_graph_view *g, const phi_reads_view *r)
+// Host -> device copies, issued without waiting: the reads on the main stream (the read stage starts right behind them),
+// the graph on the second stream (the graph preparation follows it there).  The caller's buffers must stay valid until both
+// streams have been synchronised.
+static int upload_async(phi_gpu_index_ctx *ctx, const phi_graph_view *g, const phi_reads_view *r)
 {
-    if (!ctx) return PHI_ERR_ARG;
     int rc = check_views(ctx, g, r);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
@@ -187,20 +205,30 @@ extern "C" int phi_gpu_index_upload(phi_gpu_index_ctx *ctx, const phi_graph_view
     CU(ctx->walk_vtx.reserve(ctx->n_steps * 4 + 4));
     CU(ctx->read_off.reserve((ctx->n_reads + 1) * 8));
     CU(ctx->read_bases.reserve(ctx->read_total + 64));
-    CU(cudaMemcpyAsync(ctx->seg_off.p, g->n_vtx ? g->seg_off : zero_off, ((size_t)g->n_vtx + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
     // sequence buffers carry 16 readable bytes in front and zero padding behind: the sketch kernels use unaligned 8-byte loads
-    CU(cudaMemsetAsync(ctx->seg_bases.p, 0, 16, ctx->st));
-    CU(cudaMemsetAsync((char *)ctx->seg_bases.p + 16 + ctx->seg_total, 0, 32, ctx->st));
-    if (ctx->seg_total) CU(cudaMemcpyAsync((char *)ctx->seg_bases.p + 16, g->seg_bases, ctx->seg_total, cudaMemcpyHostToDevice, ctx->st));
-    if (g->n_vtx) CU(cudaMemcpyAsync(ctx->top_order.p, g->top_order_map, (size_t)g->n_vtx * 4, cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaMemcpyAsync(ctx->walk_off.p, g->n_walks ? g->walk_off : zero_off, ((size_t)g->n_walks + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
-    if (ctx->n_steps) CU(cudaMemcpyAsync(ctx->walk_vtx.p, g->walk_vtx, ctx->n_steps * 4, cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaMemcpyAsync(ctx->read_off.p, ctx->n_reads ? r->read_off : zero_off, (ctx->n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaMemsetAsync(ctx->read_bases.p, 0, 16, ctx->st));
-    if (ctx->read_total) CU(cudaMemcpyAsync((char *)ctx->read_bases.p + 16, r->read_bases, ctx->read_total, cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaMemsetAsync((char *)ctx->read_bases.p + 16 + ctx->read_total, 0, 32, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    cudaStream_t sa = ctx->st, sb = ctx->st2;
+    CU(cudaMemcpyAsync(ctx->read_off.p, ctx->n_reads ? r->read_off : zero_off, (ctx->n_reads + 1) * 8, cudaMemcpyHostToDevice, sa));
+    CU(cudaMemsetAsync(ctx->read_bases.p, 0, 16, sa));
+    if (ctx->read_total) CU(cudaMemcpyAsync((char *)ctx->read_bases.p + 16, r->read_bases, ctx->read_total, cudaMemcpyHostToDevice, sa));
+    CU(cudaMemsetAsync((char *)ctx->read_bases.p + 16 + ctx->read_total, 0, 32, sa));
+    CU(cudaMemcpyAsync(ctx->seg_off.p, g->n_vtx ? g->seg_off : zero_off, ((size_t)g->n_vtx + 1) * 8, cudaMemcpyHostToDevice, sb));
+    CU(cudaMemsetAsync(ctx->seg_bases.p, 0, 16, sb));
+    CU(cudaMemsetAsync((char *)ctx->seg_bases.p + 16 + ctx->seg_total, 0, 32, sb));
+    if (ctx->seg_total) CU(cudaMemcpyAsync((char *)ctx->seg_bases.p + 16, g->seg_bases, ctx->seg_total, cudaMemcpyHostToDevice, sb));
+    if (g->n_vtx) CU(cudaMemcpyAsync(ctx->top_order.p, g->top_order_map, (size_t)g->n_vtx * 4, cudaMemcpyHostToDevice, sb));
+    CU(cudaMemcpyAsync(ctx->walk_off.p, g->n_walks ? g->walk_off : zero_off, ((size_t)g->n_walks + 1) * 8, cudaMemcpyHostToDevice, sb));
+    if (ctx->n_steps) CU(cudaMemcpyAsync(ctx->walk_vtx.p, g->walk_vtx, ctx->n_steps * 4, cudaMemcpyHostToDevice, sb));
     ctx->have_inputs = true;
+    return PHI_OK;
+}
+
+extern "C" int phi_gpu_index_upload(phi_gpu_index_ctx *ctx, const phi_graph_view *g, const phi_reads_view *r)
+{
+    if (!ctx) return PHI_ERR_ARG;
+    int rc = upload_async(ctx, g, r);
+    if (rc) { ctx->have_inputs = false; return rc; }
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaStreamSynchronize(ctx->st2));
     return PHI_OK;
 }
 
@@ -276,6 +304,20 @@ struct RunOut {                    // device-side products of one run
 
 }  // namespace
 
+// While alive, the ctx works on the second stream with that stream's own counters and scratch buffers.
+namespace {
+struct PrepScope {
+    phi_gpu_index_ctx *c;
+    explicit PrepScope(phi_gpu_index_ctx *ctx) : c(ctx) { swap(); }
+    ~PrepScope() { swap(); }
+    void swap()
+    {
+        std::swap(c->st, c->st2); std::swap(c->ctr, c->ctr2); std::swap(c->h_ctr, c->h_ctr2);
+        std::swap(c->scan_scr, c->scan_scr2); std::swap(c->flags, c->flags2); std::swap(c->flags64, c->flags64_2); std::swap(c->nv_out, c->nv_out2);
+    }
+};
+}  // namespace
+
 // ---- stage: graph preparation: step base offsets, walk lengths, then the chunk table and the tiles of the representative
 // chunks (depends on k and w through the chunk context)
 static ChunkTable chunk_table(phi_gpu_index_ctx *ctx)
@@ -342,11 +384,15 @@ static int stage_chunks(phi_gpu_index_ctx *ctx, int k, int w, const uint32_t *d_
 static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<uint64_t> &h_walk_len, const uint32_t *&d_walk_vtx,
                             const uint64_t *&d_walk_off, uint64_t &n_steps_eff, int &walks_monotone)
 {
+    PrepScope on_second_stream(ctx);                                    // everything below: ctx->st is the second stream
     walks_monotone = 1;
     const uint32_t H = ctx->n_walks; const uint64_t S = ctx->n_steps;
     d_walk_vtx = ctx->walk_vtx.as<uint32_t>(); d_walk_off = ctx->walk_off.as<uint64_t>(); n_steps_eff = S;
     h_walk_len.assign(H, 0);
     ctx->n_chunks = ctx->n_tiles = 0; ctx->unique_windows = 0;
+    CU(cudaEventRecord(ctx->ev[EV_PREP0], ctx->st));
+    CU(cudaMemsetAsync(ctx->ctr.p, 0, CTR_COUNT * 8, ctx->st));
+    memset(ctx->h_ctr, 0, CTR_COUNT * 8);
     if (!H) return PHI_OK;
     CU(ctx->step_len.reserve(S * 4 + 4));
     CU(ctx->gbase.reserve((S + 1) * 8));
@@ -723,44 +769,74 @@ static int exchange_records(phi_gpu_index_ctx *ctx, const RouteIn &I, uint64_t &
     return PHI_OK;
 }
 
-// ---- stage: reads -> ranked spectrum (sorted distinct hashes + radix directory)
-static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbits)
+// ---- stage: reads -> ranked spectrum (sorted distinct hashes + radix directory).  Two halves so that the graph
+// preparation can be issued on the second stream while the read kernel runs.
+namespace { struct ReadsState { uint64_t n_tiles = 0, cap = 0; }; }
+
+static int reads_sketch_launch(phi_gpu_index_ctx *ctx, int k, int w, const ReadsState &rs)
+{
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    const uint64_t limit = rs.cap + TABLE_PAD;                              // slots [0, limit) + the EMPTY sentinel
+    CU(ctx->table.reserve((limit + 1) * 8));
+    CU(fill_u64(ctx->table.as<uint64_t>(), limit + 1, TABLE_EMPTY, ctx->st, &ctx->launches));
+    CU(cudaMemsetAsync(d_ctr, 0, 4 * 8, ctx->st));                         // DISTINCT (unused), OVERFLOW, HAS_MAXKEY, READ_EMITTED
+    ReadSketchArgs A;
+    A.layout = tile_layout(k, w, false);
+    A.read_bases = ctx->read_bases.as<uint8_t>() + 16; A.read_off = ctx->read_off.as<uint64_t>();
+    A.n_reads = ctx->n_reads; A.total_bases = ctx->read_total; A.tile_first_read = ctx->tile_first_read.as<uint64_t>();
+    A.k = k; A.w = w; A.table = ctx->table.as<uint64_t>(); A.table_mult = rs.cap; A.table_limit = limit; A.ctr = d_ctr;
+    CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st));
+    CU(launch_read_sketch(A, rs.n_tiles, ctx->st)); ctx->launches++;
+    CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
+    // probe clusters sorted in place -> the table is in ascending order; per-block counts -> offsets -> total
+    const size_t nb = table_blocks(limit);
+    CU(ctx->tblk.reserve((nb + 2) * 4));
+    CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(nb + 1), (size_t)1024)));
+    CU(table_sort_and_count(ctx->table.as<uint64_t>(), limit, ctx->tblk.as<uint32_t>(), ctx->st, &ctx->launches));
+    CU(cudaMemsetAsync(ctx->tblk.as<uint32_t>() + nb, 0, 4, ctx->st));
+    CU(scan_u32_inplace(ctx->tblk.as<uint32_t>(), nb + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
+    CU(cudaMemcpyAsync(ctx->h_tot, ctx->tblk.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, ctx->st));
+    return PHI_OK;
+}
+
+static int stage_reads_begin(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &rs)
 {
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
     const int T = tile_windows();
     const uint64_t G = ctx->read_total, R = ctx->n_reads;
-    const uint64_t n_tiles = (R && G >= (uint64_t)(w + k - 1)) ? (G - k) / T + 1 : 0;
-    uint64_t n_spec = 0;
+    rs.n_tiles = (R && G >= (uint64_t)(w + k - 1)) ? (G - k) / T + 1 : 0;
+    CU(cudaEventRecord(ctx->ev[EV_RD0], ctx->st));
     CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st));
     CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
-    if (n_tiles) {
-        count_positions_kernel<<<(unsigned)((R + 255) / 256), 256, 0, ctx->st>>>(ctx->read_off.as<uint64_t>(), R, k, w, d_ctr + CTR_READ_POS);
-        CU(cudaGetLastError()); ctx->launches++;
-        CU(ctx->tile_first_read.reserve(n_tiles * 8));
-        CU(launch_read_tile_dir(ctx->read_off.as<uint64_t>(), R, w, n_tiles, ctx->tile_first_read.as<uint64_t>(), ctx->st)); ctx->launches++;
-        // expected minimizer density is 2/(w+1); size the table for ~35% load at that density, retry on overflow
-        double dens = std::min(1.0, 2.6 / (w + 1.0));
-        uint64_t want = (uint64_t)((double)G * dens * 2.0) + 1024, cap = 1024;
-        while (cap < want) cap <<= 1;
+    if (!rs.n_tiles) return PHI_OK;
+    count_positions_kernel<<<(unsigned)((R + 255) / 256), 256, 0, ctx->st>>>(ctx->read_off.as<uint64_t>(), R, k, w, d_ctr + CTR_READ_POS);
+    CU(cudaGetLastError()); ctx->launches++;
+    CU(ctx->tile_first_read.reserve(rs.n_tiles * 8));
+    CU(launch_read_tile_dir(ctx->read_off.as<uint64_t>(), R, w, rs.n_tiles, ctx->tile_first_read.as<uint64_t>(), ctx->st)); ctx->launches++;
+    // expected minimizer density is 2/(w+1); size the table for ~35% load at that density, retry on overflow
+    double dens = std::min(1.0, 2.6 / (w + 1.0));
+    uint64_t want = (uint64_t)((double)G * dens * 2.0) + 1024;
+    rs.cap = 1024;
+    while (rs.cap < want) rs.cap <<= 1;
+    return reads_sketch_launch(ctx, k, w, rs);
+}
+
+static int stage_reads_finish(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &rs, RunOut &o, int &dbits)
+{
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    uint64_t n_spec = 0;
+    if (rs.n_tiles) {
         for (;;) {
-            CU(ctx->table.reserve(cap * 8));
-            CU(fill_u64(ctx->table.as<uint64_t>(), cap, TABLE_EMPTY, ctx->st, &ctx->launches));
-            CU(cudaMemsetAsync(d_ctr, 0, 4 * 8, ctx->st));                 // DISTINCT, OVERFLOW, HAS_MAXKEY, READ_EMITTED
-            ReadSketchArgs A;
-            A.layout = tile_layout(k, w, false);
-            A.read_bases = ctx->read_bases.as<uint8_t>() + 16; A.read_off = ctx->read_off.as<uint64_t>();
-            A.n_reads = R; A.total_bases = G; A.tile_first_read = ctx->tile_first_read.as<uint64_t>();
-            A.k = k; A.w = w; A.table = ctx->table.as<uint64_t>(); A.table_mask = cap - 1; A.ctr = d_ctr;
-            CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st));
-            CU(launch_read_sketch(A, n_tiles, ctx->st)); ctx->launches++;
-            CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
             CU(read_counters(ctx));
-            if (!ctx->h_ctr[CTR_OVERFLOW] && ctx->h_ctr[CTR_DISTINCT] * 10 <= cap * 8) break;
-            cap <<= 1;
+            if (!ctx->h_ctr[CTR_OVERFLOW]) break;                          // probing ran off the padding (table far too small): double it
+            rs.cap <<= 1;
+            int rc = reads_sketch_launch(ctx, k, w, rs);
+            if (rc) return rc;
         }
+        const uint64_t cap = rs.cap;
         o.read_emitted = ctx->h_ctr[CTR_READ_EMITTED];
         o.read_pos = ctx->h_ctr[CTR_READ_POS];
-        const uint64_t nd = ctx->h_ctr[CTR_DISTINCT];
+        const uint64_t nd = *ctx->h_tot;                                   // occupied slots (copied by the same sync)
         const bool maxkey = ctx->h_ctr[CTR_HAS_MAXKEY] != 0;
         n_spec = nd + (maxkey ? 1 : 0);
         if (n_spec >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^31-1 distinct read minimizers (count_sp_r is int32 in the reference)");
@@ -768,9 +844,7 @@ static int stage_reads(phi_gpu_index_ctx *ctx, int k, int w, RunOut &o, int &dbi
         CU(ctx->spec_a.reserve((n_spec + 1) * 8));
         CU(ctx->spec_b.reserve((n_spec + 1) * 8));
         CU(ctx->sort_scr.reserve(radix_sort_scratch(std::max<uint64_t>(n_spec, 1))));
-        CU(cudaMemsetAsync(d_ctr + CTR_COMPACT, 0, 8, ctx->st));
-        CU(table_compact(ctx->table.as<uint64_t>(), cap, ctx->spec_a.as<uint64_t>(), d_ctr + CTR_COMPACT, ctx->st, &ctx->launches));
-        CU(radix_sort_u64(ctx->spec_a.as<uint64_t>(), ctx->spec_b.as<uint64_t>(), nullptr, nullptr, nd, 0, 64, ctx->sort_scr.p, ctx->st, &ctx->launches));
+        CU(table_write_ordered(ctx->table.as<uint64_t>(), cap + TABLE_PAD, ctx->tblk.as<uint32_t>(), ctx->spec_a.as<uint64_t>(), ctx->st, &ctx->launches));
         if (maxkey) CU(fill_u64(ctx->spec_a.as<uint64_t>() + nd, 1, TABLE_EMPTY, ctx->st, &ctx->launches));
     } else {
         CU(cudaEventRecord(ctx->ev[EV_READS], ctx->st));
@@ -1163,13 +1237,13 @@ static int download(phi_gpu_index_ctx *ctx, phi_index_result *res, const void *d
     return PHI_OK;
 }
 
-static void collect_times(phi_gpu_index_ctx *ctx, float h2d_ms)
+static void collect_times(phi_gpu_index_ctx *ctx)
 {
     auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return ms; };
     phi_stage_times &t = ctx->times;
-    t.h2d_ms = h2d_ms;
-    t.graph_prep_ms = el(EV_H2D, EV_PREP);
-    t.read_sketch_ms = el(EV_PREP, EV_READS);
+    t.h2d_ms = el(EV_START, EV_H2D);                                     // host -> device copies overlap the read stage (two streams)
+    t.graph_prep_ms = el(EV_PREP0, EV_PREP);                             // second stream, concurrent with the read stage
+    t.read_sketch_ms = el(EV_RD0, EV_READS);
     t.spectrum_ms = el(EV_READS, EV_SPECTRUM);
     t.walk_sketch_ms = el(EV_SPECTRUM, EV_WALKS);
     t.filter_ms = el(EV_WALKS, EV_FILTER);
@@ -1187,7 +1261,7 @@ static void collect_times(phi_gpu_index_ctx *ctx, float h2d_ms)
 }
 
 static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int mode, int do_download, phi_index_result **out,
-                        uint64_t **hashes_out, float h2d_ms, bool start_recorded)
+                        uint64_t **hashes_out, bool uploading)
 {
     if (!ctx->have_inputs) return ctx->fail(PHI_ERR_ARG, "no inputs uploaded");
     int rc = validate_params(ctx, prm);
@@ -1195,25 +1269,34 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     CU(cudaSetDevice(ctx->device));
     const int k = prm->k, w = prm->w;
     ctx->launches = 0;
-    if (!start_recorded) CU(cudaEventRecord(ctx->ev[EV_START], ctx->st));
-    CU(cudaEventRecord(ctx->ev[EV_H2D], ctx->st));
+    if (!uploading) { CU(cudaEventRecord(ctx->ev[EV_START], ctx->st)); CU(cudaEventRecord(ctx->ev[EV_H2D], ctx->st)); }
     CU(cudaMemsetAsync(ctx->ctr.p, 0, CTR_COUNT * 8, ctx->st));
+    memset(ctx->h_ctr, 0, CTR_COUNT * 8);                                 // the host mirror starts from the same state
     RunOut o;
     std::vector<uint64_t> h_walk_len; uint64_t n_steps_eff = 0;
     const uint32_t *d_walk_vtx; const uint64_t *d_walk_off;
     int walks_monotone = 1;
-    rc = stage_graph_prep(ctx, k, w, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone);
-    if (rc) return rc;
-    CU(cudaEventRecord(ctx->ev[EV_PREP], ctx->st));
+    // main stream: read sketch kernel in flight ...
     int dbits = 0;
+    ReadsState rs;
     if (mode == WALK_MODE_PROBE) {
-        rc = stage_reads(ctx, k, w, o, dbits);
+        rc = stage_reads_begin(ctx, k, w, rs);
         if (rc) return rc;
     } else {
+        CU(cudaEventRecord(ctx->ev[EV_RD0], ctx->st));
         CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st)); CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
         CU(cudaEventRecord(ctx->ev[EV_READS], ctx->st));
     }
+    // ... while the second stream prepares the graph (its host-side waits only cover that stream)
+    rc = stage_graph_prep(ctx, k, w, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[EV_PREP], ctx->st2));
+    if (mode == WALK_MODE_PROBE) {
+        rc = stage_reads_finish(ctx, k, w, rs, o, dbits);
+        if (rc) return rc;
+    }
     CU(cudaEventRecord(ctx->ev[EV_SPECTRUM], ctx->st));
+    CU(cudaStreamWaitEvent(ctx->st, ctx->ev[EV_PREP], 0));               // the walk stage needs both
     rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, o);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[EV_WALKS], ctx->st));
@@ -1264,7 +1347,7 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
         free(hashes); free(h_order);
         *hashes_out = sorted;
     }
-    collect_times(ctx, h2d_ms);
+    collect_times(ctx);
     *out = res;
     return PHI_OK;
 }
@@ -1273,7 +1356,7 @@ extern "C" int phi_gpu_index_run_resident(phi_gpu_index_ctx *ctx, const phi_inde
 {
     if (!ctx || !out) return PHI_ERR_ARG;
     *out = nullptr;
-    return run_pipeline(ctx, params, WALK_MODE_PROBE, download_result, out, nullptr, 0.f, false);
+    return run_pipeline(ctx, params, WALK_MODE_PROBE, download_result, out, nullptr, false);
 }
 
 extern "C" int phi_gpu_index_run(phi_gpu_index_ctx *ctx, const phi_graph_view *graph, const phi_reads_view *reads, const phi_index_params *params,
@@ -1285,12 +1368,12 @@ extern "C" int phi_gpu_index_run(phi_gpu_index_ctx *ctx, const phi_graph_view *g
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventRecord(ctx->ev[EV_START], ctx->st));
-    rc = phi_gpu_index_upload(ctx, graph, reads);
-    if (rc) return rc;
-    CU(cudaEventRecord(ctx->ev[EV_H2D], ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    float h2d = 0; cudaEventElapsedTime(&h2d, ctx->ev[EV_START], ctx->ev[EV_H2D]);
-    return run_pipeline(ctx, params, WALK_MODE_PROBE, 1, out, nullptr, h2d, true);
+    rc = upload_async(ctx, graph, reads);                                   // reads -> main stream, graph -> second stream; nothing waits here
+    if (rc) { cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st2); ctx->have_inputs = false; return rc; }
+    CU(cudaEventRecord(ctx->ev[EV_H2D], ctx->st2));                         // the graph is the last thing to arrive
+    rc = run_pipeline(ctx, params, WALK_MODE_PROBE, 1, out, nullptr, true);
+    if (rc) { cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st2); }   // the caller's buffers may go away after we return
+    return rc;
 }
 
 extern "C" int phi_gpu_index_sketch_walks(phi_gpu_index_ctx *ctx, const phi_graph_view *graph, const phi_index_params *params,
@@ -1301,7 +1384,7 @@ extern "C" int phi_gpu_index_sketch_walks(phi_gpu_index_ctx *ctx, const phi_grap
     phi_reads_view none = {0, nullptr, nullptr};
     int rc = phi_gpu_index_upload(ctx, graph, &none);
     if (rc) return rc;
-    return run_pipeline(ctx, params, WALK_MODE_ALL, 1, out, hashes_out, 0.f, false);
+    return run_pipeline(ctx, params, WALK_MODE_ALL, 1, out, hashes_out, false);
 }
 
 extern "C" int phi_gpu_index_set_walk_sharing(phi_gpu_index_ctx *ctx, int chunk_shift, int share)

@@ -236,30 +236,65 @@ cudaError_t radix_sort_u64(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a,
     return cudaSuccess;
 }
 
-// ------------------------------------------------------------------ table compaction
-__global__ void __launch_bounds__(256) table_compact_kernel(const uint64_t *table, uint64_t cap, uint64_t *out, unsigned long long *count)
+// ------------------------------------------------------------------ ordered spectrum table -> sorted array
+// A probe cluster is a maximal run of occupied slots.  Every key of a cluster has its home slot inside the cluster, homes are
+// monotone in the key, and clusters are separated by an EMPTY slot: sorting each cluster in place sorts the table.
+// One thread per cluster head; clusters are short (load <= ~50 %, uniform hashes), so this is a few compares per key.
+__global__ void table_cluster_sort_kernel(uint64_t *table, uint64_t limit)
+{
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= limit) return;
+    if (table[s] == TABLE_EMPTY || (s && table[s - 1] != TABLE_EMPTY)) return;   // not a cluster head
+    for (uint64_t a = s + 1; table[a] != TABLE_EMPTY; ++a) {                      // table[limit] is EMPTY: stops there at the latest
+        uint64_t x = table[a], b = a;
+        while (b > s && table[b - 1] > x) { table[b] = table[b - 1]; --b; }
+        table[b] = x;
+    }
+}
+
+__global__ void __launch_bounds__(256) table_count_kernel(const uint64_t *table, uint64_t limit, uint32_t *block_cnt)
+{
+    uint64_t base = (uint64_t)blockIdx.x * TABLE_BLOCK + threadIdx.x;
+    uint32_t c = 0;
+    #pragma unroll
+    for (int i = 0; i < (int)(TABLE_BLOCK / 256); ++i) { uint64_t j = base + (uint64_t)i * 256; c += j < limit && table[j] != TABLE_EMPTY; }
+    __shared__ uint32_t scratch[32];
+    uint32_t tot;
+    block_exclusive<uint32_t>(c, &tot, scratch);
+    if (threadIdx.x == 0) block_cnt[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256) table_write_kernel(const uint64_t *table, uint64_t limit, const uint32_t *block_off, uint64_t *out)
 {
     __shared__ uint32_t scratch[32];
-    __shared__ unsigned long long s_base;
-    constexpr int I = 8;
-    uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * I;
+    constexpr int I = (int)(TABLE_BLOCK / 256);
+    uint64_t base = (uint64_t)blockIdx.x * TABLE_BLOCK + (uint64_t)threadIdx.x * I;   // consecutive slots per thread: slot order is kept
     uint64_t v[I]; uint32_t c = 0;
     #pragma unroll
-    for (int i = 0; i < I; ++i) { v[i] = base + i < cap ? table[base + i] : TABLE_EMPTY; c += v[i] != TABLE_EMPTY; }
+    for (int i = 0; i < I; ++i) { v[i] = base + i < limit ? table[base + i] : TABLE_EMPTY; c += v[i] != TABLE_EMPTY; }
     uint32_t tot;
     uint32_t ex = block_exclusive<uint32_t>(c, &tot, scratch);
-    if (threadIdx.x == 0) s_base = tot ? atomicAdd(count, (unsigned long long)tot) : 0ull;
-    __syncthreads();
-    uint64_t o = s_base + ex;
+    uint64_t o = (uint64_t)block_off[blockIdx.x] + ex;
     #pragma unroll
     for (int i = 0; i < I; ++i) if (v[i] != TABLE_EMPTY) out[o++] = v[i];
 }
 
-cudaError_t table_compact(const uint64_t *table, uint64_t cap, uint64_t *out, unsigned long long *d_count, cudaStream_t st, uint64_t *launches)
+size_t table_blocks(uint64_t limit) { return (size_t)((limit + TABLE_BLOCK - 1) / TABLE_BLOCK); }
+
+cudaError_t table_sort_and_count(uint64_t *table, uint64_t limit, uint32_t *block_cnt, cudaStream_t st, uint64_t *launches)
 {
-    if (!cap) return cudaSuccess;
-    uint64_t nb = (cap + 2047) / 2048;
-    table_compact_kernel<<<(unsigned)nb, 256, 0, st>>>(table, cap, out, d_count);
+    if (!limit) return cudaSuccess;
+    table_cluster_sort_kernel<<<(unsigned)((limit + 255) / 256), 256, 0, st>>>(table, limit);
+    PHI_LAUNCH_CHECK();
+    table_count_kernel<<<(unsigned)table_blocks(limit), 256, 0, st>>>(table, limit, block_cnt);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t table_write_ordered(const uint64_t *table, uint64_t limit, const uint32_t *block_off, uint64_t *out, cudaStream_t st, uint64_t *launches)
+{
+    if (!limit) return cudaSuccess;
+    table_write_kernel<<<(unsigned)table_blocks(limit), 256, 0, st>>>(table, limit, block_off, out);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

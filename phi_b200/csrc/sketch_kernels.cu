@@ -38,23 +38,23 @@ __device__ __forceinline__ Scan2 block_scan2(uint32_t *scratch /* >= 32 words */
 }
 
 // ================================================================== reads
-// Insert into the open-addressing spectrum table (linear probing, u64 keys, EMPTY = ~0).
-// The key ~0 itself is recorded in flags[FLAG_HAS_MAXKEY] instead of the table.
-__device__ __forceinline__ void table_insert(uint64_t *table, uint64_t mask, uint64_t key, unsigned long long *ctr)
+// Insert into the ORDER-PRESERVING open-addressing spectrum table: the home slot is a monotone function of the key
+// (top bits of the hash: umulhi(key, mult)), collisions probe upwards without wrap-around.  Keys therefore end up sorted
+// at the granularity of probe clusters (runs of occupied slots), and sorting each short cluster in place
+// (primitives.cu: table_sort_clusters) leaves the whole table in ascending order — no radix sort of the spectrum.
+// u64 keys, EMPTY = ~0; the key ~0 itself is recorded in ctr[CTR_HAS_MAXKEY] instead of the table.
+__device__ __forceinline__ void table_insert(uint64_t *table, uint64_t mult, uint64_t limit, uint64_t key, unsigned long long *ctr)
 {
     if (key == TABLE_EMPTY) { ctr[CTR_HAS_MAXKEY] = 1; return; }
-    uint64_t slot = key & mask;
-    for (uint64_t tries = 0; tries <= mask; ++tries) {
+    for (uint64_t slot = __umul64hi(key, mult); slot < limit; ++slot) {
         uint64_t cur = table[slot];
         if (cur == key) return;
         if (cur == TABLE_EMPTY) {
             uint64_t old = atomicCAS((unsigned long long *)&table[slot], (unsigned long long)TABLE_EMPTY, (unsigned long long)key);
-            if (old == TABLE_EMPTY) { atomicAdd(&ctr[CTR_DISTINCT], 1ull); return; }
-            if (old == key) return;
+            if (old == TABLE_EMPTY || old == key) return;
         }
-        slot = (slot + 1) & mask;
     }
-    ctr[CTR_OVERFLOW] = 1;
+    ctr[CTR_OVERFLOW] = 1;                                           // ran off the padding behind the last home slot: the host retries larger
 }
 
 // unaligned 8-byte load (two aligned loads + funnel); the buffers are padded so that p-7 .. p+15 is always readable
@@ -93,7 +93,7 @@ __device__ __forceinline__ void read_tile_body(Tile &t, const ReadSketchArgs &A)
         uint64_t prev = (ent & 0x8000) ? 0xFFFFFFFFFFFFFFFFull : t.hash[tid];
         uint64_t carry = t.hash[cnt];
         bool emit = have && h != prev;
-        if (emit) table_insert(A.table, A.table_mask, h, A.ctr);
+        if (emit) table_insert(A.table, A.table_mult, A.table_limit, h, A.ctr);
         emitted += __syncthreads_count(emit);
         if (tid == 0) t.hash[0] = carry;
     }
