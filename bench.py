@@ -249,8 +249,7 @@ def main_gpu(args):
     full = ix.run(gp, rp, k, w, 1.0)
     assert full.n_anchors == n_anchors_seen
     h2d = sum(a.nbytes for a in (g.seg_off, g.seg_bases, g.walk_off, g.walk_vtx, g.top_order_map, rd.read_off, rd.read_bases))
-    d2h = sum(a.nbytes for a in (full.spectrum, full.anchor_rank, full.anchor_walk, full.anchor_off, full.anchor_vtx,
-                                 full.minimizers_per_walk, full.anchors_per_walk))
+    d2h = full.wire_bytes()
     e2e_value = units * args.steps / dt_e2e
 
     peak, peak_src = measured_peak()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PHI_GPU_INDEX_ABI_VERSION 1
+#define PHI_GPU_INDEX_ABI_VERSION 2
 
 /* status codes (0 == ok); text via phi_gpu_last_error() */
 enum {
@@ -84,12 +84,12 @@ typedef struct {
  * count_sp_r / spectrum : ILP_index.cpp:631-636 — number of distinct read
  *     minimizer hashes and the hashes themselves in ascending unsigned order;
  *     rank r <-> spectrum[r].
- * anchors (CSR, FINAL post-filter order) : ILP_index.cpp:643-716.  Anchor a is
- *     Anchor_hits[anchor_rank[a]][anchor_walk[a]][j] with j = its index among
- *     the anchors of the same (rank, walk), and its vertex list is
- *     anchor_vtx[anchor_off[a] .. anchor_off[a+1]).  Anchors are sorted by
- *     (rank, walk, j), so a single forward pass with push_back rebuilds the
- *     reference's nested vectors exactly.
+ * anchors (FINAL post-filter order) : ILP_index.cpp:643-716.  Anchors are sorted by (rank, walk, j) with j = the
+ *     index of an anchor among the anchors of the same (rank, walk), i.e. anchor a is Anchor_hits[r][anchor_walk[a]][j]
+ *     for the rank r with rank_off[r] <= a < rank_off[r + 1].  Its vertex list has anchor_len[a] vertices (1..k) and
+ *     the lists lie back to back in anchor_vtx in anchor order, so one forward pass with push_back rebuilds the
+ *     reference's nested vectors exactly (integration/phi_adapter.hpp).  The layout is compact on purpose: the result
+ *     crosses PCIe (8 + 4 + 1 bytes per rank / anchor / anchor instead of three 4..8-byte arrays per anchor).
  * minimizers_per_walk : kmer_index[h].size(), log line ILP_index.cpp:563.
  * anchors_per_walk    : log lines ILP_index.cpp:725-735.
  * n_filtered          : filtered_kmers, ILP_index.cpp:719-721 (log :738-743).
@@ -101,9 +101,9 @@ typedef struct {
     uint64_t n_anchors;
     uint64_t n_anchor_vtx;
     const uint64_t *spectrum;            /* [count_sp_r] */
-    const int32_t *anchor_rank;          /* [n_anchors] */
+    const uint64_t *rank_off;            /* [count_sp_r + 1]; NULL when count_sp_r == 0 (sketch-only results) */
     const int32_t *anchor_walk;          /* [n_anchors] */
-    const uint64_t *anchor_off;          /* [n_anchors + 1] */
+    const uint8_t *anchor_len;           /* [n_anchors] */
     const int32_t *anchor_vtx;           /* [n_anchor_vtx] */
     const uint64_t *minimizers_per_walk; /* [n_walks] */
     const uint64_t *anchors_per_walk;    /* [n_walks] */
@@ -191,7 +191,7 @@ int phi_gpu_index_last_sharing(const phi_gpu_index_ctx *ctx, phi_walk_sharing_st
  * Walk sketch alone == ILP_index::index_kmers for every walk
  * (/root/reference/src/ILP_index.cpp:359-445): every emitted minimizer of every
  * walk, in path order, with its hash and its vertex list.  Returned through a
- * phi_index_result in which  spectrum == NULL,  anchor_rank[a] is unused (0),
+ * phi_index_result in which  spectrum == NULL,  rank_off == NULL (count_sp_r == 0),
  * anchors are in (walk, path position) order and  *hashes_out[a]  is the
  * minimizer hash.  Free *hashes_out with phi_gpu_index_free_u64.
  */

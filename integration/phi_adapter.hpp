@@ -69,9 +69,12 @@ inline void run_front_end(ILP_index &ix, std::vector<std::pair<std::string, std:
     // ---- rebuild the nested vectors the model construction indexes (:643, :716)
     count_sp_r = res->count_sp_r;
     Anchor_hits.assign(count_sp_r, std::vector<std::vector<std::vector<int32_t> > >(ix.num_walks));
-    for (uint64_t a = 0; a < res->n_anchors; ++a)
-        Anchor_hits[res->anchor_rank[a]][res->anchor_walk[a]].push_back(
-            std::vector<int32_t>(res->anchor_vtx + res->anchor_off[a], res->anchor_vtx + res->anchor_off[a + 1]));
+    const int32_t *vtx = res->anchor_vtx;
+    for (int32_t r = 0; r < count_sp_r; ++r)
+        for (uint64_t a = res->rank_off[r]; a < res->rank_off[r + 1]; ++a) {
+            Anchor_hits[r][res->anchor_walk[a]].push_back(std::vector<int32_t>(vtx, vtx + res->anchor_len[a]));
+            vtx += res->anchor_len[a];
+        }
 
     std::cerr << "Number of Anchors" << std::endl;                                                 // :724
     for (uint32_t h = 0; h < ix.num_walks; ++h)

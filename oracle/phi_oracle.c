@@ -221,6 +221,24 @@ static int check_params(const phi_index_params *p)
     return p && p->k >= 1 && p->k <= 255 && p->w >= 1;
 }
 
+/* public layout of the anchors (include/phi_gpu_index.h): per-rank offsets + per-anchor list lengths instead of the
+ * per-anchor rank / offset arrays this file works with; consumes (frees) arank and aoff */
+static void to_compact(phi_index_result *r, int32_t *arank, uint64_t *aoff, int32_t n_ranks)
+{
+    const uint64_t na = r->n_anchors;
+    uint8_t *len = (uint8_t *)malloc(na ? na : 1);
+    for (uint64_t a = 0; a < na; ++a) len[a] = (uint8_t)(aoff[a + 1] - aoff[a]);
+    r->anchor_len = len;
+    r->rank_off = NULL;
+    if (n_ranks > 0) {
+        uint64_t *ro = (uint64_t *)calloc((size_t)n_ranks + 1, 8);
+        for (uint64_t a = 0; a < na; ++a) ro[arank[a] + 1]++;
+        for (int32_t q = 0; q < n_ranks; ++q) ro[q + 1] += ro[q];
+        r->rank_off = ro;
+    }
+    free(arank); free(aoff);
+}
+
 int phi_oracle_sketch_walks(const phi_graph_view *g, const phi_index_params *prm, int n_threads,
                             phi_index_result **out, uint64_t **hashes_out)
 {
@@ -257,7 +275,8 @@ int phi_oracle_sketch_walks(const phi_graph_view *g, const phi_index_params *prm
     }
     free(ws);
     r->n_walks = H; r->n_anchors = na; r->n_anchor_vtx = nv;
-    r->anchor_rank = arank; r->anchor_walk = awalk; r->anchor_off = aoff; r->anchor_vtx = avtx;
+    r->anchor_walk = awalk; r->anchor_vtx = avtx;
+    to_compact(r, arank, aoff, 0);
     r->minimizers_per_walk = mpw; r->anchors_per_walk = apw;
     r->path_minimizers_emitted = na;
     *out = r; *hashes_out = hashes;
@@ -325,6 +344,9 @@ int phi_oracle_index_run(const phi_graph_view *g, const phi_reads_view *rd, cons
 
     /* ---- loop C: match, ILP_index.cpp:495-526, :643-655.  Hits in (walk, path) order, bucketed by rank. */
     uint64_t na = wsr->n_anchors;
+    uint64_t *wsr_off = (uint64_t *)malloc((na + 1) * 8);                /* offsets of the walk minimizers' vertex lists */
+    wsr_off[0] = 0;
+    for (uint64_t a = 0; a < na; ++a) wsr_off[a + 1] = wsr_off[a] + wsr->anchor_len[a];
     int64_t *hit_rank = (int64_t *)malloc((na ? na : 1) * sizeof(int64_t));
     uint64_t *per_rank = (uint64_t *)calloc(ns + 1, 8);
     uint64_t nhits = 0;
@@ -354,7 +376,7 @@ int phi_oracle_index_run(const phi_graph_view *g, const phi_reads_view *rd, cons
         for (uint64_t i = 0; i < n; ++i) {
             uint64_t a = by_rank[b + i];
             hs[i].walk = wsr->anchor_walk[a]; hs[i].seq = i;
-            hs[i].v = wsr->anchor_vtx + wsr->anchor_off[a]; hs[i].nv = (int)(wsr->anchor_off[a + 1] - wsr->anchor_off[a]);
+            hs[i].v = wsr->anchor_vtx + wsr_off[a]; hs[i].nv = (int)wsr->anchor_len[a];
             hs[i].key = (char *)malloc((size_t)hs[i].nv * 12 + 1);
             char *q = hs[i].key;
             for (int j = 0; j < hs[i].nv; ++j) q += sprintf(q, "%d_", hs[i].v[j]);   /* to_string(v) + "_" */
@@ -386,10 +408,11 @@ int phi_oracle_index_run(const phi_graph_view *g, const phi_reads_view *rd, cons
     r->n_walks = H; r->n_filtered = n_filtered;
     r->n_anchors = o_rank.n; r->n_anchor_vtx = o_vtx.n;
     r->spectrum = ns ? all.a : (free(all.a), (uint64_t *)calloc(1, 8));
-    r->anchor_rank = o_rank.a ? o_rank.a : (int32_t *)calloc(1, 4);
     r->anchor_walk = o_walk.a ? o_walk.a : (int32_t *)calloc(1, 4);
-    r->anchor_off = o_off.a;
     r->anchor_vtx = o_vtx.a ? o_vtx.a : (int32_t *)calloc(1, 4);
+    r->count_sp_r = (int32_t)ns;
+    to_compact(r, o_rank.a ? o_rank.a : (int32_t *)calloc(1, 4), o_off.a, (int32_t)ns);
+    free(wsr_off);
     uint64_t *mpw = (uint64_t *)calloc(H ? H : 1, 8);
     memcpy(mpw, wsr->minimizers_per_walk, (size_t)H * 8);
     r->minimizers_per_walk = mpw; r->anchors_per_walk = apw;
@@ -403,8 +426,8 @@ int phi_oracle_index_run(const phi_graph_view *g, const phi_reads_view *rd, cons
 void phi_oracle_result_free(phi_index_result *r)
 {
     if (!r) return;
-    free((void *)r->spectrum); free((void *)r->anchor_rank); free((void *)r->anchor_walk);
-    free((void *)r->anchor_off); free((void *)r->anchor_vtx);
+    free((void *)r->spectrum); free((void *)r->rank_off); free((void *)r->anchor_walk);
+    free((void *)r->anchor_len); free((void *)r->anchor_vtx);
     free((void *)r->minimizers_per_walk); free((void *)r->anchors_per_walk);
     free(r);
 }

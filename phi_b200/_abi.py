@@ -31,7 +31,7 @@ class IndexParams(C.Structure):
 class IndexResult(C.Structure):
     _fields_ = [("count_sp_r", C.c_int32), ("n_walks", C.c_uint32), ("n_filtered", C.c_int64),
                 ("n_anchors", C.c_uint64), ("n_anchor_vtx", C.c_uint64),
-                ("spectrum", u64p), ("anchor_rank", i32p), ("anchor_walk", i32p), ("anchor_off", u64p),
+                ("spectrum", u64p), ("rank_off", u64p), ("anchor_walk", i32p), ("anchor_len", u8p),
                 ("anchor_vtx", i32p), ("minimizers_per_walk", u64p), ("anchors_per_walk", u64p),
                 ("read_kmer_positions", C.c_uint64), ("path_kmer_positions", C.c_uint64),
                 ("read_minimizers_emitted", C.c_uint64), ("path_minimizers_emitted", C.c_uint64),
@@ -136,7 +136,8 @@ class Reads:
 
 @dataclass
 class IndexResultPy:
-    """Host copy of phi_index_result (numpy arrays)."""
+    """Host copy of phi_index_result (numpy arrays).  anchor_rank / anchor_off are the per-anchor expansions of the ABI's
+    compact rank_off / anchor_len arrays (what the reference-side adapter walks through)."""
     count_sp_r: int
     n_walks: int
     n_filtered: int
@@ -157,6 +158,11 @@ class IndexResultPy:
     def n_anchors(self):
         return len(self.anchor_rank)
 
+    def wire_bytes(self):
+        """Bytes of the C result arrays (what crosses PCIe): spectrum, rank_off, anchor_walk, anchor_len, anchor_vtx, per-walk counters."""
+        ns, na = self.count_sp_r, self.n_anchors
+        return 8 * ns + 8 * (ns + 1) + 4 * na + na + 4 * len(self.anchor_vtx) + 16 * self.n_walks
+
     def anchors(self):
         """[(rank, walk, [vertices])] in final order."""
         off = self.anchor_off
@@ -172,12 +178,21 @@ def _np_from(ptr, n, dtype):
 
 def result_to_py(res: IndexResult) -> IndexResultPy:
     na, nv, nw, ns = res.n_anchors, res.n_anchor_vtx, res.n_walks, res.count_sp_r
+    have = bool(res.anchor_len) or na == 0
+    rank_off = _np_from(res.rank_off, ns + 1 if res.rank_off else 0, np.uint64)
+    lens = _np_from(res.anchor_len, na, np.uint8)
+    if len(rank_off):
+        assert int(rank_off[-1]) == na and int(rank_off[0]) == 0
+        anchor_rank = np.repeat(np.arange(ns, dtype=np.int32), np.diff(rank_off.astype(np.int64)))
+    else:
+        anchor_rank = np.zeros(na if have else 0, dtype=np.int32)
+    anchor_off = np.concatenate([[0], np.cumsum(lens, dtype=np.uint64)]).astype(np.uint64) if res.anchor_len else np.zeros(0, dtype=np.uint64)
     return IndexResultPy(
         count_sp_r=int(ns), n_walks=int(nw), n_filtered=int(res.n_filtered),
         spectrum=_np_from(res.spectrum, ns, np.uint64),
-        anchor_rank=_np_from(res.anchor_rank, na, np.int32),
+        anchor_rank=anchor_rank,
         anchor_walk=_np_from(res.anchor_walk, na, np.int32),
-        anchor_off=_np_from(res.anchor_off, na + 1 if res.anchor_off else 0, np.uint64),
+        anchor_off=anchor_off,
         anchor_vtx=_np_from(res.anchor_vtx, nv, np.int32),
         minimizers_per_walk=_np_from(res.minimizers_per_walk, nw, np.uint64),
         anchors_per_walk=_np_from(res.anchors_per_walk, nw, np.uint64),

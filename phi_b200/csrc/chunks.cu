@@ -49,31 +49,84 @@ __global__ void topo_coord_kernel(const int32_t *top_order_map, const uint64_t *
     coord[v] = ctr[CTR_BAD_TOPO] ? seg_off[v] : prefix[top_order_map[v]];
 }
 
-// ---- boundaries: step s starts a chunk when its vertex lies in another coordinate bucket than the previous step's
-__global__ void chunk_flag_kernel(const uint32_t *walk_vtx, uint64_t n_steps, const uint64_t *coord, int shift, uint32_t *flags)
+__device__ __forceinline__ uint32_t walk_of_step(const uint64_t *walk_off, uint32_t n_walks, uint64_t s)
 {
-    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (s >= n_steps) return;
-    uint32_t f = 1;
-    if (s) f = (coord[walk_vtx[s]] >> shift) != (coord[walk_vtx[s - 1]] >> shift);
-    flags[s] = f;
+    uint32_t lo = 0, hi = n_walks;                                   // last h with walk_off[h] <= s
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
+    return lo;
 }
-__global__ void walk_start_flag_kernel(const uint64_t *walk_off, uint32_t n_walks, uint32_t *flags)
+
+// ---- one pass over the walk steps: segment length, chunk boundary (the step's vertex lies in another coordinate bucket than the
+// previous step's, or the step is the first of its walk), zero-length steps, topological monotonicity of the walks
+__global__ void __launch_bounds__(256) step_pass_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
+                                                        const uint64_t *seg_off, const int32_t *top_order_map, const uint64_t *coord, int shift,
+                                                        PackedStep *packed, unsigned long long *ctr)
+{
+    const uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    bool zero = false, flag = false;
+    if (s < n_steps) {
+        const uint32_t v = walk_vtx[s];
+        const uint64_t len = seg_off[v + 1] - seg_off[v];
+        if (len >= (1ull << 31)) ctr[CTR_SEG_TOO_LONG] = 1;
+        const uint32_t h = walk_of_step(walk_off, n_walks, s);
+        flag = s == walk_off[h];
+        if (!flag) {
+            const uint32_t u = walk_vtx[s - 1];
+            flag = (coord[v] >> shift) != (coord[u] >> shift);
+            if (top_order_map[u] >= top_order_map[v]) ctr[CTR_NONMONO] = 1;
+        }
+        zero = len == 0;
+        PackedStep p; p.v = (uint32_t)(len & 0x7FFFFFFFu) | (flag ? 0x80000000u : 0u);
+        packed[s] = p;
+    }
+    const uint32_t bz = __ballot_sync(0xFFFFFFFFu, zero), bf = __ballot_sync(0xFFFFFFFFu, flag);
+    if ((threadIdx.x & 31) == 0) {
+        if (bz) atomicAdd(&ctr[CTR_ZERO_STEPS], (unsigned long long)__popc(bz));
+        if (bf) atomicAdd(&ctr[CTR_CHUNK_FLAGS], (unsigned long long)__popc(bf));
+    }
+}
+
+// scanned[s] = (chunks before s) << STEP_BASE_BITS | (bases before s, over all walks)
+__global__ void __launch_bounds__(256) step_finalize_kernel(ChunkTable C, const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off,
+                                                            uint32_t n_walks, uint64_t n_steps, uint32_t *step_base)
+{
+    const uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s == 0) C.chunk_step[C.n_chunks] = (uint32_t)n_steps;
+    if (s >= n_steps) return;
+    const uint64_t mask = (1ull << STEP_BASE_BITS) - 1;
+    const uint32_t h = walk_of_step(walk_off, n_walks, s);
+    const uint64_t sc = scanned[s];
+    step_base[s] = (uint32_t)((sc & mask) - (scanned[walk_off[h]] & mask));
+    if (packed[s].v >> 31) { const uint64_t c = sc >> STEP_BASE_BITS; if (c < C.n_chunks) { C.chunk_step[c] = (uint32_t)s; C.c_walk[c] = h; } }
+}
+
+__global__ void walk_len_kernel(const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, uint64_t *walk_len)
 {
     uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h < n_walks && walk_off[h] < walk_off[h + 1]) flags[walk_off[h]] = 1;
+    if (h >= n_walks) return;
+    const uint64_t mask = (1ull << STEP_BASE_BITS) - 1;
+    const uint64_t end = n_steps ? (scanned[n_steps - 1] & mask) + (packed[n_steps - 1].v & 0x7FFFFFFFu) : 0;
+    const uint64_t a = walk_off[h], b = walk_off[h + 1];
+    walk_len[h] = (b < n_steps ? scanned[b] & mask : end) - (a < n_steps ? scanned[a] & mask : end);
 }
-__global__ void chunk_fill_kernel(const uint32_t *flags, const uint32_t *pos, uint64_t n_steps, const uint64_t *walk_off, uint32_t n_walks,
-                                  uint32_t n_chunks, uint32_t *chunk_step, uint32_t *c_walk)
+
+// ---- zero-length steps (segments without bases contribute nothing, /root/reference/src/ILP_index.cpp:364-381): compaction
+__global__ void nonzero_flags_kernel(const PackedStep *packed, uint64_t n, uint32_t *flags)
 {
-    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (s == 0) chunk_step[n_chunks] = (uint32_t)n_steps;
-    if (s >= n_steps || !flags[s]) return;
-    uint32_t c = pos[s];
-    chunk_step[c] = (uint32_t)s;
-    uint32_t lo = 0, hi = n_walks;                                    // last h with walk_off[h] <= s
-    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
-    c_walk[c] = lo;
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (packed[i].v & 0x7FFFFFFFu) != 0;
+}
+__global__ void compact_steps_kernel(const uint32_t *walk_vtx, const uint32_t *flags, const uint64_t *pos, uint64_t n, uint32_t *out_vtx)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) out_vtx[pos[i]] = walk_vtx[i];
+}
+__global__ void remap_walk_off_kernel(const uint64_t *walk_off, uint32_t n_walks, const uint64_t *pos, uint64_t n_steps, uint64_t n_kept, uint64_t *out)
+{
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h > n_walks) return;
+    uint64_t o = walk_off[h];
+    out[h] = o < n_steps ? pos[o] : n_kept;
 }
 
 // ---- geometry + fingerprint, one warp per chunk
@@ -146,7 +199,7 @@ __global__ void chunk_group_kernel(ChunkTable C, uint32_t *table, uint32_t mask,
 }
 
 // ---- representative of every chunk, member counts, exact verification (warp per chunk)
-__global__ void __launch_bounds__(256) chunk_rep_kernel(ChunkTable C, const uint32_t *table, const uint32_t *walk_vtx, int dedupe, unsigned long long *ctr)
+__global__ void __launch_bounds__(256) chunk_rep_kernel(ChunkTable C, const uint32_t *table, const uint32_t *walk_vtx, int dedupe, int w, unsigned long long *ctr)
 {
     const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -166,7 +219,7 @@ __global__ void __launch_bounds__(256) chunk_rep_kernel(ChunkTable C, const uint
     if (lane == 0) {
         C.c_rep[c] = rep;
         if (active) atomicAdd(&C.c_ninst[rep], 1u);
-        const uint32_t T = TILE_WINDOWS;
+        const uint32_t T = (uint32_t)tile_cap(w);
         const uint32_t nt = (active && rep == c) ? (C.c_hi[c] - C.c_lo[c] + T - 1) / T : 0u;
         C.c_ntile[c] = nt;
         if (nt) atomicAdd(&ctr[CTR_UNIQUE_WINDOWS], (unsigned long long)(C.c_hi[c] - C.c_lo[c]));
@@ -180,14 +233,15 @@ __global__ void tile_fill_kernel(ChunkTable C, const uint64_t *walk_off, const u
     if (c >= C.n_chunks) return;
     const uint32_t nt = C.c_ntile[c];
     if (!nt) return;
-    const uint32_t h = C.c_walk[c], lo = C.c_lo[c], hi = C.c_hi[c], L = C.c_L[c], R = C.c_R[c];
+    const uint32_t h = C.c_walk[c], lo = C.c_lo[c], hi = C.c_hi[c], R = C.c_R[c];
     const uint64_t ws = walk_off[h];
     const uint32_t tb = C.c_tile_base[c];
+    const uint32_t T = (uint32_t)tile_cap(w);
     for (uint32_t t = 0; t < nt; ++t) {
         TileRec r;
-        r.walk = h; r.e0 = lo + t * TILE_WINDOWS; r.e1 = min(r.e0 + TILE_WINDOWS, hi); r.chunk = c; r.cbase = lo; r._r0 = r._r1 = 0;
-        const long long first = max((long long)r.e0 - w, 0ll);         // first base the tile stages
-        uint32_t a = L, b = R + 1;                                      // last step in [L, R] with step_base <= first
+        r.walk = h; r.e0 = lo + t * T; r.e1 = min(r.e0 + T, hi); r.chunk = c; r.cbase = lo; r._r0 = r._r1 = 0;
+        const long long first = max((long long)r.e0 - w - tile_pad(w), 0ll);   // first base the tile stages
+        uint32_t a = (uint32_t)ws, b = R + 1;                           // last step with step_base <= first (the front padding may reach before L)
         while (b - a > 1) { uint32_t m = (a + b) >> 1; if ((long long)step_base[m] <= first) a = m; else b = m; }
         r.first_step = (uint32_t)(a - ws);
         tiles[tb + t] = r;
@@ -286,30 +340,56 @@ cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_o
     return cudaSuccess;
 }
 
-cudaError_t chunk_flags(const uint32_t *walk_vtx, uint64_t n_steps, const uint64_t *walk_off, uint32_t n_walks, const uint64_t *coord, int shift,
-                        uint32_t *flags, cudaStream_t st, uint64_t *launches)
+cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint64_t *seg_off,
+                           const int32_t *top_order_map, const uint64_t *coord, int shift, PackedStep *packed, unsigned long long *ctr,
+                           cudaStream_t st, uint64_t *launches)
 {
     if (!n_steps) return cudaSuccess;
-    chunk_flag_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, n_steps, coord, shift, flags);
-    PHI_LAUNCH_CHECK();
-    walk_start_flag_kernel<<<(n_walks + 255) / 256, 256, 0, st>>>(walk_off, n_walks, flags);
+    step_pass_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, seg_off, top_order_map, coord, shift, packed, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
 
-cudaError_t chunk_build(const ChunkTable &C, const uint32_t *flags, const uint32_t *pos, const uint32_t *walk_vtx, uint64_t n_steps, const uint64_t *walk_off,
-                        uint32_t n_walks, const uint32_t *step_base, const uint64_t *walk_len, int k, int w, unsigned long long *ctr,
-                        cudaStream_t st, uint64_t *launches)
+cudaError_t walk_step_finalize(const ChunkTable &C, const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off, uint32_t n_walks,
+                               uint64_t n_steps, uint32_t *step_base, uint64_t *walk_len, cudaStream_t st, uint64_t *launches)
 {
-    if (!n_steps || !C.n_chunks) return cudaSuccess;
-    chunk_fill_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(flags, pos, n_steps, walk_off, n_walks, C.n_chunks, C.chunk_step, C.c_walk);
+    if (n_steps) {
+        step_finalize_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(C, packed, scanned, walk_off, n_walks, n_steps, step_base);
+        PHI_LAUNCH_CHECK();
+    }
+    if (n_walks) {
+        walk_len_kernel<<<(n_walks + 127) / 128, 128, 0, st>>>(packed, scanned, walk_off, n_walks, n_steps, walk_len);
+        PHI_LAUNCH_CHECK();
+    }
+    return cudaSuccess;
+}
+
+cudaError_t walk_compact_steps(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const PackedStep *packed,
+                               uint32_t *flags, uint64_t *pos, void *scan_scratch, uint64_t n_kept, uint32_t *out_vtx, uint64_t *out_off,
+                               cudaStream_t st, uint64_t *launches)
+{
+    if (!n_steps) return cudaSuccess;
+    nonzero_flags_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(packed, n_steps, flags);
     PHI_LAUNCH_CHECK();
+    cudaError_t e = scan_u32_to_u64(flags, pos, n_steps, scan_scratch, st, launches);
+    if (e != cudaSuccess) return e;
+    compact_steps_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, flags, pos, n_steps, out_vtx);
+    PHI_LAUNCH_CHECK();
+    remap_walk_off_kernel<<<(n_walks + 1 + 127) / 128, 128, 0, st>>>(walk_off, n_walks, pos, n_steps, n_kept, out_off);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t chunk_keys(const ChunkTable &C, const uint32_t *walk_vtx, const uint64_t *walk_off, const uint32_t *step_base, const uint64_t *walk_len,
+                       int k, int w, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
+{
+    if (!C.n_chunks) return cudaSuccess;
     chunk_key_kernel<<<(unsigned)(((uint64_t)C.n_chunks * 32 + 255) / 256), 256, 0, st>>>(C, walk_vtx, walk_off, step_base, walk_len, k, w, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
 
-cudaError_t chunk_group(const ChunkTable &C, uint32_t *table, uint32_t table_cap, const uint32_t *walk_vtx, int dedupe, unsigned long long *ctr,
+cudaError_t chunk_group(const ChunkTable &C, uint32_t *table, uint32_t table_cap, const uint32_t *walk_vtx, int dedupe, int w, unsigned long long *ctr,
                         cudaStream_t st, uint64_t *launches)
 {
     if (!C.n_chunks) return cudaSuccess;
@@ -321,7 +401,7 @@ cudaError_t chunk_group(const ChunkTable &C, uint32_t *table, uint32_t table_cap
     }
     chunk_group_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>(C, table, table_cap - 1, dedupe);
     PHI_LAUNCH_CHECK();
-    chunk_rep_kernel<<<(unsigned)(((uint64_t)C.n_chunks * 32 + 255) / 256), 256, 0, st>>>(C, table, walk_vtx, dedupe, ctr);
+    chunk_rep_kernel<<<(unsigned)(((uint64_t)C.n_chunks * 32 + 255) / 256), 256, 0, st>>>(C, table, walk_vtx, dedupe, w, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

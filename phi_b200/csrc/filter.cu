@@ -235,21 +235,25 @@ cudaError_t filter_fix_big(const FilterArgs &A, uint32_t *order, uint32_t *tmp, 
     return cudaSuccess;
 }
 
-__global__ void csr_sizes_kernel(FilterArgs A, const uint32_t *order, uint64_t n, uint32_t *nv_out)
+__global__ void csr_sizes_kernel(FilterArgs A, const uint32_t *order, uint64_t n, uint32_t *nv_out, uint8_t *anchor_len)
 {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (j < n) nv_out[j] = A.hit_nv[order[j]];
+    if (j < n) { uint8_t nv = A.hit_nv[order[j]]; nv_out[j] = nv; anchor_len[j] = nv; }
 }
 
-__global__ void csr_fill_kernel(FilterArgs A, const uint32_t *order, uint64_t n, const uint64_t *anchor_off, int32_t *anchor_rank,
-                                int32_t *anchor_walk, int32_t *anchor_vtx, unsigned long long *anchors_per_walk, uint32_t walk_id_base,
-                                uint32_t n_walks_out)
+// final arrays of the result: walk of every anchor, vertex lists back to back, first anchor of every rank (rank_off, optional)
+__global__ void csr_fill_kernel(FilterArgs A, const uint32_t *order, uint64_t n, const uint64_t *anchor_off, uint64_t *rank_off,
+                                int32_t *anchor_walk, int32_t *anchor_vtx, unsigned long long *anchors_per_walk, uint32_t n_walks_out)
 {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint32_t wl = 0xFFFFFFFFu;
     if (j < n) {
         uint32_t x = order[j];
-        anchor_rank[j] = (int32_t)A.hit_rank[x];
+        if (rank_off) {                                               // anchors are sorted by rank: rank r starts where it first appears
+            const int64_t r = A.hit_rank[x], rp = j ? (int64_t)A.hit_rank[order[j - 1]] : -1;
+            for (int64_t q = rp + 1; q <= r; ++q) rank_off[q] = j;
+            if (j == n - 1) for (int64_t q = r + 1; q <= (int64_t)A.n_ranks; ++q) rank_off[q] = n;
+        }
         anchor_walk[j] = (int32_t)A.hit_walk[x];
         const int32_t *p = A.vtx_pool + A.hit_voff[x];
         uint64_t o = anchor_off[j]; uint32_t nv = A.hit_nv[x];
@@ -271,21 +275,21 @@ __global__ void csr_fill_kernel(FilterArgs A, const uint32_t *order, uint64_t n,
     }
 }
 
-cudaError_t filter_csr_sizes(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, uint32_t *nv_out, cudaStream_t st, uint64_t *launches)
+cudaError_t filter_csr_sizes(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, uint32_t *nv_out, uint8_t *anchor_len, cudaStream_t st, uint64_t *launches)
 {
     if (!n_surv) return cudaSuccess;
-    csr_sizes_kernel<<<(unsigned)((n_surv + 255) / 256), 256, 0, st>>>(A, order, n_surv, nv_out);
+    csr_sizes_kernel<<<(unsigned)((n_surv + 255) / 256), 256, 0, st>>>(A, order, n_surv, nv_out, anchor_len);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
-cudaError_t filter_csr_fill(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, const uint64_t *anchor_off, int32_t *anchor_rank,
-                            int32_t *anchor_walk, int32_t *anchor_vtx, unsigned long long *anchors_per_walk, uint32_t walk_id_base,
+cudaError_t filter_csr_fill(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, const uint64_t *anchor_off, uint64_t *rank_off,
+                            int32_t *anchor_walk, int32_t *anchor_vtx, unsigned long long *anchors_per_walk,
                             uint32_t n_walks_out, cudaStream_t st, uint64_t *launches)
 {
     if (!n_surv) return cudaSuccess;
     const size_t hist_bytes = n_walks_out <= CSR_HIST_MAX ? (size_t)n_walks_out * 4 : 0;
-    csr_fill_kernel<<<(unsigned)((n_surv + 1023) / 1024), 1024, hist_bytes, st>>>(A, order, n_surv, anchor_off, anchor_rank, anchor_walk, anchor_vtx,
-                                                                     anchors_per_walk, walk_id_base, n_walks_out);
+    csr_fill_kernel<<<(unsigned)((n_surv + 1023) / 1024), 1024, hist_bytes, st>>>(A, order, n_surv, anchor_off, rank_off, anchor_walk, anchor_vtx,
+                                                                     anchors_per_walk, n_walks_out);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -28,14 +28,25 @@ enum {
     CTR_ACTIVE_CHUNKS = 16,       // chunks that own at least one valid window
     CTR_UNIQUE_WINDOWS = 17,      // window end positions owned by representative chunks (what the walk kernel really sketches)
     CTR_DEDUPE_MISMATCH = 18,
-    CTR_PATH_HITS = 19,           // hits of all walks (every member chunk counts what its representative found)     // a chunk differs from its fingerprint representative (128-bit collision): rerun without sharing
+    CTR_PATH_HITS = 19,
+    CTR_CHUNK_FLAGS = 20,         // chunk-start flags set by the step pass (guards the chunk field of the packed scan)
+    CTR_SEG_TOO_LONG = 21,        // a segment of 2^31 bases or more           // hits of all walks (every member chunk counts what its representative found)     // a chunk differs from its fingerprint representative (128-bit collision): rerun without sharing
     CTR_COUNT = 24
 };
 
 enum { WALK_MODE_PROBE = 0, WALK_MODE_ALL = 1 };
 
-constexpr int TILE_WINDOWS = 2048;   // window end positions per sketch tile
+constexpr int TILE_WINDOWS = 2048;   // window end positions per sketch tile (general path)
 constexpr int SEG_PER_TILE = 8;      // a tile emits its hits in batches of 256 runs: at most TILE_WINDOWS / 256 contiguous hit segments
+
+// Tile geometry as a function of w (sketch_tile.cuh).  For 9 <= w <= 65 a tile without non-ACGT bytes runs the
+// register-resident core: every lane owns 8 consecutive k-mer positions, a warp 256, of which the first
+// halo_lanes(w) lanes only feed the windows of the lanes behind them; the tile is padded in front so that the halo
+// window (the one before the tile's first own window) is the first window of warp 0.
+__host__ __device__ inline bool tile_fast_w(int w) { return w >= 9 && w <= 65; }
+__host__ __device__ inline int tile_halo_lanes(int w) { return (w + 6) >> 3; }                      // ceil((w - 1) / 8)
+__host__ __device__ inline int tile_pad(int w) { return tile_fast_w(w) ? 8 * tile_halo_lanes(w) - (w - 1) : 0; }
+__host__ __device__ inline int tile_cap(int w) { return tile_fast_w(w) ? 8 * (32 - tile_halo_lanes(w)) * 8 - 1 : TILE_WINDOWS; }
 
 // One walk-sketch tile: window end positions [e0, e1) of walk `walk` (the representative of chunk `chunk`).
 struct TileRec {
@@ -66,8 +77,8 @@ struct ExpandArgs {
 
 // shared-memory carve-up of a sketch tile (computed on the host: sketch_tile.cuh make_layout)
 struct TileLayout {
-    int M, M8, NB, nchunks;
-    int o_canon, o_hash, o_pack, o_dirty, o_bnd, o_scan, o_pre, o_suf, o_flag, o_base, o_stepv, o_steps, o_cfirst, o_cmask;
+    int M, M8, NB, nchunks, pad, cap;   // pad: positions in front of the halo window; cap: own windows per tile
+    int o_canon, o_hash, o_pack, o_dirty, o_bnd, o_first, o_scan, o_pre, o_suf, o_flag, o_base, o_stepv, o_steps, o_cfirst, o_cmask;
     int bytes;
 };
 TileLayout tile_layout(int k, int w, bool walk);
@@ -103,30 +114,40 @@ struct WalkSketchArgs {
     unsigned long long *ctr;
 };
 
-int tile_windows();
+int tile_windows(int w);
 
 // sketch_kernels.cu
 cudaError_t launch_read_tile_dir(const uint64_t *read_off, uint64_t n_reads, int w, uint64_t n_tiles, uint64_t *out, cudaStream_t st);
 cudaError_t launch_read_sketch(const ReadSketchArgs &A, uint64_t n_tiles, cudaStream_t st);
 cudaError_t launch_walk_sketch(const WalkSketchArgs &A, uint32_t n_tiles, cudaStream_t st);
-cudaError_t launch_step_len(const uint32_t *walk_vtx, const uint64_t *seg_off, uint64_t n_steps, uint32_t *step_len, cudaStream_t st);
-cudaError_t launch_walk_len(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
-                            uint64_t n_steps, uint64_t *walk_len, cudaStream_t st);
-cudaError_t launch_step_finalize(const uint64_t *gbase, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, uint32_t *step_base,
-                                 cudaStream_t st);
-cudaError_t launch_walk_monotone(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
-                                 const int32_t *top_order_map, unsigned long long *ctr, cudaStream_t st);
 cudaError_t launch_hash_bytes(const uint8_t *keys, uint64_t n, int len, uint64_t *out, cudaStream_t st);
 
-// chunks.cu — walk chunking, grouping of identical chunks, instantiation of the representatives' hits
+// One u32 per walk step: bits 0..30 = bases of the step's segment, bit 31 = the step starts a chunk.  Scanned as a u64 with the
+// chunk flag moved up to bit STEP_BASE_BITS: one scan yields (chunks before the step, bases before the step).
+constexpr int STEP_BASE_BITS = 38;       // < 2^38 walk bases and < 2^26 chunks per GPU (checked on the host)
+struct PackedStep {
+    uint32_t v;
+    __host__ __device__ operator uint64_t() const { return (uint64_t)(v & 0x7FFFFFFFu) | ((uint64_t)(v >> 31) << STEP_BASE_BITS); }
+};
+
+// chunks.cu — walk preparation (step lengths and bases, walk lengths), walk chunking, grouping of identical chunks,
+// instantiation of the representatives' hits
 cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, uint32_t *tlen, uint64_t *prefix, uint64_t *coord,
                              void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
-cudaError_t chunk_flags(const uint32_t *walk_vtx, uint64_t n_steps, const uint64_t *walk_off, uint32_t n_walks, const uint64_t *coord, int shift,
-                        uint32_t *flags, cudaStream_t st, uint64_t *launches);
-cudaError_t chunk_build(const ChunkTable &C, const uint32_t *flags, const uint32_t *pos, const uint32_t *walk_vtx, uint64_t n_steps, const uint64_t *walk_off,
-                        uint32_t n_walks, const uint32_t *step_base, const uint64_t *walk_len, int k, int w, unsigned long long *ctr,
-                        cudaStream_t st, uint64_t *launches);
-cudaError_t chunk_group(const ChunkTable &C, uint32_t *table, uint32_t table_cap, const uint32_t *walk_vtx, int dedupe, unsigned long long *ctr,
+// per step: segment length, chunk-start flag, zero-length count, topological monotonicity -> packed[]
+cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint64_t *seg_off,
+                           const int32_t *top_order_map, const uint64_t *coord, int shift, PackedStep *packed, unsigned long long *ctr,
+                           cudaStream_t st, uint64_t *launches);
+// scanned = exclusive scan of packed (as u64) -> step_base, walk_len, chunk_step / c_walk of C
+cudaError_t walk_step_finalize(const ChunkTable &C, const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off, uint32_t n_walks,
+                               uint64_t n_steps, uint32_t *step_base, uint64_t *walk_len, cudaStream_t st, uint64_t *launches);
+// drop the zero-length steps (rare: segments without bases): out_vtx / out_off describe the compacted walks
+cudaError_t walk_compact_steps(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const PackedStep *packed,
+                               uint32_t *flags, uint64_t *pos, void *scan_scratch, uint64_t n_kept, uint32_t *out_vtx, uint64_t *out_off,
+                               cudaStream_t st, uint64_t *launches);
+cudaError_t chunk_keys(const ChunkTable &C, const uint32_t *walk_vtx, const uint64_t *walk_off, const uint32_t *step_base, const uint64_t *walk_len,
+                       int k, int w, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
+cudaError_t chunk_group(const ChunkTable &C, uint32_t *table, uint32_t table_cap, const uint32_t *walk_vtx, int dedupe, int w, unsigned long long *ctr,
                         cudaStream_t st, uint64_t *launches);
 cudaError_t chunk_tiles(const ChunkTable &C, const uint64_t *walk_off, const uint32_t *step_base, int w, TileRec *tiles, cudaStream_t st, uint64_t *launches);
 cudaError_t chunk_emitted(const ChunkTable &C, const uint32_t *c_emitted, const uint32_t *c_hits, uint32_t walk_id_base,
@@ -143,6 +164,8 @@ cudaError_t scan_u32_to_u64(const uint32_t *in, uint64_t *out, uint64_t n, void 
 size_t scan_u32_scratch(uint64_t n);
 cudaError_t scan_u32_inplace(uint32_t *data, uint64_t n, void *scratch, cudaStream_t st, uint64_t *launches);
 cudaError_t scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, void *scratch, cudaStream_t st, uint64_t *launches);
+// exclusive scan of packed walk steps as u64 (scratch: scan_u32_to_u64_scratch)
+cudaError_t scan_packed_steps(const PackedStep *in, uint64_t *out, uint64_t n, void *scratch, cudaStream_t st, uint64_t *launches);
 // stable LSD radix sort of u64 keys (optional u32 values) on bits [bit_lo, bit_hi); result ends in keys_a/vals_a
 size_t radix_sort_scratch(uint64_t n);
 cudaError_t radix_sort_u64(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, uint64_t n, int bit_lo, int bit_hi,
@@ -189,9 +212,9 @@ cudaError_t filter_fix_multi(const FilterArgs &A, uint32_t *order, uint64_t n_su
                              unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_fix_big(const FilterArgs &A, uint32_t *order, uint32_t *tmp, const uint32_t *big_list, uint32_t n_big,
                            uint64_t n_surv, cudaStream_t st, uint64_t *launches);
-cudaError_t filter_csr_sizes(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, uint32_t *nv_out, cudaStream_t st, uint64_t *launches);
-cudaError_t filter_csr_fill(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, const uint64_t *anchor_off, int32_t *anchor_rank,
-                            int32_t *anchor_walk, int32_t *anchor_vtx, unsigned long long *anchors_per_walk, uint32_t walk_id_base,
+cudaError_t filter_csr_sizes(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, uint32_t *nv_out, uint8_t *anchor_len, cudaStream_t st, uint64_t *launches);
+cudaError_t filter_csr_fill(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, const uint64_t *anchor_off, uint64_t *rank_off,
+                            int32_t *anchor_walk, int32_t *anchor_vtx, unsigned long long *anchors_per_walk,
                             uint32_t n_walks_out, cudaStream_t st, uint64_t *launches);
 
 }  // namespace phi

@@ -73,7 +73,7 @@ struct phi_gpu_index_ctx {
     DevBuf hseg_off, hseg_cnt, c_emitted, c_hits, c_surv, member_cnt, member_off, x_rank, x_walk, x_pos, x_voff, x_nv, x_hash;
     uint32_t n_chunks = 0, n_tiles = 0; uint64_t unique_windows = 0, active_chunks = 0, rep_chunks = 0, unique_hits = 0; int dedupe = 1, chunk_shift = 11;
     DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
-    DevBuf anchor_off, anchor_rank, anchor_walk, anchor_vtx, apw, walk_gbase;
+    DevBuf anchor_off, rank_off, anchor_len, anchor_walk, anchor_vtx, apw, walk_gbase;
     unsigned long long *h_ctr = nullptr;   // pinned mirror of the counter block
     // what the second stream uses instead of ctr / h_ctr / scan_scr / flags / flags64 / nv_out (swapped in by PrepScope)
     DevBuf ctr2, scan_scr2, flags2, flags64_2, nv_out2; unsigned long long *h_ctr2 = nullptr;
@@ -154,7 +154,7 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
                       &ctx->s_voff, &ctx->s_nv, &ctx->s_vtx,
                       &ctx->hit_voff, &ctx->hit_nv, &ctx->hit_hash, &ctx->vtx_pool, &ctx->g_rep, &ctx->g_cnt, &ctx->rank_drop, &ctx->flags,
                       &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->big_list, &ctx->tmp_order, &ctx->nv_out,
-                      &ctx->anchor_off, &ctx->anchor_rank, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw, &ctx->walk_gbase};
+                      &ctx->anchor_off, &ctx->rank_off, &ctx->anchor_len, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw, &ctx->walk_gbase};
     for (DevBuf *b : bufs) b->release();
     {
         std::lock_guard<std::mutex> lk(g_live_mu);
@@ -255,35 +255,6 @@ __global__ void count_positions_kernel(const uint64_t *off, uint64_t n, int k, i
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
 }
 
-__global__ void count_zero_steps_kernel(const uint32_t *step_len, uint64_t n, unsigned long long *ctr)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    bool z = i < n && step_len[i] == 0;
-    uint32_t b = __ballot_sync(0xFFFFFFFFu, z);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&ctr[CTR_ZERO_STEPS], (unsigned long long)__popc(b));
-}
-
-__global__ void nonzero_flags_kernel(const uint32_t *step_len, uint64_t n, uint32_t *flags)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = step_len[i] != 0;
-}
-
-__global__ void compact_steps_kernel(const uint32_t *walk_vtx, const uint32_t *step_len, const uint64_t *pos, uint64_t n, uint32_t *out_vtx,
-                                     uint32_t *out_len)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n && step_len[i]) { out_vtx[pos[i]] = walk_vtx[i]; out_len[pos[i]] = step_len[i]; }
-}
-
-__global__ void remap_walk_off_kernel(const uint64_t *walk_off, uint32_t n_walks, const uint64_t *pos, uint64_t n_steps, uint64_t n_kept, uint64_t *out)
-{
-    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h > n_walks) return;
-    uint64_t o = walk_off[h];
-    out[h] = o < n_steps ? pos[o] : n_kept;
-}
-
 __global__ void count_survivors_kernel(const uint32_t *flags, uint64_t n, unsigned long long *ctr)
 {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -331,110 +302,91 @@ static ChunkTable chunk_table(phi_gpu_index_ctx *ctx)
     return C;
 }
 
-static int stage_chunks(phi_gpu_index_ctx *ctx, int k, int w, const uint32_t *d_walk_vtx, const uint64_t *d_walk_off, uint64_t S)
+// Steps: packed lengths + chunk flags (one pass), one u64 scan, step bases / walk lengths / chunk table, fingerprints,
+// grouping, tiles.  Two host-side waits (number of chunks; number of tiles + walk lengths + flags), on the second stream.
+static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<uint64_t> &h_walk_len, const uint32_t *&d_walk_vtx,
+                            const uint64_t *&d_walk_off, uint64_t &n_steps_eff, int &walks_monotone)
 {
-    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
-    const uint32_t H = ctx->n_walks, V = ctx->n_vtx;
+    PrepScope on_second_stream(ctx);                                    // everything below: ctx->st is the second stream
+    walks_monotone = 1;
+    const uint32_t H = ctx->n_walks, V = ctx->n_vtx; uint64_t S = ctx->n_steps;
+    d_walk_vtx = ctx->walk_vtx.as<uint32_t>(); d_walk_off = ctx->walk_off.as<uint64_t>(); n_steps_eff = S;
+    h_walk_len.assign(H, 0);
     ctx->n_chunks = ctx->n_tiles = 0; ctx->unique_windows = ctx->active_chunks = ctx->rep_chunks = 0;
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    CU(cudaEventRecord(ctx->ev[EV_PREP0], ctx->st));
+    CU(cudaMemsetAsync(ctx->ctr.p, 0, CTR_COUNT * 8, ctx->st));
+    memset(ctx->h_ctr, 0, CTR_COUNT * 8);
     if (!H || !S) return PHI_OK;
     if (S >= 0xFFFFFFFFull) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-2 walk steps on one GPU; shard the walks over more GPUs");
-    // topological base coordinate of every vertex
+    // topological base coordinate of every vertex (chunk boundaries are defined on it)
     CU(ctx->tlen.reserve((size_t)V * 4 + 4)); CU(ctx->tprefix.reserve(((size_t)V + 1) * 8)); CU(ctx->coord.reserve((size_t)V * 8 + 8));
-    CU(ctx->scan_scr.reserve(std::max({scan_u32_to_u64_scratch((uint64_t)V + 1), scan_u32_scratch(S + 1), (size_t)1024})));
+    CU(ctx->scan_scr.reserve(std::max({scan_u32_to_u64_scratch((uint64_t)V + 1), scan_u32_to_u64_scratch(S + 1), (size_t)1024})));
     CU(chunk_topo_coord(ctx->top_order.as<int32_t>(), ctx->seg_off.as<uint64_t>(), V, ctx->tlen.as<uint32_t>(), ctx->tprefix.as<uint64_t>(),
                         ctx->coord.as<uint64_t>(), ctx->scan_scr.p, d_ctr, ctx->st, &ctx->launches));
-    // boundaries -> chunk ids
-    CU(ctx->cflags.reserve(S * 4 + 4)); CU(ctx->cpos.reserve(S * 4 + 4));
-    CU(chunk_flags(d_walk_vtx, S, d_walk_off, H, ctx->coord.as<uint64_t>(), ctx->chunk_shift, ctx->cflags.as<uint32_t>(), ctx->st, &ctx->launches));
-    CU(scan_u32(ctx->cflags.as<uint32_t>(), ctx->cpos.as<uint32_t>(), S, ctx->scan_scr.p, ctx->st, &ctx->launches));
-    uint32_t last_pos = 0, last_flag = 0;
-    CU(cudaMemcpyAsync(&last_pos, ctx->cpos.as<uint32_t>() + (S - 1), 4, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaMemcpyAsync(&last_flag, ctx->cflags.as<uint32_t>() + (S - 1), 4, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    const uint32_t NC = last_pos + last_flag;
+    CU(ctx->step_len.reserve(S * 4 + 4));                               // packed steps
+    CU(ctx->gbase.reserve((S + 1) * 8));                                // their scan
+    uint64_t last = 0; uint32_t NC = 0;
+    for (int attempt = 0;; ++attempt) {
+        CU(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, ctx->st)); CU(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, ctx->st));
+        CU(walk_step_pass(d_walk_vtx, d_walk_off, H, S, ctx->seg_off.as<uint64_t>(), ctx->top_order.as<int32_t>(), ctx->coord.as<uint64_t>(),
+                          ctx->chunk_shift, ctx->step_len.as<PackedStep>(), d_ctr, ctx->st, &ctx->launches));
+        CU(scan_packed_steps(ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), S, ctx->scan_scr.p, ctx->st, &ctx->launches));
+        CU(cudaMemcpyAsync(&last, ctx->gbase.as<uint64_t>() + (S - 1), 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(read_counters(ctx));                                         // wait 1
+        if (ctx->h_ctr[CTR_SEG_TOO_LONG]) return ctx->fail(PHI_ERR_UNSUPPORTED, "segment of 2^31 bases or more");
+        if (!ctx->h_ctr[CTR_ZERO_STEPS] || attempt) break;
+        // zero-length segments contribute no bases (ILP_index.cpp:364-381): drop their steps and look at the walks again
+        const uint64_t kept = S - ctx->h_ctr[CTR_ZERO_STEPS];
+        CU(ctx->flags.reserve(S * 4 + 4)); CU(ctx->flags64.reserve((S + 1) * 8));
+        CU(ctx->walk_vtx_c.reserve(kept * 4 + 4)); CU(ctx->walk_off_c.reserve(((size_t)H + 1) * 8));
+        CU(walk_compact_steps(d_walk_vtx, d_walk_off, H, S, ctx->step_len.as<PackedStep>(), ctx->flags.as<uint32_t>(), ctx->flags64.as<uint64_t>(),
+                              ctx->scan_scr.p, kept, ctx->walk_vtx_c.as<uint32_t>(), ctx->walk_off_c.as<uint64_t>(), ctx->st, &ctx->launches));
+        d_walk_vtx = ctx->walk_vtx_c.as<uint32_t>(); d_walk_off = ctx->walk_off_c.as<uint64_t>(); n_steps_eff = S = kept;
+        CU(cudaMemsetAsync(d_ctr + CTR_NONMONO, 0, 8, ctx->st));
+        if (!S) return PHI_OK;
+    }
+    walks_monotone = ctx->h_ctr[CTR_NONMONO] ? 0 : 1;
+    if (ctx->h_ctr[CTR_CHUNK_FLAGS] >= (1ull << (64 - STEP_BASE_BITS)))
+        return ctx->fail(PHI_ERR_UNSUPPORTED, "too many walk chunks on one GPU: raise chunk_shift (phi_gpu_index_set_walk_sharing) or shard the walks");
+    NC = (uint32_t)ctx->h_ctr[CTR_CHUNK_FLAGS];
+    (void)last;
     ctx->n_chunks = NC;
     DevBuf *u32s[] = {&ctx->chunk_step, &ctx->c_walk, &ctx->c_L, &ctx->c_R, &ctx->c_lo, &ctx->c_hi, &ctx->c_slot, &ctx->c_rep, &ctx->c_ninst,
                       &ctx->c_ntile, &ctx->c_tile_base, &ctx->c_emitted, &ctx->c_hits, &ctx->c_surv};
     for (DevBuf *b : u32s) CU(b->reserve(((size_t)NC + 2) * 4));
     CU(ctx->c_h1.reserve(((size_t)NC + 1) * 8)); CU(ctx->c_h2.reserve(((size_t)NC + 1) * 8));
     CU(ctx->member_cnt.reserve(((size_t)NC + 2) * 4)); CU(ctx->member_off.reserve(((size_t)NC + 2) * 8));
+    CU(ctx->step_base.reserve(S * 4 + 4)); CU(ctx->walk_len.reserve((size_t)H * 8));
     ChunkTable C = chunk_table(ctx);
-    CU(chunk_build(C, ctx->cflags.as<uint32_t>(), ctx->cpos.as<uint32_t>(), d_walk_vtx, S, d_walk_off, H, ctx->step_base.as<uint32_t>(),
-                   ctx->walk_len.as<uint64_t>(), k, w, d_ctr, ctx->st, &ctx->launches));
+    CU(walk_step_finalize(C, ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), d_walk_off, H, S, ctx->step_base.as<uint32_t>(),
+                          ctx->walk_len.as<uint64_t>(), ctx->st, &ctx->launches));
+    CU(cudaMemcpyAsync(h_walk_len.data(), ctx->walk_len.p, (size_t)H * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(chunk_keys(C, d_walk_vtx, d_walk_off, ctx->step_base.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), k, w, d_ctr, ctx->st, &ctx->launches));
     uint32_t tcap = 1024; while (tcap < 2 * (uint64_t)NC) tcap <<= 1;
     CU(ctx->ctable.reserve((size_t)tcap * 4));
     CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch((uint64_t)NC + 2), scan_u32_to_u64_scratch((uint64_t)NC + 2))));
     for (int dedupe = ctx->dedupe ? 1 : 0;; dedupe = 0) {
         CU(cudaMemsetAsync(d_ctr + CTR_UNIQUE_WINDOWS, 0, 2 * 8, ctx->st));               // UNIQUE_WINDOWS, DEDUPE_MISMATCH
-        CU(chunk_group(C, ctx->ctable.as<uint32_t>(), tcap, d_walk_vtx, dedupe, d_ctr, ctx->st, &ctx->launches));
+        CU(chunk_group(C, ctx->ctable.as<uint32_t>(), tcap, d_walk_vtx, dedupe, w, d_ctr, ctx->st, &ctx->launches));
         CU(cudaMemsetAsync(ctx->c_ntile.as<uint32_t>() + NC, 0, 4, ctx->st));
         CU(scan_u32(ctx->c_ntile.as<uint32_t>(), ctx->c_tile_base.as<uint32_t>(), (uint64_t)NC + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
         uint32_t n_tiles = 0;
         CU(cudaMemcpyAsync(&n_tiles, ctx->c_tile_base.as<uint32_t>() + NC, 4, cudaMemcpyDeviceToHost, ctx->st));
-        CU(read_counters(ctx));
+        CU(read_counters(ctx));                                         // wait 2 (also: walk lengths)
         ctx->n_tiles = n_tiles;
-        if (!dedupe || !ctx->h_ctr[CTR_DEDUPE_MISMATCH]) break;                          // a fingerprint collision: sketch every chunk on its own
+        if (!dedupe || !ctx->h_ctr[CTR_DEDUPE_MISMATCH]) break;          // a fingerprint collision: sketch every chunk on its own
     }
+    uint64_t total_bases = 0;
+    for (uint32_t h = 0; h < H; ++h) {
+        if (h_walk_len[h] >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "walk longer than 2^31-1 bases (the reference's int32 position loop overflows there too)");
+        total_bases += h_walk_len[h];
+    }
+    if (total_bases >= (1ull << STEP_BASE_BITS)) return ctx->fail(PHI_ERR_UNSUPPORTED, "2^38 or more walk bases on one GPU; shard the walks over more GPUs");
     ctx->unique_windows = ctx->h_ctr[CTR_UNIQUE_WINDOWS]; ctx->active_chunks = ctx->h_ctr[CTR_ACTIVE_CHUNKS];
     CU(ctx->tiles.reserve((size_t)ctx->n_tiles * sizeof(TileRec) + 32));
     CU(chunk_tiles(C, d_walk_off, ctx->step_base.as<uint32_t>(), w, ctx->tiles.as<TileRec>(), ctx->st, &ctx->launches));
     return PHI_OK;
-}
-
-static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<uint64_t> &h_walk_len, const uint32_t *&d_walk_vtx,
-                            const uint64_t *&d_walk_off, uint64_t &n_steps_eff, int &walks_monotone)
-{
-    PrepScope on_second_stream(ctx);                                    // everything below: ctx->st is the second stream
-    walks_monotone = 1;
-    const uint32_t H = ctx->n_walks; const uint64_t S = ctx->n_steps;
-    d_walk_vtx = ctx->walk_vtx.as<uint32_t>(); d_walk_off = ctx->walk_off.as<uint64_t>(); n_steps_eff = S;
-    h_walk_len.assign(H, 0);
-    ctx->n_chunks = ctx->n_tiles = 0; ctx->unique_windows = 0;
-    CU(cudaEventRecord(ctx->ev[EV_PREP0], ctx->st));
-    CU(cudaMemsetAsync(ctx->ctr.p, 0, CTR_COUNT * 8, ctx->st));
-    memset(ctx->h_ctr, 0, CTR_COUNT * 8);
-    if (!H) return PHI_OK;
-    CU(ctx->step_len.reserve(S * 4 + 4));
-    CU(ctx->gbase.reserve((S + 1) * 8));
-    CU(ctx->scan_scr.reserve(std::max(scan_u32_to_u64_scratch(S + 1), (size_t)1024)));
-    CU(launch_step_len(d_walk_vtx, ctx->seg_off.as<uint64_t>(), S, ctx->step_len.as<uint32_t>(), ctx->st)); ctx->launches++;
-    if (S) {
-        count_zero_steps_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->st>>>(ctx->step_len.as<uint32_t>(), S, ctx->ctr.as<unsigned long long>());
-        CU(cudaGetLastError()); ctx->launches++;
-    }
-    CU(read_counters(ctx));
-    if (ctx->h_ctr[CTR_ZERO_STEPS]) {
-        // zero-length segments contribute no bases (ILP_index.cpp:364-381): drop their steps
-        const uint64_t kept = S - ctx->h_ctr[CTR_ZERO_STEPS];
-        CU(ctx->flags.reserve(S * 4 + 4));
-        CU(ctx->flags64.reserve((S + 1) * 8));
-        CU(ctx->walk_vtx_c.reserve(kept * 4 + 4));
-        CU(ctx->walk_off_c.reserve(((size_t)H + 1) * 8));
-        CU(ctx->nv_out.reserve(kept * 4 + 4));
-        nonzero_flags_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->st>>>(ctx->step_len.as<uint32_t>(), S, ctx->flags.as<uint32_t>());
-        CU(cudaGetLastError()); ctx->launches++;
-        CU(scan_u32_to_u64(ctx->flags.as<uint32_t>(), ctx->flags64.as<uint64_t>(), S, ctx->scan_scr.p, ctx->st, &ctx->launches));
-        compact_steps_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->st>>>(d_walk_vtx, ctx->step_len.as<uint32_t>(), ctx->flags64.as<uint64_t>(), S,
-                                                                              ctx->walk_vtx_c.as<uint32_t>(), ctx->nv_out.as<uint32_t>());
-        CU(cudaGetLastError()); ctx->launches++;
-        remap_walk_off_kernel<<<(H + 1 + 127) / 128, 128, 0, ctx->st>>>(d_walk_off, H, ctx->flags64.as<uint64_t>(), S, kept, ctx->walk_off_c.as<uint64_t>());
-        CU(cudaGetLastError()); ctx->launches++;
-        if (kept) CU(cudaMemcpyAsync(ctx->step_len.p, ctx->nv_out.p, kept * 4, cudaMemcpyDeviceToDevice, ctx->st));
-        d_walk_vtx = ctx->walk_vtx_c.as<uint32_t>(); d_walk_off = ctx->walk_off_c.as<uint64_t>(); n_steps_eff = kept;
-    }
-    const uint64_t S2 = n_steps_eff;
-    CU(scan_u32_to_u64(ctx->step_len.as<uint32_t>(), ctx->gbase.as<uint64_t>(), S2, ctx->scan_scr.p, ctx->st, &ctx->launches));
-    CU(launch_walk_monotone(d_walk_vtx, d_walk_off, H, S2, ctx->top_order.as<int32_t>(), ctx->ctr.as<unsigned long long>(), ctx->st)); ctx->launches++;
-    CU(ctx->walk_len.reserve((size_t)H * 8));
-    CU(launch_walk_len(ctx->gbase.as<uint64_t>(), ctx->step_len.as<uint32_t>(), d_walk_off, H, S2, ctx->walk_len.as<uint64_t>(), ctx->st)); ctx->launches++;
-    CU(cudaMemcpyAsync(h_walk_len.data(), ctx->walk_len.p, (size_t)H * 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(ctx->step_base.reserve(S2 * 4 + 4));
-    CU(launch_step_finalize(ctx->gbase.as<uint64_t>(), d_walk_off, H, S2, ctx->step_base.as<uint32_t>(), ctx->st)); ctx->launches++;
-    CU(read_counters(ctx));                                             // also syncs: walk lengths + the monotonicity flag
-    walks_monotone = ctx->h_ctr[CTR_NONMONO] ? 0 : 1;
-    for (uint32_t h = 0; h < H; ++h)
-        if (h_walk_len[h] >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "walk longer than 2^31-1 bases (the reference's int32 position loop overflows there too)");
-    return stage_chunks(ctx, k, w, d_walk_vtx, d_walk_off, S2);
 }
 
 
@@ -802,7 +754,7 @@ static int reads_sketch_launch(phi_gpu_index_ctx *ctx, int k, int w, const Reads
 static int stage_reads_begin(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &rs)
 {
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
-    const int T = tile_windows();
+    const int T = tile_windows(w);
     const uint64_t G = ctx->read_total, R = ctx->n_reads;
     rs.n_tiles = (R && G >= (uint64_t)(w + k - 1)) ? (G - k) / T + 1 : 0;
     CU(cudaEventRecord(ctx->ev[EV_RD0], ctx->st));
@@ -1030,17 +982,17 @@ static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, bool preso
             CU(filter_fix_big(A, order, ctx->tmp_order.as<uint32_t>(), ctx->big_list.as<uint32_t>(), (uint32_t)ctx->h_ctr[CTR_BIG_GROUPS], ns, ctx->st, &ctx->launches));
         }
     }
-    CU(ctx->nv_out.reserve((ns + 1) * 4));
+    CU(ctx->nv_out.reserve((ns + 1) * 4)); CU(ctx->anchor_len.reserve(ns + 4));
     CU(cudaMemsetAsync(ctx->nv_out.as<uint32_t>() + ns, 0, 4, ctx->st));
-    CU(filter_csr_sizes(A, order, ns, ctx->nv_out.as<uint32_t>(), ctx->st, &ctx->launches));
+    CU(filter_csr_sizes(A, order, ns, ctx->nv_out.as<uint32_t>(), ctx->anchor_len.as<uint8_t>(), ctx->st, &ctx->launches));
     CU(scan_u32_to_u64(ctx->nv_out.as<uint32_t>(), ctx->anchor_off.as<uint64_t>(), ns + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
     uint64_t total_vtx = 0;
     CU(cudaMemcpyAsync(&total_vtx, ctx->anchor_off.as<uint64_t>() + ns, 8, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     o.n_anchor_vtx = total_vtx;
-    CU(ctx->anchor_rank.reserve(ns * 4)); CU(ctx->anchor_walk.reserve(ns * 4)); CU(ctx->anchor_vtx.reserve(total_vtx * 4 + 4));
-    CU(filter_csr_fill(A, order, ns, ctx->anchor_off.as<uint64_t>(), ctx->anchor_rank.as<int32_t>(), ctx->anchor_walk.as<int32_t>(),
-                       ctx->anchor_vtx.as<int32_t>(), ctx->apw.as<unsigned long long>(), ctx->walk_id_base, n_walks_global, ctx->st, &ctx->launches));
+    CU(ctx->anchor_walk.reserve(ns * 4)); CU(ctx->anchor_vtx.reserve(total_vtx * 4 + 4));
+    CU(filter_csr_fill(A, order, ns, ctx->anchor_off.as<uint64_t>(), key_order ? ctx->rank_off.as<uint64_t>() : nullptr, ctx->anchor_walk.as<int32_t>(),
+                       ctx->anchor_vtx.as<int32_t>(), ctx->apw.as<unsigned long long>(), n_walks_global, ctx->st, &ctx->launches));
     return PHI_OK;
 }
 
@@ -1071,6 +1023,8 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, const std::vect
     CU(cudaMemsetAsync(ctx->rank_drop.p, 0, (size_t)o.n_spec + 4, ctx->st));
     CU(ctx->anchor_off.reserve(8));
     CU(cudaMemsetAsync(ctx->anchor_off.p, 0, 8, ctx->st));
+    CU(ctx->rank_off.reserve(((size_t)o.n_spec + 2) * 8));
+    CU(cudaMemsetAsync(ctx->rank_off.p, 0, ((size_t)o.n_spec + 1) * 8, ctx->st));   // no anchors: every rank is empty
     CU(ctx->walk_gbase.reserve(h_walk_gbase.size() * 8));
     CU(cudaMemcpyAsync(ctx->walk_gbase.p, h_walk_gbase.data(), h_walk_gbase.size() * 8, cudaMemcpyHostToDevice, ctx->st));
     o.n_surv = 0; o.n_anchor_vtx = 0; o.n_filtered = 0;
@@ -1321,9 +1275,9 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     res->read_minimizers_emitted = o.read_emitted; res->path_hits = o.path_hits;
     if (do_download) {
         rc = download<uint64_t>(ctx, res, ctx->spec_a.p, mode == WALK_MODE_PROBE ? o.n_spec : 0, &res->spectrum);
-        if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_rank.p, o.n_surv, &res->anchor_rank);
+        if (!rc && mode == WALK_MODE_PROBE) rc = download<uint64_t>(ctx, res, ctx->rank_off.p, (uint64_t)o.n_spec + 1, &res->rank_off);
         if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_walk.p, o.n_surv, &res->anchor_walk);
-        if (!rc) rc = download<uint64_t>(ctx, res, ctx->anchor_off.p, o.n_surv + 1, &res->anchor_off);
+        if (!rc) rc = download<uint8_t>(ctx, res, ctx->anchor_len.p, o.n_surv, &res->anchor_len);
         if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_vtx.p, o.n_anchor_vtx, &res->anchor_vtx);
         if (!rc) rc = download<uint64_t>(ctx, res, ctx->apw.as<uint64_t>(), HG, &res->anchors_per_walk);
         if (rc) { phi_gpu_index_result_free(res); return rc; }

@@ -94,6 +94,10 @@ cudaError_t scan_u32_inplace(uint32_t *data, uint64_t n, void *scratch, cudaStre
 {
     return scan_rec<uint32_t, uint32_t>(data, data, n, (uint32_t *)scratch, st, launches);
 }
+cudaError_t scan_packed_steps(const PackedStep *in, uint64_t *out, uint64_t n, void *scratch, cudaStream_t st, uint64_t *launches)
+{
+    return scan_rec<PackedStep, uint64_t>(in, out, n, (uint64_t *)scratch, st, launches);
+}
 cudaError_t scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, void *scratch, cudaStream_t st, uint64_t *launches)
 {
     return scan_rec<uint32_t, uint32_t>(in, out, n, (uint32_t *)scratch, st, launches);

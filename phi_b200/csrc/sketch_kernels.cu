@@ -68,26 +68,34 @@ __device__ __forceinline__ uint64_t load8_unaligned(const uint8_t *p)
     return (w0 >> s) | (w[1] << (64 - s));
 }
 
-template <bool CLEAN>
+// FAST: register-resident core (CLEAN tile, 9 <= w <= 65); otherwise the shared-memory core (any w, any byte)
+template <bool CLEAN, bool FAST>
 __device__ __forceinline__ void read_tile_body(Tile &t, const ReadSketchArgs &A)
 {
     const int tid = threadIdx.x;
-    phase_canon<CLEAN>(t);
-    __syncthreads();
-    phase_block_minima<CLEAN>(t);
-    __syncthreads();
-    uint16_t *runs = t.pre;                                          // safe: phase_runs syncs before writing runs[]
-    int halo = -1;
-    const int n_runs = phase_runs<true, CLEAN>(t, runs, &halo);
+    uint16_t *runs = t.pre;                                          // safe: both cores sync before writing runs[]
+    uint64_t *run_val = t.canon;                                     // FAST only (canon[] is not used there)
+    int halo = -1, n_runs; uint64_t halo_val = 0;
+    if (FAST) {
+        n_runs = fast_runs<true>(t, runs, run_val, &halo, &halo_val);
+    } else {
+        phase_canon<CLEAN>(t);
+        __syncthreads();
+        phase_block_minima<CLEAN>(t);
+        __syncthreads();
+        n_runs = phase_runs<true, CLEAN>(t, runs, &halo);
+    }
     if (n_runs == 0) return;
 
-    if (tid == 0) t.hash[0] = halo >= 0 ? hash_at<CLEAN>(t, halo) : 0xFFFFFFFFFFFFFFFFull;
+    if (FAST) { if (tid == 32 * 0 + tile_halo_lanes(t.w)) t.hash[0] = halo >= 0 ? hash_packed_kmer(halo_val, t.k) : 0xFFFFFFFFFFFFFFFFull; }
+    else if (tid == 0) t.hash[0] = halo >= 0 ? hash_at<CLEAN>(t, halo) : 0xFFFFFFFFFFFFFFFFull;
     int emitted = 0;
     for (int b0 = 0; b0 < n_runs; b0 += NT) {
         const int j = b0 + tid; const bool have = j < n_runs;
         const int cnt = min(NT, n_runs - b0);
         uint32_t ent = have ? runs[j] : 0;
-        uint64_t h = have ? hash_at<CLEAN>(t, ent & 0x7FFF) : 0;
+        uint64_t h = 0;
+        if (have) h = FAST ? hash_packed_kmer(run_val[j], t.k) : hash_at<CLEAN>(t, ent & 0x7FFF);
         t.hash[tid + 1] = h;
         __syncthreads();
         uint64_t prev = (ent & 0x8000) ? 0xFFFFFFFFFFFFFFFFull : t.hash[tid];
@@ -100,31 +108,45 @@ __device__ __forceinline__ void read_tile_body(Tile &t, const ReadSketchArgs &A)
     if (tid == 0 && emitted) atomicAdd(&A.ctr[CTR_READ_EMITTED], (unsigned long long)emitted);
 }
 
-__global__ void __launch_bounds__(NT, 4)
+__global__ void __launch_bounds__(NT, 3)
 read_sketch_kernel(ReadSketchArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const TileLayout &L = A.layout;
     Tile t = carve(smem, L, A.k, A.w);
     const long long tile = blockIdx.x;
-    t.g0 = tile * TILE_W - A.w;
+    t.g0 = tile * L.cap - A.w - L.pad;
     t.seq_len = (long long)A.total_bases;
     set_window_bounds(t);
     const int tid = threadIdx.x;
 
-    // ---- read boundaries -> bit mask (bit p set iff a read starts at g0 + p)
-    const int nwords = (L.NB + 31) / 32 + 1;
-    for (int i = tid; i < nwords; i += NT) t.bnd[i] = 0;
+    // ---- read boundaries -> window masks.  A read starting at local base b makes the windows e with b inside their bases
+    // (e-w+1, e+k-1], i.e. e in [b-k+1, b+w-2], invalid, and e = b+w-1 the first window of that read.
+    const int nwords = (L.M + 31) / 32 + 2;
+    for (int i = tid; i < nwords; i += NT) { t.inval[i] = 0; t.firstm[i] = 0; }
     __syncthreads();
     {
         const long long hi = t.g0 + L.NB;
+        const int nbits = 32 * nwords;
         uint64_t r0 = A.tile_first_read[tile];
         for (;;) {
             uint64_t r = r0 + tid;
             int past = 1;
             if (r <= A.n_reads) {
                 long long off = (long long)A.read_off[r];
-                if (off < hi) { past = 0; atomicOr(&t.bnd[(off - t.g0) >> 5], 1u << ((off - t.g0) & 31)); }
+                if (off < hi) {
+                    past = 0;
+                    const int b = (int)(off - t.g0);
+                    const int lo = max(b - A.k + 1, 0), hi_b = min(b + A.w - 2, nbits - 1);
+                    for (int wi = lo >> 5; wi <= (hi_b >> 5) && lo <= hi_b; ++wi) {
+                        uint32_t m = 0xFFFFFFFFu;
+                        if (wi == (lo >> 5)) m &= 0xFFFFFFFFu << (lo & 31);
+                        if (wi == (hi_b >> 5)) m &= 0xFFFFFFFFu >> (31 - (hi_b & 31));
+                        atomicOr(&t.inval[wi], m);
+                    }
+                    const int f = b + A.w - 1;
+                    if (f < nbits) atomicOr(&t.firstm[f >> 5], 1u << (f & 31));
+                }
             }
             if (__syncthreads_or(past)) break;
             r0 += NT;
@@ -146,15 +168,17 @@ read_sketch_kernel(ReadSketchArgs A)
     }
     // a tile is CLEAN when every staged byte that a valid window can touch is A/C/G/T; padding at either end of
     // the data counts as dirty and sends the (few) boundary tiles through the general path
-    if (__syncthreads_or(dirty_any != 0)) read_tile_body<false>(t, A); else read_tile_body<true>(t, A);
+    if (__syncthreads_or(dirty_any != 0)) read_tile_body<false, false>(t, A);
+    else if (tile_fast_w(A.w)) read_tile_body<true, true>(t, A);
+    else read_tile_body<true, false>(t, A);
 }
 
-// per tile: first read r with read_off[r] >= tile*TILE_W - w
+// per tile: first read r with read_off[r] >= g0 = tile*cap - w - pad
 __global__ void read_tile_dir_kernel(const uint64_t *read_off, uint64_t n_reads, int w, uint64_t n_tiles, uint64_t *tile_first_read)
 {
     uint64_t tile = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (tile >= n_tiles) return;
-    long long g0 = (long long)tile * TILE_W - w;
+    long long g0 = (long long)tile * tile_cap(w) - w - tile_pad(w);
     uint64_t lo = 0, hi = n_reads + 1;                               // search over read_off[0 .. n_reads]
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
@@ -204,27 +228,34 @@ __device__ __forceinline__ int step_of(const Tile &t, int p)
     return t.cfirst[c] + __popc((uint32_t)t.cmask[c] & ((2u << (p & 7)) - 1u));
 }
 
-template <bool CLEAN>
+template <bool CLEAN, bool FAST>
 __device__ __forceinline__ void walk_tile_body(Tile &t, const WalkSketchArgs &A, const TileRec &tr, uint32_t tile)
 {
     const int tid = threadIdx.x;
-    phase_canon<CLEAN>(t);
-    __syncthreads();
-    phase_block_minima<CLEAN>(t);
-    __syncthreads();
     uint16_t *runs = t.pre;
-    int halo = -1;
-    const int n_runs = phase_runs<false, CLEAN>(t, runs, &halo);
+    uint64_t *run_val = t.canon;                                     // FAST only
+    int halo = -1, n_runs; uint64_t halo_val = 0;
+    if (FAST) {
+        n_runs = fast_runs<false>(t, runs, run_val, &halo, &halo_val);
+    } else {
+        phase_canon<CLEAN>(t);
+        __syncthreads();
+        phase_block_minima<CLEAN>(t);
+        __syncthreads();
+        n_runs = phase_runs<false, CLEAN>(t, runs, &halo);
+    }
     if (n_runs == 0) return;
 
-    if (tid == 0) t.hash[0] = halo >= 0 ? hash_at<CLEAN>(t, halo) : 0xFFFFFFFFFFFFFFFFull;
+    if (FAST) { if (tid == tile_halo_lanes(t.w)) t.hash[0] = halo >= 0 ? hash_packed_kmer(halo_val, t.k) : 0xFFFFFFFFFFFFFFFFull; }
+    else if (tid == 0) t.hash[0] = halo >= 0 ? hash_at<CLEAN>(t, halo) : 0xFFFFFFFFFFFFFFFFull;
     int emitted = 0;
     for (int b0 = 0; b0 < n_runs; b0 += NT) {
         const int jr = b0 + tid; const bool have = jr < n_runs;
         const int cnt = min(NT, n_runs - b0);
         uint32_t ent = have ? runs[jr] : 0;
         const int a = ent & 0x7FFF;
-        uint64_t hv = have ? hash_at<CLEAN>(t, a) : 0;
+        uint64_t hv = 0;
+        if (have) hv = FAST ? hash_packed_kmer(run_val[jr], t.k) : hash_at<CLEAN>(t, a);
         t.hash[tid + 1] = hv;
         __syncthreads();
         uint64_t prev = (ent & 0x8000) ? 0xFFFFFFFFFFFFFFFFull : t.hash[tid];
@@ -281,7 +312,7 @@ __device__ __forceinline__ void walk_tile_body(Tile &t, const WalkSketchArgs &A,
     if (tid == 0 && emitted) atomicAdd(&A.chunk_emitted[tr.chunk], (uint32_t)emitted);
 }
 
-__global__ void __launch_bounds__(NT, 4)
+__global__ void __launch_bounds__(NT, 3)
 walk_sketch_kernel(WalkSketchArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -292,9 +323,9 @@ walk_sketch_kernel(WalkSketchArgs A)
     const TileLayout &L = A.layout;
     Tile t = carve(smem, L, A.k, A.w);
     // the tile owns the window end positions [e0, e1) of walk h (at most TILE_W); everything below is sized by what it really holds
-    t.M = (int)(tr.e1 - tr.e0) + A.w; t.M8 = (t.M + 7) & ~7; t.NB = t.M + A.k - 1;
+    t.M = (int)(tr.e1 - tr.e0) + A.w + L.pad; t.M8 = (t.M + 7) & ~7; t.NB = t.M + A.k - 1;
     const int nchunks = (t.NB + 7) >> 3;
-    t.g0 = (long long)tr.e0 - A.w;
+    t.g0 = (long long)tr.e0 - A.w - L.pad;
     t.seq_len = len;
     set_window_bounds(t);
     const int tid = threadIdx.x;
@@ -355,56 +386,9 @@ walk_sketch_kernel(WalkSketchArgs A)
         t.cfirst[c] = (uint16_t)first; t.cmask[c] = (uint8_t)smask;
         dirty_any |= stage_chunk(t, c, v);
     }
-    if (__syncthreads_or(dirty_any != 0)) walk_tile_body<false>(t, A, tr, tile); else walk_tile_body<true>(t, A, tr, tile);
-}
-
-// ================================================================== graph preparation
-// step_len[s] = number of bases of the segment under walk step s
-__global__ void step_len_kernel(const uint32_t *walk_vtx, const uint64_t *seg_off, uint64_t n_steps, uint32_t *step_len)
-{
-    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (s >= n_steps) return;
-    uint32_t v = walk_vtx[s];
-    step_len[s] = (uint32_t)(seg_off[v + 1] - seg_off[v]);
-}
-
-__device__ __forceinline__ uint32_t walk_of_step(const uint64_t *walk_off, uint32_t n_walks, uint64_t s)
-{
-    uint32_t lo = 0, hi = n_walks;                                   // last h with walk_off[h] <= s
-    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
-    return lo;
-}
-
-// gbase = exclusive scan of step_len over ALL steps (u64) -> walk-relative step_base (u32)
-__global__ void step_finalize_kernel(const uint64_t *gbase, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, uint32_t *step_base)
-{
-    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (s >= n_steps) return;
-    uint32_t h = walk_of_step(walk_off, n_walks, s);
-    step_base[s] = (uint32_t)(gbase[s] - gbase[walk_off[h]]);
-}
-
-// walk_len[h] (bases) from the global scan
-__global__ void walk_len_kernel(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
-                                uint64_t n_steps, uint64_t *walk_len)
-{
-    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= n_walks) return;
-    uint64_t a = walk_off[h], b = walk_off[h + 1];
-    uint64_t ga = a < n_steps ? gbase[a] : (n_steps ? gbase[n_steps - 1] + step_len[n_steps - 1] : 0);
-    uint64_t gb = b < n_steps ? gbase[b] : (n_steps ? gbase[n_steps - 1] + step_len[n_steps - 1] : 0);
-    walk_len[h] = gb - ga;
-}
-
-// flags CTR_NONMONO if some walk visits vertices out of topological order (then anchors are verified per hit)
-__global__ void walk_monotone_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
-                                     const int32_t *top_order_map, unsigned long long *ctr)
-{
-    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (s + 1 >= n_steps) return;
-    uint32_t h = walk_of_step(walk_off, n_walks, s);
-    if (s + 1 >= walk_off[h + 1]) return;                             // last step of its walk
-    if (top_order_map[walk_vtx[s]] >= top_order_map[walk_vtx[s + 1]]) ctr[CTR_NONMONO] = 1;
+    if (__syncthreads_or(dirty_any != 0)) walk_tile_body<false, false>(t, A, tr, tile);
+    else if (tile_fast_w(A.w)) walk_tile_body<true, true>(t, A, tr, tile);
+    else walk_tile_body<true, false>(t, A, tr, tile);
 }
 
 // ================================================================== hash KAT hook
@@ -455,37 +439,6 @@ cudaError_t launch_walk_sketch(const WalkSketchArgs &A, uint32_t n_tiles, cudaSt
     return cudaGetLastError();
 }
 
-cudaError_t launch_step_len(const uint32_t *walk_vtx, const uint64_t *seg_off, uint64_t n_steps, uint32_t *step_len, cudaStream_t st)
-{
-    if (!n_steps) return cudaSuccess;
-    step_len_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, seg_off, n_steps, step_len);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_walk_len(const uint64_t *gbase, const uint32_t *step_len, const uint64_t *walk_off, uint32_t n_walks,
-                            uint64_t n_steps, uint64_t *walk_len, cudaStream_t st)
-{
-    if (!n_walks) return cudaSuccess;
-    walk_len_kernel<<<(n_walks + 127) / 128, 128, 0, st>>>(gbase, step_len, walk_off, n_walks, n_steps, walk_len);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_step_finalize(const uint64_t *gbase, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, uint32_t *step_base,
-                                 cudaStream_t st)
-{
-    if (!n_steps) return cudaSuccess;
-    step_finalize_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(gbase, walk_off, n_walks, n_steps, step_base);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_walk_monotone(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
-                                 const int32_t *top_order_map, unsigned long long *ctr, cudaStream_t st)
-{
-    if (n_steps < 2) return cudaSuccess;
-    walk_monotone_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, top_order_map, ctr);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_hash_bytes(const uint8_t *keys, uint64_t n, int len, uint64_t *out, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
@@ -493,7 +446,7 @@ cudaError_t launch_hash_bytes(const uint8_t *keys, uint64_t n, int len, uint64_t
     return cudaGetLastError();
 }
 
-int tile_windows() { return TILE_W; }
+int tile_windows(int w) { return tile_cap(w); }
 TileLayout tile_layout(int k, int w, bool walk) { return make_layout(k, w, walk); }
 
 }  // namespace phi

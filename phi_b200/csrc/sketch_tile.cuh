@@ -41,7 +41,8 @@ inline int align_up_h(int x, int a) { return (x + a - 1) / a * a; }
 inline TileLayout make_layout(int k, int w, bool walk)
 {
     TileLayout L;
-    L.M = TILE_W + w;
+    L.pad = tile_pad(w); L.cap = tile_cap(w);
+    L.M = L.cap + w + L.pad;
     L.M8 = align_up_h(L.M, 8);
     L.NB = L.M + k - 1;
     L.nchunks = (L.NB + 7) / 8;
@@ -50,10 +51,11 @@ inline TileLayout make_layout(int k, int w, bool walk)
     auto take = [&o](int bytes) { int at = o; o += align_up_h(bytes, 16); return at; };   // every section 16-byte aligned
     L.o_canon = take(8 * (L.M8 + 2 * (L.M8 / 8)));       // padded: idx(p) = p + 2*(p>>3)
     L.o_hash = take(8 * (NT + 1));
-    L.o_pack = take(4 * (nb8 / 16 + 4));
+    L.o_pack = take(4 * (nb8 / 16 + 12));                // slack: the register core reads up to 8 lanes x 8 positions past the tile's last k-mer
     L.o_dirty = take(4 * (nb8 / 32 + 4));
-    L.o_bnd = take(4 * (nb8 / 32 + 4));
-    L.o_scan = take(4 * 64);
+    L.o_bnd = take(4 * (nb8 / 32 + 8));
+    L.o_first = take(4 * (nb8 / 32 + 8));
+    L.o_scan = take(4 * 96);
     L.o_pre = take(2 * (L.M8 + 8));                      // runs[] aliases pre (TILE_W + 1 entries <= M)
     L.o_suf = take(2 * (L.M8 + 8));
     L.o_flag = take(L.M8 + 8);
@@ -69,13 +71,15 @@ inline TileLayout make_layout(int k, int w, bool walk)
 struct Tile {
     // geometry
     int k, w, M, M8, NB;
+    int pad, e_halo, e_own0; // front padding; local index of the halo window (w-1+pad) and of the first own window (w+pad)
     long long g0;            // global coordinate of local 0
     long long seq_len;       // WALK: walk length in bases; MULTI: total bases of all reads
     int e_lo, e_hi;          // WALK: local window ends e with a valid window are [e_lo, e_hi); e_first: the sequence's first window
     int e_first;
     // shared arrays
     uint64_t *canon; uint64_t *hash;
-    uint32_t *pack, *dirty, *bnd, *scan;
+    uint32_t *pack, *dirty, *scan;
+    uint32_t *inval, *firstm;   // MULTI: bit e set iff window e spans a read boundary / is the first window of its read
     uint16_t *pre, *suf, *steps, *cfirst;
     uint32_t *stepv;
     uint8_t *flag, *base, *cmask;
@@ -85,9 +89,10 @@ __device__ __forceinline__ Tile carve(unsigned char *smem, const TileLayout &L, 
 {
     Tile t;
     t.k = k; t.w = w; t.M = L.M; t.M8 = L.M8; t.NB = L.NB;
+    t.pad = L.pad; t.e_halo = w - 1 + L.pad; t.e_own0 = w + L.pad;
     t.canon = (uint64_t *)(smem + L.o_canon); t.hash = (uint64_t *)(smem + L.o_hash);
     t.pack = (uint32_t *)(smem + L.o_pack); t.dirty = (uint32_t *)(smem + L.o_dirty);
-    t.bnd = (uint32_t *)(smem + L.o_bnd); t.scan = (uint32_t *)(smem + L.o_scan);
+    t.inval = (uint32_t *)(smem + L.o_bnd); t.firstm = (uint32_t *)(smem + L.o_first); t.scan = (uint32_t *)(smem + L.o_scan);
     t.pre = (uint16_t *)(smem + L.o_pre); t.suf = (uint16_t *)(smem + L.o_suf);
     t.stepv = (uint32_t *)(smem + L.o_stepv); t.steps = (uint16_t *)(smem + L.o_steps);
     t.cfirst = (uint16_t *)(smem + L.o_cfirst); t.cmask = smem + L.o_cmask;
@@ -295,12 +300,12 @@ struct SeqModel {
     __device__ static __forceinline__ bool window_valid(const Tile &t, int e)
     {
         if (e < t.e_lo || e >= t.e_hi) return false;
-        if (MULTI) return !any_bits(t.bnd, e - t.w + 2, e + t.k - 1);     // no read starts strictly inside
+        if (MULTI) return !((t.inval[e >> 5] >> (e & 31)) & 1u);          // no read starts strictly inside
         return true;
     }
     __device__ static __forceinline__ bool window_first(const Tile &t, int e)
     {
-        if (MULTI) { int s = e - t.w + 1; return (t.bnd[s >> 5] >> (s & 31)) & 1u; }
+        if (MULTI) return (t.firstm[e >> 5] >> (e & 31)) & 1u;
         return e == t.e_first;
     }
 };
@@ -310,7 +315,7 @@ __device__ __forceinline__ void set_window_bounds(Tile &t)
 {
     // valid: g0 + e - w + 1 >= 0  and  g0 + e + k <= seq_len
     long long lo = (long long)t.w - 1 - t.g0, hi = t.seq_len - t.k - t.g0 + 1;
-    t.e_lo = (int)max(lo, (long long)(t.w - 1));
+    t.e_lo = (int)max(lo, (long long)t.e_halo);
     t.e_hi = (int)min(hi, (long long)t.M);
     t.e_first = (int)min(max(lo, -1ll), (long long)t.M + 1);               // only meaningful for the walk model
 }
@@ -330,13 +335,13 @@ __device__ __forceinline__ int phase_runs(const Tile &t, uint16_t *runs, int *ha
     int total = 0;
     int carry = -1;                                                       // arg-min of the window before this lane-0's window
     {
-        int e0 = t.w + wid * PER_WARP - 1;                                // window preceding the warp's first
+        int e0 = t.e_own0 + wid * PER_WARP - 1;                           // window preceding the warp's first
         if (lane == 0 && SeqModel<MULTI>::window_valid(t, e0)) carry = window_argmin<CLEAN>(t, e0);
         if (threadIdx.x == 0) *halo_arg = carry;
     }
     #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
-        const int e = t.w + wid * PER_WARP + r * 32 + lane;
+        const int e = t.e_own0 + wid * PER_WARP + r * 32 + lane;
         if (e - lane >= t.e_hi) { ballots[r] = 0; mine[r] = 0; continue; }  // warp-uniform: a short tile has no windows here (nor further on)
         const bool valid = SeqModel<MULTI>::window_valid(t, e);
         int a = valid ? window_argmin<CLEAN>(t, e) : -1;
@@ -361,6 +366,161 @@ __device__ __forceinline__ int phase_runs(const Tile &t, uint16_t *runs, int *ha
     for (int r = 0; r < ROUNDS; ++r) {
         if ((ballots[r] >> lane) & 1u) runs[off + __popc(ballots[r] & lanemask_lt())] = mine[r];
         off += __popc(ballots[r]);
+    }
+    __syncthreads();
+    return all;
+}
+
+// =====================================================================================================
+// Register-resident core (CLEAN tiles, 9 <= w <= 65): canonical k-mers, window arg-minima and run starts
+// without the canon[] / pre[] / suf[] round trips through shared memory.
+//
+// Lane l of warp wid owns the 8 consecutive k-mer positions  p = wid*UW + 8*l + i  (UW = 8*(32-HL) windows
+// per warp, HL = ceil((w-1)/8) halo lanes).  The window ending at position e = 8*l + i of a warp starts at
+// 8*(l-q) + (i-r) with w-1 = 8q + r, so its minimum is  suffix-min of one earlier lane (from offset i-r, or
+// i-r+8 one lane further back)  (+)  the full-lane minima in between  (+)  the prefix-min of the own lane up
+// to i, combined left to right with the right operand winning ties (rightmost minimal k-mer, :397).  Suffix
+// and full-lane minima travel by warp shuffles; the register index i-r is made a compile-time constant by
+// dispatching on r.
+// =====================================================================================================
+struct MinP { uint64_t v; int pos; };
+__device__ __forceinline__ MinP comb(MinP left, MinP right) { return right.v <= left.v ? right : left; }   // right wins ties
+
+template <int R>
+__device__ __forceinline__ void window_minima(const uint64_t (&pv)[8], uint32_t pidx, const uint64_t (&sv)[8], uint32_t sidx, int q, int lane_pos0,
+                                              uint64_t (&wv)[8], int (&wp)[8])
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    // full-lane minima of lanes l-1 .. l-q, folded left to right: FA = lanes l-q+1 .. l-1, FB = lanes l-q .. l-1
+    MinP FA; FA.v = 0xFFFFFFFFFFFFFFFFull; FA.pos = -1;
+    MinP FB = FA;
+    const uint64_t fullv = pv[7]; const int fullp = lane_pos0 + (int)(pidx >> 21);
+    for (int j = q; j >= 1; --j) {
+        MinP F; F.v = __shfl_up_sync(FULL, fullv, j); F.pos = __shfl_up_sync(FULL, fullp, j);
+        if (j == q) FB = F; else { FA = comb(FA, F); FB = comb(FB, F); }
+    }
+    const uint32_t sidx_a = __shfl_up_sync(FULL, sidx, q), sidx_b = __shfl_up_sync(FULL, sidx, q + 1);
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        MinP S, cur;
+        if (i >= R) {                                        // suffix of lane l-q from offset i-R, then lanes l-q+1 .. l-1
+            S.v = __shfl_up_sync(FULL, sv[(i - R) & 7], q);
+            S.pos = lane_pos0 - 8 * q + (int)((sidx_a >> (3 * ((i - R) & 7))) & 7u);
+            cur = comb(S, FA);
+        } else {                                             // suffix of lane l-q-1 from offset i-R+8, then lanes l-q .. l-1
+            S.v = __shfl_up_sync(FULL, sv[(i - R + 8) & 7], q + 1);
+            S.pos = lane_pos0 - 8 * (q + 1) + (int)((sidx_b >> (3 * ((i - R + 8) & 7))) & 7u);
+            cur = comb(S, FB);
+        }
+        MinP P; P.v = pv[i]; P.pos = lane_pos0 + (int)((pidx >> (3 * i)) & 7u);
+        cur = comb(cur, P);
+        wv[i] = cur.v; wp[i] = cur.pos;
+    }
+}
+
+// Runs of the tile's own windows, compacted in position order: runs[j] = arg-min position (| 0x8000: first window of its
+// sequence), run_val[j] = the canonical k-mer there.  *halo_pos / *halo_val: arg-min of the halo window (-1 if it does not exist).
+// Returns the number of runs (block-uniform).
+template <bool MULTI>
+__device__ __forceinline__ int fast_runs(const Tile &t, uint16_t *runs, uint64_t *run_val, int *halo_pos, uint64_t *halo_val)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int k = t.k, w = t.w;
+    const int HL = tile_halo_lanes(w), UW = 8 * (32 - HL);
+    const int q = (w - 1) >> 3, r = (w - 1) & 7;
+    const int p0 = wid * UW + 8 * lane;                       // local position of this lane's first k-mer
+    const bool warp_live = wid * UW + 8 * HL < t.e_hi;        // warp-uniform: the warp has at least one window below e_hi
+
+    uint64_t wv[8]; int wp[8];
+    if (warp_live) {
+        // ---- canonical k-mers of positions p0 .. p0+7, rolled
+        uint64_t cv[8];
+        {
+            const uint64_t kmask = k == 32 ? ~0ull : (1ull << (2 * k)) - 1;
+            const int top = 2 * (k - 1);
+            uint64_t fwd = extract_kmer(t.pack, p0, k);
+            uint64_t rc = revcomp2(fwd, k);
+            const uint32_t nxt = extract8(t.pack, p0 + k);
+            cv[0] = rc < fwd ? rc : fwd;
+            #pragma unroll
+            for (int i = 1; i < 8; ++i) {
+                uint64_t code = (nxt >> (16 - 2 * i)) & 3u;
+                fwd = ((fwd << 2) | code) & kmask;
+                rc = (rc >> 2) | ((3ull - code) << top);
+                cv[i] = rc < fwd ? rc : fwd;
+            }
+        }
+        // ---- prefix (later position wins ties) and suffix (earlier position wins only if strictly smaller) minima inside the lane
+        uint64_t pv[8], sv[8]; uint32_t pidx = 0, sidx = 7u << 21;
+        pv[0] = cv[0]; sv[7] = cv[7];
+        {
+            uint32_t pi = 0, si = 7;
+            #pragma unroll
+            for (int i = 1; i < 8; ++i) {
+                bool take = cv[i] <= pv[i - 1];
+                pv[i] = take ? cv[i] : pv[i - 1]; pi = take ? (uint32_t)i : pi; pidx |= pi << (3 * i);
+            }
+            #pragma unroll
+            for (int i = 6; i >= 0; --i) {
+                bool take = cv[i] < sv[i + 1];
+                sv[i] = take ? cv[i] : sv[i + 1]; si = take ? (uint32_t)i : si; sidx |= si << (3 * i);
+            }
+        }
+        switch (r) {
+            case 0: window_minima<0>(pv, pidx, sv, sidx, q, p0, wv, wp); break;
+            case 1: window_minima<1>(pv, pidx, sv, sidx, q, p0, wv, wp); break;
+            case 2: window_minima<2>(pv, pidx, sv, sidx, q, p0, wv, wp); break;
+            case 3: window_minima<3>(pv, pidx, sv, sidx, q, p0, wv, wp); break;
+            case 4: window_minima<4>(pv, pidx, sv, sidx, q, p0, wv, wp); break;
+            case 5: window_minima<5>(pv, pidx, sv, sidx, q, p0, wv, wp); break;
+            case 6: window_minima<6>(pv, pidx, sv, sidx, q, p0, wv, wp); break;
+            default: window_minima<7>(pv, pidx, sv, sidx, q, p0, wv, wp); break;
+        }
+    } else {
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) { wp[i] = -1; wv[i] = 0; }
+    }
+    // windows that exist: inside the sequence (and, MULTI, not across a read boundary); none in the halo lanes.  One byte per lane.
+    uint32_t valid8 = 0, first8 = 0;
+    if (warp_live && lane >= HL) {
+        const int lo_i = min(max(t.e_lo - p0, 0), 8), hi_i = min(max(t.e_hi - p0, 0), 8);
+        valid8 = ((1u << hi_i) - 1u) & ~((1u << lo_i) - 1u);
+        if (MULTI) { valid8 &= ~(uint32_t)((const uint8_t *)t.inval)[p0 >> 3]; first8 = ((const uint8_t *)t.firstm)[p0 >> 3]; }
+        else { const int f = t.e_first - p0; first8 = (f >= 0 && f < 8) ? 1u << f : 0u; }
+    }
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) if (!((valid8 >> i) & 1u)) wp[i] = -1;
+    // the window before a warp's first one is the last window of the previous warp
+    int *warp_last = (int *)(t.scan + 64);
+    if (lane == 31) warp_last[wid] = wp[7];
+    __syncthreads();
+    int prev = __shfl_up_sync(FULL, wp[7], 1);
+    if (lane == HL) prev = wid ? warp_last[wid - 1] : -1;
+    uint32_t changed = 0;                                       // bit i: arg-min of window i differs from the previous window's
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) { changed |= (wp[i] != prev ? 1u : 0u) << i; prev = wp[i]; }
+    const uint32_t firsts = first8 & valid8;
+    uint32_t starts = valid8 & (firsts | changed);
+    if (wid == 0 && lane == HL) starts &= ~1u;                  // the halo window only hands its arg-min on
+    if (wid == 0 && lane == HL) { *halo_pos = wp[0]; *halo_val = wv[0]; }      // window e_halo = lane HL, i = 0 of warp 0
+    // ---- compaction in position order: lanes in order, inside a lane by i
+    const int cnt = __popc(starts);
+    int inc = cnt;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int tt = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += tt; }
+    if (lane == 31) t.scan[wid] = inc;
+    __syncthreads();
+    int off = inc - cnt, all = 0;
+    #pragma unroll
+    for (int j = 0; j < NT / 32; ++j) { int c = t.scan[j]; if (j < wid) off += c; all += c; }
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if ((starts >> i) & 1u) {
+            runs[off] = (uint16_t)(wp[i] | (((firsts >> i) & 1u) ? 0x8000 : 0));
+            run_val[off] = wv[i];
+            ++off;
+        }
     }
     __syncthreads();
     return all;

@@ -121,8 +121,7 @@ def bench_main(args, rank, world, local, B):
     units = torch.tensor([res.read_kmer_positions + res.path_kmer_positions, res.read_kmer_positions, res.path_kmer_positions,
                           full.n_anchors, full.n_filtered,
                           sum(a.nbytes for a in (g.seg_off, g.seg_bases, g.walk_off, g.walk_vtx, g.top_order_map, rd.read_off, rd.read_bases)),
-                          sum(a.nbytes for a in (full.spectrum, full.anchor_rank, full.anchor_walk, full.anchor_off, full.anchor_vtx,
-                                                 full.minimizers_per_walk, full.anchors_per_walk))], dtype=torch.float64, device="cuda")
+                          full.wire_bytes()], dtype=torch.float64, device="cuda")
     dist.all_reduce(units, op=dist.ReduceOp.SUM)
     tm = {key: float(np.mean([s[key] for s in stage])) for key in stage[0]}
     if rank == 0:
