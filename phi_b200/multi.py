@@ -34,19 +34,24 @@ def shard_inputs(graph, reads, rank, world):
 
 
 def merge_results(parts):
-    """Per-rank results -> the global result.  Each rank returns the anchors of the hash-rank range it owns, ranges
-    ascend with the rank id, so concatenation keeps the final (rank, walk, j) order; per-walk counters are partial sums."""
+    """Per-rank results -> the global result.  Every rank returns the anchors of ITS walks for all hash ranks, sorted by
+    (rank, walk, j); walk ranges ascend with the rank id, so a stable sort of the concatenation on the hash rank alone gives
+    the global (rank, walk, j) order (a consumer that fills Anchor_hits[rank][walk] can simply take the parts one after another).
+    Per-walk counters are partial sums; n_filtered counts the dropped hash ranks each rank owns."""
     first = parts[0]
-    off = [np.zeros(1, dtype=np.uint64)]
-    base = 0
-    for p in parts:
-        off.append(p.anchor_off[1:] + np.uint64(base))
-        base += len(p.anchor_vtx)
+    rank = np.concatenate([p.anchor_rank for p in parts])
+    walk = np.concatenate([p.anchor_walk for p in parts])
+    lens = np.concatenate([np.diff(p.anchor_off.astype(np.int64)) for p in parts])
+    vtx = np.concatenate([p.anchor_vtx for p in parts])
+    starts = np.concatenate([[0], np.cumsum(lens)])[:-1]
+    order = np.argsort(rank, kind="stable")
+    from .synth import expand_ranges
+    new_vtx = vtx[expand_ranges(starts[order], lens[order])] if len(vtx) else vtx
     return _abi.IndexResultPy(
         count_sp_r=first.count_sp_r, n_walks=first.n_walks, n_filtered=sum(p.n_filtered for p in parts),
         spectrum=first.spectrum,
-        anchor_rank=np.concatenate([p.anchor_rank for p in parts]), anchor_walk=np.concatenate([p.anchor_walk for p in parts]),
-        anchor_off=np.concatenate(off), anchor_vtx=np.concatenate([p.anchor_vtx for p in parts]),
+        anchor_rank=rank[order], anchor_walk=walk[order],
+        anchor_off=np.concatenate([[0], np.cumsum(lens[order])]).astype(np.uint64), anchor_vtx=new_vtx.astype(np.int32),
         minimizers_per_walk=np.sum([p.minimizers_per_walk for p in parts], axis=0).astype(np.uint64),
         anchors_per_walk=np.sum([p.anchors_per_walk for p in parts], axis=0).astype(np.uint64),
         read_kmer_positions=sum(p.read_kmer_positions for p in parts), path_kmer_positions=sum(p.path_kmer_positions for p in parts),
@@ -140,7 +145,8 @@ def bench_main(args, rank, world, local, B):
                         "host_memory": "pinned (phi_gpu_host_alloc) in, pinned (library pool) out"},
                 "gpu_launches": int(tm["kernel_launches"]) * args.steps * world, "clocks": clk,
                 "exchange": "NCCL: all-to-all of distinct read-minimizer hashes by hash range + broadcast of the sorted slices; "
-                            "all-to-all of walk hits to the owner of their rank",
+                            "all-to-all of (rank, count, vertex list) group summaries to the owner of the rank + broadcast of the drop flags; "
+                            "anchors stay on the GPU that holds their walk",
                 "roofline": {"bound": "hbm", "kernel": "walk_sketch_kernel (rank 0)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": tm["walk_kernel_ms"]}}
         line["config"]["workload"] += f"; weak scaling: {args.haps} haplotypes + {args.coverage:g}x reads PER GPU ({n_haps} haplotypes in total)"

@@ -4,7 +4,8 @@ gpu : every rank drives one B200 through the C ABI (NCCL exchange inside the lib
       against the oracle on the unsharded input.
 cpu : gloo, no GPU — the same partition functions (phi_shard_*) and merge code, with the per-rank compute done by the
       oracle and the exchanges done with torch.distributed object collectives: a check of the sharded ALGORITHM
-      (hash-range ownership, rank offsets, hit routing, owner-side filter, merge), not of the kernels.
+      (hash-range ownership, rank offsets, group summaries to the owner, owner-side threshold, shared drop flags,
+      local ordering, merge), not of the kernels.
 """
 import os
 import sys
@@ -106,11 +107,26 @@ def main_cpu(name):
     hit = spectrum[idx] == hashes if len(spectrum) else np.zeros(len(hashes), dtype=bool)
     off = sk.anchor_off.astype(np.int64)
     hits = [(int(idx[a]), int(sk.anchor_walk[a]) + base, int(a), sk.anchor_vtx[off[a]:off[a + 1]].tolist()) for a in np.nonzero(hit)[0]]
-    route = [[h for h in hits if own_off[o] <= h[0] < own_off[o + 1]] for o in range(world)]
+    # group summaries (rank, vertex-list key) -> count travel to the owner of the rank; the owner adds them up and decides
+    groups = {}
+    for h in hits:
+        gk = (h[0], "".join(f"{v}_" for v in h[3]))
+        groups[gk] = groups.get(gk, 0) + 1
+    route = [{gk: c for gk, c in groups.items() if own_off[o] <= gk[0] < own_off[o + 1]} for o in range(world)]
     allroute = [None] * world
     dist.all_gather_object(allroute, route)
-    owned = [h for src in range(world) for h in allroute[src][rank]]
-    kept, filtered = py_filter(owned, g.n_walks, T)
+    total = {}
+    for src in range(world):
+        for gk, c in allroute[src][rank].items():
+            total[gk] = total.get(gk, 0) + c
+    thr = np.float32(T) * np.float32(g.n_walks)
+    dropped_here = sorted({gk[0] for gk, c in total.items() if np.float32(c) >= thr})
+    alldrop = [None] * world
+    dist.all_gather_object(alldrop, dropped_here)                       # the drop flags are shared
+    dropped = set(r for d in alldrop for r in d)
+    filtered = len(dropped_here)
+    kept, none_dropped = py_filter([h for h in hits if h[0] not in dropped], 1 << 30, 1.0)   # local order of the local walks' anchors
+    assert none_dropped == 0
     mpw = np.zeros(g.n_walks, dtype=np.uint64)
     mpw[base:base + gs.n_walks] = sk.minimizers_per_walk
     apw = np.bincount([h[1] for h in kept], minlength=g.n_walks).astype(np.uint64)
