@@ -179,7 +179,8 @@ def config_dict(args, n):
     return {"workload": f"BASELINE configs[1]: synthetic MHC-shaped acyclic graph, {args.haps} haplotypes x ~{args.backbone / 1e6:g} Mbp, "
                         f"nodes chopped to <=30 bp, {args.read_len} bp reads at {args.coverage:g}x, k={args.k} w={args.w} T=1.0",
             "seed": SEED, "gpus": n,
-            "l2": "no explicit flush: per-step working set (walk steps + step offsets + reads + hit buffers) exceeds the 126 MB L2"}
+            "l2": "no explicit flush: per-step working set (walk steps, packed steps + their scan, step offsets, reads, "
+                  "spectrum table, hit and anchor buffers: > 400 MB) exceeds the 126 MB L2"}
 
 
 def measured_peak():
@@ -195,11 +196,27 @@ def measured_peak():
 def walk_kernel_algorithmic_bytes(res, g, k):
     """SURVEY.md §8(d) per-unit figure x units of one launch, with this run's measured densities:
     0.25 B/position 2-bit segment store + 4 B per walk step (vertex id) + 32 B probe sector per emitted minimizer
-    + per hit a 16 B record and 4 B per anchor vertex."""
+    + per hit a 16 B record and 4 B per anchor vertex.  Units = ALL path k-mer positions the launch accounts for (the
+    result covers every walk); with walk sharing the kernel physically sketches only the representative chunks, see
+    roofline.sharing."""
     P = res.path_kmer_positions
     steps = len(g.walk_vtx)
     hit_vtx = res.path_hits * (1.0 + (k - 1) / max(1.0, (g.walk_lengths().sum() / max(1, steps))))
     return 0.25 * P + 4.0 * steps + 32.0 * res.path_minimizers_emitted + 16.0 * res.path_hits + 4.0 * hit_vtx
+
+
+def read_kernel_algorithmic_bytes(res, rd):
+    """SURVEY.md §8(d), the part of the per-read-k-mer figure that belongs to the read sketch kernel: the ASCII bases once
+    + per emitted minimizer a 32 B table sector read and written."""
+    return float(rd.read_bases.nbytes) + 64.0 * res.read_minimizers_emitted
+
+
+def kernel_traffic(name):
+    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    try:
+        return float(json.load(open(tp))[name]["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def main_gpu(args):
@@ -253,15 +270,15 @@ def main_gpu(args):
     e2e_value = units * args.steps / dt_e2e
 
     peak, peak_src = measured_peak()
-    alg_bytes = walk_kernel_algorithmic_bytes(res, g, k)
-    achieved = alg_bytes / (tm["walk_kernel_ms"] * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "walk_kernel_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    share = ix.sharing()
+    kernels = {}
+    for name, ms, alg in (("walk_sketch_kernel", tm["walk_kernel_ms"], walk_kernel_algorithmic_bytes(res, g, k)),
+                          ("read_sketch_kernel", tm["read_kernel_ms"], read_kernel_algorithmic_bytes(res, rd))):
+        ach = alg / (ms * 1e-3) / 1e9
+        kernels[name] = {"kernel_ms": ms, "algorithmic_bytes_per_launch": alg, "achieved": ach, "frac": ach / peak, "traffic": kernel_traffic(name)}
+    dom = max(kernels, key=lambda n: kernels[n]["kernel_ms"])                # the dominant kernel of the step
+    frac_unique = share["unique_windows"] / max(1, res.path_kmer_positions)
+    kernels["walk_sketch_kernel"]["achieved_physical"] = kernels["walk_sketch_kernel"]["achieved"] * frac_unique
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -279,11 +296,17 @@ def main_gpu(args):
                     "stage_ms": {key: float(np.mean([x[key] for x in e2e_stage])) for key in e2e_stage[0]}},
             "gpu_launches": int(tm["kernel_launches"]) * args.steps,
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "walk_sketch_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tm["walk_kernel_ms"],
-                         "note": "the sketch kernels are integer-issue bound (~100+ INT instr per k-mer vs ~4 B of compulsory "
-                                 "traffic), so the HBM fraction is low by construction; see DESIGN.md and profiles/"}}
+            "device_ms_per_step": tm["total_ms"],
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved"], "peak": peak, "unit": "GB/s",
+                         "frac": kernels[dom]["frac"], "traffic": kernels[dom]["traffic"], "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_launch"], "kernel_ms": kernels[dom]["kernel_ms"],
+                         "kernels": kernels,
+                         "sharing": dict(share, path_kmer_positions=res.path_kmer_positions, unique_fraction=frac_unique),
+                         "note": "both sketch kernels are integer-issue bound (~10 warp instructions per sketched k-mer vs a few bytes "
+                                 "of compulsory traffic), so their HBM fraction is low by construction (ncu: DRAM traffic per launch in "
+                                 "'traffic'). walk_sketch_kernel: 'achieved' counts the algorithmic bytes of ALL path k-mers the launch "
+                                 "accounts for; identical walk chunks are sketched once (sharing.unique_fraction), 'achieved_physical' "
+                                 "scales to the positions really sketched. See DESIGN.md and profiles/"}}
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n_walks = args.cpu_walks or min(threads, args.haps, 16)

@@ -324,74 +324,7 @@ __global__ void __launch_bounds__(256) expand_kernel(ChunkTable C, ExpandArgs X)
     }
 }
 
-// ---- the same instantiation, but every record goes straight to its FINAL index (single GPU): anchors are ordered by
-// (rank, walk, position) and chunk ids ascend in (walk, position) order, so the index of the record (hit u of rank r, member
-// chunk c) is  rank_off[r] + sum over the hits u' of rank r of  #(members of chunk(u') below c)  [+ 1 if u' lies in the same
-// chunk at a smaller position].  Buckets are small (a locus has a handful of distinct chunk variants), member lists are sorted.
-__global__ void __launch_bounds__(256) expand_ranked_kernel(ChunkTable C, ExpandArgs X)
-{
-    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (c >= C.n_chunks) return;
-    const uint32_t rep = C.c_rep[c];
-    if (rep == C_NONE) return;
-    const uint32_t walk = X.walk_id_base + C.c_walk[c];
-    const uint32_t t0 = C.c_tile_base[rep], nt = C.c_ntile[rep];
-    for (uint32_t t = t0; t < t0 + nt; ++t) {
-        for (int sg = 0; sg < SEG_PER_TILE; ++sg) {
-            const uint32_t cnt = X.hseg_cnt[(size_t)t * SEG_PER_TILE + sg], off = X.hseg_off[(size_t)t * SEG_PER_TILE + sg];
-            for (uint32_t i0 = lane; i0 < cnt; i0 += 32) {                  // (off is only meaningful where cnt > 0)
-                const uint32_t i = off + i0;
-                const uint32_t r = X.hit_rank[i];
-                if (X.rank_drop[r]) continue;
-                const uint32_t pos = X.hit_pos[i];
-                uint64_t j = X.rank_off[r];
-                const uint32_t q1 = X.bucket_off[r + 1];
-                for (uint32_t q = X.bucket_off[r]; q < q1; ++q) {
-                    const uint4 b = X.bucket_hits[q];                      // (pos, chunk, first member, members)
-                    const uint32_t *lst = X.mem_list + b.z;
-                    uint32_t lo = 0, hi = b.w;                             // members of that chunk below c
-                    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (lst[m] < c) lo = m + 1; else hi = m; }
-                    j += lo;
-                    if (b.y == rep && b.x < pos) ++j;
-                }
-                X.x_rank[j] = r; X.x_walk[j] = walk; X.x_voff[j] = X.hit_voff[i]; X.x_nv[j] = X.hit_nv[i];
-            }
-        }
-    }
-}
-
-__global__ void member_keys_kernel(ChunkTable C, uint64_t *keys, uint32_t *vals)
-{
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C.n_chunks) return;
-    const uint32_t rep = C.c_rep[c];
-    keys[c] = rep == C_NONE ? C.n_chunks : rep;                             // inactive chunks sort behind everything
-    vals[c] = c;
-}
-
 // ------------------------------------------------------------------ launchers
-cudaError_t chunk_expand_ranked(const ChunkTable &C, const ExpandArgs &X, cudaStream_t st, uint64_t *launches)
-{
-    if (!C.n_chunks) return cudaSuccess;
-    expand_ranked_kernel<<<(unsigned)(((uint64_t)C.n_chunks * 32 + 255) / 256), 256, 0, st>>>(C, X);
-    PHI_LAUNCH_CHECK();
-    return cudaSuccess;
-}
-
-cudaError_t chunk_member_lists(const ChunkTable &C, uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, void *sort_scratch,
-                               uint32_t *mem_off, void *scan_scratch, cudaStream_t st, uint64_t *launches)
-{
-    if (!C.n_chunks) return cudaSuccess;
-    member_keys_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>(C, keys_a, vals_a);
-    PHI_LAUNCH_CHECK();
-    // stable sort on the representative id: chunk ids stay ascending inside every list
-    int bits = 1; while (bits < 32 && (C.n_chunks >> bits)) ++bits;
-    cudaError_t e = radix_sort_u64(keys_a, keys_b, vals_a, vals_b, C.n_chunks, 0, bits, sort_scratch, st, launches);
-    if (e != cudaSuccess) return e;
-    return scan_u32(C.c_ninst, mem_off, (uint64_t)C.n_chunks + 1, scan_scratch, st, launches);
-}
-
 cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, uint32_t *tlen, uint64_t *prefix, uint64_t *coord,
                              void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
 {

@@ -12,8 +12,7 @@
 //                     the hash only picks the start slot).
 //   2. mark         : a slot whose count reaches the threshold drops its rank.
 //   3. survivors    : the hits of the representative chunks are instantiated for every member chunk (chunks.cu) in
-//                     (walk, position) order, then a stable radix sort on the rank alone gives (rank, walk, position);
-//                     records that arrive from other GPUs are sorted on (rank, global path coordinate).
+//                     (walk, position) order, then a stable radix sort on the rank alone gives (rank, walk, position).
 //   4. multi-hit fix: only (rank, walk) groups with >= 2 hits need the decimal-string key order;
 //                     small groups by insertion sort in one thread, big ones by a block rank sort.
 //   5. CSR          : scan of list lengths + gather.
@@ -75,38 +74,7 @@ __global__ void mark_drop_kernel(FilterArgs A, FilterWork W)
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= A.n_hits) return;
     // anchor.second.first >= threshold * num_walks  — int32 promoted to float (:698)
-    const uint32_t r = A.hit_rank[i];
-    if ((float)(int32_t)W.g_cnt[W.hit_slot[i]] >= A.thr) W.rank_drop[r] = 1;
-    if (W.rank_cnt) atomicAdd(&W.rank_cnt[r], 1u);
-}
-
-// hits grouped by rank: bucket_off = exclusive scan of the per-rank counts, cursor zeroed by the caller
-// bucket entry = what placing a record against this hit needs, in one 16-byte load: (position inside the chunk, chunk id,
-// first member of the chunk in mem_list, members of the chunk)
-__global__ void bucket_hits_kernel(FilterArgs A, const uint32_t *bucket_off, uint32_t *cursor, const uint32_t *mem_off, const uint32_t *chunk_members,
-                                   uint4 *bucket_hits)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= A.n_hits) return;
-    const uint32_t r = A.hit_rank[i], c = A.hit_walk[i];
-    bucket_hits[bucket_off[r] + atomicAdd(&cursor[r], 1u)] = make_uint4(A.hit_pos[i], c, mem_off[c], chunk_members[c]);
-}
-
-// records of rank r once every hit is instantiated for all members of its chunk (hit_walk holds the chunk id here)
-__global__ void rank_totals_kernel(FilterArgs A, const uint8_t *rank_drop, const uint32_t *bucket_off, const uint4 *bucket_hits, uint32_t *rank_tot)
-{
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > A.n_ranks) return;
-    uint32_t tot = 0;
-    if (r < A.n_ranks && !rank_drop[r])
-        for (uint32_t q = bucket_off[r]; q < bucket_off[r + 1]; ++q) tot += bucket_hits[q].w;
-    rank_tot[r] = tot;
-}
-
-__global__ void iota_kernel(uint32_t *p, uint64_t n)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n) p[i] = (uint32_t)i;
+    if ((float)(int32_t)W.g_cnt[W.hit_slot[i]] >= A.thr) W.rank_drop[A.hit_rank[i]] = 1;
 }
 
 __global__ void count_drops_kernel(const uint8_t *rank_drop, uint32_t n, unsigned long long *ctr)
@@ -157,37 +125,24 @@ cudaError_t filter_mark_drops(const FilterArgs &A, const FilterWork &W, cudaStre
     }
     return cudaSuccess;
 }
-cudaError_t filter_bucket_hits(const FilterArgs &A, const uint32_t *bucket_off, uint32_t *cursor, const uint32_t *mem_off, const uint32_t *chunk_members,
-                               uint4 *bucket_hits, cudaStream_t st, uint64_t *launches)
+__global__ void emit_rank_keys_kernel(FilterArgs A, uint32_t *keys, uint32_t *vals)
 {
-    if (!A.n_hits) return cudaSuccess;
-    bucket_hits_kernel<<<(unsigned)((A.n_hits + 255) / 256), 256, 0, st>>>(A, bucket_off, cursor, mem_off, chunk_members, bucket_hits);
-    PHI_LAUNCH_CHECK();
-    return cudaSuccess;
-}
-cudaError_t filter_rank_totals(const FilterArgs &A, const uint8_t *rank_drop, const uint32_t *bucket_off, const uint4 *bucket_hits,
-                               uint32_t *rank_tot, cudaStream_t st, uint64_t *launches)
-{
-    rank_totals_kernel<<<(A.n_ranks + 1 + 255) / 256, 256, 0, st>>>(A, rank_drop, bucket_off, bucket_hits, rank_tot);
-    PHI_LAUNCH_CHECK();
-    return cudaSuccess;
-}
-cudaError_t fill_iota_u32(uint32_t *p, uint64_t n, cudaStream_t st, uint64_t *launches)
-{
-    if (!n) return cudaSuccess;
-    iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n);
-    PHI_LAUNCH_CHECK();
-    return cudaSuccess;
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < A.n_hits) { keys[i] = A.hit_rank[i]; vals[i] = (uint32_t)i; }
 }
 
 cudaError_t filter_sort_records(const FilterArgs &A, const FilterWork &W, bool presorted, cudaStream_t st, uint64_t *launches)
 {
     const uint64_t n = A.n_hits;
     if (!n) return cudaSuccess;
+    if (presorted) {                                                      // (u32 rank, u32 record) pairs, wide digits; keys live in keys_a / keys_b
+        emit_rank_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, (uint32_t *)W.keys_a, W.vals_a);
+        PHI_LAUNCH_CHECK();
+        return radix_sort_u32((uint32_t *)W.keys_a, (uint32_t *)W.keys_b, W.vals_a, W.vals_b, n, A.rank_bits, W.sort_scratch, st, launches);
+    }
     const bool combined = A.gpos_bits + A.rank_bits <= 64;
-    emit_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, W, presorted ? 0 : combined ? 1 : 2);
+    emit_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, W, combined ? 1 : 2);
     PHI_LAUNCH_CHECK();
-    if (presorted) return radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n, 0, A.rank_bits, W.sort_scratch, st, launches);
     if (combined) return radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n, 0, A.gpos_bits + A.rank_bits, W.sort_scratch, st, launches);
     cudaError_t e = radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n, 0, A.gpos_bits, W.sort_scratch, st, launches);
     if (e != cudaSuccess) return e;

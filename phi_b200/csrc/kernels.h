@@ -68,9 +68,6 @@ struct ChunkTable {
 
 struct ExpandArgs {
     int w; uint32_t walk_id_base;
-    // direct placement (chunk_expand_ranked): final index = rank_off[rank] + records of the same rank that sort before
-    const uint64_t *rank_off; const uint32_t *bucket_off; const uint4 *bucket_hits;   // (pos, chunk, first member, members)
-    const uint32_t *mem_list;             // members of every representative chunk, ascending chunk id (= (walk, position) order)
     const uint64_t *member_off;          // [n_chunks + 1] first expanded record of each member chunk
     const uint32_t *hseg_off, *hseg_cnt; // [n_tiles * SEG_PER_TILE]
     const uint8_t *rank_drop;
@@ -158,10 +155,7 @@ cudaError_t chunk_emitted(const ChunkTable &C, const uint32_t *c_emitted, const 
 cudaError_t chunk_survivors(const ChunkTable &C, const TileRec *tiles, uint32_t n_tiles, const uint32_t *hseg_off, const uint32_t *hseg_cnt,
                             const uint32_t *hit_rank, const uint8_t *rank_drop, uint32_t *c_surv, uint32_t *member_cnt, cudaStream_t st, uint64_t *launches);
 cudaError_t chunk_expand(const ChunkTable &C, const ExpandArgs &X, cudaStream_t st, uint64_t *launches);
-cudaError_t chunk_expand_ranked(const ChunkTable &C, const ExpandArgs &X, cudaStream_t st, uint64_t *launches);
-// member lists of the representative chunks: keys/vals scratch [n_chunks], mem_off = exclusive scan of c_ninst, mem_list sorted by chunk id
-cudaError_t chunk_member_lists(const ChunkTable &C, uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, void *sort_scratch,
-                               uint32_t *mem_off, void *scan_scratch, cudaStream_t st, uint64_t *launches);
+
 
 // primitives.cu — all on `st`, scratch supplied by the caller
 // exclusive scan of u32 -> u64 (out may not alias in); returns bytes of scratch needed when scratch == nullptr
@@ -176,6 +170,10 @@ cudaError_t scan_packed_steps(const PackedStep *in, uint64_t *out, uint64_t n, v
 // stable LSD radix sort of u64 keys (optional u32 values) on bits [bit_lo, bit_hi); result ends in keys_a/vals_a
 size_t radix_sort_scratch(uint64_t n);
 cudaError_t radix_sort_u64(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, uint64_t n, int bit_lo, int bit_hi,
+                           void *scratch, cudaStream_t st, uint64_t *launches);
+// stable LSD radix sort of (u32 key, u32 value) records on the low `bits` bits, digits of up to 11 bits; result in keys_a/vals_a
+size_t radix_sort_u32_scratch(uint64_t n);
+cudaError_t radix_sort_u32(uint32_t *keys_a, uint32_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, uint64_t n, int bits,
                            void *scratch, cudaStream_t st, uint64_t *launches);
 // Order-preserving spectrum table (sketch_kernels.cu: table_insert): slots [0, limit) + one EMPTY sentinel at table[limit].
 constexpr uint64_t TABLE_PAD = 4096;      // probe room behind the last home slot (no wrap-around)
@@ -205,7 +203,6 @@ struct FilterWork {                  // device scratch, sized by the host
     const uint32_t *weight;                        // optional [n_hits]: occurrences a record stands for (multi-GPU summaries)
     const uint32_t *chunk_weight;                  // optional [n_chunks]: members of the chunk hit_walk[i] names (hits of representatives)
     uint8_t *rank_drop;                            // [n_ranks]
-    uint32_t *rank_cnt;                            // optional [n_ranks + 1]: records per rank (counted by filter_mark_drops)
     uint32_t *flags;                               // [n_hits] survivor flags -> scanned
     uint64_t *keys_a, *keys_b; uint32_t *vals_a, *vals_b;   // [n_survivors]
     void *sort_scratch; void *scan_scratch;
@@ -213,15 +210,6 @@ struct FilterWork {                  // device scratch, sized by the host
 };
 cudaError_t filter_count_groups(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_mark_drops(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
-// Rank buckets of the representatives' hits and direct placement of the instantiated survivors (single GPU): no sort.
-//   bucket_off = exclusive scan of rank_cnt; bucket_hits = hit ids grouped by rank (any order inside a bucket)
-cudaError_t filter_bucket_hits(const FilterArgs &A, const uint32_t *bucket_off, uint32_t *cursor, const uint32_t *mem_off, const uint32_t *chunk_members,
-                               uint4 *bucket_hits, cudaStream_t st, uint64_t *launches);
-//   rank_tot[r] = instantiated records of rank r (0 if dropped) = sum over its bucket of the members of the hit's chunk
-cudaError_t filter_rank_totals(const FilterArgs &A, const uint8_t *rank_drop, const uint32_t *bucket_off, const uint4 *bucket_hits,
-                               uint32_t *rank_tot, cudaStream_t st, uint64_t *launches);
-cudaError_t fill_iota_u32(uint32_t *p, uint64_t n, cudaStream_t st, uint64_t *launches);
-
 // sort keys of records that ALL survive.  presorted: the records already are in (walk, position) order and only a stable
 // sort on the rank is needed; otherwise the key is (rank, global path coordinate), in one or two sorts.
 cudaError_t filter_sort_records(const FilterArgs &A, const FilterWork &W, bool presorted, cudaStream_t st, uint64_t *launches);

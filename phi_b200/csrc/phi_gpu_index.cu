@@ -70,7 +70,6 @@ struct phi_gpu_index_ctx {
     DevBuf mpw, hit_rank, hit_chunk, hit_pos, hit_voff, hit_nv, hit_hash, vtx_pool;
     // walk chunks (chunks.cu): boundaries, fingerprints, representatives, tiles, hit segments, expanded survivors
     DevBuf tlen, tprefix, coord, cflags, cpos, chunk_step, c_walk, c_L, c_R, c_lo, c_hi, c_h1, c_h2, c_slot, c_rep, c_ninst, c_ntile, c_tile_base, ctable, tiles;
-    DevBuf mk_a, mk_b, mv_a, mv_b, m_sort, mem_off, rank_cnt, bucket_off, bucket_cur, bucket_hits, rank_tot;
     DevBuf hseg_off, hseg_cnt, c_emitted, c_hits, c_surv, member_cnt, member_off, x_rank, x_walk, x_pos, x_voff, x_nv, x_hash;
     uint32_t n_chunks = 0, n_tiles = 0; uint64_t unique_windows = 0, active_chunks = 0, rep_chunks = 0, unique_hits = 0; int dedupe = 1, chunk_shift = 11;
     DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
@@ -148,7 +147,6 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
                       &ctx->spec_a, &ctx->spec_b, &ctx->sort_scr, &ctx->dir, &ctx->mpw, &ctx->hit_rank, &ctx->hit_chunk, &ctx->hit_pos,
                       &ctx->tlen, &ctx->tprefix, &ctx->coord, &ctx->cflags, &ctx->cpos, &ctx->chunk_step, &ctx->c_walk, &ctx->c_L, &ctx->c_R, &ctx->c_lo,
                       &ctx->c_hi, &ctx->c_h1, &ctx->c_h2, &ctx->c_slot, &ctx->c_rep, &ctx->c_ninst, &ctx->c_ntile, &ctx->c_tile_base, &ctx->ctable,
-                      &ctx->mk_a, &ctx->mk_b, &ctx->mv_a, &ctx->mv_b, &ctx->m_sort, &ctx->mem_off, &ctx->rank_cnt, &ctx->bucket_off, &ctx->bucket_cur, &ctx->bucket_hits, &ctx->rank_tot,
                       &ctx->tiles, &ctx->hseg_off, &ctx->hseg_cnt, &ctx->c_emitted, &ctx->c_hits, &ctx->c_surv, &ctx->member_cnt, &ctx->member_off,
                       &ctx->x_rank, &ctx->x_walk, &ctx->x_pos, &ctx->x_voff, &ctx->x_nv, &ctx->x_hash,
                       &ctx->xk_a, &ctx->xk_b, &ctx->xcnt, &ctx->xoff, &ctx->ag_send, &ctx->ag_recv, &ctx->m_rank, &ctx->m_cnt, &ctx->m_voff, &ctx->m_nv,
@@ -386,13 +384,6 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     }
     if (total_bases >= (1ull << STEP_BASE_BITS)) return ctx->fail(PHI_ERR_UNSUPPORTED, "2^38 or more walk bases on one GPU; shard the walks over more GPUs");
     ctx->unique_windows = ctx->h_ctr[CTR_UNIQUE_WINDOWS]; ctx->active_chunks = ctx->h_ctr[CTR_ACTIVE_CHUNKS];
-    // members of every representative chunk, ascending chunk id (used to place the instantiated hits without sorting)
-    CU(ctx->mk_a.reserve(((size_t)NC + 1) * 8)); CU(ctx->mk_b.reserve(((size_t)NC + 1) * 8));
-    CU(ctx->mv_a.reserve(((size_t)NC + 1) * 4)); CU(ctx->mv_b.reserve(((size_t)NC + 1) * 4));
-    CU(ctx->m_sort.reserve(radix_sort_scratch((uint64_t)NC + 1))); CU(ctx->mem_off.reserve(((size_t)NC + 2) * 4));
-    CU(cudaMemsetAsync(ctx->c_ninst.as<uint32_t>() + NC, 0, 4, ctx->st));
-    CU(chunk_member_lists(C, ctx->mk_a.as<uint64_t>(), ctx->mk_b.as<uint64_t>(), ctx->mv_a.as<uint32_t>(), ctx->mv_b.as<uint32_t>(), ctx->m_sort.p,
-                          ctx->mem_off.as<uint32_t>(), ctx->scan_scr.p, ctx->st, &ctx->launches));
     CU(ctx->tiles.reserve((size_t)ctx->n_tiles * sizeof(TileRec) + 32));
     CU(chunk_tiles(C, d_walk_off, ctx->step_base.as<uint32_t>(), w, ctx->tiles.as<TileRec>(), ctx->st, &ctx->launches));
     return PHI_OK;
@@ -963,7 +954,7 @@ static int expand_survivors(phi_gpu_index_ctx *ctx, int w, bool with_hash, uint6
 }
 
 // records of A (all of them survive) -> final (rank, walk, j) order -> CSR in ctx->anchor_*
-enum { ORDER_PLACED = 0, ORDER_BY_RANK = 1, ORDER_BY_RANK_AND_POS = 2 };   // records already final / in (walk, position) order / in any order
+enum { ORDER_BY_RANK = 1, ORDER_BY_RANK_AND_POS = 2 };   // records arrive in (walk, position) order / in any order
 
 static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, int order_mode, bool key_order, bool write_rank_off, uint32_t n_walks_global, RunOut &o)
 {
@@ -976,12 +967,11 @@ static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, int order_
     W.rank_drop = ctx->rank_drop.as<uint8_t>(); W.ctr = d_ctr;
     CU(cudaMemsetAsync(d_ctr + CTR_BIG_GROUPS, 0, 8, ctx->st));
     CU(ctx->keys_a.reserve(ns * 8)); CU(ctx->keys_b.reserve(ns * 8)); CU(ctx->vals_a.reserve(ns * 4)); CU(ctx->vals_b.reserve(ns * 4));
-    CU(ctx->sort_scr.reserve(radix_sort_scratch(ns)));
+    CU(ctx->sort_scr.reserve(std::max(radix_sort_scratch(ns), radix_sort_u32_scratch(ns))));
     CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(ns), scan_u32_to_u64_scratch(ns + 1))));
     W.keys_a = ctx->keys_a.as<uint64_t>(); W.keys_b = ctx->keys_b.as<uint64_t>();
     W.vals_a = ctx->vals_a.as<uint32_t>(); W.vals_b = ctx->vals_b.as<uint32_t>(); W.sort_scratch = ctx->sort_scr.p;
-    if (order_mode == ORDER_PLACED) CU(fill_iota_u32(W.vals_a, ns, ctx->st, &ctx->launches));
-    else CU(filter_sort_records(A, W, order_mode == ORDER_BY_RANK, ctx->st, &ctx->launches));
+    CU(filter_sort_records(A, W, order_mode == ORDER_BY_RANK, ctx->st, &ctx->launches));
     uint32_t *order = W.vals_a;
 
     if (key_order) {                                                      // (rank, walk) groups with several hits: std::map<std::string> order (:680-709)
@@ -1008,11 +998,6 @@ static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, int order_
     return PHI_OK;
 }
 
-__global__ void rank_count_kernel(const uint32_t *hit_rank, uint64_t n, uint32_t *rank_cnt)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(&rank_cnt[hit_rank[i]], 1u);
-}
 __global__ void summary_flags_kernel(const uint32_t *g_rep, const uint32_t *hit_slot, uint64_t n, uint32_t *flags)
 {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -1065,14 +1050,10 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, const std::vect
     // ---- which ranks are dropped.  One GPU: local group counts are the global ones.  Several GPUs: one (rank, count, list)
     // summary per local group travels to the owner of the rank, which adds the partial counts up and applies the threshold;
     // the drop flags of all owners are then shared.  Every rank takes part in every collective, also with zero hits.
-    const size_t NR = (size_t)o.n_spec + 2;
-    CU(ctx->rank_cnt.reserve(NR * 4)); CU(ctx->bucket_off.reserve(NR * 4)); CU(ctx->bucket_cur.reserve(NR * 4)); CU(ctx->rank_tot.reserve(NR * 4));
-    CU(cudaMemsetAsync(ctx->rank_cnt.p, 0, NR * 4, ctx->st)); CU(cudaMemsetAsync(ctx->bucket_cur.p, 0, NR * 4, ctx->st));
     if (ctx->world == 1) {
         if (!n) return PHI_OK;
         int rc = count_groups_adaptive(ctx, A, W, nullptr, ctx->c_ninst.as<uint32_t>());
         if (rc) return rc;
-        W.rank_cnt = ctx->rank_cnt.as<uint32_t>();                          // the marks also count the hits of every rank
         CU(filter_mark_drops(A, W, ctx->st, &ctx->launches));
     } else {
         std::string err; NcclApi *nc = nccl_api(err);
@@ -1092,8 +1073,6 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, const std::vect
             CU(ctx->m_rank.reserve(n_sum * 4 + 4)); CU(ctx->m_cnt.reserve(n_sum * 4 + 4)); CU(ctx->m_voff.reserve(n_sum * 8 + 8)); CU(ctx->m_nv.reserve(n_sum + 4));
             summary_emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(A, W.g_rep, W.g_cnt, W.hit_slot, ctx->flags64.as<uint64_t>(),
                                                                                  ctx->m_rank.as<uint32_t>(), ctx->m_cnt.as<uint32_t>(), ctx->m_voff.as<uint64_t>(), ctx->m_nv.as<uint8_t>());
-            CU(cudaGetLastError()); ctx->launches++;
-            rank_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(A.hit_rank, n, ctx->rank_cnt.as<uint32_t>());
             CU(cudaGetLastError()); ctx->launches++;
         }
         RouteIn I;
@@ -1121,35 +1100,17 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, const std::vect
         if (!n) { CU(read_counters(ctx)); o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED]; return PHI_OK; }
     }
 
-    // ---- the surviving hits of the representatives are instantiated for every member chunk of THIS GPU's walks, each record
-    // straight at its final index: rank buckets of the hits -> records per surviving rank -> rank_off (the result array itself)
-    CU(ctx->bucket_hits.reserve(n * 16 + 16));
-    CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(NR), scan_u32_to_u64_scratch(NR))));
-    CU(scan_u32(ctx->rank_cnt.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)o.n_spec + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
-    CU(filter_bucket_hits(A, ctx->bucket_off.as<uint32_t>(), ctx->bucket_cur.as<uint32_t>(), ctx->mem_off.as<uint32_t>(), ctx->c_ninst.as<uint32_t>(),
-                          ctx->bucket_hits.as<uint4>(), ctx->st, &ctx->launches));
-    CU(filter_rank_totals(A, ctx->rank_drop.as<uint8_t>(), ctx->bucket_off.as<uint32_t>(), ctx->bucket_hits.as<uint4>(), ctx->rank_tot.as<uint32_t>(),
-                          ctx->st, &ctx->launches));
-    CU(scan_u32_to_u64(ctx->rank_tot.as<uint32_t>(), ctx->rank_off.as<uint64_t>(), (uint64_t)o.n_spec + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
+    // ---- the surviving hits of the representatives are instantiated for every member chunk of THIS GPU's walks, in
+    // (walk, position) order; a stable sort on the rank alone then gives the final (rank, walk, position) order
     uint64_t ns = 0;
-    CU(cudaMemcpyAsync(&ns, ctx->rank_off.as<uint64_t>() + o.n_spec, 8, cudaMemcpyDeviceToHost, ctx->st));
+    int rc2 = expand_survivors(ctx, w, false, ns);
+    if (rc2) return rc2;
+    FilterArgs XA = filter_args(ctx, ns, ctx->x_rank, ctx->x_walk, ctx->x_pos, ctx->x_voff, ctx->x_nv, ctx->vtx_pool, o.n_spec, threshold, n_walks_global, h_walk_gbase);
+    rc2 = order_and_csr(ctx, XA, ORDER_BY_RANK, true, true, n_walks_global, o);
+    if (rc2) return rc2;
     CU(read_counters(ctx));
     o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED];                       // several GPUs: the dropped ranks this GPU owns
-    if (ns >= (1ull << 32)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-1 anchors on one GPU; shard the walks over more GPUs");
-    if (ns) {
-        CU(ctx->x_rank.reserve(ns * 4)); CU(ctx->x_walk.reserve(ns * 4)); CU(ctx->x_pos.reserve(ns * 4)); CU(ctx->x_voff.reserve(ns * 8)); CU(ctx->x_nv.reserve(ns));
-        ExpandArgs X; memset(&X, 0, sizeof(X));
-        X.w = w; X.walk_id_base = ctx->world > 1 ? ctx->walk_id_base : 0;
-        X.rank_off = ctx->rank_off.as<uint64_t>(); X.bucket_off = ctx->bucket_off.as<uint32_t>(); X.bucket_hits = ctx->bucket_hits.as<uint4>();
-        X.mem_list = ctx->mv_a.as<uint32_t>();
-        X.hseg_off = ctx->hseg_off.as<uint32_t>(); X.hseg_cnt = ctx->hseg_cnt.as<uint32_t>(); X.rank_drop = ctx->rank_drop.as<uint8_t>();
-        X.hit_rank = ctx->hit_rank.as<uint32_t>(); X.hit_pos = ctx->hit_pos.as<uint32_t>(); X.hit_voff = ctx->hit_voff.as<uint64_t>(); X.hit_nv = ctx->hit_nv.as<uint8_t>();
-        X.x_rank = ctx->x_rank.as<uint32_t>(); X.x_walk = ctx->x_walk.as<uint32_t>(); X.x_pos = ctx->x_pos.as<uint32_t>();
-        X.x_voff = ctx->x_voff.as<uint64_t>(); X.x_nv = ctx->x_nv.as<uint8_t>();
-        CU(chunk_expand_ranked(chunk_table(ctx), X, ctx->st, &ctx->launches));
-    }
-    FilterArgs XA = filter_args(ctx, ns, ctx->x_rank, ctx->x_walk, ctx->x_pos, ctx->x_voff, ctx->x_nv, ctx->vtx_pool, o.n_spec, threshold, n_walks_global, h_walk_gbase);
-    return order_and_csr(ctx, XA, ORDER_PLACED, true, false, n_walks_global, o);
+    return PHI_OK;
 }
 
 // A result owns pinned buffers borrowed from its ctx's pool; freeing it hands them back (or releases them if the ctx is gone).

@@ -240,6 +240,144 @@ cudaError_t radix_sort_u64(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a,
     return cudaSuccess;
 }
 
+// ------------------------------------------------------------------ radix sort, u32 keys with wide digits
+// Same scheme as above for (u32 key, u32 value) records with digits of up to 11 bits: a 20-bit key (the hash ranks of the
+// anchors) is sorted in 2 passes instead of 3, and every pass moves 8 instead of 12 bytes per record.
+constexpr int R32_MAXBINS = 2048;
+constexpr size_t R32_SMEM = (size_t)RS_WARPS * (R32_MAXBINS + 2) * 2 + (size_t)RS_B * 8 + (size_t)(2 * R32_MAXBINS + 2) * 4;
+
+__global__ void __launch_bounds__(RS_T) radix32_hist_kernel(const uint32_t *keys, uint64_t n, int shift, uint32_t nbins, uint32_t *hist, uint32_t nb)
+{
+    __shared__ uint32_t h[R32_MAXBINS];
+    for (uint32_t i = threadIdx.x; i < nbins; i += RS_T) h[i] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * RS_B;
+    #pragma unroll 4
+    for (int i = 0; i < RS_I; ++i) {
+        uint64_t idx = base + (uint64_t)i * RS_T + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (nbins - 1)], 1u);
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < nbins; d += RS_T) hist[(uint64_t)d * nb + blockIdx.x] = h[d];
+}
+
+__global__ void __launch_bounds__(RS_T) radix32_scatter_kernel(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
+                                                             uint64_t n, int shift, uint32_t nbins, const uint32_t *hist, uint32_t nb)
+{
+    extern __shared__ __align__(16) unsigned char r32_smem[];
+    uint16_t *wcount = (uint16_t *)r32_smem;                               // [RS_WARPS][nbins + 1] keys of a digit seen by a warp (<= 512)
+    const uint32_t wstride = nbins + 2;
+    uint32_t *skey = (uint32_t *)(r32_smem + (size_t)RS_WARPS * (R32_MAXBINS + 2) * 2);
+    uint32_t *sval = skey + RS_B;
+    uint32_t *gbase = sval + RS_B, *dstart = gbase + R32_MAXBINS;          // [nbins], [nbins + 1]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < RS_WARPS * wstride; i += RS_T) wcount[i] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * RS_B + (uint64_t)wid * (RS_I * 32);
+    uint32_t key[RS_I]; uint16_t rk[RS_I];
+    uint16_t *wc = wcount + (size_t)wid * wstride;
+    #pragma unroll
+    for (int r = 0; r < RS_I; ++r) {
+        uint64_t idx = base + r * 32 + lane;
+        bool valid = idx < n;
+        key[r] = valid ? keys_in[idx] : 0;
+        uint32_t d = valid ? ((key[r] >> shift) & (nbins - 1)) : nbins;
+        uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader) { old = wc[d]; wc[d] = (uint16_t)(old + __popc(peers)); }
+        old = __shfl_sync(0xFFFFFFFFu, old, leader);
+        rk[r] = (uint16_t)(old + __popc(peers & lanemask_lt()));
+        __syncwarp();
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < nbins; d += RS_T) {                 // exclusive offsets of the warps inside the block, per digit
+        uint32_t run = 0;
+        #pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = wcount[(size_t)w * wstride + d]; wcount[(size_t)w * wstride + d] = (uint16_t)run; run += c; }
+        gbase[d] = hist[(uint64_t)d * nb + blockIdx.x];
+        dstart[d] = run;
+    }
+    __syncthreads();
+    if (wid == 0) {                                                        // exclusive scan of the digit totals (nbins / 32 per lane)
+        const uint32_t per = nbins >> 5 ? nbins >> 5 : 1;
+        uint32_t sum = 0;
+        for (uint32_t i = 0; i < per; ++i) { uint32_t j = lane * per + i; if (j < nbins) sum += dstart[j]; }
+        uint32_t inc = sum;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+        uint32_t ex = inc - sum;
+        for (uint32_t i = 0; i < per; ++i) { uint32_t j = lane * per + i; if (j < nbins) { uint32_t v = dstart[j]; dstart[j] = ex; ex += v; } }
+        if (lane == 31) dstart[nbins] = inc;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int r = 0; r < RS_I; ++r) {
+        uint64_t idx = base + r * 32 + lane;
+        if (idx < n) {
+            uint32_t d = (key[r] >> shift) & (nbins - 1);
+            uint32_t loc = dstart[d] + wc[d] + rk[r];                      // block-local sorted position
+            skey[loc] = key[r];
+            sval[loc] = vals_in[idx];
+        }
+    }
+    __syncthreads();
+    const uint32_t cnt = dstart[nbins];
+    for (uint32_t i = threadIdx.x; i < cnt; i += RS_T) {
+        uint32_t k = skey[i];
+        uint32_t d = (k >> shift) & (nbins - 1);
+        uint32_t dst = gbase[d] + (i - dstart[d]);
+        keys_out[dst] = k;
+        vals_out[dst] = sval[i];
+    }
+}
+
+size_t radix_sort_u32_scratch(uint64_t n)
+{
+    uint64_t nb = (n + RS_B - 1) / RS_B;
+    return (size_t)(R32_MAXBINS * nb) * 4 + scan_u32_scratch(R32_MAXBINS * nb) + 64;
+}
+
+cudaError_t radix_sort_u32(uint32_t *keys_a, uint32_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, uint64_t n, int bits,
+                           void *scratch, cudaStream_t st, uint64_t *launches)
+{
+    if (n <= 1 || bits <= 0) return cudaSuccess;
+    if (n >= (1ull << 32) || bits > 32) return cudaErrorInvalidValue;
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(radix32_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R32_SMEM);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+    }
+    const int passes = (bits + 10) / 11;                                   // digits of at most 11 bits, as even as possible
+    const int dbits = (bits + passes - 1) / passes;
+    const uint32_t nbins = 1u << dbits;
+    const uint32_t nb = (uint32_t)((n + RS_B - 1) / RS_B);
+    uint32_t *hist = (uint32_t *)scratch;
+    void *scan_scr = (void *)(hist + (size_t)nbins * nb);
+    uint32_t *kin = keys_a, *kout = keys_b, *vin = vals_a, *vout = vals_b;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = p * dbits;
+        radix32_hist_kernel<<<nb, RS_T, 0, st>>>(kin, n, shift, nbins, hist, nb);
+        PHI_LAUNCH_CHECK();
+        cudaError_t e = scan_u32_inplace(hist, (uint64_t)nbins * nb, scan_scr, st, launches);
+        if (e != cudaSuccess) return e;
+        radix32_scatter_kernel<<<nb, RS_T, R32_SMEM, st>>>(kin, vin, kout, vout, n, shift, nbins, hist, nb);
+        PHI_LAUNCH_CHECK();
+        uint32_t *t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+    }
+    if (passes & 1) {                                                      // result currently in keys_b / vals_b: bring it home
+        cudaError_t e = cudaMemcpyAsync(keys_a, keys_b, n * 4, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(vals_a, vals_b, n * 4, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // ------------------------------------------------------------------ ordered spectrum table -> sorted array
 // A probe cluster is a maximal run of occupied slots.  Every key of a cluster has its home slot inside the cluster, homes are
 // monotone in the key, and clusters are separated by an EMPTY slot: sorting each cluster in place sorts the table.
