@@ -115,23 +115,24 @@ typedef struct {
     uint64_t path_hits;                  /* probes that found a rank (pre-filter anchors) */
 } phi_index_result;
 
-/* Per-stage device times of the last run, CUDA events on the ctx's stream (ms). */
+/* Per-stage device times of the last run, CUDA events on the ctx's two streams (ms).  The graph preparation (second stream)
+ * runs concurrently with the read stage (main stream), so the stage times add up to more than total_ms. */
 typedef struct {
-    float h2d_ms;            /* host -> device copies of graph + reads (0 for a resident run) */
-    float graph_prep_ms;     /* step base offsets, tile directory */
-    float read_sketch_ms;    /* read minimizers -> HBM hash table */
-    float spectrum_ms;       /* compact + sort + bucket directory */
-    float walk_sketch_ms;    /* walk minimizers + probe + anchor emit (dominant kernel) */
-    float filter_ms;         /* group count, threshold, ordering, CSR */
+    float h2d_ms;            /* first event -> last host -> device copy done (0 for a resident run); overlaps the read stage */
+    float graph_prep_ms;     /* second stream: step bases, walk chunks, fingerprints, grouping, tiles */
+    float read_sketch_ms;    /* read minimizers -> order-preserving HBM hash table -> sorted distinct hashes (waits for H2D of the reads) */
+    float spectrum_ms;       /* radix directory (multi-GPU: + exchange of the spectrum) */
+    float walk_sketch_ms;    /* minimizers of the representative chunks + probe + anchor emit */
+    float filter_ms;         /* group count, threshold, instantiation per walk, ordering, CSR */
     float d2h_ms;            /* device -> host copies of the result */
     float total_ms;          /* first event to last event */
     float walk_kernel_ms;    /* the walk sketch kernel alone (roofline numerator's denominator) */
     float read_kernel_ms;    /* the read sketch kernel alone */
     uint64_t kernel_launches;/* kernels launched by this library during the run */
-    /* multi-GPU runs only (0 otherwise): parts of read_sketch.. and walk_sketch_ms spent in the NCCL exchanges */
+    /* multi-GPU runs only (0 otherwise): parts of spectrum_ms and filter_ms spent in the NCCL exchanges */
     float exchange_spectrum_ms; /* hash-range all-to-all + owner dedup/sort + slice broadcast */
-    float route_hits_ms;        /* bucketing hits by owner (count + scatter kernels) */
-    float exchange_hits_ms;     /* counts all-gather + all-to-all of the hit records + rebase */
+    float route_hits_ms;        /* local group table + one summary per group */
+    float exchange_hits_ms;     /* all-to-all of the group summaries + owner-side counts + broadcast of the drop flags */
 } phi_stage_times;
 
 typedef struct phi_gpu_index_ctx phi_gpu_index_ctx;
@@ -214,9 +215,11 @@ int phi_gpu_hash128_to_64(phi_gpu_index_ctx *ctx, const uint8_t *keys, uint64_t 
  * phi_gpu_index_run / _run_resident treat `reads` and the walks of `graph` as
  * THIS RANK'S SHARD (segments and top_order_map replicated), exchange read
  * minimizer hashes by hash range (all-to-all), all-gather the spectrum, route
- * hits to the owner of their rank, and return on every rank the anchors whose
- * rank it owns; phi_shard_* below describe the partition.  walk ids in the
- * result are global: walk_id_base + local index.
+ * one (rank, count, vertex list) summary per local group to the owner of the
+ * rank (which applies the threshold; the drop flags are shared), and return on
+ * every rank the surviving anchors of ITS walks for all ranks (n_filtered: the
+ * dropped ranks this rank owns; sum over the ranks).  phi_shard_* below describe
+ * the partition.  walk ids in the result are global: walk_id_base + local index.
  */
 #define PHI_COMM_ID_BYTES 128
 int phi_gpu_index_comm_unique_id(uint8_t id[PHI_COMM_ID_BYTES]);
