@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) chunk_rep_kernel(ChunkTable C, const uint
     if (lane == 0) {
         C.c_rep[c] = rep;
         if (active) atomicAdd(&C.c_ninst[rep], 1u);
-        const uint32_t T = (uint32_t)tile_cap(w);
+        const uint32_t T = (uint32_t)tile_cap(w, WALK_TILE_THREADS);
         const uint32_t nt = (active && rep == c) ? (C.c_hi[c] - C.c_lo[c] + T - 1) / T : 0u;
         C.c_ntile[c] = nt;
         if (nt) atomicAdd(&ctr[CTR_UNIQUE_WINDOWS], (unsigned long long)(C.c_hi[c] - C.c_lo[c]));
@@ -236,7 +236,7 @@ __global__ void tile_fill_kernel(ChunkTable C, const uint64_t *walk_off, const u
     const uint32_t h = C.c_walk[c], lo = C.c_lo[c], hi = C.c_hi[c], R = C.c_R[c];
     const uint64_t ws = walk_off[h];
     const uint32_t tb = C.c_tile_base[c];
-    const uint32_t T = (uint32_t)tile_cap(w);
+    const uint32_t T = (hi - lo + nt - 1) / nt;                          // the chunk's windows, split evenly over its tiles (<= tile_cap each)
     for (uint32_t t = 0; t < nt; ++t) {
         TileRec r;
         r.walk = h; r.e0 = lo + t * T; r.e1 = min(r.e0 + T, hi); r.chunk = c; r.cbase = lo; r._r0 = r._r1 = 0;

@@ -36,8 +36,11 @@ enum {
 
 enum { WALK_MODE_PROBE = 0, WALK_MODE_ALL = 1 };
 
-constexpr int TILE_WINDOWS = 2048;   // window end positions per sketch tile (general path)
-constexpr int SEG_PER_TILE = 8;      // a tile emits its hits in batches of 256 runs: at most TILE_WINDOWS / 256 contiguous hit segments
+// threads of a sketch tile CTA.  Walk tiles: 4 warps (small barrier domains, 6 CTAs per SM, chunk-sized tiles fill better);
+// read tiles: 8 warps (the reads are one long coordinate system: bigger tiles amortise the per-tile set-up).
+constexpr int WALK_TILE_THREADS = 128, READ_TILE_THREADS = 256;
+constexpr int TILE_WINDOWS_PER_THREAD = 8;   // general path: window end positions per tile = 8 x threads
+constexpr int SEG_PER_TILE = TILE_WINDOWS_PER_THREAD;   // a walk tile emits its hits in batches of one run per thread: at most this many contiguous hit segments
 
 // Tile geometry as a function of w (sketch_tile.cuh).  For 9 <= w <= 65 a tile without non-ACGT bytes runs the
 // register-resident core: every lane owns 8 consecutive k-mer positions, a warp 256, of which the first
@@ -46,7 +49,7 @@ constexpr int SEG_PER_TILE = 8;      // a tile emits its hits in batches of 256 
 __host__ __device__ inline bool tile_fast_w(int w) { return w >= 9 && w <= 65; }
 __host__ __device__ inline int tile_halo_lanes(int w) { return (w + 6) >> 3; }                      // ceil((w - 1) / 8)
 __host__ __device__ inline int tile_pad(int w) { return tile_fast_w(w) ? 8 * tile_halo_lanes(w) - (w - 1) : 0; }
-__host__ __device__ inline int tile_cap(int w) { return tile_fast_w(w) ? 8 * (32 - tile_halo_lanes(w)) * 8 - 1 : TILE_WINDOWS; }
+__host__ __device__ inline int tile_cap(int w, int threads) { return tile_fast_w(w) ? (threads / 32) * (32 - tile_halo_lanes(w)) * 8 - 1 : TILE_WINDOWS_PER_THREAD * threads; }
 
 // One walk-sketch tile: window end positions [e0, e1) of walk `walk` (the representative of chunk `chunk`).
 struct TileRec {
@@ -81,7 +84,8 @@ struct TileLayout {
     int o_canon, o_hash, o_pack, o_dirty, o_bnd, o_first, o_scan, o_pre, o_suf, o_flag, o_base, o_stepv, o_steps, o_cfirst, o_cmask;
     int bytes;
 };
-TileLayout tile_layout(int k, int w, bool walk);
+TileLayout read_tile_layout(int k, int w);
+TileLayout walk_tile_layout(int k, int w);
 
 struct ReadSketchArgs {
     TileLayout layout;
@@ -114,7 +118,7 @@ struct WalkSketchArgs {
     unsigned long long *ctr;
 };
 
-int tile_windows(int w);
+int read_tile_windows(int w);
 
 // sketch_kernels.cu
 cudaError_t launch_read_tile_dir(const uint64_t *read_off, uint64_t n_reads, int w, uint64_t n_tiles, uint64_t *out, cudaStream_t st);

@@ -120,6 +120,7 @@ extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
     }
     phi_gpu_index_ctx *ctx = new phi_gpu_index_ctx();
     ctx->device = device;
+    if (const char *e_shift = getenv("PHI_GPU_CHUNK_SHIFT")) { int v = atoi(e_shift); if (v >= 4 && v <= 24) ctx->chunk_shift = v; }   // tuning only: results never depend on it
     if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     if ((e = cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
@@ -733,7 +734,7 @@ static int reads_sketch_launch(phi_gpu_index_ctx *ctx, int k, int w, const Reads
     CU(fill_u64(ctx->table.as<uint64_t>(), limit + 1, TABLE_EMPTY, ctx->st, &ctx->launches));
     CU(cudaMemsetAsync(d_ctr, 0, 4 * 8, ctx->st));                         // DISTINCT (unused), OVERFLOW, HAS_MAXKEY, READ_EMITTED
     ReadSketchArgs A;
-    A.layout = tile_layout(k, w, false);
+    A.layout = read_tile_layout(k, w);
     A.read_bases = ctx->read_bases.as<uint8_t>() + 16; A.read_off = ctx->read_off.as<uint64_t>();
     A.n_reads = ctx->n_reads; A.total_bases = ctx->read_total; A.tile_first_read = ctx->tile_first_read.as<uint64_t>();
     A.k = k; A.w = w; A.table = ctx->table.as<uint64_t>(); A.table_mult = rs.cap; A.table_limit = limit; A.ctr = d_ctr;
@@ -754,7 +755,7 @@ static int reads_sketch_launch(phi_gpu_index_ctx *ctx, int k, int w, const Reads
 static int stage_reads_begin(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &rs)
 {
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
-    const int T = tile_windows(w);
+    const int T = read_tile_windows(w);
     const uint64_t G = ctx->read_total, R = ctx->n_reads;
     rs.n_tiles = (R && G >= (uint64_t)(w + k - 1)) ? (G - k) / T + 1 : 0;
     CU(cudaEventRecord(ctx->ev[EV_RD0], ctx->st));
@@ -852,7 +853,7 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
         CU(cudaMemsetAsync(ctx->c_emitted.p, 0, (size_t)NC * 4, ctx->st));
         CU(cudaMemsetAsync(ctx->c_hits.p, 0, (size_t)NC * 4, ctx->st));
         WalkSketchArgs A;
-        A.layout = tile_layout(k, w, true); A.walks_monotone = walks_monotone;
+        A.layout = walk_tile_layout(k, w); A.walks_monotone = walks_monotone;
         A.seg_bases = ctx->seg_bases.as<uint8_t>() + 16; A.seg_off = ctx->seg_off.as<uint64_t>(); A.top_order_map = ctx->top_order.as<int32_t>();
         A.walk_vtx = d_walk_vtx; A.walk_off = d_walk_off; A.step_base = ctx->step_base.as<uint32_t>();
         A.walk_len = ctx->walk_len.as<uint64_t>(); A.tiles = ctx->tiles.as<TileRec>();

@@ -25,10 +25,15 @@
 #include "device_common.cuh"
 #include "kernels.h"
 
-namespace phi {
+#ifndef PHI_TILE_THREADS
+#error "define PHI_TILE_THREADS (threads of the tile CTA) before including sketch_tile.cuh"
+#endif
 
-constexpr int TILE_W = TILE_WINDOWS;   // windows per tile (kernels.h)
-constexpr int NT = 256;          // threads per tile CTA
+namespace phi {
+namespace {   // every translation unit gets its own copy, specialised for its tile size
+
+constexpr int NT = PHI_TILE_THREADS;                   // threads per tile CTA
+constexpr int TILE_W = TILE_WINDOWS_PER_THREAD * NT;   // windows per tile on the general path
 constexpr int MAX_W = 256;
 constexpr int MAX_K = 32;
 
@@ -36,12 +41,12 @@ constexpr uint8_t F_STRAND = 1;  // canonical == reverse complement
 constexpr uint8_t F_DIRTY = 2;   // k-mer contains a non-ACGT byte (or padding)
 
 // Dynamic shared memory carve-up: struct TileLayout lives in kernels.h (computed once on the host, passed by value).
-inline int align_up_h(int x, int a) { return (x + a - 1) / a * a; }
+static inline int align_up_h(int x, int a) { return (x + a - 1) / a * a; }
 
-inline TileLayout make_layout(int k, int w, bool walk)
+static inline TileLayout make_layout(int k, int w, bool walk)
 {
     TileLayout L;
-    L.pad = tile_pad(w); L.cap = tile_cap(w);
+    L.pad = tile_pad(w); L.cap = tile_cap(w, NT);
     L.M = L.cap + w + L.pad;
     L.M8 = align_up_h(L.M, 8);
     L.NB = L.M + k - 1;
@@ -526,4 +531,5 @@ __device__ __forceinline__ int fast_runs(const Tile &t, uint16_t *runs, uint64_t
     return all;
 }
 
+}  // namespace
 }  // namespace phi
