@@ -93,6 +93,9 @@ typedef struct {
  * minimizers_per_walk : kmer_index[h].size(), log line ILP_index.cpp:563.
  * anchors_per_walk    : log lines ILP_index.cpp:725-735.
  * n_filtered          : filtered_kmers, ILP_index.cpp:719-721 (log :738-743).
+ * n_walk_kmers / shared_kmer_hist : the -d1 statistic, ILP_index.cpp:565-606 — number of distinct walk-minimizer hashes
+ *     (uniqe_kmers.size()) and, for i in [0, n_walks], how many of them occur in exactly i walks (kmer_hist_count[i]).
+ *     Only computed when params.debug != 0 (shared_kmer_hist == NULL otherwise); single GPU only.
  */
 typedef struct {
     int32_t count_sp_r;
@@ -113,6 +116,9 @@ typedef struct {
     uint64_t read_minimizers_emitted;    /* table inserts attempted */
     uint64_t path_minimizers_emitted;    /* sum of minimizers_per_walk (== probes) */
     uint64_t path_hits;                  /* probes that found a rank (pre-filter anchors) */
+    /* debug statistic (params.debug) */
+    uint64_t n_walk_kmers;
+    const uint64_t *shared_kmer_hist;    /* [n_walks + 1] or NULL */
 } phi_index_result;
 
 /* Per-stage device times of the last run, CUDA events on the ctx's two streams (ms).  The graph preparation (second stream)

@@ -63,6 +63,12 @@ inline void run_front_end(ILP_index &ix, std::vector<std::pair<std::string, std:
     std::cerr << "Number of Minimizers" << std::endl;                                              // :556
     for (uint32_t h = 0; h < ix.num_walks; ++h)
         fprintf(stderr, "%s : %d\n", ix.hap_id2name[h].c_str(), (int)res->minimizers_per_walk[h]);   // :563
+    if (ix.debug && res->shared_kmer_hist) {                                                         // :593-606
+        fprintf(stderr, "Shared fraction of unique kmers by haplotypes\n");
+        for (uint32_t i = 1; i <= ix.num_walks; ++i)
+            fprintf(stderr, "[Haplotypes: %d, fraction of unique shared kmers: %.5f]\n", (int)i,
+                    (float)(int32_t)res->shared_kmer_hist[i] / (float)(int32_t)res->n_walk_kmers);
+    }
     fprintf(stderr, "[M::%s::%.3f*%.2f] Haplotypes sketched\n", "ILP_function", t, cputime() / t);   // :611
     fprintf(stderr, "[M::%s::%.3f*%.2f] Indexed reads with spectrum size: %d\n", "ILP_function", t, cputime() / t, res->count_sp_r);  // :641
 

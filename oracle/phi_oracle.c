@@ -306,6 +306,14 @@ static int cmp_hit_walk_key_seq(const void *a, const void *b)
     return cmp_hit_key_then_seq(a, b);
 }
 
+typedef struct { uint64_t h; int32_t w; } hw_t;
+static int cmp_hw(const void *a, const void *b)
+{
+    const hw_t *x = (const hw_t *)a, *y = (const hw_t *)b;
+    if (x->h != y->h) return x->h < y->h ? -1 : 1;
+    return x->w < y->w ? -1 : x->w > y->w;
+}
+
 int phi_oracle_index_run(const phi_graph_view *g, const phi_reads_view *rd, const phi_index_params *prm,
                          int n_threads, phi_index_result **out)
 {
@@ -320,6 +328,24 @@ int phi_oracle_index_run(const phi_graph_view *g, const phi_reads_view *rd, cons
     phi_index_result *wsr = 0; uint64_t *whash = 0;
     int rc = phi_oracle_sketch_walks(g, prm, n_threads, &wsr, &whash);
     if (rc) { free(r); return rc; }
+
+    /* ---- the -d1 statistic, ILP_index.cpp:565-606: distinct walk-minimizer hashes by the number of walks they occur in */
+    if (prm->debug) {
+        const uint64_t na = wsr->n_anchors;
+        hw_t *hw = (hw_t *)malloc((na ? na : 1) * sizeof(hw_t));
+        for (uint64_t a = 0; a < na; ++a) { hw[a].h = whash[a]; hw[a].w = wsr->anchor_walk[a]; }
+        if (na) qsort(hw, na, sizeof(hw_t), cmp_hw);
+        uint64_t *hist = (uint64_t *)calloc((size_t)g->n_walks + 1, 8);
+        uint64_t distinct = 0;
+        for (uint64_t i = 0; i < na;) {
+            uint64_t j = i, walks = 0;
+            while (j < na && hw[j].h == hw[i].h) { if (j == i || hw[j].w != hw[j - 1].w) ++walks; ++j; }
+            hist[walks]++; ++distinct;
+            i = j;
+        }
+        free(hw);
+        r->n_walk_kmers = distinct; r->shared_kmer_hist = hist;
+    }
 
     /* ---- loop B: read sketches + Sp_R, ILP_index.cpp:615-636 */
     uint64_t R = rd->n_reads;
@@ -428,7 +454,7 @@ void phi_oracle_result_free(phi_index_result *r)
     if (!r) return;
     free((void *)r->spectrum); free((void *)r->rank_off); free((void *)r->anchor_walk);
     free((void *)r->anchor_len); free((void *)r->anchor_vtx);
-    free((void *)r->minimizers_per_walk); free((void *)r->anchors_per_walk);
+    free((void *)r->minimizers_per_walk); free((void *)r->anchors_per_walk); free((void *)r->shared_kmer_hist);
     free(r);
 }
 void phi_oracle_free(void *p) { free(p); }

@@ -35,7 +35,7 @@ class IndexResult(C.Structure):
                 ("anchor_vtx", i32p), ("minimizers_per_walk", u64p), ("anchors_per_walk", u64p),
                 ("read_kmer_positions", C.c_uint64), ("path_kmer_positions", C.c_uint64),
                 ("read_minimizers_emitted", C.c_uint64), ("path_minimizers_emitted", C.c_uint64),
-                ("path_hits", C.c_uint64)]
+                ("path_hits", C.c_uint64), ("n_walk_kmers", C.c_uint64), ("shared_kmer_hist", u64p)]
 
 
 class StageTimes(C.Structure):
@@ -153,6 +153,8 @@ class IndexResultPy:
     read_minimizers_emitted: int = 0
     path_minimizers_emitted: int = 0
     path_hits: int = 0
+    n_walk_kmers: int = 0
+    shared_kmer_hist: np.ndarray = None        # [n_walks + 1] when the run had debug != 0
 
     @property
     def n_anchors(self):
@@ -198,4 +200,6 @@ def result_to_py(res: IndexResult) -> IndexResultPy:
         anchors_per_walk=_np_from(res.anchors_per_walk, nw, np.uint64),
         read_kmer_positions=int(res.read_kmer_positions), path_kmer_positions=int(res.path_kmer_positions),
         read_minimizers_emitted=int(res.read_minimizers_emitted),
-        path_minimizers_emitted=int(res.path_minimizers_emitted), path_hits=int(res.path_hits))
+        path_minimizers_emitted=int(res.path_minimizers_emitted), path_hits=int(res.path_hits),
+        n_walk_kmers=int(res.n_walk_kmers),
+        shared_kmer_hist=_np_from(res.shared_kmer_hist, nw + 1, np.uint64) if res.shared_kmer_hist else None)

@@ -112,13 +112,13 @@ class PhiGpuIndex:
             self.lib.phi_gpu_index_result_free(resp)
         return res
 
-    def run(self, graph, reads, k=31, w=25, threshold=1.0):
+    def run(self, graph, reads, k=31, w=25, threshold=1.0, debug=0):
         """Host buffers in, host result out (H2D + kernels + D2H): the drop-in call.  Returns numpy copies."""
-        return self._take(self.run_raw(graph, reads, k, w, threshold))
+        return self._take(self.run_raw(graph, reads, k, w, threshold, debug))
 
-    def run_raw(self, graph, reads, k=31, w=25, threshold=1.0):
+    def run_raw(self, graph, reads, k=31, w=25, threshold=1.0, debug=0):
         """The same call, returning the C result pointer untouched (no numpy copies); free it with free_raw()."""
-        gv, rv, prm = graph.view(), reads.view(), self._params(k, w, threshold)
+        gv, rv, prm = graph.view(), reads.view(), self._params(k, w, threshold, debug)
         out = C.POINTER(_abi.IndexResult)()
         self._check(self.lib.phi_gpu_index_run(self.ctx, C.byref(gv), C.byref(rv), C.byref(prm), C.byref(out)))
         return out

@@ -106,6 +106,38 @@ __global__ void rank_keys_kernel(FilterArgs A, const uint32_t *vals, uint64_t *k
     if (j < n) keys[j] = A.hit_rank[vals[j]];
 }
 
+// ---- the -d1 statistic (/root/reference/src/ILP_index.cpp:565-606): (hash, walk) pairs sorted by hash, walks ascending inside
+// a hash.  The thread at the start of a hash run counts the distinct walks of the run and bumps hist[count] (block-local
+// histogram first: few distinct counts -> heavy contention otherwise).
+__global__ void shared_kmer_hist_kernel(const uint64_t *hash, const uint32_t *walk, uint64_t n, uint32_t n_walks, unsigned long long *hist,
+                                        unsigned long long *distinct)
+{
+    extern __shared__ uint32_t s_h[];
+    const bool local = n_walks + 1 <= CSR_HIST_MAX;
+    if (local) { for (uint32_t i = threadIdx.x; i <= n_walks; i += blockDim.x) s_h[i] = 0; __syncthreads(); }
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint32_t cnt = 0;
+    if (i < n && (i == 0 || hash[i] != hash[i - 1])) {
+        const uint64_t h = hash[i];
+        cnt = 1;
+        for (uint64_t j = i + 1; j < n && hash[j] == h; ++j) cnt += walk[j] != walk[j - 1];
+        if (local) atomicAdd(&s_h[cnt], 1u); else atomicAdd(&hist[cnt], 1ull);
+    }
+    const uint32_t heads = __syncthreads_count(cnt != 0);
+    if (threadIdx.x == 0 && heads) atomicAdd(distinct, (unsigned long long)heads);
+    if (local) for (uint32_t q = threadIdx.x; q <= n_walks; q += blockDim.x) if (s_h[q]) atomicAdd(&hist[q], (unsigned long long)s_h[q]);
+}
+
+cudaError_t filter_shared_kmer_hist(const uint64_t *hash, const uint32_t *walk, uint64_t n, uint32_t n_walks, unsigned long long *hist,
+                                    unsigned long long *distinct, cudaStream_t st, uint64_t *launches)
+{
+    if (!n) return cudaSuccess;
+    const size_t smem = n_walks + 1 <= CSR_HIST_MAX ? ((size_t)n_walks + 1) * 4 : 0;
+    shared_kmer_hist_kernel<<<(unsigned)((n + 255) / 256), 256, smem, st>>>(hash, walk, n, n_walks, hist, distinct);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
 cudaError_t filter_count_groups(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches)
 {
     if (!A.n_hits) return cudaSuccess;

@@ -30,7 +30,8 @@ enum {
     CTR_DEDUPE_MISMATCH = 18,
     CTR_PATH_HITS = 19,
     CTR_CHUNK_FLAGS = 20,         // chunk-start flags set by the step pass (guards the chunk field of the packed scan)
-    CTR_SEG_TOO_LONG = 21,        // a segment of 2^31 bases or more           // hits of all walks (every member chunk counts what its representative found)     // a chunk differs from its fingerprint representative (128-bit collision): rerun without sharing
+    CTR_SEG_TOO_LONG = 21,        // a segment of 2^31 bases or more
+    CTR_WALK_KMERS = 22,          // distinct walk-minimizer hashes (-d1 statistic)           // hits of all walks (every member chunk counts what its representative found)     // a chunk differs from its fingerprint representative (128-bit collision): rerun without sharing
     CTR_COUNT = 24
 };
 
@@ -212,6 +213,8 @@ struct FilterWork {                  // device scratch, sized by the host
     void *sort_scratch; void *scan_scratch;
     unsigned long long *ctr;
 };
+cudaError_t filter_shared_kmer_hist(const uint64_t *hash, const uint32_t *walk, uint64_t n, uint32_t n_walks, unsigned long long *hist,
+                                    unsigned long long *distinct, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_count_groups(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_mark_drops(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
 // sort keys of records that ALL survive.  presorted: the records already are in (walk, position) order and only a stable

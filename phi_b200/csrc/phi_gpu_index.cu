@@ -73,7 +73,7 @@ struct phi_gpu_index_ctx {
     DevBuf hseg_off, hseg_cnt, c_emitted, c_hits, c_surv, member_cnt, member_off, x_rank, x_walk, x_pos, x_voff, x_nv, x_hash;
     uint32_t n_chunks = 0, n_tiles = 0; uint64_t unique_windows = 0, active_chunks = 0, rep_chunks = 0, unique_hits = 0; int dedupe = 1, chunk_shift = 11;
     DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
-    DevBuf anchor_off, rank_off, anchor_len, anchor_walk, anchor_vtx, apw, walk_gbase;
+    DevBuf anchor_off, rank_off, anchor_len, anchor_walk, anchor_vtx, apw, walk_gbase, dbg_hist;
     unsigned long long *h_ctr = nullptr;   // pinned mirror of the counter block
     // what the second stream uses instead of ctr / h_ctr / scan_scr / flags / flags64 / nv_out (swapped in by PrepScope)
     DevBuf ctr2, scan_scr2, flags2, flags64_2, nv_out2; unsigned long long *h_ctr2 = nullptr;
@@ -155,7 +155,7 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
                       &ctx->s_voff, &ctx->s_nv, &ctx->s_vtx,
                       &ctx->hit_voff, &ctx->hit_nv, &ctx->hit_hash, &ctx->vtx_pool, &ctx->g_rep, &ctx->g_cnt, &ctx->rank_drop, &ctx->flags,
                       &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->big_list, &ctx->tmp_order, &ctx->nv_out,
-                      &ctx->anchor_off, &ctx->rank_off, &ctx->anchor_len, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw, &ctx->walk_gbase};
+                      &ctx->dbg_hist, &ctx->anchor_off, &ctx->rank_off, &ctx->anchor_len, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw, &ctx->walk_gbase};
     for (DevBuf *b : bufs) b->release();
     {
         std::lock_guard<std::mutex> lk(g_live_mu);
@@ -1114,11 +1114,37 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, const std::vect
     return PHI_OK;
 }
 
+// ---- the -d1 statistic (ILP_index.cpp:565-606), after the result proper is complete: every minimizer of the representative
+// chunks with its hash -> instantiated per walk in (walk, position) order -> stable sort on the hash (walks stay ascending
+// inside a hash) -> distinct walks per hash -> histogram.  Reuses the hit / expansion / sort buffers.
+static int stage_debug_hist(phi_gpu_index_ctx *ctx, int k, int w, const std::vector<uint64_t> &h_walk_len, const uint32_t *d_walk_vtx,
+                            const uint64_t *d_walk_off, uint64_t n_steps_eff, int walks_monotone, uint32_t n_walks_global)
+{
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    if (ctx->world > 1) return ctx->fail(PHI_ERR_UNSUPPORTED, "the -d1 shared k-mer statistic is not implemented for several GPUs");
+    CU(ctx->dbg_hist.reserve(((size_t)n_walks_global + 2) * 8));
+    CU(cudaMemsetAsync(ctx->dbg_hist.p, 0, ((size_t)n_walks_global + 2) * 8, ctx->st));
+    CU(cudaMemsetAsync(d_ctr + CTR_WALK_KMERS, 0, 8, ctx->st));
+    RunOut tmp;
+    int rc = stage_walks(ctx, k, w, WALK_MODE_ALL, 0, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, tmp);
+    if (rc) return rc;
+    CU(ctx->rank_drop.reserve(4)); CU(cudaMemsetAsync(ctx->rank_drop.p, 0, 4, ctx->st));   // every record has rank 0 here: keep it
+    uint64_t ns = 0;
+    rc = expand_survivors(ctx, w, true, ns);
+    if (rc || !ns) return rc;
+    CU(ctx->keys_b.reserve(ns * 8)); CU(ctx->vals_b.reserve(ns * 4)); CU(ctx->sort_scr.reserve(radix_sort_scratch(ns)));
+    CU(radix_sort_u64(ctx->x_hash.as<uint64_t>(), ctx->keys_b.as<uint64_t>(), ctx->x_walk.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), ns, 0, 64,
+                      ctx->sort_scr.p, ctx->st, &ctx->launches));
+    CU(filter_shared_kmer_hist(ctx->x_hash.as<uint64_t>(), ctx->x_walk.as<uint32_t>(), ns, n_walks_global, ctx->dbg_hist.as<unsigned long long>(),
+                               d_ctr + CTR_WALK_KMERS, ctx->st, &ctx->launches));
+    return PHI_OK;
+}
+
 // A result owns pinned buffers borrowed from its ctx's pool; freeing it hands them back (or releases them if the ctx is gone).
 struct ResultBox {
     phi_index_result pub;              // must stay the first member: the public pointer is &box->pub
     phi_gpu_index_ctx *owner;
-    PinnedBuf bufs[8]; int nbufs;
+    PinnedBuf bufs[12]; int nbufs;
 };
 static PinnedBuf pinned_acquire(phi_gpu_index_ctx *ctx, size_t bytes)
 {
@@ -1257,6 +1283,11 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     o.path_hits = ctx->h_ctr[CTR_PATH_HITS];                               // read back by the syncs of the filter stage
     ctx->unique_hits = o.n_hits;
     CU(cudaEventRecord(ctx->ev[EV_FILTER], ctx->st));
+    const bool want_hist = mode == WALK_MODE_PROBE && prm->debug != 0;
+    if (want_hist) {
+        rc = stage_debug_hist(ctx, k, w, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, HG);
+        if (rc) { phi_gpu_index_result_free(res); return rc; }
+    }
 
     res->count_sp_r = (int32_t)o.n_spec; res->n_walks = HG; res->n_filtered = o.n_filtered;
     res->n_anchors = o.n_surv; res->n_anchor_vtx = o.n_anchor_vtx;
@@ -1270,6 +1301,12 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
         if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_vtx.p, o.n_anchor_vtx, &res->anchor_vtx);
         if (!rc) rc = download<uint64_t>(ctx, res, ctx->apw.as<uint64_t>(), HG, &res->anchors_per_walk);
         if (rc) { phi_gpu_index_result_free(res); return rc; }
+    }
+    if (want_hist) {
+        int rc3 = download<uint64_t>(ctx, res, ctx->dbg_hist.p, (uint64_t)HG + 1, &res->shared_kmer_hist);
+        if (!rc3) rc3 = read_counters(ctx) == cudaSuccess ? PHI_OK : ctx->fail(PHI_ERR_CUDA, "counter read failed");
+        if (rc3) { phi_gpu_index_result_free(res); return rc3; }
+        res->n_walk_kmers = ctx->h_ctr[CTR_WALK_KMERS];
     }
     {   // per-walk minimizer counts are tiny and always returned
         int rc2 = download<uint64_t>(ctx, res, ctx->mpw.p, HG, &res->minimizers_per_walk);

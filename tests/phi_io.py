@@ -129,10 +129,10 @@ def oracle_hash(key: bytes) -> int:
     return oracle_lib().phi_oracle_hash128_to_64(key, len(key))
 
 
-def oracle_index(graph, reads, k=31, w=25, threshold=1.0, threads=0):
+def oracle_index(graph, reads, k=31, w=25, threshold=1.0, threads=0, debug=0):
     lib = oracle_lib()
     gv, rv = graph.view(), reads.view()
-    prm = _abi.IndexParams(k, w, threshold, 0)
+    prm = _abi.IndexParams(k, w, threshold, debug)
     out = C.POINTER(_abi.IndexResult)()
     rc = lib.phi_oracle_index_run(C.byref(gv), C.byref(rv), C.byref(prm), threads, C.byref(out))
     assert rc == 0, rc

@@ -29,13 +29,14 @@ def scraped(err):
     keep = []
     for line in err.splitlines():
         line = re.sub(r"^\[M::(\w+)::[\d.]+\*[\d.]+\]", r"[M::\1]", line)
-        if re.search(r"spectrum size|Filtered/Retained|Minimizers are in ILP| : \d+$|Number of", line):
+        if re.search(r"spectrum size|Filtered/Retained|Minimizers are in ILP| : \d+$|Number of|Haplotypes: \d+, fraction|Shared fraction", line):
             keep.append(line)
     head = [l for l in keep if "Number of Minimizers" not in l]
     return sorted(head)           # the reference prints the per-walk minimizer lines in thread order (ILP_index.cpp:563)
 
 
 @pytest.mark.parametrize("name,extra", [("toy_k3_w2", ["-k", "3", "-w", "2"]), ("synth_small", []), ("synth_dirty", ["-T", "0.5"]),
+                                        ("synth_small", ["-d", "1"]),
                                         ("synth_repeats", ["-T", "2.0"]), ("mhc4", [])])
 def test_patched_reference_dumps_the_identical_model(tmp_path, name, extra):
     if not (os.path.exists(REF) and os.path.exists(GPU)):

@@ -192,3 +192,18 @@ def test_walk_sharing_does_not_change_results(gpu, shift, share):
     assert np.array_equal(hashes, ref_hashes) and np.array_equal(res.anchor_vtx, ref.anchor_vtx)
     assert np.array_equal(res.anchor_off, ref.anchor_off) and np.array_equal(res.anchor_walk, ref.anchor_walk)
     assert res.minimizers_per_walk.tolist() == ref.minimizers_per_walk.tolist()
+
+
+@pytest.mark.parametrize("name", ["toy_k3_w2", "synth_small", "synth_dirty", "synth_repeats"])
+def test_debug_shared_kmer_statistic(gpu, name):
+    """params.debug (-d1): distinct walk-minimizer hashes by the number of walks they occur in (ILP_index.cpp:565-606)."""
+    c = Case(name)
+    got = gpu.run(c.graph, c.reads, c.k, c.w, c.T, debug=1)
+    want = phi_io.oracle_index(c.graph, c.reads, c.k, c.w, c.T, debug=1)
+    assert_same_result(want, got)
+    assert got.shared_kmer_hist is not None and got.n_walk_kmers == want.n_walk_kmers > 0
+    assert got.shared_kmer_hist.tolist() == want.shared_kmer_hist.tolist()
+    assert int(got.shared_kmer_hist.sum()) == got.n_walk_kmers and got.shared_kmer_hist[0] == 0
+    plain = gpu.run(c.graph, c.reads, c.k, c.w, c.T)
+    assert plain.shared_kmer_hist is None
+    assert_same_result(plain, got)

@@ -45,3 +45,26 @@ def test_readme_pins():
     assert m["model_q1_counts"] == {"V": 836026, "C": 455633, "Q": 20717}
     assert m["model_q0_counts"] == {"V": 836026, "C": 519940, "Q": 0}
     assert Case("mhc4_N75").meta["count_sp_r"] == 150160
+
+
+@pytest.mark.parametrize("name", ["toy_k3_w2", "synth_small", "synth_repeats"])
+def test_oracle_debug_statistic_matches_reference_d1(tmp_path, name):
+    """-d1: the 'fraction of unique shared kmers' lines (ILP_index.cpp:593-606) of the UNMODIFIED reference vs the oracle."""
+    import os
+    import subprocess
+    import numpy as np
+    from phi_b200 import synth
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "PHI_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/PHI_ref not built (needs /root/reference)")
+    c = Case(name)
+    gfa, fa = str(tmp_path / "g.gfa"), str(tmp_path / "r.fa")
+    synth.write_gfa(c.graph, gfa)
+    synth.write_fasta(c.reads, fa)
+    p = subprocess.run([ref, "-g", gfa, "-r", fa, "-o", str(tmp_path / "o.fa"), "-t", "4", "-d", "1", "-k", str(c.k), "-w", str(c.w)],
+                       env=dict(os.environ, PHI_STUB_DUMP=str(tmp_path / "dump.txt")), capture_output=True, text=True)
+    lines = [l for l in p.stderr.splitlines() if "Haplotypes:" in l]
+    want = phi_io.oracle_index(c.graph, c.reads, c.k, c.w, c.T, debug=1)
+    mine = ["[Haplotypes: %d, fraction of unique shared kmers: %.5f]"
+            % (i, float(np.float32(int(want.shared_kmer_hist[i])) / np.float32(want.n_walk_kmers))) for i in range(1, c.graph.n_walks + 1)]
+    assert lines == mine and len(lines) == c.graph.n_walks
