@@ -232,6 +232,28 @@ int phi_gpu_index_comm_unique_id(uint8_t id[PHI_COMM_ID_BYTES]);
 int phi_gpu_index_comm_init(phi_gpu_index_ctx *ctx, int rank, int world, const uint8_t id[PHI_COMM_ID_BYTES],
                             uint32_t walk_id_base, uint32_t n_walks_global);
 
+/*
+ * Host-side ingest (no GPU needed), written from scratch: what gfa_read + ILP_index::read_gfa
+ * (/root/reference/src/gfa-io.cpp:462-508, /root/reference/src/ILP_index.cpp:20-155) and kseq + read_ip_reads
+ * (/root/reference/src/kseq.h:192-232, /root/reference/src/ILP_index.cpp:313-328) produce, straight into the flat
+ * views above (.gz or plain).  Vertex ids, walk order, walk names and read order are the reference's; top_order_map is a
+ * Kahn order of the same graph (ties between equally valid orders may be broken differently, results cannot differ).
+ * Errors: PHI_ERR_ARG (cannot open), PHI_ERR_UNSUPPORTED (a walk with reverse-strand steps, as ILP_index.cpp:104-107);
+ * the message goes to err[errlen] when given.
+ */
+typedef struct phi_host_graph phi_host_graph;
+typedef struct phi_host_reads phi_host_reads;
+int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, char *err, size_t errlen);
+const phi_graph_view *phi_host_graph_view(const phi_host_graph *g);
+const char *phi_host_graph_walk_name(const phi_host_graph *g, uint32_t walk);       /* sample + "." + haplotype index */
+const char *phi_host_graph_segment_name(const phi_host_graph *g, uint32_t vtx);
+uint64_t phi_host_graph_n_links(const phi_host_graph *g);
+void phi_host_graph_free(phi_host_graph *g);
+int phi_host_reads_load(const char *path, phi_host_reads **out, char *err, size_t errlen);
+const phi_reads_view *phi_host_reads_view(const phi_host_reads *r);
+const char *phi_host_reads_name(const phi_host_reads *r, uint64_t i);
+void phi_host_reads_free(phi_host_reads *r);
+
 /* Host-only partition helpers (no GPU needed). */
 /* owner rank of a hash under the range partition on the high bits */
 int phi_shard_owner_of_hash(uint64_t hash, int world);

@@ -6,6 +6,6 @@ Python callers use; it never computes anything itself and has NO CPU fallback: i
 GPU is missing, calls raise.
 """
 from ._abi import Graph, Reads, IndexResultPy, PHI_OK  # noqa: F401
-from .api import PhiGpuIndex, PhiGpuError, load_library, library_path  # noqa: F401
+from .api import PhiGpuIndex, PhiGpuError, load_library, library_path, load_gfa, load_reads  # noqa: F401
 
-__all__ = ["Graph", "Reads", "IndexResultPy", "PhiGpuIndex", "PhiGpuError", "load_library", "library_path"]
+__all__ = ["Graph", "Reads", "IndexResultPy", "PhiGpuIndex", "PhiGpuError", "load_library", "library_path", "load_gfa", "load_reads"]

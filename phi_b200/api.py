@@ -65,12 +65,70 @@ def load_library():
     lib.phi_gpu_index_comm_unique_id.argtypes = [C.c_char_p]
     lib.phi_gpu_index_comm_init.restype = C.c_int
     lib.phi_gpu_index_comm_init.argtypes = [ctxp, C.c_int, C.c_int, C.c_char_p, C.c_uint32, C.c_uint32]
+    lib.phi_host_graph_load.restype = C.c_int
+    lib.phi_host_graph_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    lib.phi_host_graph_view.restype = C.POINTER(_abi.GraphView)
+    lib.phi_host_graph_view.argtypes = [C.c_void_p]
+    lib.phi_host_graph_walk_name.restype = C.c_char_p
+    lib.phi_host_graph_walk_name.argtypes = [C.c_void_p, C.c_uint32]
+    lib.phi_host_graph_segment_name.restype = C.c_char_p
+    lib.phi_host_graph_segment_name.argtypes = [C.c_void_p, C.c_uint32]
+    lib.phi_host_graph_n_links.restype = C.c_uint64
+    lib.phi_host_graph_n_links.argtypes = [C.c_void_p]
+    lib.phi_host_graph_free.argtypes = [C.c_void_p]
+    lib.phi_host_reads_load.restype = C.c_int
+    lib.phi_host_reads_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    lib.phi_host_reads_view.restype = C.POINTER(_abi.ReadsView)
+    lib.phi_host_reads_view.argtypes = [C.c_void_p]
+    lib.phi_host_reads_name.restype = C.c_char_p
+    lib.phi_host_reads_name.argtypes = [C.c_void_p, C.c_uint64]
+    lib.phi_host_reads_free.argtypes = [C.c_void_p]
     lib.phi_shard_owner_of_hash.restype = C.c_int
     lib.phi_shard_owner_of_hash.argtypes = [C.c_uint64, C.c_int]
     lib.phi_shard_split_by_weight.restype = C.c_int
     lib.phi_shard_split_by_weight.argtypes = [_abi.u64p, C.c_uint64, C.c_int, _abi.u64p]
     _LIB = lib
     return lib
+
+
+def load_gfa(path):
+    """phi_host_graph_load: GFA (.gz or plain) -> Graph (numpy copies of the flat view) with walk and segment names."""
+    lib = load_library()
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib.phi_host_graph_load(os.fsencode(path), C.byref(h), err, len(err))
+    if rc != _abi.PHI_OK:
+        raise PhiGpuError(rc, err.value.decode())
+    try:
+        v = lib.phi_host_graph_view(h).contents
+        nv, nw = v.n_vtx, v.n_walks
+        seg_off = _abi._np_from(v.seg_off, nv + 1, np.uint64)
+        walk_off = _abi._np_from(v.walk_off, nw + 1, np.uint64)
+        g = _abi.Graph(seg_off, _abi._np_from(v.seg_bases, int(seg_off[-1]), np.uint8), walk_off,
+                       _abi._np_from(v.walk_vtx, int(walk_off[-1]), np.uint32), _abi._np_from(v.top_order_map, nv, np.int32),
+                       [lib.phi_host_graph_walk_name(h, i).decode() for i in range(nw)])
+        g.segment_names = [lib.phi_host_graph_segment_name(h, i).decode() for i in range(nv)]
+        g.n_links = int(lib.phi_host_graph_n_links(h))
+        return g
+    finally:
+        lib.phi_host_graph_free(h)
+
+
+def load_reads(path):
+    """phi_host_reads_load: FASTA / FASTQ (.gz or plain) -> (Reads, names)."""
+    lib = load_library()
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib.phi_host_reads_load(os.fsencode(path), C.byref(h), err, len(err))
+    if rc != _abi.PHI_OK:
+        raise PhiGpuError(rc, err.value.decode())
+    try:
+        v = lib.phi_host_reads_view(h).contents
+        off = _abi._np_from(v.read_off, v.n_reads + 1, np.uint64)
+        rd = _abi.Reads(off, _abi._np_from(v.read_bases, int(off[-1]), np.uint8))
+        return rd, [lib.phi_host_reads_name(h, i).decode() for i in range(v.n_reads)]
+    finally:
+        lib.phi_host_reads_free(h)
 
 
 class PhiGpuIndex:

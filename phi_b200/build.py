@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libphi_gpu_index.so")
-SOURCES = ["read_sketch.cu", "walk_sketch.cu", "chunks.cu", "primitives.cu", "filter.cu", "phi_gpu_index.cu", "shard.cu"]
+SOURCES = ["read_sketch.cu", "walk_sketch.cu", "chunks.cu", "primitives.cu", "filter.cu", "phi_gpu_index.cu", "shard.cu", "host_io.cpp"]
 HEADERS = ["kernels.h", "device_common.cuh", "sketch_tile.cuh", "sketch_common.cuh", os.path.join(ROOT, "include", "phi_gpu_index.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xptxas", "-v"]
@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     procs = []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        obj = os.path.join(objdir, s.replace(".cu", ".o").replace(".cpp", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs + [os.path.abspath(__file__)]):
             cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
             raise RuntimeError(f"nvcc failed on {s}")
     if procs or force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "static"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "static", "-lz"]
         subprocess.check_call(cmd)
     if log:
         with open(os.path.join(objdir, "ptxas.log"), "w") as f:

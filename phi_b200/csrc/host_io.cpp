@@ -1,0 +1,270 @@
+// Host-side ingest: GFA -> flat graph view, FASTA/FASTQ -> flat reads view, written from scratch.
+// What the reference does with gfatools + read_gfa + kseq (serial text I/O into nested std::vector / std::string
+// containers, /root/reference/src/gfa-io.cpp:462-508, src/ILP_index.cpp:20-155, :313-328, src/kseq.h:192-232) is done here
+// straight into the buffers include/phi_gpu_index.h describes, so nothing has to be re-flattened before the upload.
+//
+// Semantics kept (SURVEY.md §9 rule 11):
+//   * only S, L and W records are looked at (gfa-io.cpp:493-495); lines shorter than 3 bytes or without a tab in column 2
+//     are skipped (:492); P-lines are ignored
+//   * vertex id = segment index by first appearance on an S- or L-line (gfa_add_seg, gfa-base.cpp:75-96)
+//   * segment sequence '*' = no sequence (length from LN:i: only; the reference keeps no bases either)
+//   * W-line: sample, haplotype index, contig, start, end, walk; steps naming an unknown segment are dropped
+//     (gfa-io.cpp:399-405); walk name = sample + "." + hap (ILP_index.cpp:98)
+//   * walk flip (gfa-io.cpp:64-115): the first orientation a segment is seen in (over all walks, in order) is its reference
+//     strand; a walk with more steps against than with the reference strands is reverse-complemented
+//   * a walk that still has a reverse-strand step is an error (ILP_index.cpp:104-107)
+//   * adjacency = the arcs leaving forward vertices after symmetrisation (every L-line also gives the reverse-complement
+//     arc, gfa-base.cpp:421-430), strands dropped (ILP_index.cpp:77-86); Kahn order with a FIFO queue seeded in vertex
+//     order (:116-147).  The order of a vertex's arcs (which only breaks ties between equally valid topological orders;
+//     the reference's comes out of gfatools' in-place radix sort) is L-line order here: top_order_map may differ from the
+//     reference's in such ties, the front end's results cannot (SURVEY.md §9 rule 8).
+//   * reads: kseq_read — header at the next '>' or '@', name up to the first white space, sequence lines concatenated
+//     with one trailing '\r' stripped, FASTQ quality skipped and length-checked; parsing stops at the first malformed
+//     record (kseq returns -2 and read_ip_reads' loop ends)
+#include "../../include/phi_gpu_index.h"
+
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <queue>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+bool slurp(const char *path, std::string &out, std::string &err)
+{
+    gzFile fp = gzopen(path, "rb");                       // reads plain files too
+    if (!fp) { err = std::string("cannot open ") + path; return false; }
+    gzbuffer(fp, 1 << 20);
+    std::vector<char> buf(1 << 22);
+    for (;;) {
+        int n = gzread(fp, buf.data(), (unsigned)buf.size());
+        if (n < 0) { err = std::string("read error in ") + path; gzclose(fp); return false; }
+        if (n == 0) break;
+        out.append(buf.data(), (size_t)n);
+    }
+    gzclose(fp);
+    return true;
+}
+
+}  // namespace
+
+struct phi_host_graph {
+    phi_graph_view view;
+    std::vector<uint64_t> seg_off, walk_off;
+    std::string seg_bases;
+    std::vector<uint32_t> walk_vtx;
+    std::vector<int32_t> top_order_map;
+    std::vector<std::string> walk_names, seg_names;
+    uint64_t n_links = 0;
+};
+
+struct phi_host_reads {
+    phi_reads_view view;
+    std::vector<uint64_t> read_off;
+    std::string read_bases;
+    std::vector<std::string> names;
+};
+
+static void set_err(char *err, size_t errlen, const std::string &m)
+{
+    if (err && errlen) { snprintf(err, errlen, "%s", m.c_str()); }
+}
+
+extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, char *err, size_t errlen)
+{
+    if (!gfa_path || !out) return PHI_ERR_ARG;
+    *out = nullptr;
+    std::string text, e;
+    if (!slurp(gfa_path, text, e)) { set_err(err, errlen, e); return PHI_ERR_ARG; }
+    phi_host_graph *G = new phi_host_graph();
+    std::unordered_map<std::string, uint32_t> name2id;
+    std::vector<std::string> seqs;                                  // per segment
+    std::vector<std::pair<uint32_t, uint32_t>> arcs;                // oriented vertices (seg << 1 | reverse)
+    struct Walk { std::string sample; int hap; std::vector<uint32_t> v; };
+    std::vector<Walk> walks;
+    auto add_seg = [&](const std::string &name) -> uint32_t {
+        auto it = name2id.find(name);
+        if (it != name2id.end()) return it->second;
+        uint32_t id = (uint32_t)seqs.size();
+        name2id.emplace(name, id); seqs.emplace_back(); G->seg_names.push_back(name);
+        return id;
+    };
+    std::vector<std::pair<const char *, const char *>> f;            // tab-separated fields of the current line
+    const char *p = text.data(), *tend = p + text.size();
+    while (p < tend) {
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(tend - p));
+        const char *lend = nl ? nl : tend;
+        const char *next_line = nl ? nl + 1 : tend;
+        if (lend - p > 1 && lend[-1] == '\r') --lend;                    // kstream strips one trailing CR
+        if (lend - p >= 3 && p[1] == '\t' && (p[0] == 'S' || p[0] == 'L' || p[0] == 'W')) {
+            f.clear();
+            for (const char *q = p + 2;;) {
+                const char *t = (const char *)memchr(q, '\t', (size_t)(lend - q));
+                f.emplace_back(q, t ? t : lend);
+                if (!t) break;
+                q = t + 1;
+            }
+            auto str = [&](size_t i) { return std::string(f[i].first, f[i].second); };
+            if (p[0] == 'S' && f.size() >= 2) {                          // name, sequence ('*': none)
+                uint32_t id = add_seg(str(0));
+                std::string seq = str(1);
+                seqs[id] = seq == "*" ? std::string() : seq;
+            } else if (p[0] == 'L' && f.size() >= 4) {                   // from, orientation, to, orientation [, overlap]
+                const std::string oa = str(1), ob = str(3);
+                if ((oa[0] == '+' || oa[0] == '-') && (ob[0] == '+' || ob[0] == '-')) {   // the reference tests the first byte only
+                    uint32_t v = add_seg(str(0)) << 1 | (oa[0] != '+' ? 1u : 0u);
+                    uint32_t w = add_seg(str(2)) << 1 | (ob[0] != '+' ? 1u : 0u);
+                    arcs.emplace_back(v, w);
+                    ++G->n_links;
+                }
+            } else if (p[0] == 'W' && f.size() >= 6) {                   // sample, haplotype, contig, start, end, walk
+                Walk wk;
+                wk.sample = str(0); wk.hap = atoi(str(1).c_str());
+                const char *c = f[5].first, *send = f[5].second;
+                while (c < send) {
+                    if (*c == '>' || *c == '<') {
+                        const char *d = c + 1;
+                        while (d < send && *d != '>' && *d != '<') ++d;
+                        auto it = name2id.find(std::string(c + 1, d));
+                        if (it != name2id.end()) wk.v.push_back(it->second << 1 | (*c == '<' ? 1u : 0u));
+                        c = d;
+                    } else ++c;
+                }
+                walks.push_back(std::move(wk));
+            }
+        }
+        p = next_line;
+    }
+    const uint32_t V = (uint32_t)seqs.size();
+    // ---- walk flip (gfa-io.cpp:64-115)
+    {
+        std::vector<int8_t> strand(V, 0);
+        for (auto &wk : walks) for (uint32_t v : wk.v) if (!strand[v >> 1]) strand[v >> 1] = (v & 1) ? -1 : 1;
+        for (auto &wk : walks) {
+            size_t with = 0, against = 0;
+            for (uint32_t v : wk.v) (((v & 1) ? -1 : 1) == strand[v >> 1] ? with : against)++;
+            if (with >= against) continue;
+            const size_t n = wk.v.size();
+            for (size_t j = 0; j < n / 2; ++j) { uint32_t t = wk.v[j] ^ 1; wk.v[j] = wk.v[n - 1 - j] ^ 1; wk.v[n - 1 - j] = t; }
+            if (n & 1) wk.v[n / 2] ^= 1;
+        }
+    }
+    // ---- flat views
+    G->seg_off.assign(1, 0);
+    for (uint32_t v = 0; v < V; ++v) { G->seg_bases += seqs[v]; G->seg_off.push_back(G->seg_bases.size()); }
+    G->walk_off.assign(1, 0);
+    for (size_t h = 0; h < walks.size(); ++h) {
+        for (uint32_t v : walks[h].v) {
+            if (v & 1) {                                                       // ILP_index.cpp:104-107
+                set_err(err, errlen, "Error: Walk " + std::to_string(h) + " has reverse strand vertices " + std::to_string(v));
+                delete G;
+                return PHI_ERR_UNSUPPORTED;
+            }
+            G->walk_vtx.push_back(v >> 1);
+        }
+        G->walk_off.push_back(G->walk_vtx.size());
+        G->walk_names.push_back(walks[h].sample + "." + std::to_string(walks[h].hap));
+    }
+    // ---- adjacency of the forward vertices after symmetrisation, Kahn order (ILP_index.cpp:77-154)
+    {
+        std::vector<std::vector<uint32_t>> adj(V);
+        auto add = [&](uint32_t a, uint32_t b) {
+            if (a & 1) return;                                                 // only arcs leaving a forward vertex count
+            auto &l = adj[a >> 1];
+            for (uint32_t x : l) if (x == b) return;                           // multi-arcs are removed by gfa_cleanup
+            l.push_back(b);
+        };
+        for (auto &ab : arcs) { add(ab.first, ab.second); add(ab.second ^ 1, ab.first ^ 1); }
+        std::vector<int32_t> indeg(V, 0);
+        for (uint32_t v = 0; v < V; ++v) for (uint32_t w : adj[v]) indeg[w >> 1]++;
+        std::queue<uint32_t> q;
+        for (uint32_t v = 0; v < V; ++v) if (!indeg[v]) q.push(v);
+        G->top_order_map.assign(V, 0);
+        int32_t next = 0;
+        while (!q.empty()) {
+            uint32_t u = q.front(); q.pop();
+            G->top_order_map[u] = next++;
+            for (uint32_t w : adj[u]) if (--indeg[w >> 1] == 0) q.push(w >> 1);
+        }
+    }
+    G->view.n_vtx = V; G->view.seg_off = G->seg_off.data(); G->view.seg_bases = (const uint8_t *)G->seg_bases.data();
+    G->view.n_walks = (uint32_t)walks.size(); G->view.walk_off = G->walk_off.data(); G->view.walk_vtx = G->walk_vtx.data();
+    G->view.top_order_map = G->top_order_map.data();
+    *out = G;
+    return PHI_OK;
+}
+
+extern "C" const phi_graph_view *phi_host_graph_view(const phi_host_graph *g) { return g ? &g->view : nullptr; }
+extern "C" const char *phi_host_graph_walk_name(const phi_host_graph *g, uint32_t h) { return g && h < g->walk_names.size() ? g->walk_names[h].c_str() : ""; }
+extern "C" const char *phi_host_graph_segment_name(const phi_host_graph *g, uint32_t v) { return g && v < g->seg_names.size() ? g->seg_names[v].c_str() : ""; }
+extern "C" uint64_t phi_host_graph_n_links(const phi_host_graph *g) { return g ? g->n_links : 0; }
+extern "C" void phi_host_graph_free(phi_host_graph *g) { delete g; }
+
+extern "C" int phi_host_reads_load(const char *path, phi_host_reads **out, char *err, size_t errlen)
+{
+    if (!path || !out) return PHI_ERR_ARG;
+    *out = nullptr;
+    std::string text, e;
+    if (!slurp(path, text, e)) { set_err(err, errlen, e); return PHI_ERR_ARG; }
+    phi_host_reads *R = new phi_host_reads();
+    R->read_off.assign(1, 0);
+    const char *p = text.data(), *end = p + text.size();
+    auto line_end = [&](const char *s) { const char *nl = (const char *)memchr(s, '\n', (size_t)(end - s)); return nl ? nl : end; };
+    int last_char = 0;
+    for (;;) {                                                                  // kseq_read (kseq.h:192-232)
+        if (!last_char) { while (p < end && *p != '>' && *p != '@') ++p; if (p >= end) break; last_char = *p++; }
+        if (p >= end) break;                                                    // header char at the very end: ks_getuntil returns -1
+        const char *q = p;
+        while (q < end && !isspace((unsigned char)*q)) ++q;                     // name
+        std::string name(p, q);
+        if (q < end && *q != '\n') q = line_end(q);                             // comment
+        p = q < end ? q + 1 : end;
+        std::string seq;
+        int c = -1;
+        while (p < end) {
+            c = (unsigned char)*p++;
+            if (c == '>' || c == '+' || c == '@') break;
+            if (c == '\n') { c = -1; continue; }
+            seq.push_back((char)c);
+            const char *le = line_end(p);
+            seq.append(p, le);
+            p = le < end ? le + 1 : end;
+            if (seq.size() > 1 && seq.back() == '\r') seq.pop_back();
+            c = -1;
+        }
+        last_char = (c == '>' || c == '@') ? c : 0;
+        if (c == '+') {                                                         // FASTQ: skip the '+' line, read >= |seq| quality bytes
+            const char *le = line_end(p);
+            if (le >= end) break;                                               // -2: no quality string
+            p = le + 1;
+            size_t ql = 0; bool got = false;
+            while (p < end || !got) {
+                if (p >= end) break;
+                const char *l2 = line_end(p);
+                size_t n = (size_t)(l2 - p);
+                ql += n;
+                if (ql > 1 && n && l2[-1] == '\r') --ql;
+                p = l2 < end ? l2 + 1 : end;
+                got = true;
+                if (ql >= seq.size()) break;
+            }
+            last_char = 0;
+            if (ql != seq.size()) break;                                        // -2: truncated quality: the reference stops here
+        }
+        R->names.push_back(name);
+        R->read_bases += seq;
+        R->read_off.push_back(R->read_bases.size());
+    }
+    R->view.n_reads = R->read_off.size() - 1; R->view.read_off = R->read_off.data(); R->view.read_bases = (const uint8_t *)R->read_bases.data();
+    *out = R;
+    return PHI_OK;
+}
+
+extern "C" const phi_reads_view *phi_host_reads_view(const phi_host_reads *r) { return r ? &r->view : nullptr; }
+extern "C" const char *phi_host_reads_name(const phi_host_reads *r, uint64_t i) { return r && i < r->names.size() ? r->names[i].c_str() : ""; }
+extern "C" void phi_host_reads_free(phi_host_reads *r) { delete r; }

@@ -207,3 +207,17 @@ def test_debug_shared_kmer_statistic(gpu, name):
     plain = gpu.run(c.graph, c.reads, c.k, c.w, c.T)
     assert plain.shared_kmer_hist is None
     assert_same_result(plain, got)
+
+
+@pytest.mark.parametrize("name", ["synth_small", "synth_dirty"])
+def test_from_files_through_the_host_ingest(gpu, tmp_path, name):
+    """GFA + FASTA on disk -> phi_host_graph_load / phi_host_reads_load -> GPU front end == oracle on the golden views."""
+    c = Case(name)
+    gfa, fa = str(tmp_path / "g.gfa"), str(tmp_path / "r.fa")
+    synth.write_gfa(c.graph, gfa)
+    synth.write_fasta(c.reads, fa)
+    g = phi_b200.load_gfa(gfa)
+    rd, _ = phi_b200.load_reads(fa)
+    got = gpu.run(g, rd, c.k, c.w, c.T)
+    want = phi_io.oracle_index(c.graph, c.reads, c.k, c.w, c.T)
+    assert_same_result(want, got)

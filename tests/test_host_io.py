@@ -1,0 +1,158 @@
+"""CPU: the from-scratch host ingest (phi_host_graph_load / phi_host_reads_load) against the
+UNMODIFIED reference's own parsers (gfa_read + ILP_index::read_gfa, kseq + read_ip_reads) run through
+oracle/_ref/ref_probe, on the reference's fixtures and on hand-written edge cases; and against the golden graphs."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import phi_io
+import phi_b200
+from phi_b200 import synth
+from golden_cases import Case, SMALL
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROBE = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
+REFTEST = "/root/reference/test"
+needs_probe = pytest.mark.skipif(not os.path.exists(PROBE), reason="oracle/_ref/ref_probe not built (needs /root/reference)")
+
+
+def probe(gfa, reads, out):
+    cmd = [PROBE, "-g", gfa, "-o", out, "--graph-only"] + (["-r", reads] if reads else [])
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-1000:]
+    return phi_io.read_phiarr(out)
+
+
+def assert_valid_topological_order(g):
+    """every walk step goes up in top_order_map, and the map is a permutation (acyclic inputs)"""
+    top = g.top_order_map.astype(np.int64)
+    assert sorted(top.tolist()) == list(range(g.n_vtx))
+    wo = g.walk_off.astype(np.int64)
+    for h in range(g.n_walks):
+        t = top[g.walk_vtx[wo[h]:wo[h + 1]].astype(np.int64)]
+        assert np.all(np.diff(t) > 0)
+
+
+def assert_same_graph(mine, ref, ref_names):
+    for f in ("seg_off", "seg_bases", "walk_off", "walk_vtx"):
+        assert np.array_equal(getattr(mine, f), getattr(ref, f)), f
+    assert mine.walk_names == ref_names
+
+
+@pytest.mark.parametrize("name", SMALL + ["mhc4"])
+def test_gfa_loader_reproduces_the_golden_graphs(tmp_path, name):
+    """the golden graph views were dumped by the reference's parser; write them as GFA text and read them back"""
+    c = Case(name)
+    gfa = str(tmp_path / "g.gfa")
+    synth.write_gfa(c.graph, gfa)
+    g = phi_b200.load_gfa(gfa)
+    assert_same_graph(g, c.graph, c.graph.walk_names or [f"hap{h}.{h}" for h in range(c.graph.n_walks)])
+    assert_valid_topological_order(g)
+    # same front-end result with either topological order (oracle: CPU)
+    if name != "mhc4":
+        a = phi_io.oracle_index(c.graph, c.reads, c.k, c.w, c.T)
+        b = phi_io.oracle_index(g, c.reads, c.k, c.w, c.T)
+        assert np.array_equal(a.anchor_vtx, b.anchor_vtx) and np.array_equal(a.anchor_off, b.anchor_off) and np.array_equal(a.anchor_walk, b.anchor_walk)
+
+
+@needs_probe
+@pytest.mark.skipif(not os.path.isdir(REFTEST), reason="reference fixtures not present")
+@pytest.mark.parametrize("gfa,reads", [("test.gfa", "read.fa"), ("MHC_4.gfa.gz", "CHM13_reads.fq.gz")])
+def test_loaders_match_the_reference_parsers_on_its_fixtures(tmp_path, gfa, reads):
+    d = probe(os.path.join(REFTEST, gfa), os.path.join(REFTEST, reads), str(tmp_path / "p.phiarr"))
+    ref = phi_io.graph_from_arrays(d)
+    g = phi_b200.load_gfa(os.path.join(REFTEST, gfa))
+    assert_same_graph(g, ref, ref.walk_names)
+    assert_valid_topological_order(g)
+    rd, names = phi_b200.load_reads(os.path.join(REFTEST, reads))
+    assert np.array_equal(rd.read_off, d["read_off"]) and np.array_equal(rd.read_bases, d["read_bases"])
+    assert len(names) == rd.n_reads and all(names)
+
+
+GFA_EDGE = "\n".join([
+    "H\tVN:Z:1.1",
+    "S\ta\tACGTACGTAC",
+    "L\ta\t+\tzz\t+\t0M",                         # zz first appears on an L-line: it gets id 1 before its S-line
+    "S\tb\tGGGTTT\tLN:i:6\txx:Z:tag",
+    "S\tzz\tCCCCC",
+    "P\tignored\ta+,b+\t*",
+    "S\tc\ttttgggaaac",                            # lower case is kept verbatim
+    "L\tzz\t+\tb\t+\t0M",
+    "L\tb\t+\tc\t+\t0M",
+    "L\ta\t+\tb\t+\t0M",
+    "L\ta\t+\tb\t+\t0M",                           # duplicate arc
+    "x",                                           # short line
+    "W\ts1\t0\tchr\t0\t0\t>a>zz>b>c",
+    "W\ts1\t1\tchr\t0\t0\t<c<b<a",                 # reversed walk: flipped to >a>b>c
+    "W\ts2\t7\tchr\t0\t0\t>a>nosuch>b",            # unknown segment dropped
+    "W\tshort\t0\tchr",                            # too few fields: ignored
+    "S\tlate\tAC",                                 # defined after the W-lines
+    ""]) + "\n"
+
+
+@needs_probe
+@pytest.mark.parametrize("crlf,gz", [(False, False), (True, False), (False, True)])
+def test_gfa_edge_cases_match_the_reference_parser(tmp_path, crlf, gz):
+    text = GFA_EDGE.replace("\n", "\r\n") if crlf else GFA_EDGE
+    path = str(tmp_path / ("g.gfa.gz" if gz else "g.gfa"))
+    with (gzip.open(path, "wb") if gz else open(path, "wb")) as f:
+        f.write(text.encode())
+    d = probe(path, None, str(tmp_path / "p.phiarr"))
+    ref = phi_io.graph_from_arrays(d)
+    g = phi_b200.load_gfa(path)
+    assert_same_graph(g, ref, ref.walk_names)
+    assert g.segment_names[:2] == ["a", "zz"] and g.walk_names == ["s1.0", "s1.1", "s2.7"]
+    wo = g.walk_off.astype(int)
+    assert g.walk_vtx[wo[1]:wo[2]].tolist() == [0, 2, 3]           # the reversed walk came out forward
+
+
+def test_gfa_reverse_strand_walk_is_an_error(tmp_path):
+    path = str(tmp_path / "g.gfa")
+    with open(path, "w") as f:
+        f.write("S\ta\tACGT\nS\tb\tGGGG\nW\ts\t0\tc\t0\t0\t>a>b\nW\ts\t1\tc\t0\t0\t>a<b\n")
+    with pytest.raises(phi_b200.PhiGpuError) as e:                  # ILP_index.cpp:104-107 exits there
+        phi_b200.load_gfa(path)
+    assert e.value.code == 2 and "reverse strand" in str(e.value)
+    with pytest.raises(phi_b200.PhiGpuError):
+        phi_b200.load_gfa(str(tmp_path / "missing.gfa"))
+
+
+READS_EDGE = {
+    "multi.fa": ">r1 comment here\nACGT\nacgtn\n\nGG\n>r2\n>r3\tx\nTTTT\n",
+    "crlf.fq": "@q1\r\nACGTAC\r\n+\r\nIIIIII\r\n@q2 c\r\nGGG\r\nTT\r\n+q2\r\nII\r\nIII\r\n",
+    "mixed.fq": "junk before\n@a\nACGT\n+\n@@@@\n>b\nCCCC\nGG\n@c\nTT\n+\n!!\n",
+    "trunc.fq": "@ok\nACGT\n+\nIIII\n@bad\nACGTACGT\n+\nIII\n@never\nAC\n+\nII\n",
+    "empty.fa": "",
+    "noseq.fa": ">only_header\n",
+}
+
+
+@needs_probe
+@pytest.mark.parametrize("fname", sorted(READS_EDGE))
+def test_read_loader_matches_kseq(tmp_path, fname):
+    gfa = str(tmp_path / "g.gfa")
+    with open(gfa, "w") as f:
+        f.write("S\ta\tACGT\n")
+    path = str(tmp_path / fname)
+    with open(path, "wb") as f:
+        f.write(READS_EDGE[fname].encode())
+    d = probe(gfa, path, str(tmp_path / "p.phiarr"))
+    rd, names = phi_b200.load_reads(path)
+    assert rd.read_off.tolist() == d["read_off"].tolist()
+    assert bytes(rd.read_bases) == bytes(d["read_bases"])
+
+
+def test_written_fasta_round_trip(tmp_path):
+    c = Case("synth_small")
+    fa = str(tmp_path / "r.fa.gz")
+    plain = str(tmp_path / "r.fa")
+    synth.write_fasta(c.reads, plain)
+    with gzip.open(fa, "wb") as f, open(plain, "rb") as src:
+        f.write(src.read())
+    for path in (plain, fa):
+        rd, names = phi_b200.load_reads(path)
+        assert np.array_equal(rd.read_off, c.reads.read_off) and np.array_equal(rd.read_bases, c.reads.read_bases)
+        assert names[:2] == ["r0", "r1"]
