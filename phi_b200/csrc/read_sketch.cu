@@ -43,14 +43,14 @@ __device__ __forceinline__ void read_tile_body(Tile &t, const ReadSketchArgs &A)
         uint64_t prev = (ent & 0x8000) ? 0xFFFFFFFFFFFFFFFFull : t.hash[tid];
         uint64_t carry = t.hash[cnt];
         bool emit = have && h != prev;
-        if (emit) table_insert(A.table, A.table_mult, A.table_limit, h, A.ctr);
-        emitted += __syncthreads_count(emit);
+        emitted += __syncthreads_count(emit);                         // everybody has read hash[]: the next batch may overwrite it
         if (tid == 0) t.hash[0] = carry;
+        if (emit) table_insert(A.table, A.table_mult, A.table_limit, h, A.ctr);   // after the barrier: nobody waits for the table round trip
     }
     if (tid == 0 && emitted) atomicAdd(&A.ctr[CTR_READ_EMITTED], (unsigned long long)emitted);
 }
 
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, 4)
 read_sketch_kernel(ReadSketchArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];

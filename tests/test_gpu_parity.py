@@ -221,3 +221,32 @@ def test_from_files_through_the_host_ingest(gpu, tmp_path, name):
     got = gpu.run(g, rd, c.k, c.w, c.T)
     want = phi_io.oracle_index(c.graph, c.reads, c.k, c.w, c.T)
     assert_same_result(want, got)
+
+
+# ---- the other BASELINE.json configs as parity cases (shapes of configs[2..4] at a size the oracle finishes in seconds)
+def test_baseline_config2_long_reads(gpu):
+    """configs[2]: the MHC-shaped graph with 15 kb HiFi-like reads (log-normal lengths, 1 % errors) at 10x."""
+    sg = synth.make_graph(0x50484931 + 2, 400_000, 12)
+    rd = synth.make_reads(0x50484931 + 2, sg, 10.0, read_len=15000, len_sigma=0.2, sub_err=0.01)
+    assert rd.n_reads > 100 and int(np.diff(rd.read_off.astype(np.int64)).max()) > 20000
+    assert_same_result(phi_io.oracle_index(sg.graph, rd), gpu.run(sg.graph, rd))
+
+
+def test_baseline_config3_vcf2gfa_shape_many_haplotypes(gpu):
+    """configs[3]: vcf2gfa-shaped graph (SNV / small indel bubbles only, -m 30 chopping), 200 haplotypes, 150 bp reads at 10x."""
+    sg = synth.make_graph(0x50484931 + 3, 150_000, 200, sv_frac=0.0, max_indel=20, founders=24, block_sites=150)
+    rd = synth.make_reads(0x50484931 + 3, sg, 10.0)
+    want = phi_io.oracle_index(sg.graph, rd, 31, 25, 1.0)
+    got = gpu.run(sg.graph, rd, 31, 25, 1.0)
+    assert_same_result(want, got)
+    st = gpu.sharing()
+    assert st["unique_windows"] < 0.5 * got.path_kmer_positions          # 200 walks from 24 founders per block: most chunks are shared
+    # a fractional threshold on many walks exercises the float compare (count >= T * num_walks, ILP_index.cpp:698)
+    assert_same_result(phi_io.oracle_index(sg.graph, rd, 31, 25, 0.335), gpu.run(sg.graph, rd, 31, 25, 0.335))
+
+
+def test_baseline_config4_shape_500_haplotypes(gpu):
+    """configs[4] shape: 500 haplotypes, 30x short reads (backbone scaled down so that the oracle finishes in seconds)."""
+    sg = synth.make_graph(0x50484931 + 4, 40_000, 500, founders=32, block_sites=100)
+    rd = synth.make_reads(0x50484931 + 4, sg, 30.0)
+    assert_same_result(phi_io.oracle_index(sg.graph, rd), gpu.run(sg.graph, rd))
