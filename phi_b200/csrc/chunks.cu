@@ -267,26 +267,34 @@ __global__ void chunk_emitted_kernel(ChunkTable C, const uint32_t *c_emitted, co
 
 // ---- survivors per representative chunk: hits of its tiles whose rank is not dropped (one warp per tile)
 __global__ void __launch_bounds__(256) tile_survivors_kernel(const TileRec *tiles, uint32_t n_tiles, const uint32_t *seg_off, const uint32_t *seg_cnt,
-                                                             const uint32_t *hit_rank, const uint8_t *rank_drop, uint32_t *c_surv)
+                                                             const uint32_t *hit_rank, const uint8_t *hit_nv, const uint8_t *rank_drop,
+                                                             uint32_t *c_surv, uint32_t *c_surv_vtx)
 {
     const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (tile >= n_tiles) return;
-    uint32_t n = 0;
+    uint32_t n = 0, nv = 0;
     for (int sg = 0; sg < SEG_PER_TILE; ++sg) {
         const uint32_t cnt = seg_cnt[(size_t)tile * SEG_PER_TILE + sg], off = seg_off[(size_t)tile * SEG_PER_TILE + sg];
-        for (uint32_t i = lane; i < cnt; i += 32) n += rank_drop[hit_rank[off + i]] ? 0u : 1u;
+        for (uint32_t i = lane; i < cnt; i += 32) if (!rank_drop[hit_rank[off + i]]) { ++n; nv += hit_nv[off + i]; }
     }
     #pragma unroll
-    for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, d);
-    if (lane == 0 && n) atomicAdd(&c_surv[tiles[tile].chunk], n);
+    for (int d = 16; d; d >>= 1) { n += __shfl_xor_sync(0xFFFFFFFFu, n, d); nv += __shfl_xor_sync(0xFFFFFFFFu, nv, d); }
+    if (lane == 0 && n) { atomicAdd(&c_surv[tiles[tile].chunk], n); atomicAdd(&c_surv_vtx[tiles[tile].chunk], nv); }
 }
-__global__ void member_counts_kernel(ChunkTable C, const uint32_t *c_surv, uint32_t *member_cnt)
+// records (and their vertices, summed into ctr[CTR_SURV_VTX]) every member chunk will instantiate
+__global__ void member_counts_kernel(ChunkTable C, const uint32_t *c_surv, const uint32_t *c_surv_vtx, uint32_t *member_cnt, unsigned long long *ctr)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C.n_chunks) return;
-    uint32_t rep = C.c_rep[c];
-    member_cnt[c] = rep == C_NONE ? 0u : c_surv[rep];
+    unsigned long long v = 0;
+    if (c < C.n_chunks) {
+        uint32_t rep = C.c_rep[c];
+        member_cnt[c] = rep == C_NONE ? 0u : c_surv[rep];
+        v = rep == C_NONE ? 0u : c_surv_vtx[rep];
+    }
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&ctr[CTR_SURV_VTX], v);
 }
 
 // ---- instantiate the surviving hits of every member chunk (one warp per member), in (walk, position) order:
@@ -424,16 +432,21 @@ cudaError_t chunk_emitted(const ChunkTable &C, const uint32_t *c_emitted, const 
 }
 
 cudaError_t chunk_survivors(const ChunkTable &C, const TileRec *tiles, uint32_t n_tiles, const uint32_t *seg_off, const uint32_t *seg_cnt,
-                            const uint32_t *hit_rank, const uint8_t *rank_drop, uint32_t *c_surv, uint32_t *member_cnt, cudaStream_t st, uint64_t *launches)
+                            const uint32_t *hit_rank, const uint8_t *hit_nv, const uint8_t *rank_drop, uint32_t *c_surv, uint32_t *c_surv_vtx,
+                            uint32_t *member_cnt, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
 {
     if (!C.n_chunks) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(c_surv, 0, (size_t)C.n_chunks * 4, st);
     if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(c_surv_vtx, 0, (size_t)C.n_chunks * 4, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ctr + CTR_SURV_VTX, 0, 8, st);
+    if (e != cudaSuccess) return e;
     if (n_tiles) {
-        tile_survivors_kernel<<<(unsigned)(((uint64_t)n_tiles * 32 + 255) / 256), 256, 0, st>>>(tiles, n_tiles, seg_off, seg_cnt, hit_rank, rank_drop, c_surv);
+        tile_survivors_kernel<<<(unsigned)(((uint64_t)n_tiles * 32 + 255) / 256), 256, 0, st>>>(tiles, n_tiles, seg_off, seg_cnt, hit_rank, hit_nv, rank_drop, c_surv, c_surv_vtx);
         PHI_LAUNCH_CHECK();
     }
-    member_counts_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>(C, c_surv, member_cnt);
+    member_counts_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>(C, c_surv, c_surv_vtx, member_cnt, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -85,27 +85,6 @@ __global__ void count_drops_kernel(const uint8_t *rank_drop, uint32_t n, unsigne
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(&ctr[CTR_FILTERED], (unsigned long long)__popc(b));
 }
 
-// every record survives; key = rank when the records already are in (walk, position) order, else (rank, global path coordinate)
-__global__ void emit_keys_kernel(FilterArgs A, FilterWork W, int mode /* 0: rank, 1: (rank, gpos), 2: gpos */)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= A.n_hits) return;
-    uint64_t key = A.hit_rank[i];
-    if (mode) {
-        uint64_t gpos = A.walk_gbase[A.hit_walk[i]] + A.hit_pos[i];
-        key = mode == 1 ? ((key << A.gpos_bits) | gpos) : gpos;
-    }
-    W.keys_a[i] = key;
-    W.vals_a[i] = (uint32_t)i;
-}
-
-// second-stage key when (rank, gpos) does not fit one u64: key = rank of vals[j]
-__global__ void rank_keys_kernel(FilterArgs A, const uint32_t *vals, uint64_t *keys, uint64_t n)
-{
-    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (j < n) keys[j] = A.hit_rank[vals[j]];
-}
-
 // ---- the -d1 statistic (/root/reference/src/ILP_index.cpp:565-606): (hash, walk) pairs sorted by hash, walks ascending inside
 // a hash.  The thread at the start of a hash run counts the distinct walks of the run and bumps hist[count] (block-local
 // histogram first: few distinct counts -> heavy contention otherwise).
@@ -163,24 +142,15 @@ __global__ void emit_rank_keys_kernel(FilterArgs A, uint32_t *keys, uint32_t *va
     if (i < A.n_hits) { keys[i] = A.hit_rank[i]; vals[i] = (uint32_t)i; }
 }
 
-cudaError_t filter_sort_records(const FilterArgs &A, const FilterWork &W, bool presorted, cudaStream_t st, uint64_t *launches)
+// The records arrive in (walk, position) order: a stable sort of (u32 rank, u32 record) pairs on the rank gives the final
+// (rank, walk, position) order.  Wide digits; the key arrays live in keys_a / keys_b.
+cudaError_t filter_sort_records(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches)
 {
     const uint64_t n = A.n_hits;
     if (!n) return cudaSuccess;
-    if (presorted) {                                                      // (u32 rank, u32 record) pairs, wide digits; keys live in keys_a / keys_b
-        emit_rank_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, (uint32_t *)W.keys_a, W.vals_a);
-        PHI_LAUNCH_CHECK();
-        return radix_sort_u32((uint32_t *)W.keys_a, (uint32_t *)W.keys_b, W.vals_a, W.vals_b, n, A.rank_bits, W.sort_scratch, st, launches);
-    }
-    const bool combined = A.gpos_bits + A.rank_bits <= 64;
-    emit_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, W, combined ? 1 : 2);
+    emit_rank_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, (uint32_t *)W.keys_a, W.vals_a);
     PHI_LAUNCH_CHECK();
-    if (combined) return radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n, 0, A.gpos_bits + A.rank_bits, W.sort_scratch, st, launches);
-    cudaError_t e = radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n, 0, A.gpos_bits, W.sort_scratch, st, launches);
-    if (e != cudaSuccess) return e;
-    rank_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, W.vals_a, W.keys_a, n);
-    PHI_LAUNCH_CHECK();
-    return radix_sort_u64(W.keys_a, W.keys_b, W.vals_a, W.vals_b, n, 0, A.rank_bits, W.sort_scratch, st, launches);
+    return radix_sort_u32((uint32_t *)W.keys_a, (uint32_t *)W.keys_b, W.vals_a, W.vals_b, n, A.rank_bits, W.sort_scratch, st, launches);
 }
 
 // ---- decimal-string order of "v0_v1_..._" keys ('_' sorts after every digit)
@@ -243,20 +213,24 @@ __global__ void fix_multi_kernel(FilterArgs A, uint32_t *order, uint64_t n, uint
 }
 
 // one block per big group: rank sort (stable: ties keep the incoming position order)
-__global__ void fix_big_kernel(FilterArgs A, uint32_t *order, uint32_t *tmp, const uint32_t *big_list)
+__global__ void fix_big_kernel(FilterArgs A, uint32_t *order, uint32_t *tmp, const uint32_t *big_list, uint32_t big_cap, const unsigned long long *ctr)
 {
-    const uint32_t j0 = big_list[2 * blockIdx.x], len = big_list[2 * blockIdx.x + 1];
-    for (uint32_t a = threadIdx.x; a < len; a += blockDim.x) {
-        uint32_t x = order[j0 + a], pos = 0;
-        for (uint32_t b = 0; b < len; ++b) {
-            if (b == a) continue;
-            int c = cmp_list(A, order[j0 + b], x);
-            pos += (c < 0) || (c == 0 && b < a);
+    const uint32_t n_big = (uint32_t)min((unsigned long long)big_cap, ctr[CTR_BIG_GROUPS]);
+    for (uint32_t g = blockIdx.x; g < n_big; g += gridDim.x) {
+        const uint32_t j0 = big_list[2 * g], len = big_list[2 * g + 1];
+        for (uint32_t a = threadIdx.x; a < len; a += blockDim.x) {
+            uint32_t x = order[j0 + a], pos = 0;
+            for (uint32_t b = 0; b < len; ++b) {
+                if (b == a) continue;
+                int c = cmp_list(A, order[j0 + b], x);
+                pos += (c < 0) || (c == 0 && b < a);
+            }
+            tmp[j0 + pos] = x;
         }
-        tmp[j0 + pos] = x;
+        __syncthreads();
+        for (uint32_t a = threadIdx.x; a < len; a += blockDim.x) order[j0 + a] = tmp[j0 + a];
+        __syncthreads();
     }
-    __syncthreads();
-    for (uint32_t a = threadIdx.x; a < len; a += blockDim.x) order[j0 + a] = tmp[j0 + a];
 }
 
 cudaError_t filter_fix_multi(const FilterArgs &A, uint32_t *order, uint64_t n_surv, uint32_t *big_list, uint32_t big_cap,
@@ -267,11 +241,10 @@ cudaError_t filter_fix_multi(const FilterArgs &A, uint32_t *order, uint64_t n_su
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
-cudaError_t filter_fix_big(const FilterArgs &A, uint32_t *order, uint32_t *tmp, const uint32_t *big_list, uint32_t n_big,
-                           uint64_t n_surv, cudaStream_t st, uint64_t *launches)
+cudaError_t filter_fix_big(const FilterArgs &A, uint32_t *order, uint32_t *tmp, const uint32_t *big_list, uint32_t big_cap,
+                           const unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
 {
-    if (!n_big) return cudaSuccess;
-    fix_big_kernel<<<n_big, 256, 0, st>>>(A, order, tmp, big_list);
+    fix_big_kernel<<<148, 256, 0, st>>>(A, order, tmp, big_list, big_cap, ctr);     // usually nothing to do: the blocks leave at once
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -31,7 +31,8 @@ enum {
     CTR_PATH_HITS = 19,
     CTR_CHUNK_FLAGS = 20,         // chunk-start flags set by the step pass (guards the chunk field of the packed scan)
     CTR_SEG_TOO_LONG = 21,        // a segment of 2^31 bases or more
-    CTR_WALK_KMERS = 22,          // distinct walk-minimizer hashes (-d1 statistic)           // hits of all walks (every member chunk counts what its representative found)     // a chunk differs from its fingerprint representative (128-bit collision): rerun without sharing
+    CTR_WALK_KMERS = 22,          // distinct walk-minimizer hashes (-d1 statistic)
+    CTR_SURV_VTX = 23,            // vertices of all instantiated surviving anchors           // hits of all walks (every member chunk counts what its representative found)     // a chunk differs from its fingerprint representative (128-bit collision): rerun without sharing
     CTR_COUNT = 24
 };
 
@@ -158,7 +159,8 @@ cudaError_t chunk_tiles(const ChunkTable &C, const uint64_t *walk_off, const uin
 cudaError_t chunk_emitted(const ChunkTable &C, const uint32_t *c_emitted, const uint32_t *c_hits, uint32_t walk_id_base,
                           unsigned long long *minimizers_per_walk, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 cudaError_t chunk_survivors(const ChunkTable &C, const TileRec *tiles, uint32_t n_tiles, const uint32_t *hseg_off, const uint32_t *hseg_cnt,
-                            const uint32_t *hit_rank, const uint8_t *rank_drop, uint32_t *c_surv, uint32_t *member_cnt, cudaStream_t st, uint64_t *launches);
+                            const uint32_t *hit_rank, const uint8_t *hit_nv, const uint8_t *rank_drop, uint32_t *c_surv, uint32_t *c_surv_vtx,
+                            uint32_t *member_cnt, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 cudaError_t chunk_expand(const ChunkTable &C, const ExpandArgs &X, cudaStream_t st, uint64_t *launches);
 
 
@@ -185,6 +187,8 @@ constexpr uint64_t TABLE_PAD = 4096;      // probe room behind the last home slo
 constexpr uint64_t TABLE_BLOCK = 2048;    // slots per block of the count / write kernels
 // sort every probe cluster in place -> the occupied slots are in ascending order; then count per block
 size_t table_blocks(uint64_t limit);
+cudaError_t table_insert_keys(const uint64_t *keys, uint64_t n, uint64_t *table, uint64_t base, uint64_t mult, uint64_t limit,
+                              unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 cudaError_t table_sort_and_count(uint64_t *table, uint64_t limit, uint32_t *block_cnt, cudaStream_t st, uint64_t *launches);
 // block_off = exclusive scan of block_cnt: write the occupied slots in slot order to out
 cudaError_t table_write_ordered(const uint64_t *table, uint64_t limit, const uint32_t *block_off, uint64_t *out, cudaStream_t st, uint64_t *launches);
@@ -199,8 +203,7 @@ struct FilterArgs {
     const uint32_t *hit_rank, *hit_walk, *hit_pos; const uint64_t *hit_voff; const uint8_t *hit_nv; const int32_t *vtx_pool;
     uint32_t n_ranks;
     float thr;                       // threshold * num_walks, evaluated in float as the reference does (:698)
-    const uint64_t *walk_gbase;      // [n_walks_global + 1] global base coordinate of each walk start (ordering key)
-    int gpos_bits, rank_bits;
+    int rank_bits;                   // bits of the largest rank (sort width)
 };
 struct FilterWork {                  // device scratch, sized by the host
     uint32_t *g_rep, *g_cnt; uint64_t g_cap;      // group table
@@ -217,13 +220,13 @@ cudaError_t filter_shared_kmer_hist(const uint64_t *hash, const uint32_t *walk, 
                                     unsigned long long *distinct, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_count_groups(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_mark_drops(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
-// sort keys of records that ALL survive.  presorted: the records already are in (walk, position) order and only a stable
-// sort on the rank is needed; otherwise the key is (rank, global path coordinate), in one or two sorts.
-cudaError_t filter_sort_records(const FilterArgs &A, const FilterWork &W, bool presorted, cudaStream_t st, uint64_t *launches);
+// stable sort of the records (which arrive in (walk, position) order) on their rank: order ends up in W.vals_a
+cudaError_t filter_sort_records(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_fix_multi(const FilterArgs &A, uint32_t *order, uint64_t n_surv, uint32_t *big_list, uint32_t big_cap,
                              unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
-cudaError_t filter_fix_big(const FilterArgs &A, uint32_t *order, uint32_t *tmp, const uint32_t *big_list, uint32_t n_big,
-                           uint64_t n_surv, cudaStream_t st, uint64_t *launches);
+// big (rank, walk) groups recorded by filter_fix_multi (count in ctr[CTR_BIG_GROUPS], read on the device: no host round trip)
+cudaError_t filter_fix_big(const FilterArgs &A, uint32_t *order, uint32_t *tmp, const uint32_t *big_list, uint32_t big_cap,
+                           const unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_csr_sizes(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, uint32_t *nv_out, uint8_t *anchor_len, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_csr_fill(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, const uint64_t *anchor_off, uint64_t *rank_off,
                             int32_t *anchor_walk, int32_t *anchor_vtx, unsigned long long *anchors_per_walk,

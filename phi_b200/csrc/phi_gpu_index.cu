@@ -70,10 +70,10 @@ struct phi_gpu_index_ctx {
     DevBuf mpw, hit_rank, hit_chunk, hit_pos, hit_voff, hit_nv, hit_hash, vtx_pool;
     // walk chunks (chunks.cu): boundaries, fingerprints, representatives, tiles, hit segments, expanded survivors
     DevBuf tlen, tprefix, coord, cflags, cpos, chunk_step, c_walk, c_L, c_R, c_lo, c_hi, c_h1, c_h2, c_slot, c_rep, c_ninst, c_ntile, c_tile_base, ctable, tiles;
-    DevBuf hseg_off, hseg_cnt, c_emitted, c_hits, c_surv, member_cnt, member_off, x_rank, x_walk, x_pos, x_voff, x_nv, x_hash;
+    DevBuf hseg_off, hseg_cnt, c_emitted, c_hits, c_surv, c_surv_vtx, member_cnt, member_off, x_rank, x_walk, x_pos, x_voff, x_nv, x_hash;
     uint32_t n_chunks = 0, n_tiles = 0; uint64_t unique_windows = 0, active_chunks = 0, rep_chunks = 0, unique_hits = 0; int dedupe = 1, chunk_shift = 11;
     DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
-    DevBuf anchor_off, rank_off, anchor_len, anchor_walk, anchor_vtx, apw, walk_gbase, dbg_hist;
+    DevBuf anchor_off, rank_off, anchor_len, anchor_walk, anchor_vtx, apw, dbg_hist;
     unsigned long long *h_ctr = nullptr;   // pinned mirror of the counter block
     // what the second stream uses instead of ctr / h_ctr / scan_scr / flags / flags64 / nv_out (swapped in by PrepScope)
     DevBuf ctr2, scan_scr2, flags2, flags64_2, nv_out2; unsigned long long *h_ctr2 = nullptr;
@@ -148,14 +148,14 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
                       &ctx->spec_a, &ctx->spec_b, &ctx->sort_scr, &ctx->dir, &ctx->mpw, &ctx->hit_rank, &ctx->hit_chunk, &ctx->hit_pos,
                       &ctx->tlen, &ctx->tprefix, &ctx->coord, &ctx->cflags, &ctx->cpos, &ctx->chunk_step, &ctx->c_walk, &ctx->c_L, &ctx->c_R, &ctx->c_lo,
                       &ctx->c_hi, &ctx->c_h1, &ctx->c_h2, &ctx->c_slot, &ctx->c_rep, &ctx->c_ninst, &ctx->c_ntile, &ctx->c_tile_base, &ctx->ctable,
-                      &ctx->tiles, &ctx->hseg_off, &ctx->hseg_cnt, &ctx->c_emitted, &ctx->c_hits, &ctx->c_surv, &ctx->member_cnt, &ctx->member_off,
+                      &ctx->tiles, &ctx->hseg_off, &ctx->hseg_cnt, &ctx->c_emitted, &ctx->c_hits, &ctx->c_surv, &ctx->c_surv_vtx, &ctx->member_cnt, &ctx->member_off,
                       &ctx->x_rank, &ctx->x_walk, &ctx->x_pos, &ctx->x_voff, &ctx->x_nv, &ctx->x_hash,
                       &ctx->xk_a, &ctx->xk_b, &ctx->xcnt, &ctx->xoff, &ctx->ag_send, &ctx->ag_recv, &ctx->m_rank, &ctx->m_cnt, &ctx->m_voff, &ctx->m_nv,
                       &ctx->r_rank, &ctx->r_walk, &ctx->r_pos, &ctx->r_voff, &ctx->r_nv, &ctx->r_vtx, &ctx->s_rank, &ctx->s_walk, &ctx->s_pos,
                       &ctx->s_voff, &ctx->s_nv, &ctx->s_vtx,
                       &ctx->hit_voff, &ctx->hit_nv, &ctx->hit_hash, &ctx->vtx_pool, &ctx->g_rep, &ctx->g_cnt, &ctx->rank_drop, &ctx->flags,
                       &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->big_list, &ctx->tmp_order, &ctx->nv_out,
-                      &ctx->dbg_hist, &ctx->anchor_off, &ctx->rank_off, &ctx->anchor_len, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw, &ctx->walk_gbase};
+                      &ctx->dbg_hist, &ctx->anchor_off, &ctx->rank_off, &ctx->anchor_len, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw};
     for (DevBuf *b : bufs) b->release();
     {
         std::lock_guard<std::mutex> lk(g_live_mu);
@@ -354,7 +354,7 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     (void)last;
     ctx->n_chunks = NC;
     DevBuf *u32s[] = {&ctx->chunk_step, &ctx->c_walk, &ctx->c_L, &ctx->c_R, &ctx->c_lo, &ctx->c_hi, &ctx->c_slot, &ctx->c_rep, &ctx->c_ninst,
-                      &ctx->c_ntile, &ctx->c_tile_base, &ctx->c_emitted, &ctx->c_hits, &ctx->c_surv};
+                      &ctx->c_ntile, &ctx->c_tile_base, &ctx->c_emitted, &ctx->c_hits, &ctx->c_surv, &ctx->c_surv_vtx};
     for (DevBuf *b : u32s) CU(b->reserve(((size_t)NC + 2) * 4));
     CU(ctx->c_h1.reserve(((size_t)NC + 1) * 8)); CU(ctx->c_h2.reserve(((size_t)NC + 1) * 8));
     CU(ctx->member_cnt.reserve(((size_t)NC + 2) * 4)); CU(ctx->member_off.reserve(((size_t)NC + 2) * 8));
@@ -501,16 +501,6 @@ __global__ void owner_split_kernel(const uint64_t *sorted, uint64_t n, const uin
     while (lo < hi) { uint64_t m = (lo + hi) >> 1; if (sorted[m] < key) lo = m + 1; else hi = m; }
     split[o] = lo;
 }
-__global__ void unique_flags_kernel(const uint64_t *sorted, uint64_t n, uint32_t *flags)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = (i == 0 || sorted[i] != sorted[i - 1]) ? 1u : 0u;
-}
-__global__ void unique_compact_kernel(const uint64_t *sorted, uint64_t n, const uint64_t *pos, uint64_t *out)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n && (i == 0 || sorted[i] != sorted[i - 1])) out[pos[i]] = sorted[i];
-}
 
 // Exchange of the locally distinct, locally sorted hashes (n_local of them in ctx->spec_a) -> ctx->spec_a = global sorted spectrum.
 static int exchange_spectrum(phi_gpu_index_ctx *ctx, uint64_t n_local, uint64_t &n_spec)
@@ -540,23 +530,32 @@ static int exchange_spectrum(phi_gpu_index_ctx *ctx, uint64_t n_local, uint64_t 
     rc = alltoallv(ctx, nc, ctx->spec_a.p, scnt, soff, ctx->xk_a.p, rcnt, roff, 8);
     if (rc) return rc;
     NC(nc->GroupEnd());
-    // owner: sort what arrived, drop duplicates
-    CU(ctx->sort_scr.reserve(radix_sort_scratch(std::max<uint64_t>(rtot, 1))));
-    CU(radix_sort_u64(ctx->xk_a.as<uint64_t>(), ctx->xk_b.as<uint64_t>(), nullptr, nullptr, rtot, 0, 64, ctx->sort_scr.p, ctx->st, &ctx->launches));
+    // owner: what arrived goes into an order-preserving table over this owner's hash range (duplicates collapse), the probe
+    // clusters are sorted in place and the occupied slots are written out in order: the owner's sorted distinct slice
     uint64_t n_own = 0;
     if (rtot) {
-        CU(ctx->flags.reserve(rtot * 4 + 4)); CU(ctx->flags64.reserve((rtot + 1) * 8));
-        CU(ctx->scan_scr.reserve(scan_u32_to_u64_scratch(rtot + 1)));
-        unique_flags_kernel<<<(unsigned)((rtot + 255) / 256), 256, 0, ctx->st>>>(ctx->xk_a.as<uint64_t>(), rtot, ctx->flags.as<uint32_t>());
-        CU(cudaGetLastError()); ctx->launches++;
-        CU(scan_u32_to_u64(ctx->flags.as<uint32_t>(), ctx->flags64.as<uint64_t>(), rtot, ctx->scan_scr.p, ctx->st, &ctx->launches));
-        unique_compact_kernel<<<(unsigned)((rtot + 255) / 256), 256, 0, ctx->st>>>(ctx->xk_a.as<uint64_t>(), rtot, ctx->flags64.as<uint64_t>(), ctx->xk_b.as<uint64_t>());
-        CU(cudaGetLastError()); ctx->launches++;
-        uint64_t last_pos = 0; uint32_t last_flag = 0;
-        CU(cudaMemcpyAsync(&last_pos, ctx->flags64.as<uint64_t>() + rtot - 1, 8, cudaMemcpyDeviceToHost, ctx->st));
-        CU(cudaMemcpyAsync(&last_flag, ctx->flags.as<uint32_t>() + rtot - 1, 4, cudaMemcpyDeviceToHost, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));
-        n_own = last_pos + last_flag;
+        unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+        const uint64_t base = bounds[me];
+        const unsigned __int128 range = (me + 1 < W ? (unsigned __int128)bounds[me + 1] : ((unsigned __int128)1 << 64)) - base;
+        uint64_t cap = 1024; while (cap < 2 * rtot) cap <<= 1;
+        for (;;) {
+            const uint64_t limit = cap + TABLE_PAD;
+            const uint64_t mult = (uint64_t)((((unsigned __int128)cap) << 64) / range);    // home = umulhi(key - base, mult) < cap
+            const size_t nb = table_blocks(limit);
+            CU(ctx->table.reserve((limit + 1) * 8)); CU(ctx->tblk.reserve((nb + 2) * 4));
+            CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(nb + 1), (size_t)1024)));
+            CU(fill_u64(ctx->table.as<uint64_t>(), limit + 1, TABLE_EMPTY, ctx->st, &ctx->launches));
+            CU(cudaMemsetAsync(d_ctr + CTR_OVERFLOW, 0, 2 * 8, ctx->st));                   // OVERFLOW, HAS_MAXKEY
+            CU(table_insert_keys(ctx->xk_a.as<uint64_t>(), rtot, ctx->table.as<uint64_t>(), base, mult, limit, d_ctr, ctx->st, &ctx->launches));
+            CU(table_sort_and_count(ctx->table.as<uint64_t>(), limit, ctx->tblk.as<uint32_t>(), ctx->st, &ctx->launches));
+            CU(cudaMemsetAsync(ctx->tblk.as<uint32_t>() + nb, 0, 4, ctx->st));
+            CU(scan_u32_inplace(ctx->tblk.as<uint32_t>(), nb + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
+            CU(cudaMemcpyAsync(ctx->h_tot, ctx->tblk.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, ctx->st));
+            CU(read_counters(ctx));
+            if (!ctx->h_ctr[CTR_OVERFLOW]) { n_own = *ctx->h_tot; CU(table_write_ordered(ctx->table.as<uint64_t>(), limit, ctx->tblk.as<uint32_t>(), ctx->xk_b.as<uint64_t>(), ctx->st, &ctx->launches)); break; }
+            cap <<= 1;
+        }
+        if (ctx->h_ctr[CTR_HAS_MAXKEY]) { CU(fill_u64(ctx->xk_b.as<uint64_t>() + n_own, 1, TABLE_EMPTY, ctx->st, &ctx->launches)); ++n_own; }
     }
     std::vector<uint64_t> mine(1, n_own), owns;
     rc = allgather_host_u64(ctx, nc, mine, owns);
@@ -883,16 +882,14 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
 
 // ---- stage: threshold filter, final order, CSR
 static FilterArgs filter_args(phi_gpu_index_ctx *ctx, uint64_t n, const DevBuf &rank, const DevBuf &walk, const DevBuf &pos, const DevBuf &voff,
-                              const DevBuf &nv, const DevBuf &vtx, uint32_t n_spec, float threshold, uint32_t n_walks_global,
-                              const std::vector<uint64_t> &h_walk_gbase)
+                              const DevBuf &nv, const DevBuf &vtx, uint32_t n_spec, float threshold, uint32_t n_walks_global)
 {
     FilterArgs A;
     A.n_hits = n; A.hit_rank = rank.as<uint32_t>(); A.hit_walk = walk.as<uint32_t>(); A.hit_pos = pos.as<uint32_t>();
     A.hit_voff = voff.as<uint64_t>(); A.hit_nv = nv.as<uint8_t>(); A.vtx_pool = vtx.as<int32_t>();
     A.n_ranks = n_spec;
     A.thr = threshold * (float)n_walks_global;                            // float * uint32 -> float, as ILP_index.cpp:698
-    A.walk_gbase = ctx->walk_gbase.as<uint64_t>();
-    A.gpos_bits = bits_for(h_walk_gbase.back()); A.rank_bits = bits_for(n_spec ? n_spec - 1 : 0);
+    A.rank_bits = bits_for(n_spec ? n_spec - 1 : 0);
     return A;
 }
 
@@ -932,12 +929,13 @@ static int expand_survivors(phi_gpu_index_ctx *ctx, int w, bool with_hash, uint6
     if (!NC) return PHI_OK;
     ChunkTable C = chunk_table(ctx);
     CU(chunk_survivors(C, ctx->tiles.as<TileRec>(), ctx->n_tiles, ctx->hseg_off.as<uint32_t>(), ctx->hseg_cnt.as<uint32_t>(), ctx->hit_rank.as<uint32_t>(),
-                       ctx->rank_drop.as<uint8_t>(), ctx->c_surv.as<uint32_t>(), ctx->member_cnt.as<uint32_t>(), ctx->st, &ctx->launches));
+                       ctx->hit_nv.as<uint8_t>(), ctx->rank_drop.as<uint8_t>(), ctx->c_surv.as<uint32_t>(), ctx->c_surv_vtx.as<uint32_t>(),
+                       ctx->member_cnt.as<uint32_t>(), ctx->ctr.as<unsigned long long>(), ctx->st, &ctx->launches));
     CU(cudaMemsetAsync(ctx->member_cnt.as<uint32_t>() + NC, 0, 4, ctx->st));
     CU(ctx->scan_scr.reserve(scan_u32_to_u64_scratch((uint64_t)NC + 2)));
     CU(scan_u32_to_u64(ctx->member_cnt.as<uint32_t>(), ctx->member_off.as<uint64_t>(), (uint64_t)NC + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
     CU(cudaMemcpyAsync(&ns, ctx->member_off.as<uint64_t>() + NC, 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(read_counters(ctx));                                               // also: CTR_SURV_VTX (vertices of the records), CTR_FILTERED
     if (ns >= (1ull << 32)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-1 anchors on one GPU; shard the walks over more GPUs");
     if (!ns) return PHI_OK;
     CU(ctx->x_rank.reserve(ns * 4)); CU(ctx->x_walk.reserve(ns * 4)); CU(ctx->x_pos.reserve(ns * 4)); CU(ctx->x_voff.reserve(ns * 8)); CU(ctx->x_nv.reserve(ns));
@@ -955,9 +953,7 @@ static int expand_survivors(phi_gpu_index_ctx *ctx, int w, bool with_hash, uint6
 }
 
 // records of A (all of them survive) -> final (rank, walk, j) order -> CSR in ctx->anchor_*
-enum { ORDER_BY_RANK = 1, ORDER_BY_RANK_AND_POS = 2 };   // records arrive in (walk, position) order / in any order
-
-static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, int order_mode, bool key_order, bool write_rank_off, uint32_t n_walks_global, RunOut &o)
+static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, bool key_order, bool write_rank_off, uint32_t n_walks_global, RunOut &o)
 {
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
     const uint64_t ns = A.n_hits;
@@ -972,26 +968,20 @@ static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, int order_
     CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(ns), scan_u32_to_u64_scratch(ns + 1))));
     W.keys_a = ctx->keys_a.as<uint64_t>(); W.keys_b = ctx->keys_b.as<uint64_t>();
     W.vals_a = ctx->vals_a.as<uint32_t>(); W.vals_b = ctx->vals_b.as<uint32_t>(); W.sort_scratch = ctx->sort_scr.p;
-    CU(filter_sort_records(A, W, order_mode == ORDER_BY_RANK, ctx->st, &ctx->launches));
+    CU(filter_sort_records(A, W, ctx->st, &ctx->launches));
     uint32_t *order = W.vals_a;
 
     if (key_order) {                                                      // (rank, walk) groups with several hits: std::map<std::string> order (:680-709)
         const uint32_t big_cap = (uint32_t)(ns / 48 + 1);
-        CU(ctx->big_list.reserve((size_t)big_cap * 8));
+        CU(ctx->big_list.reserve((size_t)big_cap * 8)); CU(ctx->tmp_order.reserve(ns * 4));
         CU(filter_fix_multi(A, order, ns, ctx->big_list.as<uint32_t>(), big_cap, d_ctr, ctx->st, &ctx->launches));
-        CU(read_counters(ctx));
-        if (ctx->h_ctr[CTR_BIG_GROUPS]) {
-            CU(ctx->tmp_order.reserve(ns * 4));
-            CU(filter_fix_big(A, order, ctx->tmp_order.as<uint32_t>(), ctx->big_list.as<uint32_t>(), (uint32_t)ctx->h_ctr[CTR_BIG_GROUPS], ns, ctx->st, &ctx->launches));
-        }
+        CU(filter_fix_big(A, order, ctx->tmp_order.as<uint32_t>(), ctx->big_list.as<uint32_t>(), big_cap, d_ctr, ctx->st, &ctx->launches));
     }
     CU(ctx->nv_out.reserve((ns + 1) * 4)); CU(ctx->anchor_len.reserve(ns + 4));
     CU(cudaMemsetAsync(ctx->nv_out.as<uint32_t>() + ns, 0, 4, ctx->st));
     CU(filter_csr_sizes(A, order, ns, ctx->nv_out.as<uint32_t>(), ctx->anchor_len.as<uint8_t>(), ctx->st, &ctx->launches));
     CU(scan_u32_to_u64(ctx->nv_out.as<uint32_t>(), ctx->anchor_off.as<uint64_t>(), ns + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
-    uint64_t total_vtx = 0;
-    CU(cudaMemcpyAsync(&total_vtx, ctx->anchor_off.as<uint64_t>() + ns, 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    const uint64_t total_vtx = ctx->h_ctr[CTR_SURV_VTX];                  // counted with the survivors (expand_survivors): no host round trip here
     o.n_anchor_vtx = total_vtx;
     CU(ctx->anchor_walk.reserve(ns * 4)); CU(ctx->anchor_vtx.reserve(total_vtx * 4 + 4));
     CU(filter_csr_fill(A, order, ns, ctx->anchor_off.as<uint64_t>(), write_rank_off ? ctx->rank_off.as<uint64_t>() : nullptr, ctx->anchor_walk.as<int32_t>(),
@@ -1016,7 +1006,7 @@ __global__ void summary_emit_kernel(FilterArgs A, const uint32_t *g_rep, const u
     m_rank[j] = A.hit_rank[i]; m_cnt[j] = g_cnt[slot]; m_voff[j] = A.hit_voff[i]; m_nv[j] = A.hit_nv[i];
 }
 
-static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, const std::vector<uint64_t> &h_walk_gbase, uint32_t n_walks_global, float threshold, RunOut &o)
+static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walks_global, float threshold, RunOut &o)
 {
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
     CU(ctx->apw.reserve(((size_t)n_walks_global + 1) * 8));
@@ -1028,24 +1018,22 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, const std::vect
     CU(cudaMemsetAsync(ctx->anchor_off.p, 0, 8, ctx->st));
     CU(ctx->rank_off.reserve(((size_t)o.n_spec + 2) * 8));
     CU(cudaMemsetAsync(ctx->rank_off.p, 0, ((size_t)o.n_spec + 1) * 8, ctx->st));   // no anchors: every rank is empty
-    CU(ctx->walk_gbase.reserve(h_walk_gbase.size() * 8));
-    CU(cudaMemcpyAsync(ctx->walk_gbase.p, h_walk_gbase.data(), h_walk_gbase.size() * 8, cudaMemcpyHostToDevice, ctx->st));
     o.n_surv = 0; o.n_anchor_vtx = 0; o.n_filtered = 0;
     FilterWork W; memset(&W, 0, sizeof(W));
     W.rank_drop = ctx->rank_drop.as<uint8_t>(); W.ctr = d_ctr;
     const uint64_t n = o.n_hits;                                          // hits of the representative chunks
     // the representatives' hits: hit_chunk takes the place of the walk id (its member count is the record's weight)
     FilterArgs A = filter_args(ctx, n, ctx->hit_rank, ctx->hit_chunk, ctx->hit_pos, ctx->hit_voff, ctx->hit_nv, ctx->vtx_pool, o.n_spec, threshold,
-                               n_walks_global, h_walk_gbase);
+                               n_walks_global);
 
     if (mode == WALK_MODE_ALL) {
         // sketch-only: every emitted minimizer of every walk, in (walk, position) order, no filter
         uint64_t ns = 0;
         int rc = expand_survivors(ctx, w, true, ns);
         if (rc) return rc;
-        FilterArgs X = filter_args(ctx, ns, ctx->x_rank, ctx->x_walk, ctx->x_pos, ctx->x_voff, ctx->x_nv, ctx->vtx_pool, 1, 0.f, n_walks_global, h_walk_gbase);
+        FilterArgs X = filter_args(ctx, ns, ctx->x_rank, ctx->x_walk, ctx->x_pos, ctx->x_voff, ctx->x_nv, ctx->vtx_pool, 1, 0.f, n_walks_global);
         X.rank_bits = 0;                                                  // already in final order
-        return order_and_csr(ctx, X, ORDER_BY_RANK, false, false, n_walks_global, o);
+        return order_and_csr(ctx, X, false, false, n_walks_global, o);
     }
 
     // ---- which ranks are dropped.  One GPU: local group counts are the global ones.  Several GPUs: one (rank, count, list)
@@ -1084,7 +1072,7 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, const std::vect
         int rc = exchange_records(ctx, I, rs, rsv);
         if (rc) return rc;
         if (rs) {                                                             // owner: add the partial counts up, apply the threshold
-            FilterArgs B = filter_args(ctx, rs, ctx->r_rank, ctx->r_walk, ctx->r_pos, ctx->r_voff, ctx->r_nv, ctx->r_vtx, o.n_spec, threshold, n_walks_global, h_walk_gbase);
+            FilterArgs B = filter_args(ctx, rs, ctx->r_rank, ctx->r_walk, ctx->r_pos, ctx->r_voff, ctx->r_nv, ctx->r_vtx, o.n_spec, threshold, n_walks_global);
             FilterWork WB; memset(&WB, 0, sizeof(WB));
             WB.rank_drop = ctx->rank_drop.as<uint8_t>(); WB.ctr = d_ctr;
             rc = count_groups_adaptive(ctx, B, WB, ctx->r_walk.as<uint32_t>(), nullptr);
@@ -1106,12 +1094,9 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, const std::vect
     uint64_t ns = 0;
     int rc2 = expand_survivors(ctx, w, false, ns);
     if (rc2) return rc2;
-    FilterArgs XA = filter_args(ctx, ns, ctx->x_rank, ctx->x_walk, ctx->x_pos, ctx->x_voff, ctx->x_nv, ctx->vtx_pool, o.n_spec, threshold, n_walks_global, h_walk_gbase);
-    rc2 = order_and_csr(ctx, XA, ORDER_BY_RANK, true, true, n_walks_global, o);
-    if (rc2) return rc2;
-    CU(read_counters(ctx));
-    o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED];                       // several GPUs: the dropped ranks this GPU owns
-    return PHI_OK;
+    FilterArgs XA = filter_args(ctx, ns, ctx->x_rank, ctx->x_walk, ctx->x_pos, ctx->x_voff, ctx->x_nv, ctx->vtx_pool, o.n_spec, threshold, n_walks_global);
+    o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED];                       // read with the survivor count; several GPUs: the dropped ranks this GPU owns
+    return order_and_csr(ctx, XA, true, true, n_walks_global, o);
 }
 
 // ---- the -d1 statistic (ILP_index.cpp:565-606), after the result proper is complete: every minimizer of the representative
@@ -1272,13 +1257,10 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
 
     const uint32_t H = ctx->n_walks;
     const uint32_t HG = ctx->world > 1 ? ctx->n_walks_global : H;
-    std::vector<uint64_t> h_walk_gbase(HG + 1, 0);
-    if (ctx->world == 1) for (uint32_t h = 0; h < H; ++h) h_walk_gbase[h + 1] = h_walk_gbase[h] + h_walk_len[h];
-    else for (uint32_t h = 0; h < HG; ++h) h_walk_gbase[h + 1] = h_walk_gbase[h] + (1ull << 31);   // any monotone walk-major coordinate orders correctly
 
     phi_index_result *res = alloc_result(ctx);
     if (!res) return ctx->fail(PHI_ERR_NOMEM, "host allocation failed");
-    rc = stage_filter(ctx, w, mode, h_walk_gbase, HG, prm->threshold, o);
+    rc = stage_filter(ctx, w, mode, HG, prm->threshold, o);
     if (rc) { phi_gpu_index_result_free(res); return rc; }
     o.path_hits = ctx->h_ctr[CTR_PATH_HITS];                               // read back by the syncs of the filter stage
     ctx->unique_hits = o.n_hits;

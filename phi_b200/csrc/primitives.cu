@@ -421,6 +421,34 @@ __global__ void __launch_bounds__(256) table_write_kernel(const uint64_t *table,
     for (int i = 0; i < I; ++i) if (v[i] != TABLE_EMPTY) out[o++] = v[i];
 }
 
+// insert a key array (owner side of the multi-GPU spectrum exchange): home slot = umulhi(key - base, mult), upwards probing
+__global__ void table_insert_keys_kernel(const uint64_t *keys, uint64_t n, uint64_t *table, uint64_t base, uint64_t mult, uint64_t limit,
+                                         unsigned long long *ctr)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i];
+    if (key == TABLE_EMPTY) { ctr[CTR_HAS_MAXKEY] = 1; return; }
+    for (uint64_t slot = __umul64hi(key - base, mult); slot < limit; ++slot) {
+        uint64_t cur = table[slot];
+        if (cur == key) return;
+        if (cur == TABLE_EMPTY) {
+            uint64_t old = atomicCAS((unsigned long long *)&table[slot], (unsigned long long)TABLE_EMPTY, (unsigned long long)key);
+            if (old == TABLE_EMPTY || old == key) return;
+        }
+    }
+    ctr[CTR_OVERFLOW] = 1;
+}
+
+cudaError_t table_insert_keys(const uint64_t *keys, uint64_t n, uint64_t *table, uint64_t base, uint64_t mult, uint64_t limit,
+                              unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
+{
+    if (!n) return cudaSuccess;
+    table_insert_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n, table, base, mult, limit, ctr);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
 size_t table_blocks(uint64_t limit) { return (size_t)((limit + TABLE_BLOCK - 1) / TABLE_BLOCK); }
 
 cudaError_t table_sort_and_count(uint64_t *table, uint64_t limit, uint32_t *block_cnt, cudaStream_t st, uint64_t *launches)
