@@ -95,6 +95,7 @@ struct ReadSketchArgs {
     const uint64_t *read_off;         // [n_reads + 1]
     uint64_t n_reads, total_bases;
     const uint64_t *tile_first_read;  // [n_tiles]
+    uint64_t tile0;                   // first tile of this launch (the reads may be sketched piece by piece while they arrive)
     int k, w;
     uint64_t *table; uint64_t table_mult, table_limit;   // home slot = umulhi(key, table_mult); slots [0, table_limit), table[table_limit] stays EMPTY
     unsigned long long *ctr;

@@ -52,6 +52,12 @@ struct phi_gpu_index_ctx {
     cudaStream_t st2 = nullptr;            // second stream: graph upload + graph preparation / chunking, concurrent with the read stage
     cudaEvent_t ev[EV_COUNT] = {};
     cudaEvent_t ev_sync = nullptr;         // cross-stream ordering (no timing)
+    // host -> device copies of phi_gpu_index_run: one copy stream, graph first (the second stream starts preparing it), then the
+    // reads in pieces (the main stream sketches piece p while piece p+1 is on the wire)
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_graph_in = nullptr, ev_piece[8] = {};
+    int n_pieces = 0;                      // > 0: an upload is in flight and the read stage has to wait piece by piece
+    uint64_t piece_end[8] = {};            // read bases [0, piece_end[p]) are on the device once ev_piece[p] has fired
     std::string err = "no error";
     uint64_t launches = 0;
     phi_stage_times times = {};
@@ -125,6 +131,9 @@ extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
     if ((e = cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming);
+    if ((e = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    cudaEventCreateWithFlags(&ctx->ev_graph_in, cudaEventDisableTiming);
+    for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&ctx->ev_piece[i], cudaEventDisableTiming);
     if ((e = cudaHostAlloc((void **)&ctx->h_ctr, CTR_COUNT * 8, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     if ((e = cudaHostAlloc((void **)&ctx->h_tot, 64, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     if ((e = cudaHostAlloc((void **)&ctx->h_ctr2, CTR_COUNT * 8, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
@@ -168,6 +177,9 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
     if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
+    if (ctx->ev_graph_in) cudaEventDestroy(ctx->ev_graph_in);
+    for (int i = 0; i < 8; ++i) if (ctx->ev_piece[i]) cudaEventDestroy(ctx->ev_piece[i]);
+    if (ctx->st_copy) { cudaStreamSynchronize(ctx->st_copy); cudaStreamDestroy(ctx->st_copy); }
     if (ctx->st) cudaStreamDestroy(ctx->st);
     if (ctx->st2) cudaStreamDestroy(ctx->st2);
     delete ctx;
@@ -206,19 +218,28 @@ static int upload_async(phi_gpu_index_ctx *ctx, const phi_graph_view *g, const p
     CU(ctx->walk_vtx.reserve(ctx->n_steps * 4 + 4));
     CU(ctx->read_off.reserve((ctx->n_reads + 1) * 8));
     CU(ctx->read_bases.reserve(ctx->read_total + 64));
-    // sequence buffers carry 16 readable bytes in front and zero padding behind: the sketch kernels use unaligned 8-byte loads
-    cudaStream_t sa = ctx->st, sb = ctx->st2;
-    CU(cudaMemcpyAsync(ctx->read_off.p, ctx->n_reads ? r->read_off : zero_off, (ctx->n_reads + 1) * 8, cudaMemcpyHostToDevice, sa));
-    CU(cudaMemsetAsync(ctx->read_bases.p, 0, 16, sa));
-    if (ctx->read_total) CU(cudaMemcpyAsync((char *)ctx->read_bases.p + 16, r->read_bases, ctx->read_total, cudaMemcpyHostToDevice, sa));
-    CU(cudaMemsetAsync((char *)ctx->read_bases.p + 16 + ctx->read_total, 0, 32, sa));
-    CU(cudaMemcpyAsync(ctx->seg_off.p, g->n_vtx ? g->seg_off : zero_off, ((size_t)g->n_vtx + 1) * 8, cudaMemcpyHostToDevice, sb));
-    CU(cudaMemsetAsync(ctx->seg_bases.p, 0, 16, sb));
-    CU(cudaMemsetAsync((char *)ctx->seg_bases.p + 16 + ctx->seg_total, 0, 32, sb));
-    if (ctx->seg_total) CU(cudaMemcpyAsync((char *)ctx->seg_bases.p + 16, g->seg_bases, ctx->seg_total, cudaMemcpyHostToDevice, sb));
-    if (g->n_vtx) CU(cudaMemcpyAsync(ctx->top_order.p, g->top_order_map, (size_t)g->n_vtx * 4, cudaMemcpyHostToDevice, sb));
-    CU(cudaMemcpyAsync(ctx->walk_off.p, g->n_walks ? g->walk_off : zero_off, ((size_t)g->n_walks + 1) * 8, cudaMemcpyHostToDevice, sb));
-    if (ctx->n_steps) CU(cudaMemcpyAsync(ctx->walk_vtx.p, g->walk_vtx, ctx->n_steps * 4, cudaMemcpyHostToDevice, sb));
+    // sequence buffers carry 16 readable bytes in front and zero padding behind: the sketch kernels use unaligned 8-byte loads.
+    // One copy stream, in the order the pipeline wants the data: graph first, then the reads in pieces.
+    cudaStream_t sc = ctx->st_copy;
+    CU(cudaMemcpyAsync(ctx->seg_off.p, g->n_vtx ? g->seg_off : zero_off, ((size_t)g->n_vtx + 1) * 8, cudaMemcpyHostToDevice, sc));
+    if (g->n_vtx) CU(cudaMemcpyAsync(ctx->top_order.p, g->top_order_map, (size_t)g->n_vtx * 4, cudaMemcpyHostToDevice, sc));
+    CU(cudaMemcpyAsync(ctx->walk_off.p, g->n_walks ? g->walk_off : zero_off, ((size_t)g->n_walks + 1) * 8, cudaMemcpyHostToDevice, sc));
+    if (ctx->n_steps) CU(cudaMemcpyAsync(ctx->walk_vtx.p, g->walk_vtx, ctx->n_steps * 4, cudaMemcpyHostToDevice, sc));
+    CU(cudaMemsetAsync(ctx->seg_bases.p, 0, 16, sc));
+    CU(cudaMemsetAsync((char *)ctx->seg_bases.p + 16 + ctx->seg_total, 0, 32, sc));
+    if (ctx->seg_total) CU(cudaMemcpyAsync((char *)ctx->seg_bases.p + 16, g->seg_bases, ctx->seg_total, cudaMemcpyHostToDevice, sc));
+    CU(cudaEventRecord(ctx->ev_graph_in, sc));
+    CU(cudaMemcpyAsync(ctx->read_off.p, ctx->n_reads ? r->read_off : zero_off, (ctx->n_reads + 1) * 8, cudaMemcpyHostToDevice, sc));
+    CU(cudaMemsetAsync(ctx->read_bases.p, 0, 16, sc));
+    CU(cudaMemsetAsync((char *)ctx->read_bases.p + 16 + ctx->read_total, 0, 32, sc));
+    const int P = ctx->read_total >= (8u << 20) ? 8 : 1;
+    ctx->n_pieces = P;
+    for (int p = 0; p < P; ++p) {
+        const uint64_t lo = ctx->read_total * p / P, hi = ctx->read_total * (p + 1) / P;
+        if (hi > lo) CU(cudaMemcpyAsync((char *)ctx->read_bases.p + 16 + lo, r->read_bases + lo, hi - lo, cudaMemcpyHostToDevice, sc));
+        ctx->piece_end[p] = hi;
+        CU(cudaEventRecord(ctx->ev_piece[p], sc));
+    }
     ctx->have_inputs = true;
     return PHI_OK;
 }
@@ -228,8 +249,8 @@ extern "C" int phi_gpu_index_upload(phi_gpu_index_ctx *ctx, const phi_graph_view
     if (!ctx) return PHI_ERR_ARG;
     int rc = upload_async(ctx, g, r);
     if (rc) { ctx->have_inputs = false; return rc; }
-    CU(cudaStreamSynchronize(ctx->st));
-    CU(cudaStreamSynchronize(ctx->st2));
+    CU(cudaStreamSynchronize(ctx->st_copy));
+    ctx->n_pieces = 0;                                                      // resident: nothing to wait for
     return PHI_OK;
 }
 
@@ -315,6 +336,7 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     h_walk_len.assign(H, 0);
     ctx->n_chunks = ctx->n_tiles = 0; ctx->unique_windows = ctx->active_chunks = ctx->rep_chunks = 0;
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    if (ctx->n_pieces) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_graph_in, 0));   // phi_gpu_index_run: the graph is still on the wire
     CU(cudaEventRecord(ctx->ev[EV_PREP0], ctx->st));
     CU(cudaMemsetAsync(ctx->ctr.p, 0, CTR_COUNT * 8, ctx->st));
     memset(ctx->h_ctr, 0, CTR_COUNT * 8);
@@ -723,7 +745,7 @@ static int exchange_records(phi_gpu_index_ctx *ctx, const RouteIn &I, uint64_t &
 
 // ---- stage: reads -> ranked spectrum (sorted distinct hashes + radix directory).  Two halves so that the graph
 // preparation can be issued on the second stream while the read kernel runs.
-namespace { struct ReadsState { uint64_t n_tiles = 0, cap = 0; }; }
+namespace { struct ReadsState { uint64_t n_tiles = 0, cap = 0; bool relaunch = false; }; }
 
 static int reads_sketch_launch(phi_gpu_index_ctx *ctx, int k, int w, const ReadsState &rs)
 {
@@ -738,7 +760,23 @@ static int reads_sketch_launch(phi_gpu_index_ctx *ctx, int k, int w, const Reads
     A.n_reads = ctx->n_reads; A.total_bases = ctx->read_total; A.tile_first_read = ctx->tile_first_read.as<uint64_t>();
     A.k = k; A.w = w; A.table = ctx->table.as<uint64_t>(); A.table_mult = rs.cap; A.table_limit = limit; A.ctr = d_ctr;
     CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st));
-    CU(launch_read_sketch(A, rs.n_tiles, ctx->st)); ctx->launches++;
+    if (ctx->n_pieces > 1 && !rs.relaunch) {
+        // the reads are still arriving: sketch the tiles whose bases are complete after every piece
+        uint64_t t0 = 0;
+        for (int p = 0; p < ctx->n_pieces; ++p) {
+            CU(cudaStreamWaitEvent(ctx->st, ctx->ev_piece[p], 0));
+            uint64_t t1 = rs.n_tiles;
+            if (p + 1 < ctx->n_pieces) {                                   // last tile with  tile*cap - w - pad + NB <= piece_end
+                const long long lim = (long long)ctx->piece_end[p] + A.layout.pad + w - A.layout.NB;
+                t1 = lim < 0 ? 0 : std::min<uint64_t>(rs.n_tiles, (uint64_t)lim / (uint64_t)A.layout.cap + 1);
+            }
+            if (t1 > t0) { A.tile0 = t0; CU(launch_read_sketch(A, t1 - t0, ctx->st)); ctx->launches++; t0 = t1; }
+        }
+    } else {
+        if (ctx->n_pieces) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_piece[ctx->n_pieces - 1], 0));
+        A.tile0 = 0;
+        CU(launch_read_sketch(A, rs.n_tiles, ctx->st)); ctx->launches++;
+    }
     CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
     // probe clusters sorted in place -> the table is in ascending order; per-block counts -> offsets -> total
     const size_t nb = table_blocks(limit);
@@ -760,6 +798,7 @@ static int stage_reads_begin(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &r
     CU(cudaEventRecord(ctx->ev[EV_RD0], ctx->st));
     CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st));
     CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
+    if (ctx->n_pieces) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_piece[0], 0));   // read offsets (and the first piece) have arrived
     if (!rs.n_tiles) return PHI_OK;
     count_positions_kernel<<<(unsigned)((R + 255) / 256), 256, 0, ctx->st>>>(ctx->read_off.as<uint64_t>(), R, k, w, d_ctr + CTR_READ_POS);
     CU(cudaGetLastError()); ctx->launches++;
@@ -781,7 +820,7 @@ static int stage_reads_finish(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &
         for (;;) {
             CU(read_counters(ctx));
             if (!ctx->h_ctr[CTR_OVERFLOW]) break;                          // probing ran off the padding (table far too small): double it
-            rs.cap <<= 1;
+            rs.cap <<= 1; rs.relaunch = true;
             int rc = reads_sketch_launch(ctx, k, w, rs);
             if (rc) return rc;
         }
@@ -1180,13 +1219,14 @@ static int validate_params(phi_gpu_index_ctx *ctx, const phi_index_params *p)
 }
 
 template <class T>
-static int download(phi_gpu_index_ctx *ctx, phi_index_result *res, const void *dev, uint64_t n, const T **out)
+static int download(phi_gpu_index_ctx *ctx, phi_index_result *res, const void *dev, uint64_t n, const T **out, cudaStream_t stream = nullptr)
 {
+    if (!stream) stream = ctx->st;
     ResultBox *b = (ResultBox *)res;
     PinnedBuf pb = pinned_acquire(ctx, std::max<uint64_t>(n, 1) * sizeof(T));
     if (!pb.p) return ctx->fail(PHI_ERR_NOMEM, "pinned host allocation failed");
     b->bufs[b->nbufs++] = pb;
-    if (n) CU(cudaMemcpyAsync(pb.p, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->st));
+    if (n) CU(cudaMemcpyAsync(pb.p, dev, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
     *out = (const T *)pb.p;
     return PHI_OK;
 }
@@ -1249,6 +1289,18 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
         rc = stage_reads_finish(ctx, k, w, rs, o, dbits);
         if (rc) return rc;
     }
+    // the result starts to travel as soon as its parts exist: the spectrum goes out on the copy stream under the walk stage
+    struct ResGuard { phi_index_result *r; ~ResGuard() { if (r) phi_gpu_index_result_free(r); } } guard = {alloc_result(ctx)};
+    phi_index_result *res = guard.r;
+    if (!res) return ctx->fail(PHI_ERR_NOMEM, "host allocation failed");
+    const bool spec_early = do_download && mode == WALK_MODE_PROBE;
+    if (spec_early) {
+        CU(cudaEventRecord(ctx->ev_sync, ctx->st));
+        CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_sync, 0));
+        rc = download<uint64_t>(ctx, res, ctx->spec_a.p, o.n_spec, &res->spectrum, ctx->st_copy);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev_graph_in, ctx->st_copy));               // (the graph-arrived event is free again: reuse it as "spectrum out")
+    }
     CU(cudaEventRecord(ctx->ev[EV_SPECTRUM], ctx->st));
     CU(cudaStreamWaitEvent(ctx->st, ctx->ev[EV_PREP], 0));               // the walk stage needs both
     rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, o);
@@ -1258,17 +1310,15 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     const uint32_t H = ctx->n_walks;
     const uint32_t HG = ctx->world > 1 ? ctx->n_walks_global : H;
 
-    phi_index_result *res = alloc_result(ctx);
-    if (!res) return ctx->fail(PHI_ERR_NOMEM, "host allocation failed");
     rc = stage_filter(ctx, w, mode, HG, prm->threshold, o);
-    if (rc) { phi_gpu_index_result_free(res); return rc; }
+    if (rc) return rc;
     o.path_hits = ctx->h_ctr[CTR_PATH_HITS];                               // read back by the syncs of the filter stage
     ctx->unique_hits = o.n_hits;
     CU(cudaEventRecord(ctx->ev[EV_FILTER], ctx->st));
     const bool want_hist = mode == WALK_MODE_PROBE && prm->debug != 0;
     if (want_hist) {
         rc = stage_debug_hist(ctx, k, w, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, HG);
-        if (rc) { phi_gpu_index_result_free(res); return rc; }
+        if (rc) return rc;
     }
 
     res->count_sp_r = (int32_t)o.n_spec; res->n_walks = HG; res->n_filtered = o.n_filtered;
@@ -1276,23 +1326,23 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     res->read_kmer_positions = o.read_pos; res->path_kmer_positions = o.path_pos;
     res->read_minimizers_emitted = o.read_emitted; res->path_hits = o.path_hits;
     if (do_download) {
-        rc = download<uint64_t>(ctx, res, ctx->spec_a.p, mode == WALK_MODE_PROBE ? o.n_spec : 0, &res->spectrum);
+        rc = spec_early ? PHI_OK : download<uint64_t>(ctx, res, ctx->spec_a.p, 0, &res->spectrum);
         if (!rc && mode == WALK_MODE_PROBE) rc = download<uint64_t>(ctx, res, ctx->rank_off.p, (uint64_t)o.n_spec + 1, &res->rank_off);
         if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_walk.p, o.n_surv, &res->anchor_walk);
         if (!rc) rc = download<uint8_t>(ctx, res, ctx->anchor_len.p, o.n_surv, &res->anchor_len);
         if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_vtx.p, o.n_anchor_vtx, &res->anchor_vtx);
         if (!rc) rc = download<uint64_t>(ctx, res, ctx->apw.as<uint64_t>(), HG, &res->anchors_per_walk);
-        if (rc) { phi_gpu_index_result_free(res); return rc; }
+        if (rc) return rc;
     }
     if (want_hist) {
         int rc3 = download<uint64_t>(ctx, res, ctx->dbg_hist.p, (uint64_t)HG + 1, &res->shared_kmer_hist);
         if (!rc3) rc3 = read_counters(ctx) == cudaSuccess ? PHI_OK : ctx->fail(PHI_ERR_CUDA, "counter read failed");
-        if (rc3) { phi_gpu_index_result_free(res); return rc3; }
+        if (rc3) return rc3;
         res->n_walk_kmers = ctx->h_ctr[CTR_WALK_KMERS];
     }
     {   // per-walk minimizer counts are tiny and always returned
         int rc2 = download<uint64_t>(ctx, res, ctx->mpw.p, HG, &res->minimizers_per_walk);
-        if (rc2) { phi_gpu_index_result_free(res); return rc2; }
+        if (rc2) return rc2;
     }
     uint64_t *hashes = nullptr; uint32_t *h_order = nullptr;
     if (mode == WALK_MODE_ALL && hashes_out && o.n_surv) {
@@ -1300,6 +1350,7 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
         CU(cudaMemcpyAsync(hashes, ctx->x_hash.p, o.n_surv * 8, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaMemcpyAsync(h_order, ctx->vals_a.p, o.n_surv * 4, cudaMemcpyDeviceToHost, ctx->st));
     }
+    if (spec_early) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_graph_in, 0));   // the spectrum copy on the copy stream
     CU(cudaEventRecord(ctx->ev[EV_END], ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     for (uint32_t h = 0; h < HG; ++h) res->path_minimizers_emitted += res->minimizers_per_walk[h];
@@ -1310,6 +1361,7 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
         *hashes_out = sorted;
     }
     collect_times(ctx);
+    guard.r = nullptr;                                                      // success: the caller owns the result now
     *out = res;
     return PHI_OK;
 }
@@ -1330,11 +1382,12 @@ extern "C" int phi_gpu_index_run(phi_gpu_index_ctx *ctx, const phi_graph_view *g
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventRecord(ctx->ev[EV_START], ctx->st));
-    rc = upload_async(ctx, graph, reads);                                   // reads -> main stream, graph -> second stream; nothing waits here
-    if (rc) { cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st2); ctx->have_inputs = false; return rc; }
-    CU(cudaEventRecord(ctx->ev[EV_H2D], ctx->st2));                         // the graph is the last thing to arrive
+    rc = upload_async(ctx, graph, reads);                                   // copy stream: graph, then the reads in pieces; nothing waits here
+    if (rc) { cudaStreamSynchronize(ctx->st_copy); ctx->have_inputs = false; ctx->n_pieces = 0; return rc; }
+    CU(cudaEventRecord(ctx->ev[EV_H2D], ctx->st_copy));                     // the last read piece is the last thing to arrive
     rc = run_pipeline(ctx, params, WALK_MODE_PROBE, 1, out, nullptr, true);
-    if (rc) { cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st2); }   // the caller's buffers may go away after we return
+    ctx->n_pieces = 0;
+    if (rc) { cudaStreamSynchronize(ctx->st_copy); cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st2); }   // the caller's buffers may go away after we return
     return rc;
 }
 

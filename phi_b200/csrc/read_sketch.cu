@@ -56,7 +56,7 @@ read_sketch_kernel(ReadSketchArgs A)
     extern __shared__ __align__(16) unsigned char smem[];
     const TileLayout &L = A.layout;
     Tile t = carve(smem, L, A.k, A.w);
-    const long long tile = blockIdx.x;
+    const long long tile = (long long)A.tile0 + blockIdx.x;
     t.g0 = tile * L.cap - A.w - L.pad;
     t.seq_len = (long long)A.total_bases;
     set_window_bounds(t);
@@ -138,7 +138,7 @@ cudaError_t launch_read_tile_dir(const uint64_t *read_off, uint64_t n_reads, int
     return cudaGetLastError();
 }
 
-cudaError_t launch_read_sketch(const ReadSketchArgs &A, uint64_t n_tiles, cudaStream_t st)
+cudaError_t launch_read_sketch(const ReadSketchArgs &A, uint64_t n_tiles, cudaStream_t st)   // tiles [A.tile0, A.tile0 + n_tiles)
 {
     if (!n_tiles) return cudaSuccess;
     size_t smem = (size_t)A.layout.bytes;
