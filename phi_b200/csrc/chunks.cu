@@ -40,13 +40,17 @@ __global__ void topo_len_kernel(const int32_t *top_order_map, const uint64_t *se
     if (t < 0 || (uint32_t)t >= n_vtx) { ctr[CTR_BAD_TOPO] = 1; return; }
     tlen[t] = (uint32_t)(seg_off[v + 1] - seg_off[v]);
 }
-// coord[v] = prefix[top_order_map[v]]; with an unusable top_order_map the segment-store offset serves (any function of v is correct)
+// what the step pass needs of a vertex, in one 16-byte record: (bases, coordinate bucket, top_order_map, -).
+// coordinate = prefix[top_order_map[v]]; with an unusable top_order_map the segment-store offset serves (any function of v is correct)
 __global__ void topo_coord_kernel(const int32_t *top_order_map, const uint64_t *seg_off, const uint64_t *prefix, uint32_t n_vtx,
-                                  const unsigned long long *ctr, uint64_t *coord)
+                                  int shift, unsigned long long *ctr, uint4 *vinfo)
 {
     uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_vtx) return;
-    coord[v] = ctr[CTR_BAD_TOPO] ? seg_off[v] : prefix[top_order_map[v]];
+    const uint64_t len = seg_off[v + 1] - seg_off[v];
+    if (len >= (1ull << 31)) ctr[CTR_SEG_TOO_LONG] = 1;
+    const uint64_t coord = ctr[CTR_BAD_TOPO] ? seg_off[v] : prefix[top_order_map[v]];
+    vinfo[v] = make_uint4((uint32_t)len, (uint32_t)(coord >> shift), (uint32_t)top_order_map[v], 0u);
 }
 
 __device__ __forceinline__ uint32_t walk_of_step(const uint64_t *walk_off, uint32_t n_walks, uint64_t s)
@@ -59,28 +63,29 @@ __device__ __forceinline__ uint32_t walk_of_step(const uint64_t *walk_off, uint3
 // ---- one pass over the walk steps: segment length, chunk boundary (the step's vertex lies in another coordinate bucket than the
 // previous step's, or the step is the first of its walk), zero-length steps, topological monotonicity of the walks
 __global__ void __launch_bounds__(256) step_pass_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
-                                                        const uint64_t *seg_off, const int32_t *top_order_map, const uint64_t *coord, int shift,
-                                                        PackedStep *packed, unsigned long long *ctr)
+                                                        const uint4 *vinfo, PackedStep *packed, unsigned long long *ctr)
 {
     const uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     bool zero = false, flag = false;
+    uint4 me = make_uint4(0, 0, 0, 0);
+    if (s < n_steps) me = vinfo[walk_vtx[s]];                        // one 16-byte gather per step
+    // the previous step's vertex record: the neighbouring lane has it (lane 0 fetches its own)
+    uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, me.y, 1), pt = __shfl_up_sync(0xFFFFFFFFu, me.z, 1);
+    if (lane == 0 && s && s < n_steps) { const uint4 p = vinfo[walk_vtx[s - 1]]; pb = p.y; pt = p.z; }
     if (s < n_steps) {
-        const uint32_t v = walk_vtx[s];
-        const uint64_t len = seg_off[v + 1] - seg_off[v];
-        if (len >= (1ull << 31)) ctr[CTR_SEG_TOO_LONG] = 1;
         const uint32_t h = walk_of_step(walk_off, n_walks, s);
         flag = s == walk_off[h];
         if (!flag) {
-            const uint32_t u = walk_vtx[s - 1];
-            flag = (coord[v] >> shift) != (coord[u] >> shift);
-            if (top_order_map[u] >= top_order_map[v]) ctr[CTR_NONMONO] = 1;
+            flag = me.y != pb;
+            if ((int32_t)pt >= (int32_t)me.z) ctr[CTR_NONMONO] = 1;
         }
-        zero = len == 0;
-        PackedStep p; p.v = (uint32_t)(len & 0x7FFFFFFFu) | (flag ? 0x80000000u : 0u);
+        zero = me.x == 0;
+        PackedStep p; p.v = (me.x & 0x7FFFFFFFu) | (flag ? 0x80000000u : 0u);
         packed[s] = p;
     }
     const uint32_t bz = __ballot_sync(0xFFFFFFFFu, zero), bf = __ballot_sync(0xFFFFFFFFu, flag);
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (bz) atomicAdd(&ctr[CTR_ZERO_STEPS], (unsigned long long)__popc(bz));
         if (bf) atomicAdd(&ctr[CTR_CHUNK_FLAGS], (unsigned long long)__popc(bf));
     }
@@ -333,8 +338,8 @@ __global__ void __launch_bounds__(256) expand_kernel(ChunkTable C, ExpandArgs X)
 }
 
 // ------------------------------------------------------------------ launchers
-cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, uint32_t *tlen, uint64_t *prefix, uint64_t *coord,
-                             void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
+cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, int shift, uint32_t *tlen, uint64_t *prefix,
+                             uint4 *vinfo, void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
 {
     if (!n_vtx) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(tlen, 0, (size_t)n_vtx * 4, st);
@@ -343,17 +348,16 @@ cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_o
     PHI_LAUNCH_CHECK();
     e = scan_u32_to_u64(tlen, prefix, n_vtx, scan_scratch, st, launches);
     if (e != cudaSuccess) return e;
-    topo_coord_kernel<<<(n_vtx + 255) / 256, 256, 0, st>>>(top_order_map, seg_off, prefix, n_vtx, ctr, coord);
+    topo_coord_kernel<<<(n_vtx + 255) / 256, 256, 0, st>>>(top_order_map, seg_off, prefix, n_vtx, shift, ctr, vinfo);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
 
-cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint64_t *seg_off,
-                           const int32_t *top_order_map, const uint64_t *coord, int shift, PackedStep *packed, unsigned long long *ctr,
-                           cudaStream_t st, uint64_t *launches)
+cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo,
+                           PackedStep *packed, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
 {
     if (!n_steps) return cudaSuccess;
-    step_pass_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, seg_off, top_order_map, coord, shift, packed, ctr);
+    step_pass_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, packed, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -139,12 +139,12 @@ struct PackedStep {
 
 // chunks.cu — walk preparation (step lengths and bases, walk lengths), walk chunking, grouping of identical chunks,
 // instantiation of the representatives' hits
-cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, uint32_t *tlen, uint64_t *prefix, uint64_t *coord,
-                             void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
+// per-vertex record of the step pass: (bases, coordinate >> shift, top_order_map, -)
+cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, int shift, uint32_t *tlen, uint64_t *prefix,
+                             uint4 *vinfo, void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 // per step: segment length, chunk-start flag, zero-length count, topological monotonicity -> packed[]
-cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint64_t *seg_off,
-                           const int32_t *top_order_map, const uint64_t *coord, int shift, PackedStep *packed, unsigned long long *ctr,
-                           cudaStream_t st, uint64_t *launches);
+cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo,
+                           PackedStep *packed, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 // scanned = exclusive scan of packed (as u64) -> step_base, walk_len, chunk_step / c_walk of C
 cudaError_t walk_step_finalize(const ChunkTable &C, const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off, uint32_t n_walks,
                                uint64_t n_steps, uint32_t *step_base, uint64_t *walk_len, cudaStream_t st, uint64_t *launches);

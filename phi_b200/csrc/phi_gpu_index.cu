@@ -343,17 +343,16 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     if (!H || !S) return PHI_OK;
     if (S >= 0xFFFFFFFFull) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-2 walk steps on one GPU; shard the walks over more GPUs");
     // topological base coordinate of every vertex (chunk boundaries are defined on it)
-    CU(ctx->tlen.reserve((size_t)V * 4 + 4)); CU(ctx->tprefix.reserve(((size_t)V + 1) * 8)); CU(ctx->coord.reserve((size_t)V * 8 + 8));
+    CU(ctx->tlen.reserve((size_t)V * 4 + 4)); CU(ctx->tprefix.reserve(((size_t)V + 1) * 8)); CU(ctx->coord.reserve((size_t)V * 16 + 16));
     CU(ctx->scan_scr.reserve(std::max({scan_u32_to_u64_scratch((uint64_t)V + 1), scan_u32_to_u64_scratch(S + 1), (size_t)1024})));
-    CU(chunk_topo_coord(ctx->top_order.as<int32_t>(), ctx->seg_off.as<uint64_t>(), V, ctx->tlen.as<uint32_t>(), ctx->tprefix.as<uint64_t>(),
-                        ctx->coord.as<uint64_t>(), ctx->scan_scr.p, d_ctr, ctx->st, &ctx->launches));
+    CU(chunk_topo_coord(ctx->top_order.as<int32_t>(), ctx->seg_off.as<uint64_t>(), V, ctx->chunk_shift, ctx->tlen.as<uint32_t>(),
+                        ctx->tprefix.as<uint64_t>(), ctx->coord.as<uint4>(), ctx->scan_scr.p, d_ctr, ctx->st, &ctx->launches));
     CU(ctx->step_len.reserve(S * 4 + 4));                               // packed steps
     CU(ctx->gbase.reserve((S + 1) * 8));                                // their scan
     uint64_t last = 0; uint32_t NC = 0;
     for (int attempt = 0;; ++attempt) {
         CU(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, ctx->st)); CU(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, ctx->st));
-        CU(walk_step_pass(d_walk_vtx, d_walk_off, H, S, ctx->seg_off.as<uint64_t>(), ctx->top_order.as<int32_t>(), ctx->coord.as<uint64_t>(),
-                          ctx->chunk_shift, ctx->step_len.as<PackedStep>(), d_ctr, ctx->st, &ctx->launches));
+        CU(walk_step_pass(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), ctx->step_len.as<PackedStep>(), d_ctr, ctx->st, &ctx->launches));
         CU(scan_packed_steps(ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), S, ctx->scan_scr.p, ctx->st, &ctx->launches));
         CU(cudaMemcpyAsync(&last, ctx->gbase.as<uint64_t>() + (S - 1), 8, cudaMemcpyDeviceToHost, ctx->st));
         CU(read_counters(ctx));                                         // wait 1
