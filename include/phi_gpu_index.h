@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PHI_GPU_INDEX_ABI_VERSION 2
+#define PHI_GPU_INDEX_ABI_VERSION 3
 
 /* status codes (0 == ok); text via phi_gpu_last_error() */
 enum {
@@ -84,12 +84,18 @@ typedef struct {
  * count_sp_r / spectrum : ILP_index.cpp:631-636 — number of distinct read
  *     minimizer hashes and the hashes themselves in ascending unsigned order;
  *     rank r <-> spectrum[r].
- * anchors (FINAL post-filter order) : ILP_index.cpp:643-716.  Anchors are sorted by (rank, walk, j) with j = the
- *     index of an anchor among the anchors of the same (rank, walk), i.e. anchor a is Anchor_hits[r][anchor_walk[a]][j]
- *     for the rank r with rank_off[r] <= a < rank_off[r + 1].  Its vertex list has anchor_len[a] vertices (1..k) and
- *     the lists lie back to back in anchor_vtx in anchor order, so one forward pass with push_back rebuilds the
- *     reference's nested vectors exactly (integration/phi_adapter.hpp).  The layout is compact on purpose: the result
- *     crosses PCIe (8 + 4 + 1 bytes per rank / anchor / anchor instead of three 4..8-byte arrays per anchor).
+ * groups (FINAL post-filter order) : ILP_index.cpp:670-716.  The reference's filter builds, per rank, a std::map from the
+ *     key string of a vertex list to its members (walk, anchor) and re-emits the anchors group after group in key order.
+ *     The result keeps exactly that form: the groups of rank r are [rank_off[r], rank_off[r + 1]) in the reference's key
+ *     order; group g has group_len[g] vertices (1..k), the lists lie back to back in group_vtx in group order, and its
+ *     members are the walks member_walk[group_member_off[g] .. group_member_off[g + 1]) in ascending order (a walk occurs
+ *     twice when it carries the list twice).  One forward pass
+ *         for r: for g in groups(r): for h in members(g): Anchor_hits[r][h].push_back(list(g))
+ *     rebuilds the reference's nested vectors exactly (integration/phi_adapter.hpp) — it is the loop at :700-709.
+ *     n_anchors = number of members = anchors in Anchor_hits.  The form is compact on purpose: the result crosses PCIe, and
+ *     with h haplotypes the per-anchor form would repeat every vertex list up to h times.
+ *     Sketch-only results (phi_gpu_index_sketch_walks): one group per emitted minimizer in (walk, path position) order,
+ *     rank_off == NULL, group_member_off == NULL (group g has the single member member_walk[g]).
  * minimizers_per_walk : kmer_index[h].size(), log line ILP_index.cpp:563.
  * anchors_per_walk    : log lines ILP_index.cpp:725-735.
  * n_filtered          : filtered_kmers, ILP_index.cpp:719-721 (log :738-743).
@@ -101,13 +107,15 @@ typedef struct {
     int32_t count_sp_r;
     uint32_t n_walks;
     int64_t n_filtered;
-    uint64_t n_anchors;
-    uint64_t n_anchor_vtx;
+    uint64_t n_anchors;                  /* members over all groups */
+    uint64_t n_groups;
+    uint64_t n_group_vtx;
     const uint64_t *spectrum;            /* [count_sp_r] */
-    const uint64_t *rank_off;            /* [count_sp_r + 1]; NULL when count_sp_r == 0 (sketch-only results) */
-    const int32_t *anchor_walk;          /* [n_anchors] */
-    const uint8_t *anchor_len;           /* [n_anchors] */
-    const int32_t *anchor_vtx;           /* [n_anchor_vtx] */
+    const uint32_t *rank_off;            /* [count_sp_r + 1] first group of every rank; NULL for sketch-only results */
+    const uint8_t *group_len;            /* [n_groups] */
+    const int32_t *group_vtx;            /* [n_group_vtx] */
+    const uint32_t *group_member_off;    /* [n_groups + 1]; NULL for sketch-only results (one member per group) */
+    const int32_t *member_walk;          /* [n_anchors] */
     const uint64_t *minimizers_per_walk; /* [n_walks] */
     const uint64_t *anchors_per_walk;    /* [n_walks] */
     /* work counters of this run (for throughput / roofline arithmetic) */
@@ -129,7 +137,7 @@ typedef struct {
     float read_sketch_ms;    /* read minimizers -> order-preserving HBM hash table -> sorted distinct hashes (waits for H2D of the reads) */
     float spectrum_ms;       /* radix directory (multi-GPU: + exchange of the spectrum) */
     float walk_sketch_ms;    /* minimizers of the representative chunks + probe + anchor emit */
-    float filter_ms;         /* group count, threshold, instantiation per walk, ordering, CSR */
+    float filter_ms;         /* group count, threshold, group order, member walks and vertex lists of the surviving groups */
     float d2h_ms;            /* device -> host copies of the result */
     float total_ms;          /* first event to last event */
     float walk_kernel_ms;    /* the walk sketch kernel alone (roofline numerator's denominator) */

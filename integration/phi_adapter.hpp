@@ -75,11 +75,14 @@ inline void run_front_end(ILP_index &ix, std::vector<std::pair<std::string, std:
     // ---- rebuild the nested vectors the model construction indexes (:643, :716)
     count_sp_r = res->count_sp_r;
     Anchor_hits.assign(count_sp_r, std::vector<std::vector<std::vector<int32_t> > >(ix.num_walks));
-    const int32_t *vtx = res->anchor_vtx;
+    // the result is the filter's own map (:680-709): per rank the groups in key order, per group one vertex list and its walks
+    const int32_t *vtx = res->group_vtx;
     for (int32_t r = 0; r < count_sp_r; ++r)
-        for (uint64_t a = res->rank_off[r]; a < res->rank_off[r + 1]; ++a) {
-            Anchor_hits[r][res->anchor_walk[a]].push_back(std::vector<int32_t>(vtx, vtx + res->anchor_len[a]));
-            vtx += res->anchor_len[a];
+        for (uint32_t g = res->rank_off[r]; g < res->rank_off[r + 1]; ++g) {
+            const std::vector<int32_t> list(vtx, vtx + res->group_len[g]);
+            for (uint32_t m = res->group_member_off[g]; m < res->group_member_off[g + 1]; ++m)
+                Anchor_hits[r][res->member_walk[m]].push_back(list);
+            vtx += res->group_len[g];
         }
 
     std::cerr << "Number of Anchors" << std::endl;                                                 // :724

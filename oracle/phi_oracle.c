@@ -223,7 +223,7 @@ static int check_params(const phi_index_params *p)
 
 /* public layout of the anchors (include/phi_gpu_index.h): per-rank offsets + per-anchor list lengths instead of the
  * per-anchor rank / offset arrays this file works with; consumes (frees) arank and aoff */
-static void to_compact(phi_index_result *r, int32_t *arank, uint64_t *aoff, int32_t n_ranks)
+static void to_compact(phi_oracle_result *r, int32_t *arank, uint64_t *aoff, int32_t n_ranks)
 {
     const uint64_t na = r->n_anchors;
     uint8_t *len = (uint8_t *)malloc(na ? na : 1);
@@ -240,7 +240,7 @@ static void to_compact(phi_index_result *r, int32_t *arank, uint64_t *aoff, int3
 }
 
 int phi_oracle_sketch_walks(const phi_graph_view *g, const phi_index_params *prm, int n_threads,
-                            phi_index_result **out, uint64_t **hashes_out)
+                            phi_oracle_result **out, uint64_t **hashes_out)
 {
     if (!g || !out || !hashes_out || !check_params(prm)) return PHI_ERR_ARG;
     uint32_t H = g->n_walks;
@@ -251,7 +251,7 @@ int phi_oracle_sketch_walks(const phi_graph_view *g, const phi_index_params *prm
     #pragma omp parallel for num_threads(n_threads) schedule(dynamic, 1)
     for (int64_t h = 0; h < (int64_t)H; ++h) sketch_one_walk(g, (uint32_t)h, prm->k, prm->w, &ws[h]);
 
-    phi_index_result *r = (phi_index_result *)calloc(1, sizeof(*r));
+    phi_oracle_result *r = (phi_oracle_result *)calloc(1, sizeof(*r));
     uint64_t na = 0, nv = 0;
     for (uint32_t h = 0; h < H; ++h) { na += ws[h].hash.n; nv += ws[h].vtx.n; }
     uint64_t *hashes = (uint64_t *)malloc((na ? na : 1) * 8);
@@ -315,17 +315,17 @@ static int cmp_hw(const void *a, const void *b)
 }
 
 int phi_oracle_index_run(const phi_graph_view *g, const phi_reads_view *rd, const phi_index_params *prm,
-                         int n_threads, phi_index_result **out)
+                         int n_threads, phi_oracle_result **out)
 {
     if (!g || !rd || !out || !check_params(prm)) return PHI_ERR_ARG;
     const int k = prm->k, w = prm->w;
 #ifdef _OPENMP
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #endif
-    phi_index_result *r = (phi_index_result *)calloc(1, sizeof(*r));
+    phi_oracle_result *r = (phi_oracle_result *)calloc(1, sizeof(*r));
 
     /* ---- loop A: walk sketches, ILP_index.cpp:556-573 */
-    phi_index_result *wsr = 0; uint64_t *whash = 0;
+    phi_oracle_result *wsr = 0; uint64_t *whash = 0;
     int rc = phi_oracle_sketch_walks(g, prm, n_threads, &wsr, &whash);
     if (rc) { free(r); return rc; }
 
@@ -449,7 +449,7 @@ int phi_oracle_index_run(const phi_graph_view *g, const phi_reads_view *rd, cons
     return PHI_OK;
 }
 
-void phi_oracle_result_free(phi_index_result *r)
+void phi_oracle_result_free(phi_oracle_result *r)
 {
     if (!r) return;
     free((void *)r->spectrum); free((void *)r->rank_off); free((void *)r->anchor_walk);

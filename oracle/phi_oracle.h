@@ -13,8 +13,9 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may call
  * into this library.  The product (phi_b200/) never does.
  *
- * Uses the same plain-C view/result structs as the product ABI so results can
- * be compared field by field.
+ * Uses the product ABI's plain-C input views and parameters.  The result has its own struct: the reference's final
+ * Anchor_hits flattened anchor by anchor in (rank, walk, j) order — what the reference-side adapter rebuilds from the
+ * product's grouped result, so the two are compared after that expansion.
  */
 #ifndef PHI_ORACLE_H
 #define PHI_ORACLE_H
@@ -23,22 +24,41 @@
 extern "C" {
 #endif
 
+typedef struct {
+    int32_t count_sp_r;
+    uint32_t n_walks;
+    int64_t n_filtered;
+    uint64_t n_anchors;
+    uint64_t n_anchor_vtx;
+    const uint64_t *spectrum;            /* [count_sp_r] ascending */
+    const uint64_t *rank_off;            /* [count_sp_r + 1] first anchor of every rank; NULL for sketch-only results */
+    const int32_t *anchor_walk;          /* [n_anchors] anchor a is Anchor_hits[rank][anchor_walk[a]][j] */
+    const uint8_t *anchor_len;           /* [n_anchors] vertices of anchor a */
+    const int32_t *anchor_vtx;           /* [n_anchor_vtx] the lists back to back */
+    const uint64_t *minimizers_per_walk; /* [n_walks] */
+    const uint64_t *anchors_per_walk;    /* [n_walks] */
+    uint64_t read_kmer_positions, path_kmer_positions, read_minimizers_emitted, path_minimizers_emitted, path_hits;
+    uint64_t n_walk_kmers;
+    const uint64_t *shared_kmer_hist;    /* [n_walks + 1] with params.debug, else NULL */
+} phi_oracle_result;
+
 /* hash128_to_64: ILP_index.cpp:10-18 over MurmurHash3_x64_128 (seed 0). */
 uint64_t phi_oracle_hash128_to_64(const uint8_t *key, int32_t len);
 void phi_oracle_murmur3_x64_128(const uint8_t *key, int32_t len, uint32_t seed, uint64_t out[2]);
 
 /* ILP_function lines 543-743 on flat views.  n_threads <= 0: all cores. */
 int phi_oracle_index_run(const phi_graph_view *graph, const phi_reads_view *reads, const phi_index_params *params,
-                         int n_threads, phi_index_result **out);
+                         int n_threads, phi_oracle_result **out);
 
-/* index_kmers for every walk (ILP_index.cpp:359-445); layout as phi_gpu_index_sketch_walks. */
+/* index_kmers for every walk (ILP_index.cpp:359-445): one anchor per emitted minimizer in (walk, path position) order,
+ * rank_off == NULL; (*hashes_out)[a] = the minimizer hash. */
 int phi_oracle_sketch_walks(const phi_graph_view *graph, const phi_index_params *params, int n_threads,
-                            phi_index_result **out, uint64_t **hashes_out);
+                            phi_oracle_result **out, uint64_t **hashes_out);
 
 /* compute_hashes for one read (ILP_index.cpp:447-493): sorted distinct hashes; returns count, fills *out (malloc). */
 int64_t phi_oracle_read_hashes(const uint8_t *read, uint64_t len, int32_t k, int32_t w, uint64_t **out);
 
-void phi_oracle_result_free(phi_index_result *res);
+void phi_oracle_result_free(phi_oracle_result *res);
 void phi_oracle_free(void *p);
 
 #ifdef __cplusplus

@@ -30,9 +30,10 @@ class IndexParams(C.Structure):
 
 class IndexResult(C.Structure):
     _fields_ = [("count_sp_r", C.c_int32), ("n_walks", C.c_uint32), ("n_filtered", C.c_int64),
-                ("n_anchors", C.c_uint64), ("n_anchor_vtx", C.c_uint64),
-                ("spectrum", u64p), ("rank_off", u64p), ("anchor_walk", i32p), ("anchor_len", u8p),
-                ("anchor_vtx", i32p), ("minimizers_per_walk", u64p), ("anchors_per_walk", u64p),
+                ("n_anchors", C.c_uint64), ("n_groups", C.c_uint64), ("n_group_vtx", C.c_uint64),
+                ("spectrum", u64p), ("rank_off", u32p), ("group_len", u8p), ("group_vtx", i32p),
+                ("group_member_off", u32p), ("member_walk", i32p),
+                ("minimizers_per_walk", u64p), ("anchors_per_walk", u64p),
                 ("read_kmer_positions", C.c_uint64), ("path_kmer_positions", C.c_uint64),
                 ("read_minimizers_emitted", C.c_uint64), ("path_minimizers_emitted", C.c_uint64),
                 ("path_hits", C.c_uint64), ("n_walk_kmers", C.c_uint64), ("shared_kmer_hist", u64p)]
@@ -136,8 +137,10 @@ class Reads:
 
 @dataclass
 class IndexResultPy:
-    """Host copy of phi_index_result (numpy arrays).  anchor_rank / anchor_off are the per-anchor expansions of the ABI's
-    compact rank_off / anchor_len arrays (what the reference-side adapter walks through)."""
+    """Host copy of phi_index_result (numpy arrays).  group_* / member_walk are the ABI's arrays (the reference's filter map:
+    one vertex list per group plus the walks that carry it); anchor_rank / anchor_walk / anchor_off / anchor_vtx are what the
+    reference-side adapter's forward pass builds from them: one entry per anchor in (rank, walk, j) order, i.e.
+    Anchor_hits[rank][walk][j]."""
     count_sp_r: int
     n_walks: int
     n_filtered: int
@@ -155,15 +158,22 @@ class IndexResultPy:
     path_hits: int = 0
     n_walk_kmers: int = 0
     shared_kmer_hist: np.ndarray = None        # [n_walks + 1] when the run had debug != 0
+    n_groups: int = 0
+    group_rank: np.ndarray = None
+    group_len: np.ndarray = None
+    group_vtx: np.ndarray = None
+    group_member_off: np.ndarray = None
+    member_walk: np.ndarray = None
 
     @property
     def n_anchors(self):
         return len(self.anchor_rank)
 
     def wire_bytes(self):
-        """Bytes of the C result arrays (what crosses PCIe): spectrum, rank_off, anchor_walk, anchor_len, anchor_vtx, per-walk counters."""
-        ns, na = self.count_sp_r, self.n_anchors
-        return 8 * ns + 8 * (ns + 1) + 4 * na + na + 4 * len(self.anchor_vtx) + 16 * self.n_walks
+        """Bytes of the C result arrays (what crosses PCIe): spectrum, rank_off, group_len, group_vtx, group_member_off,
+        member_walk, per-walk counters."""
+        ns, ng = self.count_sp_r, self.n_groups
+        return 8 * ns + 4 * (ns + 1) + ng + 4 * len(self.group_vtx) + 4 * (ng + 1) + 4 * len(self.member_walk) + 16 * self.n_walks
 
     def anchors(self):
         """[(rank, walk, [vertices])] in final order."""
@@ -178,28 +188,73 @@ def _np_from(ptr, n, dtype):
     return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype, copy=True)
 
 
+def expand_groups(group_rank, group_len, group_vtx, group_member_off, member_walk):
+    """The adapter's forward pass (ILP_index.cpp:700-709) in numpy: for every group in order, for every member walk h, push the
+    group's vertex list onto Anchor_hits[rank][h].  Returns the anchors in (rank, walk, j) order:
+    (anchor_rank, anchor_walk, anchor_off, anchor_vtx)."""
+    ng = len(group_len)
+    lens64 = group_len.astype(np.int64)
+    gvoff = np.concatenate([[0], np.cumsum(lens64)])
+    g_of_m = np.repeat(np.arange(ng, dtype=np.int64), np.diff(group_member_off.astype(np.int64)))
+    m_rank = group_rank.astype(np.int64)[g_of_m]
+    idx = np.lexsort((member_walk, m_rank))                  # stable: pushes onto one (rank, walk) keep the group order
+    g_sorted = g_of_m[idx]
+    alen = lens64[g_sorted]
+    anchor_off = np.concatenate([[0], np.cumsum(alen)]).astype(np.uint64)
+    total = int(anchor_off[-1])
+    src = np.repeat(gvoff[g_sorted], alen) + (np.arange(total, dtype=np.int64) - np.repeat(anchor_off[:-1].astype(np.int64), alen))
+    return (m_rank[idx].astype(np.int32), member_walk[idx].astype(np.int32), anchor_off,
+            group_vtx[src].astype(np.int32) if total else np.zeros(0, dtype=np.int32))
+
+
 def result_to_py(res: IndexResult) -> IndexResultPy:
-    na, nv, nw, ns = res.n_anchors, res.n_anchor_vtx, res.n_walks, res.count_sp_r
-    have = bool(res.anchor_len) or na == 0
-    rank_off = _np_from(res.rank_off, ns + 1 if res.rank_off else 0, np.uint64)
-    lens = _np_from(res.anchor_len, na, np.uint8)
+    na, ng, nv, nw, ns = res.n_anchors, res.n_groups, res.n_group_vtx, res.n_walks, res.count_sp_r
+    have = bool(res.group_len) or ng == 0
+    rank_off = _np_from(res.rank_off, ns + 1 if res.rank_off else 0, np.uint32)
+    group_len = _np_from(res.group_len, ng, np.uint8)
+    group_vtx = _np_from(res.group_vtx, nv, np.int32)
+    member_walk = _np_from(res.member_walk, na, np.int32)
+    if not have:                                               # counters only (run_resident without download)
+        ng = 0
+    if res.group_member_off:
+        member_off = _np_from(res.group_member_off, ng + 1, np.uint32)
+        if ng == 0:
+            member_off = np.zeros(1, dtype=np.uint32)
+    else:                                                      # sketch-only result: one member per group
+        assert na == ng or not have
+        member_off = np.arange(ng + 1, dtype=np.uint32)
+    if have:
+        assert int(member_off[0]) == 0 and int(member_off[-1]) == len(member_walk), "group_member_off does not cover member_walk"
+        assert int(group_len.astype(np.int64).sum()) == len(group_vtx), "group_len does not cover group_vtx"
     if len(rank_off):
-        assert int(rank_off[-1]) == na and int(rank_off[0]) == 0
-        anchor_rank = np.repeat(np.arange(ns, dtype=np.int32), np.diff(rank_off.astype(np.int64)))
+        assert int(rank_off[-1]) == ng and int(rank_off[0]) == 0
+        group_rank = np.repeat(np.arange(ns, dtype=np.int32), np.diff(rank_off.astype(np.int64)))
+        # members of a group ascend (the ABI promises it)
+        if len(member_walk) > 1:
+            same = np.ones(len(member_walk) - 1, dtype=bool)
+            starts = member_off[1:-1].astype(np.int64)
+            same[starts[(starts > 0) & (starts < len(member_walk))] - 1] = False
+            assert np.all((np.diff(member_walk.astype(np.int64)) >= 0) | ~same), "members of a group are not ascending"
     else:
-        anchor_rank = np.zeros(na if have else 0, dtype=np.int32)
-    anchor_off = np.concatenate([[0], np.cumsum(lens, dtype=np.uint64)]).astype(np.uint64) if res.anchor_len else np.zeros(0, dtype=np.uint64)
+        group_rank = np.zeros(ng, dtype=np.int32)
+    if res.group_member_off:
+        anchor_rank, anchor_walk, anchor_off, anchor_vtx = expand_groups(group_rank, group_len, group_vtx, member_off, member_walk)
+    else:
+        anchor_rank, anchor_walk, anchor_vtx = group_rank, member_walk, group_vtx
+        anchor_off = np.concatenate([[0], np.cumsum(group_len, dtype=np.uint64)]).astype(np.uint64) if have and res.group_len else np.zeros(0, dtype=np.uint64)
     return IndexResultPy(
         count_sp_r=int(ns), n_walks=int(nw), n_filtered=int(res.n_filtered),
         spectrum=_np_from(res.spectrum, ns, np.uint64),
         anchor_rank=anchor_rank,
-        anchor_walk=_np_from(res.anchor_walk, na, np.int32),
+        anchor_walk=anchor_walk,
         anchor_off=anchor_off,
-        anchor_vtx=_np_from(res.anchor_vtx, nv, np.int32),
+        anchor_vtx=anchor_vtx,
         minimizers_per_walk=_np_from(res.minimizers_per_walk, nw, np.uint64),
         anchors_per_walk=_np_from(res.anchors_per_walk, nw, np.uint64),
         read_kmer_positions=int(res.read_kmer_positions), path_kmer_positions=int(res.path_kmer_positions),
         read_minimizers_emitted=int(res.read_minimizers_emitted),
         path_minimizers_emitted=int(res.path_minimizers_emitted), path_hits=int(res.path_hits),
         n_walk_kmers=int(res.n_walk_kmers),
-        shared_kmer_hist=_np_from(res.shared_kmer_hist, nw + 1, np.uint64) if res.shared_kmer_hist else None)
+        shared_kmer_hist=_np_from(res.shared_kmer_hist, nw + 1, np.uint64) if res.shared_kmer_hist else None,
+        n_groups=int(ng), group_rank=group_rank, group_len=group_len, group_vtx=group_vtx, group_member_off=member_off,
+        member_walk=member_walk)

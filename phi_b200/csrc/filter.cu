@@ -62,7 +62,10 @@ __global__ void group_count_kernel(FilterArgs A, FilterWork W)
         }
         if (rep == (uint32_t)i || same_list(A, (uint32_t)i, rep)) {
             const uint32_t wt = W.weight ? W.weight[i] : W.chunk_weight ? W.chunk_weight[A.hit_walk[i]] : 1u;
-            atomicAdd(&W.g_cnt[slot], wt); W.hit_slot[i] = (uint32_t)slot; return;
+            const uint32_t before = atomicAdd(&W.g_cnt[slot], wt);
+            W.hit_slot[i] = (uint32_t)slot;
+            if (W.hit_sub) W.hit_sub[i] = before;
+            return;
         }
         slot = (slot + 1) & mask;
     }
@@ -183,22 +186,22 @@ __device__ int cmp_list(const FilterArgs &A, uint32_t x, uint32_t y)
     return nx == ny ? 0 : nx < ny ? -1 : 1;                           // proper prefix string sorts first
 }
 
-__device__ __forceinline__ bool same_rw(const FilterArgs &A, uint32_t x, uint32_t y)
+__device__ __forceinline__ bool same_rw(const FilterArgs &A, uint32_t x, uint32_t y, int by_walk)
 {
-    return A.hit_rank[x] == A.hit_rank[y] && A.hit_walk[x] == A.hit_walk[y];
+    return A.hit_rank[x] == A.hit_rank[y] && (!by_walk || A.hit_walk[x] == A.hit_walk[y]);
 }
 
 // order[] = hit ids sorted by (rank, walk, position).  Each thread owning the head of a (rank, walk) group with >= 2 members
 // re-orders it by (key string, position): stable insertion sort for small groups, deferral for big ones.
-__global__ void fix_multi_kernel(FilterArgs A, uint32_t *order, uint64_t n, uint32_t *big_list, uint32_t big_cap, unsigned long long *ctr)
+__global__ void fix_multi_kernel(FilterArgs A, uint32_t *order, uint64_t n, int by_walk, uint32_t *big_list, uint32_t big_cap, unsigned long long *ctr)
 {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= n) return;
     uint32_t me = order[j];
-    if (j > 0 && same_rw(A, order[j - 1], me)) return;               // not a head
-    if (j + 1 >= n || !same_rw(A, order[j + 1], me)) return;         // singleton
+    if (j > 0 && same_rw(A, order[j - 1], me, by_walk)) return;               // not a head
+    if (j + 1 >= n || !same_rw(A, order[j + 1], me, by_walk)) return;         // singleton
     uint64_t e = j + 2;
-    while (e < n && same_rw(A, order[e], me)) ++e;
+    while (e < n && same_rw(A, order[e], me, by_walk)) ++e;
     uint64_t len = e - j;
     if (len > SMALL_GROUP) {
         unsigned long long slot = atomicAdd(&ctr[CTR_BIG_GROUPS], 1ull);
@@ -233,11 +236,11 @@ __global__ void fix_big_kernel(FilterArgs A, uint32_t *order, uint32_t *tmp, con
     }
 }
 
-cudaError_t filter_fix_multi(const FilterArgs &A, uint32_t *order, uint64_t n_surv, uint32_t *big_list, uint32_t big_cap,
+cudaError_t filter_fix_multi(const FilterArgs &A, uint32_t *order, uint64_t n_surv, int by_walk, uint32_t *big_list, uint32_t big_cap,
                              unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
 {
     if (n_surv < 2) return cudaSuccess;
-    fix_multi_kernel<<<(unsigned)((n_surv + 127) / 128), 128, 0, st>>>(A, order, n_surv, big_list, big_cap, ctr);
+    fix_multi_kernel<<<(unsigned)((n_surv + 127) / 128), 128, 0, st>>>(A, order, n_surv, by_walk, big_list, big_cap, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -33,7 +33,8 @@ enum {
     CTR_SEG_TOO_LONG = 21,        // a segment of 2^31 bases or more
     CTR_WALK_KMERS = 22,          // distinct walk-minimizer hashes (-d1 statistic)
     CTR_SURV_VTX = 23,            // vertices of all instantiated surviving anchors           // hits of all walks (every member chunk counts what its representative found)     // a chunk differs from its fingerprint representative (128-bit collision): rerun without sharing
-    CTR_COUNT = 24
+    CTR_OUT_GROUPS = 24,          // surviving (rank, vertex list) groups of the result
+    CTR_COUNT = 25
 };
 
 enum { WALK_MODE_PROBE = 0, WALK_MODE_ALL = 1 };
@@ -209,6 +210,7 @@ struct FilterArgs {
 struct FilterWork {                  // device scratch, sized by the host
     uint32_t *g_rep, *g_cnt; uint64_t g_cap;      // group table
     uint32_t *hit_slot;                            // [n_hits] slot of each hit's group
+    uint32_t *hit_sub;                             // optional [n_hits]: the group's count before this hit was added (its sub-offset in the group)
     const uint32_t *weight;                        // optional [n_hits]: occurrences a record stands for (multi-GPU summaries)
     const uint32_t *chunk_weight;                  // optional [n_chunks]: members of the chunk hit_walk[i] names (hits of representatives)
     uint8_t *rank_drop;                            // [n_ranks]
@@ -223,7 +225,9 @@ cudaError_t filter_count_groups(const FilterArgs &A, const FilterWork &W, cudaSt
 cudaError_t filter_mark_drops(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
 // stable sort of the records (which arrive in (walk, position) order) on their rank: order ends up in W.vals_a
 cudaError_t filter_sort_records(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
-cudaError_t filter_fix_multi(const FilterArgs &A, uint32_t *order, uint64_t n_surv, uint32_t *big_list, uint32_t big_cap,
+// by_walk != 0: order[] is sorted by (rank, walk, position) and (rank, walk) runs are re-ordered; by_walk == 0: order[] holds one
+// record per group sorted by rank and the runs of one rank are re-ordered (all keys distinct there)
+cudaError_t filter_fix_multi(const FilterArgs &A, uint32_t *order, uint64_t n_surv, int by_walk, uint32_t *big_list, uint32_t big_cap,
                              unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 // big (rank, walk) groups recorded by filter_fix_multi (count in ctr[CTR_BIG_GROUPS], read on the device: no host round trip)
 cudaError_t filter_fix_big(const FilterArgs &A, uint32_t *order, uint32_t *tmp, const uint32_t *big_list, uint32_t big_cap,
@@ -232,5 +236,29 @@ cudaError_t filter_csr_sizes(const FilterArgs &A, const uint32_t *order, uint64_
 cudaError_t filter_csr_fill(const FilterArgs &A, const uint32_t *order, uint64_t n_surv, const uint64_t *anchor_off, uint64_t *rank_off,
                             int32_t *anchor_walk, int32_t *anchor_vtx, unsigned long long *anchors_per_walk,
                             uint32_t n_walks_out, cudaStream_t st, uint64_t *launches);
+
+// groups.cu — the grouped result: member walks per representative chunk, surviving groups, their members and vertex lists
+constexpr uint32_t SORT_VALS_MAX = 2048;   // walks per GPU up to which member lists are merged by a shared-memory counting sort
+constexpr uint32_t GROUP_HIST_MAX = 4096;  // walks up to which the anchors-per-walk histogram is block-local
+struct GroupOut {
+    const uint32_t *order;                         // [n_groups] representing hit of every group, final order
+    const uint32_t *member_off, *vtx_off;          // [n_groups + 1]
+    const uint32_t *cm_off, *cm_walk;              // member walks (local ids, ascending) of every representative chunk
+    uint32_t *members_tmp;                         // [n_members] parts as the hits wrote them
+    int32_t *member_walk; int32_t *group_vtx;      // result arrays
+    unsigned long long *anchors_per_walk;
+    uint32_t walk_id_base;
+};
+// cm_off = exclusive scan of c_ninst; cm_walk = walks of the members of every representative, ascending
+cudaError_t chunk_members(const ChunkTable &C, uint32_t n_walks, uint32_t *cm_off, uint32_t *cursor, uint32_t *cm_tmp, uint32_t *cm_walk,
+                          void *scan_scratch, cudaStream_t st, uint64_t *launches);
+// flags/pos: [n_hits] scratch; keys/vals receive (rank, representing hit) of every surviving group, in hit order;
+// ctr[CTR_OUT_GROUPS / CTR_SURVIVORS / CTR_SURV_VTX] += groups / members / vertices
+cudaError_t groups_compact(const FilterArgs &A, const FilterWork &W, uint32_t *flags, uint32_t *pos, uint32_t *keys, uint32_t *vals,
+                           void *scan_scratch, cudaStream_t st, uint64_t *launches);
+cudaError_t groups_sizes(const FilterArgs &A, const FilterWork &W, const uint32_t *order, uint32_t n_groups, uint32_t *cnt_out, uint32_t *nv_out,
+                         uint8_t *group_len, uint32_t *rank_off, cudaStream_t st, uint64_t *launches);
+cudaError_t groups_fill(const FilterArgs &A, const FilterWork &W, const GroupOut &G, uint32_t n_groups, uint32_t n_walks_local, uint32_t n_walks_out,
+                        cudaStream_t st, uint64_t *launches);
 
 }  // namespace phi

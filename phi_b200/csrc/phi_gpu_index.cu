@@ -80,6 +80,8 @@ struct phi_gpu_index_ctx {
     uint32_t n_chunks = 0, n_tiles = 0; uint64_t unique_windows = 0, active_chunks = 0, rep_chunks = 0, unique_hits = 0; int dedupe = 1, chunk_shift = 11;
     DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
     DevBuf anchor_off, rank_off, anchor_len, anchor_walk, anchor_vtx, apw, dbg_hist;
+    // grouped result (groups.cu): member walks of the representative chunks, slot / sub-offset of every hit, group sizes and offsets
+    DevBuf cm_off, cm_cursor, cm_tmp, cm_walk, hit_slot, hit_sub, hit_slot2, g_rep2, g_cnt2, grp_cnt, grp_moff, grp_voff, members_tmp;
     unsigned long long *h_ctr = nullptr;   // pinned mirror of the counter block
     // what the second stream uses instead of ctr / h_ctr / scan_scr / flags / flags64 / nv_out (swapped in by PrepScope)
     DevBuf ctr2, scan_scr2, flags2, flags64_2, nv_out2; unsigned long long *h_ctr2 = nullptr;
@@ -88,7 +90,7 @@ struct phi_gpu_index_ctx {
     // multi-GPU (set by comm_init)
     int rank = 0, world = 1; uint32_t walk_id_base = 0, n_walks_global = 0;
     void *comm = nullptr;
-    uint64_t gcap_hint = 0;              // group-table size that worked last time
+    uint64_t gcap_hint = 0, gcap_hint2 = 0;   // group-table sizes that worked last time (local table, owner-side table)
     DevBuf xk_a, xk_b, xcnt, xoff, ag_send, ag_recv, m_rank, m_cnt, m_voff, m_nv, r_rank, r_walk, r_pos, r_voff, r_nv, r_vtx, s_rank, s_walk, s_pos, s_voff, s_nv, s_vtx;
     std::vector<uint64_t> own_off;       // [world + 1] first global rank owned by each GPU (multi-GPU runs)
 
@@ -164,6 +166,8 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
                       &ctx->s_voff, &ctx->s_nv, &ctx->s_vtx,
                       &ctx->hit_voff, &ctx->hit_nv, &ctx->hit_hash, &ctx->vtx_pool, &ctx->g_rep, &ctx->g_cnt, &ctx->rank_drop, &ctx->flags,
                       &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->big_list, &ctx->tmp_order, &ctx->nv_out,
+                      &ctx->cm_off, &ctx->cm_cursor, &ctx->cm_tmp, &ctx->cm_walk, &ctx->hit_slot, &ctx->hit_sub, &ctx->hit_slot2, &ctx->g_rep2, &ctx->g_cnt2,
+                      &ctx->grp_cnt, &ctx->grp_moff, &ctx->grp_voff, &ctx->members_tmp,
                       &ctx->dbg_hist, &ctx->anchor_off, &ctx->rank_off, &ctx->anchor_len, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw};
     for (DevBuf *b : bufs) b->release();
     {
@@ -289,7 +293,7 @@ namespace {
 
 struct RunOut {                    // device-side products of one run
     uint32_t n_spec = 0;
-    uint64_t n_hits = 0, n_hit_vtx = 0, n_surv = 0, n_anchor_vtx = 0;   // n_hits: hits of the representative chunks
+    uint64_t n_hits = 0, n_hit_vtx = 0, n_surv = 0, n_groups = 0, n_anchor_vtx = 0;   // n_hits: hits of the representative chunks
     uint64_t path_hits = 0;                                             // hits of all walks
     uint64_t read_pos = 0, path_pos = 0, read_emitted = 0, path_emitted = 0;
     int64_t n_filtered = 0;
@@ -408,6 +412,11 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     ctx->unique_windows = ctx->h_ctr[CTR_UNIQUE_WINDOWS]; ctx->active_chunks = ctx->h_ctr[CTR_ACTIVE_CHUNKS];
     CU(ctx->tiles.reserve((size_t)ctx->n_tiles * sizeof(TileRec) + 32));
     CU(chunk_tiles(C, d_walk_off, ctx->step_base.as<uint32_t>(), w, ctx->tiles.as<TileRec>(), ctx->st, &ctx->launches));
+    // member walks of every representative (the grouped result copies them instead of instantiating one record per member)
+    DevBuf *cms[] = {&ctx->cm_off, &ctx->cm_cursor, &ctx->cm_tmp, &ctx->cm_walk};
+    for (DevBuf *b : cms) CU(b->reserve(((size_t)NC + 2) * 4));
+    CU(chunk_members(C, H, ctx->cm_off.as<uint32_t>(), ctx->cm_cursor.as<uint32_t>(), ctx->cm_tmp.as<uint32_t>(), ctx->cm_walk.as<uint32_t>(),
+                     ctx->scan_scr.p, ctx->st, &ctx->launches));
     return PHI_OK;
 }
 
@@ -933,27 +942,33 @@ static FilterArgs filter_args(phi_gpu_index_ctx *ctx, uint64_t n, const DevBuf &
 
 // group table over the records of A; a record stands for weight[i] occurrences, or for as many as its chunk has members
 // (chunk_weight), or for one.  Fills W.hit_slot / g_rep / g_cnt.
-static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, FilterWork &W, const uint32_t *weight, const uint32_t *chunk_weight)
+// owner_side: the table of the summaries a rank owner received (several GPUs); the local table stays alive next to it.
+static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, FilterWork &W, const uint32_t *weight, const uint32_t *chunk_weight,
+                                 bool owner_side)
 {
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
     const uint64_t n = A.n_hits;
     // distinct (rank, vertex list) groups are usually fewer than records, so start small and grow on overflow
     uint64_t gcap = 1024; while (gcap < n / 2) gcap <<= 1;
-    if (ctx->gcap_hint > gcap) gcap = ctx->gcap_hint;
-    CU(ctx->vals_b.reserve(n * 4 + 4));
-    W.hit_slot = ctx->vals_b.as<uint32_t>();                              // free until the survivor sort
+    uint64_t &hint = owner_side ? ctx->gcap_hint2 : ctx->gcap_hint;
+    if (hint > gcap) gcap = hint;
+    DevBuf &slotb = owner_side ? ctx->hit_slot2 : ctx->hit_slot, &repb = owner_side ? ctx->g_rep2 : ctx->g_rep, &cntb = owner_side ? ctx->g_cnt2 : ctx->g_cnt;
+    CU(slotb.reserve(n * 4 + 4));
+    W.hit_slot = slotb.as<uint32_t>();
+    W.hit_sub = nullptr;
+    if (!owner_side) { CU(ctx->hit_sub.reserve(n * 4 + 4)); W.hit_sub = ctx->hit_sub.as<uint32_t>(); }
     W.weight = weight; W.chunk_weight = chunk_weight;
     for (;;) {
-        CU(ctx->g_rep.reserve(gcap * 4)); CU(ctx->g_cnt.reserve(gcap * 4));
-        CU(fill_u32(ctx->g_rep.as<uint32_t>(), gcap, 0xFFFFFFFFu, ctx->st, &ctx->launches));
-        CU(cudaMemsetAsync(ctx->g_cnt.p, 0, gcap * 4, ctx->st));
+        CU(repb.reserve(gcap * 4)); CU(cntb.reserve(gcap * 4));
+        CU(fill_u32(repb.as<uint32_t>(), gcap, 0xFFFFFFFFu, ctx->st, &ctx->launches));
+        CU(cudaMemsetAsync(cntb.p, 0, gcap * 4, ctx->st));
         CU(cudaMemsetAsync(d_ctr + CTR_GROUPS, 0, 2 * 8, ctx->st));
-        W.g_rep = ctx->g_rep.as<uint32_t>(); W.g_cnt = ctx->g_cnt.as<uint32_t>(); W.g_cap = gcap;
+        W.g_rep = repb.as<uint32_t>(); W.g_cnt = cntb.as<uint32_t>(); W.g_cap = gcap;
         CU(filter_count_groups(A, W, ctx->st, &ctx->launches));
         CU(read_counters(ctx));
         if (!ctx->h_ctr[CTR_GROUP_OVERFLOW]) break;
         gcap <<= 2;
-        ctx->gcap_hint = gcap;
+        hint = gcap;
     }
     return PHI_OK;
 }
@@ -1012,7 +1027,7 @@ static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, bool key_o
     if (key_order) {                                                      // (rank, walk) groups with several hits: std::map<std::string> order (:680-709)
         const uint32_t big_cap = (uint32_t)(ns / 48 + 1);
         CU(ctx->big_list.reserve((size_t)big_cap * 8)); CU(ctx->tmp_order.reserve(ns * 4));
-        CU(filter_fix_multi(A, order, ns, ctx->big_list.as<uint32_t>(), big_cap, d_ctr, ctx->st, &ctx->launches));
+        CU(filter_fix_multi(A, order, ns, 1, ctx->big_list.as<uint32_t>(), big_cap, d_ctr, ctx->st, &ctx->launches));
         CU(filter_fix_big(A, order, ctx->tmp_order.as<uint32_t>(), ctx->big_list.as<uint32_t>(), big_cap, d_ctr, ctx->st, &ctx->launches));
     }
     CU(ctx->nv_out.reserve((ns + 1) * 4)); CU(ctx->anchor_len.reserve(ns + 4));
@@ -1024,6 +1039,55 @@ static int order_and_csr(phi_gpu_index_ctx *ctx, const FilterArgs &A, bool key_o
     CU(ctx->anchor_walk.reserve(ns * 4)); CU(ctx->anchor_vtx.reserve(total_vtx * 4 + 4));
     CU(filter_csr_fill(A, order, ns, ctx->anchor_off.as<uint64_t>(), write_rank_off ? ctx->rank_off.as<uint64_t>() : nullptr, ctx->anchor_walk.as<int32_t>(),
                        ctx->anchor_vtx.as<int32_t>(), ctx->apw.as<unsigned long long>(), n_walks_global, ctx->st, &ctx->launches));
+    return PHI_OK;
+}
+
+// The surviving groups of the local table W (rank_drop is final) -> the grouped result in ctx->rank_off (u32), anchor_len
+// (= group_len), anchor_vtx (= group_vtx), grp_moff (= group_member_off), anchor_walk (= member_walk), apw.
+static int groups_out(phi_gpu_index_ctx *ctx, const FilterArgs &A, FilterWork &W, uint32_t n_walks_global, RunOut &o)
+{
+    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
+    const uint64_t n = A.n_hits;
+    CU(cudaMemsetAsync(d_ctr + CTR_SURVIVORS, 0, 2 * 8, ctx->st));       // SURVIVORS, BIG_GROUPS
+    CU(cudaMemsetAsync(d_ctr + CTR_SURV_VTX, 0, 2 * 8, ctx->st));        // SURV_VTX, OUT_GROUPS
+    CU(ctx->flags.reserve(n * 4 + 4)); CU(ctx->vals_b.reserve(n * 4 + 4));
+    CU(ctx->keys_a.reserve(n * 4 + 4)); CU(ctx->vals_a.reserve(n * 4 + 4));
+    CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(n + 2), (size_t)1024)));
+    // upper bound n groups: keys_a / vals_a are sized for it, the second sort buffers after the count is known
+    CU(groups_compact(A, W, ctx->flags.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), ctx->keys_a.as<uint32_t>(), ctx->vals_a.as<uint32_t>(),
+                      ctx->scan_scr.p, ctx->st, &ctx->launches));
+    CU(read_counters(ctx));                                               // groups, members, vertices (also: CTR_FILTERED)
+    const uint64_t ng = ctx->h_ctr[CTR_OUT_GROUPS], ns = ctx->h_ctr[CTR_SURVIVORS], nv = ctx->h_ctr[CTR_SURV_VTX];
+    o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED];
+    if (ns >= (1ull << 32) || nv >= (1ull << 32)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-1 anchors on one GPU; shard the walks over more GPUs");
+    o.n_surv = ns; o.n_groups = ng; o.n_anchor_vtx = nv;
+    if (!ng) return PHI_OK;
+    CU(ctx->keys_b.reserve(ng * 4 + 4)); CU(ctx->vals_b.reserve(ng * 4 + 4));
+    CU(ctx->sort_scr.reserve(radix_sort_u32_scratch(ng)));
+    CU(radix_sort_u32(ctx->keys_a.as<uint32_t>(), ctx->keys_b.as<uint32_t>(), ctx->vals_a.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), ng, A.rank_bits,
+                      ctx->sort_scr.p, ctx->st, &ctx->launches));
+    uint32_t *order = ctx->vals_a.as<uint32_t>();
+    // the groups of one rank: std::map<std::string> order of their keys (:680-709)
+    const uint32_t big_cap = (uint32_t)(ng / 48 + 1);
+    CU(ctx->big_list.reserve((size_t)big_cap * 8)); CU(ctx->tmp_order.reserve(ng * 4));
+    CU(filter_fix_multi(A, order, ng, 0, ctx->big_list.as<uint32_t>(), big_cap, d_ctr, ctx->st, &ctx->launches));
+    CU(filter_fix_big(A, order, ctx->tmp_order.as<uint32_t>(), ctx->big_list.as<uint32_t>(), big_cap, d_ctr, ctx->st, &ctx->launches));
+    // sizes -> offsets
+    CU(ctx->grp_cnt.reserve((ng + 1) * 4)); CU(ctx->nv_out.reserve((ng + 1) * 4)); CU(ctx->anchor_len.reserve(ng + 4));
+    CU(ctx->grp_moff.reserve((ng + 1) * 4)); CU(ctx->grp_voff.reserve((ng + 1) * 4));
+    CU(cudaMemsetAsync(ctx->grp_cnt.as<uint32_t>() + ng, 0, 4, ctx->st)); CU(cudaMemsetAsync(ctx->nv_out.as<uint32_t>() + ng, 0, 4, ctx->st));
+    CU(groups_sizes(A, W, order, (uint32_t)ng, ctx->grp_cnt.as<uint32_t>(), ctx->nv_out.as<uint32_t>(), ctx->anchor_len.as<uint8_t>(),
+                    ctx->rank_off.as<uint32_t>(), ctx->st, &ctx->launches));
+    CU(ctx->scan_scr.reserve(scan_u32_scratch(ng + 2)));
+    CU(scan_u32(ctx->grp_cnt.as<uint32_t>(), ctx->grp_moff.as<uint32_t>(), ng + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
+    CU(scan_u32(ctx->nv_out.as<uint32_t>(), ctx->grp_voff.as<uint32_t>(), ng + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
+    CU(ctx->members_tmp.reserve(ns * 4 + 4)); CU(ctx->anchor_walk.reserve(ns * 4 + 4)); CU(ctx->anchor_vtx.reserve(nv * 4 + 4));
+    GroupOut G;
+    G.order = order; G.member_off = ctx->grp_moff.as<uint32_t>(); G.vtx_off = ctx->grp_voff.as<uint32_t>();
+    G.cm_off = ctx->cm_off.as<uint32_t>(); G.cm_walk = ctx->cm_walk.as<uint32_t>(); G.members_tmp = ctx->members_tmp.as<uint32_t>();
+    G.member_walk = ctx->anchor_walk.as<int32_t>(); G.group_vtx = ctx->anchor_vtx.as<int32_t>();
+    G.anchors_per_walk = ctx->apw.as<unsigned long long>(); G.walk_id_base = ctx->world > 1 ? ctx->walk_id_base : 0;
+    CU(groups_fill(A, W, G, (uint32_t)ng, ctx->n_walks, n_walks_global, ctx->st, &ctx->launches));
     return PHI_OK;
 }
 
@@ -1079,7 +1143,7 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walk
     // the drop flags of all owners are then shared.  Every rank takes part in every collective, also with zero hits.
     if (ctx->world == 1) {
         if (!n) return PHI_OK;
-        int rc = count_groups_adaptive(ctx, A, W, nullptr, ctx->c_ninst.as<uint32_t>());
+        int rc = count_groups_adaptive(ctx, A, W, nullptr, ctx->c_ninst.as<uint32_t>(), false);
         if (rc) return rc;
         CU(filter_mark_drops(A, W, ctx->st, &ctx->launches));
     } else {
@@ -1089,7 +1153,7 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walk
         CU(cudaEventRecord(ctx->ev[EV_XH0], ctx->st));
         uint64_t n_sum = 0;
         if (n) {
-            int rc = count_groups_adaptive(ctx, A, W, nullptr, ctx->c_ninst.as<uint32_t>());
+            int rc = count_groups_adaptive(ctx, A, W, nullptr, ctx->c_ninst.as<uint32_t>(), false);
             if (rc) return rc;
             CU(ctx->flags.reserve(n * 4 + 4)); CU(ctx->flags64.reserve((n + 1) * 8));
             CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(n), scan_u32_to_u64_scratch(n + 1))));
@@ -1113,7 +1177,7 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walk
             FilterArgs B = filter_args(ctx, rs, ctx->r_rank, ctx->r_walk, ctx->r_pos, ctx->r_voff, ctx->r_nv, ctx->r_vtx, o.n_spec, threshold, n_walks_global);
             FilterWork WB; memset(&WB, 0, sizeof(WB));
             WB.rank_drop = ctx->rank_drop.as<uint8_t>(); WB.ctr = d_ctr;
-            rc = count_groups_adaptive(ctx, B, WB, ctx->r_walk.as<uint32_t>(), nullptr);
+            rc = count_groups_adaptive(ctx, B, WB, ctx->r_walk.as<uint32_t>(), nullptr, true);
             if (rc) return rc;
             CU(filter_mark_drops(B, WB, ctx->st, &ctx->launches));             // also counts the flags (all in this rank's owned range)
         }
@@ -1127,14 +1191,8 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walk
         if (!n) { CU(read_counters(ctx)); o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED]; return PHI_OK; }
     }
 
-    // ---- the surviving hits of the representatives are instantiated for every member chunk of THIS GPU's walks, in
-    // (walk, position) order; a stable sort on the rank alone then gives the final (rank, walk, position) order
-    uint64_t ns = 0;
-    int rc2 = expand_survivors(ctx, w, false, ns);
-    if (rc2) return rc2;
-    FilterArgs XA = filter_args(ctx, ns, ctx->x_rank, ctx->x_walk, ctx->x_pos, ctx->x_voff, ctx->x_nv, ctx->vtx_pool, o.n_spec, threshold, n_walks_global);
-    o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED];                       // read with the survivor count; several GPUs: the dropped ranks this GPU owns
-    return order_and_csr(ctx, XA, true, true, n_walks_global, o);
+    // ---- the surviving groups of THIS GPU's walks, in (rank, key) order, with their member walks
+    return groups_out(ctx, A, W, n_walks_global, o);
 }
 
 // ---- the -d1 statistic (ILP_index.cpp:565-606), after the result proper is complete: every minimizer of the representative
@@ -1321,15 +1379,20 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     }
 
     res->count_sp_r = (int32_t)o.n_spec; res->n_walks = HG; res->n_filtered = o.n_filtered;
-    res->n_anchors = o.n_surv; res->n_anchor_vtx = o.n_anchor_vtx;
+    if (mode == WALK_MODE_ALL) o.n_groups = o.n_surv;                       // sketch-only: one group per emitted minimizer
+    res->n_anchors = o.n_surv; res->n_groups = o.n_groups; res->n_group_vtx = o.n_anchor_vtx;
     res->read_kmer_positions = o.read_pos; res->path_kmer_positions = o.path_pos;
     res->read_minimizers_emitted = o.read_emitted; res->path_hits = o.path_hits;
     if (do_download) {
         rc = spec_early ? PHI_OK : download<uint64_t>(ctx, res, ctx->spec_a.p, 0, &res->spectrum);
-        if (!rc && mode == WALK_MODE_PROBE) rc = download<uint64_t>(ctx, res, ctx->rank_off.p, (uint64_t)o.n_spec + 1, &res->rank_off);
-        if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_walk.p, o.n_surv, &res->anchor_walk);
-        if (!rc) rc = download<uint8_t>(ctx, res, ctx->anchor_len.p, o.n_surv, &res->anchor_len);
-        if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_vtx.p, o.n_anchor_vtx, &res->anchor_vtx);
+        if (!rc && mode == WALK_MODE_PROBE) rc = download<uint32_t>(ctx, res, ctx->rank_off.p, (uint64_t)o.n_spec + 1, &res->rank_off);
+        if (!rc && mode == WALK_MODE_PROBE) {
+            if (o.n_groups) rc = download<uint32_t>(ctx, res, ctx->grp_moff.p, o.n_groups + 1, &res->group_member_off);
+            else { rc = download<uint32_t>(ctx, res, nullptr, 0, &res->group_member_off); if (!rc) *(uint32_t *)res->group_member_off = 0; }
+        }
+        if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_walk.p, o.n_surv, &res->member_walk);
+        if (!rc) rc = download<uint8_t>(ctx, res, ctx->anchor_len.p, o.n_groups, &res->group_len);
+        if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_vtx.p, o.n_anchor_vtx, &res->group_vtx);
         if (!rc) rc = download<uint64_t>(ctx, res, ctx->apw.as<uint64_t>(), HG, &res->anchors_per_walk);
         if (rc) return rc;
     }

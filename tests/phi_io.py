@@ -98,6 +98,42 @@ def parse_model_dump(path):
 _oracle = None
 
 
+class OracleResult(C.Structure):
+    """oracle/phi_oracle.h: phi_oracle_result (the reference's final Anchor_hits, anchor by anchor)."""
+    _fields_ = [("count_sp_r", C.c_int32), ("n_walks", C.c_uint32), ("n_filtered", C.c_int64),
+                ("n_anchors", C.c_uint64), ("n_anchor_vtx", C.c_uint64),
+                ("spectrum", _abi.u64p), ("rank_off", _abi.u64p), ("anchor_walk", _abi.i32p), ("anchor_len", _abi.u8p),
+                ("anchor_vtx", _abi.i32p), ("minimizers_per_walk", _abi.u64p), ("anchors_per_walk", _abi.u64p),
+                ("read_kmer_positions", C.c_uint64), ("path_kmer_positions", C.c_uint64),
+                ("read_minimizers_emitted", C.c_uint64), ("path_minimizers_emitted", C.c_uint64),
+                ("path_hits", C.c_uint64), ("n_walk_kmers", C.c_uint64), ("shared_kmer_hist", _abi.u64p)]
+
+
+def oracle_result_to_py(res):
+    """phi_oracle_result -> the same IndexResultPy the product's results are expanded into (anchor_* fields)."""
+    na, nv, nw, ns = res.n_anchors, res.n_anchor_vtx, res.n_walks, res.count_sp_r
+    rank_off = _abi._np_from(res.rank_off, ns + 1 if res.rank_off else 0, np.uint64)
+    lens = _abi._np_from(res.anchor_len, na, np.uint8)
+    if len(rank_off):
+        assert int(rank_off[-1]) == na and int(rank_off[0]) == 0
+        anchor_rank = np.repeat(np.arange(ns, dtype=np.int32), np.diff(rank_off.astype(np.int64)))
+    else:
+        anchor_rank = np.zeros(na, dtype=np.int32)
+    anchor_off = np.concatenate([[0], np.cumsum(lens, dtype=np.uint64)]).astype(np.uint64)
+    return _abi.IndexResultPy(
+        count_sp_r=int(ns), n_walks=int(nw), n_filtered=int(res.n_filtered),
+        spectrum=_abi._np_from(res.spectrum, ns, np.uint64),
+        anchor_rank=anchor_rank, anchor_walk=_abi._np_from(res.anchor_walk, na, np.int32),
+        anchor_off=anchor_off, anchor_vtx=_abi._np_from(res.anchor_vtx, nv, np.int32),
+        minimizers_per_walk=_abi._np_from(res.minimizers_per_walk, nw, np.uint64),
+        anchors_per_walk=_abi._np_from(res.anchors_per_walk, nw, np.uint64),
+        read_kmer_positions=int(res.read_kmer_positions), path_kmer_positions=int(res.path_kmer_positions),
+        read_minimizers_emitted=int(res.read_minimizers_emitted),
+        path_minimizers_emitted=int(res.path_minimizers_emitted), path_hits=int(res.path_hits),
+        n_walk_kmers=int(res.n_walk_kmers),
+        shared_kmer_hist=_abi._np_from(res.shared_kmer_hist, nw + 1, np.uint64) if res.shared_kmer_hist else None)
+
+
 def oracle_lib():
     """ctypes handle on oracle/libphi_oracle.so, building it with gcc if needed (test infra only)."""
     global _oracle
@@ -113,13 +149,13 @@ def oracle_lib():
         lib.phi_oracle_index_run.restype = C.c_int
         lib.phi_oracle_index_run.argtypes = [C.POINTER(_abi.GraphView), C.POINTER(_abi.ReadsView),
                                              C.POINTER(_abi.IndexParams), C.c_int,
-                                             C.POINTER(C.POINTER(_abi.IndexResult))]
+                                             C.POINTER(C.POINTER(OracleResult))]
         lib.phi_oracle_sketch_walks.restype = C.c_int
         lib.phi_oracle_sketch_walks.argtypes = [C.POINTER(_abi.GraphView), C.POINTER(_abi.IndexParams), C.c_int,
-                                                C.POINTER(C.POINTER(_abi.IndexResult)), C.POINTER(_abi.u64p)]
+                                                C.POINTER(C.POINTER(OracleResult)), C.POINTER(_abi.u64p)]
         lib.phi_oracle_read_hashes.restype = C.c_int64
         lib.phi_oracle_read_hashes.argtypes = [C.c_char_p, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(_abi.u64p)]
-        lib.phi_oracle_result_free.argtypes = [C.POINTER(_abi.IndexResult)]
+        lib.phi_oracle_result_free.argtypes = [C.POINTER(OracleResult)]
         lib.phi_oracle_free.argtypes = [C.c_void_p]
         _oracle = lib
     return _oracle
@@ -133,10 +169,10 @@ def oracle_index(graph, reads, k=31, w=25, threshold=1.0, threads=0, debug=0):
     lib = oracle_lib()
     gv, rv = graph.view(), reads.view()
     prm = _abi.IndexParams(k, w, threshold, debug)
-    out = C.POINTER(_abi.IndexResult)()
+    out = C.POINTER(OracleResult)()
     rc = lib.phi_oracle_index_run(C.byref(gv), C.byref(rv), C.byref(prm), threads, C.byref(out))
     assert rc == 0, rc
-    res = _abi.result_to_py(out.contents)
+    res = oracle_result_to_py(out.contents)
     lib.phi_oracle_result_free(out)
     return res
 
@@ -145,11 +181,11 @@ def oracle_sketch_walks(graph, k=31, w=25, threads=0):
     lib = oracle_lib()
     gv = graph.view()
     prm = _abi.IndexParams(k, w, 1.0, 0)
-    out = C.POINTER(_abi.IndexResult)()
+    out = C.POINTER(OracleResult)()
     hp = _abi.u64p()
     rc = lib.phi_oracle_sketch_walks(C.byref(gv), C.byref(prm), threads, C.byref(out), C.byref(hp))
     assert rc == 0, rc
-    res = _abi.result_to_py(out.contents)
+    res = oracle_result_to_py(out.contents)
     hashes = _abi._np_from(hp, res.n_anchors, np.uint64)
     lib.phi_oracle_result_free(out)
     lib.phi_oracle_free(hp)

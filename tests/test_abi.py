@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 15
     for s in syms:
         assert hasattr(lib, s), s
-    assert lib.phi_gpu_index_abi_version() == 2
+    assert lib.phi_gpu_index_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_gpu():
