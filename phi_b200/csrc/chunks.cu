@@ -60,6 +60,25 @@ __device__ __forceinline__ uint32_t walk_of_step(const uint64_t *walk_off, uint3
     return lo;
 }
 
+// The steps [s0, s1] of one block mostly lie in one walk: thread 0 looks the two ends up once, the block shares the answer and
+// only blocks that straddle a walk boundary search per thread (between the two ends).  Returns the walk of step s; ws = its first step.
+__device__ __forceinline__ uint32_t walk_of_step_block(const uint64_t *walk_off, uint32_t n_walks, uint64_t s, uint64_t s0, uint64_t s1, uint64_t &ws)
+{
+    __shared__ uint32_t sh_h[2];
+    __shared__ uint64_t sh_ws;
+    if (threadIdx.x == 0) {
+        const uint32_t a = walk_of_step(walk_off, n_walks, s0), b = walk_of_step(walk_off, n_walks, s1);
+        sh_h[0] = a; sh_h[1] = b; sh_ws = walk_off[a];
+    }
+    __syncthreads();
+    uint32_t lo = sh_h[0], hi = sh_h[1];
+    if (lo == hi) { ws = sh_ws; return lo; }
+    ++hi;                                                               // last h in [lo, hi) with walk_off[h] <= s
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
+    ws = walk_off[lo];
+    return lo;
+}
+
 // ---- one pass over the walk steps: segment length, chunk boundary (the step's vertex lies in another coordinate bucket than the
 // previous step's, or the step is the first of its walk), zero-length steps, topological monotonicity of the walks
 __global__ void __launch_bounds__(256) step_pass_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
@@ -73,9 +92,11 @@ __global__ void __launch_bounds__(256) step_pass_kernel(const uint32_t *walk_vtx
     // the previous step's vertex record: the neighbouring lane has it (lane 0 fetches its own)
     uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, me.y, 1), pt = __shfl_up_sync(0xFFFFFFFFu, me.z, 1);
     if (lane == 0 && s && s < n_steps) { const uint4 p = vinfo[walk_vtx[s - 1]]; pb = p.y; pt = p.z; }
+    uint64_t ws;
+    const uint64_t blk0 = blockIdx.x * (uint64_t)blockDim.x;
+    walk_of_step_block(walk_off, n_walks, s < n_steps ? s : n_steps - 1, blk0, min(blk0 + blockDim.x, n_steps) - 1, ws);
     if (s < n_steps) {
-        const uint32_t h = walk_of_step(walk_off, n_walks, s);
-        flag = s == walk_off[h];
+        flag = s == ws;
         if (!flag) {
             flag = me.y != pb;
             if ((int32_t)pt >= (int32_t)me.z) ctr[CTR_NONMONO] = 1;
@@ -97,11 +118,13 @@ __global__ void __launch_bounds__(256) step_finalize_kernel(ChunkTable C, const 
 {
     const uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (s == 0) C.chunk_step[C.n_chunks] = (uint32_t)n_steps;
+    uint64_t ws;
+    const uint64_t blk0 = blockIdx.x * (uint64_t)blockDim.x;
+    const uint32_t h = walk_of_step_block(walk_off, n_walks, s < n_steps ? s : n_steps - 1, blk0, min(blk0 + blockDim.x, n_steps) - 1, ws);
     if (s >= n_steps) return;
     const uint64_t mask = (1ull << STEP_BASE_BITS) - 1;
-    const uint32_t h = walk_of_step(walk_off, n_walks, s);
     const uint64_t sc = scanned[s];
-    step_base[s] = (uint32_t)((sc & mask) - (scanned[walk_off[h]] & mask));
+    step_base[s] = (uint32_t)((sc & mask) - (scanned[ws] & mask));
     if (packed[s].v >> 31) { const uint64_t c = sc >> STEP_BASE_BITS; if (c < C.n_chunks) { C.chunk_step[c] = (uint32_t)s; C.c_walk[c] = h; } }
 }
 
@@ -148,20 +171,35 @@ __global__ void __launch_bounds__(256) chunk_key_kernel(ChunkTable C, const uint
     const uint64_t ws = walk_off[h], we = walk_off[h + 1];
     const long long len = (long long)walk_len[h];
     const uint64_t s0 = C.chunk_step[c], s1 = C.chunk_step[c + 1];
-    uint32_t L = 0, R = 0; long long lo = 0, hi = 0;
-    if (lane == 0) {
-        lo = step_base[s0];
-        const long long b1 = s1 < we ? (long long)step_base[s1] : len;
-        hi = min(b1, len - k + 1);
-        if (len < (long long)w + k - 1 || hi <= max(lo, (long long)w - 1)) hi = lo;     // no valid window ends here
-        uint64_t l = s0; const long long need = lo - w;
-        while (l > ws && (long long)step_base[l] > need) --l;
-        uint64_t r = s1 - 1; const long long last = min(b1 + k - 2, len - 1);
-        while (r + 1 < we && (long long)step_base[r + 1] <= last) ++r;
-        L = (uint32_t)l; R = (uint32_t)r;
+    // the warp probes 32 candidate steps at a time (the context usually spans one to three steps: one round each way)
+    const long long lo = step_base[s0];
+    const long long b1 = s1 < we ? (long long)step_base[s1] : len;
+    long long hi = min(b1, len - k + 1);
+    if (len < (long long)w + k - 1 || hi <= max(lo, (long long)w - 1)) hi = lo;         // no valid window ends here
+    uint32_t L, R;
+    {   // L: going down from s0, the first step l with l == ws or step_base[l] <= lo - w
+        const long long need = lo - w;
+        uint64_t top = s0;
+        for (;;) {
+            const bool in = top >= ws + (uint64_t)lane;
+            const uint64_t l = top - lane;
+            const bool stop = !in || l == ws || (long long)step_base[l] <= need;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, stop);
+            if (b) { L = (uint32_t)(top - (__ffs(b) - 1)); break; }
+            top -= 32;
+        }
     }
-    L = __shfl_sync(0xFFFFFFFFu, L, 0); R = __shfl_sync(0xFFFFFFFFu, R, 0);
-    lo = __shfl_sync(0xFFFFFFFFu, lo, 0); hi = __shfl_sync(0xFFFFFFFFu, hi, 0);
+    {   // R: going up from s1 - 1, the first step r with r + 1 == we or step_base[r + 1] > last
+        const long long last = min(b1 + k - 2, len - 1);
+        uint64_t bot = s1 - 1;
+        for (;;) {
+            const uint64_t r = bot + lane;
+            const bool stop = r + 1 >= we || (long long)step_base[r + 1] > last;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, stop);
+            if (b) { R = (uint32_t)(bot + (__ffs(b) - 1)); break; }
+            bot += 32;
+        }
+    }
     uint64_t h1 = 0, h2 = 0;
     if (hi > lo) {
         for (uint32_t i = L + lane; i <= R; i += 32) {

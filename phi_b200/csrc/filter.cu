@@ -84,8 +84,8 @@ __global__ void count_drops_kernel(const uint8_t *rank_drop, uint32_t n, unsigne
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t v = i < n ? rank_drop[i] : 0;
-    uint32_t b = __ballot_sync(0xFFFFFFFFu, v != 0);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&ctr[CTR_FILTERED], (unsigned long long)__popc(b));
+    const int c = __syncthreads_count(v != 0);
+    if (threadIdx.x == 0 && c) atomicAdd(&ctr[CTR_FILTERED], (unsigned long long)c);
 }
 
 // ---- the -d1 statistic (/root/reference/src/ILP_index.cpp:565-606): (hash, walk) pairs sorted by hash, walks ascending inside

@@ -23,6 +23,9 @@ namespace phi {
 
 constexpr uint32_t C_NONE = 0xFFFFFFFFu;
 constexpr int SORT_WARPS = 4;                    // warps per block of the sorted-copy kernels
+constexpr uint32_t G_DROPPED = 0xFFFFFFFFu;      // g_rep of a group whose rank was dropped (set once the groups are compacted)
+constexpr uint32_t SUB_REP_BIT = 0x80000000u;    // hit_sub: this hit represents its group (writes the vertex list)
+constexpr int GROUPS_PER_WARP = 16;              // group_members_kernel: groups per warp (one histogram flush per block)
 
 // ---- src[0, n) -> dst[0, n) ascending (+ add), values < n_vals, one warp.  sorted: plain copy.  cnt: n_vals shared counters of
 // this warp (counting sort), or nullptr (rank sort, quadratic: only for walk counts beyond SORT_VALS_MAX).
@@ -104,23 +107,30 @@ cudaError_t chunk_members(const ChunkTable &C, uint32_t n_walks, uint32_t *cm_of
 // ------------------------------------------------------------------ surviving groups
 // A group is represented by the hit that claimed its slot.  flags[i] = 1 for the representing hit of a group whose rank survives;
 // totals of groups / members / vertices go to the counter block.
-__global__ void group_flags_kernel(FilterArgs A, FilterWork W, uint32_t *flags)
+__global__ void __launch_bounds__(256) group_flags_kernel(FilterArgs A, FilterWork W, uint32_t *flags)
 {
+    __shared__ unsigned long long s_tot[3];
+    if (threadIdx.x < 3) s_tot[threadIdx.x] = 0;
+    __syncthreads();
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint32_t f = 0; unsigned long long members = 0, vtx = 0;
     if (i < A.n_hits) {
         const uint32_t slot = W.hit_slot[i];
-        if (W.g_rep[slot] == (uint32_t)i && !W.rank_drop[A.hit_rank[i]]) { f = 1; members = W.g_cnt[slot]; vtx = A.hit_nv[i]; }
+        if (W.g_rep[slot] == (uint32_t)i) {
+            if (!W.rank_drop[A.hit_rank[i]]) { f = 1; members = W.g_cnt[slot]; vtx = A.hit_nv[i]; }
+            else W.g_rep[slot] = G_DROPPED;                              // the other hits of the slot only ever compare it with their own id
+        }
         flags[i] = f;
     }
     const uint32_t b = __ballot_sync(0xFFFFFFFFu, f != 0);
-    if (!b) return;
-    #pragma unroll
-    for (int d = 16; d; d >>= 1) { members += __shfl_xor_sync(0xFFFFFFFFu, members, d); vtx += __shfl_xor_sync(0xFFFFFFFFu, vtx, d); }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&W.ctr[CTR_OUT_GROUPS], (unsigned long long)__popc(b));
-        atomicAdd(&W.ctr[CTR_SURVIVORS], members);
-        atomicAdd(&W.ctr[CTR_SURV_VTX], vtx);
+    if (b) {
+        #pragma unroll
+        for (int d = 16; d; d >>= 1) { members += __shfl_xor_sync(0xFFFFFFFFu, members, d); vtx += __shfl_xor_sync(0xFFFFFFFFu, vtx, d); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_tot[0], (unsigned long long)__popc(b)); atomicAdd(&s_tot[1], members); atomicAdd(&s_tot[2], vtx); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_tot[0]) {
+        atomicAdd(&W.ctr[CTR_OUT_GROUPS], s_tot[0]); atomicAdd(&W.ctr[CTR_SURVIVORS], s_tot[1]); atomicAdd(&W.ctr[CTR_SURV_VTX], s_tot[2]);
     }
 }
 __global__ void group_emit_kernel(FilterArgs A, const uint32_t *flags, const uint32_t *pos, uint32_t *keys, uint32_t *vals)
@@ -153,6 +163,7 @@ __global__ void group_sizes_kernel(FilterArgs A, FilterWork W, const uint32_t *o
     const uint8_t nv = A.hit_nv[i];
     cnt_out[j] = W.g_cnt[slot]; nv_out[j] = nv; group_len[j] = nv;
     W.g_rep[slot] = j;
+    W.hit_sub[i] |= SUB_REP_BIT;
     const int64_t r = A.hit_rank[i], rp = j ? (int64_t)A.hit_rank[order[j - 1]] : -1;
     for (int64_t q = rp + 1; q <= r; ++q) rank_off[q] = j;
     if (j == n - 1) for (int64_t q = r + 1; q <= (int64_t)A.n_ranks; ++q) rank_off[q] = n;
@@ -165,14 +176,15 @@ __global__ void __launch_bounds__(256) group_fill_kernel(FilterArgs A, FilterWor
     const uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 3;
     const uint32_t sub = threadIdx.x & 7;
     if (i >= A.n_hits) return;
-    if (W.rank_drop[A.hit_rank[i]]) return;
-    const uint32_t j = W.g_rep[W.hit_slot[i]];
+    const uint32_t j = W.g_rep[W.hit_slot[i]];                            // output index of the hit's group
+    if (j == G_DROPPED) return;
     const uint32_t c = A.hit_walk[i];                                     // hits of representatives: the chunk takes the place of the walk
-    const uint32_t n = G.cm_off[c + 1] - G.cm_off[c];
-    const uint32_t *src = G.cm_walk + G.cm_off[c];
-    uint32_t *dst = G.members_tmp + G.member_off[j] + W.hit_sub[i];
+    const uint32_t s0 = G.cm_off[c], n = G.cm_off[c + 1] - s0;
+    const uint32_t hs = W.hit_sub[i];
+    const uint32_t *src = G.cm_walk + s0;
+    uint32_t *dst = G.members_tmp + G.member_off[j] + (hs & ~SUB_REP_BIT);
     for (uint32_t q = sub; q < n; q += 8) dst[q] = src[q];
-    if (G.order[j] == (uint32_t)i) {
+    if (hs & SUB_REP_BIT) {
         const int32_t *p = A.vtx_pool + A.hit_voff[i];
         int32_t *o = G.group_vtx + G.vtx_off[j];
         const uint32_t nv = A.hit_nv[i];
@@ -189,13 +201,13 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) group_members_kernel(FilterAr
     uint32_t *s_cnt = s_mem + (use_hist ? n_walks_out : 0);               // [SORT_WARPS][n_vals] when use_cnt
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (use_hist) { for (uint32_t q = threadIdx.x; q < n_walks_out; q += blockDim.x) s_hist[q] = 0; __syncthreads(); }
-    const uint32_t j = blockIdx.x * SORT_WARPS + wid;
-    if (j < n_groups) {
+    unsigned long long *g_hist = G.anchors_per_walk;
+    auto hist = [&](uint32_t v, uint32_t cnt) { if (use_hist) atomicAdd(&s_hist[v], cnt); else atomicAdd(&g_hist[v], (unsigned long long)cnt); };
+    const uint32_t j0 = (blockIdx.x * SORT_WARPS + wid) * GROUPS_PER_WARP;
+    for (uint32_t j = j0; j < j0 + GROUPS_PER_WARP && j < n_groups; ++j) {
         const uint32_t i = G.order[j], off = G.member_off[j], n = G.member_off[j + 1] - off;
         const uint32_t c = A.hit_walk[i];
         const bool single = G.cm_off[c + 1] - G.cm_off[c] == n;            // one part: the chunk's member list, already ascending
-        unsigned long long *g_hist = G.anchors_per_walk;
-        auto hist = [&](uint32_t v, uint32_t cnt) { if (use_hist) atomicAdd(&s_hist[v], cnt); else atomicAdd(&g_hist[v], (unsigned long long)cnt); };
         warp_sorted_copy(G.members_tmp + off, (uint32_t *)G.member_walk + off, n, single, n_vals, G.walk_id_base,
                          use_cnt ? s_cnt + (size_t)wid * n_vals : nullptr, lane, hist);
     }
@@ -222,7 +234,7 @@ cudaError_t groups_fill(const FilterArgs &A, const FilterWork &W, const GroupOut
     PHI_LAUNCH_CHECK();
     const int use_cnt = n_walks_local <= SORT_VALS_MAX, use_hist = n_walks_out <= GROUP_HIST_MAX;
     const size_t smem = ((use_hist ? (size_t)n_walks_out : 0) + (use_cnt ? (size_t)SORT_WARPS * n_walks_local : 0)) * 4;
-    group_members_kernel<<<(n_groups + SORT_WARPS - 1) / SORT_WARPS, SORT_WARPS * 32, smem, st>>>(A, W, G, n_groups, n_walks_local, use_cnt, n_walks_out, use_hist);
+    group_members_kernel<<<(n_groups + SORT_WARPS * GROUPS_PER_WARP - 1) / (SORT_WARPS * GROUPS_PER_WARP), SORT_WARPS * 32, smem, st>>>(A, W, G, n_groups, n_walks_local, use_cnt, n_walks_out, use_hist);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

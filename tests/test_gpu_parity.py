@@ -250,3 +250,18 @@ def test_baseline_config4_shape_500_haplotypes(gpu):
     sg = synth.make_graph(0x50484931 + 4, 40_000, 500, founders=32, block_sites=100)
     rd = synth.make_reads(0x50484931 + 4, sg, 30.0)
     assert_same_result(phi_io.oracle_index(sg.graph, rd), gpu.run(sg.graph, rd))
+
+
+@pytest.mark.parametrize("n_haps", [2500, 4500])
+def test_many_walks_group_members(gpu, n_haps):
+    """More walks than the shared-memory paths of the grouped result hold (member merge by counting sort up to 2048 walks,
+    block-local anchors-per-walk histogram up to 4096): the quadratic merge and the global histogram give the same result."""
+    sg = synth.make_graph(900 + n_haps, 3_000, n_haps, founders=12, block_sites=20)
+    rd = synth.make_reads(900 + n_haps, sg, 20.0)
+    for T in (1.0, 0.4):
+        want = phi_io.oracle_index(sg.graph, rd, 31, 25, T)
+        got = gpu.run(sg.graph, rd, 31, 25, T)
+        assert_same_result(want, got)
+    assert got.n_groups < got.n_anchors                                   # the lists are shared between walks
+    # the members of every group ascend (checked on the raw arrays by result_to_py); most groups have several parts here
+    assert int(np.diff(got.group_member_off.astype(np.int64)).max()) > 32
