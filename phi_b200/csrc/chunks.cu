@@ -60,15 +60,30 @@ __device__ __forceinline__ uint32_t walk_of_step(const uint64_t *walk_off, uint3
     return lo;
 }
 
-// The steps [s0, s1] of one block mostly lie in one walk: thread 0 looks the two ends up once, the block shares the answer and
+// last h in [0, n_walks) with walk_off[h] <= s, by one warp: 32 evenly spaced probes per round
+__device__ __forceinline__ uint32_t walk_of_step_warp(const uint64_t *walk_off, uint32_t n_walks, uint64_t s, int lane)
+{
+    uint32_t lo = 0, hi = n_walks;                                   // walk_off[lo] <= s, walk_off[hi] > s (hi == n_walks: virtual)
+    while (hi - lo > 1) {
+        const uint32_t step = (hi - lo + 31) / 32;
+        const uint64_t idx = (uint64_t)lo + (uint64_t)(lane + 1) * step;
+        const bool le = idx < hi && walk_off[idx] <= s;              // monotone over the lanes
+        const uint32_t c = __popc(__ballot_sync(0xFFFFFFFFu, le));
+        lo += c * step;
+        hi = min(hi, lo + step);
+    }
+    return lo;
+}
+// The steps [s0, s1] of one block mostly lie in one walk: warps 0 and 1 look the two ends up, the block shares the answer and
 // only blocks that straddle a walk boundary search per thread (between the two ends).  Returns the walk of step s; ws = its first step.
 __device__ __forceinline__ uint32_t walk_of_step_block(const uint64_t *walk_off, uint32_t n_walks, uint64_t s, uint64_t s0, uint64_t s1, uint64_t &ws)
 {
     __shared__ uint32_t sh_h[2];
     __shared__ uint64_t sh_ws;
-    if (threadIdx.x == 0) {
-        const uint32_t a = walk_of_step(walk_off, n_walks, s0), b = walk_of_step(walk_off, n_walks, s1);
-        sh_h[0] = a; sh_h[1] = b; sh_ws = walk_off[a];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (wid < 2) {
+        const uint32_t a = walk_of_step_warp(walk_off, n_walks, wid ? s1 : s0, lane);
+        if (lane == 0) { sh_h[wid] = a; if (!wid) sh_ws = walk_off[a]; }
     }
     __syncthreads();
     uint32_t lo = sh_h[0], hi = sh_h[1];
@@ -204,8 +219,9 @@ __global__ void __launch_bounds__(256) chunk_key_kernel(ChunkTable C, const uint
     if (hi > lo) {
         for (uint32_t i = L + lane; i <= R; i += 32) {
             const uint64_t x = walk_vtx[i], idx = i - L;
-            h1 += cmix(x * 0x9E3779B97F4A7C15ull + idx * 0xD6E8FEB86659FD93ull + 0x2545F4914F6CDD1Dull);
-            h2 += cmix((x + 0x632BE59BD9B4E019ull) * 0xBF58476D1CE4E5B9ull ^ (idx + 1) * 0x94D049BB133111EBull);
+            const uint64_t m = cmix(((x + 1) << 32 | (idx + 1)) * 0x9E3779B97F4A7C15ull);
+            h1 += m;
+            h2 += (uint64_t)((uint32_t)(m >> 32) * 0x85EBCA6Bu + (uint32_t)idx) * (uint64_t)((uint32_t)m | 1u);   // a second, differently weighted sum
         }
         #pragma unroll
         for (int d = 16; d; d >>= 1) { h1 += __shfl_xor_sync(0xFFFFFFFFu, h1, d); h2 += __shfl_xor_sync(0xFFFFFFFFu, h2, d); }

@@ -10,7 +10,7 @@
 // Device formulation:
 //   1. group table  : open addressing over (rank, vertex list) -> count, exact (lists are compared,
 //                     the hash only picks the start slot).
-//   2. mark         : a slot whose count reaches the threshold drops its rank.
+//   2. mark         : the addition that takes a slot's count to the threshold drops its rank (inside the group count kernel).
 //   3. survivors    : the hits of the representative chunks are instantiated for every member chunk (chunks.cu) in
 //                     (walk, position) order, then a stable radix sort on the rank alone gives (rank, walk, position).
 //   4. multi-hit fix: only (rank, walk) groups with >= 2 hits need the decimal-string key order;
@@ -65,27 +65,18 @@ __global__ void group_count_kernel(FilterArgs A, FilterWork W)
             const uint32_t before = atomicAdd(&W.g_cnt[slot], wt);
             W.hit_slot[i] = (uint32_t)slot;
             if (W.hit_sub) W.hit_sub[i] = before;
+            // anchor.second.first >= threshold * num_walks — int32 promoted to float (:698).  Counts only grow, so the group ends
+            // at or above the threshold iff some addition lands there: that thread drops the rank (and counts it once).
+            if (W.mark_inline && (float)(int32_t)(before + wt) >= A.thr) {
+                const uint32_t r = A.hit_rank[i], bit = 1u << (8 * (r & 3u));
+                const uint32_t old = atomicOr((uint32_t *)(W.rank_drop + (r & ~3u)), bit);
+                if (!(old & bit)) atomicAdd(&W.ctr[CTR_FILTERED], 1ull);
+            }
             return;
         }
         slot = (slot + 1) & mask;
     }
     W.ctr[CTR_GROUP_OVERFLOW] = 1;
-}
-
-__global__ void mark_drop_kernel(FilterArgs A, FilterWork W)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= A.n_hits) return;
-    // anchor.second.first >= threshold * num_walks  — int32 promoted to float (:698)
-    if ((float)(int32_t)W.g_cnt[W.hit_slot[i]] >= A.thr) W.rank_drop[A.hit_rank[i]] = 1;
-}
-
-__global__ void count_drops_kernel(const uint8_t *rank_drop, uint32_t n, unsigned long long *ctr)
-{
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t v = i < n ? rank_drop[i] : 0;
-    const int c = __syncthreads_count(v != 0);
-    if (threadIdx.x == 0 && c) atomicAdd(&ctr[CTR_FILTERED], (unsigned long long)c);
 }
 
 // ---- the -d1 statistic (/root/reference/src/ILP_index.cpp:565-606): (hash, walk) pairs sorted by hash, walks ascending inside
@@ -125,18 +116,6 @@ cudaError_t filter_count_groups(const FilterArgs &A, const FilterWork &W, cudaSt
     if (!A.n_hits) return cudaSuccess;
     group_count_kernel<<<(unsigned)((A.n_hits + 255) / 256), 256, 0, st>>>(A, W);
     PHI_LAUNCH_CHECK();
-    return cudaSuccess;
-}
-cudaError_t filter_mark_drops(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches)
-{
-    if (A.n_hits) {
-        mark_drop_kernel<<<(unsigned)((A.n_hits + 255) / 256), 256, 0, st>>>(A, W);
-        PHI_LAUNCH_CHECK();
-    }
-    if (A.n_ranks) {
-        count_drops_kernel<<<(A.n_ranks + 255) / 256, 256, 0, st>>>(W.rank_drop, A.n_ranks, W.ctr);
-        PHI_LAUNCH_CHECK();
-    }
     return cudaSuccess;
 }
 __global__ void emit_rank_keys_kernel(FilterArgs A, uint32_t *keys, uint32_t *vals)

@@ -169,12 +169,12 @@ __global__ void group_sizes_kernel(FilterArgs A, FilterWork W, const uint32_t *o
     if (j == n - 1) for (int64_t q = r + 1; q <= (int64_t)A.n_ranks; ++q) rank_off[q] = n;
 }
 
-// 8 lanes per surviving hit: the member walks of its chunk go to the hit's sub-offset inside its group; the representing hit
+// 4 lanes per surviving hit: the member walks of its chunk go to the hit's sub-offset inside its group; the representing hit
 // also writes the vertex list
 __global__ void __launch_bounds__(256) group_fill_kernel(FilterArgs A, FilterWork W, GroupOut G)
 {
-    const uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 3;
-    const uint32_t sub = threadIdx.x & 7;
+    const uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 2;
+    const uint32_t sub = threadIdx.x & 3;
     if (i >= A.n_hits) return;
     const uint32_t j = W.g_rep[W.hit_slot[i]];                            // output index of the hit's group
     if (j == G_DROPPED) return;
@@ -183,12 +183,12 @@ __global__ void __launch_bounds__(256) group_fill_kernel(FilterArgs A, FilterWor
     const uint32_t hs = W.hit_sub[i];
     const uint32_t *src = G.cm_walk + s0;
     uint32_t *dst = G.members_tmp + G.member_off[j] + (hs & ~SUB_REP_BIT);
-    for (uint32_t q = sub; q < n; q += 8) dst[q] = src[q];
+    for (uint32_t q = sub; q < n; q += 4) dst[q] = src[q];
     if (hs & SUB_REP_BIT) {
         const int32_t *p = A.vtx_pool + A.hit_voff[i];
         int32_t *o = G.group_vtx + G.vtx_off[j];
         const uint32_t nv = A.hit_nv[i];
-        for (uint32_t q = sub; q < nv; q += 8) o[q] = p[q];
+        for (uint32_t q = sub; q < nv; q += 4) o[q] = p[q];
     }
 }
 
@@ -230,7 +230,7 @@ cudaError_t groups_fill(const FilterArgs &A, const FilterWork &W, const GroupOut
                         cudaStream_t st, uint64_t *launches)
 {
     if (!n_groups || !A.n_hits) return cudaSuccess;
-    group_fill_kernel<<<(unsigned)((A.n_hits * 8 + 255) / 256), 256, 0, st>>>(A, W, G);
+    group_fill_kernel<<<(unsigned)((A.n_hits * 4 + 255) / 256), 256, 0, st>>>(A, W, G);
     PHI_LAUNCH_CHECK();
     const int use_cnt = n_walks_local <= SORT_VALS_MAX, use_hist = n_walks_out <= GROUP_HIST_MAX;
     const size_t smem = ((use_hist ? (size_t)n_walks_out : 0) + (use_cnt ? (size_t)SORT_WARPS * n_walks_local : 0)) * 4;

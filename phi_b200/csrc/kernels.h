@@ -213,7 +213,8 @@ struct FilterWork {                  // device scratch, sized by the host
     uint32_t *hit_sub;                             // optional [n_hits]: the group's count before this hit was added (its sub-offset in the group)
     const uint32_t *weight;                        // optional [n_hits]: occurrences a record stands for (multi-GPU summaries)
     const uint32_t *chunk_weight;                  // optional [n_chunks]: members of the chunk hit_walk[i] names (hits of representatives)
-    uint8_t *rank_drop;                            // [n_ranks]
+    uint8_t *rank_drop;                            // [n_ranks] (4-byte aligned, padded to a multiple of 4)
+    int mark_inline;                               // the counts of this table are global: apply the threshold while counting
     uint32_t *flags;                               // [n_hits] survivor flags -> scanned
     uint64_t *keys_a, *keys_b; uint32_t *vals_a, *vals_b;   // [n_survivors]
     void *sort_scratch; void *scan_scratch;
@@ -222,7 +223,6 @@ struct FilterWork {                  // device scratch, sized by the host
 cudaError_t filter_shared_kmer_hist(const uint64_t *hash, const uint32_t *walk, uint64_t n, uint32_t n_walks, unsigned long long *hist,
                                     unsigned long long *distinct, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_count_groups(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
-cudaError_t filter_mark_drops(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
 // stable sort of the records (which arrive in (walk, position) order) on their rank: order ends up in W.vals_a
 cudaError_t filter_sort_records(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
 // by_walk != 0: order[] is sorted by (rank, walk, position) and (rank, walk) runs are re-ordered; by_walk == 0: order[] holds one

@@ -1143,9 +1143,9 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walk
     // the drop flags of all owners are then shared.  Every rank takes part in every collective, also with zero hits.
     if (ctx->world == 1) {
         if (!n) return PHI_OK;
+        W.mark_inline = 1;                                                // one GPU: the local counts are the global ones
         int rc = count_groups_adaptive(ctx, A, W, nullptr, ctx->c_ninst.as<uint32_t>(), false);
         if (rc) return rc;
-        CU(filter_mark_drops(A, W, ctx->st, &ctx->launches));
     } else {
         std::string err; NcclApi *nc = nccl_api(err);
         if (!nc || !ctx->comm) return ctx->fail(PHI_ERR_COMM, "communicator not initialised");
@@ -1177,9 +1177,9 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walk
             FilterArgs B = filter_args(ctx, rs, ctx->r_rank, ctx->r_walk, ctx->r_pos, ctx->r_voff, ctx->r_nv, ctx->r_vtx, o.n_spec, threshold, n_walks_global);
             FilterWork WB; memset(&WB, 0, sizeof(WB));
             WB.rank_drop = ctx->rank_drop.as<uint8_t>(); WB.ctr = d_ctr;
+            WB.mark_inline = 1;                                                // drops (and counts) the ranks of this owner's range
             rc = count_groups_adaptive(ctx, B, WB, ctx->r_walk.as<uint32_t>(), nullptr, true);
             if (rc) return rc;
-            CU(filter_mark_drops(B, WB, ctx->st, &ctx->launches));             // also counts the flags (all in this rank's owned range)
         }
         NC(nc->GroupStart());                                                   // share the drop flags: owner o holds the truth for its rank range
         for (int q = 0; q < Wn; ++q) {
