@@ -127,6 +127,141 @@ __global__ void __launch_bounds__(256) step_pass_kernel(const uint32_t *walk_vtx
     }
 }
 
+// ---- the same pass, the scan and the finalisation in ONE kernel (the common case: no zero-length steps).  Every tile of
+// FS_TILE steps scans (chunk flag, bases since the walk start) in registers and gets the total of the tiles before it by a
+// decoupled look-back over one 64-bit word per tile; nothing but walk_vtx is read and nothing but step_base (and the few
+// per-chunk / per-walk values) is written.  The scanned value: bits [0,35) bases since the last walk start, [35,61) chunk
+// starts, bit 61 "a walk started" (the bases of the left operand are discarded); bits 62-63 of a tile word: 1 = aggregate, 2 = prefix.
+constexpr int FS_THREADS = 256, FS_ROUNDS = 4, FS_TILE = FS_THREADS * FS_ROUNDS;
+constexpr uint64_t FS_BASES = (1ull << 35) - 1, FS_CHUNKS = ((1ull << 26) - 1) << 35, FS_RESET = 1ull << 61, FS_VALUE = (1ull << 62) - 1;
+__device__ __forceinline__ uint64_t fs_comb(uint64_t a, uint64_t b)           // a, then b
+{
+    const uint64_t chunks = ((a & FS_CHUNKS) + (b & FS_CHUNKS)) & FS_CHUNKS;
+    if (b & FS_RESET) return (b & FS_BASES) | chunks | FS_RESET;
+    return (((a & FS_BASES) + (b & FS_BASES)) & FS_BASES) | chunks | (a & FS_RESET);
+}
+__global__ void __launch_bounds__(FS_THREADS, 4) fused_steps_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
+                                                                 const uint4 *vinfo, unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base,
+                                                                 uint32_t *chunk_step, uint32_t *c_walk, uint64_t *walk_len, unsigned long long *ctr)
+{
+    __shared__ uint32_t sh_tile, sh_h[2];
+    __shared__ uint64_t sh_ws, sh_excl, sh_warp[FS_ROUNDS][FS_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sh_tile = atomicAdd(ticket, 1u);              // tiles start in order: a tile only ever waits for tiles that run
+    __syncthreads();
+    const uint32_t tile = sh_tile;
+    const uint64_t s0 = (uint64_t)tile * FS_TILE, s1 = min(s0 + FS_TILE, n_steps) - 1;
+    if (wid < 2) {                                                      // walks of the two ends of the tile
+        const uint32_t a = walk_of_step_warp(walk_off, n_walks, wid ? s1 : s0, lane);
+        if (lane == 0) { sh_h[wid] = a; if (!wid) sh_ws = walk_off[a]; }
+    }
+    __syncthreads();
+    const uint32_t h_lo = sh_h[0], h_hi = sh_h[1];
+    uint64_t inc[FS_ROUNDS]; uint32_t len[FS_ROUNDS]; uint32_t startm = 0, flagm = 0;
+    bool nonmono = false; uint32_t zeros = 0;
+    // all loads of the tile first (FS_ROUNDS independent gathers in flight per thread), then the arithmetic
+    uint32_t vtx[FS_ROUNDS], pvtx[FS_ROUNDS]; uint4 me[FS_ROUNDS], pm[FS_ROUNDS];
+    #pragma unroll
+    for (int r = 0; r < FS_ROUNDS; ++r) {
+        const uint64_t s = s0 + (uint64_t)r * FS_THREADS + threadIdx.x;
+        vtx[r] = s < n_steps ? walk_vtx[s] : 0u;
+        pvtx[r] = (lane == 0 && s < n_steps && s) ? walk_vtx[s - 1] : 0u;     // the previous step of a warp's first lane
+    }
+    #pragma unroll
+    for (int r = 0; r < FS_ROUNDS; ++r) {
+        me[r] = vinfo[vtx[r]];
+        pm[r] = lane == 0 ? vinfo[pvtx[r]] : make_uint4(0, 0, 0, 0);
+    }
+    #pragma unroll
+    for (int r = 0; r < FS_ROUNDS; ++r) {
+        const uint64_t s = s0 + (uint64_t)r * FS_THREADS + threadIdx.x;
+        const bool valid = s < n_steps;
+        if (!valid) me[r] = make_uint4(0, 0, 0, 0);
+        uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, me[r].y, 1), pt = __shfl_up_sync(0xFFFFFFFFu, me[r].z, 1);
+        if (lane == 0) { pb = pm[r].y; pt = pm[r].z; }
+        uint64_t ws = sh_ws;
+        if (h_lo != h_hi && valid) {
+            uint32_t lo = h_lo, hi = h_hi + 1;
+            while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
+            ws = walk_off[lo];
+        }
+        const bool start = valid && s == ws;
+        const bool flag = valid && (start || me[r].y != pb);
+        if (valid && !start && (int32_t)pt >= (int32_t)me[r].z) nonmono = true;
+        zeros += valid && me[r].x == 0;
+        len[r] = me[r].x; startm |= (start ? 1u : 0u) << r; flagm |= (flag ? 1u : 0u) << r;
+        uint64_t v = valid ? ((uint64_t)me[r].x | ((uint64_t)flag << 35) | (start ? FS_RESET : 0ull)) : 0ull;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v = fs_comb(o, v); }
+        inc[r] = v;
+        if (lane == 31) sh_warp[r][wid] = v;
+    }
+    if (nonmono) ctr[CTR_NONMONO] = 1;
+    const uint32_t bz = __ballot_sync(0xFFFFFFFFu, zeros != 0);
+    if (bz) { for (int d = 16; d; d >>= 1) zeros += __shfl_xor_sync(0xFFFFFFFFu, zeros, d); if (lane == 0) atomicAdd(&ctr[CTR_ZERO_STEPS], (unsigned long long)zeros); }
+    __syncthreads();
+    if (wid == 0) {
+        // exclusive prefixes of the warp totals in (round, warp) order: 32 values, one per lane
+        static_assert(FS_ROUNDS * (FS_THREADS / 32) == 32, "one warp total per lane");
+        uint64_t *flat = &sh_warp[0][0];
+        uint64_t v = flat[lane];
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v = fs_comb(o, v); }
+        const uint64_t total = __shfl_sync(0xFFFFFFFFu, v, 31);
+        uint64_t ex = __shfl_up_sync(0xFFFFFFFFu, v, 1); if (lane == 0) ex = 0;
+        flat[lane] = ex;
+        // look-back: 32 predecessors per round, nearest in lane 0
+        uint64_t excl = 0;
+        if (tile == 0) { if (lane == 0) ((volatile unsigned long long *)tile_state)[0] = (2ull << 62) | total; }
+        else {
+            if (lane == 0) ((volatile unsigned long long *)tile_state)[tile] = (1ull << 62) | total;
+            uint64_t run = 0;                                              // aggregate of the tiles already folded in (nearer than the window)
+            for (int64_t top = (int64_t)tile - 1;; top -= 32) {
+                const int64_t j = top - lane;
+                unsigned long long w = 2ull << 62;                          // before tile 0: an empty prefix
+                if (j >= 0) { do { w = ((volatile unsigned long long *)tile_state)[j]; } while (!(w >> 62)); }
+                const uint32_t pref = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 2);
+                const int stop = pref ? __ffs(pref) - 1 : 31;                // lanes 0..stop take part
+                uint64_t v2 = lane <= stop ? (w & FS_VALUE) : 0ull;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_down_sync(0xFFFFFFFFu, v2, d); if (lane + d < 32) v2 = fs_comb(o, v2); }
+                run = fs_comb(__shfl_sync(0xFFFFFFFFu, v2, 0), run);
+                if (pref) break;
+            }
+            excl = run;
+            if (lane == 0) ((volatile unsigned long long *)tile_state)[tile] = (2ull << 62) | fs_comb(excl, total);
+        }
+        if (lane == 0) sh_excl = excl;
+    }
+    __syncthreads();
+    const uint64_t excl = sh_excl;
+    #pragma unroll
+    for (int r = 0; r < FS_ROUNDS; ++r) {
+        const uint64_t s = s0 + (uint64_t)r * FS_THREADS + threadIdx.x;
+        uint64_t x = __shfl_up_sync(0xFFFFFFFFu, inc[r], 1); if (lane == 0) x = 0;
+        if (s >= n_steps) continue;
+        const uint64_t pre = fs_comb(excl, fs_comb(sh_warp[r][wid], x));    // everything before step s
+        const bool start = (startm >> r) & 1u, flag = (flagm >> r) & 1u;
+        const uint64_t before = start ? 0ull : (pre & FS_BASES);
+        uint32_t h = h_lo;
+        if (h_lo != h_hi) {                                                // rare: the tile straddles a walk boundary
+            uint32_t lo = h_lo, hi = h_hi + 1;
+            while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
+            h = lo;
+        }
+        step_base[s] = (uint32_t)before;
+        const uint32_t c = (uint32_t)((pre & FS_CHUNKS) >> 35);
+        if (flag) { chunk_step[c] = (uint32_t)s; c_walk[c] = h; }
+        if (s + 1 == n_steps || s + 1 == walk_off[h + 1]) walk_len[h] = before + len[r];
+        if (s + 1 == n_steps) chunk_step[c + (flag ? 1u : 0u)] = (uint32_t)n_steps;
+    }
+    // the chunk count is also kept by plain counting: it guards the 26-bit field of the scanned value
+    uint32_t nf = __popc(flagm);
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) nf += __shfl_xor_sync(0xFFFFFFFFu, nf, d);
+    if (lane == 0 && nf) atomicAdd(&ctr[CTR_CHUNK_FLAGS], (unsigned long long)nf);
+}
+
 // scanned[s] = (chunks before s) << STEP_BASE_BITS | (bases before s, over all walks)
 __global__ void __launch_bounds__(256) step_finalize_kernel(ChunkTable C, const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off,
                                                             uint32_t n_walks, uint64_t n_steps, uint32_t *step_base)
@@ -415,6 +550,24 @@ cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, u
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
+
+cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo,
+                             unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base, uint32_t *chunk_step, uint32_t *c_walk,
+                             uint64_t *walk_len, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
+{
+    if (!n_steps) return cudaSuccess;
+    const uint64_t nt = walk_steps_fused_tiles(n_steps);
+    cudaError_t e = cudaMemsetAsync(tile_state, 0, nt * 8, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ticket, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(walk_len, 0, (size_t)n_walks * 8, st);           // walks without steps
+    if (e != cudaSuccess) return e;
+    fused_steps_kernel<<<(unsigned)nt, FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+uint64_t walk_steps_fused_tiles(uint64_t n_steps) { return (n_steps + FS_TILE - 1) / FS_TILE; }
 
 cudaError_t walk_step_finalize(const ChunkTable &C, const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off, uint32_t n_walks,
                                uint64_t n_steps, uint32_t *step_base, uint64_t *walk_len, cudaStream_t st, uint64_t *launches)

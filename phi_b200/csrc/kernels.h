@@ -146,6 +146,13 @@ cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_o
 // per step: segment length, chunk-start flag, zero-length count, topological monotonicity -> packed[]
 cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo,
                            PackedStep *packed, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
+// step pass + scan + finalisation in one kernel (decoupled look-back; the common case without zero-length steps, which it only
+// counts): step_base, walk_len, chunk_step[0..chunks] / c_walk (both sized for n_steps + 1 chunks), ctr[CTR_CHUNK_FLAGS] = chunks.
+// tile_state: walk_steps_fused_tiles(n_steps) words.
+uint64_t walk_steps_fused_tiles(uint64_t n_steps);
+cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo,
+                             unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base, uint32_t *chunk_step, uint32_t *c_walk,
+                             uint64_t *walk_len, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 // scanned = exclusive scan of packed (as u64) -> step_base, walk_len, chunk_step / c_walk of C
 cudaError_t walk_step_finalize(const ChunkTable &C, const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off, uint32_t n_walks,
                                uint64_t n_steps, uint32_t *step_base, uint64_t *walk_len, cudaStream_t st, uint64_t *launches);

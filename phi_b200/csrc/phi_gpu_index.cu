@@ -81,6 +81,7 @@ struct phi_gpu_index_ctx {
     DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
     DevBuf anchor_off, rank_off, anchor_len, anchor_walk, anchor_vtx, apw, dbg_hist;
     // grouped result (groups.cu): member walks of the representative chunks, slot / sub-offset of every hit, group sizes and offsets
+    DevBuf fs_state;                       // ticket + one look-back word per tile of the fused step kernel
     DevBuf cm_off, cm_cursor, cm_tmp, cm_walk, hit_slot, hit_sub, hit_slot2, g_rep2, g_cnt2, grp_cnt, grp_moff, grp_voff, members_tmp;
     unsigned long long *h_ctr = nullptr;   // pinned mirror of the counter block
     // what the second stream uses instead of ctr / h_ctr / scan_scr / flags / flags64 / nv_out (swapped in by PrepScope)
@@ -130,7 +131,11 @@ extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
     ctx->device = device;
     if (const char *e_shift = getenv("PHI_GPU_CHUNK_SHIFT")) { int v = atoi(e_shift); if (v >= 4 && v <= 24) ctx->chunk_shift = v; }   // tuning only: results never depend on it
     if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
-    if ((e = cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    // the graph preparation is a chain of short memory-bound kernels with host waits in between; it runs next to the long
+    // ALU-bound read kernel.  Higher priority: its blocks are dispatched as soon as read blocks retire instead of behind them.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if ((e = cudaStreamCreateWithPriority(&ctx->st2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming);
     if ((e = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
@@ -166,7 +171,7 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
                       &ctx->s_voff, &ctx->s_nv, &ctx->s_vtx,
                       &ctx->hit_voff, &ctx->hit_nv, &ctx->hit_hash, &ctx->vtx_pool, &ctx->g_rep, &ctx->g_cnt, &ctx->rank_drop, &ctx->flags,
                       &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->big_list, &ctx->tmp_order, &ctx->nv_out,
-                      &ctx->cm_off, &ctx->cm_cursor, &ctx->cm_tmp, &ctx->cm_walk, &ctx->hit_slot, &ctx->hit_sub, &ctx->hit_slot2, &ctx->g_rep2, &ctx->g_cnt2,
+                      &ctx->fs_state, &ctx->cm_off, &ctx->cm_cursor, &ctx->cm_tmp, &ctx->cm_walk, &ctx->hit_slot, &ctx->hit_sub, &ctx->hit_slot2, &ctx->g_rep2, &ctx->g_cnt2,
                       &ctx->grp_cnt, &ctx->grp_moff, &ctx->grp_voff, &ctx->members_tmp,
                       &ctx->dbg_hist, &ctx->anchor_off, &ctx->rank_off, &ctx->anchor_len, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw};
     for (DevBuf *b : bufs) b->release();
@@ -351,18 +356,28 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     CU(ctx->scan_scr.reserve(std::max({scan_u32_to_u64_scratch((uint64_t)V + 1), scan_u32_to_u64_scratch(S + 1), (size_t)1024})));
     CU(chunk_topo_coord(ctx->top_order.as<int32_t>(), ctx->seg_off.as<uint64_t>(), V, ctx->chunk_shift, ctx->tlen.as<uint32_t>(),
                         ctx->tprefix.as<uint64_t>(), ctx->coord.as<uint4>(), ctx->scan_scr.p, d_ctr, ctx->st, &ctx->launches));
-    CU(ctx->step_len.reserve(S * 4 + 4));                               // packed steps
-    CU(ctx->gbase.reserve((S + 1) * 8));                                // their scan
+    // common case: one kernel for step lengths, chunk flags, their scan, step bases, walk lengths and the chunk starts
+    const uint64_t S0 = S;
+    CU(ctx->step_base.reserve(S * 4 + 4)); CU(ctx->walk_len.reserve((size_t)H * 8 + 8));
+    CU(ctx->chunk_step.reserve((S + 2) * 4)); CU(ctx->c_walk.reserve((S + 2) * 4));       // at most one chunk per step
+    CU(ctx->fs_state.reserve(walk_steps_fused_tiles(S) * 8 + 16));
+    CU(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, ctx->st)); CU(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, ctx->st));
+    CU(walk_steps_fused(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), ctx->fs_state.as<unsigned long long>() + 1, ctx->fs_state.as<uint32_t>(),
+                        ctx->step_base.as<uint32_t>(), ctx->chunk_step.as<uint32_t>(), ctx->c_walk.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), d_ctr,
+                        ctx->st, &ctx->launches));
+    CU(read_counters(ctx));                                             // wait 1
+    if (ctx->h_ctr[CTR_SEG_TOO_LONG]) return ctx->fail(PHI_ERR_UNSUPPORTED, "segment of 2^31 bases or more");
+    const bool fused = ctx->h_ctr[CTR_ZERO_STEPS] == 0;
     uint64_t last = 0; uint32_t NC = 0;
-    for (int attempt = 0;; ++attempt) {
+    // zero-length segments contribute no bases (ILP_index.cpp:364-381): the general path drops their steps and looks at the walks again
+    if (!fused) { CU(ctx->step_len.reserve(S * 4 + 4)); CU(ctx->gbase.reserve((S + 1) * 8)); CU(cudaMemsetAsync(d_ctr + CTR_NONMONO, 0, 8, ctx->st)); }
+    for (int attempt = 0; !fused; ++attempt) {
         CU(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, ctx->st)); CU(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, ctx->st));
         CU(walk_step_pass(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), ctx->step_len.as<PackedStep>(), d_ctr, ctx->st, &ctx->launches));
         CU(scan_packed_steps(ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), S, ctx->scan_scr.p, ctx->st, &ctx->launches));
         CU(cudaMemcpyAsync(&last, ctx->gbase.as<uint64_t>() + (S - 1), 8, cudaMemcpyDeviceToHost, ctx->st));
-        CU(read_counters(ctx));                                         // wait 1
-        if (ctx->h_ctr[CTR_SEG_TOO_LONG]) return ctx->fail(PHI_ERR_UNSUPPORTED, "segment of 2^31 bases or more");
+        CU(read_counters(ctx));
         if (!ctx->h_ctr[CTR_ZERO_STEPS] || attempt) break;
-        // zero-length segments contribute no bases (ILP_index.cpp:364-381): drop their steps and look at the walks again
         const uint64_t kept = S - ctx->h_ctr[CTR_ZERO_STEPS];
         CU(ctx->flags.reserve(S * 4 + 4)); CU(ctx->flags64.reserve((S + 1) * 8));
         CU(ctx->walk_vtx_c.reserve(kept * 4 + 4)); CU(ctx->walk_off_c.reserve(((size_t)H + 1) * 8));
@@ -372,6 +387,7 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
         CU(cudaMemsetAsync(d_ctr + CTR_NONMONO, 0, 8, ctx->st));
         if (!S) return PHI_OK;
     }
+    (void)S0;
     walks_monotone = ctx->h_ctr[CTR_NONMONO] ? 0 : 1;
     if (ctx->h_ctr[CTR_CHUNK_FLAGS] >= (1ull << (64 - STEP_BASE_BITS)))
         return ctx->fail(PHI_ERR_UNSUPPORTED, "too many walk chunks on one GPU: raise chunk_shift (phi_gpu_index_set_walk_sharing) or shard the walks");
@@ -383,10 +399,10 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     for (DevBuf *b : u32s) CU(b->reserve(((size_t)NC + 2) * 4));
     CU(ctx->c_h1.reserve(((size_t)NC + 1) * 8)); CU(ctx->c_h2.reserve(((size_t)NC + 1) * 8));
     CU(ctx->member_cnt.reserve(((size_t)NC + 2) * 4)); CU(ctx->member_off.reserve(((size_t)NC + 2) * 8));
-    CU(ctx->step_base.reserve(S * 4 + 4)); CU(ctx->walk_len.reserve((size_t)H * 8));
     ChunkTable C = chunk_table(ctx);
-    CU(walk_step_finalize(C, ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), d_walk_off, H, S, ctx->step_base.as<uint32_t>(),
-                          ctx->walk_len.as<uint64_t>(), ctx->st, &ctx->launches));
+    if (!fused)
+        CU(walk_step_finalize(C, ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), d_walk_off, H, S, ctx->step_base.as<uint32_t>(),
+                              ctx->walk_len.as<uint64_t>(), ctx->st, &ctx->launches));
     CU(cudaMemcpyAsync(h_walk_len.data(), ctx->walk_len.p, (size_t)H * 8, cudaMemcpyDeviceToHost, ctx->st));
     CU(chunk_keys(C, d_walk_vtx, d_walk_off, ctx->step_base.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), k, w, d_ctr, ctx->st, &ctx->launches));
     uint32_t tcap = 1024; while (tcap < 2 * (uint64_t)NC) tcap <<= 1;
@@ -413,7 +429,7 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     CU(ctx->tiles.reserve((size_t)ctx->n_tiles * sizeof(TileRec) + 32));
     CU(chunk_tiles(C, d_walk_off, ctx->step_base.as<uint32_t>(), w, ctx->tiles.as<TileRec>(), ctx->st, &ctx->launches));
     // member walks of every representative (the grouped result copies them instead of instantiating one record per member)
-    DevBuf *cms[] = {&ctx->cm_off, &ctx->cm_cursor, &ctx->cm_tmp, &ctx->cm_walk};
+    DevBuf *cms[] = {&ctx->fs_state, &ctx->cm_off, &ctx->cm_cursor, &ctx->cm_tmp, &ctx->cm_walk};
     for (DevBuf *b : cms) CU(b->reserve(((size_t)NC + 2) * 4));
     CU(chunk_members(C, H, ctx->cm_off.as<uint32_t>(), ctx->cm_cursor.as<uint32_t>(), ctx->cm_tmp.as<uint32_t>(), ctx->cm_walk.as<uint32_t>(),
                      ctx->scan_scr.p, ctx->st, &ctx->launches));
