@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) step_pass_kernel(const uint32_t *walk_vtx
 // decoupled look-back over one 64-bit word per tile; nothing but walk_vtx is read and nothing but step_base (and the few
 // per-chunk / per-walk values) is written.  The scanned value: bits [0,35) bases since the last walk start, [35,61) chunk
 // starts, bit 61 "a walk started" (the bases of the left operand are discarded); bits 62-63 of a tile word: 1 = aggregate, 2 = prefix.
-constexpr int FS_THREADS = 256, FS_ROUNDS = 4, FS_TILE = FS_THREADS * FS_ROUNDS;
+constexpr int FS_THREADS = 256, FS_ITEMS = 4, FS_TILE = FS_THREADS * FS_ITEMS;   // every thread owns FS_ITEMS consecutive steps
 constexpr uint64_t FS_BASES = (1ull << 35) - 1, FS_CHUNKS = ((1ull << 26) - 1) << 35, FS_RESET = 1ull << 61, FS_VALUE = (1ull << 62) - 1;
 __device__ __forceinline__ uint64_t fs_comb(uint64_t a, uint64_t b)           // a, then b
 {
@@ -141,11 +141,11 @@ __device__ __forceinline__ uint64_t fs_comb(uint64_t a, uint64_t b)           //
     return (((a & FS_BASES) + (b & FS_BASES)) & FS_BASES) | chunks | (a & FS_RESET);
 }
 __global__ void __launch_bounds__(FS_THREADS, 4) fused_steps_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
-                                                                 const uint4 *vinfo, unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base,
-                                                                 uint32_t *chunk_step, uint32_t *c_walk, uint64_t *walk_len, unsigned long long *ctr)
+                                                                    const uint4 *vinfo, unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base,
+                                                                    uint32_t *chunk_step, uint32_t *c_walk, uint64_t *walk_len, unsigned long long *ctr)
 {
     __shared__ uint32_t sh_tile, sh_h[2];
-    __shared__ uint64_t sh_ws, sh_excl, sh_warp[FS_ROUNDS][FS_THREADS / 32];
+    __shared__ uint64_t sh_ws, sh_excl, sh_warp[FS_THREADS / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) sh_tile = atomicAdd(ticket, 1u);              // tiles start in order: a tile only ever waits for tiles that run
     __syncthreads();
@@ -155,62 +155,58 @@ __global__ void __launch_bounds__(FS_THREADS, 4) fused_steps_kernel(const uint32
         const uint32_t a = walk_of_step_warp(walk_off, n_walks, wid ? s1 : s0, lane);
         if (lane == 0) { sh_h[wid] = a; if (!wid) sh_ws = walk_off[a]; }
     }
+    // the thread's steps and their vertex records (independent gathers), the record of the step before the first one
+    const uint64_t sb = s0 + (uint64_t)FS_ITEMS * threadIdx.x;
+    uint32_t vtx[FS_ITEMS];
+    if (sb + FS_ITEMS <= n_steps) { const uint4 q = *(const uint4 *)(walk_vtx + sb); vtx[0] = q.x; vtx[1] = q.y; vtx[2] = q.z; vtx[3] = q.w; }
+    else { for (int j = 0; j < FS_ITEMS; ++j) vtx[j] = sb + j < n_steps ? walk_vtx[sb + j] : 0u; }
+    static_assert(FS_ITEMS == 4, "one 16-byte load per thread");
+    uint4 me[FS_ITEMS];
+    #pragma unroll
+    for (int j = 0; j < FS_ITEMS; ++j) me[j] = vinfo[vtx[j]];
+    uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, me[FS_ITEMS - 1].y, 1), pt = __shfl_up_sync(0xFFFFFFFFu, me[FS_ITEMS - 1].z, 1);
+    if (lane == 0 && sb && sb < n_steps) { const uint4 p = vinfo[walk_vtx[sb - 1]]; pb = p.y; pt = p.z; }
     __syncthreads();
     const uint32_t h_lo = sh_h[0], h_hi = sh_h[1];
-    uint64_t inc[FS_ROUNDS]; uint32_t len[FS_ROUNDS]; uint32_t startm = 0, flagm = 0;
-    bool nonmono = false; uint32_t zeros = 0;
-    // all loads of the tile first (FS_ROUNDS independent gathers in flight per thread), then the arithmetic
-    uint32_t vtx[FS_ROUNDS], pvtx[FS_ROUNDS]; uint4 me[FS_ROUNDS], pm[FS_ROUNDS];
+    // per step: first of its walk?  starts a chunk?  -> the thread's total
+    uint32_t startm = 0, flagm = 0, zeros = 0; bool nonmono = false;
+    uint64_t tot = 0;
     #pragma unroll
-    for (int r = 0; r < FS_ROUNDS; ++r) {
-        const uint64_t s = s0 + (uint64_t)r * FS_THREADS + threadIdx.x;
-        vtx[r] = s < n_steps ? walk_vtx[s] : 0u;
-        pvtx[r] = (lane == 0 && s < n_steps && s) ? walk_vtx[s - 1] : 0u;     // the previous step of a warp's first lane
-    }
-    #pragma unroll
-    for (int r = 0; r < FS_ROUNDS; ++r) {
-        me[r] = vinfo[vtx[r]];
-        pm[r] = lane == 0 ? vinfo[pvtx[r]] : make_uint4(0, 0, 0, 0);
-    }
-    #pragma unroll
-    for (int r = 0; r < FS_ROUNDS; ++r) {
-        const uint64_t s = s0 + (uint64_t)r * FS_THREADS + threadIdx.x;
+    for (int j = 0; j < FS_ITEMS; ++j) {
+        const uint64_t s = sb + j;
         const bool valid = s < n_steps;
-        if (!valid) me[r] = make_uint4(0, 0, 0, 0);
-        uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, me[r].y, 1), pt = __shfl_up_sync(0xFFFFFFFFu, me[r].z, 1);
-        if (lane == 0) { pb = pm[r].y; pt = pm[r].z; }
         uint64_t ws = sh_ws;
         if (h_lo != h_hi && valid) {
             uint32_t lo = h_lo, hi = h_hi + 1;
             while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
             ws = walk_off[lo];
         }
+        const uint32_t qb = j ? me[j - 1 < 0 ? 0 : j - 1].y : pb, qt = j ? me[j - 1 < 0 ? 0 : j - 1].z : pt;
         const bool start = valid && s == ws;
-        const bool flag = valid && (start || me[r].y != pb);
-        if (valid && !start && (int32_t)pt >= (int32_t)me[r].z) nonmono = true;
-        zeros += valid && me[r].x == 0;
-        len[r] = me[r].x; startm |= (start ? 1u : 0u) << r; flagm |= (flag ? 1u : 0u) << r;
-        uint64_t v = valid ? ((uint64_t)me[r].x | ((uint64_t)flag << 35) | (start ? FS_RESET : 0ull)) : 0ull;
-        #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v = fs_comb(o, v); }
-        inc[r] = v;
-        if (lane == 31) sh_warp[r][wid] = v;
+        const bool flag = valid && (start || me[j].y != qb);
+        if (valid && !start && (int32_t)qt >= (int32_t)me[j].z) nonmono = true;
+        zeros += valid && me[j].x == 0;
+        startm |= (start ? 1u : 0u) << j; flagm |= (flag ? 1u : 0u) << j;
+        if (valid) tot = fs_comb(tot, (uint64_t)me[j].x | ((uint64_t)flag << 35) | (start ? FS_RESET : 0ull));
     }
     if (nonmono) ctr[CTR_NONMONO] = 1;
     const uint32_t bz = __ballot_sync(0xFFFFFFFFu, zeros != 0);
     if (bz) { for (int d = 16; d; d >>= 1) zeros += __shfl_xor_sync(0xFFFFFFFFu, zeros, d); if (lane == 0) atomicAdd(&ctr[CTR_ZERO_STEPS], (unsigned long long)zeros); }
+    uint64_t inc = tot;                                                 // inclusive scan of the thread totals inside the warp
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc = fs_comb(o, inc); }
+    if (lane == 31) sh_warp[wid] = inc;
+    uint64_t tex = __shfl_up_sync(0xFFFFFFFFu, inc, 1); if (lane == 0) tex = 0;   // the threads of this warp before this one
     __syncthreads();
     if (wid == 0) {
-        // exclusive prefixes of the warp totals in (round, warp) order: 32 values, one per lane
-        static_assert(FS_ROUNDS * (FS_THREADS / 32) == 32, "one warp total per lane");
-        uint64_t *flat = &sh_warp[0][0];
-        uint64_t v = flat[lane];
+        // exclusive prefixes of the warp totals, then the look-back: 32 predecessors per round, nearest in lane 0
+        constexpr int NW = FS_THREADS / 32;
+        uint64_t v = lane < NW ? sh_warp[lane] : 0ull;
         #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v = fs_comb(o, v); }
-        const uint64_t total = __shfl_sync(0xFFFFFFFFu, v, 31);
+        for (int d = 1; d < NW; d <<= 1) { const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v = fs_comb(o, v); }
+        const uint64_t total = __shfl_sync(0xFFFFFFFFu, v, NW - 1);
         uint64_t ex = __shfl_up_sync(0xFFFFFFFFu, v, 1); if (lane == 0) ex = 0;
-        flat[lane] = ex;
-        // look-back: 32 predecessors per round, nearest in lane 0
+        if (lane < NW) sh_warp[lane] = ex;
         uint64_t excl = 0;
         if (tile == 0) { if (lane == 0) ((volatile unsigned long long *)tile_state)[0] = (2ull << 62) | total; }
         else {
@@ -234,27 +230,30 @@ __global__ void __launch_bounds__(FS_THREADS, 4) fused_steps_kernel(const uint32
         if (lane == 0) sh_excl = excl;
     }
     __syncthreads();
-    const uint64_t excl = sh_excl;
+    uint64_t pre = fs_comb(sh_excl, fs_comb(sh_warp[wid], tex));         // everything before the thread's first step
+    uint32_t out[FS_ITEMS];
     #pragma unroll
-    for (int r = 0; r < FS_ROUNDS; ++r) {
-        const uint64_t s = s0 + (uint64_t)r * FS_THREADS + threadIdx.x;
-        uint64_t x = __shfl_up_sync(0xFFFFFFFFu, inc[r], 1); if (lane == 0) x = 0;
-        if (s >= n_steps) continue;
-        const uint64_t pre = fs_comb(excl, fs_comb(sh_warp[r][wid], x));    // everything before step s
-        const bool start = (startm >> r) & 1u, flag = (flagm >> r) & 1u;
+    for (int j = 0; j < FS_ITEMS; ++j) {
+        const uint64_t s = sb + j;
+        const bool start = (startm >> j) & 1u, flag = (flagm >> j) & 1u;
         const uint64_t before = start ? 0ull : (pre & FS_BASES);
-        uint32_t h = h_lo;
-        if (h_lo != h_hi) {                                                // rare: the tile straddles a walk boundary
-            uint32_t lo = h_lo, hi = h_hi + 1;
-            while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
-            h = lo;
+        out[j] = (uint32_t)before;
+        if (s < n_steps) {
+            uint32_t h = h_lo;
+            if (h_lo != h_hi) {                                            // rare: the tile straddles a walk boundary
+                uint32_t lo = h_lo, hi = h_hi + 1;
+                while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
+                h = lo;
+            }
+            const uint32_t c = (uint32_t)((pre & FS_CHUNKS) >> 35);
+            if (flag) { chunk_step[c] = (uint32_t)s; c_walk[c] = h; }
+            if (s + 1 == n_steps || s + 1 == walk_off[h + 1]) walk_len[h] = before + me[j].x;
+            if (s + 1 == n_steps) chunk_step[c + (flag ? 1u : 0u)] = (uint32_t)n_steps;
+            pre = fs_comb(pre, (uint64_t)me[j].x | ((uint64_t)flag << 35) | (start ? FS_RESET : 0ull));
         }
-        step_base[s] = (uint32_t)before;
-        const uint32_t c = (uint32_t)((pre & FS_CHUNKS) >> 35);
-        if (flag) { chunk_step[c] = (uint32_t)s; c_walk[c] = h; }
-        if (s + 1 == n_steps || s + 1 == walk_off[h + 1]) walk_len[h] = before + len[r];
-        if (s + 1 == n_steps) chunk_step[c + (flag ? 1u : 0u)] = (uint32_t)n_steps;
     }
+    if (sb + FS_ITEMS <= n_steps) *(uint4 *)(step_base + sb) = make_uint4(out[0], out[1], out[2], out[3]);
+    else { for (int j = 0; j < FS_ITEMS; ++j) if (sb + j < n_steps) step_base[sb + j] = out[j]; }
     // the chunk count is also kept by plain counting: it guards the 26-bit field of the scanned value
     uint32_t nf = __popc(flagm);
     #pragma unroll
