@@ -302,7 +302,7 @@ def main_gpu(args):
                          "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_launch"], "kernel_ms": kernels[dom]["kernel_ms"],
                          "kernels": kernels,
                          "sharing": dict(share, path_kmer_positions=res.path_kmer_positions, unique_fraction=frac_unique),
-                         "note": "both sketch kernels are integer-issue bound (~10 warp instructions per sketched k-mer vs a few bytes "
+                         "note": "both sketch kernels are integer-issue bound (~7 warp instructions per sketched k-mer, ALU pipe 60-72 % busy, vs a few bytes "
                                  "of compulsory traffic), so their HBM fraction is low by construction (ncu: DRAM traffic per launch in "
                                  "'traffic'). walk_sketch_kernel: 'achieved' counts the algorithmic bytes of ALL path k-mers the launch "
                                  "accounts for; identical walk chunks are sketched once (sharing.unique_fraction), 'achieved_physical' "

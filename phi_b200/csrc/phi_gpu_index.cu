@@ -131,11 +131,9 @@ extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
     ctx->device = device;
     if (const char *e_shift = getenv("PHI_GPU_CHUNK_SHIFT")) { int v = atoi(e_shift); if (v >= 4 && v <= 24) ctx->chunk_shift = v; }   // tuning only: results never depend on it
     if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
-    // the graph preparation is a chain of short memory-bound kernels with host waits in between; it runs next to the long
-    // ALU-bound read kernel.  Higher priority: its blocks are dispatched as soon as read blocks retire instead of behind them.
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if ((e = cudaStreamCreateWithPriority(&ctx->st2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    // (a higher priority for this stream was tried: the preparation then finishes earlier but the read kernel, which fills every SM,
+    // is slowed by exactly as much: the two together take the sum of their times either way)
+    if ((e = cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming);
     if ((e = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
