@@ -89,13 +89,14 @@ typedef struct {
  *     The result keeps exactly that form: the groups of rank r are [rank_off[r], rank_off[r + 1]) in the reference's key
  *     order; group g has group_len[g] vertices (1..k), the lists lie back to back in group_vtx in group order, and its
  *     members are the walks member_walk[group_member_off[g] .. group_member_off[g + 1]) in ascending order (a walk occurs
- *     twice when it carries the list twice).  One forward pass
+ *     twice when it carries the list twice); member_walk is member_walk16 (u16 walk ids, half the bytes over PCIe) when
+ *     n_walks <= 65536, else member_walk32.  One forward pass
  *         for r: for g in groups(r): for h in members(g): Anchor_hits[r][h].push_back(list(g))
  *     rebuilds the reference's nested vectors exactly (integration/phi_adapter.hpp) — it is the loop at :700-709.
  *     n_anchors = number of members = anchors in Anchor_hits.  The form is compact on purpose: the result crosses PCIe, and
  *     with h haplotypes the per-anchor form would repeat every vertex list up to h times.
  *     Sketch-only results (phi_gpu_index_sketch_walks): one group per emitted minimizer in (walk, path position) order,
- *     rank_off == NULL, group_member_off == NULL (group g has the single member member_walk[g]).
+ *     rank_off == NULL, group_member_off == NULL (group g has the single member member_walk32[g]).
  * minimizers_per_walk : kmer_index[h].size(), log line ILP_index.cpp:563.
  * anchors_per_walk    : log lines ILP_index.cpp:725-735.
  * n_filtered          : filtered_kmers, ILP_index.cpp:719-721 (log :738-743).
@@ -115,7 +116,8 @@ typedef struct {
     const uint8_t *group_len;            /* [n_groups] */
     const int32_t *group_vtx;            /* [n_group_vtx] */
     const uint32_t *group_member_off;    /* [n_groups + 1]; NULL for sketch-only results (one member per group) */
-    const int32_t *member_walk;          /* [n_anchors] */
+    const uint16_t *member_walk16;       /* [n_anchors] when n_walks <= 65536 (and not sketch-only), else NULL */
+    const int32_t *member_walk32;        /* [n_anchors] otherwise; exactly one of the two is non-NULL */
     const uint64_t *minimizers_per_walk; /* [n_walks] */
     const uint64_t *anchors_per_walk;    /* [n_walks] */
     /* work counters of this run (for throughput / roofline arithmetic) */

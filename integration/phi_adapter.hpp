@@ -81,7 +81,7 @@ inline void run_front_end(ILP_index &ix, std::vector<std::pair<std::string, std:
         for (uint32_t g = res->rank_off[r]; g < res->rank_off[r + 1]; ++g) {
             const std::vector<int32_t> list(vtx, vtx + res->group_len[g]);
             for (uint32_t m = res->group_member_off[g]; m < res->group_member_off[g + 1]; ++m)
-                Anchor_hits[r][res->member_walk[m]].push_back(list);
+                Anchor_hits[r][res->member_walk16 ? (int32_t)res->member_walk16[m] : res->member_walk32[m]].push_back(list);
             vtx += res->group_len[g];
         }
 

@@ -13,6 +13,7 @@ PHI_ERR_ARG, PHI_ERR_UNSUPPORTED, PHI_ERR_CUDA, PHI_ERR_NOMEM, PHI_ERR_COMM = 1,
 PHI_COMM_ID_BYTES = 128
 
 u8p, u32p, i32p, u64p = (C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64))
+u16p = C.POINTER(C.c_uint16)
 
 
 class GraphView(C.Structure):
@@ -32,7 +33,7 @@ class IndexResult(C.Structure):
     _fields_ = [("count_sp_r", C.c_int32), ("n_walks", C.c_uint32), ("n_filtered", C.c_int64),
                 ("n_anchors", C.c_uint64), ("n_groups", C.c_uint64), ("n_group_vtx", C.c_uint64),
                 ("spectrum", u64p), ("rank_off", u32p), ("group_len", u8p), ("group_vtx", i32p),
-                ("group_member_off", u32p), ("member_walk", i32p),
+                ("group_member_off", u32p), ("member_walk16", u16p), ("member_walk32", i32p),
                 ("minimizers_per_walk", u64p), ("anchors_per_walk", u64p),
                 ("read_kmer_positions", C.c_uint64), ("path_kmer_positions", C.c_uint64),
                 ("read_minimizers_emitted", C.c_uint64), ("path_minimizers_emitted", C.c_uint64),
@@ -164,6 +165,7 @@ class IndexResultPy:
     group_vtx: np.ndarray = None
     group_member_off: np.ndarray = None
     member_walk: np.ndarray = None
+    member_walk_bytes: int = 4
 
     @property
     def n_anchors(self):
@@ -173,7 +175,7 @@ class IndexResultPy:
         """Bytes of the C result arrays (what crosses PCIe): spectrum, rank_off, group_len, group_vtx, group_member_off,
         member_walk, per-walk counters."""
         ns, ng = self.count_sp_r, self.n_groups
-        return 8 * ns + 4 * (ns + 1) + ng + 4 * len(self.group_vtx) + 4 * (ng + 1) + 4 * len(self.member_walk) + 16 * self.n_walks
+        return 8 * ns + 4 * (ns + 1) + ng + 4 * len(self.group_vtx) + 4 * (ng + 1) + self.member_walk_bytes * len(self.member_walk) + 16 * self.n_walks
 
     def anchors(self):
         """[(rank, walk, [vertices])] in final order."""
@@ -213,7 +215,8 @@ def result_to_py(res: IndexResult) -> IndexResultPy:
     rank_off = _np_from(res.rank_off, ns + 1 if res.rank_off else 0, np.uint32)
     group_len = _np_from(res.group_len, ng, np.uint8)
     group_vtx = _np_from(res.group_vtx, nv, np.int32)
-    member_walk = _np_from(res.member_walk, na, np.int32)
+    walk_bytes = 2 if res.member_walk16 else 4
+    member_walk = _np_from(res.member_walk16, na, np.uint16).astype(np.int32) if res.member_walk16 else _np_from(res.member_walk32, na, np.int32)
     if not have:                                               # counters only (run_resident without download)
         ng = 0
     if res.group_member_off:
@@ -257,4 +260,4 @@ def result_to_py(res: IndexResult) -> IndexResultPy:
         n_walk_kmers=int(res.n_walk_kmers),
         shared_kmer_hist=_np_from(res.shared_kmer_hist, nw + 1, np.uint64) if res.shared_kmer_hist else None,
         n_groups=int(ng), group_rank=group_rank, group_len=group_len, group_vtx=group_vtx, group_member_off=member_off,
-        member_walk=member_walk)
+        member_walk=member_walk, member_walk_bytes=walk_bytes)

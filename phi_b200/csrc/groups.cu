@@ -16,6 +16,7 @@
 //                                        base of this GPU and counts the anchors per walk
 #include "kernels.h"
 #include "device_common.cuh"
+#include <algorithm>
 
 namespace phi {
 
@@ -27,38 +28,33 @@ constexpr uint32_t G_DROPPED = 0xFFFFFFFFu;      // g_rep of a group whose rank 
 constexpr uint32_t SUB_REP_BIT = 0x80000000u;    // hit_sub: this hit represents its group (writes the vertex list)
 constexpr int GROUPS_PER_WARP = 16;              // group_members_kernel: groups per warp (one histogram flush per block)
 
-// ---- src[0, n) -> dst[0, n) ascending (+ add), values < n_vals, one warp.  sorted: plain copy.  cnt: n_vals shared counters of
-// this warp (counting sort), or nullptr (rank sort, quadratic: only for walk counts beyond SORT_VALS_MAX).
-template <class Hist>
-__device__ __forceinline__ void warp_sorted_copy(const uint32_t *src, uint32_t *dst, uint32_t n, bool sorted, uint32_t n_vals, uint32_t add,
+// ---- src[0, n) -> dst[0, n) ascending (+ add), values < n_vals, one warp.  sorted: plain copy.  Otherwise a counting sort over
+// the warp's cnt[min(n_vals, SORT_VALS_MAX)] shared counters, one pass per range of SORT_VALS_MAX values.
+template <class OutT, class Hist>
+__device__ __forceinline__ void warp_sorted_copy(const uint32_t *src, OutT *dst, uint32_t n, bool sorted, uint32_t n_vals, uint32_t add,
                                                  uint32_t *cnt, int lane, Hist hist)
 {
     if (sorted || n < 2) {
-        for (uint32_t i = lane; i < n; i += 32) { const uint32_t v = src[i] + add; dst[i] = v; hist(v, 1u); }
+        for (uint32_t i = lane; i < n; i += 32) { const uint32_t v = src[i] + add; dst[i] = (OutT)v; hist(v, 1u); }
         return;
     }
-    if (cnt) {
-        for (uint32_t v = lane; v < n_vals; v += 32) cnt[v] = 0;
+    uint32_t base = 0;
+    for (uint32_t r0 = 0; r0 < n_vals && base < n; r0 += SORT_VALS_MAX) {
+        const uint32_t span = min(n_vals - r0, SORT_VALS_MAX);
+        for (uint32_t v = lane; v < span; v += 32) cnt[v] = 0;
         __syncwarp();
-        for (uint32_t i = lane; i < n; i += 32) atomicAdd(&cnt[src[i]], 1u);
+        for (uint32_t i = lane; i < n; i += 32) { const uint32_t v = src[i] - r0; if (v < span) atomicAdd(&cnt[v], 1u); }
         __syncwarp();
-        uint32_t base = 0;
-        for (uint32_t v0 = 0; v0 < n_vals && base < n; v0 += 32) {
-            const uint32_t v = v0 + lane, c = v < n_vals ? cnt[v] : 0u;
+        for (uint32_t v0 = 0; v0 < span && base < n; v0 += 32) {
+            const uint32_t v = v0 + lane, c = v < span ? cnt[v] : 0u;
             uint32_t inc = c;
             #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
-            for (uint32_t q = 0; q < c; ++q) dst[base + inc - c + q] = v + add;
-            if (c) hist(v + add, c);
+            for (uint32_t q = 0; q < c; ++q) dst[base + inc - c + q] = (OutT)(r0 + v + add);
+            if (c) hist(r0 + v + add, c);
             base += __shfl_sync(0xFFFFFFFFu, inc, 31);
         }
         __syncwarp();
-        return;
-    }
-    for (uint32_t i = lane; i < n; i += 32) {
-        const uint32_t v = src[i]; uint32_t r = 0;
-        for (uint32_t j = 0; j < n; ++j) { const uint32_t u = src[j]; r += (u < v) || (u == v && j < i); }
-        dst[r] = v + add; hist(v + add, 1u);
     }
 }
 
@@ -74,7 +70,7 @@ __global__ void chunk_member_fill_kernel(ChunkTable C, const uint32_t *cm_off, u
     cm_tmp[cm_off[rep] + atomicAdd(&cursor[rep], 1u)] = C.c_walk[c];
 }
 __global__ void __launch_bounds__(SORT_WARPS * 32) chunk_member_sort_kernel(ChunkTable C, const uint32_t *cm_off, const uint32_t *cm_tmp, uint32_t *cm_walk,
-                                                                          uint32_t n_vals, int use_cnt)
+                                                                          uint32_t n_vals)
 {
     extern __shared__ uint32_t s_cnt[];
     const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -82,7 +78,7 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) chunk_member_sort_kernel(Chun
     if (c >= C.n_chunks) return;
     const uint32_t off = cm_off[c], n = cm_off[c + 1] - off;
     if (!n) return;
-    warp_sorted_copy(cm_tmp + off, cm_walk + off, n, false, n_vals, 0u, use_cnt ? s_cnt + (size_t)wid * n_vals : nullptr, lane, NoHist());
+    warp_sorted_copy(cm_tmp + off, cm_walk + off, n, false, n_vals, 0u, s_cnt + (size_t)wid * min(n_vals, SORT_VALS_MAX), lane, NoHist());
 }
 
 cudaError_t chunk_members(const ChunkTable &C, uint32_t n_walks, uint32_t *cm_off, uint32_t *cursor, uint32_t *cm_tmp, uint32_t *cm_walk,
@@ -97,9 +93,8 @@ cudaError_t chunk_members(const ChunkTable &C, uint32_t n_walks, uint32_t *cm_of
     if (e != cudaSuccess) return e;
     chunk_member_fill_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>(C, cm_off, cursor, cm_tmp);
     PHI_LAUNCH_CHECK();
-    const int use_cnt = n_walks <= SORT_VALS_MAX;
     chunk_member_sort_kernel<<<(unsigned)(((uint64_t)C.n_chunks + SORT_WARPS - 1) / SORT_WARPS), SORT_WARPS * 32,
-                               use_cnt ? (size_t)SORT_WARPS * n_walks * 4 : 0, st>>>(C, cm_off, cm_tmp, cm_walk, n_walks, use_cnt);
+                               (size_t)SORT_WARPS * std::min(n_walks, SORT_VALS_MAX) * 4, st>>>(C, cm_off, cm_tmp, cm_walk, n_walks);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -193,12 +188,13 @@ __global__ void __launch_bounds__(256) group_fill_kernel(FilterArgs A, FilterWor
 }
 
 // one warp per group: parts -> ascending member walks (global walk ids), anchors per walk
-__global__ void __launch_bounds__(SORT_WARPS * 32) group_members_kernel(FilterArgs A, FilterWork W, GroupOut G, uint32_t n_groups, uint32_t n_vals, int use_cnt,
+template <class OutT>
+__global__ void __launch_bounds__(SORT_WARPS * 32) group_members_kernel(FilterArgs A, FilterWork W, GroupOut G, uint32_t n_groups, uint32_t n_vals,
                                                                       uint32_t n_walks_out, int use_hist)
 {
     extern __shared__ uint32_t s_mem[];
     uint32_t *s_hist = s_mem;                                             // [n_walks_out] when use_hist
-    uint32_t *s_cnt = s_mem + (use_hist ? n_walks_out : 0);               // [SORT_WARPS][n_vals] when use_cnt
+    uint32_t *s_cnt = s_mem + (use_hist ? n_walks_out : 0);               // [SORT_WARPS][min(n_vals, SORT_VALS_MAX)]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (use_hist) { for (uint32_t q = threadIdx.x; q < n_walks_out; q += blockDim.x) s_hist[q] = 0; __syncthreads(); }
     unsigned long long *g_hist = G.anchors_per_walk;
@@ -208,8 +204,8 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) group_members_kernel(FilterAr
         const uint32_t i = G.order[j], off = G.member_off[j], n = G.member_off[j + 1] - off;
         const uint32_t c = A.hit_walk[i];
         const bool single = G.cm_off[c + 1] - G.cm_off[c] == n;            // one part: the chunk's member list, already ascending
-        warp_sorted_copy(G.members_tmp + off, (uint32_t *)G.member_walk + off, n, single, n_vals, G.walk_id_base,
-                         use_cnt ? s_cnt + (size_t)wid * n_vals : nullptr, lane, hist);
+        warp_sorted_copy(G.members_tmp + off, (OutT *)G.member_walk + off, n, single, n_vals, G.walk_id_base,
+                         s_cnt + (size_t)wid * min(n_vals, SORT_VALS_MAX), lane, hist);
     }
     if (use_hist) {
         __syncthreads();
@@ -232,9 +228,11 @@ cudaError_t groups_fill(const FilterArgs &A, const FilterWork &W, const GroupOut
     if (!n_groups || !A.n_hits) return cudaSuccess;
     group_fill_kernel<<<(unsigned)((A.n_hits * 4 + 255) / 256), 256, 0, st>>>(A, W, G);
     PHI_LAUNCH_CHECK();
-    const int use_cnt = n_walks_local <= SORT_VALS_MAX, use_hist = n_walks_out <= GROUP_HIST_MAX;
-    const size_t smem = ((use_hist ? (size_t)n_walks_out : 0) + (use_cnt ? (size_t)SORT_WARPS * n_walks_local : 0)) * 4;
-    group_members_kernel<<<(n_groups + SORT_WARPS * GROUPS_PER_WARP - 1) / (SORT_WARPS * GROUPS_PER_WARP), SORT_WARPS * 32, smem, st>>>(A, W, G, n_groups, n_walks_local, use_cnt, n_walks_out, use_hist);
+    const int use_hist = n_walks_out <= GROUP_HIST_MAX;
+    const size_t smem = ((use_hist ? (size_t)n_walks_out : 0) + (size_t)SORT_WARPS * std::min(n_walks_local, SORT_VALS_MAX)) * 4;
+    const unsigned nb = (n_groups + SORT_WARPS * GROUPS_PER_WARP - 1) / (SORT_WARPS * GROUPS_PER_WARP);
+    if (G.member_walk_bytes == 2) group_members_kernel<uint16_t><<<nb, SORT_WARPS * 32, smem, st>>>(A, W, G, n_groups, n_walks_local, n_walks_out, use_hist);
+    else group_members_kernel<uint32_t><<<nb, SORT_WARPS * 32, smem, st>>>(A, W, G, n_groups, n_walks_local, n_walks_out, use_hist);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

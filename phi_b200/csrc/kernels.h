@@ -252,7 +252,8 @@ struct GroupOut {
     const uint32_t *member_off, *vtx_off;          // [n_groups + 1]
     const uint32_t *cm_off, *cm_walk;              // member walks (local ids, ascending) of every representative chunk
     uint32_t *members_tmp;                         // [n_members] parts as the hits wrote them
-    int32_t *member_walk; int32_t *group_vtx;      // result arrays
+    void *member_walk; int member_walk_bytes;      // result: u16 walk ids when they all fit (member_walk_bytes == 2), else i32
+    int32_t *group_vtx;
     unsigned long long *anchors_per_walk;
     uint32_t walk_id_base;
 };

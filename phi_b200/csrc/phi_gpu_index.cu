@@ -296,6 +296,7 @@ namespace {
 
 struct RunOut {                    // device-side products of one run
     uint32_t n_spec = 0;
+    int member_walk_bytes = 4;
     uint64_t n_hits = 0, n_hit_vtx = 0, n_surv = 0, n_groups = 0, n_anchor_vtx = 0;   // n_hits: hits of the representative chunks
     uint64_t path_hits = 0;                                             // hits of all walks
     uint64_t read_pos = 0, path_pos = 0, read_emitted = 0, path_emitted = 0;
@@ -1099,7 +1100,8 @@ static int groups_out(phi_gpu_index_ctx *ctx, const FilterArgs &A, FilterWork &W
     GroupOut G;
     G.order = order; G.member_off = ctx->grp_moff.as<uint32_t>(); G.vtx_off = ctx->grp_voff.as<uint32_t>();
     G.cm_off = ctx->cm_off.as<uint32_t>(); G.cm_walk = ctx->cm_walk.as<uint32_t>(); G.members_tmp = ctx->members_tmp.as<uint32_t>();
-    G.member_walk = ctx->anchor_walk.as<int32_t>(); G.group_vtx = ctx->anchor_vtx.as<int32_t>();
+    G.member_walk = ctx->anchor_walk.p; G.member_walk_bytes = o.member_walk_bytes;
+    G.group_vtx = ctx->anchor_vtx.as<int32_t>();
     G.anchors_per_walk = ctx->apw.as<unsigned long long>(); G.walk_id_base = ctx->world > 1 ? ctx->walk_id_base : 0;
     CU(groups_fill(A, W, G, (uint32_t)ng, ctx->n_walks, n_walks_global, ctx->st, &ctx->launches));
     return PHI_OK;
@@ -1135,6 +1137,7 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walk
     CU(ctx->rank_off.reserve(((size_t)o.n_spec + 2) * 8));
     CU(cudaMemsetAsync(ctx->rank_off.p, 0, ((size_t)o.n_spec + 1) * 8, ctx->st));   // no anchors: every rank is empty
     o.n_surv = 0; o.n_anchor_vtx = 0; o.n_filtered = 0;
+    o.member_walk_bytes = (mode == WALK_MODE_PROBE && n_walks_global <= 65536) ? 2 : 4;
     FilterWork W; memset(&W, 0, sizeof(W));
     W.rank_drop = ctx->rank_drop.as<uint8_t>(); W.ctr = d_ctr;
     const uint64_t n = o.n_hits;                                          // hits of the representative chunks
@@ -1404,7 +1407,8 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
             if (o.n_groups) rc = download<uint32_t>(ctx, res, ctx->grp_moff.p, o.n_groups + 1, &res->group_member_off);
             else { rc = download<uint32_t>(ctx, res, nullptr, 0, &res->group_member_off); if (!rc) *(uint32_t *)res->group_member_off = 0; }
         }
-        if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_walk.p, o.n_surv, &res->member_walk);
+        if (!rc && o.member_walk_bytes == 2 && mode == WALK_MODE_PROBE) rc = download<uint16_t>(ctx, res, ctx->anchor_walk.p, o.n_surv, &res->member_walk16);
+        else if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_walk.p, o.n_surv, &res->member_walk32);
         if (!rc) rc = download<uint8_t>(ctx, res, ctx->anchor_len.p, o.n_groups, &res->group_len);
         if (!rc) rc = download<int32_t>(ctx, res, ctx->anchor_vtx.p, o.n_anchor_vtx, &res->group_vtx);
         if (!rc) rc = download<uint64_t>(ctx, res, ctx->apw.as<uint64_t>(), HG, &res->anchors_per_walk);

@@ -255,7 +255,7 @@ def test_baseline_config4_shape_500_haplotypes(gpu):
 @pytest.mark.parametrize("n_haps", [2500, 4500])
 def test_many_walks_group_members(gpu, n_haps):
     """More walks than the shared-memory paths of the grouped result hold (member merge by counting sort up to 2048 walks,
-    block-local anchors-per-walk histogram up to 4096): the quadratic merge and the global histogram give the same result."""
+    block-local anchors-per-walk histogram up to 4096): the multi-pass merge and the global histogram give the same result."""
     sg = synth.make_graph(900 + n_haps, 3_000, n_haps, founders=12, block_sites=20)
     rd = synth.make_reads(900 + n_haps, sg, 20.0)
     for T in (1.0, 0.4):
@@ -265,3 +265,17 @@ def test_many_walks_group_members(gpu, n_haps):
     assert got.n_groups < got.n_anchors                                   # the lists are shared between walks
     # the members of every group ascend (checked on the raw arrays by result_to_py); most groups have several parts here
     assert int(np.diff(got.group_member_off.astype(np.int64)).max()) > 32
+
+
+def test_more_than_65536_walks_use_32_bit_member_ids(gpu):
+    """member_walk16 holds walk ids up to 65535; beyond that the result switches to member_walk32 (and the member merge runs one
+    counting pass per 2048 walk ids)."""
+    sg = synth.make_graph(977, 600, 70000, founders=6, block_sites=8, sv_frac=0.0)
+    rd = synth.make_reads(977, sg, 30.0)
+    want = phi_io.oracle_index(sg.graph, rd, 31, 25, 1.0)
+    got = gpu.run(sg.graph, rd, 31, 25, 1.0)
+    assert_same_result(want, got)
+    assert got.member_walk_bytes == 4 and got.n_anchors > 100000 and int(got.member_walk.max()) > 65535
+    sg2 = synth.make_graph(978, 20000, 5)
+    small = gpu.run(sg2.graph, synth.make_reads(978, sg2, 5.0), 31, 25, 1.0)
+    assert small.member_walk_bytes == 2 and small.n_anchors > 0
