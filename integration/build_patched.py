@@ -18,6 +18,9 @@ SRC = os.path.join(REF, "src")
 OUT = os.path.join(ROOT, "oracle", "_ref")
 START = "std::vector<int32_t> hap_sizes(num_walks);"
 END = "(float)retained_kmers/(float)count_sp_r * 100);"
+# second variant (PHI_gpu_model): additionally the k-mer constraint block of the model construction, :782-880
+BLOCK_START = "        if (is_ilp)"
+BLOCK_END = "// print count_sp_r_ilp/count_sp_r * 100% kmer matches are in ilp"
 
 
 def main():
@@ -26,23 +29,35 @@ def main():
     e = next(i for i, l in enumerate(lines) if END in l)
     assert (s + 1, e + 1) == (543, 743), f"seam moved: {s + 1}-{e + 1}"
     inc = next(i for i, l in enumerate(lines) if '#include "ILP_index.h"' in l)
-    seam = open(os.path.join(ROOT, "integration", "seam.inc")).read().rstrip("\n").split("\n")
-    patched = lines[:inc + 1] + ['#include "phi_adapter.hpp"'] + lines[inc + 1:s] + seam + lines[e + 1:]
+    bs = next(i for i, l in enumerate(lines) if l.rstrip() == BLOCK_START)
+    be = next(i for i, l in enumerate(lines) if BLOCK_END in l) - 2                     # the closing brace of the else branch
+    assert (bs + 1, be + 1) == (782, 880) and lines[be].strip() == "}", f"model block moved: {bs + 1}-{be + 1}"
+
+    def read(name):
+        return open(os.path.join(ROOT, "integration", name)).read().rstrip("\n").split("\n")
+    variants = {
+        # the drop-in proper: only the front end is replaced
+        "PHI_gpu": (lines[:inc + 1] + ['#include "phi_adapter.hpp"'] + lines[inc + 1:s] + read("seam.inc") + lines[e + 1:], []),
+        # + the k-mer constraint block built straight from the result; test hook compiled in
+        "PHI_gpu_model": (lines[:inc + 1] + ['#include "phi_model.hpp"'] + lines[inc + 1:s] + read("seam_model.inc") + lines[e + 1:bs]
+                          + read("model_block.inc") + lines[be + 1:], ["-DPHI_ADAPTER_TESTHOOK"]),
+    }
     os.makedirs(OUT, exist_ok=True)
     flags = ["-std=c++11", "-fopenmp", "-pthread", "-O3", "-march=x86-64-v2", "-mtune=generic", "-w",
              "-I", os.path.join(ROOT, "oracle", "ref_build", "stub"), "-I", SRC, "-I", os.path.join(ROOT, "include"),
              "-I", os.path.join(ROOT, "integration")]
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    others = [os.path.join(OUT, "obj", f + ".o") for f in ("gfa-io", "gfa-base", "options", "kalloc", "misc", "sys", "MurmurHash3", "main")]
+    libdir = os.path.join(ROOT, "phi_b200")
     with tempfile.TemporaryDirectory() as tmp:
-        cpp = os.path.join(tmp, "ILP_index_gpu.cpp")
-        open(cpp, "w").write("\n".join(patched))
-        obj = os.path.join(tmp, "ILP_index_gpu.o")
-        subprocess.check_call(["g++"] + flags + ["-c", cpp, "-o", obj])
-        others = [os.path.join(OUT, "obj", f + ".o") for f in ("gfa-io", "gfa-base", "options", "kalloc", "misc", "sys", "MurmurHash3", "main")]
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
-        libdir = os.path.join(ROOT, "phi_b200")
-        subprocess.check_call(["g++"] + flags + [obj] + others + ["-o", os.path.join(OUT, "PHI_gpu"), "-L", libdir, "-lphi_gpu_index",
-                               "-Wl,-rpath,$ORIGIN/../../phi_b200", "-lm", "-lz", "-lpthread", "-ldl"])
-    print(os.path.join(OUT, "PHI_gpu"))
+        for name, (patched, extra) in variants.items():
+            cpp = os.path.join(tmp, name + ".cpp")
+            open(cpp, "w").write("\n".join(patched))
+            obj = os.path.join(tmp, name + ".o")
+            subprocess.check_call(["g++"] + flags + extra + ["-c", cpp, "-o", obj])
+            subprocess.check_call(["g++"] + flags + [obj] + others + ["-o", os.path.join(OUT, name), "-L", libdir, "-lphi_gpu_index",
+                                   "-Wl,-rpath,$ORIGIN/../../phi_b200", "-lm", "-lz", "-lpthread", "-ldl"])
+            print(os.path.join(OUT, name))
 
 
 if __name__ == "__main__":

@@ -199,3 +199,41 @@ def oracle_read_hashes(seq: bytes, k=31, w=25):
     a = _abi._np_from(hp, n, np.uint64)
     lib.phi_oracle_free(hp)
     return a
+
+
+# ---- the grouped result form (include/phi_gpu_index.h, ABI v3) derived from per-anchor results: test infrastructure for the
+# CPU tests of integration/phi_model.hpp
+def group_anchors(res):
+    """IndexResultPy with anchors in (rank, walk, j) order -> (rank_off u32, group_len u8, group_vtx i32, group_member_off u32,
+    member_walk i32): per rank the distinct vertex lists in std::map<std::string> order of "v0_v1_..._"
+    (/root/reference/src/ILP_index.cpp:680-709), per list the walks that carry it, ascending."""
+    off = res.anchor_off.astype(np.int64)
+    rank_off = np.zeros(res.count_sp_r + 1, dtype=np.uint32)
+    glen, gvtx, moff, mwalk = [], [], [0], []
+    a, na = 0, res.n_anchors
+    for r in range(res.count_sp_r):
+        groups = {}
+        while a < na and int(res.anchor_rank[a]) == r:
+            groups.setdefault(tuple(res.anchor_vtx[off[a]:off[a + 1]].tolist()), []).append(int(res.anchor_walk[a]))
+            a += 1
+        for key in sorted(groups, key=lambda t: "".join(f"{v}_" for v in t).encode()):
+            glen.append(len(key)); gvtx.extend(key)
+            mwalk.extend(sorted(groups[key])); moff.append(len(mwalk))
+        rank_off[r + 1] = len(glen)
+    return (rank_off, np.array(glen, dtype=np.uint8), np.array(gvtx, dtype=np.int32), np.array(moff, dtype=np.uint32),
+            np.array(mwalk, dtype=np.int32))
+
+
+def write_result_file(path, res, member_bytes=2):
+    """integration/phi_adapter_testhook.hpp's file format, from a per-anchor result (the oracle's)."""
+    rank_off, glen, gvtx, moff, mwalk = group_anchors(res)
+    head = np.array([res.count_sp_r, res.n_walks, res.n_filtered, len(mwalk), len(glen), len(gvtx), member_bytes], dtype=np.uint64)
+    arrays = [res.spectrum.astype(np.uint64), rank_off, glen, gvtx, moff,
+              mwalk.astype(np.uint16) if member_bytes == 2 else mwalk, res.minimizers_per_walk.astype(np.uint64),
+              res.anchors_per_walk.astype(np.uint64)]
+    with open(path, "wb") as f:
+        f.write(b"PHIRES3\0")
+        f.write(head.tobytes())
+        for a in arrays:
+            b = a.tobytes()
+            f.write(b + b"\0" * (-len(b) % 8))

@@ -1,0 +1,60 @@
+"""CPU: SURVEY 8(f) row 3 — the k-mer constraint block of the model construction built straight from the grouped result
+(integration/phi_model.hpp, replacing /root/reference/src/ILP_index.cpp:782-880).  oracle/_ref/PHI_gpu_model is the reference CLI
+with the front end AND that block replaced; here the front end's result comes from a file written from the CPU oracle's anchors
+(test hook), so only the block is under test.  The recorded model must be the unmodified reference's, byte for byte: the dump of
+oracle/_ref/PHI_ref on the same files, and for the synthetic cases also the SHA-256 tests/golden/ holds (the mhc4 fixture was
+dumped from the original .gfa.gz, whose link order the re-written GFA does not keep)."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import phi_io
+from phi_b200 import synth
+from golden_cases import Case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "oracle", "_ref", "PHI_gpu_model")
+REF = os.path.join(ROOT, "oracle", "_ref", "PHI_ref")
+
+
+def test_grouping_round_trip():
+    """group_anchors (test infrastructure) followed by the adapter's expansion gives the anchors back."""
+    from phi_b200 import _abi
+    c = Case("synth_repeats")
+    want = phi_io.oracle_index(c.graph, c.reads, c.k, c.w, 2.0)
+    rank_off, glen, gvtx, moff, mwalk = phi_io.group_anchors(want)
+    grank = np.repeat(np.arange(want.count_sp_r, dtype=np.int32), np.diff(rank_off.astype(np.int64)))
+    a_rank, a_walk, a_off, a_vtx = _abi.expand_groups(grank, glen, gvtx, moff, mwalk)
+    assert np.array_equal(a_rank, want.anchor_rank) and np.array_equal(a_walk, want.anchor_walk)
+    assert np.array_equal(a_off, want.anchor_off) and np.array_equal(a_vtx, want.anchor_vtx)
+    assert len(glen) < want.n_anchors
+
+
+@pytest.mark.parametrize("name,extra,member_bytes", [("toy_k3_w2", ["-k", "3", "-w", "2"], 2), ("synth_small", [], 2), ("synth_dirty", ["-T", "0.5"], 4),
+                                                     ("synth_repeats", ["-T", "2.0"], 2), ("synth_unchopped", [], 2), ("mhc4", [], 2)])
+def test_model_block_from_the_grouped_result_dumps_the_reference_model(tmp_path, name, extra, member_bytes):
+    if not (os.path.exists(EXE) and os.path.exists(REF)):
+        pytest.skip("oracle/_ref/PHI_gpu_model / PHI_ref not built (it is built where /root/reference exists and travels with the snapshot)")
+    c = Case(name)
+    res = phi_io.oracle_index(c.graph, c.reads, c.k, c.w, c.T)
+    gfa, fa, rf = str(tmp_path / "g.gfa"), str(tmp_path / "r.fa"), str(tmp_path / "result.bin")
+    synth.write_gfa(c.graph, gfa)
+    synth.write_fasta(c.reads, fa)
+    phi_io.write_result_file(rf, res, member_bytes)
+    for q in ("1", "0"):
+        dump = str(tmp_path / f"model_q{q}.dump")
+        env = dict(os.environ, PHI_STUB_DUMP=dump, PHI_ADAPTER_RESULT_FILE=rf)
+        p = subprocess.run([EXE, "-g", gfa, "-r", fa, "-o", dump + ".fa", "-t", "4", "-q", q] + extra, env=env, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert ("QP model started" if q == "1" else "ILP model started") in p.stderr
+        got = hashlib.sha256(open(dump, "rb").read()).hexdigest()
+        ref_dump = str(tmp_path / f"ref_q{q}.dump")
+        p = subprocess.run([REF, "-g", gfa, "-r", fa, "-o", ref_dump + ".fa", "-t", "8", "-q", q] + extra, env=dict(os.environ, PHI_STUB_DUMP=ref_dump),
+                           capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert got == hashlib.sha256(open(ref_dump, "rb").read()).hexdigest(), f"model dump differs from the reference's for -q{q}"
+        if name != "mhc4":
+            assert got == c.meta[f"model_q{q}_sha256"], f"model dump differs from the golden one for -q{q}"
