@@ -43,6 +43,14 @@ public:
             if (e.u == u && e.v == v && e.j == j) return e.idx;
         }
     }
+    int64_t find(int32_t u, int32_t v, int32_t j) const
+    {
+        for (size_t s = hash(u, v, j) & mask_;; s = (s + 1) & mask_) {
+            const Slot &e = slots_[s];
+            if (e.idx < 0) return -1;
+            if (e.u == u && e.v == v && e.j == j) return e.idx;
+        }
+    }
 private:
     struct Slot { int32_t u, v, j; int64_t idx; };
     static size_t hash(int32_t u, int32_t v, int32_t j)
@@ -65,14 +73,21 @@ private:
     std::vector<Slot> slots_; size_t mask_, used_;
 };
 
+// What the blocks share: every edge variable u_j_v_j created so far (the string map `vars` of the reference stays in step for the
+// code that is not replaced).
+struct ModelState {
+    EdgeVarTable same_walk;            // (u, v, j)  ->  variable "u_j_v_j"
+    std::vector<GRBVar> pool;          // all variables created through the tables, in creation order
+};
+
 // Replaces ILP_index.cpp:782-880.  `vars`, `Zvars`, `count_kmer_matches` are the reference's locals (:774-780).
-inline void add_kmer_constraints(GRBModel &model, const phi_index_result *res, int32_t num_walks, int32_t k_mer, bool is_ilp, bool is_mixed,
+inline void add_kmer_constraints(GRBModel &model, ModelState &st, const phi_index_result *res, int32_t num_walks, int32_t k_mer, bool is_ilp, bool is_mixed,
                                  std::map<std::string, GRBVar> &vars, std::vector<GRBVar> &Zvars, int32_t &count_kmer_matches)
 {
     fprintf(stderr, "[M::%s::%.3f*%.2f] %s model started\n", "ILP_function", realtime() - mg_realtime0, cputime() / (realtime() - mg_realtime0),
             is_ilp ? "ILP" : "QP");                                                                  // :784 / :830
-    EdgeVarTable table;
-    std::vector<GRBVar> pool;                          // edge variables in creation order
+    EdgeVarTable &table = st.same_walk;
+    std::vector<GRBVar> &pool = st.pool;               // edge variables in creation order
     std::vector<uint32_t> walk_cnt(num_walks + 1), pair_group;      // per rank: groups of every walk, in (walk, group) order
     std::vector<uint64_t> group_voff(1, 0);
     const int32_t count_sp_r = res->count_sp_r;
@@ -141,6 +156,255 @@ inline void add_kmer_constraints(GRBModel &model, const phi_index_result *res, i
             count_kmer_matches++;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The "optimized expanded graph" part of the model (the default branch, /root/reference/src/ILP_index.cpp:1201-1406): edge
+// variables without recombination, the recombination vertices w_u_v with their edges, the objective, and the flow
+// conservation constraints.  The reference keeps the expanded graph in std::map<std::string, std::vector<std::string>>
+// (new_adj, in_nodes_new) and finds every variable by a freshly concatenated name in std::map<std::string, GRBVar>; that is
+// where its 6-7 s on the README data go.  Here nodes are integers (A(v, i) = vertex v on walk i, W(u, v) = the recombination
+// vertex of the edge u -> v), adjacency lists are vectors, variables are found through integer-keyed tables, and the ONE place
+// where the reference's result depends on string order — in_nodes_new is filled by iterating new_adj in key order, so the
+// predecessors of a node come in the std::string order of their names — is reproduced by sorting every predecessor list with
+// an integer comparator that orders (v, i) / (u, v) exactly as "v_i" / "w_u_v" compare as strings.
+// Every model call is the reference's, in its order, with its names (tests/test_model_block.py, tests/test_gpu_dropin.py).
+
+// key (a, b) -> dense index (assigned in order of first appearance)
+class PairIndex {
+public:
+    PairIndex() : mask_(0), n_(0) { rehash(1u << 16); }
+    uint32_t get(uint32_t a, uint32_t b, bool *is_new = 0)
+    {
+        if ((n_ + 1) * 10 > (mask_ + 1) * 7) rehash((mask_ + 1) * 2);
+        const uint64_t key = (uint64_t)a << 32 | b;
+        size_t s = mix(key) & mask_;
+        for (;; s = (s + 1) & mask_) {
+            if (slots_[s].idx == NONE) { slots_[s].key = key; slots_[s].idx = n_; if (is_new) *is_new = true; return n_++; }
+            if (slots_[s].key == key) { if (is_new) *is_new = false; return slots_[s].idx; }
+        }
+    }
+    bool find(uint32_t a, uint32_t b, uint32_t &idx) const
+    {
+        const uint64_t key = (uint64_t)a << 32 | b;
+        for (size_t s = mix(key) & mask_;; s = (s + 1) & mask_) {
+            if (slots_[s].idx == NONE) return false;
+            if (slots_[s].key == key) { idx = slots_[s].idx; return true; }
+        }
+    }
+    uint32_t size() const { return n_; }
+private:
+    enum { NONE = 0xFFFFFFFFu };
+    struct Slot { uint64_t key; uint32_t idx; };
+    static size_t mix(uint64_t x) { x *= 0x9E3779B97F4A7C15ull; x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32; return (size_t)x; }
+    void rehash(size_t n)
+    {
+        std::vector<Slot> old; old.swap(slots_);
+        Slot e; e.key = 0; e.idx = NONE;
+        slots_.assign(n, e); mask_ = n - 1;
+        for (size_t i = 0; i < old.size(); ++i) if (old[i].idx != NONE) {
+            size_t s = mix(old[i].key) & mask_;
+            while (slots_[s].idx != NONE) s = (s + 1) & mask_;
+            slots_[s] = old[i];
+        }
+    }
+    std::vector<Slot> slots_; size_t mask_; uint32_t n_;
+};
+
+inline int dec_digits(uint32_t v) { int d = 1; while (v >= 10) { v /= 10; ++d; } return d; }
+// order of std::to_string(a) + tail_a vs std::to_string(b) + tail_b as strings, where both tails are empty (underscore == false: a
+// proper prefix sorts first) or start with '_' (underscore == true: '_' sorts after every digit, so a proper prefix sorts last)
+inline int dec_cmp(uint32_t a, uint32_t b, bool underscore)
+{
+    if (a == b) return 0;
+    const int da = dec_digits(a), db = dec_digits(b);
+    if (da == db) return a < b ? -1 : 1;
+    uint32_t x = a, y = b;
+    if (da < db) for (int i = 0; i < db - da; ++i) y /= 10; else for (int i = 0; i < da - db; ++i) x /= 10;
+    if (x != y) return x < y ? -1 : 1;
+    return ((da < db) != underscore) ? -1 : 1;          // the shorter one is a proper prefix of the longer one
+}
+
+struct XNode { uint32_t w, a, b; };                      // w == 0: A(v = a, walk = b), name "a_b";  w == 1: W(u = a, v = b), name "w_a_b"
+inline bool xnode_less(const XNode &x, const XNode &y)   // std::string order of the names
+{
+    if (x.w != y.w) return x.w < y.w;                    // digits sort before 'w'
+    if (x.a != y.a) return dec_cmp(x.a, y.a, true) < 0;  // "a_..." : the number is followed by '_'
+    return dec_cmp(x.b, y.b, false) < 0;                 // same first number: the second one ends the name
+}
+
+// Replaces ILP_index.cpp:1201-1406.  vtx_expr / obj are the reference's locals (:1163, :1197); c_1 = recombination (:776).
+inline void add_expanded_graph(GRBModel &model, ModelState &st, ILP_index &ix, bool is_mixed, int32_t c_1,
+                               std::map<std::string, GRBVar> &vars, std::vector<GRBVar> &Zvars, GRBLinExpr &vtx_expr, GRBLinExpr &obj)
+{
+    const char vtype = is_mixed ? GRB_CONTINUOUS : GRB_BINARY;
+    const int32_t num_walks = (int32_t)ix.num_walks;
+    std::vector<GRBVar> &pool = st.pool;
+    EdgeVarTable to_w, from_w;                           // (u, v, h) -> "u_h_w_u_v",  (u, v, h) -> "w_u_v_v_h"
+    PairIndex a_index, w_index;                          // A(v, i), W(u, v) -> dense ids
+    std::vector<XNode> a_node, w_node;
+    std::vector<std::vector<uint32_t> > a_adj, w_adj;    // successors; bit 31 set: a W node
+    std::vector<char> w_is_key;                          // W(u, v) has an entry in new_adj (it has successors)
+    const uint32_t WBIT = 0x80000000u;
+    struct Ids {
+        static uint32_t a(PairIndex &ai, std::vector<XNode> &nodes, std::vector<std::vector<uint32_t> > &adj, uint32_t v, uint32_t i)
+        {
+            bool is_new; const uint32_t id = ai.get(v, i, &is_new);
+            if (is_new) { XNode n; n.w = 0; n.a = v; n.b = i; nodes.push_back(n); adj.push_back(std::vector<uint32_t>()); }
+            return id;
+        }
+    };
+
+    // w/o recombination (:1202-1226)
+    for (int32_t i = 0; i < num_walks; i++) {
+        for (size_t idx = 0; idx + 1 < ix.paths[i].size(); idx++) {
+            const int32_t u = ix.paths[i][idx], v = ix.paths[i][idx + 1];
+            const uint32_t au = Ids::a(a_index, a_node, a_adj, u, i), av = Ids::a(a_index, a_node, a_adj, v, i);
+            a_adj[au].push_back(av);
+            if (st.same_walk.find_or_reserve(u, v, i, (int64_t)pool.size()) < 0) {      // variable does not exist
+                const std::string var_name = std::to_string(u) + "_" + std::to_string(i) + "_" + std::to_string(v) + "_" + std::to_string(i);
+                pool.push_back(model.addVar(0.0, 1.0, 0.0, vtype, var_name));
+                vtx_expr += 0 * pool.back();             // no need without recombination
+            }
+        }
+    }
+    if (getenv("PHI_MODEL_TIMES")) fprintf(stderr, "[phi_model] %.3f same-walk edges\n", realtime() - mg_realtime0);
+    // index of a vertex in a haplotype, last occurrence (:1229-1238)
+    PairIndex pos_index; std::vector<uint32_t> pos_of;
+    for (size_t h = 0; h < ix.paths.size(); h++)
+        for (size_t i = 0; i < ix.paths[h].size(); ++i) {
+            const uint32_t id = pos_index.get(ix.paths[h][i], (uint32_t)h);
+            if (id == pos_of.size()) pos_of.push_back((uint32_t)i); else pos_of[id] = (uint32_t)i;
+        }
+    // recombination vertices and edges (:1241-1298)
+    for (uint32_t u = 0; u < ix.adj_list.size(); u++) {
+        for (size_t q = 0; q < ix.adj_list[u].size(); ++q) {
+            const uint32_t v = ix.adj_list[u][q];
+            bool new_vertex_used = false;
+            uint32_t wid = 0;
+            std::string new_vtx;
+            for (size_t t = 0; t < ix.haps[u].size(); ++t) {
+                const uint32_t h = ix.haps[u][t];
+                uint32_t pid; int index = 0;
+                if (pos_index.find(u, h, pid)) index = (int)pos_of[pid];                 // (a missing entry reads as 0 in the reference's map)
+                if (index == (int)ix.paths[h].size() - 1 || ix.paths[h][index + 1] != v) {
+                    if (!new_vertex_used) {
+                        new_vertex_used = true;
+                        bool is_new; wid = w_index.get(u, v, &is_new);
+                        if (is_new) { XNode n; n.w = 1; n.a = u; n.b = v; w_node.push_back(n); w_adj.push_back(std::vector<uint32_t>()); w_is_key.push_back(0); }
+                        new_vtx = "w_" + std::to_string(u) + "_" + std::to_string(v);
+                    }
+                    a_adj[Ids::a(a_index, a_node, a_adj, u, h)].push_back(wid | WBIT);
+                    int64_t idx = to_w.find_or_reserve((int32_t)u, (int32_t)v, (int32_t)h, (int64_t)pool.size());
+                    if (idx < 0) {
+                        idx = (int64_t)pool.size();
+                        pool.push_back(model.addVar(0.0, 1.0, 0.0, vtype, std::to_string(u) + "_" + std::to_string(h) + "_" + new_vtx));
+                    }
+                    vtx_expr += (c_1 / 2) * pool[idx];
+                }
+            }
+            if (new_vertex_used) {
+                for (size_t t = 0; t < ix.haps[v].size(); ++t) {
+                    const uint32_t h = ix.haps[v][t];
+                    w_adj[wid].push_back(Ids::a(a_index, a_node, a_adj, v, h)); w_is_key[wid] = 1;
+                    int64_t idx = from_w.find_or_reserve((int32_t)u, (int32_t)v, (int32_t)h, (int64_t)pool.size());
+                    if (idx < 0) {
+                        idx = (int64_t)pool.size();
+                        pool.push_back(model.addVar(0.0, 1.0, 0.0, vtype, new_vtx + "_" + std::to_string(v) + "_" + std::to_string(h)));
+                    }
+                    vtx_expr += (c_1 / 2) * pool[idx];
+                }
+            }
+        }
+    }
+    if (getenv("PHI_MODEL_TIMES")) fprintf(stderr, "[phi_model] %.3f recombination edges\n", realtime() - mg_realtime0);
+    // (1 - z_i) terms, objective (:1301-1309)
+    GRBLinExpr z_expr;
+    for (size_t i = 0; i < Zvars.size(); i++) z_expr += (1 - Zvars[i]);
+    obj = vtx_expr + z_expr;
+    model.setObjective(obj, GRB_MINIMIZE);
+
+    if (getenv("PHI_MODEL_TIMES")) fprintf(stderr, "[phi_model] %.3f objective\n", realtime() - mg_realtime0);
+    // reverse adjacency (:1312-1317): the reference iterates new_adj in key order, so every predecessor list is in the string
+    // order of the predecessors' names (equal names stay together)
+    std::vector<std::vector<uint32_t> > a_in(a_node.size()), w_in(w_node.size());
+    for (uint32_t s = 0; s < a_adj.size(); ++s)
+        for (size_t q = 0; q < a_adj[s].size(); ++q) { const uint32_t t = a_adj[s][q]; if (t & WBIT) w_in[t & ~WBIT].push_back(s); else a_in[t].push_back(s); }
+    for (uint32_t s = 0; s < w_adj.size(); ++s)
+        for (size_t q = 0; q < w_adj[s].size(); ++q) a_in[w_adj[s][q]].push_back(s | WBIT);
+    struct ByName {
+        const std::vector<XNode> *an, *wn;
+        bool operator()(uint32_t x, uint32_t y) const
+        {
+            const XNode &nx = (x & 0x80000000u) ? (*wn)[x & 0x7FFFFFFFu] : (*an)[x], &ny = (y & 0x80000000u) ? (*wn)[y & 0x7FFFFFFFu] : (*an)[y];
+            return xnode_less(nx, ny);
+        }
+    } by_name; by_name.an = &a_node; by_name.wn = &w_node;
+    for (size_t t = 0; t < a_in.size(); ++t) if (a_in[t].size() > 1) std::stable_sort(a_in[t].begin(), a_in[t].end(), by_name);
+    for (size_t t = 0; t < w_in.size(); ++t) if (w_in[t].size() > 1) std::stable_sort(w_in[t].begin(), w_in[t].end(), by_name);
+
+    // variable of the edge s -> t of the expanded graph
+    struct EdgeVar {
+        ModelState *st; EdgeVarTable *to_w, *from_w; const std::vector<XNode> *an, *wn;
+        GRBVar &operator()(uint32_t s, uint32_t t) const
+        {
+            int64_t idx;
+            if (t & 0x80000000u) { const XNode &a = (*an)[s], &w = (*wn)[t & 0x7FFFFFFFu]; idx = to_w->find((int32_t)w.a, (int32_t)w.b, (int32_t)a.b); }
+            else if (s & 0x80000000u) { const XNode &w = (*wn)[s & 0x7FFFFFFFu], &a = (*an)[t]; idx = from_w->find((int32_t)w.a, (int32_t)w.b, (int32_t)a.b); }
+            else { const XNode &a = (*an)[s], &b = (*an)[t]; idx = st->same_walk.find((int32_t)a.a, (int32_t)b.a, (int32_t)a.b); }
+            if (idx < 0) { fprintf(stderr, "Error: expanded-graph edge without a variable\n"); exit(1); }
+            return st->pool[idx];
+        }
+    } edge_var; edge_var.st = &st; edge_var.to_w = &to_w; edge_var.from_w = &from_w; edge_var.an = &a_node; edge_var.wn = &w_node;
+
+    if (getenv("PHI_MODEL_TIMES")) fprintf(stderr, "[phi_model] %.3f reverse adjacency\n", realtime() - mg_realtime0);
+    // paths based flow constraints (:1320-1343)
+    for (int32_t i = 0; i < num_walks; i++) {
+        for (size_t idx = 0; idx < ix.paths[i].size(); idx++) {
+            if (idx == 0 || idx == ix.paths[i].size() - 1) continue;                     // skip source and sink nodes
+            GRBLinExpr in_expr, out_expr;
+            const int32_t v = ix.paths[i][idx];
+            const uint32_t t = Ids::a(a_index, a_node, a_adj, v, i);
+            if (t >= a_in.size()) a_in.resize(a_node.size());
+            for (size_t q = 0; q < a_in[t].size(); ++q) in_expr += edge_var(a_in[t][q], t);
+            for (size_t q = 0; q < a_adj[t].size(); ++q) out_expr += edge_var(t, a_adj[t][q]);
+            model.addConstr(in_expr == out_expr, "Flow_conservation_" + std::to_string(v) + "_" + std::to_string(i));
+        }
+    }
+    if (getenv("PHI_MODEL_TIMES")) fprintf(stderr, "[phi_model] %.3f path flow constraints\n", realtime() - mg_realtime0);
+    // w_u_v vertices (:1345-1368)
+    for (uint32_t u = 0; u < ix.n_vtx; u++) {
+        for (size_t q = 0; q < ix.adj_list[u].size(); ++q) {
+            const uint32_t v = ix.adj_list[u][q];
+            uint32_t wid;
+            if (!w_index.find(u, v, wid) || !w_is_key[wid]) continue;                    // w_vtx exists
+            GRBLinExpr in_expr, out_expr;
+            for (size_t r = 0; r < w_adj[wid].size(); ++r) out_expr += edge_var(wid | WBIT, w_adj[wid][r]);
+            for (size_t r = 0; r < w_in[wid].size(); ++r) in_expr += edge_var(w_in[wid][r], wid | WBIT);
+            model.addConstr(in_expr == out_expr, "Flow_conservation_w_" + std::to_string(u) + "_" + std::to_string(v));
+        }
+    }
+    if (getenv("PHI_MODEL_TIMES")) fprintf(stderr, "[phi_model] %.3f w flow constraints\n", realtime() - mg_realtime0);
+    // source nodes (:1371-1382)
+    for (int32_t i = 0; i < num_walks; i++) {
+        const int32_t u = ix.paths[i][0];
+        GRBLinExpr s_expr;
+        s_expr += vars["s_" + std::to_string(u) + "_" + std::to_string(i)];
+        const uint32_t t = Ids::a(a_index, a_node, a_adj, u, i);
+        for (size_t q = 0; q < a_adj[t].size(); ++q) s_expr -= edge_var(t, a_adj[t][q]);
+        model.addConstr(s_expr == 0, "Source_conservation_" + std::to_string(u) + "_" + std::to_string(i));
+    }
+    // sink nodes (:1385-1398)
+    for (int32_t i = 0; i < num_walks; i++) {
+        const int32_t u = ix.paths[i].back();
+        GRBLinExpr e_expr;
+        const uint32_t t = Ids::a(a_index, a_node, a_adj, u, i);
+        if (t >= a_in.size()) a_in.resize(a_node.size());
+        for (size_t q = 0; q < a_in[t].size(); ++q) e_expr += edge_var(a_in[t][q], t);
+        e_expr += -1 * vars[std::to_string(u) + "_" + std::to_string(i) + "_e"];
+        model.addConstr(e_expr == 0, "Sink_conservation_" + std::to_string(u) + "_" + std::to_string(i));
+    }
+    vars.clear();                                                                        // :1402
 }
 
 }  // namespace phi_adapter

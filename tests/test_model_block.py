@@ -1,7 +1,8 @@
-"""CPU: SURVEY 8(f) row 3 — the k-mer constraint block of the model construction built straight from the grouped result
-(integration/phi_model.hpp, replacing /root/reference/src/ILP_index.cpp:782-880).  oracle/_ref/PHI_gpu_model is the reference CLI
-with the front end AND that block replaced; here the front end's result comes from a file written from the CPU oracle's anchors
-(test hook), so only the block is under test.  The recorded model must be the unmodified reference's, byte for byte: the dump of
+"""CPU: SURVEY 8(f) row 3 — the k-mer constraint block of the model construction built straight from the grouped result and the
+expanded graph of the default branch built with integer keys (integration/phi_model.hpp, replacing
+/root/reference/src/ILP_index.cpp:782-880 and :1201-1406).  oracle/_ref/PHI_gpu_model is the reference CLI with the front end AND
+those blocks replaced; here the front end's result comes from a file written from the CPU oracle's anchors
+(test hook), so only the blocks are under test.  The recorded model must be the unmodified reference's, byte for byte: the dump of
 oracle/_ref/PHI_ref on the same files, and for the synthetic cases also the SHA-256 tests/golden/ holds (the mhc4 fixture was
 dumped from the original .gfa.gz, whose link order the re-written GFA does not keep)."""
 import hashlib
