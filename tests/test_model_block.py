@@ -59,3 +59,30 @@ def test_model_block_from_the_grouped_result_dumps_the_reference_model(tmp_path,
         assert got == hashlib.sha256(open(ref_dump, "rb").read()).hexdigest(), f"model dump differs from the reference's for -q{q}"
         if name != "mhc4":
             assert got == c.meta[f"model_q{q}_sha256"], f"model dump differs from the golden one for -q{q}"
+
+
+@pytest.mark.parametrize("n_haps,T,flags", [(12, 1.0, []), (105, 0.3, []), (12, 1.0, ["-m", "0", "-R", "7"]), (12, 1.0, ["-N", "1"])])
+def test_model_blocks_with_multi_digit_walk_ids(tmp_path, n_haps, T, flags):
+    """The predecessor lists of the expanded graph come in the std::string order of names like "17_10" < "17_2" < "17_9": walk ids of
+    two and three digits exercise the integer comparator that stands in for it.  Also: integer instead of mixed variables with an odd
+recombination penalty (-m0 -R7: the coefficient is the integer c_1 / 2), and the naive expanded graph (-N1), whose branch is not
+replaced and must keep working behind the replaced k-mer block (it reads the string map `vars` the block keeps filling)."""
+    if not (os.path.exists(EXE) and os.path.exists(REF)):
+        pytest.skip("oracle/_ref/PHI_gpu_model / PHI_ref not built")
+    sg = synth.make_graph(4000 + n_haps, 4000, n_haps, founders=5, block_sites=12)
+    rd = synth.make_reads(4000 + n_haps, sg, 8.0)
+    res = phi_io.oracle_index(sg.graph, rd, 31, 25, T)
+    assert res.n_anchors > 0
+    gfa, fa, rf = str(tmp_path / "g.gfa"), str(tmp_path / "r.fa"), str(tmp_path / "result.bin")
+    synth.write_gfa(sg.graph, gfa)
+    synth.write_fasta(rd, fa)
+    phi_io.write_result_file(rf, res, 2)
+    for q in ("1", "0"):
+        dumps = []
+        for exe, env in ((EXE, dict(PHI_ADAPTER_RESULT_FILE=rf)), (REF, {})):
+            dump = str(tmp_path / f"{os.path.basename(exe)}_q{q}.dump")
+            p = subprocess.run([exe, "-g", gfa, "-r", fa, "-o", dump + ".fa", "-t", "4", "-q", q, "-T", str(T)] + flags,
+                               env=dict(os.environ, PHI_STUB_DUMP=dump, **env), capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr[-2000:]
+            dumps.append(hashlib.sha256(open(dump, "rb").read()).hexdigest())
+        assert dumps[0] == dumps[1], f"model dump differs from the reference's for -q{q}"
