@@ -178,9 +178,33 @@ def main_reference(args):
 def config_dict(args, n):
     return {"workload": f"BASELINE configs[1]: synthetic MHC-shaped acyclic graph, {args.haps} haplotypes x ~{args.backbone / 1e6:g} Mbp, "
                         f"nodes chopped to <=30 bp, {args.read_len} bp reads at {args.coverage:g}x, k={args.k} w={args.w} T=1.0",
-            "seed": SEED, "gpus": n,
-            "l2": "no explicit flush: per-step working set (walk steps, packed steps + their scan, step offsets, reads, "
+            "seed": SEED, "gpus": n, "cpu_affinity": getattr(args, "cpu_affinity", "unchanged"),
+            "l2": "no explicit flush: per-step working set (walk steps, step offsets, chunk table, reads, "
                   "spectrum table, hit and anchor buffers: > 400 MB) exceeds the 126 MB L2"}
+
+
+def bind_to_gpu_numa(device):
+    """Pin this process (and the threads / pinned allocations that follow) to the CPUs of the NUMA node the GPU hangs off: host <-> device
+    copies of the end-to-end arm then stay on the local socket.  Plumbing only; silently does nothing where sysfs / NVML say nothing."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                      # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        cpus = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return f"numa-local ({len(ids)} cpus: {cpus})"
+    except Exception:
+        pass
+    return "unchanged"
 
 
 def measured_peak():
@@ -224,6 +248,8 @@ def main_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    all_cpus = os.sched_getaffinity(0)
+    args.cpu_affinity = bind_to_gpu_numa(local)
     if world > 1:
         from phi_b200 import multi
         return multi.bench_main(args, rank, world, local, globals())
@@ -308,6 +334,7 @@ def main_gpu(args):
                                  "accounts for; identical walk chunks are sketched once (sharing.unique_fraction), 'achieved_physical' "
                                  "scales to the positions really sketched. See DESIGN.md and profiles/"}}
     if not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)                        # the CPU arm gets every host core again
         threads = os.cpu_count() or 1
         n_walks = args.cpu_walks or min(threads, args.haps, 16)
         r = run_reference_sample(sg, rd, args, n_walks, args.cpu_coverage, threads)

@@ -233,7 +233,8 @@ int phi_gpu_hash128_to_64(phi_gpu_index_ctx *ctx, const uint8_t *keys, uint64_t 
  * minimizer hashes by hash range (all-to-all), all-gather the spectrum, route
  * one (rank, count, vertex list) summary per local group to the owner of the
  * rank (which applies the threshold; the drop flags are shared), and return on
- * every rank the surviving anchors of ITS walks for all ranks (n_filtered: the
+ * every rank the surviving groups of ITS walks for all ranks (spectrum: rank 0
+ * only, NULL elsewhere - it is the same everywhere; n_filtered: the
  * dropped ranks this rank owns; sum over the ranks).  phi_shard_* below describe
  * the partition.  walk ids in the result are global: walk_id_base + local index.
  */

@@ -175,7 +175,7 @@ class IndexResultPy:
         """Bytes of the C result arrays (what crosses PCIe): spectrum, rank_off, group_len, group_vtx, group_member_off,
         member_walk, per-walk counters."""
         ns, ng = self.count_sp_r, self.n_groups
-        return 8 * ns + 4 * (ns + 1) + ng + 4 * len(self.group_vtx) + 4 * (ng + 1) + self.member_walk_bytes * len(self.member_walk) + 16 * self.n_walks
+        return 8 * len(self.spectrum) + 4 * (ns + 1) + ng + 4 * len(self.group_vtx) + 4 * (ng + 1) + self.member_walk_bytes * len(self.member_walk) + 16 * self.n_walks
 
     def anchors(self):
         """[(rank, walk, [vertices])] in final order."""

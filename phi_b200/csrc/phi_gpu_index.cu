@@ -1367,7 +1367,8 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     struct ResGuard { phi_index_result *r; ~ResGuard() { if (r) phi_gpu_index_result_free(r); } } guard = {alloc_result(ctx)};
     phi_index_result *res = guard.r;
     if (!res) return ctx->fail(PHI_ERR_NOMEM, "host allocation failed");
-    const bool spec_early = do_download && mode == WALK_MODE_PROBE;
+    // several GPUs: the ranked spectrum is the same on every rank; rank 0 alone copies it out (the others return spectrum == NULL)
+    const bool spec_early = do_download && mode == WALK_MODE_PROBE && (ctx->world == 1 || ctx->rank == 0);
     if (spec_early) {
         CU(cudaEventRecord(ctx->ev_sync, ctx->st));
         CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_sync, 0));
@@ -1401,7 +1402,7 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     res->read_kmer_positions = o.read_pos; res->path_kmer_positions = o.path_pos;
     res->read_minimizers_emitted = o.read_emitted; res->path_hits = o.path_hits;
     if (do_download) {
-        rc = spec_early ? PHI_OK : download<uint64_t>(ctx, res, ctx->spec_a.p, 0, &res->spectrum);
+        rc = (spec_early || ctx->world > 1) ? PHI_OK : download<uint64_t>(ctx, res, ctx->spec_a.p, 0, &res->spectrum);
         if (!rc && mode == WALK_MODE_PROBE) rc = download<uint32_t>(ctx, res, ctx->rank_off.p, (uint64_t)o.n_spec + 1, &res->rank_off);
         if (!rc && mode == WALK_MODE_PROBE) {
             if (o.n_groups) rc = download<uint32_t>(ctx, res, ctx->grp_moff.p, o.n_groups + 1, &res->group_member_off);

@@ -47,6 +47,7 @@ def main_gpu(name):
     part = ix.run(gs, rs, k, w, T)
     part2 = ix.run(gs, rs, k, w, T)                      # repeatable
     assert_same_result(part, part2)
+    assert rank == 0 or len(part.spectrum) == 0          # the ranked spectrum is copied out on rank 0 only
     parts = [None] * world
     dist.gather_object(part, parts if rank == 0 else None, dst=0)
     if rank == 0:
