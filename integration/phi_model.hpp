@@ -20,6 +20,7 @@
 #define PHI_MODEL_HPP
 
 #include "phi_adapter.hpp"
+#include "phi_model_tables.hpp"
 
 #include <algorithm>
 #include <map>
@@ -27,51 +28,6 @@
 #include <vector>
 
 namespace phi_adapter {
-
-// (u, v, j) -> index into a GRBVar pool; linear probing, grows by doubling
-class EdgeVarTable {
-public:
-    EdgeVarTable() : mask_(0), used_(0) { rehash(1u << 16); }
-    // returns the slot's pool index, or -1 after reserving the slot for `next_index`
-    int64_t find_or_reserve(int32_t u, int32_t v, int32_t j, int64_t next_index)
-    {
-        if ((used_ + 1) * 10 > (mask_ + 1) * 7) rehash((mask_ + 1) * 2);
-        size_t s = hash(u, v, j) & mask_;
-        for (;; s = (s + 1) & mask_) {
-            Slot &e = slots_[s];
-            if (e.idx < 0) { e.u = u; e.v = v; e.j = j; e.idx = next_index; ++used_; return -1; }
-            if (e.u == u && e.v == v && e.j == j) return e.idx;
-        }
-    }
-    int64_t find(int32_t u, int32_t v, int32_t j) const
-    {
-        for (size_t s = hash(u, v, j) & mask_;; s = (s + 1) & mask_) {
-            const Slot &e = slots_[s];
-            if (e.idx < 0) return -1;
-            if (e.u == u && e.v == v && e.j == j) return e.idx;
-        }
-    }
-private:
-    struct Slot { int32_t u, v, j; int64_t idx; };
-    static size_t hash(int32_t u, int32_t v, int32_t j)
-    {
-        uint64_t x = ((uint64_t)(uint32_t)u << 32 | (uint32_t)v) * 0x9E3779B97F4A7C15ull ^ (uint64_t)(uint32_t)j * 0xD6E8FEB86659FD93ull;
-        x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
-        return (size_t)x;
-    }
-    void rehash(size_t n)
-    {
-        std::vector<Slot> old; old.swap(slots_);
-        Slot empty; empty.u = empty.v = empty.j = 0; empty.idx = -1;
-        slots_.assign(n, empty); mask_ = n - 1; used_ = 0;
-        for (size_t i = 0; i < old.size(); ++i) if (old[i].idx >= 0) {
-            size_t s = hash(old[i].u, old[i].v, old[i].j) & mask_;
-            while (slots_[s].idx >= 0) s = (s + 1) & mask_;
-            slots_[s] = old[i]; ++used_;
-        }
-    }
-    std::vector<Slot> slots_; size_t mask_, used_;
-};
 
 // What the blocks share: every edge variable u_j_v_j created so far (the string map `vars` of the reference stays in step for the
 // code that is not replaced).
@@ -169,69 +125,6 @@ inline void add_kmer_constraints(GRBModel &model, ModelState &st, const phi_inde
 // predecessors of a node come in the std::string order of their names — is reproduced by sorting every predecessor list with
 // an integer comparator that orders (v, i) / (u, v) exactly as "v_i" / "w_u_v" compare as strings.
 // Every model call is the reference's, in its order, with its names (tests/test_model_block.py, tests/test_gpu_dropin.py).
-
-// key (a, b) -> dense index (assigned in order of first appearance)
-class PairIndex {
-public:
-    PairIndex() : mask_(0), n_(0) { rehash(1u << 16); }
-    uint32_t get(uint32_t a, uint32_t b, bool *is_new = 0)
-    {
-        if ((n_ + 1) * 10 > (mask_ + 1) * 7) rehash((mask_ + 1) * 2);
-        const uint64_t key = (uint64_t)a << 32 | b;
-        size_t s = mix(key) & mask_;
-        for (;; s = (s + 1) & mask_) {
-            if (slots_[s].idx == NONE) { slots_[s].key = key; slots_[s].idx = n_; if (is_new) *is_new = true; return n_++; }
-            if (slots_[s].key == key) { if (is_new) *is_new = false; return slots_[s].idx; }
-        }
-    }
-    bool find(uint32_t a, uint32_t b, uint32_t &idx) const
-    {
-        const uint64_t key = (uint64_t)a << 32 | b;
-        for (size_t s = mix(key) & mask_;; s = (s + 1) & mask_) {
-            if (slots_[s].idx == NONE) return false;
-            if (slots_[s].key == key) { idx = slots_[s].idx; return true; }
-        }
-    }
-    uint32_t size() const { return n_; }
-private:
-    enum { NONE = 0xFFFFFFFFu };
-    struct Slot { uint64_t key; uint32_t idx; };
-    static size_t mix(uint64_t x) { x *= 0x9E3779B97F4A7C15ull; x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32; return (size_t)x; }
-    void rehash(size_t n)
-    {
-        std::vector<Slot> old; old.swap(slots_);
-        Slot e; e.key = 0; e.idx = NONE;
-        slots_.assign(n, e); mask_ = n - 1;
-        for (size_t i = 0; i < old.size(); ++i) if (old[i].idx != NONE) {
-            size_t s = mix(old[i].key) & mask_;
-            while (slots_[s].idx != NONE) s = (s + 1) & mask_;
-            slots_[s] = old[i];
-        }
-    }
-    std::vector<Slot> slots_; size_t mask_; uint32_t n_;
-};
-
-inline int dec_digits(uint32_t v) { int d = 1; while (v >= 10) { v /= 10; ++d; } return d; }
-// order of std::to_string(a) + tail_a vs std::to_string(b) + tail_b as strings, where both tails are empty (underscore == false: a
-// proper prefix sorts first) or start with '_' (underscore == true: '_' sorts after every digit, so a proper prefix sorts last)
-inline int dec_cmp(uint32_t a, uint32_t b, bool underscore)
-{
-    if (a == b) return 0;
-    const int da = dec_digits(a), db = dec_digits(b);
-    if (da == db) return a < b ? -1 : 1;
-    uint32_t x = a, y = b;
-    if (da < db) for (int i = 0; i < db - da; ++i) y /= 10; else for (int i = 0; i < da - db; ++i) x /= 10;
-    if (x != y) return x < y ? -1 : 1;
-    return ((da < db) != underscore) ? -1 : 1;          // the shorter one is a proper prefix of the longer one
-}
-
-struct XNode { uint32_t w, a, b; };                      // w == 0: A(v = a, walk = b), name "a_b";  w == 1: W(u = a, v = b), name "w_a_b"
-inline bool xnode_less(const XNode &x, const XNode &y)   // std::string order of the names
-{
-    if (x.w != y.w) return x.w < y.w;                    // digits sort before 'w'
-    if (x.a != y.a) return dec_cmp(x.a, y.a, true) < 0;  // "a_..." : the number is followed by '_'
-    return dec_cmp(x.b, y.b, false) < 0;                 // same first number: the second one ends the name
-}
 
 // Replaces ILP_index.cpp:1201-1406.  vtx_expr / obj are the reference's locals (:1163, :1197); c_1 = recombination (:776).
 inline void add_expanded_graph(GRBModel &model, ModelState &st, ILP_index &ix, bool is_mixed, int32_t c_1,

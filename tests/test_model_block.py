@@ -86,3 +86,13 @@ replaced and must keep working behind the replaced k-mer block (it reads the str
             assert p.returncode == 0, p.stderr[-2000:]
             dumps.append(hashlib.sha256(open(dump, "rb").read()).hexdigest())
         assert dumps[0] == dumps[1], f"model dump differs from the reference's for -q{q}"
+
+
+def test_integer_comparators_and_tables_against_std_string_and_std_map(tmp_path):
+    """tests/cpp/model_order_selftest.cpp: dec_cmp / xnode_less (integration/phi_model_tables.hpp) order numbers and node names exactly as
+    their std::strings compare; EdgeVarTable / PairIndex behave like std::map."""
+    exe = str(tmp_path / "selftest")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "integration"),
+                           os.path.join(ROOT, "tests", "cpp", "model_order_selftest.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "MODEL_ORDER_OK" in out.stdout, out.stdout + out.stderr
