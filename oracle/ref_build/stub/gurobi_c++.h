@@ -56,7 +56,8 @@ struct phi_stub_state {
     std::vector<std::string> var_names;
     FILE *fp;
     long n_vars, n_lin, n_quad;
-    phi_stub_state() : fp(0), n_vars(0), n_lin(0), n_quad(0) {}
+    bool quiet;                       // PHI_STUB_QUIET=1: count the calls, write nothing (timing of the caller's own model construction)
+    phi_stub_state() : fp(0), n_vars(0), n_lin(0), n_quad(0), quiet(getenv("PHI_STUB_QUIET") != 0) {}
     FILE *out() {
         if (!fp) {
             const char *p = getenv("PHI_STUB_DUMP");
@@ -177,25 +178,28 @@ public:
         phi_stub_state &s = phi_stub();
         s.var_names.push_back(name);
         s.n_vars++;
-        fprintf(s.out(), "V %s %c %.17g %.17g %.17g\n", name.c_str(), type, lb, ub, obj);
+        if (!s.quiet) fprintf(s.out(), "V %s %c %.17g %.17g %.17g\n", name.c_str(), type, lb, ub, obj);
         return GRBVar((int)s.var_names.size() - 1);
     }
     GRBConstr addConstr(const GRBTempConstr &c, const std::string &name) {
-        FILE *f = phi_stub().out();
         phi_stub().n_lin++;
+        if (phi_stub().quiet) return GRBConstr();
+        FILE *f = phi_stub().out();
         fprintf(f, "C %s %c |", name.c_str(), c.sense);
         put_lin(f, c.lhs.lin); fputs(" |", f); put_lin(f, c.rhs.lin); fputc('\n', f);
         return GRBConstr();
     }
     GRBQConstr addQConstr(const GRBTempConstr &c, const std::string &name) {
-        FILE *f = phi_stub().out();
         phi_stub().n_quad++;
+        if (phi_stub().quiet) return GRBQConstr();
+        FILE *f = phi_stub().out();
         fprintf(f, "Q %s %c |", name.c_str(), c.sense);
         put_lin(f, c.lhs.lin); fputs(" ;", f); put_quad(f, c.lhs);
         fputs(" |", f); put_lin(f, c.rhs.lin); fputs(" ;", f); put_quad(f, c.rhs); fputc('\n', f);
         return GRBQConstr();
     }
     void setObjective(const GRBLinExpr &e, int sense) {
+        if (phi_stub().quiet) return;
         FILE *f = phi_stub().out();
         fprintf(f, "O %d |", sense); put_lin(f, e); fputc('\n', f);
     }
