@@ -82,16 +82,53 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
     std::string text, e;
     if (!slurp(gfa_path, text, e)) { set_err(err, errlen, e); return PHI_ERR_ARG; }
     phi_host_graph *G = new phi_host_graph();
-    std::unordered_map<std::string, uint32_t> name2id;
-    std::vector<std::string> seqs;                                  // per segment
+    // Names and sequences are views into `text` while parsing: no per-field std::string, one open-addressing table keyed by the
+    // bytes of the name (the reference goes through a khash of strdup'ed names, gfa-base.cpp:75-96).
+    struct View { const char *p; uint32_t n; };
+    struct NameTable {
+        std::vector<uint32_t> slot; std::vector<View> *names; size_t mask;
+        static uint64_t hash(const char *p, uint32_t n)
+        {
+            uint64_t h = 0xCBF29CE484222325ull ^ n;
+            while (n >= 8) { uint64_t w; memcpy(&w, p, 8); h = (h ^ w) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; p += 8; n -= 8; }
+            uint64_t w = 0; memcpy(&w, p, n); h = (h ^ w) * 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+            return h;
+        }
+        void grow()
+        {
+            const size_t cap = slot.empty() ? (1u << 16) : slot.size() * 2;
+            slot.assign(cap, 0xFFFFFFFFu); mask = cap - 1;
+            for (uint32_t id = 0; id < names->size(); ++id) {
+                size_t s = hash((*names)[id].p, (*names)[id].n) & mask;
+                while (slot[s] != 0xFFFFFFFFu) s = (s + 1) & mask;
+                slot[s] = id;
+            }
+        }
+        // id of the name, or 0xFFFFFFFF; with add: the name gets the next id
+        uint32_t find(const char *p, uint32_t n, bool add)
+        {
+            if (slot.empty() || (names->size() + 1) * 10 > slot.size() * 7) grow();
+            size_t s = hash(p, n) & mask;
+            for (;; s = (s + 1) & mask) {
+                const uint32_t id = slot[s];
+                if (id == 0xFFFFFFFFu) break;
+                if ((*names)[id].n == n && memcmp((*names)[id].p, p, n) == 0) return id;
+            }
+            if (!add) return 0xFFFFFFFFu;
+            View v; v.p = p; v.n = n;
+            slot[s] = (uint32_t)names->size(); names->push_back(v);
+            return slot[s];
+        }
+    };
+    std::vector<View> seg_name;                                      // per segment, in order of first appearance
+    std::vector<View> seqs;                                          // per segment (n == 0: no sequence)
+    NameTable name2id; name2id.names = &seg_name; name2id.mask = 0;
     std::vector<std::pair<uint32_t, uint32_t>> arcs;                // oriented vertices (seg << 1 | reverse)
     struct Walk { std::string sample; int hap; std::vector<uint32_t> v; };
     std::vector<Walk> walks;
-    auto add_seg = [&](const std::string &name) -> uint32_t {
-        auto it = name2id.find(name);
-        if (it != name2id.end()) return it->second;
-        uint32_t id = (uint32_t)seqs.size();
-        name2id.emplace(name, id); seqs.emplace_back(); G->seg_names.push_back(name);
+    auto add_seg = [&](const char *b, const char *e) -> uint32_t {
+        const uint32_t id = name2id.find(b, (uint32_t)(e - b), true);
+        if (id == seqs.size()) { View none; none.p = b; none.n = 0; seqs.push_back(none); }
         return id;
     };
     std::vector<std::pair<const char *, const char *>> f;            // tab-separated fields of the current line
@@ -103,35 +140,37 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
         if (lend - p > 1 && lend[-1] == '\r') --lend;                    // kstream strips one trailing CR
         if (lend - p >= 3 && p[1] == '\t' && (p[0] == 'S' || p[0] == 'L' || p[0] == 'W')) {
             f.clear();
+            const size_t want = p[0] == 'S' ? 2 : p[0] == 'L' ? 4 : 6;   // the fields that are looked at (the walk is the 6th)
             for (const char *q = p + 2;;) {
                 const char *t = (const char *)memchr(q, '\t', (size_t)(lend - q));
                 f.emplace_back(q, t ? t : lend);
-                if (!t) break;
+                if (!t || f.size() == want) break;
                 q = t + 1;
             }
-            auto str = [&](size_t i) { return std::string(f[i].first, f[i].second); };
             if (p[0] == 'S' && f.size() >= 2) {                          // name, sequence ('*': none)
-                uint32_t id = add_seg(str(0));
-                std::string seq = str(1);
-                seqs[id] = seq == "*" ? std::string() : seq;
+                const uint32_t id = add_seg(f[0].first, f[0].second);
+                View sq; sq.p = f[1].first; sq.n = (uint32_t)(f[1].second - f[1].first);
+                if (sq.n == 1 && sq.p[0] == '*') sq.n = 0;
+                seqs[id] = sq;
             } else if (p[0] == 'L' && f.size() >= 4) {                   // from, orientation, to, orientation [, overlap]
-                const std::string oa = str(1), ob = str(3);
-                if ((oa[0] == '+' || oa[0] == '-') && (ob[0] == '+' || ob[0] == '-')) {   // the reference tests the first byte only
-                    uint32_t v = add_seg(str(0)) << 1 | (oa[0] != '+' ? 1u : 0u);
-                    uint32_t w = add_seg(str(2)) << 1 | (ob[0] != '+' ? 1u : 0u);
+                const char oa = f[1].second > f[1].first ? f[1].first[0] : 0, ob = f[3].second > f[3].first ? f[3].first[0] : 0;
+                if ((oa == '+' || oa == '-') && (ob == '+' || ob == '-')) {   // the reference tests the first byte only
+                    uint32_t v = add_seg(f[0].first, f[0].second) << 1 | (oa != '+' ? 1u : 0u);
+                    uint32_t w = add_seg(f[2].first, f[2].second) << 1 | (ob != '+' ? 1u : 0u);
                     arcs.emplace_back(v, w);
                     ++G->n_links;
                 }
             } else if (p[0] == 'W' && f.size() >= 6) {                   // sample, haplotype, contig, start, end, walk
                 Walk wk;
-                wk.sample = str(0); wk.hap = atoi(str(1).c_str());
+                wk.sample.assign(f[0].first, f[0].second); wk.hap = atoi(std::string(f[1].first, f[1].second).c_str());
                 const char *c = f[5].first, *send = f[5].second;
+                wk.v.reserve((size_t)(send - c) / 4);
                 while (c < send) {
                     if (*c == '>' || *c == '<') {
                         const char *d = c + 1;
                         while (d < send && *d != '>' && *d != '<') ++d;
-                        auto it = name2id.find(std::string(c + 1, d));
-                        if (it != name2id.end()) wk.v.push_back(it->second << 1 | (*c == '<' ? 1u : 0u));
+                        const uint32_t id = name2id.find(c + 1, (uint32_t)(d - c - 1), false);
+                        if (id != 0xFFFFFFFFu) wk.v.push_back(id << 1 | (*c == '<' ? 1u : 0u));
                         c = d;
                     } else ++c;
                 }
@@ -140,6 +179,8 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
         }
         p = next_line;
     }
+    G->seg_names.reserve(seg_name.size());
+    for (const View &v : seg_name) G->seg_names.emplace_back(v.p, v.n);
     const uint32_t V = (uint32_t)seqs.size();
     // ---- walk flip (gfa-io.cpp:64-115)
     {
@@ -155,8 +196,10 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
         }
     }
     // ---- flat views
-    G->seg_off.assign(1, 0);
-    for (uint32_t v = 0; v < V; ++v) { G->seg_bases += seqs[v]; G->seg_off.push_back(G->seg_bases.size()); }
+    G->seg_off.assign((size_t)V + 1, 0);
+    for (uint32_t v = 0; v < V; ++v) G->seg_off[v + 1] = G->seg_off[v] + seqs[v].n;
+    G->seg_bases.resize(G->seg_off[V]);
+    for (uint32_t v = 0; v < V; ++v) if (seqs[v].n) memcpy(&G->seg_bases[G->seg_off[v]], seqs[v].p, seqs[v].n);
     G->walk_off.assign(1, 0);
     for (size_t h = 0; h < walks.size(); ++h) {
         for (uint32_t v : walks[h].v) {
