@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -28,9 +29,44 @@
 namespace phi_adapter {
 
 
+// What the front end returns: one result per GPU (one part with a single GPU).  Part p holds the groups of ITS walks for all
+// ranks; walk ranges ascend with p, so "the parts one after another" is the reference's walk order.
+struct FrontEnd {
+    std::vector<const phi_index_result *> parts;
+    bool from_files;
+    FrontEnd() : from_files(false) {}
+    int32_t count_sp_r() const { return parts.empty() ? 0 : parts[0]->count_sp_r; }
+};
+
+inline int32_t member_walk(const phi_index_result *res, uint64_t m)
+{
+    return res->member_walk16 ? (int32_t)res->member_walk16[m] : res->member_walk32[m];
+}
+
+namespace detail {
+struct Shard {                                     // the views of one GPU: its walks and reads, offsets rebased to 0
+    std::vector<uint64_t> walk_off, read_off;
+    phi_graph_view g; phi_reads_view rd;
+    uint32_t walk_id_base;
+};
+struct Job { int device, rank, world; const uint8_t *id; uint32_t n_walks_global; Shard *sh; const phi_index_params *prm; phi_index_result *res; int rc; std::string err; };
+inline void run_job(Job *j)
+{
+    phi_gpu_index_ctx *ctx = 0;
+    j->rc = phi_gpu_index_create(j->device, &ctx);
+    if (j->rc == PHI_OK && j->world > 1) j->rc = phi_gpu_index_comm_init(ctx, j->rank, j->world, j->id, j->sh->walk_id_base, j->n_walks_global);
+    if (j->rc == PHI_OK) j->rc = phi_gpu_index_run(ctx, &j->sh->g, &j->sh->rd, j->prm, &j->res);
+    if (j->rc != PHI_OK) j->err = phi_gpu_last_error(ctx);
+    if (ctx) phi_gpu_index_destroy(ctx);           // the result outlives its ctx (phi_gpu_index_result_free is safe afterwards)
+}
+}  // namespace detail
+
 // Replaces ILP_function lines 543-743 up to the result: runs the library and prints the same stderr lines
 // (:556, :563, :611, :641, :724-735, :738-743) from the returned counters.  The caller frees the result with release().
-inline const phi_index_result *run_front_end_result(ILP_index &ix, std::vector<std::pair<std::string, std::string> > &ip_reads, int32_t &count_sp_r)
+// PHI_GPU_DEVICE=n selects the GPU; PHI_GPU_DEVICES=a,b,c runs one ctx per listed GPU in one thread each (walks and reads sharded
+// by phi_shard_split_by_weight, NCCL inside the library) — EXPERIMENTAL: compiled and exercised up to the error path, not yet run on
+// a multi-GPU box (the multi-GPU path proper is measured through one process per GPU, bench.py --gpus N).
+inline FrontEnd run_front_end_result(ILP_index &ix, std::vector<std::pair<std::string, std::string> > &ip_reads, int32_t &count_sp_r)
 {
     // ---- flat views of the members read_gfa() filled (ILP_index.cpp:20-155)
     std::vector<uint64_t> seg_off(1, 0), walk_off(1, 0), read_off(1, 0);
@@ -42,36 +78,74 @@ inline const phi_index_result *run_front_end_result(ILP_index &ix, std::vector<s
         walk_off.push_back(walk_vtx.size());
     }
     for (size_t r = 0; r < ip_reads.size(); ++r) { read_bases += ip_reads[r].second; read_off.push_back(read_bases.size()); }
-
-    phi_graph_view g;
-    g.n_vtx = ix.n_vtx; g.seg_off = seg_off.data(); g.seg_bases = (const uint8_t *)seg_bases.data();
-    g.n_walks = ix.num_walks; g.walk_off = walk_off.data(); g.walk_vtx = walk_vtx.data();
-    g.top_order_map = ix.top_order_map.data();
-    phi_reads_view rd;
-    rd.n_reads = ip_reads.size(); rd.read_off = read_off.data(); rd.read_bases = (const uint8_t *)read_bases.data();
     phi_index_params prm;
     prm.k = ix.k_mer; prm.w = ix.window; prm.threshold = ix.threshold; prm.debug = ix.debug ? 1 : 0;
 
-    const char *dev_env = getenv("PHI_GPU_DEVICE");
-    phi_gpu_index_ctx *ctx = 0;
-    phi_index_result *res = 0;
+    FrontEnd fe;
 #ifdef PHI_ADAPTER_TESTHOOK
-    if (const char *f = getenv("PHI_ADAPTER_RESULT_FILE")) res = const_cast<phi_index_result *>(load_result_file(f));   // CPU tests of the model block
+    if (const char *f = getenv("PHI_ADAPTER_RESULT_FILE")) {            // CPU tests of the model blocks: "a.bin" or "a.bin,b.bin,..." (parts)
+        fe.from_files = true;
+        std::string list(f);
+        for (size_t p = 0; p <= list.size();) {
+            size_t c = list.find(',', p); if (c == std::string::npos) c = list.size();
+            fe.parts.push_back(load_result_file(list.substr(p, c - p).c_str()));
+            p = c + 1;
+        }
+    }
 #endif
-    if (!res) {
-        int rc = phi_gpu_index_create(dev_env ? atoi(dev_env) : -1, &ctx);
-        if (rc == PHI_OK) rc = phi_gpu_index_run(ctx, &g, &rd, &prm, &res);
-        if (rc != PHI_OK) {                   // the reference's error style: message on stderr, exit(1) (:105-106)
-            fprintf(stderr, "Error: GPU ILP_index front end failed (%d): %s\n", rc, phi_gpu_last_error(ctx));
-            exit(1);
+    if (fe.parts.empty()) {
+        std::vector<int> devices;
+        if (const char *dl = getenv("PHI_GPU_DEVICES")) {
+            std::string list(dl);
+            for (size_t p = 0; p < list.size();) { size_t c = list.find(',', p); if (c == std::string::npos) c = list.size(); devices.push_back(atoi(list.substr(p, c - p).c_str())); p = c + 1; }
+        }
+        if (devices.empty()) { const char *d = getenv("PHI_GPU_DEVICE"); devices.push_back(d ? atoi(d) : -1); }
+        const int W = (int)devices.size();
+        std::vector<uint64_t> wb(W + 1, 0), rb(W + 1, 0);
+        wb[W] = ix.num_walks; rb[W] = ip_reads.size();
+        if (W > 1) {
+            phi_shard_split_by_weight(walk_off.data(), ix.num_walks, W, wb.data());
+            phi_shard_split_by_weight(read_off.data(), ip_reads.size(), W, rb.data());
+        }
+        uint8_t id[PHI_COMM_ID_BYTES];
+        if (W > 1 && phi_gpu_index_comm_unique_id(id) != PHI_OK) { fprintf(stderr, "Error: %s\n", phi_gpu_last_error(0)); exit(1); }
+        std::vector<detail::Shard> shards(W);
+        std::vector<detail::Job> jobs(W);
+        for (int r = 0; r < W; ++r) {
+            detail::Shard &s = shards[r];
+            for (uint64_t h = wb[r]; h <= wb[r + 1]; ++h) s.walk_off.push_back(walk_off[h] - walk_off[wb[r]]);
+            for (uint64_t q = rb[r]; q <= rb[r + 1]; ++q) s.read_off.push_back(read_off[q] - read_off[rb[r]]);
+            s.g.n_vtx = ix.n_vtx; s.g.seg_off = seg_off.data(); s.g.seg_bases = (const uint8_t *)seg_bases.data();
+            s.g.n_walks = (uint32_t)(wb[r + 1] - wb[r]); s.g.walk_off = s.walk_off.data(); s.g.walk_vtx = walk_vtx.data() + walk_off[wb[r]];
+            s.g.top_order_map = ix.top_order_map.data();
+            s.rd.n_reads = rb[r + 1] - rb[r]; s.rd.read_off = s.read_off.data(); s.rd.read_bases = (const uint8_t *)read_bases.data() + read_off[rb[r]];
+            s.walk_id_base = (uint32_t)wb[r];
+            detail::Job &j = jobs[r];
+            j.device = devices[r]; j.rank = r; j.world = W; j.id = id; j.n_walks_global = ix.num_walks; j.sh = &s; j.prm = &prm; j.res = 0; j.rc = PHI_OK;
+        }
+        if (W == 1) detail::run_job(&jobs[0]);
+        else {
+            std::vector<std::thread> th;
+            for (int r = 0; r < W; ++r) th.push_back(std::thread(detail::run_job, &jobs[r]));
+            for (int r = 0; r < W; ++r) th[r].join();
+        }
+        for (int r = 0; r < W; ++r) {
+            if (jobs[r].rc != PHI_OK) {           // the reference's error style: message on stderr, exit(1) (:105-106)
+                fprintf(stderr, "Error: GPU ILP_index front end failed (%d): %s\n", jobs[r].rc, jobs[r].err.c_str());
+                exit(1);
+            }
+            fe.parts.push_back(jobs[r].res);
         }
     }
 
-    // ---- the log lines downstream scripts scrape (data/postprocessing_*.py)
+    // ---- the log lines downstream scripts scrape (data/postprocessing_*.py); per-walk counters and n_filtered are partial sums
+    const phi_index_result *res = fe.parts[0];
     const double t = realtime() - mg_realtime0;
     std::cerr << "Number of Minimizers" << std::endl;                                              // :556
-    for (uint32_t h = 0; h < ix.num_walks; ++h)
-        fprintf(stderr, "%s : %d\n", ix.hap_id2name[h].c_str(), (int)res->minimizers_per_walk[h]);   // :563
+    for (uint32_t h = 0; h < ix.num_walks; ++h) {
+        uint64_t n = 0; for (size_t p = 0; p < fe.parts.size(); ++p) n += fe.parts[p]->minimizers_per_walk[h];
+        fprintf(stderr, "%s : %d\n", ix.hap_id2name[h].c_str(), (int)n);                            // :563
+    }
     if (ix.debug && res->shared_kmer_hist) {                                                         // :593-606
         fprintf(stderr, "Shared fraction of unique kmers by haplotypes\n");
         for (uint32_t i = 1; i <= ix.num_walks; ++i)
@@ -83,53 +157,51 @@ inline const phi_index_result *run_front_end_result(ILP_index &ix, std::vector<s
 
     count_sp_r = res->count_sp_r;
     std::cerr << "Number of Anchors" << std::endl;                                                 // :724
-    for (uint32_t h = 0; h < ix.num_walks; ++h)
-        fprintf(stderr, "%s : %d\n", ix.hap_id2name[h].c_str(), (int)res->anchors_per_walk[h]);      // :734
-    const int64_t filtered_kmers = res->n_filtered, retained_kmers = count_sp_r - filtered_kmers;    // :719-721
+    for (uint32_t h = 0; h < ix.num_walks; ++h) {
+        uint64_t n = 0; for (size_t p = 0; p < fe.parts.size(); ++p) n += fe.parts[p]->anchors_per_walk[h];
+        fprintf(stderr, "%s : %d\n", ix.hap_id2name[h].c_str(), (int)n);                            // :734
+    }
+    int64_t filtered_kmers = 0; for (size_t p = 0; p < fe.parts.size(); ++p) filtered_kmers += fe.parts[p]->n_filtered;
+    const int64_t retained_kmers = count_sp_r - filtered_kmers;                                      // :719-721
     fprintf(stderr, "[M::%s::%.3f*%.2f] Filtered/Retained Minimizers: %.2f/%.2f%%\n", "ILP_function",
             realtime() - mg_realtime0, cputime() / (realtime() - mg_realtime0),
             (float)filtered_kmers / (float)count_sp_r * 100, (float)retained_kmers / (float)count_sp_r * 100);  // :738-743
-
-    if (ctx) phi_gpu_index_destroy(ctx);          // the result outlives its ctx (phi_gpu_index_result_free is safe afterwards)
-    return res;
+    return fe;
 }
 
-inline void release(const phi_index_result *res)
+inline void release(FrontEnd &fe)
 {
-#ifdef PHI_ADAPTER_TESTHOOK
-    if (getenv("PHI_ADAPTER_RESULT_FILE")) return;                       // owned by the test hook
-#endif
-    phi_gpu_index_result_free(const_cast<phi_index_result *>(res));
+    if (!fe.from_files)                                                    // (file-fed parts are owned by the test hook)
+        for (size_t p = 0; p < fe.parts.size(); ++p) phi_gpu_index_result_free(const_cast<phi_index_result *>(fe.parts[p]));
+    fe.parts.clear();
 }
 
-inline int32_t member_walk(const phi_index_result *res, uint64_t m)
-{
-    return res->member_walk16 ? (int32_t)res->member_walk16[m] : res->member_walk32[m];
-}
-
-// Rebuilds the nested vectors the model construction indexes (:643, :716).  The result is the filter's own map (:680-709):
+// Rebuilds the nested vectors the model construction indexes (:643, :716).  A result is the filter's own map (:680-709):
 // per rank the groups in key order, per group one vertex list and its walks.
-inline void fill_anchor_hits(const phi_index_result *res, uint32_t num_walks,
+inline void fill_anchor_hits(const FrontEnd &fe, uint32_t num_walks,
                              std::vector<std::vector<std::vector<std::vector<int32_t> > > > &Anchor_hits)
 {
-    Anchor_hits.assign(res->count_sp_r, std::vector<std::vector<std::vector<int32_t> > >(num_walks));
-    const int32_t *vtx = res->group_vtx;
-    for (int32_t r = 0; r < res->count_sp_r; ++r)
-        for (uint32_t g = res->rank_off[r]; g < res->rank_off[r + 1]; ++g) {
-            const std::vector<int32_t> list(vtx, vtx + res->group_len[g]);
-            for (uint32_t m = res->group_member_off[g]; m < res->group_member_off[g + 1]; ++m)
-                Anchor_hits[r][member_walk(res, m)].push_back(list);
-            vtx += res->group_len[g];
-        }
+    Anchor_hits.assign(fe.count_sp_r(), std::vector<std::vector<std::vector<int32_t> > >(num_walks));
+    for (size_t p = 0; p < fe.parts.size(); ++p) {
+        const phi_index_result *res = fe.parts[p];
+        const int32_t *vtx = res->group_vtx;
+        for (int32_t r = 0; r < res->count_sp_r; ++r)
+            for (uint32_t g = res->rank_off[r]; g < res->rank_off[r + 1]; ++g) {
+                const std::vector<int32_t> list(vtx, vtx + res->group_len[g]);
+                for (uint32_t m = res->group_member_off[g]; m < res->group_member_off[g + 1]; ++m)
+                    Anchor_hits[r][member_walk(res, m)].push_back(list);
+                vtx += res->group_len[g];
+            }
+    }
 }
 
 // The drop-in call of seam.inc: front end + nested vectors, exactly what ILP_function lines 543-743 leave behind.
 inline void run_front_end(ILP_index &ix, std::vector<std::pair<std::string, std::string> > &ip_reads,
                           std::vector<std::vector<std::vector<std::vector<int32_t> > > > &Anchor_hits, int32_t &count_sp_r)
 {
-    const phi_index_result *res = run_front_end_result(ix, ip_reads, count_sp_r);
-    fill_anchor_hits(res, ix.num_walks, Anchor_hits);
-    release(res);
+    FrontEnd fe = run_front_end_result(ix, ip_reads, count_sp_r);
+    fill_anchor_hits(fe, ix.num_walks, Anchor_hits);
+    release(fe);
 }
 
 }  // namespace phi_adapter

@@ -37,7 +37,7 @@ struct ModelState {
 };
 
 // Replaces ILP_index.cpp:782-880.  `vars`, `Zvars`, `count_kmer_matches` are the reference's locals (:774-780).
-inline void add_kmer_constraints(GRBModel &model, ModelState &st, const phi_index_result *res, int32_t num_walks, int32_t k_mer, bool is_ilp, bool is_mixed,
+inline void add_kmer_constraints(GRBModel &model, ModelState &st, const FrontEnd &fe, int32_t num_walks, int32_t k_mer, bool is_ilp, bool is_mixed,
                                  std::map<std::string, GRBVar> &vars, std::vector<GRBVar> &Zvars, int32_t &count_kmer_matches)
 {
     fprintf(stderr, "[M::%s::%.3f*%.2f] %s model started\n", "ILP_function", realtime() - mg_realtime0, cputime() / (realtime() - mg_realtime0),
@@ -46,13 +46,18 @@ inline void add_kmer_constraints(GRBModel &model, ModelState &st, const phi_inde
     std::vector<GRBVar> &pool = st.pool;               // edge variables in creation order
     std::vector<uint32_t> walk_cnt(num_walks + 1), pair_group;      // per rank: groups of every walk, in (walk, group) order
     std::vector<uint64_t> group_voff(1, 0);
-    const int32_t count_sp_r = res->count_sp_r;
-    uint64_t voff = 0;
+    const int32_t count_sp_r = fe.count_sp_r();
+    std::vector<uint64_t> part_voff(fe.parts.size(), 0);            // running vertex offset inside every part
     for (int32_t i = 0; i < count_sp_r; ++i) {
-        const uint32_t g0 = res->rank_off[i], g1 = res->rank_off[i + 1];
         GRBQuadExpr q_expr;                            // QP: one quadratic expression per rank (:834)
         GRBLinExpr z_expr;
         int32_t temp = 0;
+        // several GPUs: part p holds the groups of its own walks, and walk ranges ascend with p — the parts one after another
+        // give the reference's ascending j; the k of an anchor only counts the groups of its own walk, which live in one part
+        for (size_t part = 0; part < fe.parts.size(); ++part) {
+        const phi_index_result *res = fe.parts[part];
+        uint64_t &voff = part_voff[part];
+        const uint32_t g0 = res->rank_off[i], g1 = res->rank_off[i + 1];
         if (g1 > g0) {
             // (walk, group) order of the rank's anchors: counting pass over the member walks; groups stay in key order inside a walk
             std::fill(walk_cnt.begin(), walk_cnt.end(), 0u);
@@ -100,6 +105,7 @@ inline void add_kmer_constraints(GRBModel &model, ModelState &st, const phi_inde
                     temp += 1;
                 }
             }
+        }
         }
         if (temp != 0) {                               // :822-832 / :864-874
             const std::string constraint_name = "Kmer_constraints_" + std::to_string(i);

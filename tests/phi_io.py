@@ -237,3 +237,25 @@ def write_result_file(path, res, member_bytes=2):
         for a in arrays:
             b = a.tobytes()
             f.write(b + b"\0" * (-len(b) % 8))
+
+
+def split_result_by_walks(res, bounds):
+    """Per-anchor result -> what every GPU of a multi-GPU run returns (the anchors of ITS walks for all ranks; per-walk counters are
+    partial sums; n_filtered is reported once): test infrastructure for the multi-part adapter paths."""
+    import dataclasses
+    parts = []
+    lens = np.diff(res.anchor_off.astype(np.int64))
+    for p in range(len(bounds) - 1):
+        lo, hi = int(bounds[p]), int(bounds[p + 1])
+        keep = (res.anchor_walk >= lo) & (res.anchor_walk < hi)
+        idx = np.nonzero(keep)[0]
+        starts = res.anchor_off.astype(np.int64)[idx]
+        vtx = np.concatenate([res.anchor_vtx[s:s + n] for s, n in zip(starts, lens[idx])]) if len(idx) else np.zeros(0, dtype=np.int32)
+        in_range = (np.arange(res.n_walks) >= lo) & (np.arange(res.n_walks) < hi)
+        parts.append(dataclasses.replace(
+            res, n_filtered=res.n_filtered if p == 0 else 0,
+            anchor_rank=res.anchor_rank[idx], anchor_walk=res.anchor_walk[idx],
+            anchor_off=np.concatenate([[0], np.cumsum(lens[idx])]).astype(np.uint64), anchor_vtx=vtx.astype(np.int32),
+            minimizers_per_walk=np.where(in_range, res.minimizers_per_walk, 0).astype(np.uint64),
+            anchors_per_walk=np.where(in_range, res.anchors_per_walk, 0).astype(np.uint64)))
+    return parts

@@ -96,3 +96,33 @@ def test_integer_comparators_and_tables_against_std_string_and_std_map(tmp_path)
                            os.path.join(ROOT, "tests", "cpp", "model_order_selftest.cpp"), "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "MODEL_ORDER_OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("bounds", [[0, 5, 12], [0, 1, 2, 7, 12], [0, 0, 12, 12]])
+def test_model_blocks_from_several_parts(tmp_path, bounds):
+    """Several GPUs return one result each (the groups of their own walks for all ranks); the adapter walks the parts one after another.
+    Here the parts are cut out of the CPU oracle's anchors by walk range (also with empty parts) and fed through the file hook."""
+    if not (os.path.exists(EXE) and os.path.exists(REF)):
+        pytest.skip("oracle/_ref/PHI_gpu_model / PHI_ref not built")
+    sg = synth.make_graph(4012, 4000, 12, founders=5, block_sites=12)
+    rd = synth.make_reads(4012, sg, 8.0)
+    res = phi_io.oracle_index(sg.graph, rd, 31, 25, 1.0)
+    gfa, fa = str(tmp_path / "g.gfa"), str(tmp_path / "r.fa")
+    synth.write_gfa(sg.graph, gfa)
+    synth.write_fasta(rd, fa)
+    files = []
+    for i, part in enumerate(phi_io.split_result_by_walks(res, bounds)):
+        files.append(str(tmp_path / f"part{i}.bin"))
+        phi_io.write_result_file(files[-1], part, 2 if i % 2 == 0 else 4)
+    for q in ("1", "0"):
+        outs = []
+        for exe, env in ((EXE, dict(PHI_ADAPTER_RESULT_FILE=",".join(files))), (REF, {})):
+            dump = str(tmp_path / f"{os.path.basename(exe)}_q{q}.dump")
+            p = subprocess.run([exe, "-g", gfa, "-r", fa, "-o", dump + ".fa", "-t", "4", "-q", q],
+                               env=dict(os.environ, PHI_STUB_DUMP=dump, **env), capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr[-2000:]
+            counts = sorted(l for l in p.stderr.splitlines() if " : " in l or "Filtered/Retained" in l.split("]")[-1])
+            counts = [l.split("] ")[-1] for l in counts]
+            outs.append((hashlib.sha256(open(dump, "rb").read()).hexdigest(), counts))
+        assert outs[0][0] == outs[1][0], f"model dump differs from the reference's for -q{q}"
+        assert outs[0][1] == outs[1][1], "scraped per-walk counters differ"
