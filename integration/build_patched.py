@@ -22,6 +22,9 @@ END = "(float)retained_kmers/(float)count_sp_r * 100);"
 BLOCK_START = "        if (is_ilp)"
 BLOCK_END = "// print count_sp_r_ilp/count_sp_r * 100% kmer matches are in ilp"
 # and the "optimized expanded graph" part of the default branch, :1201-1406
+# the naive expanded graph (-N1), :942-1154: from the first "// w/o recombination" to the line before the first "// clear vars"
+NAIVE_START = "            // w/o recombination"
+NAIVE_END = "            // clear vars"
 GRAPH_START = "            std::map<std::string, std::vector<std::string>> new_adj;"
 GRAPH_END = "            in_nodes_new.clear();"
 
@@ -35,6 +38,9 @@ def main():
     bs = next(i for i, l in enumerate(lines) if l.rstrip() == BLOCK_START)
     be = next(i for i, l in enumerate(lines) if BLOCK_END in l) - 2                     # the closing brace of the else branch
     assert (bs + 1, be + 1) == (782, 880) and lines[be].strip() == "}", f"model block moved: {bs + 1}-{be + 1}"
+    ns = next(i for i, l in enumerate(lines) if l.rstrip() == NAIVE_START)
+    ne = next(i for i, l in enumerate(lines) if l.rstrip() == NAIVE_END) - 1
+    assert (ns + 1, ne + 1) == (942, 1155) and lines[ne].strip() == "", f"naive block moved: {ns + 1}-{ne + 1}"
     gs = next(i for i, l in enumerate(lines) if l.rstrip() == GRAPH_START)
     ge = next(i for i, l in enumerate(lines) if l.rstrip() == GRAPH_END)
     assert (gs + 1, ge + 1) == (1201, 1406), f"expanded-graph block moved: {gs + 1}-{ge + 1}"
@@ -46,7 +52,8 @@ def main():
         "PHI_gpu": (lines[:inc + 1] + ['#include "phi_adapter.hpp"'] + lines[inc + 1:s] + read("seam.inc") + lines[e + 1:], []),
         # + the k-mer constraint block built straight from the result; test hook compiled in
         "PHI_gpu_model": (lines[:inc + 1] + ['#include "phi_model.hpp"'] + lines[inc + 1:s] + read("seam_model.inc") + lines[e + 1:bs]
-                          + read("model_block.inc") + lines[be + 1:gs] + read("model_graph.inc") + lines[ge + 1:], ["-DPHI_ADAPTER_TESTHOOK"]),
+                          + read("model_block.inc") + lines[be + 1:ns] + read("model_naive.inc") + lines[ne:gs] + read("model_graph.inc") + lines[ge + 1:],
+                          ["-DPHI_ADAPTER_TESTHOOK"]),
     }
     os.makedirs(OUT, exist_ok=True)
     flags = ["-std=c++11", "-fopenmp", "-pthread", "-O3", "-march=x86-64-v2", "-mtune=generic", "-w",

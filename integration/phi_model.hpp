@@ -306,5 +306,104 @@ inline void add_expanded_graph(GRBModel &model, ModelState &st, ILP_index &ix, b
     vars.clear();                                                                        // :1402
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The "naive expanded graph" part of the model (-N1, /root/reference/src/ILP_index.cpp:942-1154): every edge variable
+// u_i_v_j (vertex u on walk i -> vertex v on walk j), the objective and the flow conservation constraints.  The reference's
+// only string-keyed structure here is `vars`; it is replaced by two integer-keyed tables (same walk: the one the k-mer block
+// filled, (u, v, i); two walks: (u, i, v, j)).  Loops, call order and names are the reference's.
+inline void add_naive_graph(GRBModel &model, ModelState &st, ILP_index &ix, bool is_mixed, int32_t c_1,
+                            const std::vector<std::vector<int32_t> > &in_nodes, std::map<std::string, GRBVar> &vars, std::vector<GRBVar> &Zvars,
+                            GRBLinExpr &vtx_expr, GRBLinExpr &obj)
+{
+    const char vtype = is_mixed ? GRB_CONTINUOUS : GRB_BINARY;
+    const int32_t num_walks = (int32_t)ix.num_walks;
+    std::vector<GRBVar> &pool = st.pool;
+    CrossVarTable cross;
+    struct Vars {
+        GRBModel *model; ModelState *st; CrossVarTable *cross; char vtype;
+        // the variable "u_i_v_j"; created (and *created set) when it does not exist yet
+        GRBVar &get(int32_t u, int32_t i, int32_t v, int32_t j, bool *created = 0)
+        {
+            std::vector<GRBVar> &pool = st->pool;
+            int64_t idx = i == j ? st->same_walk.find_or_reserve(u, v, i, (int64_t)pool.size()) : cross->find_or_reserve(u, i, v, j, (int64_t)pool.size());
+            if (created) *created = idx < 0;
+            if (idx < 0) {
+                idx = (int64_t)pool.size();
+                pool.push_back(model->addVar(0.0, 1.0, 0.0, vtype, std::to_string(u) + "_" + std::to_string(i) + "_" + std::to_string(v) + "_" + std::to_string(j)));
+            }
+            return pool[idx];
+        }
+    } V; V.model = &model; V.st = &st; V.cross = &cross; V.vtype = vtype;
+    (void)pool;
+
+    // w/o recombination (:942-962)
+    for (int32_t i = 0; i < num_walks; i++)
+        for (size_t idx = 0; idx + 1 < ix.paths[i].size(); idx++) {
+            bool created; GRBVar &var = V.get(ix.paths[i][idx], i, ix.paths[i][idx + 1], i, &created);
+            if (created) vtx_expr += 0 * var;                                              // no need without recombination
+        }
+    // with recombination (:965-995)
+    for (int32_t i = 0; i < num_walks; i++)
+        for (size_t idx = 0; idx + 1 < ix.paths[i].size(); idx++) {
+            const int32_t u = ix.paths[i][idx];
+            for (size_t a = 0; a < ix.adj_list[u].size(); ++a) {
+                const int32_t v = ix.adj_list[u][a];
+                for (size_t b = 0; b < ix.haps[v].size(); ++b) {
+                    const int32_t j = ix.haps[v][b];
+                    if (i == j) continue;
+                    bool created; GRBVar &var = V.get(u, i, v, j, &created);
+                    if (created) vtx_expr += c_1 * var;
+                }
+            }
+        }
+    // (1 - z_i) terms, objective (:998-1004)
+    GRBLinExpr z_expr;
+    for (size_t i = 0; i < Zvars.size(); i++) z_expr += (1 - Zvars[i]);
+    obj = vtx_expr + z_expr;
+    model.setObjective(obj, GRB_MINIMIZE);
+    // paths based flow constraints (:1007-1088)
+    for (int32_t i = 0; i < num_walks; i++)
+        for (size_t idx = 0; idx < ix.paths[i].size(); idx++) {
+            if (idx == 0 || idx == ix.paths[i].size() - 1) continue;                       // skip source and sink nodes
+            GRBLinExpr in_expr, out_expr;
+            const int32_t v = ix.paths[i][idx], v_in = ix.paths[i][idx - 1], v_out = ix.paths[i][idx + 1];
+            in_expr += V.get(v_in, i, v, i);
+            out_expr += V.get(v, i, v_out, i);
+            for (size_t a = 0; a < in_nodes[v].size(); ++a) {                              // in expression
+                const int32_t u = in_nodes[v][a];
+                for (size_t b = 0; b < ix.haps[u].size(); ++b) { const int32_t j = ix.haps[u][b]; if (i != j) in_expr += V.get(u, j, v, i); }
+            }
+            for (size_t a = 0; a < ix.adj_list[v].size(); ++a) {                           // out expression
+                const int32_t u = ix.adj_list[v][a];
+                for (size_t b = 0; b < ix.haps[u].size(); ++b) { const int32_t j = ix.haps[u][b]; if (i != j) out_expr += V.get(v, i, u, j); }
+            }
+            model.addConstr(in_expr == out_expr, "Flow_conservation_" + std::to_string(v) + "_" + std::to_string(i));
+        }
+    // source nodes (:1092-1113)
+    for (int32_t i = 0; i < num_walks; i++) {
+        const int32_t u = ix.paths[i][0];
+        GRBLinExpr s_expr;
+        s_expr += vars["s_" + std::to_string(u) + "_" + std::to_string(i)];
+        for (size_t a = 0; a < ix.adj_list[u].size(); ++a) {
+            const int32_t v = ix.adj_list[u][a];
+            for (size_t b = 0; b < ix.haps[v].size(); ++b) s_expr -= V.get(u, i, v, (int32_t)ix.haps[v][b]);
+        }
+        model.addConstr(s_expr == 0, "Source_conservation_" + std::to_string(u) + "_" + std::to_string(i));
+    }
+    // sink nodes (:1116-1153)
+    for (int32_t i = 0; i < num_walks; i++) {
+        const int32_t u = ix.paths[i][ix.paths[i].size() - 1];
+        GRBLinExpr e_expr;
+        for (size_t a = 0; a < in_nodes[u].size(); ++a) {
+            const int32_t v = in_nodes[u][a];
+            for (size_t b = 0; b < ix.haps[v].size(); ++b) e_expr += V.get(v, (int32_t)ix.haps[v][b], u, i);
+        }
+        const std::string var_name = std::to_string(u) + "_" + std::to_string(i) + "_e";
+        if (vars.find(var_name) == vars.end()) vars[var_name] = model.addVar(0.0, 1.0, 0.0, vtype, var_name);   // (it exists: created with the start variables)
+        e_expr += -1 * vars[var_name];
+        model.addConstr(e_expr == 0, "Sink_conservation_" + std::to_string(u) + "_" + std::to_string(i));
+    }
+}
+
 }  // namespace phi_adapter
 #endif

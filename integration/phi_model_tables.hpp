@@ -55,6 +55,42 @@ private:
     std::vector<Slot> slots_; size_t mask_, used_;
 };
 
+// (u, i, v, j) -> index into a GRBVar pool (variables "u_i_v_j" between two walks); same scheme as EdgeVarTable
+class CrossVarTable {
+public:
+    CrossVarTable() : mask_(0), used_(0) { rehash(1u << 16); }
+    int64_t find_or_reserve(int32_t u, int32_t i, int32_t v, int32_t j, int64_t next_index)
+    {
+        if ((used_ + 1) * 10 > (mask_ + 1) * 7) rehash((mask_ + 1) * 2);
+        const uint64_t k1 = (uint64_t)(uint32_t)u << 32 | (uint32_t)v, k2 = (uint64_t)(uint32_t)i << 32 | (uint32_t)j;
+        for (size_t s = hash(k1, k2) & mask_;; s = (s + 1) & mask_) {
+            Slot &e = slots_[s];
+            if (e.idx < 0) { e.k1 = k1; e.k2 = k2; e.idx = next_index; ++used_; return -1; }
+            if (e.k1 == k1 && e.k2 == k2) return e.idx;
+        }
+    }
+private:
+    struct Slot { uint64_t k1, k2; int64_t idx; };
+    static size_t hash(uint64_t a, uint64_t b)
+    {
+        uint64_t x = a * 0x9E3779B97F4A7C15ull ^ (b + 0x7F4A7C15ull) * 0xD6E8FEB86659FD93ull;
+        x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+        return (size_t)x;
+    }
+    void rehash(size_t n)
+    {
+        std::vector<Slot> old; old.swap(slots_);
+        Slot empty; empty.k1 = empty.k2 = 0; empty.idx = -1;
+        slots_.assign(n, empty); mask_ = n - 1; used_ = 0;
+        for (size_t q = 0; q < old.size(); ++q) if (old[q].idx >= 0) {
+            size_t s = hash(old[q].k1, old[q].k2) & mask_;
+            while (slots_[s].idx >= 0) s = (s + 1) & mask_;
+            slots_[s] = old[q]; ++used_;
+        }
+    }
+    std::vector<Slot> slots_; size_t mask_, used_;
+};
+
 // key (a, b) -> dense index (assigned in order of first appearance)
 class PairIndex {
 public:

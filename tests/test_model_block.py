@@ -61,12 +61,13 @@ def test_model_block_from_the_grouped_result_dumps_the_reference_model(tmp_path,
             assert got == c.meta[f"model_q{q}_sha256"], f"model dump differs from the golden one for -q{q}"
 
 
-@pytest.mark.parametrize("n_haps,T,flags", [(12, 1.0, []), (105, 0.3, []), (12, 1.0, ["-m", "0", "-R", "7"]), (12, 1.0, ["-N", "1"])])
+@pytest.mark.parametrize("n_haps,T,flags", [(12, 1.0, []), (105, 0.3, []), (12, 1.0, ["-m", "0", "-R", "7"]), (12, 1.0, ["-N", "1"]),
+                                            (30, 0.3, ["-N", "1", "-m", "0", "-R", "3"])])
 def test_model_blocks_with_multi_digit_walk_ids(tmp_path, n_haps, T, flags):
     """The predecessor lists of the expanded graph come in the std::string order of names like "17_10" < "17_2" < "17_9": walk ids of
     two and three digits exercise the integer comparator that stands in for it.  Also: integer instead of mixed variables with an odd
-recombination penalty (-m0 -R7: the coefficient is the integer c_1 / 2), and the naive expanded graph (-N1), whose branch is not
-replaced and must keep working behind the replaced k-mer block (it reads the string map `vars` the block keeps filling)."""
+recombination penalty (-m0 -R7: the coefficient is the integer c_1 / 2), and the naive expanded graph (-N1, ILP_index.cpp:942-1154,
+replaced by add_naive_graph: same-walk and two-walk edge variables through integer-keyed tables)."""
     if not (os.path.exists(EXE) and os.path.exists(REF)):
         pytest.skip("oracle/_ref/PHI_gpu_model / PHI_ref not built")
     sg = synth.make_graph(4000 + n_haps, 4000, n_haps, founders=5, block_sites=12)
