@@ -80,7 +80,7 @@ inline void add_kmer_constraints(GRBModel &model, ModelState &st, const FrontEnd
                     const int32_t *list = res->group_vtx + group_voff[g - g0];
                     const int32_t n = res->group_len[g];
                     GRBLinExpr kmer_expr;              // ILP: one linear expression per anchor (:792)
-                    const std::string extra_var = "z_" + std::to_string(i) + "_" + std::to_string(j) + "_" + std::to_string(k);
+                    const std::string extra_var = Name().s("z_").i(i).c('_').i(j).c('_').i(k).str();
                     GRBVar kmer_expr_var = model.addVar(0.0, 1.0, 0.0, GRB_BINARY, extra_var);
                     if (n - 1 == 0) continue;          // ignore matches with only one vertex (:795 / :841)
                     if (!is_ilp) { const int32_t weight = (k_mer - 1) - (n - 1); q_expr += weight * kmer_expr_var; }   // :842-843
@@ -88,7 +88,7 @@ inline void add_kmer_constraints(GRBModel &model, ModelState &st, const FrontEnd
                         const int32_t u = list[l - 1], v = list[l];
                         int64_t idx = table.find_or_reserve(u, v, j, (int64_t)pool.size());
                         if (idx < 0) {                 // variable does not exist (:802-812 / :848-857)
-                            const std::string var_name = std::to_string(u) + "_" + std::to_string(j) + "_" + std::to_string(v) + "_" + std::to_string(j);
+                            const std::string var_name = Name().i(u).c('_').i(j).c('_').i(v).c('_').i(j).str();
                             idx = (int64_t)pool.size();
                             pool.push_back(model.addVar(0.0, 1.0, 0.0, is_mixed ? GRB_CONTINUOUS : GRB_BINARY, var_name));
                             vars[var_name] = pool.back();
@@ -99,7 +99,7 @@ inline void add_kmer_constraints(GRBModel &model, ModelState &st, const FrontEnd
                     if (is_ilp) {
                         const int32_t weight = n - 1;                                                // :816-817
                         model.addConstr(kmer_expr >= weight * kmer_expr_var,
-                                        "Kmer_constraints_" + std::to_string(i) + "_" + std::to_string(j) + "_" + std::to_string(k));
+                                        Name().s("Kmer_constraints_").i(i).c('_').i(j).c('_').i(k).str());
                     }
                     z_expr += kmer_expr_var;
                     temp += 1;
@@ -161,7 +161,7 @@ inline void add_expanded_graph(GRBModel &model, ModelState &st, ILP_index &ix, b
             const uint32_t au = Ids::a(a_index, a_node, a_adj, u, i), av = Ids::a(a_index, a_node, a_adj, v, i);
             a_adj[au].push_back(av);
             if (st.same_walk.find_or_reserve(u, v, i, (int64_t)pool.size()) < 0) {      // variable does not exist
-                const std::string var_name = std::to_string(u) + "_" + std::to_string(i) + "_" + std::to_string(v) + "_" + std::to_string(i);
+                const std::string var_name = Name().i(u).c('_').i(i).c('_').i(v).c('_').i(i).str();
                 pool.push_back(model.addVar(0.0, 1.0, 0.0, vtype, var_name));
                 vtx_expr += 0 * pool.back();             // no need without recombination
             }
@@ -191,13 +191,13 @@ inline void add_expanded_graph(GRBModel &model, ModelState &st, ILP_index &ix, b
                         new_vertex_used = true;
                         bool is_new; wid = w_index.get(u, v, &is_new);
                         if (is_new) { XNode n; n.w = 1; n.a = u; n.b = v; w_node.push_back(n); w_adj.push_back(std::vector<uint32_t>()); w_is_key.push_back(0); }
-                        new_vtx = "w_" + std::to_string(u) + "_" + std::to_string(v);
+                        new_vtx = Name().s("w_").i(u).c('_').i(v).str();
                     }
                     a_adj[Ids::a(a_index, a_node, a_adj, u, h)].push_back(wid | WBIT);
                     int64_t idx = to_w.find_or_reserve((int32_t)u, (int32_t)v, (int32_t)h, (int64_t)pool.size());
                     if (idx < 0) {
                         idx = (int64_t)pool.size();
-                        pool.push_back(model.addVar(0.0, 1.0, 0.0, vtype, std::to_string(u) + "_" + std::to_string(h) + "_" + new_vtx));
+                        pool.push_back(model.addVar(0.0, 1.0, 0.0, vtype, Name().i(u).c('_').i(h).c('_').s(new_vtx.c_str()).str()));
                     }
                     vtx_expr += (c_1 / 2) * pool[idx];
                 }
@@ -209,7 +209,7 @@ inline void add_expanded_graph(GRBModel &model, ModelState &st, ILP_index &ix, b
                     int64_t idx = from_w.find_or_reserve((int32_t)u, (int32_t)v, (int32_t)h, (int64_t)pool.size());
                     if (idx < 0) {
                         idx = (int64_t)pool.size();
-                        pool.push_back(model.addVar(0.0, 1.0, 0.0, vtype, new_vtx + "_" + std::to_string(v) + "_" + std::to_string(h)));
+                        pool.push_back(model.addVar(0.0, 1.0, 0.0, vtype, Name().s(new_vtx.c_str()).c('_').i(v).c('_').i(h).str()));
                     }
                     vtx_expr += (c_1 / 2) * pool[idx];
                 }
@@ -267,7 +267,7 @@ inline void add_expanded_graph(GRBModel &model, ModelState &st, ILP_index &ix, b
             if (t >= a_in.size()) a_in.resize(a_node.size());
             for (size_t q = 0; q < a_in[t].size(); ++q) in_expr += edge_var(a_in[t][q], t);
             for (size_t q = 0; q < a_adj[t].size(); ++q) out_expr += edge_var(t, a_adj[t][q]);
-            model.addConstr(in_expr == out_expr, "Flow_conservation_" + std::to_string(v) + "_" + std::to_string(i));
+            model.addConstr(in_expr == out_expr, Name().s("Flow_conservation_").i(v).c('_').i(i).str());
         }
     }
     if (getenv("PHI_MODEL_TIMES")) fprintf(stderr, "[phi_model] %.3f path flow constraints\n", realtime() - mg_realtime0);
@@ -280,7 +280,7 @@ inline void add_expanded_graph(GRBModel &model, ModelState &st, ILP_index &ix, b
             GRBLinExpr in_expr, out_expr;
             for (size_t r = 0; r < w_adj[wid].size(); ++r) out_expr += edge_var(wid | WBIT, w_adj[wid][r]);
             for (size_t r = 0; r < w_in[wid].size(); ++r) in_expr += edge_var(w_in[wid][r], wid | WBIT);
-            model.addConstr(in_expr == out_expr, "Flow_conservation_w_" + std::to_string(u) + "_" + std::to_string(v));
+            model.addConstr(in_expr == out_expr, Name().s("Flow_conservation_w_").i(u).c('_').i(v).str());
         }
     }
     if (getenv("PHI_MODEL_TIMES")) fprintf(stderr, "[phi_model] %.3f w flow constraints\n", realtime() - mg_realtime0);
@@ -329,7 +329,7 @@ inline void add_naive_graph(GRBModel &model, ModelState &st, ILP_index &ix, bool
             if (created) *created = idx < 0;
             if (idx < 0) {
                 idx = (int64_t)pool.size();
-                pool.push_back(model->addVar(0.0, 1.0, 0.0, vtype, std::to_string(u) + "_" + std::to_string(i) + "_" + std::to_string(v) + "_" + std::to_string(j)));
+                pool.push_back(model->addVar(0.0, 1.0, 0.0, vtype, Name().i(u).c('_').i(i).c('_').i(v).c('_').i(j).str()));
             }
             return pool[idx];
         }
@@ -377,7 +377,7 @@ inline void add_naive_graph(GRBModel &model, ModelState &st, ILP_index &ix, bool
                 const int32_t u = ix.adj_list[v][a];
                 for (size_t b = 0; b < ix.haps[u].size(); ++b) { const int32_t j = ix.haps[u][b]; if (i != j) out_expr += V.get(v, i, u, j); }
             }
-            model.addConstr(in_expr == out_expr, "Flow_conservation_" + std::to_string(v) + "_" + std::to_string(i));
+            model.addConstr(in_expr == out_expr, Name().s("Flow_conservation_").i(v).c('_').i(i).str());
         }
     // source nodes (:1092-1113)
     for (int32_t i = 0; i < num_walks; i++) {

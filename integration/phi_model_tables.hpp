@@ -6,9 +6,31 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <string>
 #include <vector>
 
 namespace phi_adapter {
+
+// Names like "17_3_18_3" or "Flow_conservation_w_5_9" without one temporary std::string per piece: same text as the reference's
+// std::to_string concatenations (decimal, '-' for negative numbers).
+class Name {
+public:
+    Name() : n_(0) {}
+    Name &s(const char *t) { while (*t) buf_[n_++] = *t++; return *this; }
+    Name &c(char ch) { buf_[n_++] = ch; return *this; }
+    Name &i(int64_t v)
+    {
+        char tmp[24]; int k = 0;
+        uint64_t x = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+        do { tmp[k++] = (char)('0' + x % 10); x /= 10; } while (x);
+        if (v < 0) buf_[n_++] = '-';
+        while (k) buf_[n_++] = tmp[--k];
+        return *this;
+    }
+    std::string str() const { return std::string(buf_, (size_t)n_); }
+private:
+    char buf_[160]; int n_;
+};
 
 // (u, v, j) -> index into a GRBVar pool; linear probing, grows by doubling
 class EdgeVarTable {
