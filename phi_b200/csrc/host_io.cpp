@@ -24,7 +24,9 @@
 #include "../../include/phi_gpu_index.h"
 
 #include <zlib.h>
+#include <time.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -35,19 +37,46 @@
 
 namespace {
 
+// PHI_HOST_TIMES=1: phase times of the loaders on stderr
+struct PhaseTimer {
+    bool on; double t0;
+    static double now() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+    PhaseTimer() : on(getenv("PHI_HOST_TIMES") != nullptr), t0(now()) {}
+    void lap(const char *what) { if (!on) return; const double t = now(); fprintf(stderr, "[phi_host] %-24s %.3f s\n", what, t - t0); t0 = t; }
+};
+
 bool slurp(const char *path, std::string &out, std::string &err)
 {
+    // size hint: the gzip trailer holds the uncompressed size mod 2^32 (a plain file: its own size); the text is inflated
+    // straight into the string, no staging copy
+    size_t hint = 1 << 20;
+    if (FILE *raw = fopen(path, "rb")) {
+        unsigned char magic[2] = {0, 0}, tail[4];
+        if (fread(magic, 1, 2, raw) == 2 && fseek(raw, 0, SEEK_END) == 0) {
+            const long fsz = ftell(raw);
+            if (magic[0] == 0x1f && magic[1] == 0x8b) {
+                if (fsz >= 18 && fseek(raw, -4, SEEK_END) == 0 && fread(tail, 1, 4, raw) == 4)
+                    hint = (size_t)tail[0] | (size_t)tail[1] << 8 | (size_t)tail[2] << 16 | (size_t)tail[3] << 24;
+                if (hint < (size_t)fsz) hint = (size_t)fsz * 4;                 // wrapped or multi-member: only a starting point
+            } else if (fsz > 0) hint = (size_t)fsz;
+        }
+        fclose(raw);
+    }
     gzFile fp = gzopen(path, "rb");                       // reads plain files too
     if (!fp) { err = std::string("cannot open ") + path; return false; }
     gzbuffer(fp, 1 << 20);
-    std::vector<char> buf(1 << 22);
+    size_t have = 0;
+    out.resize(hint + 1);
     for (;;) {
-        int n = gzread(fp, buf.data(), (unsigned)buf.size());
+        if (have == out.size()) out.resize(out.size() + out.size() / 2 + (1 << 20));
+        const size_t room = std::min<size_t>(out.size() - have, (size_t)1 << 30);
+        const int n = gzread(fp, &out[have], (unsigned)room);
         if (n < 0) { err = std::string("read error in ") + path; gzclose(fp); return false; }
         if (n == 0) break;
-        out.append(buf.data(), (size_t)n);
+        have += (size_t)n;
     }
     gzclose(fp);
+    out.resize(have);
     return true;
 }
 
@@ -80,7 +109,9 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
     if (!gfa_path || !out) return PHI_ERR_ARG;
     *out = nullptr;
     std::string text, e;
+    PhaseTimer pt;
     if (!slurp(gfa_path, text, e)) { set_err(err, errlen, e); return PHI_ERR_ARG; }
+    pt.lap("inflate");
     phi_host_graph *G = new phi_host_graph();
     // Names and sequences are views into `text` while parsing: no per-field std::string, one open-addressing table keyed by the
     // bytes of the name (the reference goes through a khash of strdup'ed names, gfa-base.cpp:75-96).
@@ -99,15 +130,44 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
             const size_t cap = slot.empty() ? (1u << 16) : slot.size() * 2;
             slot.assign(cap, 0xFFFFFFFFu); mask = cap - 1;
             for (uint32_t id = 0; id < names->size(); ++id) {
+                uint32_t num;
+                if (numeric((*names)[id].p, (*names)[id].n, num)) continue;          // lives in `direct`
                 size_t s = hash((*names)[id].p, (*names)[id].n) & mask;
                 while (slot[s] != 0xFFFFFFFFu) s = (s + 1) & mask;
                 slot[s] = id;
             }
         }
+        // Names of the form <fixed prefix><decimal number> (minigraph's s1, s2, ...; plain numbers from vg / pggb) skip the hash
+        // table: the number indexes `direct`.  The prefix is the one of the first such name; a number with a leading zero, more
+        // than 8 digits or another prefix is an ordinary name (hash table), so equal strings always take the same route.
+        std::vector<uint32_t> direct; const char *prefix = nullptr; uint32_t prefix_len = 0; bool have_prefix = false; size_t hashed = 0;
+        bool numeric(const char *p, uint32_t n, uint32_t &num)
+        {
+            uint32_t i = 0;
+            while (i < n && (p[i] < '0' || p[i] > '9')) ++i;
+            const uint32_t nd = n - i;
+            if (nd == 0 || nd > 8 || (p[i] == '0' && nd > 1)) return false;
+            uint32_t v = 0;
+            for (uint32_t q = i; q < n; ++q) { if (p[q] < '0' || p[q] > '9') return false; v = v * 10 + (uint32_t)(p[q] - '0'); }
+            if (v >= (1u << 24)) return false;
+            if (!have_prefix) { have_prefix = true; prefix = p; prefix_len = i; }
+            else if (i != prefix_len || memcmp(p, prefix, i) != 0) return false;
+            num = v;
+            return true;
+        }
         // id of the name, or 0xFFFFFFFF; with add: the name gets the next id
         uint32_t find(const char *p, uint32_t n, bool add)
         {
-            if (slot.empty() || (names->size() + 1) * 10 > slot.size() * 7) grow();
+            uint32_t num;
+            if (numeric(p, n, num)) {
+                if (num < direct.size() && direct[num] != 0xFFFFFFFFu) return direct[num];
+                if (!add) return 0xFFFFFFFFu;
+                if (num >= direct.size()) direct.resize(std::max<size_t>((size_t)num + 1, direct.size() * 2), 0xFFFFFFFFu);
+                View v; v.p = p; v.n = n;
+                direct[num] = (uint32_t)names->size(); names->push_back(v);
+                return direct[num];
+            }
+            if (slot.empty() || (hashed + 1) * 10 > slot.size() * 7) grow();
             size_t s = hash(p, n) & mask;
             for (;; s = (s + 1) & mask) {
                 const uint32_t id = slot[s];
@@ -116,7 +176,7 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
             }
             if (!add) return 0xFFFFFFFFu;
             View v; v.p = p; v.n = n;
-            slot[s] = (uint32_t)names->size(); names->push_back(v);
+            slot[s] = (uint32_t)names->size(); names->push_back(v); ++hashed;
             return slot[s];
         }
     };
@@ -179,8 +239,10 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
         }
         p = next_line;
     }
+    pt.lap("parse lines");
     G->seg_names.reserve(seg_name.size());
     for (const View &v : seg_name) G->seg_names.emplace_back(v.p, v.n);
+    pt.lap("segment names");
     const uint32_t V = (uint32_t)seqs.size();
     // ---- walk flip (gfa-io.cpp:64-115)
     {
@@ -213,6 +275,7 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
         G->walk_off.push_back(G->walk_vtx.size());
         G->walk_names.push_back(walks[h].sample + "." + std::to_string(walks[h].hap));
     }
+    pt.lap("walk flip + flat views");
     // ---- adjacency of the forward vertices after symmetrisation, Kahn order (ILP_index.cpp:77-154)
     {
         std::vector<std::vector<uint32_t>> adj(V);
@@ -235,6 +298,7 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
             for (uint32_t w : adj[u]) if (--indeg[w >> 1] == 0) q.push(w >> 1);
         }
     }
+    pt.lap("adjacency + Kahn order");
     G->view.n_vtx = V; G->view.seg_off = G->seg_off.data(); G->view.seg_bases = (const uint8_t *)G->seg_bases.data();
     G->view.n_walks = (uint32_t)walks.size(); G->view.walk_off = G->walk_off.data(); G->view.walk_vtx = G->walk_vtx.data();
     G->view.top_order_map = G->top_order_map.data();

@@ -109,6 +109,41 @@ def test_gfa_edge_cases_match_the_reference_parser(tmp_path, crlf, gz):
     assert g.walk_vtx[wo[1]:wo[2]].tolist() == [0, 2, 3]           # the reversed walk came out forward
 
 
+GFA_NAMES = "\n".join([
+    "H\tVN:Z:1.1",
+    "S\ts7\tACGTAC",                               # first <prefix><number> name: "s" becomes the prefix of the direct-index route
+    "S\ts07\tGGGA",                                # leading zero: an ordinary name, not s7
+    "S\t7\tTTTT",                                  # no prefix: ordinary
+    "S\tx7\tCCAA",                                 # other prefix: ordinary
+    "S\ts123456789\tAAC",                          # nine digits: ordinary
+    "S\ts16777216\tGT",                            # beyond the direct range: ordinary
+    "S\ts0\tA",
+    "S\ts\tCG",                                    # no digits
+    "S\ts7a\tTG",                                  # digits not at the end
+    "L\ts7\t+\ts07\t+\t0M", "L\ts07\t+\t7\t+\t0M", "L\t7\t+\tx7\t+\t0M", "L\tx7\t+\ts123456789\t+\t0M",
+    "L\ts123456789\t+\ts16777216\t+\t0M", "L\ts16777216\t+\ts0\t+\t0M", "L\ts0\t+\ts\t+\t0M", "L\ts\t+\ts7a\t+\t0M",
+    "L\ts7a\t+\ts9\t+\t0M",                     # s9 first appears on an L-line
+    "S\ts9\tACG",
+    "W\th\t0\tc\t0\t0\t>s7>s07>7>x7>s123456789>s16777216>s0>s>s7a>s9",
+    "W\th\t1\tc\t0\t0\t>s7>s007>s9",           # s007 is unknown: dropped
+    ""]) + "\n"
+
+
+@needs_probe
+def test_gfa_segment_name_routes_match_the_reference_parser(tmp_path):
+    """Names of the form <prefix><number> are looked up through a direct index, everything else through the hash table: the mix
+    of both must number the segments exactly as the reference does."""
+    path = str(tmp_path / "names.gfa")
+    open(path, "w").write(GFA_NAMES)
+    d = probe(path, None, str(tmp_path / "p.phiarr"))
+    ref = phi_io.graph_from_arrays(d)
+    g = phi_b200.load_gfa(path)
+    assert_same_graph(g, ref, ref.walk_names)
+    assert g.segment_names == ["s7", "s07", "7", "x7", "s123456789", "s16777216", "s0", "s", "s7a", "s9"]
+    wo = g.walk_off.astype(int)
+    assert g.walk_vtx[wo[0]:wo[1]].tolist() == list(range(10)) and g.walk_vtx[wo[1]:wo[2]].tolist() == [0, 9]
+
+
 def test_gfa_reverse_strand_walk_is_an_error(tmp_path):
     path = str(tmp_path / "g.gfa")
     with open(path, "w") as f:
