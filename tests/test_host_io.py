@@ -191,3 +191,58 @@ def test_written_fasta_round_trip(tmp_path):
         rd, names = phi_b200.load_reads(path)
         assert np.array_equal(rd.read_off, c.reads.read_off) and np.array_equal(rd.read_bases, c.reads.read_bases)
         assert names[:2] == ["r0", "r1"]
+
+
+@needs_probe
+@pytest.mark.parametrize("seed", range(40))
+def test_random_gfas_match_the_reference_parser(tmp_path, seed):
+    """Random acyclic GFAs with every naming style mixed (numbers, prefixed numbers, leading zeros, words), segments first seen on L-lines
+    (S-lines after their uses), reversed walks, unknown walk steps, CRLF: same numbering, sequences and walks as the reference."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(5, 60))
+    styles = [lambda i: str(i + 1), lambda i: f"s{i + 1}", lambda i: f"s{i + 1:04d}", lambda i: f"node_{i}", lambda i: f"{i + 1}x",
+              lambda i: f"utg{i * 7 + 3}", lambda i: f"s{(i + 1) * 1000003}"]
+    mix = rng.random() < 0.5
+    pick = int(rng.integers(0, len(styles)))
+    names = []
+    for i in range(n):
+        nm = styles[int(rng.integers(0, len(styles))) if mix else pick](i)
+        names.append(nm if nm not in names else nm + f"_{i}")
+    order = rng.permutation(n)                                        # topological order of the DAG: order[a] before order[b] for a < b
+    edges = set()
+    walks = []
+    for _ in range(int(rng.integers(1, 6))):
+        steps = sorted(rng.choice(n, size=int(rng.integers(2, min(n, 12) + 1)), replace=False).tolist())
+        w = [int(order[s]) for s in steps]
+        edges.update(zip(w[:-1], w[1:]))
+        walks.append(w)
+    lines = ["H\tVN:Z:1.1"]
+    recs = [("S", i) for i in range(n)] + [("L", e) for e in edges]   # (the reference crashes on segments that are never defined: all are)
+    rng.shuffle(recs)
+    for kind, x in recs:
+        if kind == "S":
+            seq = "".join(rng.choice(list("ACGTacgtN"), size=int(rng.integers(1, 9))))      # (no '*': the reference crashes on it)
+            lines.append(f"S\t{names[x]}\t{seq}" + ("\tLN:i:5" if rng.random() < 0.2 else ""))
+        else:
+            lines.append(f"L\t{names[x[0]]}\t+\t{names[x[1]]}\t+\t0M")
+    for h, w in enumerate(walks):
+        if rng.random() < 0.3:                                        # written backwards: the flip rule turns it forward again
+            body = "".join("<" + names[v] for v in reversed(w))
+        else:
+            body = "".join(">" + names[v] for v in w)
+        if rng.random() < 0.3:
+            body += ">no_such_segment"
+        lines.append(f"W\tsample{h % 2}\t{h}\tchr\t0\t0\t{body}")
+    text = ("\r\n" if rng.random() < 0.25 else "\n").join(lines) + "\n"
+    path = str(tmp_path / "rand.gfa")
+    open(path, "w", newline="").write(text)
+    p = subprocess.run([PROBE, "-g", path, "-o", str(tmp_path / "p.phiarr"), "--graph-only"], capture_output=True, text=True)
+    if p.returncode == 1 and "reverse strand" in p.stderr:            # a backward walk set the strand of its segments: both refuse
+        with pytest.raises(phi_b200.PhiGpuError):
+            phi_b200.load_gfa(path)
+        return
+    assert p.returncode == 0, p.stderr[-1000:]
+    ref = phi_io.graph_from_arrays(phi_io.read_phiarr(str(tmp_path / "p.phiarr")))
+    g = phi_b200.load_gfa(path)
+    assert_same_graph(g, ref, ref.walk_names)
+    assert_valid_topological_order(g)
