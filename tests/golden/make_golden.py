@@ -147,6 +147,9 @@ if __name__ == "__main__":
     synth_case("synth_k21_w40_long", 15, 60000, 4, 4.0, k=21, w=40, read_len=3000, r_len_sigma=0.3, var_spacing=25, chop=8)
     synth_case("synth_unchopped", 16, 80000, 7, 3.0, chop=100000, T=0.9)
     synth_case("synth_repeats", 17, 30000, 5, 5.0, T=2.0, var_spacing=200)               # T > 1: nothing filtered -> multi-occurrence order
+    # shapes of BASELINE.json configs[2] / configs[3] at a size the reference finishes in seconds (oracle pin only: tests/test_oracle_golden.py)
+    synth_case("shape_long_reads_15kb", 0x50484931 + 2, 60000, 6, 6.0, read_len=15000, r_len_sigma=0.2, r_sub_err=0.01)
+    synth_case("shape_200_haplotypes", 0x50484931 + 3, 12000, 200, 10.0, T=0.335, sv_frac=0.0, max_indel=20, founders=24, block_sites=60)
     make_case("mhc4", f"{REF}/MHC_4.gfa.gz", f"{REF}/CHM13_reads.fq.gz", full_minimizers=False)
     make_case("mhc4_N75", f"{REF}/MHC_4.gfa.gz", f"{REF}/CHM13_reads.fq.gz", full_minimizers=False, store_inputs=False,
               transform=reads_transform(lambda s: s[:74] + "N" + s[75:] if len(s) > 74 else s))

@@ -10,6 +10,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SMALL = ["toy_k3_w2", "toy_defaults", "synth_small", "synth_dirty", "synth_k15_w10", "synth_k32_w1",
          "synth_k21_w40_long", "synth_unchopped", "synth_repeats"]
 MHC = ["mhc4", "mhc4_N75", "mhc4_lower"]
+# shapes of BASELINE.json configs[2] (15 kb reads) and configs[3] (200 haplotypes, fractional threshold): they pin the oracle on those
+# shapes against the unmodified reference (the GPU parity tests of the same shapes compare with the oracle)
+SHAPES = ["shape_long_reads_15kb", "shape_200_haplotypes"]
 
 
 class Case:

@@ -35,7 +35,8 @@ def test_grouping_round_trip():
 
 
 @pytest.mark.parametrize("name,extra,member_bytes", [("toy_k3_w2", ["-k", "3", "-w", "2"], 2), ("synth_small", [], 2), ("synth_dirty", ["-T", "0.5"], 4),
-                                                     ("synth_repeats", ["-T", "2.0"], 2), ("synth_unchopped", [], 2), ("mhc4", [], 2)])
+                                                     ("synth_repeats", ["-T", "2.0"], 2), ("synth_unchopped", [], 2), ("mhc4", [], 2),
+                                                     ("shape_200_haplotypes", ["-T", "0.335"], 2), ("shape_long_reads_15kb", [], 2)])
 def test_model_block_from_the_grouped_result_dumps_the_reference_model(tmp_path, name, extra, member_bytes):
     if not (os.path.exists(EXE) and os.path.exists(REF)):
         pytest.skip("oracle/_ref/PHI_gpu_model / PHI_ref not built (it is built where /root/reference exists and travels with the snapshot)")
