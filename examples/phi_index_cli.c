@@ -1,0 +1,86 @@
+/*
+ * phi_index_cli — the ILP_index front end as a stand-alone command, written against the C ABI only (include/phi_gpu_index.h):
+ * what /root/reference/src/main.cpp + ILP_index::ILP_function do up to line 743, with the same flags and the same log lines.
+ *
+ *   phi_index_cli -g graph.gfa[.gz] -r reads.fa|fq[.gz] [-k 31] [-w 25] [-T 1.0] [-d 0] [-o result.bin]
+ *
+ * -o writes the result in the "PHIRES3" layout integration/phi_adapter_testhook.hpp reads (header of seven u64, then the arrays
+ * of phi_index_result in declaration order, each padded to 8 bytes).  Plain C99: the same calls work from cgo / JNI / ctypes.
+ * Build: gcc -std=c99 -O2 -Iinclude examples/phi_index_cli.c -o phi_index_cli -Lphi_b200 -lphi_gpu_index -Wl,-rpath,$PWD/phi_b200
+ */
+#include "phi_gpu_index.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static void put(FILE *f, const void *p, size_t bytes)
+{
+    static const char zero[8] = {0};
+    if (bytes) fwrite(p, 1, bytes, f);
+    if (bytes & 7) fwrite(zero, 1, 8 - (bytes & 7), f);
+}
+
+int main(int argc, char **argv)
+{
+    const char *gfa = NULL, *reads = NULL, *out = NULL;
+    phi_index_params prm = {31, 25, 1.0f, 0};
+    for (int i = 1; i + 1 < argc; i += 2) {
+        if (!strcmp(argv[i], "-g")) gfa = argv[i + 1];
+        else if (!strcmp(argv[i], "-r")) reads = argv[i + 1];
+        else if (!strcmp(argv[i], "-o")) out = argv[i + 1];
+        else if (!strcmp(argv[i], "-k")) prm.k = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "-w")) prm.w = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "-T")) prm.threshold = (float)atof(argv[i + 1]);
+        else if (!strcmp(argv[i], "-d")) prm.debug = atoi(argv[i + 1]);
+        else { fprintf(stderr, "unknown option %s\n", argv[i]); return 1; }
+    }
+    if (!gfa || !reads) { fprintf(stderr, "usage: phi_index_cli -g graph.gfa -r reads.fq [-k 31] [-w 25] [-T 1.0] [-d 0] [-o result.bin]\n"); return 1; }
+
+    char err[512];
+    phi_host_graph *hg = NULL; phi_host_reads *hr = NULL;
+    if (phi_host_graph_load(gfa, &hg, err, sizeof err) != PHI_OK) { fprintf(stderr, "Error: %s\n", err); return 1; }
+    if (phi_host_reads_load(reads, &hr, err, sizeof err) != PHI_OK) { fprintf(stderr, "Error: %s\n", err); return 1; }
+    const phi_graph_view *g = phi_host_graph_view(hg);
+    const phi_reads_view *rd = phi_host_reads_view(hr);
+    fprintf(stderr, "Graph has %u vertices, %u walks and read has %llu reads\n", g->n_vtx, g->n_walks, (unsigned long long)rd->n_reads);
+
+    phi_gpu_index_ctx *ctx = NULL; phi_index_result *res = NULL;
+    int rc = phi_gpu_index_create(-1, &ctx);
+    if (rc == PHI_OK) rc = phi_gpu_index_run(ctx, g, rd, &prm, &res);
+    if (rc != PHI_OK) { fprintf(stderr, "Error: GPU ILP_index front end failed (%d): %s\n", rc, phi_gpu_last_error(ctx)); return 1; }
+
+    fprintf(stderr, "Number of Minimizers\n");
+    for (uint32_t h = 0; h < g->n_walks; ++h) fprintf(stderr, "%s : %d\n", phi_host_graph_walk_name(hg, h), (int)res->minimizers_per_walk[h]);
+    fprintf(stderr, "Indexed reads with spectrum size: %d\n", res->count_sp_r);
+    fprintf(stderr, "Number of Anchors\n");
+    for (uint32_t h = 0; h < g->n_walks; ++h) fprintf(stderr, "%s : %d\n", phi_host_graph_walk_name(hg, h), (int)res->anchors_per_walk[h]);
+    const long long filtered = res->n_filtered, retained = res->count_sp_r - filtered;
+    fprintf(stderr, "Filtered/Retained Minimizers: %.2f/%.2f%%\n", (float)filtered / (float)res->count_sp_r * 100, (float)retained / (float)res->count_sp_r * 100);
+    phi_stage_times t;
+    if (phi_gpu_index_last_times(ctx, &t) == PHI_OK)
+        fprintf(stderr, "GPU front end: %.3f ms (copies in %.3f ms, out %.3f ms; %llu kernel launches); %llu groups, %llu anchors\n", t.total_ms, t.h2d_ms,
+                t.d2h_ms, (unsigned long long)t.kernel_launches, (unsigned long long)res->n_groups, (unsigned long long)res->n_anchors);
+
+    if (out) {
+        FILE *f = fopen(out, "wb");
+        if (!f) { fprintf(stderr, "Error: cannot write %s\n", out); return 1; }
+        const uint64_t mb = res->member_walk16 ? 2 : 4;
+        const uint64_t head[7] = {(uint64_t)res->count_sp_r, res->n_walks, (uint64_t)res->n_filtered, res->n_anchors, res->n_groups, res->n_group_vtx, mb};
+        fwrite("PHIRES3\0", 1, 8, f); fwrite(head, 8, 7, f);
+        put(f, res->spectrum, 8 * (size_t)res->count_sp_r);
+        put(f, res->rank_off, 4 * ((size_t)res->count_sp_r + 1));
+        put(f, res->group_len, res->n_groups);
+        put(f, res->group_vtx, 4 * res->n_group_vtx);
+        put(f, res->group_member_off, 4 * (res->n_groups + 1));
+        if (mb == 2) put(f, res->member_walk16, 2 * res->n_anchors); else put(f, res->member_walk32, 4 * res->n_anchors);
+        put(f, res->minimizers_per_walk, 8 * (size_t)res->n_walks);
+        put(f, res->anchors_per_walk, 8 * (size_t)res->n_walks);
+        fclose(f);
+    }
+    phi_gpu_index_result_free(res);
+    phi_gpu_index_destroy(ctx);
+    phi_host_reads_free(hr);
+    phi_host_graph_free(hg);
+    return 0;
+}

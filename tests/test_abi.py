@@ -52,3 +52,26 @@ def test_shard_helpers():
     b = np.zeros(4, dtype=np.uint64)
     assert lib.phi_shard_split_by_weight(off.ctypes.data_as(_abi.u64p), 6, 3, b.ctypes.data_as(_abi.u64p)) == 0
     assert b[0] == 0 and b[3] == 6 and list(b) == sorted(b)
+
+
+def test_c_example_builds_against_the_header_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/phi_index_cli.c uses nothing but include/phi_gpu_index.h (plain C99): it must compile without warnings, ingest a GFA and
+    reads through the host loaders, and — without a GPU — stop with the library's error instead of computing anything on the CPU."""
+    import subprocess
+    import torch
+    from phi_b200 import synth
+    from golden_cases import Case
+    exe = str(tmp_path / "phi_index_cli")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "phi_index_cli.c"),
+                           "-o", exe, "-L", os.path.join(ROOT, "phi_b200"), "-lphi_gpu_index", "-Wl,-rpath," + os.path.join(ROOT, "phi_b200")])
+    c = Case("synth_small")
+    gfa, fa = str(tmp_path / "g.gfa"), str(tmp_path / "r.fa")
+    synth.write_gfa(c.graph, gfa)
+    synth.write_fasta(c.reads, fa)
+    p = subprocess.run([exe, "-g", gfa, "-r", fa, "-o", str(tmp_path / "res.bin")], capture_output=True, text=True)
+    assert f"Graph has {c.graph.n_vtx} vertices, {c.graph.n_walks} walks and read has {c.reads.n_reads} reads" in p.stderr
+    if torch.cuda.is_available():
+        assert p.returncode == 0, p.stderr
+        assert f"Indexed reads with spectrum size: {c.meta['count_sp_r']}" in p.stderr
+    else:
+        assert p.returncode == 1 and "no CPU fallback" in p.stderr
