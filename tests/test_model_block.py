@@ -128,3 +128,34 @@ def test_model_blocks_from_several_parts(tmp_path, bounds):
             outs.append((hashlib.sha256(open(dump, "rb").read()).hexdigest(), counts))
         assert outs[0][0] == outs[1][0], f"model dump differs from the reference's for -q{q}"
         assert outs[0][1] == outs[1][1], "scraped per-walk counters differ"
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_group_and_expand_are_inverse_on_random_results(seed):
+    """phi_b200._abi.expand_groups is what every GPU parity test looks through, phi_io.group_anchors what the CPU model tests feed the
+    adapter with: on random anchors (repeated lists, a walk carrying a list twice, vertex ids whose decimal strings are prefixes of one
+    another) grouping and expanding must give the anchors back, in (rank, walk, key order) order."""
+    from phi_b200 import _abi
+    rng = np.random.default_rng(seed)
+    n_ranks, n_walks = int(rng.integers(1, 30)), int(rng.integers(1, 120))
+    pool = [tuple(int(v) for v in rng.choice([1, 10, 100, 11, 2, 20, 9, 90, 99, 12345, 1234, 7], size=int(rng.integers(1, 5)))) for _ in range(12)]
+    anchors = []                                                           # (rank, walk, list), reference order: key string, then insertion
+    for r in range(n_ranks):
+        per_walk = {}
+        for _ in range(int(rng.integers(0, 40))):
+            per_walk.setdefault(int(rng.integers(0, n_walks)), []).append(pool[int(rng.integers(0, len(pool)))])
+        for h in sorted(per_walk):
+            for lst in sorted(per_walk[h], key=lambda t: "".join(f"{v}_" for v in t).encode()):
+                anchors.append((r, h, lst))
+    lens = np.array([len(a[2]) for a in anchors], dtype=np.int64)
+    res = _abi.IndexResultPy(
+        count_sp_r=n_ranks, n_walks=n_walks, n_filtered=0, spectrum=np.arange(n_ranks, dtype=np.uint64),
+        anchor_rank=np.array([a[0] for a in anchors], dtype=np.int32), anchor_walk=np.array([a[1] for a in anchors], dtype=np.int32),
+        anchor_off=np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64),
+        anchor_vtx=np.array([v for a in anchors for v in a[2]], dtype=np.int32),
+        minimizers_per_walk=np.zeros(n_walks, dtype=np.uint64), anchors_per_walk=np.zeros(n_walks, dtype=np.uint64))
+    rank_off, glen, gvtx, moff, mwalk = phi_io.group_anchors(res)
+    grank = np.repeat(np.arange(n_ranks, dtype=np.int32), np.diff(rank_off.astype(np.int64)))
+    a_rank, a_walk, a_off, a_vtx = _abi.expand_groups(grank, glen, gvtx, moff, mwalk)
+    assert np.array_equal(a_rank, res.anchor_rank) and np.array_equal(a_walk, res.anchor_walk)
+    assert np.array_equal(a_off, res.anchor_off) and np.array_equal(a_vtx, res.anchor_vtx)
