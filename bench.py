@@ -2,18 +2,30 @@
 """bench.py — the ILP_index front end on N B200s, one JSON line (driver contract).
 
 A "step" is one pass of the hot path (/root/reference/src/ILP_index.cpp:543-743: read sketch ->
-ranked spectrum -> walk sketch + match -> threshold filter -> anchor CSR) over one batch of synthetic
-input of the shape BASELINE.json configs[1] names: an MHC-shaped acyclic graph, 49 haplotypes x ~5 Mbp,
-150 bp reads at 10x.
+ranked spectrum -> walk sketch + match -> threshold filter -> grouped anchors) over one batch of synthetic
+input of a shape BASELINE.json names (--config):
 
-  value  : (read k-mer positions + path k-mer positions) / s, inputs resident in HBM, wall clock over K steps
-           bracketed by device synchronisation (the pipeline's own CUDA-event stage times are reported too).
-  e2e    : the same through phi_gpu_index_run() — host buffers in, host CSR out, H2D/D2H inside the timed region.
-  --impl reference : the UNMODIFIED reference CLI (oracle/_ref/PHI_ref: reference sources + recording Gurobi
-           stub) on the box's host cores, bounded sample of the same workload, front-end stage timed from
-           the reference's own log stamps.
+  readme  configs[0]  test/MHC_4.gfa.gz + test/CHM13_reads.fq.gz (the inputs are kept in tests/golden/mhc4.npz)
+  c2      configs[1]  MHC-shaped graph, 49 haplotypes x ~5 Mbp, 150 bp reads at --coverage 0.1 / 1 / 10 (default 10)
+  c3long  configs[2]  the same graph, 15 kb reads at 10x
+  c4      configs[3]  vcf2gfa-shaped graph, 200 haplotypes x 50 Mbp, 10x 150 bp reads            (DEFAULT: the config the
+                      metric "... at 1/2/4/8 B200" is quoted on; it fits one GPU)
+  c5      configs[4]  500 haplotypes x 150 Mbp, 30x reads, meant for 8 GPUs (--gpus 1 runs the slice rank 0 of 8 would get)
+
+--gpus N > 1 is STRONG scaling: ONE fixed global input, sharded over the ranks (reads by bases, walks by region of the
+topological coordinate — phi_b200/multi.py), exchanged inside the library over NCCL.  After the timed region the per-rank
+parts are merged (phi_index_result_merge) and a sha256 over the merged result is printed as `result_digest`: it is the
+same at every N.  `parity_n` is a bounded case run through the same N-rank path and compared with the CPU oracle.
+
+  value  : (read k-mer positions + path k-mer positions) / s, inputs resident in HBM, K steps bracketed by barrier +
+           device synchronise, max over ranks.
+  e2e    : the same through phi_gpu_index_run() — host buffers in, host result out, H2D/D2H inside the timed region.
+  --impl reference : the UNMODIFIED reference CLI (oracle/_ref/PHI_ref: reference sources + recording Gurobi stub) on
+           the box's host cores, front-end stage timed from the reference's own log stamps; readme / c2 / c3long run in
+           full, c4 / c5 on a stated slice (the reference's data structures cannot hold them).
 """
 import argparse
+import hashlib
 import json
 import os
 import re
@@ -28,9 +40,24 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SEED = 0x50484931 + 1          # "PHI1" + config index
+SEED0 = 0x50484931             # "PHI1" + config index
 METRIC = "read k-mers counted/s + path k-mers matched/s (ILP_index front end)"
 UNIT = "k-mers/s"
+
+CONFIGS = {
+    # name: (index in BASELINE.json configs, seed, backbone, haplotypes, read length, coverage, generator keywords, description)
+    "readme": dict(idx=0, desc="BASELINE configs[0]: README test, MHC_4.gfa.gz (5 walks x ~5 Mbp) + CHM13_reads.fq.gz (16,401 x 150 bp)"),
+    "c2": dict(idx=1, backbone=5_000_000, haps=49, read_len=150, coverage=10.0, gen=dict(founders=8),
+               desc="BASELINE configs[1]: synthetic MHC-shaped acyclic graph, 49 haplotypes x ~5 Mbp, nodes chopped to <=30 bp, 150 bp reads"),
+    "c3long": dict(idx=2, backbone=5_000_000, haps=49, read_len=15000, coverage=10.0, gen=dict(founders=8), graph_seed_idx=1,
+                   desc="BASELINE configs[2]: the configs[1] graph (49 haplotypes x ~5 Mbp) with 15 kb long reads (log-normal, sigma 0.2, 1 % errors)"),
+    "c4": dict(idx=3, backbone=50_000_000, haps=200, read_len=150, coverage=10.0, gen=dict(founders=16, sv_frac=0.0, max_indel=50),
+               desc="BASELINE configs[3]: vcf2gfa-shaped graph (SNV/indel bubbles, -m 30 chopping), 200 haplotypes x 50 Mbp, 150 bp reads"),
+    "c5": dict(idx=4, backbone=150_000_000, haps=500, read_len=150, coverage=30.0, gen=dict(founders=24, sv_frac=0.0, max_indel=50),
+               desc="BASELINE configs[4]: chromosome-scale graph, 500 haplotypes x 150 Mbp, 150 bp reads"),
+}
+BIG = ("c4", "c5")
+C5_WORLD = 8                    # configs[4] is defined on 8 GPUs; fewer GPUs run the first ranks' slices of the 8-way partition
 
 
 def parse_args():
@@ -39,28 +66,145 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="phi_b200", choices=["phi_b200", "reference"])
-    ap.add_argument("--haps", type=int, default=49)
-    ap.add_argument("--backbone", type=int, default=5_000_000)
-    ap.add_argument("--coverage", type=float, default=10.0)
-    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--coverage", type=float, default=None, help="read coverage (default: the config's)")
+    ap.add_argument("--haps", type=int, default=None)
+    ap.add_argument("--backbone", type=int, default=None)
+    ap.add_argument("--founders", type=int, default=None, help="distinct local haplotypes per LD block of the generator")
     ap.add_argument("-k", type=int, default=31)
     ap.add_argument("-w", type=int, default=25)
-    ap.add_argument("--cpu-walks", type=int, default=0, help="walks in the CPU-baseline sample (0: min(nproc, haps, 16))")
-    ap.add_argument("--cpu-coverage", type=float, default=0.5)
+    ap.add_argument("--partition", default="region", choices=["region", "walk"], help="how the walks are sharded over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
-
-
-def workload(args):
-    from phi_b200 import synth
-    sg = synth.make_graph(SEED, args.backbone, args.haps)
-    rd = synth.make_reads(SEED, sg, args.coverage, read_len=args.read_len)
-    return sg, rd
+    ap.add_argument("--no-extras", action="store_true", help="skip digest / parity_n / no-sharing extras (profiling runs)")
+    ap.add_argument("--cpu-walks", type=int, default=0, help="walks in the reference slice of c4/c5 (0: min(nproc, 16))")
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    if a.config != "readme":
+        a.coverage = c["coverage"] if a.coverage is None else a.coverage
+        a.haps = c["haps"] if a.haps is None else a.haps
+        a.backbone = c["backbone"] if a.backbone is None else a.backbone
+        a.read_len = c["read_len"]
+        a.gen = dict(c["gen"])
+        if a.founders is not None:
+            a.gen["founders"] = a.founders
+    return a
 
 
 def positions(lengths, k, w):
     lengths = np.asarray(lengths, dtype=np.int64)
     return int(np.sum(np.where(lengths >= w + k - 1, lengths - k + 1, 0)))
+
+
+# ------------------------------------------------------------------ workloads
+class Workload:
+    """One fixed GLOBAL input + the shard of it a rank works on."""
+
+    def __init__(self, args):
+        self.args, self.name = args, args.config
+        self.k, self.w, self.T = args.k, args.w, 1.0
+        c = CONFIGS[self.name]
+        self.seed = SEED0 + c["idx"]
+        self.graph_seed = SEED0 + c.get("graph_seed_idx", c["idx"])
+        self.sg = None
+
+    def describe(self):
+        a, c = self.args, CONFIGS[self.name]
+        if self.name == "readme":
+            return c["desc"] + f", k={self.k} w={self.w} T={self.T:g}"
+        return (c["desc"] + f" at {a.coverage:g}x; generator: {a.haps} haplotypes x {a.backbone / 1e6:g} Mbp backbone, "
+                f"{a.gen.get('founders', 8)} distinct local haplotypes per LD block of 400 sites, k={self.k} w={self.w} T={self.T:g}")
+
+    # ---- small configs: the whole input on every rank, then the library's own partition helpers
+    def _small(self):
+        from phi_b200 import synth
+        a = self.args
+        if self.name == "readme":
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from golden_cases import Case
+            c = Case("mhc4")
+            return c.graph, c.reads
+        sg = synth.make_graph(self.graph_seed, a.backbone, a.haps, **a.gen)
+        if self.name == "c3long":
+            rd = synth.make_reads(self.seed, sg, a.coverage, read_len=a.read_len, len_sigma=0.2, sub_err=0.01)
+        else:
+            rd = synth.make_reads(self.seed, sg, a.coverage, read_len=a.read_len)
+        return sg.graph, rd
+
+    def shard(self, rank, world):
+        """(graph shard, reads shard, walk_id_base, n_walks_global, region or None, global units (P, Q) or None)."""
+        from phi_b200 import multi, synth, _abi
+        a = self.args
+        if self.name not in BIG:
+            g, rd = self._small()
+            P = positions(g.walk_lengths(), self.k, self.w)
+            Q = positions(np.diff(rd.read_off.astype(np.int64)), self.k, self.w)
+            if world == 1:
+                return g, rd, 0, g.n_walks, None, (P, Q)
+            gs, rs, base, region = multi.shard_inputs(g, rd, rank, world, self.k, self.w, a.partition)
+            return gs, rs, base, g.n_walks, region, (P, Q)
+        # ---- chromosome-scale configs: never hold the whole walk set; spell walk after walk and keep this rank's part
+        part_world, part_rank = world, rank
+        if self.name == "c5" and world < C5_WORLD:
+            part_world = C5_WORLD                                   # the slice rank `rank` of the 8-way partition would get
+        sg = synth.make_graph(self.graph_seed, a.backbone, a.haps, walk_range=(0, 0), **a.gen)
+        self.sg = sg
+        g0 = sg.graph
+        seg_len = np.diff(g0.seg_off.astype(np.int64))
+        seq = synth.mosaic_sequence(self.seed, sg)
+        n_reads = synth.n_reads_big(len(seq), a.coverage, a.read_len)
+        rlo, rhi = n_reads * part_rank // part_world, n_reads * (part_rank + 1) // part_world
+        rd = synth.make_reads_big(self.seed, sg, a.coverage, read_len=a.read_len, read_range=(rlo, rhi), seq=seq)
+        Q = n_reads * (min(a.read_len, len(seq)) - self.k + 1)
+        del seq
+        region, base = None, 0
+        bounds = None
+        if part_world > 1 and a.partition == "region":
+            sample = [sg.walk_of(sg.allele_row(h)) for h in range(0, a.haps, max(1, a.haps // 4))][:4]
+            gsample = _abi.Graph(g0.seg_off, g0.seg_bases, np.concatenate([[0], np.cumsum([len(x) for x in sample])]),
+                                 np.concatenate(sample), g0.top_order_map)
+            bounds = multi.region_bounds(gsample, part_world)
+            region = (int(bounds[part_rank]), int(bounds[part_rank + 1]))
+        walks, P = [], 0
+        wlo, whi = 0, a.haps
+        if part_world > 1 and a.partition == "walk":
+            wlo, whi = a.haps * part_rank // part_world, a.haps * (part_rank + 1) // part_world
+            base = wlo
+        BATCH = 8
+        for h0 in range(0, a.haps, BATCH):
+            full = [sg.walk_of(sg.allele_row(h)) for h in range(h0, min(h0 + BATCH, a.haps))]
+            for x in full:
+                P += positions([int(seg_len[x].sum())], self.k, self.w)
+            if region is not None:
+                gb = _abi.Graph(g0.seg_off, g0.seg_bases, np.concatenate([[0], np.cumsum([len(x) for x in full])]),
+                                np.concatenate(full), g0.top_order_map)
+                sl = multi.slice_walks(gb, self.k, self.w, region[0], region[1])
+                so = sl.walk_off.astype(np.int64)
+                walks.extend(sl.walk_vtx[so[i]:so[i + 1]] for i in range(len(full)))
+            else:
+                walks.extend(x for i, x in enumerate(full) if wlo <= h0 + i < whi)
+        gs = _abi.Graph(g0.seg_off, g0.seg_bases, np.concatenate([[0], np.cumsum([len(x) for x in walks])]).astype(np.uint64),
+                        np.concatenate(walks).astype(np.uint32) if walks else np.zeros(0, dtype=np.uint32), g0.top_order_map)
+        units = (P, Q)
+        if self.name == "c5" and world < C5_WORLD:
+            units = None                                            # a slice: the units are what the ranks report
+        return gs, rd, base, a.haps, region, units
+
+    # ---- what the reference arm (and the cpu_baseline leg) runs
+    def reference_input(self, threads):
+        """(graph, reads, sample description, full?) for the CPU reference."""
+        from phi_b200 import synth
+        a = self.args
+        if self.name not in BIG:
+            g, rd = self._small()
+            return g, rd, "the full configuration (all walks, all reads); front-end stage only (log stamps 'Graph has' -> 'Filtered/Retained')", True
+        n_walks = a.cpu_walks or min(threads, a.haps, 16)
+        frac = 10 if self.name == "c4" else 30
+        sg = synth.make_graph(self.graph_seed, a.backbone // frac, a.haps, walk_range=(0, n_walks), **a.gen)
+        rd = synth.make_reads_big(self.seed, sg, a.coverage if self.name == "c4" else a.coverage / 3, read_len=a.read_len)
+        desc = (f"SLICE (the reference's kmer_index / Anchor_hits / in_paths cannot hold this config, BASELINE.md §3): the same generator on 1/{frac} of the "
+                f"backbone ({a.backbone // frac / 1e6:g} Mbp), {n_walks} of its {a.haps} walks, {rd.n_reads} reads of {a.read_len} bp; per-k-mer rate, "
+                f"EXTRAPOLATED to the full config; front-end stage only (log stamps 'Graph has' -> 'Filtered/Retained')")
+        return sg.graph, rd, desc, False
 
 
 # ------------------------------------------------------------------ clocks
@@ -101,33 +245,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------ CPU reference (bounded sample)
-def run_reference_sample(sg, rd, args, n_walks, cov, threads):
-    """Times the reference's own front end (log-stamp deltas) on `n_walks` walks of the graph and a
-    `cov`-coverage prefix of the reads.  Kills the process once the front end is done (model construction is not timed)."""
+# ------------------------------------------------------------------ CPU reference
+def run_reference(g, rd, k, w, threads):
+    """Times the reference's own front end (log-stamp deltas) on the given graph and reads.  Kills the process once
+    the front end is done (model construction is not timed)."""
     from phi_b200 import synth
     exe = os.path.join(ROOT, "oracle", "_ref", "PHI_ref")
-    g = sg.graph
-    n_reads = max(1, int(rd.n_reads * cov / args.coverage))
-    sub_reads = rd.take(0, n_reads)
-    wl = g.walk_lengths()[:n_walks]
-    P = positions(wl, args.k, args.w)
-    Q = positions(np.diff(sub_reads.read_off.astype(np.int64)), args.k, args.w)
+    P = positions(g.walk_lengths(), k, w)
+    Q = positions(np.diff(rd.read_off.astype(np.int64)), k, w)
     if not os.path.exists(exe):
         # the reference did not compile here: time the plain-C port instead (kind "port")
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import phi_io
         t0 = time.time()
-        phi_io.oracle_index(g.take_walks(0, n_walks), sub_reads, args.k, args.w, 1.0, threads)
+        phi_io.oracle_index(g, rd, k, w, 1.0, threads)
         dt = time.time() - t0
         return dict(kind="port", P=P, Q=Q, t_index=dt, t_reads=None, t_paths=None)
     with tempfile.TemporaryDirectory() as tmp:
         gfa, fa = os.path.join(tmp, "g.gfa"), os.path.join(tmp, "r.fa")
-        synth.write_gfa(g, gfa, walks=range(n_walks))
-        synth.write_fasta(sub_reads, fa)
+        synth.write_gfa(g, gfa)
+        synth.write_fasta(rd, fa)
         env = dict(os.environ, PHI_STUB_DUMP=os.path.join(tmp, "dump.txt"))
-        p = subprocess.Popen([exe, "-g", gfa, "-r", fa, "-o", os.path.join(tmp, "o.fa"), "-t", str(threads), "-k", str(args.k),
-                              "-w", str(args.w)], env=env, stderr=subprocess.PIPE, stdout=subprocess.DEVNULL, text=True)
+        p = subprocess.Popen([exe, "-g", gfa, "-r", fa, "-o", os.path.join(tmp, "o.fa"), "-t", str(threads), "-k", str(k),
+                              "-w", str(w)], env=env, stderr=subprocess.PIPE, stdout=subprocess.DEVNULL, text=True)
         stamps = {}
         for line in p.stderr:
             m = re.match(r"\[M::ILP_function::([\d.]+)\*", line)
@@ -145,42 +285,36 @@ def run_reference_sample(sg, rd, args, n_walks, cov, threads):
     return dict(kind="reference", P=P, Q=Q, t_index=t_a + t_b + t_c, t_reads=t_b, t_paths=t_a + t_c)
 
 
-def cpu_sample_desc(n_walks, cov, args):
-    return (f"{n_walks} of {args.haps} walks (~{args.backbone / 1e6:g} Mbp each) + {cov:g}x of the {args.read_len} bp reads; "
-            f"front-end stage only (log stamps 'Graph has' -> 'Filtered/Retained')")
+def config_dict(wl, n):
+    return {"workload": wl.describe(), "seed": wl.seed, "gpus": n,
+            "l2": "no explicit flush: the per-step working set (walk steps, step offsets, chunk table, reads, spectrum table, hit and "
+                  "group buffers: > 400 MB per GPU) exceeds the 126 MB L2"}
 
 
 def main_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
+    wl = Workload(args)
     threads = os.cpu_count() or 1
-    sg, rd = workload(args)
-    n_walks = args.cpu_walks or min(threads, args.haps, 16)
-    vals, times = [], []
+    g, rd, desc, full = wl.reference_input(threads)
+    vals, times, r = [], [], None
     for i in range(args.warmup + args.steps):
-        r = run_reference_sample(sg, rd, args, n_walks, args.cpu_coverage, threads)
+        r = run_reference(g, rd, args.k, args.w, threads)
         if i >= args.warmup:
             vals.append((r["P"] + r["Q"]) / r["t_index"])
             times.append(r["t_index"])
     v = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8/u64", "data": "synthetic",
-            "config": config_dict(args, 1),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": r["kind"],
-                             "sample": cpu_sample_desc(n_walks, args.cpu_coverage, args)},
+            "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8/u64", "data": "synthetic" if args.config != "readme" else "README test files",
+            "config": config_dict(wl, args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": r["kind"], "sample": desc, "full_config": full,
+                             "units_per_step": {"read_kmer_positions": r["Q"], "path_kmer_positions": r["P"]},
+                             "read_kmers_per_s": r["Q"] / r["t_reads"] if r["t_reads"] else None,
+                             "path_kmers_per_s": r["P"] / r["t_paths"] if r["t_paths"] else None},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
-
-
-def config_dict(args, n):
-    return {"workload": f"BASELINE configs[1]: synthetic MHC-shaped acyclic graph, {args.haps} haplotypes x ~{args.backbone / 1e6:g} Mbp, "
-                        f"nodes chopped to <=30 bp, {args.read_len} bp reads at {args.coverage:g}x, k={args.k} w={args.w} T=1.0",
-            "seed": SEED, "gpus": n, "cpu_affinity": getattr(args, "cpu_affinity", "unchanged"),
-            "l2": "no explicit flush: per-step working set (walk steps, step offsets, chunk table, reads, "
-                  "spectrum table, hit and anchor buffers: > 400 MB) exceeds the 126 MB L2"}
 
 
 def bind_to_gpu_numa(device):
@@ -217,134 +351,303 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def walk_kernel_algorithmic_bytes(res, g, k):
-    """SURVEY.md §8(d) per-unit figure x units of one launch, with this run's measured densities:
-    0.25 B/position 2-bit segment store + 4 B per walk step (vertex id) + 32 B probe sector per emitted minimizer
-    + per hit a 16 B record and 4 B per anchor vertex.  Units = ALL path k-mer positions the launch accounts for (the
-    result covers every walk); with walk sharing the kernel physically sketches only the representative chunks, see
-    roofline.sharing."""
-    P = res.path_kmer_positions
-    steps = len(g.walk_vtx)
-    hit_vtx = res.path_hits * (1.0 + (k - 1) / max(1.0, (g.walk_lengths().sum() / max(1, steps))))
-    return 0.25 * P + 4.0 * steps + 32.0 * res.path_minimizers_emitted + 16.0 * res.path_hits + 4.0 * hit_vtx
-
-
-def read_kernel_algorithmic_bytes(res, rd):
-    """SURVEY.md §8(d), the part of the per-read-k-mer figure that belongs to the read sketch kernel: the ASCII bases once
-    + per emitted minimizer a 32 B table sector read and written."""
-    return float(rd.read_bases.nbytes) + 64.0 * res.read_minimizers_emitted
-
-
-def kernel_traffic(name):
+def kernel_profile(name):
+    """ncu numbers of the current build (profiles/kernel_traffic.json; re-captured per round, version inside)."""
     tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     try:
-        return float(json.load(open(tp))[name]["dram_bytes_per_launch"])
+        j = json.load(open(tp))
+        return j.get(name, {}), j.get("source")
     except Exception:
-        return None
+        return {}, None
+
+
+def result_digest(res):
+    """sha256 over the merged result in global order: the ranked spectrum, first group of every rank, the vertex lists, the member
+    walks, per-walk counters, filtered ranks.  Independent of the number of GPUs."""
+    h = hashlib.sha256()
+    for a, dt in ((res.spectrum, np.uint64), (res.rank_off if res.rank_off is not None else np.zeros(1), np.uint32), (res.group_len, np.uint8),
+                  (res.group_vtx, np.int32), (res.group_member_off, np.uint32), (res.member_walk, np.int32),
+                  (res.minimizers_per_walk, np.uint64), (res.anchors_per_walk, np.uint64)):
+        h.update(np.ascontiguousarray(a, dtype=dt).tobytes())
+    h.update(np.array([res.count_sp_r, res.n_filtered, res.n_walks], dtype=np.int64).tobytes())
+    return h.hexdigest()
+
+
+class Dist:
+    """torch.distributed plumbing (barrier, max / sum over ranks, object hand-round); a no-op at world 1."""
+
+    def __init__(self, rank, world, local):
+        self.rank, self.world = rank, world
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+            self.torch, self.dist = torch, dist
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def reduce(self, values, op="sum"):
+        if self.world == 1:
+            return [float(v) for v in values]
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def bcast_obj(self, obj):
+        if self.world == 1:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def gather_results(self, part, tag):
+        """Per-rank results -> list on rank 0 (through /dev/shm: the parts can be hundreds of MB)."""
+        if self.world == 1:
+            return [part]
+        import pickle
+        d = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(), f"phi_bench_{os.environ.get('MASTER_PORT', '0')}_{tag}")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, f"part{self.rank}.pkl"), "wb") as f:
+            pickle.dump(part, f, protocol=4)
+        self.dist.barrier()
+        parts = None
+        if self.rank == 0:
+            parts = []
+            for r in range(self.world):
+                with open(os.path.join(d, f"part{r}.pkl"), "rb") as f:
+                    parts.append(pickle.load(f))
+                os.remove(os.path.join(d, f"part{r}.pkl"))
+            os.rmdir(d)
+        self.dist.barrier()
+        return parts
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def setup_index(local, rank, world, base, n_walks_global, region, D):
+    import phi_b200
+    ix = phi_b200.PhiGpuIndex(local)
+    if world > 1:
+        uid = D.bcast_obj(ix.comm_unique_id() if rank == 0 else None)
+        ix.comm_init(rank, world, uid, base, n_walks_global)
+    if region is not None:
+        ix.set_walk_region(region[0], region[1])
+    return ix
+
+
+def parity_case(rank, world, local, D, partition):
+    """A bounded case (dirty bytes included) through the same N-rank path, merged and compared with the CPU oracle on the unsharded
+    input.  The oracle is the checker here, nothing else (oracle/phi_oracle.h)."""
+    from phi_b200 import synth, multi
+    sg = synth.make_graph(4242, 400_000, 11, lower_frac=0.004, n_frac=0.001)
+    rd = synth.make_reads(4242, sg, 3.0, lower_frac=0.004, n_frac=0.001)
+    k, w, T = 31, 25, 0.9
+    if world == 1:
+        gs, rs, base, region = sg.graph, rd, 0, None
+    else:
+        gs, rs, base, region = multi.shard_inputs(sg.graph, rd, rank, world, k, w, partition)
+    ix = setup_index(local, rank, world, base, sg.graph.n_walks, region, D)
+    part = ix.run(gs, rs, k, w, T, expand=False)
+    ix.close()
+    parts = D.gather_results(part, "parity")
+    verdict = None
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import phi_io
+        got = multi.merge_results(parts)
+        want = phi_io.oracle_index(sg.graph, rd, k, w, T)
+        ok = (got.count_sp_r == want.count_sp_r and got.n_filtered == want.n_filtered
+              and all(np.array_equal(getattr(got, f), getattr(want, f)) for f in
+                      ("spectrum", "anchor_rank", "anchor_walk", "anchor_off", "anchor_vtx", "minimizers_per_walk", "anchors_per_walk"))
+              and got.path_kmer_positions == want.path_kmer_positions and got.read_kmer_positions == want.read_kmer_positions)
+        verdict = "ok" if ok else "MISMATCH"
+    return D.bcast_obj(verdict)
 
 
 def main_gpu(args):
-    import phi_b200
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     all_cpus = os.sched_getaffinity(0)
-    args.cpu_affinity = bind_to_gpu_numa(local)
-    if world > 1:
-        from phi_b200 import multi
-        return multi.bench_main(args, rank, world, local, globals())
-    sg, rd = workload(args)
-    g = sg.graph
-    ix = phi_b200.PhiGpuIndex(local)
-    k, w = args.k, args.w
+    affinity = bind_to_gpu_numa(local)
+    D = Dist(rank, world, local)
+    wl = Workload(args)
+    k, w, T = wl.k, wl.w, wl.T
+    t_gen = time.time()
+    g, rd, base, n_walks_global, region, units_global = wl.shard(rank, world)
+    t_gen = time.time() - t_gen
+    ix = setup_index(local, rank, world, base, n_walks_global, region, D)
+
+    def timed(fn):
+        D.barrier()
+        t0 = time.perf_counter()
+        out = fn()                                           # every run ends with a stream synchronise inside the library
+        dt = time.perf_counter() - t0
+        dt = D.reduce([dt], "max")[0]                        # max over ranks
+        D.barrier()
+        return dt, out
 
     # ---- resident: inputs already in HBM when the timed region starts
     ix.upload(g, rd)
-    clocks = ClockSampler(local)                                # samples from the first warm-up step to the end of the e2e loop:
-    clocks.start()                                              # the GPU is busy for that whole interval (steps are ~10 ms each)
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(args.warmup):
-        res = ix.run_resident(k, w, 1.0, download=False)
+        res = ix.run_resident(k, w, T, download=False)
     stage = []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = ix.run_resident(k, w, 1.0, download=False)        # ends with a stream synchronise
-        stage.append(ix.times())
-    dt = time.perf_counter() - t0
-    units = res.read_kmer_positions + res.path_kmer_positions
-    value = units * args.steps / dt
+
+    def steps():
+        r = None
+        for _ in range(args.steps):
+            r = ix.run_resident(k, w, T, download=False)
+            stage.append(ix.times())
+        return r
+    dt, res = timed(steps)
+    share = ix.sharing()
     tm = {key: float(np.mean([s[key] for s in stage])) for key in stage[0]}
 
-    # ---- end to end through the drop-in call: host buffers -> host CSR
-    # inputs sit in pinned host memory (phi_gpu_host_alloc), the result lands in pinned memory owned by the library;
-    # every step copies all inputs host->device and the whole CSR device->host inside the timed region
+    # ---- end to end through the drop-in call: pinned host buffers -> host result; every step copies all inputs host->device
+    # and the whole result device->host inside the timed region
     gp, rp = ix.pinned_inputs(g, rd)
     for _ in range(args.warmup):
-        ix.free_raw(ix.run_raw(gp, rp, k, w, 1.0))
+        ix.free_raw(ix.run_raw(gp, rp, k, w, T))
     e2e_stage = []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        raw = ix.run_raw(gp, rp, k, w, 1.0)
-        n_anchors_seen = raw.contents.n_anchors           # the caller reads the result
-        ix.free_raw(raw)
-        e2e_stage.append(ix.times())
-    dt_e2e = time.perf_counter() - t0
+
+    def e2e_steps():
+        n = 0
+        for _ in range(args.steps):
+            raw = ix.run_raw(gp, rp, k, w, T)
+            n = raw.contents.n_anchors                       # the caller reads the result
+            ix.free_raw(raw)
+            e2e_stage.append(ix.times())
+        return n
+    dt_e2e, n_anchors_seen = timed(e2e_steps)
     clk = clocks.stop()
-    full = ix.run(gp, rp, k, w, 1.0)
+    full = ix.run(gp, rp, k, w, T, expand=False)
     assert full.n_anchors == n_anchors_seen
     h2d = sum(a.nbytes for a in (g.seg_off, g.seg_bases, g.walk_off, g.walk_vtx, g.top_order_map, rd.read_off, rd.read_bases))
     d2h = full.wire_bytes()
-    e2e_value = units * args.steps / dt_e2e
+
+    # ---- sums over the ranks
+    loc = [res.read_kmer_positions, res.path_kmer_positions, res.read_minimizers_emitted, full.path_minimizers_emitted, res.path_hits,
+           h2d, d2h, share["unique_windows"], share["unique_hits"], len(g.walk_vtx), int(tm["kernel_launches"]), share["chunks"], share["tiles"]]
+    tot = D.reduce(loc, "sum")
+    Q_run, P_run = tot[0], tot[1]
+    if units_global is not None:
+        assert (int(P_run), int(Q_run)) == (units_global[0], units_global[1]), ("units", P_run, Q_run, units_global)
+    units = P_run + Q_run
+    tmax = dict(zip(tm, D.reduce(list(tm.values()), "max")))
+
+    extras = {}
+    if not args.no_extras:
+        # ---- the merged result and its digest (the same at every N), the N-rank parity case
+        t0 = time.time()
+        parts = D.gather_results(full, "digest")
+        if rank == 0:
+            from phi_b200 import multi
+            t1 = time.time()
+            merged = multi.merge_results(parts, expand=False) if world > 1 else full
+            extras["merge_ms"] = (time.time() - t1) * 1e3
+            extras["result_digest"] = result_digest(merged)
+            extras["result"] = {"spectrum": merged.count_sp_r, "groups": merged.n_groups, "anchors": int(len(merged.member_walk)),
+                                "group_vertices": int(len(merged.group_vtx)), "filtered_ranks": merged.n_filtered}
+            del merged
+        del parts
+        extras["parity_n"] = parity_case(rank, world, local, D, args.partition)
+        # ---- the same resident step with walk sharing switched off (every chunk of every walk sketched on its own), when it fits
+        est_hits = tot[1] / max(1, world) * 2.0 / (w + 1.0) * 1.3
+        if est_hits * 40 < 60e9 and est_hits < 3.5e9:
+            ix.set_walk_sharing(share=False)
+            for _ in range(2):
+                ix.run_resident(k, w, T, download=False)
+            st2 = []
+
+            def ns_steps():
+                for _ in range(3):
+                    ix.run_resident(k, w, T, download=False)
+                    st2.append(ix.times())
+            dt_ns, _ = timed(ns_steps)
+            extras["no_sharing"] = {"value": units * 3 / dt_ns, "ms_per_step": dt_ns / 3 * 1e3,
+                                    "walk_kernel_ms": float(np.mean([s["walk_kernel_ms"] for s in st2])),
+                                    "note": "walk sharing off (phi_gpu_index_set_walk_sharing share=0): every chunk of every walk is sketched; same result"}
+            ix.set_walk_sharing(share=True)
+        else:
+            extras["no_sharing"] = None
 
     peak, peak_src = measured_peak()
-    share = ix.sharing()
-    kernels = {}
-    for name, ms, alg in (("walk_sketch_kernel", tm["walk_kernel_ms"], walk_kernel_algorithmic_bytes(res, g, k)),
-                          ("read_sketch_kernel", tm["read_kernel_ms"], read_kernel_algorithmic_bytes(res, rd))):
-        ach = alg / (ms * 1e-3) / 1e9
-        kernels[name] = {"kernel_ms": ms, "algorithmic_bytes_per_launch": alg, "achieved": ach, "frac": ach / peak, "traffic": kernel_traffic(name)}
-    dom = max(kernels, key=lambda n: kernels[n]["kernel_ms"])                # the dominant kernel of the step
-    frac_unique = share["unique_windows"] / max(1, res.path_kmer_positions)
-    kernels["walk_sketch_kernel"]["achieved_physical"] = kernels["walk_sketch_kernel"]["achieved"] * frac_unique
-
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8/u64", "data": "synthetic", "config": config_dict(args, 1),
-            "read_kmers_per_s": res.read_kmer_positions / ((tm["read_sketch_ms"] + tm["spectrum_ms"]) * 1e-3),
-            "path_kmers_per_s": res.path_kmer_positions / ((tm["graph_prep_ms"] + tm["walk_sketch_ms"] + tm["filter_ms"]) * 1e-3),
-            "index_wall_s": dt_e2e / args.steps,
-            "units_per_step": {"read_kmer_positions": res.read_kmer_positions, "path_kmer_positions": res.path_kmer_positions,
-                               "read_minimizers": res.read_minimizers_emitted, "path_minimizers": res.path_minimizers_emitted,
-                               "path_hits": res.path_hits, "spectrum": res.count_sp_r, "anchors": full.n_anchors,
-                               "filtered_ranks": full.n_filtered},
-            "stage_ms": tm,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": dt_e2e / args.steps * 1e3, "host_memory": "pinned (phi_gpu_host_alloc) in, pinned (library pool) out",
-                    "stage_ms": {key: float(np.mean([x[key] for x in e2e_stage])) for key in e2e_stage[0]}},
-            "gpu_launches": int(tm["kernel_launches"]) * args.steps,
-            "clocks": clk,
-            "device_ms_per_step": tm["total_ms"],
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved"], "peak": peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac"], "traffic": kernels[dom]["traffic"], "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_launch"], "kernel_ms": kernels[dom]["kernel_ms"],
-                         "kernels": kernels,
-                         "sharing": dict(share, path_kmer_positions=res.path_kmer_positions, unique_fraction=frac_unique),
-                         "note": "both sketch kernels are integer-issue bound (~7 warp instructions per sketched k-mer, ALU pipe 60-72 % busy, vs a few bytes "
-                                 "of compulsory traffic), so their HBM fraction is low by construction (ncu: DRAM traffic per launch in "
-                                 "'traffic'). walk_sketch_kernel: 'achieved' counts the algorithmic bytes of ALL path k-mers the launch "
-                                 "accounts for; identical walk chunks are sketched once (sharing.unique_fraction), 'achieved_physical' "
-                                 "scales to the positions really sketched. See DESIGN.md and profiles/"}}
-    if not args.no_cpu_baseline:
-        os.sched_setaffinity(0, all_cpus)                        # the CPU arm gets every host core again
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant sketch kernel (rank 0's launch), on the units THE LAUNCH physically processes
+        steps_r0, P_r0 = len(g.walk_vtx), max(1, res.path_kmer_positions)
+        uf = share["unique_windows"] / P_r0
+        mean_node = max(1.0, float(np.diff(g.seg_off.astype(np.int64))[g.walk_vtx[:: max(1, len(g.walk_vtx) // 1_000_000)]].mean())) if steps_r0 else 1.0
+        hit_vtx = share["unique_hits"] * (1.0 + (k - 1) / mean_node)
+        walk_alg = (0.25 * share["unique_windows"] + 4.0 * steps_r0 * uf + 32.0 * full.path_minimizers_emitted * uf
+                    + 16.0 * share["unique_hits"] + 4.0 * hit_vtx)
+        walk_eff = walk_alg / max(uf, 1e-12) if uf > 0 else 0.0
+        read_alg = float(rd.read_bases.nbytes) + 64.0 * res.read_minimizers_emitted
+        kernels = {}
+        for name, ms, alg, nunits in (("walk_sketch_kernel", tm["walk_kernel_ms"], walk_alg, share["unique_windows"]),
+                                      ("read_sketch_kernel", tm["read_kernel_ms"], read_alg, res.read_kmer_positions)):
+            prof, _ = kernel_profile(name)
+            ach = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            kernels[name] = {"kernel_ms": ms, "units_per_launch": int(nunits), "algorithmic_bytes_per_launch": alg, "achieved": ach, "frac": ach / peak,
+                             "traffic": prof.get("dram_bytes_per_launch"), "issue_slot_util": prof.get("issue_slot_util"),
+                             "warp_inst_per_kmer": prof.get("warp_inst_per_kmer")}
+        kernels["walk_sketch_kernel"]["effective"] = {
+            "achieved": walk_eff / (tm["walk_kernel_ms"] * 1e-3) / 1e9 if tm["walk_kernel_ms"] > 0 else 0.0,
+            "note": "bytes of ALL path k-mer positions the launch accounts for (identical chunks are sketched once): not a roofline figure"}
+        dom = max(kernels, key=lambda n: kernels[n]["kernel_ms"])
+        _, prof_src = kernel_profile(dom)
+        line = {"metric": METRIC, "value": units * args.steps / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u8/u64", "data": "synthetic" if args.config != "readme" else "README test files", "config": config_dict(wl, world),
+                "read_kmers_per_s": Q_run / ((tmax["read_sketch_ms"] + tmax["spectrum_ms"]) * 1e-3),
+                "path_kmers_per_s": P_run / ((tmax["graph_prep_ms"] + tmax["walk_sketch_ms"] + tmax["filter_ms"]) * 1e-3),
+                "index_wall_s": dt_e2e / args.steps,
+                "units_per_step": {"read_kmer_positions": Q_run, "path_kmer_positions": P_run, "read_minimizers": tot[2], "path_minimizers": tot[3],
+                                   "path_hits": tot[4], "spectrum": res.count_sp_r, "walk_steps_uploaded": tot[9]},
+                "stage_ms_rank0": tm, "stage_ms_max": tmax,
+                "e2e": {"value": units * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(tot[5]), "d2h_bytes_per_step": int(tot[6]),
+                        "ms_per_step": dt_e2e / args.steps * 1e3, "host_memory": "pinned (phi_gpu_host_alloc) in, pinned (library pool) out",
+                        "stage_ms_rank0": {key: float(np.mean([x[key] for x in e2e_stage])) for key in e2e_stage[0]},
+                        "note": "per-rank parts; the host-side merge of the parts (merge_ms, N > 1 only) is outside the timed region"},
+                "gpu_launches": int(tot[10]) * args.steps,
+                "clocks": clk, "cpu_affinity": affinity, "partition": (args.partition if world > 1 else "none"), "generate_s": t_gen,
+                "device_ms_per_step_rank0": tm["total_ms"],
+                "sharing": {"chunks": tot[11], "tiles": tot[12], "unique_windows": tot[7], "unique_hits": tot[8], "path_kmer_positions": P_run,
+                            "unique_fraction": tot[7] / max(1.0, P_run)},
+                "roofline": {"bound": "hbm", "kernel": dom + (" (rank 0)" if world > 1 else ""), "achieved": kernels[dom]["achieved"], "peak": peak,
+                             "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": kernels[dom]["traffic"], "peak_source": peak_src,
+                             "traffic_source": prof_src,
+                             "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_launch"], "kernel_ms": kernels[dom]["kernel_ms"],
+                             "kernels": kernels,
+                             "note": "achieved = SURVEY §8(d) bytes of the units the launch physically processes (walk kernel: the windows of the representative "
+                                     "chunks only) / the kernel's CUDA-event time. Both sketch kernels are integer-issue bound (issue_slot_util, "
+                                     "warp_inst_per_kmer from ncu), so their HBM fraction is low by construction. See DESIGN.md §3.4 and profiles/"}}
+        line.update(extras)
+        if world > 1:
+            line["exchange"] = ("NCCL inside the library: all-to-all of the locally distinct read-minimizer hashes by hash range + all-gather of the owners' sorted "
+                                "slices; all-to-all of one (rank, count, vertex list) summary per local group to the owner of the rank + all-reduce of the drop flags")
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        os.sched_setaffinity(0, all_cpus)                    # the CPU arm gets every host core again
         threads = os.cpu_count() or 1
-        n_walks = args.cpu_walks or min(threads, args.haps, 16)
-        r = run_reference_sample(sg, rd, args, n_walks, args.cpu_coverage, threads)
-        line["cpu_baseline"] = {"value": (r["P"] + r["Q"]) / r["t_index"], "unit": UNIT, "cores": threads, "kind": r["kind"],
-                                "sample": cpu_sample_desc(n_walks, args.cpu_coverage, args),
+        cg, crd, desc, fullcfg = wl.reference_input(threads)
+        r = run_reference(cg, crd, k, w, threads)
+        line["cpu_baseline"] = {"value": (r["P"] + r["Q"]) / r["t_index"], "unit": UNIT, "cores": threads, "kind": r["kind"], "sample": desc,
+                                "full_config": fullcfg, "units": {"read_kmer_positions": r["Q"], "path_kmer_positions": r["P"]},
                                 "read_kmers_per_s": r["Q"] / r["t_reads"] if r["t_reads"] else None,
                                 "path_kmers_per_s": r["P"] / r["t_paths"] if r["t_paths"] else None,
                                 "index_wall_s_sample": r["t_index"]}
     ix.close()
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
+    D.close()
 
 
 if __name__ == "__main__":

@@ -265,6 +265,31 @@ const phi_reads_view *phi_host_reads_view(const phi_host_reads *r);
 const char *phi_host_reads_name(const phi_host_reads *r, uint64_t i);
 void phi_host_reads_free(phi_host_reads *r);
 
+/*
+ * Region partition of the walks over several GPUs (no counterpart in the reference: one process, OpenMP over whole walks,
+ * /root/reference/src/ILP_index.cpp:559-562).  Splitting BY WALK would undo walk sharing, so every GPU gets ALL walks cut to the
+ * steps whose vertices lie in its range [coord_lo, coord_hi) of the topological base coordinate (bases of all vertices that
+ * precede a vertex in top_order_map) plus context (>= w bases in front, >= k-1 bases behind):
+ *   phi_shard_walk_regions   : world+1 coordinate bounds, balanced by walk steps (the walks of `g` may be a sample);
+ *   phi_shard_slice_walks    : for every walk of `g` the slice [slice_first[h], slice_first[h] + slice_len[h]) of g->walk_vtx
+ *                              (absolute step indices) that the GPU owning [coord_lo, coord_hi) needs; the caller builds that GPU's
+ *                              graph view from the slices (same walk order, walk_id_base 0, n_walks_global = n_walks);
+ *   phi_gpu_index_set_walk_region : tells the ctx which coordinate range it owns: of the walks (slices) it is given, only the
+ *                              windows whose last k-mer starts on a vertex inside the range are produced (path_kmer_positions,
+ *                              minimizers_per_walk and the groups then cover the owned part only; sum / merge over the GPUs).
+ *                              Default: [0, 2^64) — everything.
+ *   phi_index_result_merge   : the per-GPU parts -> ONE result in the reference's order: groups of a rank merged in key order
+ *                              (/root/reference/src/ILP_index.cpp:680-709), member lists of a group that occurs in several parts
+ *                              united, per-walk counters / n_filtered / work counters summed, spectrum from the part that has it.
+ *                              Works for parts of a by-walk partition (walk_id_base) as well.  Free with phi_gpu_index_result_free.
+ * PHI_ERR_UNSUPPORTED: top_order_map is not a permutation, or a walk does not follow it (use the by-walk partition then).
+ */
+int phi_shard_walk_regions(const phi_graph_view *g, int world, uint64_t *coord_bounds /* [world + 1] */);
+int phi_shard_slice_walks(const phi_graph_view *g, int k, int w, uint64_t coord_lo, uint64_t coord_hi,
+                          uint64_t *slice_first /* [n_walks] */, uint64_t *slice_len /* [n_walks] */);
+int phi_gpu_index_set_walk_region(phi_gpu_index_ctx *ctx, uint64_t coord_lo, uint64_t coord_hi);
+int phi_index_result_merge(const phi_index_result *const *parts, int n_parts, phi_index_result **out);
+
 /* Host-only partition helpers (no GPU needed). */
 /* owner rank of a hash under the range partition on the high bits */
 int phi_shard_owner_of_hash(uint64_t hash, int world);

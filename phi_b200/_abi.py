@@ -166,10 +166,11 @@ class IndexResultPy:
     group_member_off: np.ndarray = None
     member_walk: np.ndarray = None
     member_walk_bytes: int = 4
+    rank_off: np.ndarray = None                # [count_sp_r + 1] first group of every rank (the ABI's array)
 
     @property
     def n_anchors(self):
-        return len(self.anchor_rank)
+        return len(self.anchor_rank) if len(self.anchor_rank) or self.member_walk is None else len(self.member_walk)
 
     def wire_bytes(self):
         """Bytes of the C result arrays (what crosses PCIe): spectrum, rank_off, group_len, group_vtx, group_member_off,
@@ -209,7 +210,39 @@ def expand_groups(group_rank, group_len, group_vtx, group_member_off, member_wal
             group_vtx[src].astype(np.int32) if total else np.zeros(0, dtype=np.int32))
 
 
-def result_to_py(res: IndexResult) -> IndexResultPy:
+def py_to_c_result(py: IndexResultPy):
+    """IndexResultPy (grouped arrays) -> (IndexResult, keep-alive list): input of phi_index_result_merge."""
+    rank_off = np.ascontiguousarray(py.rank_off, dtype=np.uint32)
+    glen = np.ascontiguousarray(py.group_len, dtype=np.uint8)
+    gvtx = np.ascontiguousarray(py.group_vtx, dtype=np.int32)
+    moff = np.ascontiguousarray(py.group_member_off, dtype=np.uint32)
+    w16 = py.n_walks <= 65536
+    mw = np.ascontiguousarray(py.member_walk, dtype=np.uint16 if w16 else np.int32)
+    spec = np.ascontiguousarray(py.spectrum, dtype=np.uint64)
+    mpw = np.ascontiguousarray(py.minimizers_per_walk, dtype=np.uint64)
+    apw = np.ascontiguousarray(py.anchors_per_walk, dtype=np.uint64)
+    keep = [rank_off, glen, gvtx, moff, mw, spec, mpw, apw]
+    r = IndexResult()
+    r.count_sp_r, r.n_walks, r.n_filtered = py.count_sp_r, py.n_walks, py.n_filtered
+    r.n_anchors, r.n_groups, r.n_group_vtx = len(mw), len(glen), len(gvtx)
+    r.spectrum = spec.ctypes.data_as(u64p) if len(spec) == py.count_sp_r and py.count_sp_r else None
+    r.rank_off = rank_off.ctypes.data_as(u32p)
+    r.group_len = glen.ctypes.data_as(u8p)
+    r.group_vtx = gvtx.ctypes.data_as(i32p)
+    r.group_member_off = moff.ctypes.data_as(u32p)
+    if w16:
+        r.member_walk16 = mw.ctypes.data_as(u16p)
+    else:
+        r.member_walk32 = mw.ctypes.data_as(i32p)
+    r.minimizers_per_walk = mpw.ctypes.data_as(u64p)
+    r.anchors_per_walk = apw.ctypes.data_as(u64p)
+    r.read_kmer_positions, r.path_kmer_positions = py.read_kmer_positions, py.path_kmer_positions
+    r.read_minimizers_emitted, r.path_minimizers_emitted, r.path_hits = py.read_minimizers_emitted, py.path_minimizers_emitted, py.path_hits
+    return r, keep
+
+
+def result_to_py(res: IndexResult, expand=True) -> IndexResultPy:
+    """expand=False skips the adapter's forward pass (anchor_* stay empty): for big results of which only the ABI arrays are wanted."""
     na, ng, nv, nw, ns = res.n_anchors, res.n_groups, res.n_group_vtx, res.n_walks, res.count_sp_r
     have = bool(res.group_len) or ng == 0
     rank_off = _np_from(res.rank_off, ns + 1 if res.rank_off else 0, np.uint32)
@@ -240,7 +273,10 @@ def result_to_py(res: IndexResult) -> IndexResultPy:
             assert np.all((np.diff(member_walk.astype(np.int64)) >= 0) | ~same), "members of a group are not ascending"
     else:
         group_rank = np.zeros(ng, dtype=np.int32)
-    if res.group_member_off:
+    if not expand:
+        anchor_rank = anchor_walk = anchor_vtx = np.zeros(0, dtype=np.int32)
+        anchor_off = np.zeros(1, dtype=np.uint64)
+    elif res.group_member_off:
         anchor_rank, anchor_walk, anchor_off, anchor_vtx = expand_groups(group_rank, group_len, group_vtx, member_off, member_walk)
     else:
         anchor_rank, anchor_walk, anchor_vtx = group_rank, member_walk, group_vtx
@@ -260,4 +296,4 @@ def result_to_py(res: IndexResult) -> IndexResultPy:
         n_walk_kmers=int(res.n_walk_kmers),
         shared_kmer_hist=_np_from(res.shared_kmer_hist, nw + 1, np.uint64) if res.shared_kmer_hist else None,
         n_groups=int(ng), group_rank=group_rank, group_len=group_len, group_vtx=group_vtx, group_member_off=member_off,
-        member_walk=member_walk, member_walk_bytes=walk_bytes)
+        member_walk=member_walk, member_walk_bytes=walk_bytes, rank_off=rank_off if len(rank_off) else None)

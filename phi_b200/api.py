@@ -87,6 +87,14 @@ def load_library():
     lib.phi_shard_owner_of_hash.argtypes = [C.c_uint64, C.c_int]
     lib.phi_shard_split_by_weight.restype = C.c_int
     lib.phi_shard_split_by_weight.argtypes = [_abi.u64p, C.c_uint64, C.c_int, _abi.u64p]
+    lib.phi_shard_walk_regions.restype = C.c_int
+    lib.phi_shard_walk_regions.argtypes = [C.POINTER(_abi.GraphView), C.c_int, _abi.u64p]
+    lib.phi_shard_slice_walks.restype = C.c_int
+    lib.phi_shard_slice_walks.argtypes = [C.POINTER(_abi.GraphView), C.c_int, C.c_int, C.c_uint64, C.c_uint64, _abi.u64p, _abi.u64p]
+    lib.phi_gpu_index_set_walk_region.restype = C.c_int
+    lib.phi_gpu_index_set_walk_region.argtypes = [ctxp, C.c_uint64, C.c_uint64]
+    lib.phi_index_result_merge.restype = C.c_int
+    lib.phi_index_result_merge.argtypes = [C.POINTER(resp), C.c_int, C.POINTER(resp)]
     _LIB = lib
     return lib
 
@@ -164,15 +172,15 @@ class PhiGpuIndex:
     def _params(k, w, threshold, debug=0):
         return _abi.IndexParams(int(k), int(w), float(threshold), int(debug))
 
-    def _take(self, resp, free=True):
-        res = _abi.result_to_py(resp.contents)
+    def _take(self, resp, free=True, expand=True):
+        res = _abi.result_to_py(resp.contents, expand)
         if free:
             self.lib.phi_gpu_index_result_free(resp)
         return res
 
-    def run(self, graph, reads, k=31, w=25, threshold=1.0, debug=0):
+    def run(self, graph, reads, k=31, w=25, threshold=1.0, debug=0, expand=True):
         """Host buffers in, host result out (H2D + kernels + D2H): the drop-in call.  Returns numpy copies."""
-        return self._take(self.run_raw(graph, reads, k, w, threshold, debug))
+        return self._take(self.run_raw(graph, reads, k, w, threshold, debug), expand=expand)
 
     def run_raw(self, graph, reads, k=31, w=25, threshold=1.0, debug=0):
         """The same call, returning the C result pointer untouched (no numpy copies); free it with free_raw()."""
@@ -222,6 +230,10 @@ class PhiGpuIndex:
 
     def set_walk_sharing(self, chunk_shift=11, share=True):
         self._check(self.lib.phi_gpu_index_set_walk_sharing(self.ctx, int(chunk_shift), 1 if share else 0))
+
+    def set_walk_region(self, coord_lo, coord_hi):
+        """Own only the windows whose last k-mer starts on a vertex with topological base coordinate in [coord_lo, coord_hi)."""
+        self._check(self.lib.phi_gpu_index_set_walk_region(self.ctx, int(coord_lo), int(coord_hi)))
 
     def sharing(self):
         t = _abi.SharingStats()

@@ -43,14 +43,15 @@ __global__ void topo_len_kernel(const int32_t *top_order_map, const uint64_t *se
 // what the step pass needs of a vertex, in one 16-byte record: (bases, coordinate bucket, top_order_map, -).
 // coordinate = prefix[top_order_map[v]]; with an unusable top_order_map the segment-store offset serves (any function of v is correct)
 __global__ void topo_coord_kernel(const int32_t *top_order_map, const uint64_t *seg_off, const uint64_t *prefix, uint32_t n_vtx,
-                                  int shift, unsigned long long *ctr, uint4 *vinfo)
+                                  int shift, uint64_t own_lo, uint64_t own_hi, unsigned long long *ctr, uint4 *vinfo)
 {
     uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_vtx) return;
     const uint64_t len = seg_off[v + 1] - seg_off[v];
     if (len >= (1ull << 31)) ctr[CTR_SEG_TOO_LONG] = 1;
     const uint64_t coord = ctr[CTR_BAD_TOPO] ? seg_off[v] : prefix[top_order_map[v]];
-    vinfo[v] = make_uint4((uint32_t)len, (uint32_t)(coord >> shift), (uint32_t)top_order_map[v], 0u);
+    const uint32_t region = (coord >= own_lo ? 1u : 0u) + (coord >= own_hi ? 1u : 0u);   // 1: owned by this GPU
+    vinfo[v] = make_uint4((uint32_t)len, (uint32_t)(coord >> shift), (uint32_t)top_order_map[v], region);
 }
 
 __device__ __forceinline__ uint32_t walk_of_step(const uint64_t *walk_off, uint32_t n_walks, uint64_t s)
@@ -96,24 +97,32 @@ __device__ __forceinline__ uint32_t walk_of_step_block(const uint64_t *walk_off,
 
 // ---- one pass over the walk steps: segment length, chunk boundary (the step's vertex lies in another coordinate bucket than the
 // previous step's, or the step is the first of its walk), zero-length steps, topological monotonicity of the walks
+// vertex record of a step; an id outside [0, n_vtx) (caller error) is flagged and reads as an empty vertex
+__device__ __forceinline__ uint4 vinfo_of(const uint4 *vinfo, uint32_t n_vtx, uint32_t v, unsigned long long *ctr)
+{
+    if (v < n_vtx) return vinfo[v];
+    ctr[CTR_BAD_VTX] = 1;
+    return make_uint4(0, 0, 0, 0);
+}
+
 __global__ void __launch_bounds__(256) step_pass_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
-                                                        const uint4 *vinfo, PackedStep *packed, unsigned long long *ctr)
+                                                        const uint4 *vinfo, uint32_t n_vtx, PackedStep *packed, unsigned long long *ctr)
 {
     const uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     bool zero = false, flag = false;
     uint4 me = make_uint4(0, 0, 0, 0);
-    if (s < n_steps) me = vinfo[walk_vtx[s]];                        // one 16-byte gather per step
+    if (s < n_steps) me = vinfo_of(vinfo, n_vtx, walk_vtx[s], ctr);   // one 16-byte gather per step
     // the previous step's vertex record: the neighbouring lane has it (lane 0 fetches its own)
-    uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, me.y, 1), pt = __shfl_up_sync(0xFFFFFFFFu, me.z, 1);
-    if (lane == 0 && s && s < n_steps) { const uint4 p = vinfo[walk_vtx[s - 1]]; pb = p.y; pt = p.z; }
+    uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, me.y, 1), pt = __shfl_up_sync(0xFFFFFFFFu, me.z, 1), pr = __shfl_up_sync(0xFFFFFFFFu, me.w, 1);
+    if (lane == 0 && s && s < n_steps) { const uint4 p = vinfo_of(vinfo, n_vtx, walk_vtx[s - 1], ctr); pb = p.y; pt = p.z; pr = p.w; }
     uint64_t ws;
     const uint64_t blk0 = blockIdx.x * (uint64_t)blockDim.x;
     walk_of_step_block(walk_off, n_walks, s < n_steps ? s : n_steps - 1, blk0, min(blk0 + blockDim.x, n_steps) - 1, ws);
     if (s < n_steps) {
         flag = s == ws;
         if (!flag) {
-            flag = me.y != pb;
+            flag = me.y != pb || me.w != pr;                          // another coordinate bucket, or across the owned range's border
             if ((int32_t)pt >= (int32_t)me.z) ctr[CTR_NONMONO] = 1;
         }
         zero = me.x == 0;
@@ -141,7 +150,7 @@ __device__ __forceinline__ uint64_t fs_comb(uint64_t a, uint64_t b)           //
     return (((a & FS_BASES) + (b & FS_BASES)) & FS_BASES) | chunks | (a & FS_RESET);
 }
 __global__ void __launch_bounds__(FS_THREADS, 4) fused_steps_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
-                                                                    const uint4 *vinfo, unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base,
+                                                                    const uint4 *vinfo, uint32_t n_vtx, unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base,
                                                                     uint32_t *chunk_step, uint32_t *c_walk, uint64_t *walk_len, unsigned long long *ctr)
 {
     __shared__ uint32_t sh_tile, sh_h[2];
@@ -163,9 +172,10 @@ __global__ void __launch_bounds__(FS_THREADS, 4) fused_steps_kernel(const uint32
     static_assert(FS_ITEMS == 4, "one 16-byte load per thread");
     uint4 me[FS_ITEMS];
     #pragma unroll
-    for (int j = 0; j < FS_ITEMS; ++j) me[j] = vinfo[vtx[j]];
+    for (int j = 0; j < FS_ITEMS; ++j) me[j] = vinfo_of(vinfo, n_vtx, vtx[j], ctr);
     uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, me[FS_ITEMS - 1].y, 1), pt = __shfl_up_sync(0xFFFFFFFFu, me[FS_ITEMS - 1].z, 1);
-    if (lane == 0 && sb && sb < n_steps) { const uint4 p = vinfo[walk_vtx[sb - 1]]; pb = p.y; pt = p.z; }
+    uint32_t pr = __shfl_up_sync(0xFFFFFFFFu, me[FS_ITEMS - 1].w, 1);
+    if (lane == 0 && sb && sb < n_steps) { const uint4 p = vinfo_of(vinfo, n_vtx, walk_vtx[sb - 1], ctr); pb = p.y; pt = p.z; pr = p.w; }
     __syncthreads();
     const uint32_t h_lo = sh_h[0], h_hi = sh_h[1];
     // per step: first of its walk?  starts a chunk?  -> the thread's total
@@ -181,9 +191,9 @@ __global__ void __launch_bounds__(FS_THREADS, 4) fused_steps_kernel(const uint32
             while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (walk_off[m] <= s) lo = m; else hi = m; }
             ws = walk_off[lo];
         }
-        const uint32_t qb = j ? me[j - 1 < 0 ? 0 : j - 1].y : pb, qt = j ? me[j - 1 < 0 ? 0 : j - 1].z : pt;
+        const uint32_t qb = j ? me[j - 1 < 0 ? 0 : j - 1].y : pb, qt = j ? me[j - 1 < 0 ? 0 : j - 1].z : pt, qr = j ? me[j - 1 < 0 ? 0 : j - 1].w : pr;
         const bool start = valid && s == ws;
-        const bool flag = valid && (start || me[j].y != qb);
+        const bool flag = valid && (start || me[j].y != qb || me[j].w != qr);
         if (valid && !start && (int32_t)qt >= (int32_t)me[j].z) nonmono = true;
         zeros += valid && me[j].x == 0;
         startm |= (start ? 1u : 0u) << j; flagm |= (flag ? 1u : 0u) << j;
@@ -310,8 +320,9 @@ __global__ void remap_walk_off_kernel(const uint64_t *walk_off, uint32_t n_walks
 // Owned windows: end positions e (start of the window's last k-mer) in [lo, hi), lo = first base of the chunk, hi = first base of
 // the next chunk clipped to the walk's last k-mer.  Context steps [L, R]: from the step under base lo - w (halo window) to the
 // step under base (next chunk start) + k - 2.
+// A chunk whose first vertex lies outside the owned coordinate range (a walk region is set: another GPU sketches it) owns nothing.
 __global__ void __launch_bounds__(256) chunk_key_kernel(ChunkTable C, const uint32_t *walk_vtx, const uint64_t *walk_off, const uint32_t *step_base,
-                                                        const uint64_t *walk_len, int k, int w, unsigned long long *ctr)
+                                                        const uint64_t *walk_len, const uint4 *vinfo, int k, int w, unsigned long long *ctr)
 {
     const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -324,7 +335,9 @@ __global__ void __launch_bounds__(256) chunk_key_kernel(ChunkTable C, const uint
     const long long lo = step_base[s0];
     const long long b1 = s1 < we ? (long long)step_base[s1] : len;
     long long hi = min(b1, len - k + 1);
-    if (len < (long long)w + k - 1 || hi <= max(lo, (long long)w - 1)) hi = lo;         // no valid window ends here
+    const bool owned = vinfo[walk_vtx[s0]].w == 1u;
+    const long long kpos = (owned && len >= (long long)w + k - 1 && hi > lo) ? hi - lo : 0;   // k-mer positions of the walk that start in this chunk
+    if (len < (long long)w + k - 1 || hi <= max(lo, (long long)w - 1) || !owned) hi = lo;     // no valid window ends here
     uint32_t L, R;
     {   // L: going down from s0, the first step l with l == ws or step_base[l] <= lo - w
         const long long need = lo - w;
@@ -366,6 +379,7 @@ __global__ void __launch_bounds__(256) chunk_key_kernel(ChunkTable C, const uint
     if (lane == 0) {
         C.c_L[c] = L; C.c_R[c] = R; C.c_lo[c] = (uint32_t)lo; C.c_hi[c] = (uint32_t)hi; C.c_h1[c] = h1; C.c_h2[c] = h2;
         if (hi > lo) atomicAdd(&ctr[CTR_ACTIVE_CHUNKS], 1ull);
+        if (kpos) atomicAdd(&ctr[CTR_PATH_POS], (unsigned long long)kpos);
     }
 }
 
@@ -526,8 +540,8 @@ __global__ void __launch_bounds__(256) expand_kernel(ChunkTable C, ExpandArgs X)
 }
 
 // ------------------------------------------------------------------ launchers
-cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, int shift, uint32_t *tlen, uint64_t *prefix,
-                             uint4 *vinfo, void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
+cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, int shift, uint64_t own_lo, uint64_t own_hi,
+                             uint32_t *tlen, uint64_t *prefix, uint4 *vinfo, void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
 {
     if (!n_vtx) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(tlen, 0, (size_t)n_vtx * 4, st);
@@ -536,21 +550,21 @@ cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_o
     PHI_LAUNCH_CHECK();
     e = scan_u32_to_u64(tlen, prefix, n_vtx, scan_scratch, st, launches);
     if (e != cudaSuccess) return e;
-    topo_coord_kernel<<<(n_vtx + 255) / 256, 256, 0, st>>>(top_order_map, seg_off, prefix, n_vtx, shift, ctr, vinfo);
+    topo_coord_kernel<<<(n_vtx + 255) / 256, 256, 0, st>>>(top_order_map, seg_off, prefix, n_vtx, shift, own_lo, own_hi, ctr, vinfo);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
 
-cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo,
+cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo, uint32_t n_vtx,
                            PackedStep *packed, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
 {
     if (!n_steps) return cudaSuccess;
-    step_pass_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, packed, ctr);
+    step_pass_kernel<<<(unsigned)((n_steps + 255) / 256), 256, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, packed, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
 
-cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo,
+cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo, uint32_t n_vtx,
                              unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base, uint32_t *chunk_step, uint32_t *c_walk,
                              uint64_t *walk_len, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
 {
@@ -562,7 +576,7 @@ cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off,
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(walk_len, 0, (size_t)n_walks * 8, st);           // walks without steps
     if (e != cudaSuccess) return e;
-    fused_steps_kernel<<<(unsigned)nt, FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr);
+    fused_steps_kernel<<<(unsigned)nt, FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -599,10 +613,10 @@ cudaError_t walk_compact_steps(const uint32_t *walk_vtx, const uint64_t *walk_of
 }
 
 cudaError_t chunk_keys(const ChunkTable &C, const uint32_t *walk_vtx, const uint64_t *walk_off, const uint32_t *step_base, const uint64_t *walk_len,
-                       int k, int w, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
+                       const uint4 *vinfo, int k, int w, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
 {
     if (!C.n_chunks) return cudaSuccess;
-    chunk_key_kernel<<<(unsigned)(((uint64_t)C.n_chunks * 32 + 255) / 256), 256, 0, st>>>(C, walk_vtx, walk_off, step_base, walk_len, k, w, ctr);
+    chunk_key_kernel<<<(unsigned)(((uint64_t)C.n_chunks * 32 + 255) / 256), 256, 0, st>>>(C, walk_vtx, walk_off, step_base, walk_len, vinfo, k, w, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

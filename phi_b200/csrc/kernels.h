@@ -34,7 +34,9 @@ enum {
     CTR_WALK_KMERS = 22,          // distinct walk-minimizer hashes (-d1 statistic)
     CTR_SURV_VTX = 23,            // vertices of all instantiated surviving anchors           // hits of all walks (every member chunk counts what its representative found)     // a chunk differs from its fingerprint representative (128-bit collision): rerun without sharing
     CTR_OUT_GROUPS = 24,          // surviving (rank, vertex list) groups of the result
-    CTR_COUNT = 25
+    CTR_PATH_POS = 25,            // k-mer positions of the walks that lie in owned chunks (all of them unless a walk region is set)
+    CTR_BAD_VTX = 26,             // a walk step names a vertex id >= n_vtx (caller error: PHI_ERR_ARG)
+    CTR_COUNT = 27
 };
 
 enum { WALK_MODE_PROBE = 0, WALK_MODE_ALL = 1 };
@@ -140,17 +142,18 @@ struct PackedStep {
 
 // chunks.cu — walk preparation (step lengths and bases, walk lengths), walk chunking, grouping of identical chunks,
 // instantiation of the representatives' hits
-// per-vertex record of the step pass: (bases, coordinate >> shift, top_order_map, -)
-cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, int shift, uint32_t *tlen, uint64_t *prefix,
-                             uint4 *vinfo, void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
+// per-vertex record of the step pass: (bases, coordinate >> shift, top_order_map, region) with region = 0 / 1 / 2 for a
+// coordinate below / inside / at or above the owned range [own_lo, own_hi) (phi_gpu_index_set_walk_region; everything is owned by default)
+cudaError_t chunk_topo_coord(const int32_t *top_order_map, const uint64_t *seg_off, uint32_t n_vtx, int shift, uint64_t own_lo, uint64_t own_hi,
+                             uint32_t *tlen, uint64_t *prefix, uint4 *vinfo, void *scan_scratch, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 // per step: segment length, chunk-start flag, zero-length count, topological monotonicity -> packed[]
-cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo,
+cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo, uint32_t n_vtx,
                            PackedStep *packed, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 // step pass + scan + finalisation in one kernel (decoupled look-back; the common case without zero-length steps, which it only
 // counts): step_base, walk_len, chunk_step[0..chunks] / c_walk (both sized for n_steps + 1 chunks), ctr[CTR_CHUNK_FLAGS] = chunks.
 // tile_state: walk_steps_fused_tiles(n_steps) words.
 uint64_t walk_steps_fused_tiles(uint64_t n_steps);
-cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo,
+cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo, uint32_t n_vtx,
                              unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base, uint32_t *chunk_step, uint32_t *c_walk,
                              uint64_t *walk_len, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 // scanned = exclusive scan of packed (as u64) -> step_base, walk_len, chunk_step / c_walk of C
@@ -161,7 +164,7 @@ cudaError_t walk_compact_steps(const uint32_t *walk_vtx, const uint64_t *walk_of
                                uint32_t *flags, uint64_t *pos, void *scan_scratch, uint64_t n_kept, uint32_t *out_vtx, uint64_t *out_off,
                                cudaStream_t st, uint64_t *launches);
 cudaError_t chunk_keys(const ChunkTable &C, const uint32_t *walk_vtx, const uint64_t *walk_off, const uint32_t *step_base, const uint64_t *walk_len,
-                       int k, int w, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
+                       const uint4 *vinfo, int k, int w, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 cudaError_t chunk_group(const ChunkTable &C, uint32_t *table, uint32_t table_cap, const uint32_t *walk_vtx, int dedupe, int w, unsigned long long *ctr,
                         cudaStream_t st, uint64_t *launches);
 cudaError_t chunk_tiles(const ChunkTable &C, const uint64_t *walk_off, const uint32_t *step_base, int w, TileRec *tiles, cudaStream_t st, uint64_t *launches);

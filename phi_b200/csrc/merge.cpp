@@ -1,0 +1,145 @@
+// phi_index_result_merge: the per-GPU parts of a multi-GPU run -> one result in the reference's order (host only).
+//
+// Every part holds, for all hash ranks, the surviving groups (rank, vertex list) found on ITS GPU, in the reference's key order
+// (/root/reference/src/ILP_index.cpp:680-709: std::map<std::string> over "v0_v1_..._"), with ascending member walks.  The groups
+// of one rank are merged in key order; a group that occurs in several parts (its occurrences were owned by several GPUs) gets
+// the union of the member lists.  Per-walk counters and n_filtered are sums over the parts; the spectrum comes from the part
+// that carries it (rank 0).  With one part this is a copy.
+#include "result_box.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+std::string key_of(const int32_t *v, uint32_t n)
+{
+    std::string s;
+    char buf[16];
+    for (uint32_t i = 0; i < n; ++i) { int len = snprintf(buf, sizeof buf, "%d_", v[i]); s.append(buf, (size_t)len); }
+    return s;
+}
+
+template <class T> T *heap_array(ResultBox *b, uint64_t n)
+{
+    T *p = (T *)malloc((n ? n : 1) * sizeof(T));
+    if (p) { b->bufs[b->nbufs].p = p; b->bufs[b->nbufs].cap = n * sizeof(T); b->nbufs++; }
+    return p;
+}
+
+struct Cursor { uint32_t g, end; uint64_t voff; };   // next group of this part inside the current rank, its vertex offset
+
+}  // namespace
+
+extern "C" int phi_index_result_merge(const phi_index_result *const *parts, int n_parts, phi_index_result **out)
+{
+    if (!parts || n_parts < 1 || !out) return PHI_ERR_ARG;
+    *out = nullptr;
+    const phi_index_result *p0 = parts[0];
+    const int32_t NS = p0->count_sp_r; const uint32_t NW = p0->n_walks;
+    uint64_t tot_groups = 0, tot_members = 0, tot_vtx = 0;
+    const uint64_t *spectrum = nullptr;
+    for (int p = 0; p < n_parts; ++p) {
+        const phi_index_result *r = parts[p];
+        if (!r || r->count_sp_r != NS || r->n_walks != NW) return PHI_ERR_ARG;
+        if (r->n_groups && (!r->rank_off || !r->group_len || !r->group_member_off || (!r->member_walk16 && !r->member_walk32))) return PHI_ERR_ARG;
+        if (NS && !r->rank_off) return PHI_ERR_ARG;
+        tot_groups += r->n_groups; tot_members += r->n_anchors; tot_vtx += r->n_group_vtx;
+        if (!spectrum && r->spectrum) spectrum = r->spectrum;
+    }
+    if (tot_groups >= (1ull << 32) || tot_members >= (1ull << 32)) return PHI_ERR_UNSUPPORTED;   // the ABI's offsets are u32
+    ResultBox *b = (ResultBox *)calloc(1, sizeof(ResultBox));
+    if (!b) return PHI_ERR_NOMEM;
+    b->heap = 1;
+    phi_index_result *m = &b->pub;
+    const bool w16 = NW <= 65536;
+    uint64_t *o_spec = heap_array<uint64_t>(b, spectrum ? (uint64_t)NS : 0);
+    uint32_t *o_rank_off = heap_array<uint32_t>(b, (uint64_t)NS + 1);
+    uint8_t *o_len = heap_array<uint8_t>(b, tot_groups);
+    int32_t *o_vtx = heap_array<int32_t>(b, tot_vtx);
+    uint32_t *o_moff = heap_array<uint32_t>(b, tot_groups + 1);
+    uint16_t *o_w16 = w16 ? heap_array<uint16_t>(b, tot_members) : nullptr;
+    int32_t *o_w32 = w16 ? nullptr : heap_array<int32_t>(b, tot_members);
+    uint64_t *o_mpw = heap_array<uint64_t>(b, NW), *o_apw = heap_array<uint64_t>(b, NW);
+    if (!o_spec || !o_rank_off || !o_len || !o_vtx || !o_moff || (w16 ? !o_w16 : !o_w32) || !o_mpw || !o_apw) { phi_gpu_index_result_free(m); return PHI_ERR_NOMEM; }
+    if (spectrum && NS) memcpy(o_spec, spectrum, (size_t)NS * 8);
+    memset(o_mpw, 0, (size_t)NW * 8); memset(o_apw, 0, (size_t)NW * 8);
+
+    // vertex offset of every group of every part (group_len is u8: the lists lie back to back)
+    std::vector<std::vector<uint64_t>> gvoff(n_parts);
+    for (int p = 0; p < n_parts; ++p) {
+        const phi_index_result *r = parts[p];
+        gvoff[p].resize(r->n_groups + 1);
+        uint64_t run = 0;
+        for (uint64_t g = 0; g < r->n_groups; ++g) { gvoff[p][g] = run; run += r->group_len[g]; }
+        gvoff[p][r->n_groups] = run;
+    }
+    auto member = [&](const phi_index_result *r, uint64_t i) -> uint32_t { return r->member_walk16 ? (uint32_t)r->member_walk16[i] : (uint32_t)r->member_walk32[i]; };
+    uint64_t ng = 0, nm = 0, nv = 0;
+    std::vector<int> live; std::vector<uint32_t> cur(n_parts), end(n_parts);
+    std::vector<std::string> keys(n_parts);
+    std::vector<uint32_t> merged;
+    auto put_member = [&](uint32_t wk) { if (w16) o_w16[nm] = (uint16_t)wk; else o_w32[nm] = (int32_t)wk; ++nm; };
+    for (int32_t rk = 0; rk < NS; ++rk) {
+        o_rank_off[rk] = (uint32_t)ng;
+        live.clear();
+        for (int p = 0; p < n_parts; ++p) {
+            const phi_index_result *r = parts[p];
+            cur[p] = r->rank_off[rk]; end[p] = r->rank_off[rk + 1];
+            if (cur[p] < end[p]) live.push_back(p);
+        }
+        if (live.empty()) continue;
+        if (live.size() == 1) {                                           // the usual case: all groups of this rank come from one GPU
+            const int p = live[0]; const phi_index_result *r = parts[p];
+            for (uint32_t g = cur[p]; g < end[p]; ++g) {
+                o_len[ng] = r->group_len[g]; o_moff[ng] = (uint32_t)nm;
+                memcpy(o_vtx + nv, r->group_vtx + gvoff[p][g], (size_t)r->group_len[g] * 4); nv += r->group_len[g];
+                for (uint32_t i = r->group_member_off[g]; i < r->group_member_off[g + 1]; ++i) put_member(member(r, i));
+                ++ng;
+            }
+            continue;
+        }
+        for (int p : live) keys[p] = key_of(parts[p]->group_vtx + gvoff[p][cur[p]], parts[p]->group_len[cur[p]]);
+        while (!live.empty()) {
+            int best = live[0];
+            for (int p : live) if (keys[p] < keys[best]) best = p;
+            const std::string key = keys[best];
+            const phi_index_result *rb = parts[best];
+            o_len[ng] = rb->group_len[cur[best]]; o_moff[ng] = (uint32_t)nm;
+            memcpy(o_vtx + nv, rb->group_vtx + gvoff[best][cur[best]], (size_t)o_len[ng] * 4); nv += o_len[ng];
+            // members: union over the parts that hold this key, ascending (every part's list ascends: merge)
+            merged.clear();
+            for (size_t li = 0; li < live.size();) {
+                const int p = live[li];
+                if (keys[p] != key) { ++li; continue; }
+                const phi_index_result *r = parts[p];
+                const uint32_t g = cur[p];
+                const size_t old = merged.size();
+                for (uint32_t i = r->group_member_off[g]; i < r->group_member_off[g + 1]; ++i) merged.push_back(member(r, i));
+                std::inplace_merge(merged.begin(), merged.begin() + old, merged.end());
+                if (++cur[p] < end[p]) { keys[p] = key_of(r->group_vtx + gvoff[p][cur[p]], r->group_len[cur[p]]); ++li; }
+                else live.erase(live.begin() + li);
+            }
+            for (uint32_t wk : merged) put_member(wk);
+            ++ng;
+        }
+    }
+    o_rank_off[NS] = (uint32_t)ng; o_moff[ng] = (uint32_t)nm;
+    for (int p = 0; p < n_parts; ++p) {
+        const phi_index_result *r = parts[p];
+        for (uint32_t h = 0; h < NW; ++h) { if (r->minimizers_per_walk) o_mpw[h] += r->minimizers_per_walk[h]; if (r->anchors_per_walk) o_apw[h] += r->anchors_per_walk[h]; }
+        m->n_filtered += r->n_filtered;
+        m->read_kmer_positions += r->read_kmer_positions; m->path_kmer_positions += r->path_kmer_positions;
+        m->read_minimizers_emitted += r->read_minimizers_emitted; m->path_minimizers_emitted += r->path_minimizers_emitted;
+        m->path_hits += r->path_hits;
+    }
+    m->count_sp_r = NS; m->n_walks = NW; m->n_anchors = nm; m->n_groups = ng; m->n_group_vtx = nv;
+    m->spectrum = spectrum ? o_spec : nullptr; m->rank_off = o_rank_off; m->group_len = o_len; m->group_vtx = o_vtx; m->group_member_off = o_moff;
+    m->member_walk16 = o_w16; m->member_walk32 = o_w32; m->minimizers_per_walk = o_mpw; m->anchors_per_walk = o_apw;
+    *out = m;
+    return PHI_OK;
+}

@@ -4,6 +4,7 @@
 // phi_gpu_index_create() fails and nothing else can be called.
 #include "../../include/phi_gpu_index.h"
 #include "kernels.h"
+#include "result_box.h"
 
 #include <algorithm>
 #include <dlfcn.h>
@@ -39,8 +40,6 @@ struct DevBuf {                       // grow-only device buffer
     template <class T> T *as() const { return (T *)p; }
 };
 
-// pinned host buffer recycled through the ctx's pool (result arrays land here: D2H at full PCIe speed, no staging copy)
-struct PinnedBuf { void *p = nullptr; size_t cap = 0; };
 
 enum { EV_START, EV_H2D, EV_PREP0, EV_PREP, EV_RD0, EV_READS, EV_SPECTRUM, EV_WALKS, EV_FILTER, EV_END, EV_RK0, EV_RK1, EV_WK0, EV_WK1, EV_XS0, EV_XS1, EV_XH0, EV_XH1, EV_XH2, EV_COUNT };
 
@@ -77,7 +76,8 @@ struct phi_gpu_index_ctx {
     // walk chunks (chunks.cu): boundaries, fingerprints, representatives, tiles, hit segments, expanded survivors
     DevBuf tlen, tprefix, coord, cflags, cpos, chunk_step, c_walk, c_L, c_R, c_lo, c_hi, c_h1, c_h2, c_slot, c_rep, c_ninst, c_ntile, c_tile_base, ctable, tiles;
     DevBuf hseg_off, hseg_cnt, c_emitted, c_hits, c_surv, c_surv_vtx, member_cnt, member_off, x_rank, x_walk, x_pos, x_voff, x_nv, x_hash;
-    uint32_t n_chunks = 0, n_tiles = 0; uint64_t unique_windows = 0, active_chunks = 0, rep_chunks = 0, unique_hits = 0; int dedupe = 1, chunk_shift = 11;
+    uint32_t n_chunks = 0, n_tiles = 0; uint64_t unique_windows = 0, active_chunks = 0, rep_chunks = 0, unique_hits = 0, path_pos = 0; int dedupe = 1, chunk_shift = 11;
+    uint64_t own_lo = 0, own_hi = ~0ull;   // owned range of the topological base coordinate (phi_gpu_index_set_walk_region); default: everything
     DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
     DevBuf anchor_off, rank_off, anchor_len, anchor_walk, anchor_vtx, apw, dbg_hist;
     // grouped result (groups.cu): member walks of the representative chunks, slot / sub-offset of every hit, group sizes and offsets
@@ -149,12 +149,15 @@ extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
     return PHI_OK;
 }
 
+static void comm_release(phi_gpu_index_ctx *ctx, bool abort);
+
 extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     if (ctx->st2) cudaStreamSynchronize(ctx->st2);
+    comm_release(ctx, false);
     DevBuf *bufs[] = {&ctx->ctr2, &ctx->scan_scr2, &ctx->flags2, &ctx->flags64_2, &ctx->nv_out2,
                       &ctx->seg_off, &ctx->seg_bases, &ctx->walk_off, &ctx->walk_vtx, &ctx->top_order, &ctx->read_off, &ctx->read_bases,
                       &ctx->step_len, &ctx->gbase, &ctx->step_base, &ctx->walk_len,
@@ -197,6 +200,15 @@ static int check_views(phi_gpu_index_ctx *ctx, const phi_graph_view *g, const ph
     if (!g || !r) return ctx->fail(PHI_ERR_ARG, "graph/reads view is NULL");
     if ((g->n_vtx && (!g->seg_off || !g->top_order_map)) || (g->n_walks && !g->walk_off)) return ctx->fail(PHI_ERR_ARG, "graph view has NULL arrays");
     if (r->n_reads && !r->read_off) return ctx->fail(PHI_ERR_ARG, "reads view has NULL arrays");
+    // offsets: start at 0, never decrease; data arrays present when the totals say so (O(n_vtx + n_walks + n_reads); the vertex ids of the
+    // walk steps are range-checked on the device by the step pass, before anything indexes with them)
+    auto monotone = [](const uint64_t *off, uint64_t n) { if (off[0] != 0) return false; for (uint64_t i = 0; i < n; ++i) if (off[i + 1] < off[i]) return false; return true; };
+    if (g->n_vtx && !monotone(g->seg_off, g->n_vtx)) return ctx->fail(PHI_ERR_ARG, "graph view: seg_off must start at 0 and be non-decreasing");
+    if (g->n_walks && !monotone(g->walk_off, g->n_walks)) return ctx->fail(PHI_ERR_ARG, "graph view: walk_off must start at 0 and be non-decreasing");
+    if (r->n_reads && !monotone(r->read_off, r->n_reads)) return ctx->fail(PHI_ERR_ARG, "reads view: read_off must start at 0 and be non-decreasing");
+    if (g->n_vtx && g->seg_off[g->n_vtx] && !g->seg_bases) return ctx->fail(PHI_ERR_ARG, "graph view: seg_bases is NULL");
+    if (g->n_walks && g->walk_off[g->n_walks] && (!g->walk_vtx || !g->n_vtx)) return ctx->fail(PHI_ERR_ARG, "graph view: walk_vtx is NULL (or there are no vertices)");
+    if (r->n_reads && r->read_off[r->n_reads] && !r->read_bases) return ctx->fail(PHI_ERR_ARG, "reads view: read_bases is NULL");
     return PHI_OK;
 }
 
@@ -342,7 +354,7 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     const uint32_t H = ctx->n_walks, V = ctx->n_vtx; uint64_t S = ctx->n_steps;
     d_walk_vtx = ctx->walk_vtx.as<uint32_t>(); d_walk_off = ctx->walk_off.as<uint64_t>(); n_steps_eff = S;
     h_walk_len.assign(H, 0);
-    ctx->n_chunks = ctx->n_tiles = 0; ctx->unique_windows = ctx->active_chunks = ctx->rep_chunks = 0;
+    ctx->n_chunks = ctx->n_tiles = 0; ctx->unique_windows = ctx->active_chunks = ctx->rep_chunks = ctx->path_pos = 0;
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
     if (ctx->n_pieces) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_graph_in, 0));   // phi_gpu_index_run: the graph is still on the wire
     CU(cudaEventRecord(ctx->ev[EV_PREP0], ctx->st));
@@ -353,7 +365,7 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     // topological base coordinate of every vertex (chunk boundaries are defined on it)
     CU(ctx->tlen.reserve((size_t)V * 4 + 4)); CU(ctx->tprefix.reserve(((size_t)V + 1) * 8)); CU(ctx->coord.reserve((size_t)V * 16 + 16));
     CU(ctx->scan_scr.reserve(std::max({scan_u32_to_u64_scratch((uint64_t)V + 1), scan_u32_to_u64_scratch(S + 1), (size_t)1024})));
-    CU(chunk_topo_coord(ctx->top_order.as<int32_t>(), ctx->seg_off.as<uint64_t>(), V, ctx->chunk_shift, ctx->tlen.as<uint32_t>(),
+    CU(chunk_topo_coord(ctx->top_order.as<int32_t>(), ctx->seg_off.as<uint64_t>(), V, ctx->chunk_shift, ctx->own_lo, ctx->own_hi, ctx->tlen.as<uint32_t>(),
                         ctx->tprefix.as<uint64_t>(), ctx->coord.as<uint4>(), ctx->scan_scr.p, d_ctr, ctx->st, &ctx->launches));
     // common case: one kernel for step lengths, chunk flags, their scan, step bases, walk lengths and the chunk starts
     const uint64_t S0 = S;
@@ -361,10 +373,11 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     CU(ctx->chunk_step.reserve((S + 2) * 4)); CU(ctx->c_walk.reserve((S + 2) * 4));       // at most one chunk per step
     CU(ctx->fs_state.reserve(walk_steps_fused_tiles(S) * 8 + 16));
     CU(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, ctx->st)); CU(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, ctx->st));
-    CU(walk_steps_fused(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), ctx->fs_state.as<unsigned long long>() + 1, ctx->fs_state.as<uint32_t>(),
+    CU(walk_steps_fused(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), V, ctx->fs_state.as<unsigned long long>() + 1, ctx->fs_state.as<uint32_t>(),
                         ctx->step_base.as<uint32_t>(), ctx->chunk_step.as<uint32_t>(), ctx->c_walk.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), d_ctr,
                         ctx->st, &ctx->launches));
     CU(read_counters(ctx));                                             // wait 1
+    if (ctx->h_ctr[CTR_BAD_VTX]) return ctx->fail(PHI_ERR_ARG, "graph view: a walk step names a vertex id >= n_vtx");
     if (ctx->h_ctr[CTR_SEG_TOO_LONG]) return ctx->fail(PHI_ERR_UNSUPPORTED, "segment of 2^31 bases or more");
     const bool fused = ctx->h_ctr[CTR_ZERO_STEPS] == 0;
     uint64_t last = 0; uint32_t NC = 0;
@@ -372,7 +385,7 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     if (!fused) { CU(ctx->step_len.reserve(S * 4 + 4)); CU(ctx->gbase.reserve((S + 1) * 8)); CU(cudaMemsetAsync(d_ctr + CTR_NONMONO, 0, 8, ctx->st)); }
     for (int attempt = 0; !fused; ++attempt) {
         CU(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, ctx->st)); CU(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, ctx->st));
-        CU(walk_step_pass(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), ctx->step_len.as<PackedStep>(), d_ctr, ctx->st, &ctx->launches));
+        CU(walk_step_pass(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), V, ctx->step_len.as<PackedStep>(), d_ctr, ctx->st, &ctx->launches));
         CU(scan_packed_steps(ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), S, ctx->scan_scr.p, ctx->st, &ctx->launches));
         CU(cudaMemcpyAsync(&last, ctx->gbase.as<uint64_t>() + (S - 1), 8, cudaMemcpyDeviceToHost, ctx->st));
         CU(read_counters(ctx));
@@ -403,7 +416,7 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
         CU(walk_step_finalize(C, ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), d_walk_off, H, S, ctx->step_base.as<uint32_t>(),
                               ctx->walk_len.as<uint64_t>(), ctx->st, &ctx->launches));
     CU(cudaMemcpyAsync(h_walk_len.data(), ctx->walk_len.p, (size_t)H * 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(chunk_keys(C, d_walk_vtx, d_walk_off, ctx->step_base.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), k, w, d_ctr, ctx->st, &ctx->launches));
+    CU(chunk_keys(C, d_walk_vtx, d_walk_off, ctx->step_base.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), ctx->coord.as<uint4>(), k, w, d_ctr, ctx->st, &ctx->launches));
     uint32_t tcap = 1024; while (tcap < 2 * (uint64_t)NC) tcap <<= 1;
     CU(ctx->ctable.reserve((size_t)tcap * 4));
     CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch((uint64_t)NC + 2), scan_u32_to_u64_scratch((uint64_t)NC + 2))));
@@ -424,7 +437,7 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
         total_bases += h_walk_len[h];
     }
     if (total_bases >= (1ull << STEP_BASE_BITS)) return ctx->fail(PHI_ERR_UNSUPPORTED, "2^38 or more walk bases on one GPU; shard the walks over more GPUs");
-    ctx->unique_windows = ctx->h_ctr[CTR_UNIQUE_WINDOWS]; ctx->active_chunks = ctx->h_ctr[CTR_ACTIVE_CHUNKS];
+    ctx->unique_windows = ctx->h_ctr[CTR_UNIQUE_WINDOWS]; ctx->active_chunks = ctx->h_ctr[CTR_ACTIVE_CHUNKS]; ctx->path_pos = ctx->h_ctr[CTR_PATH_POS];
     CU(ctx->tiles.reserve((size_t)ctx->n_tiles * sizeof(TileRec) + 32));
     CU(chunk_tiles(C, d_walk_off, ctx->step_base.as<uint32_t>(), w, ctx->tiles.as<TileRec>(), ctx->st, &ctx->launches));
     // member walks of every representative (the grouped result copies them instead of instantiating one record per member)
@@ -450,6 +463,8 @@ struct NcclApi {
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclCommAbort) CommAbort = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
@@ -473,11 +488,23 @@ NcclApi *nccl_api(std::string &err)
     PHI_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") PHI_NCCL_SYM(CommInitRank, "ncclCommInitRank") PHI_NCCL_SYM(CommDestroy, "ncclCommDestroy")
     PHI_NCCL_SYM(GetErrorString, "ncclGetErrorString") PHI_NCCL_SYM(GroupStart, "ncclGroupStart") PHI_NCCL_SYM(GroupEnd, "ncclGroupEnd")
     PHI_NCCL_SYM(Send, "ncclSend") PHI_NCCL_SYM(Recv, "ncclRecv") PHI_NCCL_SYM(AllGather, "ncclAllGather") PHI_NCCL_SYM(Broadcast, "ncclBroadcast")
+    PHI_NCCL_SYM(CommAbort, "ncclCommAbort") PHI_NCCL_SYM(AllReduce, "ncclAllReduce")
 #undef PHI_NCCL_SYM
     return &api;
 }
 
 }  // namespace
+
+// the ctx's communicator goes away: orderly (destroy) or, after a failure in the middle of an exchange, by abort so that this
+// rank does not sit in a half-issued collective
+static void comm_release(phi_gpu_index_ctx *ctx, bool abort)
+{
+    if (!ctx->comm) return;
+    std::string err;
+    NcclApi *nc = nccl_api(err);
+    if (nc) { if (abort) nc->CommAbort((ncclComm_t)ctx->comm); else nc->CommDestroy((ncclComm_t)ctx->comm); }
+    ctx->comm = nullptr;
+}
 
 #define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return ctx->fail(PHI_ERR_COMM, std::string(#call) + ": " + nc->GetErrorString(r_)); } while (0)
 
@@ -499,6 +526,7 @@ extern "C" int phi_gpu_index_comm_init(phi_gpu_index_ctx *ctx, int rank, int wor
     if (!ctx) return PHI_ERR_ARG;
     if (world < 1 || rank < 0 || rank >= world || !id) return ctx->fail(PHI_ERR_ARG, "bad rank/world/id");
     if (world > 64) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 64 ranks");
+    comm_release(ctx, false);                                               // a repeated comm_init replaces the communicator
     ctx->rank = rank; ctx->world = world; ctx->walk_id_base = walk_id_base; ctx->n_walks_global = n_walks_global;
     if (world == 1) return PHI_OK;
     std::string err;
@@ -888,9 +916,9 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
     const uint32_t wbase = ctx->world > 1 ? ctx->walk_id_base : 0;
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
     CU(ctx->mpw.reserve(((size_t)HM + 1) * 8));
-    uint64_t positions = 0, bases = 0;
-    for (uint32_t h = 0; h < H; ++h) { bases += h_walk_len[h]; if (h_walk_len[h] >= (uint64_t)(w + k - 1)) positions += h_walk_len[h] - k + 1; }
-    o.path_pos = positions;
+    uint64_t bases = 0;
+    for (uint32_t h = 0; h < H; ++h) bases += h_walk_len[h];
+    o.path_pos = ctx->path_pos;                                          // counted with the chunk geometry: only owned chunks when a walk region is set
     CU(cudaEventRecord(ctx->ev[EV_WK0], ctx->st));
     CU(cudaEventRecord(ctx->ev[EV_WK1], ctx->st));
     CU(cudaMemsetAsync(ctx->mpw.p, 0, ((size_t)HM + 1) * 8, ctx->st));
@@ -1238,12 +1266,6 @@ static int stage_debug_hist(phi_gpu_index_ctx *ctx, int k, int w, const std::vec
     return PHI_OK;
 }
 
-// A result owns pinned buffers borrowed from its ctx's pool; freeing it hands them back (or releases them if the ctx is gone).
-struct ResultBox {
-    phi_index_result pub;              // must stay the first member: the public pointer is &box->pub
-    phi_gpu_index_ctx *owner;
-    PinnedBuf bufs[12]; int nbufs;
-};
 static PinnedBuf pinned_acquire(phi_gpu_index_ctx *ctx, size_t bytes)
 {
     PinnedBuf best; int bi = -1;
@@ -1266,6 +1288,11 @@ extern "C" void phi_gpu_index_result_free(phi_index_result *r)
 {
     if (!r) return;
     ResultBox *b = (ResultBox *)r;
+    if (b->heap) {                                                          // phi_index_result_merge: plain malloc'ed arrays
+        for (int i = 0; i < b->nbufs; ++i) free(b->bufs[i].p);
+        free(b);
+        return;
+    }
     std::lock_guard<std::mutex> lk(g_live_mu);
     const bool alive = g_live_ctx.count(b->owner) != 0;
     for (int i = 0; i < b->nbufs; ++i) {
@@ -1488,6 +1515,14 @@ extern "C" int phi_gpu_index_set_walk_sharing(phi_gpu_index_ctx *ctx, int chunk_
     if (!ctx) return PHI_ERR_ARG;
     if (chunk_shift < 4 || chunk_shift > 24) return ctx->fail(PHI_ERR_ARG, "chunk_shift must be in [4, 24]");
     ctx->chunk_shift = chunk_shift; ctx->dedupe = share ? 1 : 0;
+    return PHI_OK;
+}
+
+extern "C" int phi_gpu_index_set_walk_region(phi_gpu_index_ctx *ctx, uint64_t coord_lo, uint64_t coord_hi)
+{
+    if (!ctx) return PHI_ERR_ARG;
+    if (coord_lo > coord_hi) return ctx->fail(PHI_ERR_ARG, "walk region: coord_lo > coord_hi");
+    ctx->own_lo = coord_lo; ctx->own_hi = coord_hi;
     return PHI_OK;
 }
 

@@ -32,11 +32,29 @@ def expand_ranges(starts, lens):
 class SynthGraph:
     """Graph (flat views) + what is needed to spell any allele vector as a sequence / walk."""
 
-    def __init__(self, graph, piece_first_node, piece_n_nodes, piece_off, piece_len, n_sites, alleles):
+    def __init__(self, graph, piece_first_node, piece_n_nodes, piece_off, piece_len, n_sites, alleles, fa=None, pick=None, block=None):
         self.graph = graph
         self.piece_first_node, self.piece_n_nodes = piece_first_node, piece_n_nodes
         self.piece_off, self.piece_len = piece_off, piece_len
-        self.n_sites, self.alleles = n_sites, alleles
+        self.n_sites, self.alleles = n_sites, alleles          # alleles: [n_haps, n_sites], or None for big graphs (use allele_row)
+        self.fa, self.pick, self.block = fa, pick, block       # founder alleles [founders, n_sites], founder of (haplotype, LD block), block of a site
+
+    @property
+    def n_haps(self):
+        return self.pick.shape[0] if self.pick is not None else self.alleles.shape[0]
+
+    def allele_row(self, h):
+        """Allele vector of haplotype h (never materialises the whole [n_haps, n_sites] matrix)."""
+        if self.alleles is not None:
+            return self.alleles[h]
+        return self.fa[self.pick[h][self.block], np.arange(self.n_sites)].astype(np.uint8)
+
+    def mosaic_row(self, src_of_site):
+        """Allele vector of a mosaic: site s takes the allele of haplotype src_of_site[s]."""
+        cols = np.arange(self.n_sites)
+        if self.alleles is not None:
+            return self.alleles[src_of_site, cols]
+        return self.fa[self.pick[src_of_site, self.block], cols].astype(np.uint8)
 
     def pieces_of(self, allele_vec):
         n = self.n_sites
@@ -125,13 +143,14 @@ def make_graph(seed, backbone_len, n_haps, var_spacing=50, chop=30, founders=8, 
     nblocks = n_sites // block_sites + 1
     block = np.arange(n_sites) // block_sites
     pick = rng.integers(0, founders, (n_haps, nblocks))
-    alleles = fa[pick[:, block], np.arange(n_sites)].astype(np.uint8)      # [n_haps, n_sites]
+    # [n_haps, n_sites]; big graphs (chromosome-scale configs) keep only founders + picks and spell rows on demand
+    alleles = fa[pick[:, block], np.arange(n_sites)].astype(np.uint8) if n_haps * n_sites <= (1 << 27) else None
 
     g = Graph(seg_off, seg_bases, np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint32),
               np.arange(n_vtx, dtype=np.int32), [])
-    sg = SynthGraph(g, piece_first_node, piece_n_nodes, piece_off, piece_len, n_sites, alleles)
+    sg = SynthGraph(g, piece_first_node, piece_n_nodes, piece_off, piece_len, n_sites, alleles, fa, pick, block)
     lo, hi = walk_range if walk_range is not None else (0, n_haps)      # only these walks are spelled out (multi-GPU shards)
-    walks = [sg.walk_of(alleles[h]) for h in range(lo, hi)]
+    walks = [sg.walk_of(sg.allele_row(h)) for h in range(lo, hi)]
     g.walk_off = np.concatenate([[0], np.cumsum([len(x) for x in walks])]).astype(np.uint64)
     g.walk_vtx = np.concatenate(walks).astype(np.uint32) if walks else np.zeros(0, dtype=np.uint32)
     g.walk_names = [f"hap{h}.{h}" for h in range(lo, hi)]
@@ -142,10 +161,10 @@ def make_reads(seed, sg, coverage, read_len=150, sub_err=0.005, len_sigma=0.0, m
                lower_frac=0.0, n_frac=0.0, sample_seed=0):
     """Reads sampled from a held-out mosaic of the graph's haplotypes, both strands, substitution errors."""
     rng = np.random.Generator(np.random.PCG64(seed ^ 0x5EED))
-    n_haps = sg.alleles.shape[0]
+    n_haps = sg.n_haps
     nseg = sg.n_sites // mosaic_block + 1
     src = rng.integers(0, n_haps, nseg)
-    mosaic = sg.alleles[src[np.arange(sg.n_sites) // mosaic_block], np.arange(sg.n_sites)]
+    mosaic = sg.mosaic_row(src[np.arange(sg.n_sites) // mosaic_block])
     seq = sg.sequence_of(mosaic)
     n = len(seq)
     if sample_seed:                                               # same sample (mosaic), independent read draw
@@ -173,6 +192,50 @@ def make_reads(seed, sg, coverage, read_len=150, sub_err=0.005, len_sigma=0.0, m
         bases[m] |= 0x20
         bases[rng.random(len(bases)) < n_frac] = ord("N")
     return Reads(off.astype(np.uint64), bases.astype(np.uint8))
+
+
+def mosaic_sequence(seed, sg, mosaic_block=2000):
+    """The held-out mosaic sample make_reads / make_reads_big draw from (same for both)."""
+    rng = np.random.Generator(np.random.PCG64(seed ^ 0x5EED))
+    nseg = sg.n_sites // mosaic_block + 1
+    src = rng.integers(0, sg.n_haps, nseg)
+    return sg.sequence_of(sg.mosaic_row(src[np.arange(sg.n_sites) // mosaic_block]))
+
+
+READ_BATCH = 1 << 16
+
+
+def n_reads_big(seq_len, coverage, read_len):
+    return max(1, int(round(coverage * seq_len / read_len)))
+
+
+def make_reads_big(seed, sg, coverage, read_len=150, sub_err=0.005, read_range=None, seq=None):
+    """Fixed-length reads for the chromosome-scale configs, generated in independent batches of READ_BATCH reads (batch b has its
+    own generator), so that a rank can spell just its own contiguous range [lo, hi) of the global read set and memory stays bounded.
+    Same sample, strands and error model as make_reads; the draws differ (make_reads consumes one sequential stream)."""
+    if seq is None:
+        seq = mosaic_sequence(seed, sg)
+    n = len(seq)
+    L = min(read_len, n)
+    total = n_reads_big(n, coverage, read_len)
+    lo, hi = read_range if read_range is not None else (0, total)
+    lo, hi = max(0, lo), min(total, hi)
+    out = np.empty((max(hi - lo, 0), L), dtype=np.uint8)
+    ar = np.arange(L, dtype=np.int64)
+    for b in range(lo // READ_BATCH, (hi + READ_BATCH - 1) // READ_BATCH if hi > lo else 0):
+        rng = np.random.Generator(np.random.PCG64([seed ^ 0x5EED, 0xB47C4, b]))
+        cnt = min(READ_BATCH, total - b * READ_BATCH)
+        starts = (rng.random(cnt) * (n - L + 1)).astype(np.int64)
+        rev = rng.random(cnt) < 0.5
+        bases = seq[starts[:, None] + ar]
+        err = rng.random((cnt, L)) < sub_err
+        code = np.searchsorted(_ACGT, bases[err])
+        bases[err] = _ACGT[(code + rng.integers(1, 4, len(code))) % 4]
+        bases[rev] = _COMP[bases[rev][:, ::-1]]
+        a, z = max(lo, b * READ_BATCH), min(hi, b * READ_BATCH + cnt)
+        out[a - lo:z - lo] = bases[a - b * READ_BATCH:z - b * READ_BATCH]
+    off = np.arange(out.shape[0] + 1, dtype=np.uint64) * np.uint64(L)
+    return Reads(off, out.reshape(-1))
 
 
 # ------------------------------------------------------------------ text writers (for the reference CLI)

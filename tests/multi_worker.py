@@ -34,16 +34,18 @@ def load(name):
     return c.graph, c.reads, c.k, c.w, c.T
 
 
-def main_gpu(name):
+def main_gpu(name, mode="region"):
     import torch
     import phi_b200
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
     g, rd, k, w, T = load(name)
-    gs, rs, base = multi.shard_inputs(g, rd, rank, world)
+    gs, rs, base, region = multi.shard_inputs(g, rd, rank, world, k, w, mode)
     ix = phi_b200.PhiGpuIndex(local)
     multi.init_comm(ix, rank, world, base, g.n_walks, dist)
+    if region is not None:
+        ix.set_walk_region(*region)
     part = ix.run(gs, rs, k, w, T)
     part2 = ix.run(gs, rs, k, w, T)                      # repeatable
     assert_same_result(part, part2)
@@ -55,7 +57,7 @@ def main_gpu(name):
         want = phi_io.oracle_index(g, rd, k, w, T)
         got.path_hits = want.path_hits                   # pre-filter hit count is per-GPU bookkeeping
         assert_same_result(want, got)
-        print(f"MULTI_OK gpu world={world} case={name} spectrum={got.count_sp_r} anchors={got.n_anchors}")
+        print(f"MULTI_OK gpu world={world} case={name} mode={mode} region={region} spectrum={got.count_sp_r} anchors={got.n_anchors}")
     ix.close()
     dist.barrier()
 
@@ -88,7 +90,7 @@ def main_cpu(name):
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo")
     g, rd, k, w, T = load(name)
-    gs, rs, base = multi.shard_inputs(g, rd, rank, world)
+    gs, rs, base, _ = multi.shard_inputs(g, rd, rank, world, k, w, "walk")
     empty = _abi.Graph(g.seg_off, g.seg_bases, np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint32), g.top_order_map)
     local = phi_io.oracle_index(empty, rs, k, w, T).spectrum            # this rank's distinct read-minimizer hashes
     owner = np.array([multi.owner_of_hash(h, world) for h in local], dtype=np.int64)
@@ -150,4 +152,7 @@ def main_cpu(name):
 
 
 if __name__ == "__main__":
-    (main_gpu if sys.argv[1] == "gpu" else main_cpu)(sys.argv[2])
+    if sys.argv[1] == "gpu":
+        main_gpu(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "region")
+    else:
+        main_cpu(sys.argv[2])

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     h = open(os.path.join(ROOT, "include", "phi_gpu_index.h")).read()
     h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
-    return sorted(set(re.findall(r"\b(phi_(?:gpu|shard)_\w+)\s*\(", h)))
+    return sorted(set(re.findall(r"\b(phi_(?:gpu|shard|host|index)_\w+)\s*\(", h)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -5,7 +5,7 @@ import pytest
 
 import phi_io
 import phi_b200
-from phi_b200 import synth
+from phi_b200 import synth, _abi
 from golden_cases import Case, SMALL, MHC, check_against_golden, assert_same_result
 from test_oracle_golden import KAT
 
@@ -154,7 +154,6 @@ def test_full_size_properties(gpu):
     assert got2.n_filtered == got.n_filtered and np.array_equal(got2.spectrum, got.spectrum)
     # read order does not matter; duplicated reads change nothing (set semantics, ILP_index.cpp:631-635)
     rd2 = phi_b200.Reads(np.concatenate([rd.read_off, rd.read_off[1:] + rd.read_off[-1]]), np.concatenate([rd.read_bases, rd.read_bases]))
-    assert_same_result(got, gpu.run(sg.graph, rd2)) if False else None
     got3 = gpu.run(sg.graph, rd2)
     assert np.array_equal(got3.spectrum, got.spectrum) and np.array_equal(got3.anchor_vtx, got.anchor_vtx)
 
@@ -279,3 +278,56 @@ def test_more_than_65536_walks_use_32_bit_member_ids(gpu):
     sg2 = synth.make_graph(978, 20000, 5)
     small = gpu.run(sg2.graph, synth.make_reads(978, sg2, 5.0), 31, 25, 1.0)
     assert small.member_walk_bytes == 2 and small.n_anchors > 0
+
+
+# ---- region partition of the walks on ONE GPU: every region is run by its own ctx (no communicator, so the group counts are
+# local: with a threshold nothing can reach no rank is dropped and the merged parts must equal the oracle's unfiltered result)
+@pytest.mark.parametrize("world,seed,kw", [(2, 31, {}), (3, 32, dict(lower_frac=0.01, n_frac=0.002)), (5, 33, dict(chop=8)), (4, 34, dict(founders=3, block_sites=25))])
+def test_region_slices_merge_to_the_whole(gpu, world, seed, kw):
+    from phi_b200 import multi
+    sg = synth.make_graph(seed, 90_000, 9, **kw)
+    rd = synth.make_reads(seed, sg, 4.0)
+    g = sg.graph
+    k, w, T = 31, 25, 1000.0
+    want = phi_io.oracle_index(g, rd, k, w, T)
+    bounds = multi.region_bounds(g, world)
+    parts = []
+    for r in range(world):
+        gs = multi.slice_walks(g, k, w, bounds[r], bounds[r + 1])
+        ix = phi_b200.PhiGpuIndex(0)
+        ix.set_walk_region(bounds[r], bounds[r + 1])
+        p = ix.run(gs, rd, k, w, T)
+        ix.close()
+        if r:
+            p.spectrum = np.zeros(0, dtype=np.uint64)                      # as in a multi-GPU run: rank 0 alone carries the spectrum
+            p.read_kmer_positions = p.read_minimizers_emitted = 0
+        parts.append(p)
+    got = multi.merge_results(parts)
+    assert sum(p.path_kmer_positions for p in parts) == want.path_kmer_positions
+    got.path_hits = want.path_hits
+    assert_same_result(want, got)
+    # the whole range in one region is the plain run
+    ix = phi_b200.PhiGpuIndex(0)
+    ix.set_walk_region(0, 2 ** 64 - 1)
+    assert_same_result(want, ix.run(g, rd, k, w, T))
+    ix.close()
+
+
+def test_inconsistent_views_are_rejected(gpu):
+    sg = synth.make_graph(5, 3000, 2)
+    rd = synth.make_reads(5, sg, 1.0)
+    g = sg.graph
+    bad = phi_b200.Graph(g.seg_off, g.seg_bases, g.walk_off, g.walk_vtx.copy(), g.top_order_map)
+    bad.walk_vtx[len(bad.walk_vtx) // 2] = g.n_vtx + 7                     # vertex id out of range: caught on the device by the step pass
+    with pytest.raises(phi_b200.PhiGpuError) as e:
+        gpu.run(bad, rd)
+    assert e.value.code == _abi.PHI_ERR_ARG
+    so = g.seg_off.copy(); so[3] = so[5] + 1                               # offsets that go backwards
+    with pytest.raises(phi_b200.PhiGpuError) as e:
+        gpu.run(phi_b200.Graph(so, g.seg_bases, g.walk_off, g.walk_vtx, g.top_order_map), rd)
+    assert e.value.code == _abi.PHI_ERR_ARG
+    ro = rd.read_off.copy(); ro[0] = 1
+    with pytest.raises(phi_b200.PhiGpuError) as e:
+        gpu.run(g, phi_b200.Reads(ro, rd.read_bases))
+    assert e.value.code == _abi.PHI_ERR_ARG
+    assert_same_result(phi_io.oracle_index(g, rd, 31, 25, 1.0), gpu.run(g, rd))   # the ctx is still usable

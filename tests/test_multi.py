@@ -18,9 +18,9 @@ def free_port():
     return p
 
 
-def launch(mode, case, world):
+def launch(mode, case, world, partition="region"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(free_port()), os.path.join(ROOT, "tests", "multi_worker.py"), mode, case]
+           "--master-port", str(free_port()), os.path.join(ROOT, "tests", "multi_worker.py"), mode, case, partition]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "MULTI_OK" in p.stdout, p.stdout[-2000:]
@@ -33,10 +33,11 @@ def test_sharded_algorithm_cpu_gloo(case, world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("partition", ["region", "walk"])
 @pytest.mark.parametrize("case", ["toy_k3_w2", "synth_small", "synth_dirty", "synth_repeats", "mhc4", "synth:77:400000:11:3.0"])
-def test_multi_gpu_matches_oracle(case):
+def test_multi_gpu_matches_oracle(case, partition):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
-    launch("gpu", case, min(n, 4) if case != "toy_k3_w2" else 2)
+    launch("gpu", case, min(n, 4) if case != "toy_k3_w2" else 2, partition)

@@ -1,0 +1,108 @@
+"""CPU: the host side of the multi-GPU path — region partition of the walks (phi_shard_walk_regions / phi_shard_slice_walks) and the
+merge of per-GPU parts (phi_index_result_merge), checked against the oracle's result re-partitioned on the host."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+import phi_io
+from phi_b200 import _abi, multi, synth
+
+
+def grouped(res):
+    ro, gl, gv, mo, mw = phi_io.group_anchors(res)
+    return dataclasses.replace(res, rank_off=ro, group_len=gl, group_vtx=gv, group_member_off=mo, member_walk=mw, n_groups=len(gl))
+
+
+def take_anchors(res, idx, **over):
+    lens = np.diff(res.anchor_off.astype(np.int64))
+    starts = res.anchor_off.astype(np.int64)[idx]
+    vtx = np.concatenate([res.anchor_vtx[s:s + n] for s, n in zip(starts, lens[idx])]) if len(idx) else np.zeros(0, dtype=np.int32)
+    return dataclasses.replace(res, anchor_rank=res.anchor_rank[idx], anchor_walk=res.anchor_walk[idx],
+                               anchor_off=np.concatenate([[0], np.cumsum(lens[idx])]).astype(np.uint64), anchor_vtx=vtx.astype(np.int32),
+                               anchors_per_walk=np.bincount(res.anchor_walk[idx], minlength=res.n_walks).astype(np.uint64), **over)
+
+
+@pytest.fixture(scope="module")
+def case():
+    sg = synth.make_graph(42, 60000, 9, founders=4, block_sites=30)
+    rd = synth.make_reads(42, sg, 6.0)
+    return sg.graph, rd, phi_io.oracle_index(sg.graph, rd, 31, 25, 1.0)
+
+
+@pytest.mark.parametrize("n_parts,seed", [(1, 0), (2, 1), (3, 2), (8, 3)])
+def test_merge_of_arbitrary_parts_is_the_whole(case, n_parts, seed):
+    """Anchors dealt to the parts at random: the same (rank, vertex list) group then lives in several parts with different member
+    walks, the groups of one rank are spread over the parts — the merge must restore key order and unite the members."""
+    g, rd, want = case
+    rng = np.random.default_rng(seed)
+    assign = rng.integers(0, n_parts, want.n_anchors)
+    parts = []
+    for p in range(n_parts):
+        parts.append(grouped(take_anchors(
+            want, np.nonzero(assign == p)[0], n_filtered=want.n_filtered if p == n_parts - 1 else 0,
+            minimizers_per_walk=want.minimizers_per_walk if p == 0 else want.minimizers_per_walk * 0,
+            spectrum=want.spectrum if p == n_parts // 2 else np.zeros(0, dtype=np.uint64),
+            read_kmer_positions=want.read_kmer_positions if p == 0 else 0, path_kmer_positions=want.path_kmer_positions if p == 0 else 0,
+            read_minimizers_emitted=0, path_minimizers_emitted=want.path_minimizers_emitted if p == 0 else 0, path_hits=want.path_hits if p == 0 else 0)))
+    got = multi.merge_results(parts)
+    whole = grouped(want)
+    for f in ("rank_off", "group_len", "group_vtx", "group_member_off", "member_walk"):
+        assert np.array_equal(getattr(got, f), getattr(whole, f)), f
+    for f in ("spectrum", "anchor_rank", "anchor_walk", "anchor_off", "anchor_vtx", "minimizers_per_walk", "anchors_per_walk"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+    assert got.n_filtered == want.n_filtered and got.count_sp_r == want.count_sp_r
+    assert got.path_kmer_positions == want.path_kmer_positions and got.path_hits == want.path_hits
+
+
+def test_merge_of_walk_parts(case):
+    g, rd, want = case
+    parts = [grouped(p) for p in phi_io.split_result_by_walks(want, [0, 3, 5, 9])]
+    got = multi.merge_results(parts)
+    for f in ("spectrum", "anchor_rank", "anchor_walk", "anchor_off", "anchor_vtx", "minimizers_per_walk", "anchors_per_walk"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("k,w", [(31, 25), (5, 3), (32, 256)])
+def test_region_slices_cover_the_walks_with_context(case, world, k, w):
+    g = case[0]
+    seg_len = np.diff(g.seg_off.astype(np.int64))
+    order = np.argsort(g.top_order_map)
+    coord = np.zeros(g.n_vtx, dtype=np.int64)
+    coord[order] = np.concatenate([[0], np.cumsum(seg_len[order])])[:-1]
+    b = multi.region_bounds(g, world)
+    assert b[0] == 0 and b[-1] == 2 ** 64 - 1 and np.all(np.diff(b.astype(np.float64)) >= 0)
+    wo = g.walk_off.astype(np.int64)
+    owned = [np.zeros(int(wo[h + 1] - wo[h]), dtype=np.int64) for h in range(g.n_walks)]
+    for r in range(world):
+        gs = multi.slice_walks(g, k, w, b[r], b[r + 1])
+        assert gs.n_walks == g.n_walks
+        so = gs.walk_off.astype(np.int64)
+        for h in range(g.n_walks):
+            full = g.walk_vtx[wo[h]:wo[h + 1]]
+            sl = gs.walk_vtx[so[h]:so[h + 1]]
+            c = coord[full]
+            mine = (c >= int(b[r])) & (c < (int(b[r + 1]) if r + 1 < world else 2 ** 63))
+            owned[h] += mine
+            if not mine.any():
+                assert len(sl) == 0
+                continue
+            a, z = np.nonzero(mine)[0][[0, -1]]
+            # the slice is a contiguous piece of the walk around the owned steps ...
+            first = next(i for i in range(a + 1) if np.array_equal(full[i:i + len(sl)], sl) and i + len(sl) > z)
+            # ... with >= w bases in front of the first owned step and >= k-1 behind the last one, unless the walk ends there
+            assert first == 0 or seg_len[full[first:a]].sum() >= w
+            end = first + len(sl)
+            assert end == len(full) or seg_len[full[z + 1:end]].sum() >= k - 1
+    for h in range(g.n_walks):
+        assert np.all(owned[h] == 1)                       # every step is owned by exactly one region
+
+
+def test_region_cut_refuses_walks_against_the_order(case):
+    g = case[0]
+    bad = _abi.Graph(g.seg_off, g.seg_bases, g.walk_off, g.walk_vtx[::-1].copy(), g.top_order_map)
+    assert multi.slice_walks(bad, 31, 25, 0, 1000) is None
+    assert multi.region_bounds(_abi.Graph(g.seg_off, g.seg_bases, g.walk_off, g.walk_vtx, np.zeros(g.n_vtx, dtype=np.int32)), 2) is None
+    gs, rs, base, region = multi.shard_inputs(bad, case[1], 1, 2, 31, 25, "region")    # falls back to whole walks
+    assert region is None and base > 0
