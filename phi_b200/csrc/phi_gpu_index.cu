@@ -94,6 +94,8 @@ struct phi_gpu_index_ctx {
     uint64_t gcap_hint = 0, gcap_hint2 = 0;   // group-table sizes that worked last time (local table, owner-side table)
     DevBuf xk_a, xk_b, xcnt, xoff, ag_send, ag_recv, m_rank, m_cnt, m_voff, m_nv, r_rank, r_walk, r_pos, r_voff, r_nv, r_vtx, s_rank, s_walk, s_pos, s_voff, s_nv, s_vtx;
     std::vector<uint64_t> own_off;       // [world + 1] first global rank owned by each GPU (multi-GPU runs)
+    uint64_t *h_words = nullptr; size_t h_words_cap = 0;   // pinned: gathered words of the small collectives
+    uint64_t *h_route = nullptr;         // pinned [512]: small host -> device parameter blocks of the record exchange
 
     int fail(int code, const std::string &m) { err = m; return code; }
 };
@@ -144,6 +146,7 @@ extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
     if ((e = cudaHostAlloc((void **)&ctx->h_ctr2, CTR_COUNT * 8, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     if ((e = ctx->ctr.reserve(CTR_COUNT * 8)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     if ((e = ctx->ctr2.reserve(CTR_COUNT * 8)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
+    if ((e = cudaHostAlloc((void **)&ctx->h_route, 512 * 8, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     { std::lock_guard<std::mutex> lk(g_live_mu); g_live_ctx.insert(ctx); }
     *out = ctx;
     return PHI_OK;
@@ -185,6 +188,8 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->h_ctr2) cudaFreeHost(ctx->h_ctr2);
     if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
+    if (ctx->h_words) cudaFreeHost(ctx->h_words);
+    if (ctx->h_route) cudaFreeHost(ctx->h_route);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->ev_graph_in) cudaEventDestroy(ctx->ev_graph_in);
@@ -540,78 +545,104 @@ extern "C" int phi_gpu_index_comm_init(phi_gpu_index_ctx *ctx, int rank, int wor
     return PHI_OK;
 }
 
-// byte-wise all-to-all with per-peer counts and offsets (in elements of `esz` bytes)
-static int alltoallv(phi_gpu_index_ctx *ctx, NcclApi *nc, const void *send, const std::vector<uint64_t> &scnt, const std::vector<uint64_t> &soff,
-                     void *recv, const std::vector<uint64_t> &rcnt, const std::vector<uint64_t> &roff, size_t esz)
+// ---- small collectives of the exchange steps.  Every rank contributes `n` u64 words that already sit on the device (d_send);
+// the gathered words come back on the host (pinned).  ONE collective + ONE copy + ONE wait: counts never travel host -> device -> host.
+// The last word of every rank's contribution is its status: 0, or the error code of a stage that failed on that rank, so that all
+// ranks leave the exchange together instead of one rank returning while its peers sit in the next collective.
+static int allgather_words(phi_gpu_index_ctx *ctx, NcclApi *nc, const uint64_t *d_send, size_t n, const uint64_t *&h_all)
 {
-    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    const size_t W = ctx->world;
+    CU(ctx->ag_recv.reserve(n * W * 8 + 8));
+    if (ctx->h_words_cap < n * W) {
+        if (ctx->h_words) cudaFreeHost(ctx->h_words);
+        ctx->h_words = nullptr; ctx->h_words_cap = 0;
+        CU(cudaHostAlloc((void **)&ctx->h_words, n * W * 8 + 64, cudaHostAllocDefault));
+        ctx->h_words_cap = n * W;
+    }
+    NC(nc->AllGather(d_send, ctx->ag_recv.p, n, ncclUint64, (ncclComm_t)ctx->comm, ctx->st));
+    CU(cudaMemcpyAsync(ctx->h_words, ctx->ag_recv.p, n * W * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    h_all = ctx->h_words;
+    return PHI_OK;
+}
+
+// did any rank report a failure?  (word `n - 1` of every rank's contribution)
+static int peers_status(phi_gpu_index_ctx *ctx, const uint64_t *h_all, size_t n, int own_status)
+{
     for (int p = 0; p < ctx->world; ++p) {
-        if (scnt[p]) NC(nc->Send((const char *)send + soff[p] * esz, scnt[p] * esz, ncclUint8, p, comm, ctx->st));
-        if (rcnt[p]) NC(nc->Recv((char *)recv + roff[p] * esz, rcnt[p] * esz, ncclUint8, p, comm, ctx->st));
+        const uint64_t st = h_all[(size_t)p * n + n - 1];
+        if (!st) continue;
+        if (p == ctx->rank) return own_status ? own_status : PHI_ERR_COMM;    // this rank's own error text is already in place
+        return ctx->fail(PHI_ERR_COMM, "rank " + std::to_string(p) + " of the multi-GPU run failed (status " + std::to_string(st) + "); this rank stops with it");
     }
     return PHI_OK;
 }
 
-// every rank contributes `n` u64 values (host), receives world*n (host)
-static int allgather_host_u64(phi_gpu_index_ctx *ctx, NcclApi *nc, const std::vector<uint64_t> &mine, std::vector<uint64_t> &all)
-{
-    const size_t n = mine.size(), W = ctx->world;
-    CU(ctx->ag_send.reserve(n * 8 + 8)); CU(ctx->ag_recv.reserve(n * W * 8 + 8));
-    CU(cudaMemcpyAsync(ctx->ag_send.p, mine.data(), n * 8, cudaMemcpyHostToDevice, ctx->st));
-    NC(nc->AllGather(ctx->ag_send.p, ctx->ag_recv.p, n, ncclUint64, (ncclComm_t)ctx->comm, ctx->st));
-    all.resize(n * W);
-    CU(cudaMemcpyAsync(all.data(), ctx->ag_recv.p, n * W * 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    return PHI_OK;
-}
-
-__global__ void owner_split_kernel(const uint64_t *sorted, uint64_t n, const uint64_t *bounds, int world, uint64_t *split)
+__global__ void owner_split_kernel(const uint64_t *sorted, uint64_t n, int world, uint64_t status, uint64_t *split /* [world + 2] */)
 {
     int o = threadIdx.x;
-    if (o > world) return;
+    if (o > world + 1) return;
+    if (o == world + 1) { split[o] = status; return; }
     if (o == world) { split[o] = n; return; }
-    uint64_t key = bounds[o], lo = 0, hi = n;                        // first index with sorted[i] >= bounds[o]
+    // smallest hash owned by o is ceil(o * 2^64 / world)   (phi_shard_owner_of_hash)
+    const uint64_t key = (uint64_t)((((unsigned __int128)o << 64) + world - 1) / world);
+    uint64_t lo = 0, hi = n;                                            // first index with sorted[i] >= key
     while (lo < hi) { uint64_t m = (lo + hi) >> 1; if (sorted[m] < key) lo = m + 1; else hi = m; }
     split[o] = lo;
 }
 
-// Exchange of the locally distinct, locally sorted hashes (n_local of them in ctx->spec_a) -> ctx->spec_a = global sorted spectrum.
-static int exchange_spectrum(phi_gpu_index_ctx *ctx, uint64_t n_local, uint64_t &n_spec)
+// the owner's slice is complete: (distinct keys incl. the key ~0, overflow flag, status) for the second small collective
+__global__ void owner_tail_kernel(const uint32_t *tblk_total, const unsigned long long *ctr, uint64_t status, uint64_t *slice, uint64_t *words /* [3] */)
+{
+    uint64_t n = tblk_total ? *tblk_total : 0;
+    if (tblk_total && ctr[CTR_HAS_MAXKEY]) { slice[n] = TABLE_EMPTY; ++n; }   // the key ~0 is the largest of the last owner's range
+    words[0] = n; words[1] = tblk_total ? ctr[CTR_OVERFLOW] : 0; words[2] = status;
+}
+
+// Exchange of the locally distinct, locally sorted hashes (n_local of them in ctx->spec_a) -> ctx->spec_a = global sorted spectrum,
+// ctx->own_off = first global rank of every owner.  status: error code of an earlier stage of this rank (all ranks stop together).
+static int exchange_spectrum(phi_gpu_index_ctx *ctx, uint64_t n_local, uint64_t &n_spec, int status)
 {
     std::string err; NcclApi *nc = nccl_api(err);
     if (!nc || !ctx->comm) return ctx->fail(PHI_ERR_COMM, "communicator not initialised");
     const int W = ctx->world, me = ctx->rank;
-    // owner boundaries: smallest hash owned by o is ceil(o * 2^64 / W)   (phi_shard_owner_of_hash)
-    std::vector<uint64_t> bounds(W + 1, 0), split(W + 1, 0);
-    for (int o = 0; o < W; ++o) bounds[o] = (uint64_t)((((unsigned __int128)o << 64) + W - 1) / W);
-    CU(ctx->xcnt.reserve((W + 1) * 16));
-    uint64_t *d_bounds = ctx->xcnt.as<uint64_t>(), *d_split = d_bounds + (W + 1);
-    CU(cudaMemcpyAsync(d_bounds, bounds.data(), (W + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
-    owner_split_kernel<<<1, 128, 0, ctx->st>>>(ctx->spec_a.as<uint64_t>(), n_local, d_bounds, W, d_split);
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    CU(ctx->xcnt.reserve(8192));
+    uint64_t *d_split = ctx->xcnt.as<uint64_t>();                       // [W + 2] | tail words [3]
+    uint64_t *d_tail = d_split + 72;
+    owner_split_kernel<<<1, 128, 0, ctx->st>>>(ctx->spec_a.as<uint64_t>(), n_local, W, (uint64_t)status, d_split);
     CU(cudaGetLastError()); ctx->launches++;
-    CU(cudaMemcpyAsync(split.data(), d_split, (W + 1) * 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    std::vector<uint64_t> scnt(W), soff(W), all;
-    for (int o = 0; o < W; ++o) { scnt[o] = split[o + 1] - split[o]; soff[o] = split[o]; }
-    int rc = allgather_host_u64(ctx, nc, scnt, all);                   // all[src * W + dst]
+    const uint64_t *all = nullptr;
+    int rc = allgather_words(ctx, nc, d_split, W + 2, all);            // all[src * (W + 2) + o] = first index of owner o's part in src's array
     if (rc) return rc;
-    std::vector<uint64_t> rcnt(W), roff(W);
+    if ((rc = peers_status(ctx, all, W + 2, status))) return rc;
+    std::vector<uint64_t> scnt(W), soff(W), rcnt(W), roff(W);
     uint64_t rtot = 0;
-    for (int p = 0; p < W; ++p) { rcnt[p] = all[(size_t)p * W + me]; roff[p] = rtot; rtot += rcnt[p]; }
-    CU(ctx->xk_a.reserve((rtot + 1) * 8)); CU(ctx->xk_b.reserve((rtot + 1) * 8));
-    NC(nc->GroupStart());
-    rc = alltoallv(ctx, nc, ctx->spec_a.p, scnt, soff, ctx->xk_a.p, rcnt, roff, 8);
-    if (rc) return rc;
-    NC(nc->GroupEnd());
-    // owner: what arrived goes into an order-preserving table over this owner's hash range (duplicates collapse), the probe
-    // clusters are sorted in place and the occupied slots are written out in order: the owner's sorted distinct slice
-    uint64_t n_own = 0;
-    if (rtot) {
+    for (int p = 0; p < W; ++p) {
+        const uint64_t *sp = all + (size_t)p * (W + 2), *mine = all + (size_t)me * (W + 2);
+        scnt[p] = mine[p + 1] - mine[p]; soff[p] = mine[p];
+        rcnt[p] = sp[me + 1] - sp[me]; roff[p] = rtot; rtot += rcnt[p];
+    }
+    // from here on a failure of this rank alone would leave the peers inside a collective: the communicator is aborted then
+    struct AbortGuard { phi_gpu_index_ctx *c; bool armed; ~AbortGuard() { if (armed) comm_release(c, true); } } guard = {ctx, true};
+    CU(ctx->xk_a.reserve((rtot + 1) * 8)); CU(ctx->xk_b.reserve((rtot + 2) * 8));
+    for (uint64_t cap_mul = 2;; cap_mul <<= 1) {
+        NC(nc->GroupStart());
+        for (int p = 0; p < W; ++p) {
+            if (p == me) continue;
+            if (scnt[p]) NC(nc->Send(ctx->spec_a.as<uint64_t>() + soff[p], scnt[p], ncclUint64, p, comm, ctx->st));
+            if (rcnt[p]) NC(nc->Recv(ctx->xk_a.as<uint64_t>() + roff[p], rcnt[p], ncclUint64, p, comm, ctx->st));
+        }
+        NC(nc->GroupEnd());
+        if (scnt[me]) CU(cudaMemcpyAsync(ctx->xk_a.as<uint64_t>() + roff[me], ctx->spec_a.as<uint64_t>() + soff[me], scnt[me] * 8, cudaMemcpyDeviceToDevice, ctx->st));
+        // owner: what arrived goes into an order-preserving table over this owner's hash range (duplicates collapse), the probe
+        // clusters are sorted in place and the occupied slots are written out in order: the owner's sorted distinct slice
         unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
-        const uint64_t base = bounds[me];
-        const unsigned __int128 range = (me + 1 < W ? (unsigned __int128)bounds[me + 1] : ((unsigned __int128)1 << 64)) - base;
-        uint64_t cap = 1024; while (cap < 2 * rtot) cap <<= 1;
-        for (;;) {
+        const uint32_t *d_total = nullptr;
+        if (rtot) {
+            const uint64_t base = (uint64_t)((((unsigned __int128)me << 64) + W - 1) / W);
+            const unsigned __int128 range = (me + 1 < W ? (unsigned __int128)(uint64_t)((((unsigned __int128)(me + 1) << 64) + W - 1) / W) : ((unsigned __int128)1 << 64)) - base;
+            uint64_t cap = 1024; while (cap < cap_mul * rtot) cap <<= 1;
             const uint64_t limit = cap + TABLE_PAD;
             const uint64_t mult = (uint64_t)((((unsigned __int128)cap) << 64) / range);    // home = umulhi(key - base, mult) < cap
             const size_t nb = table_blocks(limit);
@@ -623,37 +654,45 @@ static int exchange_spectrum(phi_gpu_index_ctx *ctx, uint64_t n_local, uint64_t 
             CU(table_sort_and_count(ctx->table.as<uint64_t>(), limit, ctx->tblk.as<uint32_t>(), ctx->st, &ctx->launches));
             CU(cudaMemsetAsync(ctx->tblk.as<uint32_t>() + nb, 0, 4, ctx->st));
             CU(scan_u32_inplace(ctx->tblk.as<uint32_t>(), nb + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
-            CU(cudaMemcpyAsync(ctx->h_tot, ctx->tblk.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, ctx->st));
-            CU(read_counters(ctx));
-            if (!ctx->h_ctr[CTR_OVERFLOW]) { n_own = *ctx->h_tot; CU(table_write_ordered(ctx->table.as<uint64_t>(), limit, ctx->tblk.as<uint32_t>(), ctx->xk_b.as<uint64_t>(), ctx->st, &ctx->launches)); break; }
-            cap <<= 1;
+            CU(table_write_ordered(ctx->table.as<uint64_t>(), limit, ctx->tblk.as<uint32_t>(), ctx->xk_b.as<uint64_t>(), ctx->st, &ctx->launches));
+            d_total = ctx->tblk.as<uint32_t>() + nb;
         }
-        if (ctx->h_ctr[CTR_HAS_MAXKEY]) { CU(fill_u64(ctx->xk_b.as<uint64_t>() + n_own, 1, TABLE_EMPTY, ctx->st, &ctx->launches)); ++n_own; }
+        owner_tail_kernel<<<1, 1, 0, ctx->st>>>(d_total, d_ctr, 0, ctx->xk_b.as<uint64_t>(), d_tail);
+        CU(cudaGetLastError()); ctx->launches++;
+        rc = allgather_words(ctx, nc, d_tail, 3, all);                  // (distinct keys of the owner, overflow, status) of every owner
+        if (rc) return rc;
+        bool overflow = false;
+        for (int p = 0; p < W; ++p) overflow |= all[(size_t)p * 3 + 1] != 0;
+        if (!overflow) break;                                           // (every rank sees the same flags and repeats, or not, together)
+        if (cap_mul > 64) return ctx->fail(PHI_ERR_CUDA, "owner-side spectrum table overflowed repeatedly (internal error)");
     }
-    std::vector<uint64_t> mine(1, n_own), owns;
-    rc = allgather_host_u64(ctx, nc, mine, owns);
-    if (rc) return rc;
     ctx->own_off.assign(W + 1, 0);
-    for (int o = 0; o < W; ++o) ctx->own_off[o + 1] = ctx->own_off[o] + owns[o];
+    for (int o = 0; o < W; ++o) ctx->own_off[o + 1] = ctx->own_off[o] + all[(size_t)o * 3];
     n_spec = ctx->own_off[W];
     CU(ctx->spec_a.reserve((n_spec + 1) * 8));
+    // every owner's sorted slice to everybody: concatenation of range slices is the sorted spectrum
+    const uint64_t mine_n = ctx->own_off[me + 1] - ctx->own_off[me];
     NC(nc->GroupStart());
-    for (int o = 0; o < W; ++o) {
-        if (!owns[o]) continue;
-        uint64_t *dst = ctx->spec_a.as<uint64_t>() + ctx->own_off[o];
-        NC(nc->Broadcast(o == me ? (const void *)ctx->xk_b.p : (const void *)dst, dst, owns[o], ncclUint64, o, (ncclComm_t)ctx->comm, ctx->st));
+    for (int p = 0; p < W; ++p) {
+        if (p == me) continue;
+        if (mine_n) NC(nc->Send(ctx->xk_b.p, mine_n, ncclUint64, p, comm, ctx->st));
+        const uint64_t cnt = ctx->own_off[p + 1] - ctx->own_off[p];
+        if (cnt) NC(nc->Recv(ctx->spec_a.as<uint64_t>() + ctx->own_off[p], cnt, ncclUint64, p, comm, ctx->st));
     }
     NC(nc->GroupEnd());
+    if (mine_n) CU(cudaMemcpyAsync(ctx->spec_a.as<uint64_t>() + ctx->own_off[me], ctx->xk_b.p, mine_n * 8, cudaMemcpyDeviceToDevice, ctx->st));
+    guard.armed = false;
     return PHI_OK;
 }
 
-// ---- record routing (hits or group summaries) to the owner of their rank
+// ---- record routing (group summaries) to the owner of their rank.  A record is (rank, count, vertex list).  Every (src -> dst)
+// pair moves ONE packed byte stream:  voff u64[n] | rank u32[n] | cnt u32[n] | nv u8[n] (padded to 8) | vtx i32[nvtx]
 constexpr int ROUTE_ITEMS = 8;                      // records per thread: 2048 per block -> few global atomics
 struct RouteIn {
-    const uint32_t *rank, *walk, *pos; const uint64_t *voff; const uint8_t *nv; const int32_t *vtx;
+    const uint32_t *rank, *cnt; const uint64_t *voff; const uint8_t *nv; const int32_t *vtx;
     uint64_t n;
-    const uint8_t *drop;                            // optional: records whose rank is flagged are not routed
 };
+__host__ __device__ inline uint64_t route_seg_bytes(uint64_t n, uint64_t nvtx) { return 16 * n + ((n + 7) & ~7ull) + ((4 * nvtx + 7) & ~7ull); }
 __device__ __forceinline__ int owner_of_rank(const uint64_t *own_off, int world, uint64_t r)
 {
     int o = 0;
@@ -670,7 +709,7 @@ __global__ void __launch_bounds__(256) route_count_kernel(RouteIn I, const uint6
     for (int it = 0; it < ROUTE_ITEMS; ++it) {
         uint64_t i = base + it * 256 + threadIdx.x;
         int o = -1; uint32_t nv = 0;
-        if (i < I.n) { uint32_t r = I.rank[i]; if (!I.drop || !I.drop[r]) { o = owner_of_rank(own_off, world, r); nv = I.nv[i]; } }
+        if (i < I.n) { o = owner_of_rank(own_off, world, I.rank[i]); nv = I.nv[i]; }
         // warp-aggregated: one shared-memory atomic per distinct owner per warp
         uint32_t peers = __match_any_sync(0xFFFFFFFFu, o);
         if (o >= 0) { atomicAdd(&sh[world + o], (unsigned long long)nv); if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[o], (unsigned long long)__popc(peers)); }
@@ -679,12 +718,15 @@ __global__ void __launch_bounds__(256) route_count_kernel(RouteIn I, const uint6
     for (int j = threadIdx.x; j < 2 * world; j += blockDim.x) if (sh[j]) atomicAdd(&cnt[j], sh[j]);
 }
 
-struct RouteOut {
-    unsigned long long *cursor;                   // [2*world] running (records, vertices) per owner, initialised with the segment starts
-    const uint64_t *vtx_seg_start;                // [world] start of each owner's vertex segment in s_vtx
-    uint32_t *s_rank, *s_walk, *s_pos; uint64_t *s_voff; uint8_t *s_nv; int32_t *s_vtx;
-};
-__global__ void __launch_bounds__(256) route_scatter_kernel(RouteIn I, RouteOut O, const uint64_t *own_off, int world)
+struct RouteSeg { uint64_t byte_off, n, nvtx; };    // one (src -> dst) segment inside a packed buffer
+struct RouteLayout { RouteSeg seg[64]; };
+__device__ __forceinline__ void route_seg_ptrs(unsigned char *buf, const RouteSeg &s, uint64_t *&voff, uint32_t *&rank, uint32_t *&cnt, uint8_t *&nv, int32_t *&vtx)
+{
+    unsigned char *p = buf + s.byte_off;
+    voff = (uint64_t *)p; rank = (uint32_t *)(p + 8 * s.n); cnt = rank + s.n; nv = (uint8_t *)(cnt + s.n); vtx = (int32_t *)(nv + ((s.n + 7) & ~7ull));
+}
+__global__ void __launch_bounds__(256) route_pack_kernel(RouteIn I, RouteLayout L, unsigned char *buf, unsigned long long *cursor /* [2*world], zeroed */,
+                                                         const uint64_t *own_off, int world)
 {
     __shared__ unsigned long long sh_cnt[128], sh_base[128];
     for (int i = threadIdx.x; i < 2 * world; i += blockDim.x) sh_cnt[i] = 0;
@@ -696,101 +738,109 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(RouteIn I, RouteOut 
         uint64_t i = base + it * 256 + threadIdx.x;
         own[it] = -1; lh[it] = lv[it] = 0;
         if (i < I.n) {
-            uint32_t r = I.rank[i];
-            if (!I.drop || !I.drop[r]) {
-                int o = own[it] = owner_of_rank(own_off, world, r);
-                lh[it] = (uint32_t)atomicAdd(&sh_cnt[o], 1ull); lv[it] = (uint32_t)atomicAdd(&sh_cnt[world + o], (unsigned long long)I.nv[i]);
-            }
+            int o = own[it] = owner_of_rank(own_off, world, I.rank[i]);
+            lh[it] = (uint32_t)atomicAdd(&sh_cnt[o], 1ull); lv[it] = (uint32_t)atomicAdd(&sh_cnt[world + o], (unsigned long long)I.nv[i]);
         }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < 2 * world; j += blockDim.x) sh_base[j] = sh_cnt[j] ? atomicAdd(&O.cursor[j], sh_cnt[j]) : 0ull;
+    for (int j = threadIdx.x; j < 2 * world; j += blockDim.x) sh_base[j] = sh_cnt[j] ? atomicAdd(&cursor[j], sh_cnt[j]) : 0ull;
     __syncthreads();
     #pragma unroll
     for (int it = 0; it < ROUTE_ITEMS; ++it) {
         if (own[it] < 0) continue;
         const uint64_t i = base + it * 256 + threadIdx.x;
         const int o = own[it];
+        uint64_t *s_voff; uint32_t *s_rank, *s_cnt; uint8_t *s_nv; int32_t *s_vtx;
+        route_seg_ptrs(buf, L.seg[o], s_voff, s_rank, s_cnt, s_nv, s_vtx);
         const unsigned long long dh = sh_base[o] + lh[it], dv = sh_base[world + o] + lv[it];
         const uint32_t nv = I.nv[i];
-        O.s_rank[dh] = I.rank[i]; O.s_walk[dh] = I.walk[i]; O.s_pos[dh] = I.pos[i]; O.s_nv[dh] = (uint8_t)nv;
-        O.s_voff[dh] = dv - O.vtx_seg_start[o];                       // relative to the (src -> owner) vertex segment
+        s_rank[dh] = I.rank[i]; s_cnt[dh] = I.cnt[i]; s_nv[dh] = (uint8_t)nv; s_voff[dh] = dv;   // vertex offset inside the segment
         const int32_t *src = I.vtx + I.voff[i];
-        for (uint32_t q = 0; q < nv; ++q) O.s_vtx[dv + q] = src[q];
+        for (uint32_t q = 0; q < nv; ++q) s_vtx[dv + q] = src[q];
     }
 }
-__global__ void rebase_voff_kernel(uint64_t *voff, uint64_t n, const uint64_t *hit_seg_off, const uint64_t *vtx_seg_off, int world)
+// received segments -> flat record arrays (the owner-side group table indexes records, not segments)
+__global__ void __launch_bounds__(256) route_unpack_kernel(RouteLayout L, int world, unsigned char *buf, const uint64_t rec0[65], const uint64_t vtx0[65],
+                                                           uint32_t *r_rank, uint32_t *r_cnt, uint64_t *r_voff, uint8_t *r_nv, int32_t *r_vtx)
 {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int p = 0;
-    while (p + 1 < world && hit_seg_off[p + 1] <= i) ++p;
-    voff[i] += vtx_seg_off[p];
+    const int p = blockIdx.y;
+    const RouteSeg s = L.seg[p];
+    uint64_t *s_voff; uint32_t *s_rank, *s_cnt; uint8_t *s_nv; int32_t *s_vtx;
+    route_seg_ptrs(buf, s, s_voff, s_rank, s_cnt, s_nv, s_vtx);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint64_t i = t0; i < s.n; i += stride) {
+        const uint64_t d = rec0[p] + i;
+        r_rank[d] = s_rank[i]; r_cnt[d] = s_cnt[i]; r_nv[d] = s_nv[i]; r_voff[d] = vtx0[p] + s_voff[i];
+    }
+    for (uint64_t i = t0; i < s.nvtx; i += stride) r_vtx[vtx0[p] + i] = s_vtx[i];
 }
 
-// Route the records of `I` to the owners of their ranks.  Received records land in ctx->r_* (rh records, rv vertices).
-static int exchange_records(phi_gpu_index_ctx *ctx, const RouteIn &I, uint64_t &rh, uint64_t &rv)
+// Route the records of `I` to the owners of their ranks.  Received records land in ctx->r_rank / r_walk (= count) / r_voff / r_nv /
+// r_vtx (rh records, rv vertices).  status: error code of an earlier stage of this rank (all ranks stop together).
+static int exchange_records(phi_gpu_index_ctx *ctx, const RouteIn &I, uint64_t &rh, uint64_t &rv, int status)
 {
     std::string err; NcclApi *nc = nccl_api(err);
     if (!nc || !ctx->comm) return ctx->fail(PHI_ERR_COMM, "communicator not initialised");
     const int W = ctx->world, me = ctx->rank;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
     const uint64_t n = I.n;
     const unsigned nblk = (unsigned)((n + 256 * ROUTE_ITEMS - 1) / (256 * ROUTE_ITEMS));
     CU(ctx->xcnt.reserve(8192));
-    uint64_t *d_own = ctx->xcnt.as<uint64_t>();                        // [W+1] own_off | [2W] counts | [2W] cursors | [W] vtx seg start | recv seg offs
-    unsigned long long *d_cnt = (unsigned long long *)(d_own + 65), *d_cur = d_cnt + 128;
-    uint64_t *d_vseg = (uint64_t *)(d_cur + 128), *d_rh = d_vseg + 64, *d_rv = d_rh + 65;
-    CU(cudaMemcpyAsync(d_own, ctx->own_off.data(), (W + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaMemsetAsync(d_cnt, 0, 2 * W * 8, ctx->st));
+    uint64_t *d_own = ctx->xcnt.as<uint64_t>() + 128;                   // [65] own_off | [2W + 1] counts + status | [2W] cursors | [65] rec0 | [65] vtx0
+    unsigned long long *d_cnt = (unsigned long long *)(d_own + 65), *d_cur = d_cnt + 130;
+    uint64_t *d_rec0 = (uint64_t *)(d_cur + 128), *d_vtx0 = d_rec0 + 65;
+    // own_off, zeroed counts and the status word in one small copy from pinned memory
+    uint64_t *hp = ctx->h_route;
+    for (int o = 0; o <= W; ++o) hp[o] = ctx->own_off[o];
+    for (int j = 0; j < 2 * W; ++j) hp[65 + j] = 0;
+    hp[65 + 2 * W] = (uint64_t)status;
+    CU(cudaMemcpyAsync(d_own, hp, (65 + 2 * W + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemsetAsync(d_cur, 0, 2 * W * 8, ctx->st));
     if (n) {
         route_count_kernel<<<nblk, 256, 0, ctx->st>>>(I, d_own, W, d_cnt);
         CU(cudaGetLastError()); ctx->launches++;
     }
-    std::vector<uint64_t> cnt(2 * W, 0), all;
-    CU(cudaMemcpyAsync(cnt.data(), d_cnt, 2 * W * 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    std::vector<uint64_t> sh_cnt(W), sh_off(W), sv_cnt(W), sv_off(W), cur(2 * W);
-    uint64_t th = 0, tv = 0;
-    for (int p = 0; p < W; ++p) { sh_cnt[p] = cnt[p]; sv_cnt[p] = cnt[W + p]; sh_off[p] = th; sv_off[p] = tv; th += cnt[p]; tv += cnt[W + p]; cur[p] = sh_off[p]; cur[W + p] = sv_off[p]; }
-    CU(ctx->s_rank.reserve(th * 4 + 4)); CU(ctx->s_walk.reserve(th * 4 + 4)); CU(ctx->s_pos.reserve(th * 4 + 4));
-    CU(ctx->s_voff.reserve(th * 8 + 8)); CU(ctx->s_nv.reserve(th + 4)); CU(ctx->s_vtx.reserve(tv * 4 + 4));
-    CU(cudaMemcpyAsync(d_cur, cur.data(), 2 * W * 8, cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaMemcpyAsync(d_vseg, sv_off.data(), W * 8, cudaMemcpyHostToDevice, ctx->st));
-    if (n) {
-        RouteOut O;
-        O.cursor = d_cur; O.vtx_seg_start = d_vseg;
-        O.s_rank = ctx->s_rank.as<uint32_t>(); O.s_walk = ctx->s_walk.as<uint32_t>(); O.s_pos = ctx->s_pos.as<uint32_t>();
-        O.s_voff = ctx->s_voff.as<uint64_t>(); O.s_nv = ctx->s_nv.as<uint8_t>(); O.s_vtx = ctx->s_vtx.as<int32_t>();
-        route_scatter_kernel<<<nblk, 256, 0, ctx->st>>>(I, O, d_own, W);
-        CU(cudaGetLastError()); ctx->launches++;
-    }
-    int rc = allgather_host_u64(ctx, nc, cnt, all);                     // all[src * 2W + {dst, W + dst}]
+    const uint64_t *all = nullptr;
+    const size_t NWORDS = 2 * W + 1;
+    int rc = allgather_words(ctx, nc, (const uint64_t *)d_cnt, NWORDS, all);   // all[src * NWORDS + {dst, W + dst}] = records, vertices
     if (rc) return rc;
-    std::vector<uint64_t> rh_cnt(W), rh_off(W + 1, 0), rv_cnt(W), rv_off(W + 1, 0);
+    if ((rc = peers_status(ctx, all, NWORDS, status))) return rc;
+    RouteLayout SL, RL; memset(&SL, 0, sizeof SL); memset(&RL, 0, sizeof RL);
+    uint64_t sbytes = 0, rbytes = 0; rh = rv = 0;
+    uint64_t *h_rec0 = hp + 256, *h_vtx0 = hp + 256 + 65;
     for (int p = 0; p < W; ++p) {
-        rh_cnt[p] = all[(size_t)p * 2 * W + me]; rv_cnt[p] = all[(size_t)p * 2 * W + W + me];
-        rh_off[p + 1] = rh_off[p] + rh_cnt[p]; rv_off[p + 1] = rv_off[p] + rv_cnt[p];
+        const uint64_t *mine = all + (size_t)me * NWORDS, *src = all + (size_t)p * NWORDS;
+        SL.seg[p] = {sbytes, mine[p], mine[W + p]}; sbytes += route_seg_bytes(mine[p], mine[W + p]);
+        RL.seg[p] = {rbytes, src[me], src[W + me]}; rbytes += route_seg_bytes(src[me], src[W + me]);
+        h_rec0[p] = rh; h_vtx0[p] = rv; rh += src[me]; rv += src[W + me];
     }
-    rh = rh_off[W]; rv = rv_off[W];
     if (rh >= (1ull << 32)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-1 records routed to one GPU");
-    CU(ctx->r_rank.reserve(rh * 4 + 4)); CU(ctx->r_walk.reserve(rh * 4 + 4)); CU(ctx->r_pos.reserve(rh * 4 + 4));
-    CU(ctx->r_voff.reserve(rh * 8 + 8)); CU(ctx->r_nv.reserve(rh + 4)); CU(ctx->r_vtx.reserve(rv * 4 + 4));
-    NC(nc->GroupStart());
-    rc = alltoallv(ctx, nc, ctx->s_rank.p, sh_cnt, sh_off, ctx->r_rank.p, rh_cnt, rh_off, 4);
-    if (!rc) rc = alltoallv(ctx, nc, ctx->s_walk.p, sh_cnt, sh_off, ctx->r_walk.p, rh_cnt, rh_off, 4);
-    if (!rc) rc = alltoallv(ctx, nc, ctx->s_pos.p, sh_cnt, sh_off, ctx->r_pos.p, rh_cnt, rh_off, 4);
-    if (!rc) rc = alltoallv(ctx, nc, ctx->s_voff.p, sh_cnt, sh_off, ctx->r_voff.p, rh_cnt, rh_off, 8);
-    if (!rc) rc = alltoallv(ctx, nc, ctx->s_nv.p, sh_cnt, sh_off, ctx->r_nv.p, rh_cnt, rh_off, 1);
-    if (!rc) rc = alltoallv(ctx, nc, ctx->s_vtx.p, sv_cnt, sv_off, ctx->r_vtx.p, rv_cnt, rv_off, 4);
-    if (rc) return rc;
-    NC(nc->GroupEnd());
-    if (rh) {
-        CU(cudaMemcpyAsync(d_rh, rh_off.data(), (W + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
-        CU(cudaMemcpyAsync(d_rv, rv_off.data(), (W + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
-        rebase_voff_kernel<<<(unsigned)((rh + 255) / 256), 256, 0, ctx->st>>>(ctx->r_voff.as<uint64_t>(), rh, d_rh, d_rv, W);
+    struct AbortGuard { phi_gpu_index_ctx *c; bool armed; ~AbortGuard() { if (armed) comm_release(c, true); } } guard = {ctx, true};
+    CU(ctx->s_vtx.reserve(sbytes + 64)); CU(ctx->s_voff.reserve(rbytes + 64));           // packed send / receive buffers
+    CU(ctx->r_rank.reserve(rh * 4 + 4)); CU(ctx->r_walk.reserve(rh * 4 + 4)); CU(ctx->r_voff.reserve(rh * 8 + 8)); CU(ctx->r_nv.reserve(rh + 4)); CU(ctx->r_vtx.reserve(rv * 4 + 4));
+    unsigned char *sbuf = ctx->s_vtx.as<unsigned char>(), *rbuf = ctx->s_voff.as<unsigned char>();
+    if (n) {
+        route_pack_kernel<<<nblk, 256, 0, ctx->st>>>(I, SL, sbuf, d_cur, d_own, W);
         CU(cudaGetLastError()); ctx->launches++;
     }
-    CU(cudaStreamSynchronize(ctx->st));                                  // host vectors above were the source of async copies
+    NC(nc->GroupStart());
+    for (int p = 0; p < W; ++p) {
+        if (p == me) continue;
+        const uint64_t sb = route_seg_bytes(SL.seg[p].n, SL.seg[p].nvtx), rb = route_seg_bytes(RL.seg[p].n, RL.seg[p].nvtx);
+        if (SL.seg[p].n) NC(nc->Send(sbuf + SL.seg[p].byte_off, sb, ncclUint8, p, comm, ctx->st));
+        if (RL.seg[p].n) NC(nc->Recv(rbuf + RL.seg[p].byte_off, rb, ncclUint8, p, comm, ctx->st));
+    }
+    NC(nc->GroupEnd());
+    if (SL.seg[me].n) CU(cudaMemcpyAsync(rbuf + RL.seg[me].byte_off, sbuf + SL.seg[me].byte_off, route_seg_bytes(SL.seg[me].n, SL.seg[me].nvtx), cudaMemcpyDeviceToDevice, ctx->st));
+    if (rh) {
+        CU(cudaMemcpyAsync(d_rec0, h_rec0, 130 * 8, cudaMemcpyHostToDevice, ctx->st));   // rec0 | vtx0 (pinned: stays valid until the next exchange)
+        uint64_t big = 0; for (int p = 0; p < W; ++p) big = std::max(big, std::max(RL.seg[p].n, RL.seg[p].nvtx));
+        dim3 grid((unsigned)std::min<uint64_t>((big + 255) / 256, 4096), (unsigned)W);
+        route_unpack_kernel<<<grid, 256, 0, ctx->st>>>(RL, W, rbuf, d_rec0, d_vtx0, ctx->r_rank.as<uint32_t>(), ctx->r_walk.as<uint32_t>(), ctx->r_voff.as<uint64_t>(),
+                                                      ctx->r_nv.as<uint8_t>(), ctx->r_vtx.as<int32_t>());
+        CU(cudaGetLastError()); ctx->launches++;
+    }
+    guard.armed = false;
     return PHI_OK;
 }
 
@@ -863,10 +913,9 @@ static int stage_reads_begin(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &r
     return reads_sketch_launch(ctx, k, w, rs);
 }
 
-static int stage_reads_finish(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &rs, RunOut &o, int &dbits)
+static int stage_reads_local(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &rs, RunOut &o, uint64_t &n_spec)
 {
-    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
-    uint64_t n_spec = 0;
+    n_spec = 0;
     if (rs.n_tiles) {
         for (;;) {
             CU(read_counters(ctx));
@@ -892,9 +941,19 @@ static int stage_reads_finish(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &
         CU(cudaEventRecord(ctx->ev[EV_READS], ctx->st));
         CU(ctx->spec_a.reserve(8));
     }
-    if (ctx->world > 1) {                                                 // every rank takes part, also with zero local reads
+    return PHI_OK;
+}
+
+// status (several GPUs only): error code of an earlier stage of this rank; it travels with the first small collective of the
+// exchange so that all ranks stop together.
+static int stage_reads_finish(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &rs, RunOut &o, int &dbits, int status)
+{
+    uint64_t n_spec = 0;
+    int rc_local = status ? status : stage_reads_local(ctx, k, w, rs, o, n_spec);
+    if (rc_local && ctx->world == 1) return rc_local;
+    if (ctx->world > 1) {                                                 // every rank takes part, also with zero local reads or a failure to report
         CU(cudaEventRecord(ctx->ev[EV_XS0], ctx->st));
-        int rc = exchange_spectrum(ctx, n_spec, n_spec);
+        int rc = exchange_spectrum(ctx, rc_local ? 0 : n_spec, n_spec, rc_local);
         if (rc) return rc;
         CU(cudaEventRecord(ctx->ev[EV_XS1], ctx->st));
         if (n_spec >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^31-1 distinct read minimizers (count_sp_r is int32 in the reference)");
@@ -994,7 +1053,8 @@ static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, Fi
     // distinct (rank, vertex list) groups are usually fewer than records, so start small and grow on overflow
     uint64_t gcap = 1024; while (gcap < n / 2) gcap <<= 1;
     uint64_t &hint = owner_side ? ctx->gcap_hint2 : ctx->gcap_hint;
-    if (hint > gcap) gcap = hint;
+    if (owner_side) { gcap = 1024; while (gcap < 2 * n) gcap <<= 1; }     // at most n groups: the 80 % load limit is out of reach, no host wait needed
+    else if (hint > gcap) gcap = hint;
     DevBuf &slotb = owner_side ? ctx->hit_slot2 : ctx->hit_slot, &repb = owner_side ? ctx->g_rep2 : ctx->g_rep, &cntb = owner_side ? ctx->g_cnt2 : ctx->g_cnt;
     CU(slotb.reserve(n * 4 + 4));
     W.hit_slot = slotb.as<uint32_t>();
@@ -1008,6 +1068,7 @@ static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, Fi
         CU(cudaMemsetAsync(d_ctr + CTR_GROUPS, 0, 2 * 8, ctx->st));
         W.g_rep = repb.as<uint32_t>(); W.g_cnt = cntb.as<uint32_t>(); W.g_cap = gcap;
         CU(filter_count_groups(A, W, ctx->st, &ctx->launches));
+        if (owner_side) break;
         CU(read_counters(ctx));
         if (!ctx->h_ctr[CTR_GROUP_OVERFLOW]) break;
         gcap <<= 2;
@@ -1152,8 +1213,16 @@ __global__ void summary_emit_kernel(FilterArgs A, const uint32_t *g_rep, const u
     m_rank[j] = A.hit_rank[i]; m_cnt[j] = g_cnt[slot]; m_voff[j] = A.hit_voff[i]; m_nv[j] = A.hit_nv[i];
 }
 
-static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walks_global, float threshold, RunOut &o)
+// status (several GPUs only): error code of the walk stage of this rank; it travels with the small collective of the record
+// exchange so that all ranks stop together.
+static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walks_global, float threshold, RunOut &o, int status)
 {
+    if (status && ctx->world > 1 && mode == WALK_MODE_PROBE) {
+        RouteIn none; memset(&none, 0, sizeof none);
+        uint64_t a = 0, b = 0;
+        int rc = exchange_records(ctx, none, a, b, status);
+        return rc ? rc : status;
+    }
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
     CU(ctx->apw.reserve(((size_t)n_walks_global + 1) * 8));
     CU(cudaMemsetAsync(ctx->apw.p, 0, ((size_t)n_walks_global + 1) * 8, ctx->st));
@@ -1194,10 +1263,10 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walk
     } else {
         std::string err; NcclApi *nc = nccl_api(err);
         if (!nc || !ctx->comm) return ctx->fail(PHI_ERR_COMM, "communicator not initialised");
-        const int Wn = ctx->world;
         CU(cudaEventRecord(ctx->ev[EV_XH0], ctx->st));
         uint64_t n_sum = 0;
-        if (n) {
+        auto summaries = [&]() -> int {                                       // local group table -> one summary per local group
+            if (!n) return PHI_OK;
             int rc = count_groups_adaptive(ctx, A, W, nullptr, ctx->c_ninst.as<uint32_t>(), false);
             if (rc) return rc;
             CU(ctx->flags.reserve(n * 4 + 4)); CU(ctx->flags64.reserve((n + 1) * 8));
@@ -1210,28 +1279,26 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walk
             summary_emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(A, W.g_rep, W.g_cnt, W.hit_slot, ctx->flags64.as<uint64_t>(),
                                                                                  ctx->m_rank.as<uint32_t>(), ctx->m_cnt.as<uint32_t>(), ctx->m_voff.as<uint64_t>(), ctx->m_nv.as<uint8_t>());
             CU(cudaGetLastError()); ctx->launches++;
-        }
+            return PHI_OK;
+        };
+        const int rc_local = summaries();
         RouteIn I;
-        I.rank = ctx->m_rank.as<uint32_t>(); I.walk = ctx->m_cnt.as<uint32_t>(); I.pos = ctx->m_cnt.as<uint32_t>(); I.voff = ctx->m_voff.as<uint64_t>();
-        I.nv = ctx->m_nv.as<uint8_t>(); I.vtx = ctx->vtx_pool.as<int32_t>(); I.n = n_sum; I.drop = nullptr;
+        I.rank = ctx->m_rank.as<uint32_t>(); I.cnt = ctx->m_cnt.as<uint32_t>(); I.voff = ctx->m_voff.as<uint64_t>();
+        I.nv = ctx->m_nv.as<uint8_t>(); I.vtx = ctx->vtx_pool.as<int32_t>(); I.n = rc_local ? 0 : n_sum;
         CU(cudaEventRecord(ctx->ev[EV_XH1], ctx->st));
         uint64_t rs = 0, rsv = 0;
-        int rc = exchange_records(ctx, I, rs, rsv);
+        int rc = exchange_records(ctx, I, rs, rsv, rc_local);
         if (rc) return rc;
         if (rs) {                                                             // owner: add the partial counts up, apply the threshold
-            FilterArgs B = filter_args(ctx, rs, ctx->r_rank, ctx->r_walk, ctx->r_pos, ctx->r_voff, ctx->r_nv, ctx->r_vtx, o.n_spec, threshold, n_walks_global);
+            FilterArgs B = filter_args(ctx, rs, ctx->r_rank, ctx->r_walk, ctx->r_walk, ctx->r_voff, ctx->r_nv, ctx->r_vtx, o.n_spec, threshold, n_walks_global);
             FilterWork WB; memset(&WB, 0, sizeof(WB));
             WB.rank_drop = ctx->rank_drop.as<uint8_t>(); WB.ctr = d_ctr;
             WB.mark_inline = 1;                                                // drops (and counts) the ranks of this owner's range
             rc = count_groups_adaptive(ctx, B, WB, ctx->r_walk.as<uint32_t>(), nullptr, true);
-            if (rc) return rc;
+            if (rc) { comm_release(ctx, true); return rc; }
         }
-        NC(nc->GroupStart());                                                   // share the drop flags: owner o holds the truth for its rank range
-        for (int q = 0; q < Wn; ++q) {
-            const uint64_t lo = ctx->own_off[q], cnt = ctx->own_off[q + 1] - lo;
-            if (cnt) NC(nc->Broadcast(ctx->rank_drop.as<uint8_t>() + lo, ctx->rank_drop.as<uint8_t>() + lo, cnt, ncclUint8, q, (ncclComm_t)ctx->comm, ctx->st));
-        }
-        NC(nc->GroupEnd());
+        // share the drop flags: every owner marked ranks of its own range only, so the byte-wise maximum over the GPUs is the truth
+        if (o.n_spec) NC(nc->AllReduce(ctx->rank_drop.p, ctx->rank_drop.p, (size_t)o.n_spec, ncclUint8, ncclMax, (ncclComm_t)ctx->comm, ctx->st));
         CU(cudaEventRecord(ctx->ev[EV_XH2], ctx->st));
         if (!n) { CU(read_counters(ctx)); o.n_filtered = (int64_t)ctx->h_ctr[CTR_FILTERED]; return PHI_OK; }
     }
@@ -1374,9 +1441,10 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     // main stream: read sketch kernel in flight ...
     int dbits = 0;
     ReadsState rs;
+    int status = PHI_OK;          // several GPUs: a stage that fails on this rank is reported through the next exchange (all ranks stop together)
     if (mode == WALK_MODE_PROBE) {
         rc = stage_reads_begin(ctx, k, w, rs);
-        if (rc) return rc;
+        if (rc) { if (ctx->world == 1) return rc; status = rc; }
     } else {
         CU(cudaEventRecord(ctx->ev[EV_RD0], ctx->st));
         CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st)); CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
@@ -1384,10 +1452,10 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     }
     // ... while the second stream prepares the graph (its host-side waits only cover that stream)
     rc = stage_graph_prep(ctx, k, w, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone);
-    if (rc) return rc;
+    if (rc) { if (ctx->world == 1 || mode != WALK_MODE_PROBE) return rc; if (!status) status = rc; }
     CU(cudaEventRecord(ctx->ev[EV_PREP], ctx->st2));
     if (mode == WALK_MODE_PROBE) {
-        rc = stage_reads_finish(ctx, k, w, rs, o, dbits);
+        rc = stage_reads_finish(ctx, k, w, rs, o, dbits, status);
         if (rc) return rc;
     }
     // the result starts to travel as soon as its parts exist: the spectrum goes out on the copy stream under the walk stage
@@ -1406,13 +1474,13 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     CU(cudaEventRecord(ctx->ev[EV_SPECTRUM], ctx->st));
     CU(cudaStreamWaitEvent(ctx->st, ctx->ev[EV_PREP], 0));               // the walk stage needs both
     rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, o);
-    if (rc) return rc;
+    if (rc) { if (ctx->world == 1 || mode != WALK_MODE_PROBE) return rc; status = rc; }
     CU(cudaEventRecord(ctx->ev[EV_WALKS], ctx->st));
 
     const uint32_t H = ctx->n_walks;
     const uint32_t HG = ctx->world > 1 ? ctx->n_walks_global : H;
 
-    rc = stage_filter(ctx, w, mode, HG, prm->threshold, o);
+    rc = stage_filter(ctx, w, mode, HG, prm->threshold, o, status);
     if (rc) return rc;
     o.path_hits = ctx->h_ctr[CTR_PATH_HITS];                               // read back by the syncs of the filter stage
     ctx->unique_hits = o.n_hits;
