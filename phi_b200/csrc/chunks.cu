@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) step_pass_kernel(const uint32_t *walk_vtx
 // decoupled look-back over one 64-bit word per tile; nothing but walk_vtx is read and nothing but step_base (and the few
 // per-chunk / per-walk values) is written.  The scanned value: bits [0,35) bases since the last walk start, [35,61) chunk
 // starts, bit 61 "a walk started" (the bases of the left operand are discarded); bits 62-63 of a tile word: 1 = aggregate, 2 = prefix.
-constexpr int FS_THREADS = 256, FS_ITEMS = 4, FS_TILE = FS_THREADS * FS_ITEMS;   // every thread owns FS_ITEMS consecutive steps
+constexpr int FS_THREADS = 256, FS_ITEMS = 8, FS_TILE = FS_THREADS * FS_ITEMS;   // every thread owns FS_ITEMS consecutive steps
 constexpr uint64_t FS_BASES = (1ull << 35) - 1, FS_CHUNKS = ((1ull << 26) - 1) << 35, FS_RESET = 1ull << 61, FS_VALUE = (1ull << 62) - 1;
 __device__ __forceinline__ uint64_t fs_comb(uint64_t a, uint64_t b)           // a, then b
 {
@@ -167,9 +167,11 @@ __global__ void __launch_bounds__(FS_THREADS, 4) fused_steps_kernel(const uint32
     // the thread's steps and their vertex records (independent gathers), the record of the step before the first one
     const uint64_t sb = s0 + (uint64_t)FS_ITEMS * threadIdx.x;
     uint32_t vtx[FS_ITEMS];
-    if (sb + FS_ITEMS <= n_steps) { const uint4 q = *(const uint4 *)(walk_vtx + sb); vtx[0] = q.x; vtx[1] = q.y; vtx[2] = q.z; vtx[3] = q.w; }
-    else { for (int j = 0; j < FS_ITEMS; ++j) vtx[j] = sb + j < n_steps ? walk_vtx[sb + j] : 0u; }
-    static_assert(FS_ITEMS == 4, "one 16-byte load per thread");
+    static_assert(FS_ITEMS % 4 == 0, "16-byte loads and stores per thread");
+    if (sb + FS_ITEMS <= n_steps) {
+        #pragma unroll
+        for (int j = 0; j < FS_ITEMS; j += 4) { const uint4 q = *(const uint4 *)(walk_vtx + sb + j); vtx[j] = q.x; vtx[j + 1] = q.y; vtx[j + 2] = q.z; vtx[j + 3] = q.w; }
+    } else { for (int j = 0; j < FS_ITEMS; ++j) vtx[j] = sb + j < n_steps ? walk_vtx[sb + j] : 0u; }
     uint4 me[FS_ITEMS];
     #pragma unroll
     for (int j = 0; j < FS_ITEMS; ++j) me[j] = vinfo_of(vinfo, n_vtx, vtx[j], ctr);
@@ -262,8 +264,10 @@ __global__ void __launch_bounds__(FS_THREADS, 4) fused_steps_kernel(const uint32
             pre = fs_comb(pre, (uint64_t)me[j].x | ((uint64_t)flag << 35) | (start ? FS_RESET : 0ull));
         }
     }
-    if (sb + FS_ITEMS <= n_steps) *(uint4 *)(step_base + sb) = make_uint4(out[0], out[1], out[2], out[3]);
-    else { for (int j = 0; j < FS_ITEMS; ++j) if (sb + j < n_steps) step_base[sb + j] = out[j]; }
+    if (sb + FS_ITEMS <= n_steps) {
+        #pragma unroll
+        for (int j = 0; j < FS_ITEMS; j += 4) *(uint4 *)(step_base + sb + j) = make_uint4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+    } else { for (int j = 0; j < FS_ITEMS; ++j) if (sb + j < n_steps) step_base[sb + j] = out[j]; }
     // the chunk count is also kept by plain counting: it guards the 26-bit field of the scanned value
     uint32_t nf = __popc(flagm);
     #pragma unroll
