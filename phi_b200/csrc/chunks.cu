@@ -320,71 +320,86 @@ __global__ void remap_walk_off_kernel(const uint64_t *walk_off, uint32_t n_walks
     out[h] = o < n_steps ? pos[o] : n_kept;
 }
 
-// ---- geometry + fingerprint, one warp per chunk
+// ---- geometry + fingerprint, 8 lanes per chunk (four chunks per warp: the chain of dependent loads of one chunk — walk, chunk
+// bounds, step bases, context search — is latency, so the more chunks in flight the better)
 // Owned windows: end positions e (start of the window's last k-mer) in [lo, hi), lo = first base of the chunk, hi = first base of
 // the next chunk clipped to the walk's last k-mer.  Context steps [L, R]: from the step under base lo - w (halo window) to the
 // step under base (next chunk start) + k - 2.
 // A chunk whose first vertex lies outside the owned coordinate range (a walk region is set: another GPU sketches it) owns nothing.
+constexpr int CK_LANES = 8;
 __global__ void __launch_bounds__(256) chunk_key_kernel(ChunkTable C, const uint32_t *walk_vtx, const uint64_t *walk_off, const uint32_t *step_base,
                                                         const uint64_t *walk_len, const uint4 *vinfo, int k, int w, unsigned long long *ctr)
 {
-    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (c >= C.n_chunks) return;
-    const uint32_t h = C.c_walk[c];
-    const uint64_t ws = walk_off[h], we = walk_off[h + 1];
-    const long long len = (long long)walk_len[h];
-    const uint64_t s0 = C.chunk_step[c], s1 = C.chunk_step[c + 1];
-    // the warp probes 32 candidate steps at a time (the context usually spans one to three steps: one round each way)
-    const long long lo = step_base[s0];
-    const long long b1 = s1 < we ? (long long)step_base[s1] : len;
-    long long hi = min(b1, len - k + 1);
-    const bool owned = vinfo[walk_vtx[s0]].w == 1u;
-    const long long kpos = (owned && len >= (long long)w + k - 1 && hi > lo) ? hi - lo : 0;   // k-mer positions of the walk that start in this chunk
-    if (len < (long long)w + k - 1 || hi <= max(lo, (long long)w - 1) || !owned) hi = lo;     // no valid window ends here
-    uint32_t L, R;
-    {   // L: going down from s0, the first step l with l == ws or step_base[l] <= lo - w
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, sub = lane & (CK_LANES - 1), grp = lane / CK_LANES;
+    const uint64_t c64 = (uint64_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / CK_LANES) + grp;
+    const bool live = c64 < C.n_chunks;                                  // lanes of a group beyond the last chunk only take part in the warp votes
+    const uint32_t c = live ? (uint32_t)c64 : 0u;
+    uint32_t h = 0; uint64_t ws = 0, we = 0, s0 = 0, s1 = 0; long long len = 0, lo = 0, b1 = 0, hi = 0, kpos = 0;
+    if (live) {
+        h = C.c_walk[c];
+        ws = walk_off[h]; we = walk_off[h + 1];
+        len = (long long)walk_len[h];
+        s0 = C.chunk_step[c]; s1 = C.chunk_step[c + 1];
+        lo = step_base[s0];
+        b1 = s1 < we ? (long long)step_base[s1] : len;
+        hi = min(b1, len - k + 1);
+        const bool owned = vinfo[walk_vtx[s0]].w == 1u;
+        kpos = (owned && len >= (long long)w + k - 1 && hi > lo) ? hi - lo : 0;   // k-mer positions of the walk that start in this chunk
+        if (len < (long long)w + k - 1 || hi <= max(lo, (long long)w - 1) || !owned) hi = lo;     // no valid window ends here
+    }
+    const uint32_t gsh = CK_LANES * grp, gmask = (1u << CK_LANES) - 1u;
+    uint32_t L = 0, R = 0;
+    {   // L: going down from s0, the first step l with l == ws or step_base[l] <= lo - w (the group probes 8 candidate steps per round)
         const long long need = lo - w;
-        uint64_t top = s0;
+        uint64_t top = s0; bool done = !live;
         for (;;) {
-            const bool in = top >= ws + (uint64_t)lane;
-            const uint64_t l = top - lane;
-            const bool stop = !in || l == ws || (long long)step_base[l] <= need;
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, stop);
-            if (b) { L = (uint32_t)(top - (__ffs(b) - 1)); break; }
-            top -= 32;
+            bool stop = false;
+            if (!done) {
+                const bool in = top >= ws + (uint64_t)sub;
+                const uint64_t l = top - sub;
+                stop = !in || l == ws || (long long)step_base[l] <= need;
+            }
+            const uint32_t b = (__ballot_sync(FULL, stop) >> gsh) & gmask;
+            if (!done) { if (b) { L = (uint32_t)(top - (__ffs(b) - 1)); done = true; } else top -= CK_LANES; }
+            if (__all_sync(FULL, done)) break;
         }
     }
     {   // R: going up from s1 - 1, the first step r with r + 1 == we or step_base[r + 1] > last
         const long long last = min(b1 + k - 2, len - 1);
-        uint64_t bot = s1 - 1;
+        uint64_t bot = s1 - 1; bool done = !live;
         for (;;) {
-            const uint64_t r = bot + lane;
-            const bool stop = r + 1 >= we || (long long)step_base[r + 1] > last;
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, stop);
-            if (b) { R = (uint32_t)(bot + (__ffs(b) - 1)); break; }
-            bot += 32;
+            bool stop = false;
+            if (!done) { const uint64_t r = bot + sub; stop = r + 1 >= we || (long long)step_base[r + 1] > last; }
+            const uint32_t b = (__ballot_sync(FULL, stop) >> gsh) & gmask;
+            if (!done) { if (b) { R = (uint32_t)(bot + (__ffs(b) - 1)); done = true; } else bot += CK_LANES; }
+            if (__all_sync(FULL, done)) break;
         }
     }
     uint64_t h1 = 0, h2 = 0;
-    if (hi > lo) {
-        for (uint32_t i = L + lane; i <= R; i += 32) {
+    if (live && hi > lo) {
+        for (uint32_t i = L + sub; i <= R; i += CK_LANES) {
             const uint64_t x = walk_vtx[i], idx = i - L;
             const uint64_t m = cmix(((x + 1) << 32 | (idx + 1)) * 0x9E3779B97F4A7C15ull);
             h1 += m;
             h2 += (uint64_t)((uint32_t)(m >> 32) * 0x85EBCA6Bu + (uint32_t)idx) * (uint64_t)((uint32_t)m | 1u);   // a second, differently weighted sum
         }
-        #pragma unroll
-        for (int d = 16; d; d >>= 1) { h1 += __shfl_xor_sync(0xFFFFFFFFu, h1, d); h2 += __shfl_xor_sync(0xFFFFFFFFu, h2, d); }
+    }
+    #pragma unroll
+    for (int d = CK_LANES / 2; d; d >>= 1) { h1 += __shfl_xor_sync(FULL, h1, d); h2 += __shfl_xor_sync(FULL, h2, d); }
+    if (live && hi > lo) {
         const uint64_t meta = ((uint64_t)(s0 - L) << 40) ^ ((uint64_t)(s1 - L) << 20) ^ (uint64_t)(R - L);
         const uint64_t span = (uint64_t)(hi - lo);
         h1 = cmix(h1 ^ cmix(meta + 0x1234567ull) ^ (span << 32)); h2 = cmix(h2 + cmix(meta ^ 0xABCDEF01ull) + span);
-    }
-    if (lane == 0) {
-        C.c_L[c] = L; C.c_R[c] = R; C.c_lo[c] = (uint32_t)lo; C.c_hi[c] = (uint32_t)hi; C.c_h1[c] = h1; C.c_h2[c] = h2;
-        if (hi > lo) atomicAdd(&ctr[CTR_ACTIVE_CHUNKS], 1ull);
-        if (kpos) atomicAdd(&ctr[CTR_PATH_POS], (unsigned long long)kpos);
-    }
+    } else { h1 = h2 = 0; }
+    // per warp: one atomic for the active chunks and one for the k-mer positions
+    const bool lead = live && sub == 0;
+    const uint32_t act = __ballot_sync(FULL, lead && hi > lo);
+    unsigned long long kp = lead ? (unsigned long long)kpos : 0ull;
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) kp += __shfl_xor_sync(FULL, kp, d);
+    if (lane == 0) { if (act) atomicAdd(&ctr[CTR_ACTIVE_CHUNKS], (unsigned long long)__popc(act)); if (kp) atomicAdd(&ctr[CTR_PATH_POS], kp); }
+    if (lead) { C.c_L[c] = L; C.c_R[c] = R; C.c_lo[c] = (uint32_t)lo; C.c_hi[c] = (uint32_t)hi; C.c_h1[c] = h1; C.c_h2[c] = h2; }
 }
 
 // ---- grouping by fingerprint: the slot ends up holding the smallest chunk id of its group
@@ -409,25 +424,28 @@ __global__ void chunk_group_kernel(ChunkTable C, uint32_t *table, uint32_t mask,
     C.c_slot[c] = slot;
 }
 
-// ---- representative of every chunk, member counts, exact verification (warp per chunk)
+// ---- representative of every chunk, member counts, exact verification (8 lanes per chunk)
 __global__ void __launch_bounds__(256) chunk_rep_kernel(ChunkTable C, const uint32_t *table, const uint32_t *walk_vtx, int dedupe, int w, unsigned long long *ctr)
 {
-    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (c >= C.n_chunks) return;
-    const bool active = C.c_hi[c] > C.c_lo[c];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, sub = lane & (CK_LANES - 1), grp = lane / CK_LANES;
+    const uint64_t c64 = (uint64_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / CK_LANES) + grp;
+    const bool live = c64 < C.n_chunks;
+    const uint32_t c = live ? (uint32_t)c64 : 0u;
+    const bool active = live && C.c_hi[c] > C.c_lo[c];
     uint32_t rep = C_NONE;
     if (active) rep = dedupe ? table[C.c_slot[c]] : c;
+    bool same = true;
     if (active && rep != c) {
         // a member must match its representative exactly: same shape, same vertex sequence (the fingerprint only proposes)
         const uint32_t L = C.c_L[c], R = C.c_R[c], Lr = C.c_L[rep], Rr = C.c_R[rep];
-        bool same = (R - L) == (Rr - Lr) && (C.chunk_step[c] - L) == (C.chunk_step[rep] - Lr) && (C.chunk_step[c + 1] - L) == (C.chunk_step[rep + 1] - Lr)
-                    && (C.c_hi[c] - C.c_lo[c]) == (C.c_hi[rep] - C.c_lo[rep]);
-        if (same) for (uint32_t i = lane; i <= R - L; i += 32) same &= walk_vtx[L + i] == walk_vtx[Lr + i];
-        same = __all_sync(0xFFFFFFFFu, same);
-        if (!same && lane == 0) ctr[CTR_DEDUPE_MISMATCH] = 1;
+        same = (R - L) == (Rr - Lr) && (C.chunk_step[c] - L) == (C.chunk_step[rep] - Lr) && (C.chunk_step[c + 1] - L) == (C.chunk_step[rep + 1] - Lr)
+               && (C.c_hi[c] - C.c_lo[c]) == (C.c_hi[rep] - C.c_lo[rep]);
+        if (same) for (uint32_t i = sub; i <= R - L; i += CK_LANES) same &= walk_vtx[L + i] == walk_vtx[Lr + i];
     }
-    if (lane == 0) {
+    const uint32_t bad = (__ballot_sync(FULL, !same) >> (CK_LANES * grp)) & ((1u << CK_LANES) - 1u);
+    if (live && sub == 0) {
+        if (bad) ctr[CTR_DEDUPE_MISMATCH] = 1;
         C.c_rep[c] = rep;
         if (active) atomicAdd(&C.c_ninst[rep], 1u);
         const uint32_t T = (uint32_t)tile_cap(w, WALK_TILE_THREADS);
@@ -570,21 +588,26 @@ cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, u
 
 cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo, uint32_t n_vtx,
                              unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base, uint32_t *chunk_step, uint32_t *c_walk,
-                             uint64_t *walk_len, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
+                             uint64_t *walk_len, unsigned long long *ctr, cudaStream_t st, uint64_t *launches, uint64_t tile_first, uint64_t tile_last)
 {
     if (!n_steps) return cudaSuccess;
     const uint64_t nt = walk_steps_fused_tiles(n_steps);
-    cudaError_t e = cudaMemsetAsync(tile_state, 0, nt * 8, st);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(ticket, 0, 4, st);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(walk_len, 0, (size_t)n_walks * 8, st);           // walks without steps
-    if (e != cudaSuccess) return e;
-    fused_steps_kernel<<<(unsigned)nt, FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr);
+    if (tile_last > nt) tile_last = nt;
+    if (tile_first == 0) {
+        cudaError_t e = cudaMemsetAsync(tile_state, 0, nt * 8, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(ticket, 0, 4, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(walk_len, 0, (size_t)n_walks * 8, st);       // walks without steps
+        if (e != cudaSuccess) return e;
+    }
+    if (tile_last <= tile_first) return cudaSuccess;
+    fused_steps_kernel<<<(unsigned)(tile_last - tile_first), FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
 uint64_t walk_steps_fused_tiles(uint64_t n_steps) { return (n_steps + FS_TILE - 1) / FS_TILE; }
+uint64_t walk_steps_fused_tile_steps() { return FS_TILE; }
 
 cudaError_t walk_step_finalize(const ChunkTable &C, const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off, uint32_t n_walks,
                                uint64_t n_steps, uint32_t *step_base, uint64_t *walk_len, cudaStream_t st, uint64_t *launches)
@@ -620,7 +643,7 @@ cudaError_t chunk_keys(const ChunkTable &C, const uint32_t *walk_vtx, const uint
                        const uint4 *vinfo, int k, int w, unsigned long long *ctr, cudaStream_t st, uint64_t *launches)
 {
     if (!C.n_chunks) return cudaSuccess;
-    chunk_key_kernel<<<(unsigned)(((uint64_t)C.n_chunks * 32 + 255) / 256), 256, 0, st>>>(C, walk_vtx, walk_off, step_base, walk_len, vinfo, k, w, ctr);
+    chunk_key_kernel<<<(unsigned)(((uint64_t)C.n_chunks * CK_LANES + 255) / 256), 256, 0, st>>>(C, walk_vtx, walk_off, step_base, walk_len, vinfo, k, w, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -637,7 +660,7 @@ cudaError_t chunk_group(const ChunkTable &C, uint32_t *table, uint32_t table_cap
     }
     chunk_group_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>(C, table, table_cap - 1, dedupe);
     PHI_LAUNCH_CHECK();
-    chunk_rep_kernel<<<(unsigned)(((uint64_t)C.n_chunks * 32 + 255) / 256), 256, 0, st>>>(C, table, walk_vtx, dedupe, w, ctr);
+    chunk_rep_kernel<<<(unsigned)(((uint64_t)C.n_chunks * CK_LANES + 255) / 256), 256, 0, st>>>(C, table, walk_vtx, dedupe, w, ctr);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

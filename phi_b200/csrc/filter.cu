@@ -33,42 +33,63 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x)
     return x;
 }
 
-__device__ __forceinline__ bool same_list(const FilterArgs &A, uint32_t a, uint32_t b)
+// ---- probe records: what the group table compares.  (rank, number of vertices, the first PROBE_VTX vertices) of a hit in one
+// 32-byte sector; longer lists (rare: k-mers over many tiny segments) continue in the vertex pool.
+constexpr uint32_t PROBE_VTX = 6;
+__global__ void __launch_bounds__(256) probe_build_kernel(FilterArgs A, uint4 *probe)
 {
-    if (A.hit_rank[a] != A.hit_rank[b]) return false;
-    uint32_t n = A.hit_nv[a];
-    if (n != A.hit_nv[b]) return false;
-    const int32_t *pa = A.vtx_pool + A.hit_voff[a], *pb = A.vtx_pool + A.hit_voff[b];
-    for (uint32_t i = 0; i < n; ++i) if (pa[i] != pb[i]) return false;
-    return true;
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= A.n_hits) return;
+    const int32_t *p = A.vtx_pool + A.hit_voff[i];
+    const uint32_t n = A.hit_nv[i];
+    uint32_t v[PROBE_VTX];
+    #pragma unroll
+    for (uint32_t q = 0; q < PROBE_VTX; ++q) v[q] = q < n ? (uint32_t)p[q] : 0u;
+    probe[2 * i] = make_uint4(A.hit_rank[i], n, v[0], v[1]);
+    probe[2 * i + 1] = make_uint4(v[2], v[3], v[4], v[5]);
 }
 
-__global__ void group_count_kernel(FilterArgs A, FilterWork W)
+__global__ void __launch_bounds__(256) group_count_kernel(FilterArgs A, FilterWork W)
 {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= A.n_hits) return;
-    const int32_t *p = A.vtx_pool + A.hit_voff[i];
-    uint32_t n = A.hit_nv[i];
-    uint64_t hsh = mix64(A.hit_rank[i] + 0x9E3779B97F4A7C15ull);
-    for (uint32_t q = 0; q < n; ++q) hsh = mix64(hsh ^ (uint64_t)(uint32_t)p[q]);
+    const uint4 m0 = W.probe[2 * i], m1 = W.probe[2 * i + 1];
+    const uint32_t n = m0.y;
+    const int32_t *tail = n > PROBE_VTX ? A.vtx_pool + A.hit_voff[i] : nullptr;
+    uint64_t hsh = mix64(m0.x + 0x9E3779B97F4A7C15ull);
+    {
+        const uint32_t v[PROBE_VTX] = {m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        #pragma unroll
+        for (uint32_t q = 0; q < PROBE_VTX; ++q) if (q < n) hsh = mix64(hsh ^ (uint64_t)v[q]);
+        for (uint32_t q = PROBE_VTX; q < n; ++q) hsh = mix64(hsh ^ (uint64_t)(uint32_t)tail[q]);
+    }
     const uint64_t mask = W.g_cap - 1;
     uint64_t slot = hsh & mask;
     for (uint64_t tries = 0; tries <= mask; ++tries) {
-        uint32_t rep = W.g_rep[slot];
+        uint32_t rep = W.g_slot[slot].x;
         if (rep == G_EMPTY) {
             if (W.ctr[CTR_GROUPS] * 10 > W.g_cap * 8) break;             // table too full: the host retries with a larger one
-            uint32_t old = atomicCAS(&W.g_rep[slot], G_EMPTY, (uint32_t)i);
+            uint32_t old = atomicCAS(&W.g_slot[slot].x, G_EMPTY, (uint32_t)i);
             if (old == G_EMPTY) { rep = (uint32_t)i; atomicAdd(&W.ctr[CTR_GROUPS], 1ull); } else rep = old;
         }
-        if (rep == (uint32_t)i || same_list(A, (uint32_t)i, rep)) {
+        bool same = rep == (uint32_t)i;
+        if (!same) {                                                      // exact: (rank, list) against the representing record's
+            const uint4 r0 = W.probe[2 * (uint64_t)rep], r1 = W.probe[2 * (uint64_t)rep + 1];
+            same = r0.x == m0.x && r0.y == m0.y && r0.z == m0.z && r0.w == m0.w && r1.x == m1.x && r1.y == m1.y && r1.z == m1.z && r1.w == m1.w;
+            if (same && n > PROBE_VTX) {
+                const int32_t *rt = A.vtx_pool + A.hit_voff[rep];
+                for (uint32_t q = PROBE_VTX; q < n; ++q) same &= rt[q] == tail[q];
+            }
+        }
+        if (same) {
             const uint32_t wt = W.weight ? W.weight[i] : W.chunk_weight ? W.chunk_weight[A.hit_walk[i]] : 1u;
-            const uint32_t before = atomicAdd(&W.g_cnt[slot], wt);
+            const uint32_t before = atomicAdd(&W.g_slot[slot].y, wt);
             W.hit_slot[i] = (uint32_t)slot;
             if (W.hit_sub) W.hit_sub[i] = before;
             // anchor.second.first >= threshold * num_walks — int32 promoted to float (:698).  Counts only grow, so the group ends
             // at or above the threshold iff some addition lands there: that thread drops the rank (and counts it once).
             if (W.mark_inline && (float)(int32_t)(before + wt) >= A.thr) {
-                const uint32_t r = A.hit_rank[i], bit = 1u << (8 * (r & 3u));
+                const uint32_t r = m0.x, bit = 1u << (8 * (r & 3u));
                 const uint32_t old = atomicOr((uint32_t *)(W.rank_drop + (r & ~3u)), bit);
                 if (!(old & bit)) atomicAdd(&W.ctr[CTR_FILTERED], 1ull);
             }
@@ -107,6 +128,14 @@ cudaError_t filter_shared_kmer_hist(const uint64_t *hash, const uint32_t *walk, 
     if (!n) return cudaSuccess;
     const size_t smem = n_walks + 1 <= CSR_HIST_MAX ? ((size_t)n_walks + 1) * 4 : 0;
     shared_kmer_hist_kernel<<<(unsigned)((n + 255) / 256), 256, smem, st>>>(hash, walk, n, n_walks, hist, distinct);
+    PHI_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t filter_build_probe(const FilterArgs &A, uint4 *probe, cudaStream_t st, uint64_t *launches)
+{
+    if (!A.n_hits) return cudaSuccess;
+    probe_build_kernel<<<(unsigned)((A.n_hits + 255) / 256), 256, 0, st>>>(A, probe);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -111,9 +111,10 @@ __global__ void __launch_bounds__(256) group_flags_kernel(FilterArgs A, FilterWo
     uint32_t f = 0; unsigned long long members = 0, vtx = 0;
     if (i < A.n_hits) {
         const uint32_t slot = W.hit_slot[i];
-        if (W.g_rep[slot] == (uint32_t)i) {
-            if (!W.rank_drop[A.hit_rank[i]]) { f = 1; members = W.g_cnt[slot]; vtx = A.hit_nv[i]; }
-            else W.g_rep[slot] = G_DROPPED;                              // the other hits of the slot only ever compare it with their own id
+        const uint2 gs = W.g_slot[slot];
+        if (gs.x == (uint32_t)i) {
+            if (!W.rank_drop[A.hit_rank[i]]) { f = 1; members = gs.y; vtx = A.hit_nv[i]; }
+            else W.g_slot[slot].x = G_DROPPED;                           // the other hits of the slot only ever compare it with their own id
         }
         flags[i] = f;
     }
@@ -156,8 +157,8 @@ __global__ void group_sizes_kernel(FilterArgs A, FilterWork W, const uint32_t *o
     if (j >= n) return;
     const uint32_t i = order[j], slot = W.hit_slot[i];
     const uint8_t nv = A.hit_nv[i];
-    cnt_out[j] = W.g_cnt[slot]; nv_out[j] = nv; group_len[j] = nv;
-    W.g_rep[slot] = j;
+    cnt_out[j] = W.g_slot[slot].y; nv_out[j] = nv; group_len[j] = nv;
+    W.g_slot[slot].x = j;
     W.hit_sub[i] |= SUB_REP_BIT;
     const int64_t r = A.hit_rank[i], rp = j ? (int64_t)A.hit_rank[order[j - 1]] : -1;
     for (int64_t q = rp + 1; q <= r; ++q) rank_off[q] = j;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(256) group_fill_kernel(FilterArgs A, FilterWor
     const uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 2;
     const uint32_t sub = threadIdx.x & 3;
     if (i >= A.n_hits) return;
-    const uint32_t j = W.g_rep[W.hit_slot[i]];                            // output index of the hit's group
+    const uint32_t j = W.g_slot[W.hit_slot[i]].x;                         // output index of the hit's group
     if (j == G_DROPPED) return;
     const uint32_t c = A.hit_walk[i];                                     // hits of representatives: the chunk takes the place of the walk
     const uint32_t s0 = G.cm_off[c], n = G.cm_off[c + 1] - s0;

@@ -152,10 +152,14 @@ cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, u
 // step pass + scan + finalisation in one kernel (decoupled look-back; the common case without zero-length steps, which it only
 // counts): step_base, walk_len, chunk_step[0..chunks] / c_walk (both sized for n_steps + 1 chunks), ctr[CTR_CHUNK_FLAGS] = chunks.
 // tile_state: walk_steps_fused_tiles(n_steps) words.
+// tile_first / tile_last: the tiles [tile_first, tile_last) are launched (the steps may arrive piece by piece: tiles take their index
+// from a ticket, so consecutive launches continue the scan); tile_first == 0 also resets the scan state.
 uint64_t walk_steps_fused_tiles(uint64_t n_steps);
+uint64_t walk_steps_fused_tile_steps();
 cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo, uint32_t n_vtx,
                              unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base, uint32_t *chunk_step, uint32_t *c_walk,
-                             uint64_t *walk_len, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
+                             uint64_t *walk_len, unsigned long long *ctr, cudaStream_t st, uint64_t *launches,
+                             uint64_t tile_first = 0, uint64_t tile_last = ~0ull);
 // scanned = exclusive scan of packed (as u64) -> step_base, walk_len, chunk_step / c_walk of C
 cudaError_t walk_step_finalize(const ChunkTable &C, const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off, uint32_t n_walks,
                                uint64_t n_steps, uint32_t *step_base, uint64_t *walk_len, cudaStream_t st, uint64_t *launches);
@@ -218,7 +222,8 @@ struct FilterArgs {
     int rank_bits;                   // bits of the largest rank (sort width)
 };
 struct FilterWork {                  // device scratch, sized by the host
-    uint32_t *g_rep, *g_cnt; uint64_t g_cap;      // group table
+    uint2 *g_slot; uint64_t g_cap;                 // group table: slot = (representing record, count), one 8-byte word
+    const uint4 *probe;                            // [2 * n_hits] one 32-byte probe record per hit: (rank, vertices, first 6 vertices)
     uint32_t *hit_slot;                            // [n_hits] slot of each hit's group
     uint32_t *hit_sub;                             // optional [n_hits]: the group's count before this hit was added (its sub-offset in the group)
     const uint32_t *weight;                        // optional [n_hits]: occurrences a record stands for (multi-GPU summaries)
@@ -232,6 +237,9 @@ struct FilterWork {                  // device scratch, sized by the host
 };
 cudaError_t filter_shared_kmer_hist(const uint64_t *hash, const uint32_t *walk, uint64_t n, uint32_t n_walks, unsigned long long *hist,
                                     unsigned long long *distinct, cudaStream_t st, uint64_t *launches);
+// probe records of the hits of A (filter_count_groups compares a hit with the record that represents a slot through them: one
+// 32-byte sector instead of a chain of four dependent scattered reads)
+cudaError_t filter_build_probe(const FilterArgs &A, uint4 *probe, cudaStream_t st, uint64_t *launches);
 cudaError_t filter_count_groups(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);
 // stable sort of the records (which arrive in (walk, position) order) on their rank: order ends up in W.vals_a
 cudaError_t filter_sort_records(const FilterArgs &A, const FilterWork &W, cudaStream_t st, uint64_t *launches);

@@ -54,9 +54,11 @@ struct phi_gpu_index_ctx {
     // host -> device copies of phi_gpu_index_run: one copy stream, graph first (the second stream starts preparing it), then the
     // reads in pieces (the main stream sketches piece p while piece p+1 is on the wire)
     cudaStream_t st_copy = nullptr;
-    cudaEvent_t ev_graph_in = nullptr, ev_piece[8] = {};
+    cudaEvent_t ev_graph_in = nullptr, ev_piece[8] = {}, ev_wpiece[8] = {};
     int n_pieces = 0;                      // > 0: an upload is in flight and the read stage has to wait piece by piece
     uint64_t piece_end[8] = {};            // read bases [0, piece_end[p]) are on the device once ev_piece[p] has fired
+    int n_wpieces = 0;                     // the walk steps arrive in this many pieces (after everything else of the graph: ev_graph_in)
+    uint64_t wpiece_end[8] = {};           // walk steps [0, wpiece_end[p]) are on the device once ev_wpiece[p] has fired
     std::string err = "no error";
     uint64_t launches = 0;
     phi_stage_times times = {};
@@ -78,11 +80,11 @@ struct phi_gpu_index_ctx {
     DevBuf hseg_off, hseg_cnt, c_emitted, c_hits, c_surv, c_surv_vtx, member_cnt, member_off, x_rank, x_walk, x_pos, x_voff, x_nv, x_hash;
     uint32_t n_chunks = 0, n_tiles = 0; uint64_t unique_windows = 0, active_chunks = 0, rep_chunks = 0, unique_hits = 0, path_pos = 0; int dedupe = 1, chunk_shift = 11;
     uint64_t own_lo = 0, own_hi = ~0ull;   // owned range of the topological base coordinate (phi_gpu_index_set_walk_region); default: everything
-    DevBuf g_rep, g_cnt, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
+    DevBuf g_slot, probe, rank_drop, flags, keys_a, keys_b, vals_a, vals_b, big_list, tmp_order, nv_out;
     DevBuf anchor_off, rank_off, anchor_len, anchor_walk, anchor_vtx, apw, dbg_hist;
     // grouped result (groups.cu): member walks of the representative chunks, slot / sub-offset of every hit, group sizes and offsets
     DevBuf fs_state;                       // ticket + one look-back word per tile of the fused step kernel
-    DevBuf cm_off, cm_cursor, cm_tmp, cm_walk, hit_slot, hit_sub, hit_slot2, g_rep2, g_cnt2, grp_cnt, grp_moff, grp_voff, members_tmp;
+    DevBuf cm_off, cm_cursor, cm_tmp, cm_walk, hit_slot, hit_sub, hit_slot2, g_slot2, probe2, grp_cnt, grp_moff, grp_voff, members_tmp;
     unsigned long long *h_ctr = nullptr;   // pinned mirror of the counter block
     // what the second stream uses instead of ctr / h_ctr / scan_scr / flags / flags64 / nv_out (swapped in by PrepScope)
     DevBuf ctr2, scan_scr2, flags2, flags64_2, nv_out2; unsigned long long *h_ctr2 = nullptr;
@@ -92,6 +94,7 @@ struct phi_gpu_index_ctx {
     int rank = 0, world = 1; uint32_t walk_id_base = 0, n_walks_global = 0;
     void *comm = nullptr;
     uint64_t gcap_hint = 0, gcap_hint2 = 0;   // group-table sizes that worked last time (local table, owner-side table)
+    uint64_t spec_hint = 0, spec_hint_bases = 0;   // distinct read minimizers of the last run and the read bases they came from (spectrum table sizing)
     DevBuf xk_a, xk_b, xcnt, xoff, ag_send, ag_recv, m_rank, m_cnt, m_voff, m_nv, r_rank, r_walk, r_pos, r_voff, r_nv, r_vtx, s_rank, s_walk, s_pos, s_voff, s_nv, s_vtx;
     std::vector<uint64_t> own_off;       // [world + 1] first global rank owned by each GPU (multi-GPU runs)
     uint64_t *h_words = nullptr; size_t h_words_cap = 0;   // pinned: gathered words of the small collectives
@@ -140,7 +143,7 @@ extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
     cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming);
     if ((e = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     cudaEventCreateWithFlags(&ctx->ev_graph_in, cudaEventDisableTiming);
-    for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&ctx->ev_piece[i], cudaEventDisableTiming);
+    for (int i = 0; i < 8; ++i) { cudaEventCreateWithFlags(&ctx->ev_piece[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_wpiece[i], cudaEventDisableTiming); }
     if ((e = cudaHostAlloc((void **)&ctx->h_ctr, CTR_COUNT * 8, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     if ((e = cudaHostAlloc((void **)&ctx->h_tot, 64, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     if ((e = cudaHostAlloc((void **)&ctx->h_ctr2, CTR_COUNT * 8, cudaHostAllocDefault)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
@@ -173,9 +176,9 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
                       &ctx->xk_a, &ctx->xk_b, &ctx->xcnt, &ctx->xoff, &ctx->ag_send, &ctx->ag_recv, &ctx->m_rank, &ctx->m_cnt, &ctx->m_voff, &ctx->m_nv,
                       &ctx->r_rank, &ctx->r_walk, &ctx->r_pos, &ctx->r_voff, &ctx->r_nv, &ctx->r_vtx, &ctx->s_rank, &ctx->s_walk, &ctx->s_pos,
                       &ctx->s_voff, &ctx->s_nv, &ctx->s_vtx,
-                      &ctx->hit_voff, &ctx->hit_nv, &ctx->hit_hash, &ctx->vtx_pool, &ctx->g_rep, &ctx->g_cnt, &ctx->rank_drop, &ctx->flags,
+                      &ctx->hit_voff, &ctx->hit_nv, &ctx->hit_hash, &ctx->vtx_pool, &ctx->g_slot, &ctx->probe, &ctx->rank_drop, &ctx->flags,
                       &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->big_list, &ctx->tmp_order, &ctx->nv_out,
-                      &ctx->fs_state, &ctx->cm_off, &ctx->cm_cursor, &ctx->cm_tmp, &ctx->cm_walk, &ctx->hit_slot, &ctx->hit_sub, &ctx->hit_slot2, &ctx->g_rep2, &ctx->g_cnt2,
+                      &ctx->fs_state, &ctx->cm_off, &ctx->cm_cursor, &ctx->cm_tmp, &ctx->cm_walk, &ctx->hit_slot, &ctx->hit_sub, &ctx->hit_slot2, &ctx->g_slot2, &ctx->probe2,
                       &ctx->grp_cnt, &ctx->grp_moff, &ctx->grp_voff, &ctx->members_tmp,
                       &ctx->dbg_hist, &ctx->anchor_off, &ctx->rank_off, &ctx->anchor_len, &ctx->anchor_walk, &ctx->anchor_vtx, &ctx->apw};
     for (DevBuf *b : bufs) b->release();
@@ -193,7 +196,7 @@ extern "C" void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx)
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->ev_graph_in) cudaEventDestroy(ctx->ev_graph_in);
-    for (int i = 0; i < 8; ++i) if (ctx->ev_piece[i]) cudaEventDestroy(ctx->ev_piece[i]);
+    for (int i = 0; i < 8; ++i) { if (ctx->ev_piece[i]) cudaEventDestroy(ctx->ev_piece[i]); if (ctx->ev_wpiece[i]) cudaEventDestroy(ctx->ev_wpiece[i]); }
     if (ctx->st_copy) { cudaStreamSynchronize(ctx->st_copy); cudaStreamDestroy(ctx->st_copy); }
     if (ctx->st) cudaStreamDestroy(ctx->st);
     if (ctx->st2) cudaStreamDestroy(ctx->st2);
@@ -248,11 +251,22 @@ static int upload_async(phi_gpu_index_ctx *ctx, const phi_graph_view *g, const p
     CU(cudaMemcpyAsync(ctx->seg_off.p, g->n_vtx ? g->seg_off : zero_off, ((size_t)g->n_vtx + 1) * 8, cudaMemcpyHostToDevice, sc));
     if (g->n_vtx) CU(cudaMemcpyAsync(ctx->top_order.p, g->top_order_map, (size_t)g->n_vtx * 4, cudaMemcpyHostToDevice, sc));
     CU(cudaMemcpyAsync(ctx->walk_off.p, g->n_walks ? g->walk_off : zero_off, ((size_t)g->n_walks + 1) * 8, cudaMemcpyHostToDevice, sc));
-    if (ctx->n_steps) CU(cudaMemcpyAsync(ctx->walk_vtx.p, g->walk_vtx, ctx->n_steps * 4, cudaMemcpyHostToDevice, sc));
     CU(cudaMemsetAsync(ctx->seg_bases.p, 0, 16, sc));
     CU(cudaMemsetAsync((char *)ctx->seg_bases.p + 16 + ctx->seg_total, 0, 32, sc));
     if (ctx->seg_total) CU(cudaMemcpyAsync((char *)ctx->seg_bases.p + 16, g->seg_bases, ctx->seg_total, cudaMemcpyHostToDevice, sc));
-    CU(cudaEventRecord(ctx->ev_graph_in, sc));
+    CU(cudaEventRecord(ctx->ev_graph_in, sc));                               // everything of the graph but the walk steps
+    {   // the walk steps (the bulk of a big graph) in pieces: the step pass of the graph preparation follows piece by piece
+        const uint64_t S = ctx->n_steps, tile = walk_steps_fused_tile_steps();
+        const int WP = S >= (8u << 20) ? 8 : 1;
+        ctx->n_wpieces = WP;
+        uint64_t lo = 0;
+        for (int p = 0; p < WP; ++p) {
+            uint64_t hi = p + 1 == WP ? S : (S * (p + 1) / WP) / tile * tile;
+            if (hi > lo) CU(cudaMemcpyAsync(ctx->walk_vtx.as<uint32_t>() + lo, g->walk_vtx + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, sc));
+            ctx->wpiece_end[p] = hi; lo = hi;
+            CU(cudaEventRecord(ctx->ev_wpiece[p], sc));
+        }
+    }
     CU(cudaMemcpyAsync(ctx->read_off.p, ctx->n_reads ? r->read_off : zero_off, (ctx->n_reads + 1) * 8, cudaMemcpyHostToDevice, sc));
     CU(cudaMemsetAsync(ctx->read_bases.p, 0, 16, sc));
     CU(cudaMemsetAsync((char *)ctx->read_bases.p + 16 + ctx->read_total, 0, 32, sc));
@@ -378,9 +392,25 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     CU(ctx->chunk_step.reserve((S + 2) * 4)); CU(ctx->c_walk.reserve((S + 2) * 4));       // at most one chunk per step
     CU(ctx->fs_state.reserve(walk_steps_fused_tiles(S) * 8 + 16));
     CU(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, ctx->st)); CU(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, ctx->st));
-    CU(walk_steps_fused(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), V, ctx->fs_state.as<unsigned long long>() + 1, ctx->fs_state.as<uint32_t>(),
-                        ctx->step_base.as<uint32_t>(), ctx->chunk_step.as<uint32_t>(), ctx->c_walk.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), d_ctr,
-                        ctx->st, &ctx->launches));
+    if (ctx->n_pieces && ctx->n_wpieces > 1) {
+        // phi_gpu_index_run: the walk steps are still arriving; every piece is scanned as soon as it is there
+        const uint64_t tile = walk_steps_fused_tile_steps();
+        uint64_t t0 = 0;
+        for (int p = 0; p < ctx->n_wpieces; ++p) {
+            CU(cudaStreamWaitEvent(ctx->st, ctx->ev_wpiece[p], 0));
+            const uint64_t t1 = p + 1 == ctx->n_wpieces ? walk_steps_fused_tiles(S) : ctx->wpiece_end[p] / tile;
+            if (t1 > t0 || p == 0)
+                CU(walk_steps_fused(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), V, ctx->fs_state.as<unsigned long long>() + 1, ctx->fs_state.as<uint32_t>(),
+                                    ctx->step_base.as<uint32_t>(), ctx->chunk_step.as<uint32_t>(), ctx->c_walk.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), d_ctr,
+                                    ctx->st, &ctx->launches, t0, t1));
+            t0 = std::max(t0, t1);
+        }
+    } else {
+        if (ctx->n_pieces) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_wpiece[ctx->n_wpieces - 1], 0));
+        CU(walk_steps_fused(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), V, ctx->fs_state.as<unsigned long long>() + 1, ctx->fs_state.as<uint32_t>(),
+                            ctx->step_base.as<uint32_t>(), ctx->chunk_step.as<uint32_t>(), ctx->c_walk.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), d_ctr,
+                            ctx->st, &ctx->launches));
+    }
     CU(read_counters(ctx));                                             // wait 1
     if (ctx->h_ctr[CTR_BAD_VTX]) return ctx->fail(PHI_ERR_ARG, "graph view: a walk step names a vertex id >= n_vtx");
     if (ctx->h_ctr[CTR_SEG_TOO_LONG]) return ctx->fail(PHI_ERR_UNSUPPORTED, "segment of 2^31 bases or more");
@@ -905,9 +935,13 @@ static int stage_reads_begin(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &r
     CU(cudaGetLastError()); ctx->launches++;
     CU(ctx->tile_first_read.reserve(rs.n_tiles * 8));
     CU(launch_read_tile_dir(ctx->read_off.as<uint64_t>(), R, w, rs.n_tiles, ctx->tile_first_read.as<uint64_t>(), ctx->st)); ctx->launches++;
-    // expected minimizer density is 2/(w+1); size the table for ~35% load at that density, retry on overflow
+    // expected minimizer density is 2/(w+1); size the table for ~35% load at that density, retry on overflow.  Reads repeat k-mers
+    // (coverage), so far fewer keys are DISTINCT than emitted: when this ctx has sketched a read set of about this size before, the
+    // table is sized from the distinct count seen then (every pass over the table streams all of its slots, occupied or not).
     double dens = std::min(1.0, 2.6 / (w + 1.0));
     uint64_t want = (uint64_t)((double)G * dens * 2.0) + 1024;
+    if (ctx->spec_hint && G <= ctx->spec_hint_bases + ctx->spec_hint_bases / 8 && G + G / 8 >= ctx->spec_hint_bases)
+        want = std::min(want, ctx->spec_hint * 5 / 2 + 1024);
     rs.cap = 1024;
     while (rs.cap < want) rs.cap <<= 1;
     return reads_sketch_launch(ctx, k, w, rs);
@@ -928,6 +962,7 @@ static int stage_reads_local(phi_gpu_index_ctx *ctx, int k, int w, ReadsState &r
         o.read_emitted = ctx->h_ctr[CTR_READ_EMITTED];
         o.read_pos = ctx->h_ctr[CTR_READ_POS];
         const uint64_t nd = *ctx->h_tot;                                   // occupied slots (copied by the same sync)
+        ctx->spec_hint = nd; ctx->spec_hint_bases = ctx->read_total;
         const bool maxkey = ctx->h_ctr[CTR_HAS_MAXKEY] != 0;
         n_spec = nd + (maxkey ? 1 : 0);
         if (n_spec >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^31-1 distinct read minimizers (count_sp_r is int32 in the reference)");
@@ -1055,18 +1090,20 @@ static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, Fi
     uint64_t &hint = owner_side ? ctx->gcap_hint2 : ctx->gcap_hint;
     if (owner_side) { gcap = 1024; while (gcap < 2 * n) gcap <<= 1; }     // at most n groups: the 80 % load limit is out of reach, no host wait needed
     else if (hint > gcap) gcap = hint;
-    DevBuf &slotb = owner_side ? ctx->hit_slot2 : ctx->hit_slot, &repb = owner_side ? ctx->g_rep2 : ctx->g_rep, &cntb = owner_side ? ctx->g_cnt2 : ctx->g_cnt;
+    DevBuf &slotb = owner_side ? ctx->hit_slot2 : ctx->hit_slot, &tabb = owner_side ? ctx->g_slot2 : ctx->g_slot, &probeb = owner_side ? ctx->probe2 : ctx->probe;
     CU(slotb.reserve(n * 4 + 4));
     W.hit_slot = slotb.as<uint32_t>();
     W.hit_sub = nullptr;
     if (!owner_side) { CU(ctx->hit_sub.reserve(n * 4 + 4)); W.hit_sub = ctx->hit_sub.as<uint32_t>(); }
     W.weight = weight; W.chunk_weight = chunk_weight;
+    CU(probeb.reserve(n * 32 + 32));
+    CU(filter_build_probe(A, probeb.as<uint4>(), ctx->st, &ctx->launches));
+    W.probe = probeb.as<uint4>();
     for (;;) {
-        CU(repb.reserve(gcap * 4)); CU(cntb.reserve(gcap * 4));
-        CU(fill_u32(repb.as<uint32_t>(), gcap, 0xFFFFFFFFu, ctx->st, &ctx->launches));
-        CU(cudaMemsetAsync(cntb.p, 0, gcap * 4, ctx->st));
+        CU(tabb.reserve(gcap * 8));
+        CU(fill_u64(tabb.as<uint64_t>(), gcap, 0x00000000FFFFFFFFull, ctx->st, &ctx->launches));   // (representative: none, count: 0)
         CU(cudaMemsetAsync(d_ctr + CTR_GROUPS, 0, 2 * 8, ctx->st));
-        W.g_rep = repb.as<uint32_t>(); W.g_cnt = cntb.as<uint32_t>(); W.g_cap = gcap;
+        W.g_slot = tabb.as<uint2>(); W.g_cap = gcap;
         CU(filter_count_groups(A, W, ctx->st, &ctx->launches));
         if (owner_side) break;
         CU(read_counters(ctx));
@@ -1196,21 +1233,22 @@ static int groups_out(phi_gpu_index_ctx *ctx, const FilterArgs &A, FilterWork &W
     return PHI_OK;
 }
 
-__global__ void summary_flags_kernel(const uint32_t *g_rep, const uint32_t *hit_slot, uint64_t n, uint32_t *flags)
+__global__ void summary_flags_kernel(const uint2 *g_slot, const uint32_t *hit_slot, uint64_t n, uint32_t *flags)
 {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = g_rep[hit_slot[i]] == (uint32_t)i ? 1u : 0u;
+    if (i < n) flags[i] = g_slot[hit_slot[i]].x == (uint32_t)i ? 1u : 0u;
 }
 // one summary per local group: (rank, count, vertex list of the representative)
-__global__ void summary_emit_kernel(FilterArgs A, const uint32_t *g_rep, const uint32_t *g_cnt, const uint32_t *hit_slot, const uint64_t *pos,
+__global__ void summary_emit_kernel(FilterArgs A, const uint2 *g_slot, const uint32_t *hit_slot, const uint64_t *pos,
                                     uint32_t *m_rank, uint32_t *m_cnt, uint64_t *m_voff, uint8_t *m_nv)
 {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= A.n_hits) return;
     uint32_t slot = hit_slot[i];
-    if (g_rep[slot] != (uint32_t)i) return;
+    const uint2 gs = g_slot[slot];
+    if (gs.x != (uint32_t)i) return;
     uint64_t j = pos[i];
-    m_rank[j] = A.hit_rank[i]; m_cnt[j] = g_cnt[slot]; m_voff[j] = A.hit_voff[i]; m_nv[j] = A.hit_nv[i];
+    m_rank[j] = A.hit_rank[i]; m_cnt[j] = gs.y; m_voff[j] = A.hit_voff[i]; m_nv[j] = A.hit_nv[i];
 }
 
 // status (several GPUs only): error code of the walk stage of this rank; it travels with the small collective of the record
@@ -1271,12 +1309,12 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walk
             if (rc) return rc;
             CU(ctx->flags.reserve(n * 4 + 4)); CU(ctx->flags64.reserve((n + 1) * 8));
             CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch(n), scan_u32_to_u64_scratch(n + 1))));
-            summary_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(W.g_rep, W.hit_slot, n, ctx->flags.as<uint32_t>());
+            summary_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(W.g_slot, W.hit_slot, n, ctx->flags.as<uint32_t>());
             CU(cudaGetLastError()); ctx->launches++;
             CU(scan_u32_to_u64(ctx->flags.as<uint32_t>(), ctx->flags64.as<uint64_t>(), n, ctx->scan_scr.p, ctx->st, &ctx->launches));
             n_sum = ctx->h_ctr[CTR_GROUPS];                                   // distinct local groups (read by count_groups_adaptive)
             CU(ctx->m_rank.reserve(n_sum * 4 + 4)); CU(ctx->m_cnt.reserve(n_sum * 4 + 4)); CU(ctx->m_voff.reserve(n_sum * 8 + 8)); CU(ctx->m_nv.reserve(n_sum + 4));
-            summary_emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(A, W.g_rep, W.g_cnt, W.hit_slot, ctx->flags64.as<uint64_t>(),
+            summary_emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(A, W.g_slot, W.hit_slot, ctx->flags64.as<uint64_t>(),
                                                                                  ctx->m_rank.as<uint32_t>(), ctx->m_cnt.as<uint32_t>(), ctx->m_voff.as<uint64_t>(), ctx->m_nv.as<uint8_t>());
             CU(cudaGetLastError()); ctx->launches++;
             return PHI_OK;

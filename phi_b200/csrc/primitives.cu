@@ -382,28 +382,37 @@ cudaError_t radix_sort_u32(uint32_t *keys_a, uint32_t *keys_b, uint32_t *vals_a,
 // A probe cluster is a maximal run of occupied slots.  Every key of a cluster has its home slot inside the cluster, homes are
 // monotone in the key, and clusters are separated by an EMPTY slot: sorting each cluster in place sorts the table.
 // One thread per cluster head; clusters are short (load <= ~50 %, uniform hashes), so this is a few compares per key.
-__global__ void table_cluster_sort_kernel(uint64_t *table, uint64_t limit)
+// The same pass counts the occupied slots of every TABLE_BLOCK slots (sorting moves keys inside a cluster only: which slots
+// are occupied does not change), so the table is streamed once for both.
+__global__ void __launch_bounds__(256) table_cluster_sort_kernel(uint64_t *table, uint64_t limit, uint32_t *block_cnt)
 {
-    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (s >= limit) return;
-    if (table[s] == TABLE_EMPTY || (s && table[s - 1] != TABLE_EMPTY)) return;   // not a cluster head
-    for (uint64_t a = s + 1; table[a] != TABLE_EMPTY; ++a) {                      // table[limit] is EMPTY: stops there at the latest
-        uint64_t x = table[a], b = a;
-        while (b > s && table[b - 1] > x) { table[b] = table[b - 1]; --b; }
-        table[b] = x;
-    }
-}
-
-__global__ void __launch_bounds__(256) table_count_kernel(const uint64_t *table, uint64_t limit, uint32_t *block_cnt)
-{
-    uint64_t base = (uint64_t)blockIdx.x * TABLE_BLOCK + threadIdx.x;
-    uint32_t c = 0;
-    #pragma unroll
-    for (int i = 0; i < (int)(TABLE_BLOCK / 256); ++i) { uint64_t j = base + (uint64_t)i * 256; c += j < limit && table[j] != TABLE_EMPTY; }
     __shared__ uint32_t scratch[32];
+    constexpr int I = (int)(TABLE_BLOCK / 256);
+    const uint64_t base = (uint64_t)blockIdx.x * TABLE_BLOCK + threadIdx.x;       // slot j = base + i * 256: coalesced
+    uint32_t c = 0, heads = 0;
+    #pragma unroll
+    for (int i = 0; i < I; ++i) {
+        const uint64_t j = base + (uint64_t)i * 256;
+        const uint64_t v = j < limit ? table[j] : TABLE_EMPTY;
+        uint64_t left = __shfl_up_sync(0xFFFFFFFFu, v, 1);
+        if ((threadIdx.x & 31) == 0) left = (j && j <= limit) ? table[j - 1] : TABLE_EMPTY;
+        const bool occ = v != TABLE_EMPTY;
+        c += occ;
+        if (occ && left == TABLE_EMPTY) heads |= 1u << i;                         // cluster head
+    }
     uint32_t tot;
     block_exclusive<uint32_t>(c, &tot, scratch);
     if (threadIdx.x == 0) block_cnt[blockIdx.x] = tot;
+    #pragma unroll
+    for (int i = 0; i < I; ++i) {
+        if (!((heads >> i) & 1u)) continue;
+        const uint64_t s = base + (uint64_t)i * 256;
+        for (uint64_t a = s + 1; table[a] != TABLE_EMPTY; ++a) {                  // table[limit] is EMPTY: stops there at the latest
+            uint64_t x = table[a], b = a;
+            while (b > s && table[b - 1] > x) { table[b] = table[b - 1]; --b; }
+            table[b] = x;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) table_write_kernel(const uint64_t *table, uint64_t limit, const uint32_t *block_off, uint64_t *out)
@@ -454,9 +463,7 @@ size_t table_blocks(uint64_t limit) { return (size_t)((limit + TABLE_BLOCK - 1) 
 cudaError_t table_sort_and_count(uint64_t *table, uint64_t limit, uint32_t *block_cnt, cudaStream_t st, uint64_t *launches)
 {
     if (!limit) return cudaSuccess;
-    table_cluster_sort_kernel<<<(unsigned)((limit + 255) / 256), 256, 0, st>>>(table, limit);
-    PHI_LAUNCH_CHECK();
-    table_count_kernel<<<(unsigned)table_blocks(limit), 256, 0, st>>>(table, limit, block_cnt);
+    table_cluster_sort_kernel<<<(unsigned)table_blocks(limit), 256, 0, st>>>(table, limit, block_cnt);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

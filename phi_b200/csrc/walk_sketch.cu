@@ -8,6 +8,7 @@
 #define PHI_TILE_THREADS 128
 #include "kernels.h"
 #include "sketch_common.cuh"
+#include <cstdlib>
 
 namespace phi {
 static_assert(PHI_TILE_THREADS == WALK_TILE_THREADS, "tile size");
@@ -137,8 +138,7 @@ __device__ __forceinline__ void walk_tile_body(Tile &t, const WalkSketchArgs &A,
     if (tid == 0 && emitted) atomicAdd(&A.chunk_emitted[tr.chunk], (uint32_t)emitted);
 }
 
-__global__ void __launch_bounds__(NT, 6)
-walk_sketch_kernel(WalkSketchArgs A)
+__device__ __forceinline__ void walk_sketch_body(const WalkSketchArgs &A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t tile = blockIdx.x;
@@ -216,6 +216,12 @@ walk_sketch_kernel(WalkSketchArgs A)
     else walk_tile_body<true, false>(t, A, tr, tile);
 }
 
+// The same body under three register budgets (resident CTAs per SM: 6 -> 80 registers, 7 -> 72, 8 -> 64 with a few spills); which one
+// wins is a measurement (PHI_GPU_WALK_CTAS picks; default below).
+__global__ void __launch_bounds__(NT, 6) walk_sketch_kernel(WalkSketchArgs A) { walk_sketch_body(A); }
+__global__ void __launch_bounds__(NT, 7) walk_sketch_kernel_r72(WalkSketchArgs A) { walk_sketch_body(A); }
+__global__ void __launch_bounds__(NT, 8) walk_sketch_kernel_r64(WalkSketchArgs A) { walk_sketch_body(A); }
+
 // ================================================================== hash KAT hook
 __global__ void hash_bytes_kernel(const uint8_t *keys, uint64_t n, int len, uint64_t *out)
 {
@@ -241,9 +247,12 @@ cudaError_t launch_walk_sketch(const WalkSketchArgs &A, uint32_t n_tiles, cudaSt
 {
     if (!n_tiles) return cudaSuccess;
     size_t smem = (size_t)A.layout.bytes;
-    cudaError_t e = cudaFuncSetAttribute(walk_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static int ctas = 0;
+    if (!ctas) { const char *e = getenv("PHI_GPU_WALK_CTAS"); ctas = e ? atoi(e) : 6; if (ctas < 6 || ctas > 8) ctas = 6; }
+    auto kern = ctas == 8 ? walk_sketch_kernel_r64 : ctas == 7 ? walk_sketch_kernel_r72 : walk_sketch_kernel;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    walk_sketch_kernel<<<n_tiles, NT, smem, st>>>(A);
+    kern<<<n_tiles, NT, smem, st>>>(A);
     return cudaGetLastError();
 }
 

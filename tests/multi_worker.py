@@ -139,6 +139,11 @@ def main_cpu(name):
         anchor_rank=np.array([h[0] for h in kept], dtype=np.int32), anchor_walk=np.array([h[1] for h in kept], dtype=np.int32),
         anchor_off=voff, anchor_vtx=np.array([v for h in kept for v in h[3]], dtype=np.int32),
         minimizers_per_walk=mpw, anchors_per_walk=apw)
+    # the ABI's grouped form of this rank's anchors (what the library returns and phi_index_result_merge takes)
+    import dataclasses
+    ro, gl, gv, mo, mw = phi_io.group_anchors(part)
+    part = dataclasses.replace(part, rank_off=ro, group_len=gl, group_vtx=gv, group_member_off=mo, member_walk=mw, n_groups=len(gl),
+                               spectrum=spectrum if rank == 0 else np.zeros(0, dtype=np.uint64))
     parts = [None] * world
     dist.gather_object(part, parts if rank == 0 else None, dst=0)
     if rank == 0:
