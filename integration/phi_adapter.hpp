@@ -29,8 +29,9 @@
 namespace phi_adapter {
 
 
-// What the front end returns: one result per GPU (one part with a single GPU).  Part p holds the groups of ITS walks for all
-// ranks; walk ranges ascend with p, so "the parts one after another" is the reference's walk order.
+// What the front end returns: ONE result in the reference's order (the per-GPU parts of a multi-GPU run are merged by
+// phi_index_result_merge).  `parts` stays a list for the test hook, which can feed by-walk parts from files: walk ranges ascend
+// with p there, so "the parts one after another" is the reference's walk order.
 struct FrontEnd {
     std::vector<const phi_index_result *> parts;
     bool from_files;
@@ -44,40 +45,66 @@ inline int32_t member_walk(const phi_index_result *res, uint64_t m)
 }
 
 namespace detail {
-struct Shard {                                     // the views of one GPU: its walks and reads, offsets rebased to 0
+struct Shard {                                     // the views of one GPU: its walks (whole walks or region slices) and reads, offsets rebased to 0
     std::vector<uint64_t> walk_off, read_off;
+    std::vector<uint32_t> walk_vtx;                // region slices only (by-walk shards point into the caller's array)
     phi_graph_view g; phi_reads_view rd;
     uint32_t walk_id_base;
+    bool region; uint64_t coord_lo, coord_hi;
 };
-struct Job { int device, rank, world; const uint8_t *id; uint32_t n_walks_global; Shard *sh; const phi_index_params *prm; phi_index_result *res; int rc; std::string err; };
+struct Job { phi_gpu_index_ctx *ctx; int rank, world; const uint8_t *id; uint32_t n_walks_global; Shard *sh; const phi_index_params *prm; phi_index_result *res; int rc; std::string err; };
 inline void run_job(Job *j)
 {
-    phi_gpu_index_ctx *ctx = 0;
-    j->rc = phi_gpu_index_create(j->device, &ctx);
-    if (j->rc == PHI_OK && j->world > 1) j->rc = phi_gpu_index_comm_init(ctx, j->rank, j->world, j->id, j->sh->walk_id_base, j->n_walks_global);
+    phi_gpu_index_ctx *ctx = j->ctx;
+    j->rc = PHI_OK;
+    if (j->world > 1) j->rc = phi_gpu_index_comm_init(ctx, j->rank, j->world, j->id, j->sh->walk_id_base, j->n_walks_global);
+    if (j->rc == PHI_OK) j->rc = j->sh->region ? phi_gpu_index_set_walk_region(ctx, j->sh->coord_lo, j->sh->coord_hi) : phi_gpu_index_set_walk_region(ctx, 0, ~0ull);
     if (j->rc == PHI_OK) j->rc = phi_gpu_index_run(ctx, &j->sh->g, &j->sh->rd, j->prm, &j->res);
     if (j->rc != PHI_OK) j->err = phi_gpu_last_error(ctx);
-    if (ctx) phi_gpu_index_destroy(ctx);           // the result outlives its ctx (phi_gpu_index_result_free is safe afterwards)
 }
+
+// The ctxs of this process: one per GPU named by PHI_GPU_DEVICES=a,b,c (or PHI_GPU_DEVICE=n, default: the current device).  They are
+// created ONCE, by a thread that starts when the program is loaded, so that CUDA context creation (a few hundred ms) runs under the
+// reference's own GFA / read parsing instead of inside the front end, and they are kept for every later call (all device buffers
+// and the pinned result pool are grow-only members of a ctx: a second call allocates nothing).
+struct Pool {
+    std::vector<int> devices;
+    std::vector<phi_gpu_index_ctx *> ctx;
+    std::vector<int> rc; std::vector<std::string> err;
+    std::thread th; bool started, joined;
+    Pool() : started(false), joined(false) {}
+    ~Pool() { if (started && !joined && th.joinable()) th.join(); }      // (the ctxs themselves live until the process ends)
+    void start()
+    {
+        if (started) return;
+        started = true;
+        if (const char *dl = getenv("PHI_GPU_DEVICES")) {
+            std::string list(dl);
+            for (size_t p = 0; p < list.size();) { size_t c = list.find(',', p); if (c == std::string::npos) c = list.size(); devices.push_back(atoi(list.substr(p, c - p).c_str())); p = c + 1; }
+        }
+        if (devices.empty()) { const char *d = getenv("PHI_GPU_DEVICE"); devices.push_back(d ? atoi(d) : -1); }
+        ctx.assign(devices.size(), (phi_gpu_index_ctx *)0); rc.assign(devices.size(), PHI_OK); err.assign(devices.size(), std::string());
+        th = std::thread([this]() {
+            std::vector<std::thread> each;
+            for (size_t i = 0; i < devices.size(); ++i)
+                each.push_back(std::thread([this, i]() { rc[i] = phi_gpu_index_create(devices[i], &ctx[i]); if (rc[i] != PHI_OK) err[i] = phi_gpu_last_error(0); }));
+            for (size_t i = 0; i < each.size(); ++i) each[i].join();
+        });
+    }
+    void wait() { start(); if (!joined) { th.join(); joined = true; } }
+};
+inline Pool &pool() { static Pool p; return p; }
+struct Warm { Warm() { if (!getenv("PHI_ADAPTER_RESULT_FILE")) pool().start(); } };
+static Warm g_warm;                                // program load: start creating the ctxs
 }  // namespace detail
 
 // Replaces ILP_function lines 543-743 up to the result: runs the library and prints the same stderr lines
 // (:556, :563, :611, :641, :724-735, :738-743) from the returned counters.  The caller frees the result with release().
-// PHI_GPU_DEVICE=n selects the GPU; PHI_GPU_DEVICES=a,b,c runs one ctx per listed GPU in one thread each (walks and reads sharded
-// by phi_shard_split_by_weight, NCCL inside the library) — EXPERIMENTAL: compiled and exercised up to the error path, not yet run on
-// a multi-GPU box (the multi-GPU path proper is measured through one process per GPU, bench.py --gpus N).
+// PHI_GPU_DEVICE=n selects the GPU; PHI_GPU_DEVICES=a,b,c runs one ctx per listed GPU, one host thread each: reads sharded by bases,
+// walks by REGION of the topological coordinate (phi_shard_walk_regions / phi_shard_slice_walks: walk sharing keeps working across
+// GPUs; by whole walks when the graph does not allow a region cut), NCCL inside the library, parts merged by phi_index_result_merge.
 inline FrontEnd run_front_end_result(ILP_index &ix, std::vector<std::pair<std::string, std::string> > &ip_reads, int32_t &count_sp_r)
 {
-    // ---- flat views of the members read_gfa() filled (ILP_index.cpp:20-155)
-    std::vector<uint64_t> seg_off(1, 0), walk_off(1, 0), read_off(1, 0);
-    std::string seg_bases, read_bases;
-    std::vector<uint32_t> walk_vtx;
-    for (uint32_t v = 0; v < ix.n_vtx; ++v) { seg_bases += ix.node_seq[v]; seg_off.push_back(seg_bases.size()); }
-    for (uint32_t h = 0; h < ix.num_walks; ++h) {
-        walk_vtx.insert(walk_vtx.end(), ix.paths[h].begin(), ix.paths[h].end());
-        walk_off.push_back(walk_vtx.size());
-    }
-    for (size_t r = 0; r < ip_reads.size(); ++r) { read_bases += ip_reads[r].second; read_off.push_back(read_bases.size()); }
     phi_index_params prm;
     prm.k = ix.k_mer; prm.w = ix.window; prm.threshold = ix.threshold; prm.debug = ix.debug ? 1 : 0;
 
@@ -94,34 +121,69 @@ inline FrontEnd run_front_end_result(ILP_index &ix, std::vector<std::pair<std::s
     }
 #endif
     if (fe.parts.empty()) {
-        std::vector<int> devices;
-        if (const char *dl = getenv("PHI_GPU_DEVICES")) {
-            std::string list(dl);
-            for (size_t p = 0; p < list.size();) { size_t c = list.find(',', p); if (c == std::string::npos) c = list.size(); devices.push_back(atoi(list.substr(p, c - p).c_str())); p = c + 1; }
-        }
-        if (devices.empty()) { const char *d = getenv("PHI_GPU_DEVICE"); devices.push_back(d ? atoi(d) : -1); }
-        const int W = (int)devices.size();
-        std::vector<uint64_t> wb(W + 1, 0), rb(W + 1, 0);
+        // ---- flat views of the members read_gfa() filled (ILP_index.cpp:20-155): sized once, filled in parallel
+        std::vector<uint64_t> seg_off(ix.n_vtx + 1, 0), walk_off(ix.num_walks + 1, 0), read_off(ip_reads.size() + 1, 0);
+        for (uint32_t v = 0; v < ix.n_vtx; ++v) seg_off[v + 1] = seg_off[v] + ix.node_seq[v].size();
+        for (uint32_t h = 0; h < ix.num_walks; ++h) walk_off[h + 1] = walk_off[h] + ix.paths[h].size();
+        for (size_t r = 0; r < ip_reads.size(); ++r) read_off[r + 1] = read_off[r] + ip_reads[r].second.size();
+        std::string seg_bases(seg_off[ix.n_vtx], '\0'), read_bases(read_off[ip_reads.size()], '\0');
+        std::vector<uint32_t> walk_vtx(walk_off[ix.num_walks]);
+        #pragma omp parallel for schedule(static) num_threads(ix.num_threads > 0 ? ix.num_threads : 1)
+        for (int64_t v = 0; v < (int64_t)ix.n_vtx; ++v) ix.node_seq[v].copy(&seg_bases[seg_off[v]], ix.node_seq[v].size());
+        #pragma omp parallel for schedule(dynamic, 1) num_threads(ix.num_threads > 0 ? ix.num_threads : 1)
+        for (int64_t h = 0; h < (int64_t)ix.num_walks; ++h) std::copy(ix.paths[h].begin(), ix.paths[h].end(), walk_vtx.begin() + walk_off[h]);
+        #pragma omp parallel for schedule(static) num_threads(ix.num_threads > 0 ? ix.num_threads : 1)
+        for (int64_t r = 0; r < (int64_t)ip_reads.size(); ++r) ip_reads[r].second.copy(&read_bases[read_off[r]], ip_reads[r].second.size());
+
+        detail::Pool &P = detail::pool();
+        P.wait();
+        const int W = (int)P.devices.size();
+        for (int r = 0; r < W; ++r)
+            if (P.rc[r] != PHI_OK) { fprintf(stderr, "Error: GPU ILP_index front end failed (%d): %s\n", P.rc[r], P.err[r].c_str()); exit(1); }
+        phi_graph_view gfull;
+        gfull.n_vtx = ix.n_vtx; gfull.seg_off = seg_off.data(); gfull.seg_bases = (const uint8_t *)seg_bases.data();
+        gfull.n_walks = ix.num_walks; gfull.walk_off = walk_off.data(); gfull.walk_vtx = walk_vtx.data(); gfull.top_order_map = ix.top_order_map.data();
+        std::vector<uint64_t> wb(W + 1, 0), rb(W + 1, 0), cb(W + 1, 0);
         wb[W] = ix.num_walks; rb[W] = ip_reads.size();
+        bool by_region = false;
         if (W > 1) {
-            phi_shard_split_by_weight(walk_off.data(), ix.num_walks, W, wb.data());
             phi_shard_split_by_weight(read_off.data(), ip_reads.size(), W, rb.data());
+            by_region = phi_shard_walk_regions(&gfull, W, cb.data()) == PHI_OK;
         }
         uint8_t id[PHI_COMM_ID_BYTES];
         if (W > 1 && phi_gpu_index_comm_unique_id(id) != PHI_OK) { fprintf(stderr, "Error: %s\n", phi_gpu_last_error(0)); exit(1); }
         std::vector<detail::Shard> shards(W);
+        std::vector<uint64_t> sl_first(ix.num_walks), sl_len(ix.num_walks);
+        if (by_region) {
+            for (int r = 0; r < W && by_region; ++r) {
+                detail::Shard &s = shards[r];
+                if (phi_shard_slice_walks(&gfull, prm.k, prm.w, cb[r], cb[r + 1], sl_first.data(), sl_len.data()) != PHI_OK) { by_region = false; break; }
+                s.walk_off.assign(1, 0);
+                for (uint32_t h = 0; h < ix.num_walks; ++h) {
+                    s.walk_vtx.insert(s.walk_vtx.end(), walk_vtx.begin() + sl_first[h], walk_vtx.begin() + sl_first[h] + sl_len[h]);
+                    s.walk_off.push_back(s.walk_vtx.size());
+                }
+                s.region = true; s.coord_lo = cb[r]; s.coord_hi = cb[r + 1]; s.walk_id_base = 0;
+                s.g = gfull; s.g.walk_off = s.walk_off.data(); s.g.walk_vtx = s.walk_vtx.data();
+            }
+        }
+        if (!by_region) {
+            if (W > 1) phi_shard_split_by_weight(walk_off.data(), ix.num_walks, W, wb.data());
+            for (int r = 0; r < W; ++r) {
+                detail::Shard &s = shards[r];
+                s.walk_off.clear(); s.walk_vtx.clear();
+                for (uint64_t h = wb[r]; h <= wb[r + 1]; ++h) s.walk_off.push_back(walk_off[h] - walk_off[wb[r]]);
+                s.region = false; s.coord_lo = 0; s.coord_hi = ~0ull; s.walk_id_base = (uint32_t)wb[r];
+                s.g = gfull; s.g.n_walks = (uint32_t)(wb[r + 1] - wb[r]); s.g.walk_off = s.walk_off.data(); s.g.walk_vtx = walk_vtx.data() + walk_off[wb[r]];
+            }
+        }
         std::vector<detail::Job> jobs(W);
         for (int r = 0; r < W; ++r) {
             detail::Shard &s = shards[r];
-            for (uint64_t h = wb[r]; h <= wb[r + 1]; ++h) s.walk_off.push_back(walk_off[h] - walk_off[wb[r]]);
             for (uint64_t q = rb[r]; q <= rb[r + 1]; ++q) s.read_off.push_back(read_off[q] - read_off[rb[r]]);
-            s.g.n_vtx = ix.n_vtx; s.g.seg_off = seg_off.data(); s.g.seg_bases = (const uint8_t *)seg_bases.data();
-            s.g.n_walks = (uint32_t)(wb[r + 1] - wb[r]); s.g.walk_off = s.walk_off.data(); s.g.walk_vtx = walk_vtx.data() + walk_off[wb[r]];
-            s.g.top_order_map = ix.top_order_map.data();
             s.rd.n_reads = rb[r + 1] - rb[r]; s.rd.read_off = s.read_off.data(); s.rd.read_bases = (const uint8_t *)read_bases.data() + read_off[rb[r]];
-            s.walk_id_base = (uint32_t)wb[r];
             detail::Job &j = jobs[r];
-            j.device = devices[r]; j.rank = r; j.world = W; j.id = id; j.n_walks_global = ix.num_walks; j.sh = &s; j.prm = &prm; j.res = 0; j.rc = PHI_OK;
+            j.ctx = P.ctx[r]; j.rank = r; j.world = W; j.id = id; j.n_walks_global = ix.num_walks; j.sh = &s; j.prm = &prm; j.res = 0; j.rc = PHI_OK;
         }
         if (W == 1) detail::run_job(&jobs[0]);
         else {
@@ -129,12 +191,21 @@ inline FrontEnd run_front_end_result(ILP_index &ix, std::vector<std::pair<std::s
             for (int r = 0; r < W; ++r) th.push_back(std::thread(detail::run_job, &jobs[r]));
             for (int r = 0; r < W; ++r) th[r].join();
         }
+        std::vector<const phi_index_result *> parts;
         for (int r = 0; r < W; ++r) {
             if (jobs[r].rc != PHI_OK) {           // the reference's error style: message on stderr, exit(1) (:105-106)
                 fprintf(stderr, "Error: GPU ILP_index front end failed (%d): %s\n", jobs[r].rc, jobs[r].err.c_str());
                 exit(1);
             }
-            fe.parts.push_back(jobs[r].res);
+            parts.push_back(jobs[r].res);
+        }
+        if (W == 1) fe.parts = parts;
+        else {                                    // one result in the reference's order
+            phi_index_result *merged = 0;
+            const int mrc = phi_index_result_merge(parts.data(), W, &merged);
+            if (mrc != PHI_OK) { fprintf(stderr, "Error: merging the per-GPU results failed (%d)\n", mrc); exit(1); }
+            for (int r = 0; r < W; ++r) phi_gpu_index_result_free(const_cast<phi_index_result *>(parts[r]));
+            fe.parts.push_back(merged);
         }
     }
 

@@ -52,6 +52,38 @@ __device__ __forceinline__ uint64_t murmur3_x64_128_xor(const uint64_t W[4], int
     return h1 ^ h2;
 }
 
+// The same hash over a key of any length whose bytes come from a functor (byte(i), i in [0, len)): k-mers longer than 32 bases and
+// k-mers with non-ACGT bytes are hashed from their spelling (/root/reference/src/MurmurHash3.cpp:255-332: 16-byte blocks as two
+// little-endian u64, then the tail switch, then the finalisation).
+template <class ByteAt>
+__device__ __forceinline__ uint64_t murmur3_x64_128_xor_bytes(ByteAt byte, int len)
+{
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    uint64_t h1 = 0, h2 = 0;
+    const int nblocks = len >> 4;
+    for (int b = 0; b < nblocks; ++b) {
+        uint64_t k1 = 0, k2 = 0;
+        for (int j = 0; j < 8; ++j) { k1 |= (uint64_t)byte(16 * b + j) << (8 * j); k2 |= (uint64_t)byte(16 * b + 8 + j) << (8 * j); }
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    const int rem = len & 15;
+    if (rem) {
+        uint64_t t1 = 0, t2 = 0;
+        for (int j = 0; j < rem && j < 8; ++j) t1 |= (uint64_t)byte(16 * nblocks + j) << (8 * j);
+        for (int j = 8; j < rem; ++j) t2 |= (uint64_t)byte(16 * nblocks + j) << (8 * (j - 8));
+        if (rem > 8) { t2 *= c2; t2 = rotl64(t2, 33); t2 *= c1; h2 ^= t2; }
+        t1 *= c1; t1 = rotl64(t1, 31); t1 *= c2; h1 ^= t1;
+    }
+    h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2; h2 += h1;
+    return h1 ^ h2;
+}
+
 // ::toupper in the C locale (/root/reference/src/ILP_index.cpp:369, :449)
 __device__ __forceinline__ uint32_t upcase(uint32_t c) { return (c - 'a' < 26u) ? c - 32 : c; }
 // upper-cased byte -> is it one of A C G T

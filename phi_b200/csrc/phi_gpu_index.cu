@@ -16,6 +16,7 @@
 #include <mutex>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace phi;
@@ -100,13 +101,18 @@ struct phi_gpu_index_ctx {
     uint64_t *h_words = nullptr; size_t h_words_cap = 0;   // pinned: gathered words of the small collectives
     uint64_t *h_route = nullptr;         // pinned [512]: small host -> device parameter blocks of the record exchange
 
+    std::string err2;                      // error text of the graph-preparation thread (moved into err when its failure is reported)
+    uint64_t launches2 = 0;                // kernels launched by that thread
     int fail(int code, const std::string &m) { err = m; return code; }
+    int fail2(int code, const std::string &m) { err2 = m; return code; }
 };
 
 static std::mutex g_live_mu;                       // live ctxs: a result freed after its ctx releases its pinned buffers itself
 static std::set<phi_gpu_index_ctx *> g_live_ctx;
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx->fail(PHI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+// the same for the graph-preparation thread (its own error text: the main thread may be failing at the same time)
+#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx->fail2(PHI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
 extern "C" int phi_gpu_index_abi_version(void) { return PHI_GPU_INDEX_ABI_VERSION; }
 
@@ -299,6 +305,14 @@ static int bits_for(uint64_t max_value)     // number of bits needed to represen
     return b ? b : 1;
 }
 
+static cudaError_t read_counters_on(phi_gpu_index_ctx *ctx, cudaStream_t st, DevBuf &ctr, unsigned long long *h_ctr)
+{
+    (void)ctx;
+    cudaError_t e = cudaMemcpyAsync(h_ctr, ctr.p, CTR_COUNT * 8, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+}
+
 static cudaError_t read_counters(phi_gpu_index_ctx *ctx)
 {
     cudaError_t e = cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p, CTR_COUNT * 8, cudaMemcpyDeviceToHost, ctx->st);
@@ -336,20 +350,6 @@ struct RunOut {                    // device-side products of one run
 
 }  // namespace
 
-// While alive, the ctx works on the second stream with that stream's own counters and scratch buffers.
-namespace {
-struct PrepScope {
-    phi_gpu_index_ctx *c;
-    explicit PrepScope(phi_gpu_index_ctx *ctx) : c(ctx) { swap(); }
-    ~PrepScope() { swap(); }
-    void swap()
-    {
-        std::swap(c->st, c->st2); std::swap(c->ctr, c->ctr2); std::swap(c->h_ctr, c->h_ctr2);
-        std::swap(c->scan_scr, c->scan_scr2); std::swap(c->flags, c->flags2); std::swap(c->flags64, c->flags64_2); std::swap(c->nv_out, c->nv_out2);
-    }
-};
-}  // namespace
-
 // ---- stage: graph preparation: step base offsets, walk lengths, then the chunk table and the tiles of the representative
 // chunks (depends on k and w through the chunk context)
 static ChunkTable chunk_table(phi_gpu_index_ctx *ctx)
@@ -368,118 +368,123 @@ static ChunkTable chunk_table(phi_gpu_index_ctx *ctx)
 static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<uint64_t> &h_walk_len, const uint32_t *&d_walk_vtx,
                             const uint64_t *&d_walk_off, uint64_t &n_steps_eff, int &walks_monotone)
 {
-    PrepScope on_second_stream(ctx);                                    // everything below: ctx->st is the second stream
+    // Runs on its own host thread (run_pipeline) next to the read stage and the spectrum exchange: it touches the second stream, that
+    // stream's counter block and scratch buffers and the graph-side buffers only, counts its launches apart and keeps its own error text.
+    cudaStream_t st = ctx->st2;
+    DevBuf &ctr = ctx->ctr2, &scan_scr = ctx->scan_scr2, &flags = ctx->flags2, &flags64 = ctx->flags64_2;
+    unsigned long long *h_ctr = ctx->h_ctr2;
+    uint64_t *launches = &ctx->launches2;
     walks_monotone = 1;
     const uint32_t H = ctx->n_walks, V = ctx->n_vtx; uint64_t S = ctx->n_steps;
     d_walk_vtx = ctx->walk_vtx.as<uint32_t>(); d_walk_off = ctx->walk_off.as<uint64_t>(); n_steps_eff = S;
     h_walk_len.assign(H, 0);
     ctx->n_chunks = ctx->n_tiles = 0; ctx->unique_windows = ctx->active_chunks = ctx->rep_chunks = ctx->path_pos = 0;
-    unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
-    if (ctx->n_pieces) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_graph_in, 0));   // phi_gpu_index_run: the graph is still on the wire
-    CU(cudaEventRecord(ctx->ev[EV_PREP0], ctx->st));
-    CU(cudaMemsetAsync(ctx->ctr.p, 0, CTR_COUNT * 8, ctx->st));
-    memset(ctx->h_ctr, 0, CTR_COUNT * 8);
+    unsigned long long *d_ctr = ctr.as<unsigned long long>();
+    if (ctx->n_pieces) CUP(cudaStreamWaitEvent(st, ctx->ev_graph_in, 0));   // phi_gpu_index_run: the graph is still on the wire
+    CUP(cudaEventRecord(ctx->ev[EV_PREP0], st));
+    CUP(cudaMemsetAsync(ctr.p, 0, CTR_COUNT * 8, st));
+    memset(h_ctr, 0, CTR_COUNT * 8);
     if (!H || !S) return PHI_OK;
-    if (S >= 0xFFFFFFFFull) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-2 walk steps on one GPU; shard the walks over more GPUs");
+    if (S >= 0xFFFFFFFFull) return ctx->fail2(PHI_ERR_UNSUPPORTED, "more than 2^32-2 walk steps on one GPU; shard the walks over more GPUs");
     // topological base coordinate of every vertex (chunk boundaries are defined on it)
-    CU(ctx->tlen.reserve((size_t)V * 4 + 4)); CU(ctx->tprefix.reserve(((size_t)V + 1) * 8)); CU(ctx->coord.reserve((size_t)V * 16 + 16));
-    CU(ctx->scan_scr.reserve(std::max({scan_u32_to_u64_scratch((uint64_t)V + 1), scan_u32_to_u64_scratch(S + 1), (size_t)1024})));
-    CU(chunk_topo_coord(ctx->top_order.as<int32_t>(), ctx->seg_off.as<uint64_t>(), V, ctx->chunk_shift, ctx->own_lo, ctx->own_hi, ctx->tlen.as<uint32_t>(),
-                        ctx->tprefix.as<uint64_t>(), ctx->coord.as<uint4>(), ctx->scan_scr.p, d_ctr, ctx->st, &ctx->launches));
+    CUP(ctx->tlen.reserve((size_t)V * 4 + 4)); CUP(ctx->tprefix.reserve(((size_t)V + 1) * 8)); CUP(ctx->coord.reserve((size_t)V * 16 + 16));
+    CUP(scan_scr.reserve(std::max({scan_u32_to_u64_scratch((uint64_t)V + 1), scan_u32_to_u64_scratch(S + 1), (size_t)1024})));
+    CUP(chunk_topo_coord(ctx->top_order.as<int32_t>(), ctx->seg_off.as<uint64_t>(), V, ctx->chunk_shift, ctx->own_lo, ctx->own_hi, ctx->tlen.as<uint32_t>(),
+                        ctx->tprefix.as<uint64_t>(), ctx->coord.as<uint4>(), scan_scr.p, d_ctr, st, launches));
     // common case: one kernel for step lengths, chunk flags, their scan, step bases, walk lengths and the chunk starts
     const uint64_t S0 = S;
-    CU(ctx->step_base.reserve(S * 4 + 4)); CU(ctx->walk_len.reserve((size_t)H * 8 + 8));
-    CU(ctx->chunk_step.reserve((S + 2) * 4)); CU(ctx->c_walk.reserve((S + 2) * 4));       // at most one chunk per step
-    CU(ctx->fs_state.reserve(walk_steps_fused_tiles(S) * 8 + 16));
-    CU(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, ctx->st)); CU(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, ctx->st));
+    CUP(ctx->step_base.reserve(S * 4 + 4)); CUP(ctx->walk_len.reserve((size_t)H * 8 + 8));
+    CUP(ctx->chunk_step.reserve((S + 2) * 4)); CUP(ctx->c_walk.reserve((S + 2) * 4));       // at most one chunk per step
+    CUP(ctx->fs_state.reserve(walk_steps_fused_tiles(S) * 8 + 16));
+    CUP(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, st)); CUP(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, st));
     if (ctx->n_pieces && ctx->n_wpieces > 1) {
         // phi_gpu_index_run: the walk steps are still arriving; every piece is scanned as soon as it is there
         const uint64_t tile = walk_steps_fused_tile_steps();
         uint64_t t0 = 0;
         for (int p = 0; p < ctx->n_wpieces; ++p) {
-            CU(cudaStreamWaitEvent(ctx->st, ctx->ev_wpiece[p], 0));
+            CUP(cudaStreamWaitEvent(st, ctx->ev_wpiece[p], 0));
             const uint64_t t1 = p + 1 == ctx->n_wpieces ? walk_steps_fused_tiles(S) : ctx->wpiece_end[p] / tile;
             if (t1 > t0 || p == 0)
-                CU(walk_steps_fused(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), V, ctx->fs_state.as<unsigned long long>() + 1, ctx->fs_state.as<uint32_t>(),
+                CUP(walk_steps_fused(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), V, ctx->fs_state.as<unsigned long long>() + 1, ctx->fs_state.as<uint32_t>(),
                                     ctx->step_base.as<uint32_t>(), ctx->chunk_step.as<uint32_t>(), ctx->c_walk.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), d_ctr,
-                                    ctx->st, &ctx->launches, t0, t1));
+                                    st, launches, t0, t1));
             t0 = std::max(t0, t1);
         }
     } else {
-        if (ctx->n_pieces) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_wpiece[ctx->n_wpieces - 1], 0));
-        CU(walk_steps_fused(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), V, ctx->fs_state.as<unsigned long long>() + 1, ctx->fs_state.as<uint32_t>(),
+        if (ctx->n_pieces) CUP(cudaStreamWaitEvent(st, ctx->ev_wpiece[ctx->n_wpieces - 1], 0));
+        CUP(walk_steps_fused(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), V, ctx->fs_state.as<unsigned long long>() + 1, ctx->fs_state.as<uint32_t>(),
                             ctx->step_base.as<uint32_t>(), ctx->chunk_step.as<uint32_t>(), ctx->c_walk.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), d_ctr,
-                            ctx->st, &ctx->launches));
+                            st, launches));
     }
-    CU(read_counters(ctx));                                             // wait 1
-    if (ctx->h_ctr[CTR_BAD_VTX]) return ctx->fail(PHI_ERR_ARG, "graph view: a walk step names a vertex id >= n_vtx");
-    if (ctx->h_ctr[CTR_SEG_TOO_LONG]) return ctx->fail(PHI_ERR_UNSUPPORTED, "segment of 2^31 bases or more");
-    const bool fused = ctx->h_ctr[CTR_ZERO_STEPS] == 0;
+    CUP(read_counters_on(ctx, st, ctr, h_ctr));                                             // wait 1
+    if (h_ctr[CTR_BAD_VTX]) return ctx->fail2(PHI_ERR_ARG, "graph view: a walk step names a vertex id >= n_vtx");
+    if (h_ctr[CTR_SEG_TOO_LONG]) return ctx->fail2(PHI_ERR_UNSUPPORTED, "segment of 2^31 bases or more");
+    const bool fused = h_ctr[CTR_ZERO_STEPS] == 0;
     uint64_t last = 0; uint32_t NC = 0;
     // zero-length segments contribute no bases (ILP_index.cpp:364-381): the general path drops their steps and looks at the walks again
-    if (!fused) { CU(ctx->step_len.reserve(S * 4 + 4)); CU(ctx->gbase.reserve((S + 1) * 8)); CU(cudaMemsetAsync(d_ctr + CTR_NONMONO, 0, 8, ctx->st)); }
+    if (!fused) { CUP(ctx->step_len.reserve(S * 4 + 4)); CUP(ctx->gbase.reserve((S + 1) * 8)); CUP(cudaMemsetAsync(d_ctr + CTR_NONMONO, 0, 8, st)); }
     for (int attempt = 0; !fused; ++attempt) {
-        CU(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, ctx->st)); CU(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, ctx->st));
-        CU(walk_step_pass(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), V, ctx->step_len.as<PackedStep>(), d_ctr, ctx->st, &ctx->launches));
-        CU(scan_packed_steps(ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), S, ctx->scan_scr.p, ctx->st, &ctx->launches));
-        CU(cudaMemcpyAsync(&last, ctx->gbase.as<uint64_t>() + (S - 1), 8, cudaMemcpyDeviceToHost, ctx->st));
-        CU(read_counters(ctx));
-        if (!ctx->h_ctr[CTR_ZERO_STEPS] || attempt) break;
-        const uint64_t kept = S - ctx->h_ctr[CTR_ZERO_STEPS];
-        CU(ctx->flags.reserve(S * 4 + 4)); CU(ctx->flags64.reserve((S + 1) * 8));
-        CU(ctx->walk_vtx_c.reserve(kept * 4 + 4)); CU(ctx->walk_off_c.reserve(((size_t)H + 1) * 8));
-        CU(walk_compact_steps(d_walk_vtx, d_walk_off, H, S, ctx->step_len.as<PackedStep>(), ctx->flags.as<uint32_t>(), ctx->flags64.as<uint64_t>(),
-                              ctx->scan_scr.p, kept, ctx->walk_vtx_c.as<uint32_t>(), ctx->walk_off_c.as<uint64_t>(), ctx->st, &ctx->launches));
+        CUP(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, st)); CUP(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, st));
+        CUP(walk_step_pass(d_walk_vtx, d_walk_off, H, S, ctx->coord.as<uint4>(), V, ctx->step_len.as<PackedStep>(), d_ctr, st, launches));
+        CUP(scan_packed_steps(ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), S, scan_scr.p, st, launches));
+        CUP(cudaMemcpyAsync(&last, ctx->gbase.as<uint64_t>() + (S - 1), 8, cudaMemcpyDeviceToHost, st));
+        CUP(read_counters_on(ctx, st, ctr, h_ctr));
+        if (!h_ctr[CTR_ZERO_STEPS] || attempt) break;
+        const uint64_t kept = S - h_ctr[CTR_ZERO_STEPS];
+        CUP(flags.reserve(S * 4 + 4)); CUP(flags64.reserve((S + 1) * 8));
+        CUP(ctx->walk_vtx_c.reserve(kept * 4 + 4)); CUP(ctx->walk_off_c.reserve(((size_t)H + 1) * 8));
+        CUP(walk_compact_steps(d_walk_vtx, d_walk_off, H, S, ctx->step_len.as<PackedStep>(), flags.as<uint32_t>(), flags64.as<uint64_t>(),
+                              scan_scr.p, kept, ctx->walk_vtx_c.as<uint32_t>(), ctx->walk_off_c.as<uint64_t>(), st, launches));
         d_walk_vtx = ctx->walk_vtx_c.as<uint32_t>(); d_walk_off = ctx->walk_off_c.as<uint64_t>(); n_steps_eff = S = kept;
-        CU(cudaMemsetAsync(d_ctr + CTR_NONMONO, 0, 8, ctx->st));
+        CUP(cudaMemsetAsync(d_ctr + CTR_NONMONO, 0, 8, st));
         if (!S) return PHI_OK;
     }
     (void)S0;
-    walks_monotone = ctx->h_ctr[CTR_NONMONO] ? 0 : 1;
-    if (ctx->h_ctr[CTR_CHUNK_FLAGS] >= (1ull << (64 - STEP_BASE_BITS)))
-        return ctx->fail(PHI_ERR_UNSUPPORTED, "too many walk chunks on one GPU: raise chunk_shift (phi_gpu_index_set_walk_sharing) or shard the walks");
-    NC = (uint32_t)ctx->h_ctr[CTR_CHUNK_FLAGS];
+    walks_monotone = h_ctr[CTR_NONMONO] ? 0 : 1;
+    if (h_ctr[CTR_CHUNK_FLAGS] >= (1ull << (64 - STEP_BASE_BITS)))
+        return ctx->fail2(PHI_ERR_UNSUPPORTED, "too many walk chunks on one GPU: raise chunk_shift (phi_gpu_index_set_walk_sharing) or shard the walks");
+    NC = (uint32_t)h_ctr[CTR_CHUNK_FLAGS];
     (void)last;
     ctx->n_chunks = NC;
     DevBuf *u32s[] = {&ctx->chunk_step, &ctx->c_walk, &ctx->c_L, &ctx->c_R, &ctx->c_lo, &ctx->c_hi, &ctx->c_slot, &ctx->c_rep, &ctx->c_ninst,
                       &ctx->c_ntile, &ctx->c_tile_base, &ctx->c_emitted, &ctx->c_hits, &ctx->c_surv, &ctx->c_surv_vtx};
-    for (DevBuf *b : u32s) CU(b->reserve(((size_t)NC + 2) * 4));
-    CU(ctx->c_h1.reserve(((size_t)NC + 1) * 8)); CU(ctx->c_h2.reserve(((size_t)NC + 1) * 8));
-    CU(ctx->member_cnt.reserve(((size_t)NC + 2) * 4)); CU(ctx->member_off.reserve(((size_t)NC + 2) * 8));
+    for (DevBuf *b : u32s) CUP(b->reserve(((size_t)NC + 2) * 4));
+    CUP(ctx->c_h1.reserve(((size_t)NC + 1) * 8)); CUP(ctx->c_h2.reserve(((size_t)NC + 1) * 8));
+    CUP(ctx->member_cnt.reserve(((size_t)NC + 2) * 4)); CUP(ctx->member_off.reserve(((size_t)NC + 2) * 8));
     ChunkTable C = chunk_table(ctx);
     if (!fused)
-        CU(walk_step_finalize(C, ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), d_walk_off, H, S, ctx->step_base.as<uint32_t>(),
-                              ctx->walk_len.as<uint64_t>(), ctx->st, &ctx->launches));
-    CU(cudaMemcpyAsync(h_walk_len.data(), ctx->walk_len.p, (size_t)H * 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(chunk_keys(C, d_walk_vtx, d_walk_off, ctx->step_base.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), ctx->coord.as<uint4>(), k, w, d_ctr, ctx->st, &ctx->launches));
+        CUP(walk_step_finalize(C, ctx->step_len.as<PackedStep>(), ctx->gbase.as<uint64_t>(), d_walk_off, H, S, ctx->step_base.as<uint32_t>(),
+                              ctx->walk_len.as<uint64_t>(), st, launches));
+    CUP(cudaMemcpyAsync(h_walk_len.data(), ctx->walk_len.p, (size_t)H * 8, cudaMemcpyDeviceToHost, st));
+    CUP(chunk_keys(C, d_walk_vtx, d_walk_off, ctx->step_base.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), ctx->coord.as<uint4>(), k, w, d_ctr, st, launches));
     uint32_t tcap = 1024; while (tcap < 2 * (uint64_t)NC) tcap <<= 1;
-    CU(ctx->ctable.reserve((size_t)tcap * 4));
-    CU(ctx->scan_scr.reserve(std::max(scan_u32_scratch((uint64_t)NC + 2), scan_u32_to_u64_scratch((uint64_t)NC + 2))));
+    CUP(ctx->ctable.reserve((size_t)tcap * 4));
+    CUP(scan_scr.reserve(std::max(scan_u32_scratch((uint64_t)NC + 2), scan_u32_to_u64_scratch((uint64_t)NC + 2))));
     for (int dedupe = ctx->dedupe ? 1 : 0;; dedupe = 0) {
-        CU(cudaMemsetAsync(d_ctr + CTR_UNIQUE_WINDOWS, 0, 2 * 8, ctx->st));               // UNIQUE_WINDOWS, DEDUPE_MISMATCH
-        CU(chunk_group(C, ctx->ctable.as<uint32_t>(), tcap, d_walk_vtx, dedupe, w, d_ctr, ctx->st, &ctx->launches));
-        CU(cudaMemsetAsync(ctx->c_ntile.as<uint32_t>() + NC, 0, 4, ctx->st));
-        CU(scan_u32(ctx->c_ntile.as<uint32_t>(), ctx->c_tile_base.as<uint32_t>(), (uint64_t)NC + 1, ctx->scan_scr.p, ctx->st, &ctx->launches));
+        CUP(cudaMemsetAsync(d_ctr + CTR_UNIQUE_WINDOWS, 0, 2 * 8, st));               // UNIQUE_WINDOWS, DEDUPE_MISMATCH
+        CUP(chunk_group(C, ctx->ctable.as<uint32_t>(), tcap, d_walk_vtx, dedupe, w, d_ctr, st, launches));
+        CUP(cudaMemsetAsync(ctx->c_ntile.as<uint32_t>() + NC, 0, 4, st));
+        CUP(scan_u32(ctx->c_ntile.as<uint32_t>(), ctx->c_tile_base.as<uint32_t>(), (uint64_t)NC + 1, scan_scr.p, st, launches));
         uint32_t n_tiles = 0;
-        CU(cudaMemcpyAsync(&n_tiles, ctx->c_tile_base.as<uint32_t>() + NC, 4, cudaMemcpyDeviceToHost, ctx->st));
-        CU(read_counters(ctx));                                         // wait 2 (also: walk lengths)
+        CUP(cudaMemcpyAsync(&n_tiles, ctx->c_tile_base.as<uint32_t>() + NC, 4, cudaMemcpyDeviceToHost, st));
+        CUP(read_counters_on(ctx, st, ctr, h_ctr));                                         // wait 2 (also: walk lengths)
         ctx->n_tiles = n_tiles;
-        if (!dedupe || !ctx->h_ctr[CTR_DEDUPE_MISMATCH]) break;          // a fingerprint collision: sketch every chunk on its own
+        if (!dedupe || !h_ctr[CTR_DEDUPE_MISMATCH]) break;          // a fingerprint collision: sketch every chunk on its own
     }
     uint64_t total_bases = 0;
     for (uint32_t h = 0; h < H; ++h) {
-        if (h_walk_len[h] >= (1ull << 31)) return ctx->fail(PHI_ERR_UNSUPPORTED, "walk longer than 2^31-1 bases (the reference's int32 position loop overflows there too)");
+        if (h_walk_len[h] >= (1ull << 31)) return ctx->fail2(PHI_ERR_UNSUPPORTED, "walk longer than 2^31-1 bases (the reference's int32 position loop overflows there too)");
         total_bases += h_walk_len[h];
     }
-    if (total_bases >= (1ull << STEP_BASE_BITS)) return ctx->fail(PHI_ERR_UNSUPPORTED, "2^38 or more walk bases on one GPU; shard the walks over more GPUs");
-    ctx->unique_windows = ctx->h_ctr[CTR_UNIQUE_WINDOWS]; ctx->active_chunks = ctx->h_ctr[CTR_ACTIVE_CHUNKS]; ctx->path_pos = ctx->h_ctr[CTR_PATH_POS];
-    CU(ctx->tiles.reserve((size_t)ctx->n_tiles * sizeof(TileRec) + 32));
-    CU(chunk_tiles(C, d_walk_off, ctx->step_base.as<uint32_t>(), w, ctx->tiles.as<TileRec>(), ctx->st, &ctx->launches));
+    if (total_bases >= (1ull << STEP_BASE_BITS)) return ctx->fail2(PHI_ERR_UNSUPPORTED, "2^38 or more walk bases on one GPU; shard the walks over more GPUs");
+    ctx->unique_windows = h_ctr[CTR_UNIQUE_WINDOWS]; ctx->active_chunks = h_ctr[CTR_ACTIVE_CHUNKS]; ctx->path_pos = h_ctr[CTR_PATH_POS];
+    CUP(ctx->tiles.reserve((size_t)ctx->n_tiles * sizeof(TileRec) + 32));
+    CUP(chunk_tiles(C, d_walk_off, ctx->step_base.as<uint32_t>(), w, ctx->tiles.as<TileRec>(), st, launches));
     // member walks of every representative (the grouped result copies them instead of instantiating one record per member)
     DevBuf *cms[] = {&ctx->fs_state, &ctx->cm_off, &ctx->cm_cursor, &ctx->cm_tmp, &ctx->cm_walk};
-    for (DevBuf *b : cms) CU(b->reserve(((size_t)NC + 2) * 4));
-    CU(chunk_members(C, H, ctx->cm_off.as<uint32_t>(), ctx->cm_cursor.as<uint32_t>(), ctx->cm_tmp.as<uint32_t>(), ctx->cm_walk.as<uint32_t>(),
-                     ctx->scan_scr.p, ctx->st, &ctx->launches));
+    for (DevBuf *b : cms) CUP(b->reserve(((size_t)NC + 2) * 4));
+    CUP(chunk_members(C, H, ctx->cm_off.as<uint32_t>(), ctx->cm_cursor.as<uint32_t>(), ctx->cm_tmp.as<uint32_t>(), ctx->cm_walk.as<uint32_t>(),
+                     scan_scr.p, st, launches));
     return PHI_OK;
 }
 
@@ -1419,7 +1424,7 @@ static int validate_params(phi_gpu_index_ctx *ctx, const phi_index_params *p)
 {
     if (!p) return ctx->fail(PHI_ERR_ARG, "params is NULL");
     if (p->k < 1 || p->w < 1) return ctx->fail(PHI_ERR_ARG, "k and w must be >= 1");
-    if (p->k > 32) return ctx->fail(PHI_ERR_UNSUPPORTED, "k > 32 is not implemented on the GPU path (packed 2-bit k-mers); refusing rather than diverging");
+    if (p->k > 255) return ctx->fail(PHI_ERR_UNSUPPORTED, "k > 255 is not implemented on the GPU path (vertex lists carry a one-byte length); refusing rather than diverging");
     if (p->w > 256) return ctx->fail(PHI_ERR_UNSUPPORTED, "w > 256 is not implemented on the GPU path");
     return PHI_OK;
 }
@@ -1488,13 +1493,26 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
         CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st)); CU(cudaEventRecord(ctx->ev[EV_RK1], ctx->st));
         CU(cudaEventRecord(ctx->ev[EV_READS], ctx->st));
     }
-    // ... while the second stream prepares the graph (its host-side waits only cover that stream)
-    rc = stage_graph_prep(ctx, k, w, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone);
-    if (rc) { if (ctx->world == 1 || mode != WALK_MODE_PROBE) return rc; if (!status) status = rc; }
-    CU(cudaEventRecord(ctx->ev[EV_PREP], ctx->st2));
+    // ... while a second host thread prepares the graph on the second stream: its host-side waits (number of chunks, number of
+    // tiles) and the main thread's (spectrum size, and with several GPUs the whole spectrum exchange) no longer queue up behind each other
+    int rc_prep = PHI_OK;
+    ctx->launches2 = 0;
+    std::thread prep([&]() {
+        cudaSetDevice(ctx->device);
+        rc_prep = stage_graph_prep(ctx, k, w, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone);
+        if (!rc_prep && cudaEventRecord(ctx->ev[EV_PREP], ctx->st2) != cudaSuccess) rc_prep = ctx->fail2(PHI_ERR_CUDA, "cudaEventRecord failed");
+    });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner = {prep};   // every return path waits for the thread
     if (mode == WALK_MODE_PROBE) {
         rc = stage_reads_finish(ctx, k, w, rs, o, dbits, status);
         if (rc) return rc;
+    }
+    prep.join();
+    ctx->launches += ctx->launches2;
+    if (rc_prep) {                                                         // (several GPUs: reported through the record exchange, all ranks stop together)
+        ctx->err = ctx->err2;
+        if (ctx->world == 1 || mode != WALK_MODE_PROBE) return rc_prep;
+        status = rc_prep;
     }
     // the result starts to travel as soon as its parts exist: the spectrum goes out on the copy stream under the walk stage
     struct ResGuard { phi_index_result *r; ~ResGuard() { if (r) phi_gpu_index_result_free(r); } } guard = {alloc_result(ctx)};
@@ -1511,8 +1529,10 @@ static int run_pipeline(phi_gpu_index_ctx *ctx, const phi_index_params *prm, int
     }
     CU(cudaEventRecord(ctx->ev[EV_SPECTRUM], ctx->st));
     CU(cudaStreamWaitEvent(ctx->st, ctx->ev[EV_PREP], 0));               // the walk stage needs both
-    rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, o);
-    if (rc) { if (ctx->world == 1 || mode != WALK_MODE_PROBE) return rc; status = rc; }
+    if (!status) {
+        rc = stage_walks(ctx, k, w, mode, dbits, h_walk_len, d_walk_vtx, d_walk_off, n_steps_eff, walks_monotone, o);
+        if (rc) { if (ctx->world == 1 || mode != WALK_MODE_PROBE) return rc; status = rc; }
+    }
     CU(cudaEventRecord(ctx->ev[EV_WALKS], ctx->st));
 
     const uint32_t H = ctx->n_walks;
@@ -1649,7 +1669,7 @@ extern "C" int phi_gpu_index_last_times(const phi_gpu_index_ctx *ctx, phi_stage_
 
 extern "C" int phi_gpu_hash128_to_64(phi_gpu_index_ctx *ctx, const uint8_t *keys, uint64_t n, int32_t len, uint64_t *out)
 {
-    if (!ctx || !keys || !out || len < 1 || len > 32) return ctx ? ctx->fail(PHI_ERR_ARG, "bad arguments (len must be 1..32)") : PHI_ERR_ARG;
+    if (!ctx || !keys || !out || len < 1 || len > 255) return ctx ? ctx->fail(PHI_ERR_ARG, "bad arguments (len must be 1..255)") : PHI_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     DevBuf dk, dout;
     CU(dk.reserve(n * len)); CU(dout.reserve(n * 8));

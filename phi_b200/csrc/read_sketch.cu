@@ -110,7 +110,7 @@ read_sketch_kernel(ReadSketchArgs A)
     }
     // a tile is CLEAN when every staged byte that a valid window can touch is A/C/G/T; padding at either end of
     // the data counts as dirty and sends the (few) boundary tiles through the general path
-    if (__syncthreads_or(dirty_any != 0)) read_tile_body<false, false>(t, A);
+    if (__syncthreads_or(dirty_any != 0 || A.k > MAX_PACKED_K)) read_tile_body<false, false>(t, A);
     else if (tile_fast_w(A.w)) read_tile_body<true, true>(t, A);
     else read_tile_body<true, false>(t, A);
 }

@@ -35,7 +35,8 @@ namespace {   // every translation unit gets its own copy, specialised for its t
 constexpr int NT = PHI_TILE_THREADS;                   // threads per tile CTA
 constexpr int TILE_W = TILE_WINDOWS_PER_THREAD * NT;   // windows per tile on the general path
 constexpr int MAX_W = 256;
-constexpr int MAX_K = 32;
+constexpr int MAX_K = 255;                             // k-mers of up to 32 bases are packed 2-bit; longer ones are compared and hashed byte-wise
+constexpr int MAX_PACKED_K = 32;
 
 constexpr uint8_t F_STRAND = 1;  // canonical == reverse complement
 constexpr uint8_t F_DIRTY = 2;   // k-mer contains a non-ACGT byte (or padding)
@@ -196,12 +197,8 @@ __device__ __forceinline__ bool canon_lt(const Tile &t, int a, uint64_t va, uint
 // hash128_to_64 of the canonical k-mer at local position a
 __device__ __noinline__ uint64_t hash_dirty(const Tile &t, int a, int strand)
 {
-    uint64_t W[4] = {0, 0, 0, 0};
-    for (int j = 0; j < t.k; ++j) {
-        uint64_t c = strand ? comp_byte(t.base[a + t.k - 1 - j]) : t.base[a + j];
-        W[j >> 3] |= c << (8 * (j & 7));
-    }
-    return murmur3_x64_128_xor(W, t.k);
+    const uint8_t *base = t.base; const int k = t.k;
+    return murmur3_x64_128_xor_bytes([&](int j) -> uint32_t { return strand ? comp_byte(base[a + k - 1 - j]) : (uint32_t)base[a + j]; }, k);
 }
 template <bool CLEAN>
 __device__ __forceinline__ uint64_t hash_at(const Tile &t, int a)
@@ -222,6 +219,19 @@ __device__ __forceinline__ void phase_canon(const Tile &t)
     const int top = 2 * (k - 1);
     for (int g8 = threadIdx.x; g8 < t.M8 / 8; g8 += NT) {
         const int p0 = 8 * g8;
+        if (!CLEAN && k > MAX_PACKED_K) {
+            // long k-mers: every one is spelled out (the tile is treated like one full of non-ACGT bytes: byte-wise compare and hash)
+            uint64_t fl = 0;
+            #pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                const int c = cmp_canon_bytes(t, p0 + i, 1, p0 + i, 0);        // std::min(fwd, rev): rev only if strictly smaller (:394)
+                fl |= (uint64_t)(F_DIRTY | (c < 0 ? F_STRAND : 0)) << (8 * i);
+            }
+            *(uint64_t *)(t.flag + p0) = fl;
+            ulonglong2 *dst = (ulonglong2 *)(t.canon + cidx(p0));
+            dst[0] = dst[1] = dst[2] = dst[3] = make_ulonglong2(0ull, 0ull);
+            continue;
+        }
         uint64_t fwd = extract_kmer(t.pack, p0, k);
         uint64_t rc = revcomp2(fwd, k);
         const uint32_t nxt = extract8(t.pack, p0 + k);                 // bases entering at steps 1..7 (+1 spare)

@@ -211,7 +211,7 @@ __device__ __forceinline__ void walk_sketch_body(const WalkSketchArgs &A)
         t.cfirst[c] = (uint16_t)first; t.cmask[c] = (uint8_t)smask;
         dirty_any |= stage_chunk(t, c, v);
     }
-    if (__syncthreads_or(dirty_any != 0)) walk_tile_body<false, false>(t, A, tr, tile);
+    if (__syncthreads_or(dirty_any != 0 || A.k > MAX_PACKED_K)) walk_tile_body<false, false>(t, A, tr, tile);
     else if (tile_fast_w(A.w)) walk_tile_body<true, true>(t, A, tr, tile);
     else walk_tile_body<true, false>(t, A, tr, tile);
 }
@@ -228,11 +228,15 @@ __global__ void hash_bytes_kernel(const uint8_t *keys, uint64_t n, int len, uint
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint8_t *p = keys + i * (uint64_t)len;
-    uint64_t W[4] = {0, 0, 0, 0};
     bool clean = true;
-    for (int j = 0; j < len; ++j) { W[j >> 3] |= (uint64_t)p[j] << (8 * (j & 7)); clean &= is_acgt(p[j]); }
-    uint64_t h = murmur3_x64_128_xor(W, len);
-    if (clean) {                                                      // cross-check the packed path used by the sketch kernels
+    for (int j = 0; j < len; ++j) clean &= is_acgt(p[j]);
+    uint64_t h = murmur3_x64_128_xor_bytes([&](int j) -> uint32_t { return p[j]; }, len);
+    if (len <= 32) {                                                  // the word form used for short keys must agree
+        uint64_t W[4] = {0, 0, 0, 0};
+        for (int j = 0; j < len; ++j) W[j >> 3] |= (uint64_t)p[j] << (8 * (j & 7));
+        if (murmur3_x64_128_xor(W, len) != h) h = ~h;
+    }
+    if (clean && len <= 32) {                                         // cross-check the packed path used by the sketch kernels
         uint64_t km = 0;
         for (int j = 0; j < len; ++j) km = (km << 2) | code2(p[j]);
         uint64_t h2 = hash_packed_kmer(km, len);
@@ -248,7 +252,7 @@ cudaError_t launch_walk_sketch(const WalkSketchArgs &A, uint32_t n_tiles, cudaSt
     if (!n_tiles) return cudaSuccess;
     size_t smem = (size_t)A.layout.bytes;
     static int ctas = 0;
-    if (!ctas) { const char *e = getenv("PHI_GPU_WALK_CTAS"); ctas = e ? atoi(e) : 6; if (ctas < 6 || ctas > 8) ctas = 6; }
+    if (!ctas) { const char *e = getenv("PHI_GPU_WALK_CTAS"); ctas = e ? atoi(e) : 8; if (ctas < 6 || ctas > 8) ctas = 8; }
     auto kern = ctas == 8 ? walk_sketch_kernel_r64 : ctas == 7 ? walk_sketch_kernel_r72 : walk_sketch_kernel;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -58,3 +58,29 @@ def test_patched_reference_dumps_the_identical_model(tmp_path, name, extra):
             h_gpu = hashlib.sha256(open(d_gpu, "rb").read()).hexdigest()
             assert h_ref == h_gpu, f"model dump of {os.path.basename(exe)} differs for -q{q}"
             assert scraped(e_ref) == scraped(e_gpu)
+
+
+@pytest.mark.parametrize("name,extra", [("synth_small", []), ("synth_dirty", ["-T", "0.5"]), ("synth_repeats", []), ("mhc4", [])])
+def test_patched_reference_on_several_gpus_dumps_the_identical_model(tmp_path, name, extra):
+    """PHI_GPU_DEVICES=0,1[,..]: the adapter runs one ctx per GPU (host thread each), walks sharded by region, reads by bases, the
+    parts merged by phi_index_result_merge — the model dump must not change."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    if not (os.path.exists(REF) and os.path.exists(GPU)):
+        pytest.skip("oracle/_ref/PHI_ref / PHI_gpu not built")
+    c = Case(name)
+    gfa, fa = str(tmp_path / "g.gfa"), str(tmp_path / "r.fa")
+    synth.write_gfa(c.graph, gfa)
+    synth.write_fasta(c.reads, fa)
+    d_ref, d_gpu = str(tmp_path / "ref.dump"), str(tmp_path / "gpu.dump")
+    e_ref = run(REF, gfa, fa, d_ref, extra)
+    os.environ["PHI_GPU_DEVICES"] = ",".join(str(i) for i in range(min(n, 4)))
+    try:
+        for exe in (GPU, GPU_MODEL):
+            e_gpu = run(exe, gfa, fa, d_gpu, extra)
+            assert hashlib.sha256(open(d_ref, "rb").read()).hexdigest() == hashlib.sha256(open(d_gpu, "rb").read()).hexdigest(), os.path.basename(exe)
+            assert scraped(e_ref) == scraped(e_gpu)
+    finally:
+        del os.environ["PHI_GPU_DEVICES"]

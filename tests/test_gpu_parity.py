@@ -23,7 +23,7 @@ def test_device_murmur_known_answers(gpu):
     for key, want in KAT.items():
         assert int(gpu.hash128_to_64(key, len(key))[0]) == want, key
     rng = np.random.default_rng(7)
-    for ln in range(1, 33):                       # every length the packed path supports, clean and dirty keys
+    for ln in list(range(1, 50)) + [63, 64, 65, 100, 255]:   # packed path (<= 32), word path and byte path, clean and dirty keys
         keys = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, (64, ln))]
         keys[32:, rng.integers(0, ln)] = ord("N")
         got = gpu.hash128_to_64(keys.tobytes(), ln)
@@ -58,6 +58,10 @@ def test_walk_sketch_matches_reference_index_kmers(gpu, name):
     (105, 5, 3, 1.0, dict(var_spacing=10, chop=3)),
     (106, 28, 256, 1.0, {}),
     (107, 1, 1, 1.0, dict(snv_only=True)),
+    # k > 32: no 2-bit packing, every k-mer is compared and hashed from its spelling (the reference takes any k, ILP_index.cpp:390-394)
+    (108, 33, 25, 1.0, {}),
+    (109, 64, 9, 0.7, dict(lower_frac=0.02, n_frac=0.005, r_lower_frac=0.02, r_n_frac=0.005)),
+    (110, 101, 31, 1.0, dict(chop=12)),
 ])
 def test_random_graphs_match_oracle(gpu, seed, k, w, T, kw):
     rk = {a[2:]: kw.pop(a) for a in list(kw) if a.startswith("r_")}
