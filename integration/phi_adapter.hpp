@@ -121,6 +121,7 @@ inline FrontEnd run_front_end_result(ILP_index &ix, std::vector<std::pair<std::s
     }
 #endif
     if (fe.parts.empty()) {
+        const double t_enter = realtime();
         // ---- flat views of the members read_gfa() filled (ILP_index.cpp:20-155): sized once, filled in parallel
         std::vector<uint64_t> seg_off(ix.n_vtx + 1, 0), walk_off(ix.num_walks + 1, 0), read_off(ip_reads.size() + 1, 0);
         for (uint32_t v = 0; v < ix.n_vtx; ++v) seg_off[v + 1] = seg_off[v] + ix.node_seq[v].size();
@@ -135,8 +136,10 @@ inline FrontEnd run_front_end_result(ILP_index &ix, std::vector<std::pair<std::s
         #pragma omp parallel for schedule(static) num_threads(ix.num_threads > 0 ? ix.num_threads : 1)
         for (int64_t r = 0; r < (int64_t)ip_reads.size(); ++r) ip_reads[r].second.copy(&read_bases[read_off[r]], ip_reads[r].second.size());
 
+        const double t_flat = realtime();
         detail::Pool &P = detail::pool();
         P.wait();
+        const double t_ctx = realtime();
         const int W = (int)P.devices.size();
         for (int r = 0; r < W; ++r)
             if (P.rc[r] != PHI_OK) { fprintf(stderr, "Error: GPU ILP_index front end failed (%d): %s\n", P.rc[r], P.err[r].c_str()); exit(1); }
@@ -199,6 +202,9 @@ inline FrontEnd run_front_end_result(ILP_index &ix, std::vector<std::pair<std::s
             }
             parts.push_back(jobs[r].res);
         }
+        if (getenv("PHI_ADAPTER_TIMES"))          // where the front end's wall time goes (stderr, one line)
+            fprintf(stderr, "[phi_adapter] flat views %.4f s, wait for the CUDA context(s) %.4f s, shard + run on %d GPU(s) %.4f s\n",
+                    t_flat - t_enter, t_ctx - t_flat, W, realtime() - t_ctx);
         if (W == 1) fe.parts = parts;
         else {                                    // one result in the reference's order
             phi_index_result *merged = 0;

@@ -236,6 +236,11 @@ def py_to_c_result(py: IndexResultPy):
         r.member_walk32 = mw.ctypes.data_as(i32p)
     r.minimizers_per_walk = mpw.ctypes.data_as(u64p)
     r.anchors_per_walk = apw.ctypes.data_as(u64p)
+    if py.shared_kmer_hist is not None:
+        hist = np.ascontiguousarray(py.shared_kmer_hist, dtype=np.uint64)
+        keep.append(hist)
+        r.shared_kmer_hist = hist.ctypes.data_as(u64p)
+        r.n_walk_kmers = py.n_walk_kmers
     r.read_kmer_positions, r.path_kmer_positions = py.read_kmer_positions, py.path_kmer_positions
     r.read_minimizers_emitted, r.path_minimizers_emitted, r.path_hits = py.read_minimizers_emitted, py.path_minimizers_emitted, py.path_hits
     return r, keep

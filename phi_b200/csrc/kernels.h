@@ -87,6 +87,7 @@ struct ExpandArgs {
 struct TileLayout {
     int M, M8, NB, nchunks, pad, cap;   // pad: positions in front of the halo window; cap: own windows per tile
     int o_canon, o_hash, o_pack, o_dirty, o_bnd, o_first, o_scan, o_pre, o_suf, o_flag, o_base, o_stepv, o_steps, o_cfirst, o_cmask;
+    int o_raw;                          // read tiles: landing zone of the bulk copy (cp.async.bulk) of the tile's bytes
     int bytes;
 };
 TileLayout read_tile_layout(int k, int w);
@@ -101,6 +102,7 @@ struct ReadSketchArgs {
     uint64_t tile0;                   // first tile of this launch (the reads may be sketched piece by piece while they arrive)
     int k, w;
     uint64_t *table; uint64_t table_mult, table_limit;   // home slot = umulhi(key, table_mult); slots [0, table_limit), table[table_limit] stays EMPTY
+    int bulk;                         // stage the tile's bytes with one cp.async.bulk into shared memory (issued before the boundary pass) instead of per-thread loads
     unsigned long long *ctr;
 };
 

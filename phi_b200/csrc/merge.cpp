@@ -137,6 +137,15 @@ extern "C" int phi_index_result_merge(const phi_index_result *const *parts, int 
         m->read_minimizers_emitted += r->read_minimizers_emitted; m->path_minimizers_emitted += r->path_minimizers_emitted;
         m->path_hits += r->path_hits;
     }
+    for (int p = 0; p < n_parts; ++p) {                                  // the -d1 statistic is global already (every part carries the same)
+        const phi_index_result *r = parts[p];
+        if (!r->shared_kmer_hist) continue;
+        uint64_t *o_hist = heap_array<uint64_t>(b, (uint64_t)NW + 1);
+        if (!o_hist) { phi_gpu_index_result_free(m); return PHI_ERR_NOMEM; }
+        memcpy(o_hist, r->shared_kmer_hist, ((size_t)NW + 1) * 8);
+        m->shared_kmer_hist = o_hist; m->n_walk_kmers = r->n_walk_kmers;
+        break;
+    }
     m->count_sp_r = NS; m->n_walks = NW; m->n_anchors = nm; m->n_groups = ng; m->n_group_vtx = nv;
     m->spectrum = spectrum ? o_spec : nullptr; m->rank_off = o_rank_off; m->group_len = o_len; m->group_vtx = o_vtx; m->group_member_off = o_moff;
     m->member_walk16 = o_w16; m->member_walk32 = o_w32; m->minimizers_per_walk = o_mpw; m->anchors_per_walk = o_apw;

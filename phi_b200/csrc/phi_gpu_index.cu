@@ -895,6 +895,7 @@ static int reads_sketch_launch(phi_gpu_index_ctx *ctx, int k, int w, const Reads
     A.read_bases = ctx->read_bases.as<uint8_t>() + 16; A.read_off = ctx->read_off.as<uint64_t>();
     A.n_reads = ctx->n_reads; A.total_bases = ctx->read_total; A.tile_first_read = ctx->tile_first_read.as<uint64_t>();
     A.k = k; A.w = w; A.table = ctx->table.as<uint64_t>(); A.table_mult = rs.cap; A.table_limit = limit; A.ctr = d_ctr;
+    { static int bulk = -1; if (bulk < 0) { const char *e = getenv("PHI_GPU_READ_BULK"); bulk = e ? atoi(e) : 0; } A.bulk = bulk; }
     CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st));
     if (ctx->n_pieces > 1 && !rs.relaunch) {
         // the reads are still arriving: sketch the tiles whose bases are complete after every piece
@@ -1353,11 +1354,77 @@ static int stage_filter(phi_gpu_index_ctx *ctx, int w, int mode, uint32_t n_walk
 // ---- the -d1 statistic (ILP_index.cpp:565-606), after the result proper is complete: every minimizer of the representative
 // chunks with its hash -> instantiated per walk in (walk, position) order -> stable sort on the hash (walks stay ascending
 // inside a hash) -> distinct walks per hash -> histogram.  Reuses the hit / expansion / sort buffers.
+__global__ void gather_u64_kernel(const uint64_t *src, const uint32_t *idx, uint64_t n, uint64_t *dst)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void iota_u32_kernel(uint32_t *p, uint64_t n)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+
+// Several GPUs: the (hash, walk) pairs of this GPU's walk slices (ns of them, sorted by hash, in x_hash / x_walk) travel to the owner
+// of the hash (the range partition of the spectrum exchange); the owner orders what it received by (hash, walk).  ns becomes the
+// number of pairs this GPU owns.  The same pair can arrive from two GPUs (one walk carrying a minimizer in two regions): the
+// statistic counts distinct walks per hash, so duplicates do not matter once the walks of a hash are sorted.
+static int exchange_hash_walk_pairs(phi_gpu_index_ctx *ctx, uint64_t &ns)
+{
+    std::string err; NcclApi *nc = nccl_api(err);
+    if (!nc || !ctx->comm) return ctx->fail(PHI_ERR_COMM, "communicator not initialised");
+    const int W = ctx->world, me = ctx->rank;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    CU(ctx->xcnt.reserve(8192));
+    uint64_t *d_split = ctx->xcnt.as<uint64_t>();
+    owner_split_kernel<<<1, 128, 0, ctx->st>>>(ctx->x_hash.as<uint64_t>(), ns, W, 0, d_split);
+    CU(cudaGetLastError()); ctx->launches++;
+    const uint64_t *all = nullptr;
+    int rc = allgather_words(ctx, nc, d_split, W + 2, all);
+    if (rc) return rc;
+    std::vector<uint64_t> scnt(W), soff(W), rcnt(W), roff(W);
+    uint64_t rtot = 0;
+    for (int p = 0; p < W; ++p) {
+        const uint64_t *sp = all + (size_t)p * (W + 2), *mine = all + (size_t)me * (W + 2);
+        scnt[p] = mine[p + 1] - mine[p]; soff[p] = mine[p];
+        rcnt[p] = sp[me + 1] - sp[me]; roff[p] = rtot; rtot += rcnt[p];
+    }
+    if (rtot >= (1ull << 32)) return ctx->fail(PHI_ERR_UNSUPPORTED, "more than 2^32-1 (hash, walk) pairs routed to one GPU");
+    struct AbortGuard { phi_gpu_index_ctx *c; bool armed; ~AbortGuard() { if (armed) comm_release(c, true); } } guard = {ctx, true};
+    CU(ctx->keys_a.reserve(rtot * 8 + 8)); CU(ctx->vals_a.reserve(rtot * 4 + 4));
+    NC(nc->GroupStart());
+    for (int p = 0; p < W; ++p) {
+        if (p == me) continue;
+        if (scnt[p]) { NC(nc->Send(ctx->x_hash.as<uint64_t>() + soff[p], scnt[p], ncclUint64, p, comm, ctx->st)); NC(nc->Send(ctx->x_walk.as<uint32_t>() + soff[p], scnt[p], ncclUint32, p, comm, ctx->st)); }
+        if (rcnt[p]) { NC(nc->Recv(ctx->keys_a.as<uint64_t>() + roff[p], rcnt[p], ncclUint64, p, comm, ctx->st)); NC(nc->Recv(ctx->vals_a.as<uint32_t>() + roff[p], rcnt[p], ncclUint32, p, comm, ctx->st)); }
+    }
+    NC(nc->GroupEnd());
+    if (scnt[me]) {
+        CU(cudaMemcpyAsync(ctx->keys_a.as<uint64_t>() + roff[me], ctx->x_hash.as<uint64_t>() + soff[me], scnt[me] * 8, cudaMemcpyDeviceToDevice, ctx->st));
+        CU(cudaMemcpyAsync(ctx->vals_a.as<uint32_t>() + roff[me], ctx->x_walk.as<uint32_t>() + soff[me], scnt[me] * 4, cudaMemcpyDeviceToDevice, ctx->st));
+    }
+    guard.armed = false;
+    ns = rtot;
+    if (!ns) return PHI_OK;
+    // (hash, walk) order: stable sort on the walk first (carrying the pair index), then on the hash
+    CU(ctx->x_hash.reserve(ns * 8)); CU(ctx->x_walk.reserve(ns * 4)); CU(ctx->keys_b.reserve(ns * 8)); CU(ctx->vals_b.reserve(ns * 4)); CU(ctx->tmp_order.reserve(ns * 4));
+    CU(ctx->sort_scr.reserve(std::max(radix_sort_scratch(ns), radix_sort_u32_scratch(ns))));
+    const unsigned nb = (unsigned)((ns + 255) / 256);
+    iota_u32_kernel<<<nb, 256, 0, ctx->st>>>(ctx->tmp_order.as<uint32_t>(), ns);
+    CU(cudaGetLastError()); ctx->launches++;
+    CU(radix_sort_u32(ctx->vals_a.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), ctx->tmp_order.as<uint32_t>(), ctx->x_walk.as<uint32_t>(), ns, 32, ctx->sort_scr.p, ctx->st, &ctx->launches));
+    gather_u64_kernel<<<nb, 256, 0, ctx->st>>>(ctx->keys_a.as<uint64_t>(), ctx->tmp_order.as<uint32_t>(), ns, ctx->x_hash.as<uint64_t>());
+    CU(cudaGetLastError()); ctx->launches++;
+    CU(cudaMemcpyAsync(ctx->x_walk.p, ctx->vals_a.p, ns * 4, cudaMemcpyDeviceToDevice, ctx->st));       // the walks, ascending
+    CU(radix_sort_u64(ctx->x_hash.as<uint64_t>(), ctx->keys_b.as<uint64_t>(), ctx->x_walk.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), ns, 0, 64,
+                      ctx->sort_scr.p, ctx->st, &ctx->launches));
+    return PHI_OK;
+}
+
 static int stage_debug_hist(phi_gpu_index_ctx *ctx, int k, int w, const std::vector<uint64_t> &h_walk_len, const uint32_t *d_walk_vtx,
                             const uint64_t *d_walk_off, uint64_t n_steps_eff, int walks_monotone, uint32_t n_walks_global)
 {
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
-    if (ctx->world > 1) return ctx->fail(PHI_ERR_UNSUPPORTED, "the -d1 shared k-mer statistic is not implemented for several GPUs");
     CU(ctx->dbg_hist.reserve(((size_t)n_walks_global + 2) * 8));
     CU(cudaMemsetAsync(ctx->dbg_hist.p, 0, ((size_t)n_walks_global + 2) * 8, ctx->st));
     CU(cudaMemsetAsync(d_ctr + CTR_WALK_KMERS, 0, 8, ctx->st));
@@ -1367,12 +1434,25 @@ static int stage_debug_hist(phi_gpu_index_ctx *ctx, int k, int w, const std::vec
     CU(ctx->rank_drop.reserve(4)); CU(cudaMemsetAsync(ctx->rank_drop.p, 0, 4, ctx->st));   // every record has rank 0 here: keep it
     uint64_t ns = 0;
     rc = expand_survivors(ctx, w, true, ns);
-    if (rc || !ns) return rc;
-    CU(ctx->keys_b.reserve(ns * 8)); CU(ctx->vals_b.reserve(ns * 4)); CU(ctx->sort_scr.reserve(radix_sort_scratch(ns)));
-    CU(radix_sort_u64(ctx->x_hash.as<uint64_t>(), ctx->keys_b.as<uint64_t>(), ctx->x_walk.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), ns, 0, 64,
-                      ctx->sort_scr.p, ctx->st, &ctx->launches));
-    CU(filter_shared_kmer_hist(ctx->x_hash.as<uint64_t>(), ctx->x_walk.as<uint32_t>(), ns, n_walks_global, ctx->dbg_hist.as<unsigned long long>(),
-                               d_ctr + CTR_WALK_KMERS, ctx->st, &ctx->launches));
+    if (rc) return rc;                                                     // (several GPUs: every rank reaches the collectives below or none does — the
+    if (ns) {                                                              //  failures above are allocation failures, which abort the run on this rank)
+        CU(ctx->keys_b.reserve(ns * 8)); CU(ctx->vals_b.reserve(ns * 4)); CU(ctx->sort_scr.reserve(radix_sort_scratch(ns)));
+        CU(radix_sort_u64(ctx->x_hash.as<uint64_t>(), ctx->keys_b.as<uint64_t>(), ctx->x_walk.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), ns, 0, 64,
+                          ctx->sort_scr.p, ctx->st, &ctx->launches));
+    }
+    unsigned long long *d_hist = ctx->dbg_hist.as<unsigned long long>();
+    if (ctx->world > 1) {
+        if (!ns) { CU(ctx->x_hash.reserve(8)); CU(ctx->x_walk.reserve(8)); }
+        rc = exchange_hash_walk_pairs(ctx, ns);
+        if (rc) return rc;
+    }
+    if (ns) CU(filter_shared_kmer_hist(ctx->x_hash.as<uint64_t>(), ctx->x_walk.as<uint32_t>(), ns, n_walks_global, d_hist, d_hist + n_walks_global + 1,
+                                       ctx->st, &ctx->launches));
+    if (ctx->world > 1) {                                                  // every hash has one owner: the histograms and the distinct counts add up
+        std::string err; NcclApi *nc = nccl_api(err);
+        NC(nc->AllReduce(d_hist, d_hist, (size_t)n_walks_global + 2, ncclUint64, ncclSum, (ncclComm_t)ctx->comm, ctx->st));
+    }
+    CU(cudaMemcpyAsync(d_ctr + CTR_WALK_KMERS, d_hist + n_walks_global + 1, 8, cudaMemcpyDeviceToDevice, ctx->st));
     return PHI_OK;
 }
 

@@ -62,6 +62,28 @@ read_sketch_kernel(ReadSketchArgs A)
     set_window_bounds(t);
     const int tid = threadIdx.x;
 
+    // ---- optional: the tile's bytes are contiguous in the read buffer, so ONE bulk copy (cp.async.bulk, completion on an mbarrier)
+    // brings them to shared memory while the boundary pass below runs; source, destination and size are multiples of 16 bytes
+    // (the buffer has 16 readable bytes in front and 48 behind the reads).
+    __shared__ __align__(8) unsigned long long s_mbar;
+    unsigned char *raw = smem + L.o_raw;
+    long long a0 = 0; bool bulk = A.bulk != 0;
+    if (bulk) {
+        a0 = t.g0 & ~15ll; if (a0 < -16) a0 = -16;
+        long long a1 = (t.g0 + L.NB + 15) & ~15ll;
+        const long long lim = ((long long)A.total_bases + 48) & ~15ll;
+        if (a1 > lim) a1 = lim;
+        const uint32_t bytes = (uint32_t)(a1 - a0);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_mbar), dst = (uint32_t)__cvta_generic_to_shared(raw);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst), "l"(A.read_bases + a0), "r"(bytes), "r"(bar) : "memory");
+        }
+    }
+
     // ---- read boundaries -> window masks.  A read starting at local base b makes the windows e with b inside their bases
     // (e-w+1, e+k-1], i.e. e in [b-k+1, b+w-2], invalid, and e = b+w-1 the first window of that read.
     const int nwords = (L.M + 31) / 32 + 2;
@@ -94,13 +116,20 @@ read_sketch_kernel(ReadSketchArgs A)
             r0 += NT;
         }
     }
-    // ---- stage bases: unaligned 8-byte loads, mask outside [0, total)
+    // ---- stage bases: unaligned 8-byte loads (from the landing zone of the bulk copy, or straight from global memory), mask outside [0, total)
+    if (bulk) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+        uint32_t done = 0;
+        for (int it = 0; it < (1 << 22) && !done; ++it)              // phase 0 of the barrier completes when all bytes have landed
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+        if (!__syncthreads_and(done)) bulk = false;                  // (never seen; the direct loads below are always right)
+    }
     uint32_t dirty_any = 0;
     for (int c = tid; c < L.nchunks; c += NT) {
         long long g = t.g0 + 8ll * c;
         uint64_t v = 0;
         if (g + 8 > 0 && g < t.seq_len) {
-            v = load8_unaligned(A.read_bases + g);                   // front padding covers g in [-7, -1]
+            v = bulk ? load8_unaligned(raw + (g - a0)) : load8_unaligned(A.read_bases + g);   // front padding covers g in [-7, -1]
             if (g < 0) v &= ~0ull << (8 * (int)(-g));
             long long nvalid = t.seq_len - g;                        // bytes [0, nvalid) of the chunk are real
             if (nvalid < 8) v &= (1ull << (8 * nvalid)) - 1;

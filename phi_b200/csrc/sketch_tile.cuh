@@ -70,6 +70,7 @@ static inline TileLayout make_layout(int k, int w, bool walk)
     L.o_steps = take(walk ? 2 * (L.NB + 2) : 0);
     L.o_cfirst = take(walk ? 2 * (L.nchunks + 2) : 0);
     L.o_cmask = take(walk ? (L.nchunks + 2) : 0);
+    L.o_raw = take(walk ? 0 : 8 * L.nchunks + 64);
     L.bytes = align_up_h(o, 16);
     return L;
 }

@@ -40,23 +40,27 @@ def main_gpu(name, mode="region"):
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
+    debug = 1 if name.endswith("+d1") else 0             # "+d1": with the shared k-mer statistic (ILP_index.cpp:565-606)
+    name = name[:-3] if debug else name
     g, rd, k, w, T = load(name)
     gs, rs, base, region = multi.shard_inputs(g, rd, rank, world, k, w, mode)
     ix = phi_b200.PhiGpuIndex(local)
     multi.init_comm(ix, rank, world, base, g.n_walks, dist)
     if region is not None:
         ix.set_walk_region(*region)
-    part = ix.run(gs, rs, k, w, T)
-    part2 = ix.run(gs, rs, k, w, T)                      # repeatable
+    part = ix.run(gs, rs, k, w, T, debug=debug)
+    part2 = ix.run(gs, rs, k, w, T, debug=debug)         # repeatable
     assert_same_result(part, part2)
     assert rank == 0 or len(part.spectrum) == 0          # the ranked spectrum is copied out on rank 0 only
     parts = [None] * world
     dist.gather_object(part, parts if rank == 0 else None, dst=0)
     if rank == 0:
         got = multi.merge_results(parts)
-        want = phi_io.oracle_index(g, rd, k, w, T)
+        want = phi_io.oracle_index(g, rd, k, w, T, debug=debug)
         got.path_hits = want.path_hits                   # pre-filter hit count is per-GPU bookkeeping
         assert_same_result(want, got)
+        if debug:
+            assert parts[0].n_walk_kmers == want.n_walk_kmers and all(np.array_equal(p.shared_kmer_hist, want.shared_kmer_hist) for p in parts)
         print(f"MULTI_OK gpu world={world} case={name} mode={mode} region={region} spectrum={got.count_sp_r} anchors={got.n_anchors}")
     ix.close()
     dist.barrier()

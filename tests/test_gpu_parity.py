@@ -119,7 +119,7 @@ def test_unsupported_parameters_fail_loudly(gpu):
     sg = synth.make_graph(5, 3000, 2)
     rd = synth.make_reads(5, sg, 1.0)
     with pytest.raises(phi_b200.PhiGpuError) as e:
-        gpu.run(sg.graph, rd, 33, 25, 1.0)
+        gpu.run(sg.graph, rd, 256, 25, 1.0)                 # vertex lists carry a one-byte length: k <= 255
     assert e.value.code == 2
     with pytest.raises(phi_b200.PhiGpuError):
         gpu.run(sg.graph, rd, 31, 300, 1.0)

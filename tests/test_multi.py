@@ -34,7 +34,8 @@ def test_sharded_algorithm_cpu_gloo(case, world):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,partition", [(c, "region") for c in ["toy_k3_w2", "synth_small", "synth_dirty", "synth_repeats", "mhc4", "synth:77:400000:11:3.0"]]
-                         + [(c, "walk") for c in ["synth_small", "synth_dirty", "synth:77:400000:11:3.0"]])
+                         + [(c, "walk") for c in ["synth_small", "synth_dirty", "synth:77:400000:11:3.0"]]
+                         + [("synth_small+d1", "region"), ("synth_repeats+d1", "walk")])
 def test_multi_gpu_matches_oracle(case, partition):
     import torch
     n = torch.cuda.device_count()
