@@ -169,11 +169,27 @@ class Workload:
         if part_world > 1 and a.partition == "walk":
             wlo, whi = a.haps * part_rank // part_world, a.haps * (part_rank + 1) // part_world
             base = wlo
+        s_lo, s_hi = 0, sg.n_sites
+        if region is not None:
+            # the generator numbers the vertices along the backbone and top_order_map is the identity: the topological coordinate of a
+            # vertex is its offset in the segment store, so the region is a vertex range, i.e. a range of variant sites (+ a margin that
+            # holds far more than the w / k-1 bases of context the slicer keeps)
+            v_lo = int(np.searchsorted(g0.seg_off, np.uint64(region[0]), side="left"))
+            v_hi = int(np.searchsorted(g0.seg_off, np.uint64(min(region[1], int(g0.seg_off[-1]))), side="left"))
+            pf = sg.piece_first_node
+            s_lo = max(0, int(np.searchsorted(pf, v_lo, side="right") - 1) // 3 - 64)
+            s_hi = min(sg.n_sites, int(np.searchsorted(pf, v_hi, side="right")) // 3 + 64)
         BATCH = 8
         for h0 in range(0, a.haps, BATCH):
-            full = [sg.walk_of(sg.allele_row(h)) for h in range(h0, min(h0 + BATCH, a.haps))]
-            for x in full:
-                P += positions([int(seg_len[x].sum())], self.k, self.w)
+            hs = range(h0, min(h0 + BATCH, a.haps))
+            if region is not None:
+                full = [sg.walk_of_hap_sites(h, s_lo, s_hi) for h in hs]
+                for h in hs:
+                    P += positions([sg.hap_length(h)], self.k, self.w)
+            else:
+                full = [sg.walk_of(sg.allele_row(h)) for h in hs]
+                for x in full:
+                    P += positions([int(seg_len[x].sum())], self.k, self.w)
             if region is not None:
                 gb = _abi.Graph(g0.seg_off, g0.seg_bases, np.concatenate([[0], np.cumsum([len(x) for x in full])]),
                                 np.concatenate(full), g0.top_order_map)

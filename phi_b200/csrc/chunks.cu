@@ -18,6 +18,7 @@
 //   against its representative -> tile records of the representatives.
 #include "kernels.h"
 #include "device_common.cuh"
+#include <cstdlib>
 
 namespace phi {
 
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) step_pass_kernel(const uint32_t *walk_vtx
 // decoupled look-back over one 64-bit word per tile; nothing but walk_vtx is read and nothing but step_base (and the few
 // per-chunk / per-walk values) is written.  The scanned value: bits [0,35) bases since the last walk start, [35,61) chunk
 // starts, bit 61 "a walk started" (the bases of the left operand are discarded); bits 62-63 of a tile word: 1 = aggregate, 2 = prefix.
-constexpr int FS_THREADS = 256, FS_ITEMS = 8, FS_TILE = FS_THREADS * FS_ITEMS;   // every thread owns FS_ITEMS consecutive steps
+constexpr int FS_THREADS = 256;   // every thread owns FS_ITEMS consecutive steps (template parameter: 4, 8 or 16; PHI_GPU_FS_ITEMS picks, default 8)
 constexpr uint64_t FS_BASES = (1ull << 35) - 1, FS_CHUNKS = ((1ull << 26) - 1) << 35, FS_RESET = 1ull << 61, FS_VALUE = (1ull << 62) - 1;
 __device__ __forceinline__ uint64_t fs_comb(uint64_t a, uint64_t b)           // a, then b
 {
@@ -149,12 +150,14 @@ __device__ __forceinline__ uint64_t fs_comb(uint64_t a, uint64_t b)           //
     if (b & FS_RESET) return (b & FS_BASES) | chunks | FS_RESET;
     return (((a & FS_BASES) + (b & FS_BASES)) & FS_BASES) | chunks | (a & FS_RESET);
 }
-__global__ void __launch_bounds__(FS_THREADS, 4) fused_steps_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
+template <int FS_ITEMS>
+__global__ void __launch_bounds__(FS_THREADS, FS_ITEMS >= 16 ? 2 : 4) fused_steps_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
                                                                     const uint4 *vinfo, uint32_t n_vtx, unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base,
                                                                     uint32_t *chunk_step, uint32_t *c_walk, uint64_t *walk_len, unsigned long long *ctr)
 {
     __shared__ uint32_t sh_tile, sh_h[2];
     __shared__ uint64_t sh_ws, sh_excl, sh_warp[FS_THREADS / 32];
+    constexpr int FS_TILE = FS_THREADS * FS_ITEMS;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) sh_tile = atomicAdd(ticket, 1u);              // tiles start in order: a tile only ever waits for tiles that run
     __syncthreads();
@@ -456,23 +459,24 @@ __global__ void __launch_bounds__(256) chunk_rep_kernel(ChunkTable C, const uint
 }
 
 // ---- tile records of the representatives (c_tile_base = exclusive scan of c_ntile)
-__global__ void tile_fill_kernel(ChunkTable C, const uint64_t *walk_off, const uint32_t *step_base, int w, TileRec *tiles)
+__global__ void tile_fill_kernel(ChunkTable C, const uint64_t *walk_off, const uint64_t *walk_len, const uint32_t *step_base, int w, TileRec *tiles)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C.n_chunks) return;
     const uint32_t nt = C.c_ntile[c];
     if (!nt) return;
     const uint32_t h = C.c_walk[c], lo = C.c_lo[c], hi = C.c_hi[c], R = C.c_R[c];
-    const uint64_t ws = walk_off[h];
+    const uint64_t ws = walk_off[h], we = walk_off[h + 1];
+    const uint32_t wl = (uint32_t)walk_len[h];
     const uint32_t tb = C.c_tile_base[c];
     const uint32_t T = (hi - lo + nt - 1) / nt;                          // the chunk's windows, split evenly over its tiles (<= tile_cap each)
     for (uint32_t t = 0; t < nt; ++t) {
         TileRec r;
-        r.walk = h; r.e0 = lo + t * T; r.e1 = min(r.e0 + T, hi); r.chunk = c; r.cbase = lo; r._r0 = r._r1 = 0;
+        r.walk = h; r.e0 = lo + t * T; r.e1 = min(r.e0 + T, hi); r.chunk = c; r.cbase = lo; r.walk_len = wl; r._r1 = 0;
         const long long first = max((long long)r.e0 - w - tile_pad(w), 0ll);   // first base the tile stages
         uint32_t a = (uint32_t)ws, b = R + 1;                           // last step with step_base <= first (the front padding may reach before L)
         while (b - a > 1) { uint32_t m = (a + b) >> 1; if ((long long)step_base[m] <= first) a = m; else b = m; }
-        r.first_step = (uint32_t)(a - ws);
+        r.first_step = (uint32_t)(a - ws); r.step0 = a; r.step_end = we;
         tiles[tb + t] = r;
     }
 }
@@ -586,6 +590,13 @@ cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, u
     return cudaSuccess;
 }
 
+static int fs_items()
+{
+    static int v = 0;
+    if (!v) { const char *e = getenv("PHI_GPU_FS_ITEMS"); v = e ? atoi(e) : 8; if (v != 4 && v != 8 && v != 16) v = 8; }
+    return v;
+}
+
 cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps, const uint4 *vinfo, uint32_t n_vtx,
                              unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base, uint32_t *chunk_step, uint32_t *c_walk,
                              uint64_t *walk_len, unsigned long long *ctr, cudaStream_t st, uint64_t *launches, uint64_t tile_first, uint64_t tile_last)
@@ -602,12 +613,17 @@ cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off,
         if (e != cudaSuccess) return e;
     }
     if (tile_last <= tile_first) return cudaSuccess;
-    fused_steps_kernel<<<(unsigned)(tile_last - tile_first), FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr);
+    const unsigned grid = (unsigned)(tile_last - tile_first);
+    switch (fs_items()) {
+        case 4: fused_steps_kernel<4><<<grid, FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr); break;
+        case 16: fused_steps_kernel<16><<<grid, FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr); break;
+        default: fused_steps_kernel<8><<<grid, FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr); break;
+    }
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
-uint64_t walk_steps_fused_tiles(uint64_t n_steps) { return (n_steps + FS_TILE - 1) / FS_TILE; }
-uint64_t walk_steps_fused_tile_steps() { return FS_TILE; }
+uint64_t walk_steps_fused_tile_steps() { return (uint64_t)FS_THREADS * fs_items(); }
+uint64_t walk_steps_fused_tiles(uint64_t n_steps) { const uint64_t t = walk_steps_fused_tile_steps(); return (n_steps + t - 1) / t; }
 
 cudaError_t walk_step_finalize(const ChunkTable &C, const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off, uint32_t n_walks,
                                uint64_t n_steps, uint32_t *step_base, uint64_t *walk_len, cudaStream_t st, uint64_t *launches)
@@ -665,10 +681,10 @@ cudaError_t chunk_group(const ChunkTable &C, uint32_t *table, uint32_t table_cap
     return cudaSuccess;
 }
 
-cudaError_t chunk_tiles(const ChunkTable &C, const uint64_t *walk_off, const uint32_t *step_base, int w, TileRec *tiles, cudaStream_t st, uint64_t *launches)
+cudaError_t chunk_tiles(const ChunkTable &C, const uint64_t *walk_off, const uint64_t *walk_len, const uint32_t *step_base, int w, TileRec *tiles, cudaStream_t st, uint64_t *launches)
 {
     if (!C.n_chunks) return cudaSuccess;
-    tile_fill_kernel<<<(C.n_chunks + 127) / 128, 128, 0, st>>>(C, walk_off, step_base, w, tiles);
+    tile_fill_kernel<<<(C.n_chunks + 127) / 128, 128, 0, st>>>(C, walk_off, walk_len, step_base, w, tiles);
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }

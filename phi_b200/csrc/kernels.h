@@ -59,8 +59,9 @@ __host__ __device__ inline int tile_cap(int w, int threads) { return tile_fast_w
 // One walk-sketch tile: window end positions [e0, e1) of walk `walk` (the representative of chunk `chunk`).
 struct TileRec {
     uint32_t walk, e0, e1, first_step;   // first_step: step under the tile's first staged base, relative to walk_off[walk]
-    uint32_t chunk, cbase, _r0, _r1;     // cbase: first base of the chunk; hit positions are stored as p + w - cbase
-};
+    uint32_t chunk, cbase, walk_len, _r1; // cbase: first base of the chunk; hit positions are stored as p + w - cbase; walk_len: bases of the walk
+    uint64_t step0, step_end;            // global index of that first step and of the walk's last step + 1: the sketch kernel needs no
+};                                       // walk_off / walk_len lookups of its own (one dependent round trip less per tile)
 
 // Chunk table (chunks.cu): chunks are numbered along the walks, walk after walk.
 struct ChunkTable {
@@ -173,7 +174,7 @@ cudaError_t chunk_keys(const ChunkTable &C, const uint32_t *walk_vtx, const uint
                        const uint4 *vinfo, int k, int w, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 cudaError_t chunk_group(const ChunkTable &C, uint32_t *table, uint32_t table_cap, const uint32_t *walk_vtx, int dedupe, int w, unsigned long long *ctr,
                         cudaStream_t st, uint64_t *launches);
-cudaError_t chunk_tiles(const ChunkTable &C, const uint64_t *walk_off, const uint32_t *step_base, int w, TileRec *tiles, cudaStream_t st, uint64_t *launches);
+cudaError_t chunk_tiles(const ChunkTable &C, const uint64_t *walk_off, const uint64_t *walk_len, const uint32_t *step_base, int w, TileRec *tiles, cudaStream_t st, uint64_t *launches);
 cudaError_t chunk_emitted(const ChunkTable &C, const uint32_t *c_emitted, const uint32_t *c_hits, uint32_t walk_id_base,
                           unsigned long long *minimizers_per_walk, unsigned long long *ctr, cudaStream_t st, uint64_t *launches);
 cudaError_t chunk_survivors(const ChunkTable &C, const TileRec *tiles, uint32_t n_tiles, const uint32_t *hseg_off, const uint32_t *hseg_cnt,

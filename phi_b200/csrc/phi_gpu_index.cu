@@ -479,7 +479,7 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     if (total_bases >= (1ull << STEP_BASE_BITS)) return ctx->fail2(PHI_ERR_UNSUPPORTED, "2^38 or more walk bases on one GPU; shard the walks over more GPUs");
     ctx->unique_windows = h_ctr[CTR_UNIQUE_WINDOWS]; ctx->active_chunks = h_ctr[CTR_ACTIVE_CHUNKS]; ctx->path_pos = h_ctr[CTR_PATH_POS];
     CUP(ctx->tiles.reserve((size_t)ctx->n_tiles * sizeof(TileRec) + 32));
-    CUP(chunk_tiles(C, d_walk_off, ctx->step_base.as<uint32_t>(), w, ctx->tiles.as<TileRec>(), st, launches));
+    CUP(chunk_tiles(C, d_walk_off, ctx->walk_len.as<uint64_t>(), ctx->step_base.as<uint32_t>(), w, ctx->tiles.as<TileRec>(), st, launches));
     // member walks of every representative (the grouped result copies them instead of instantiating one record per member)
     DevBuf *cms[] = {&ctx->fs_state, &ctx->cm_off, &ctx->cm_cursor, &ctx->cm_tmp, &ctx->cm_walk};
     for (DevBuf *b : cms) CUP(b->reserve(((size_t)NC + 2) * 4));

@@ -210,11 +210,11 @@ cudaError_t radix_sort_u64(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a,
     if (n <= 1 || bit_hi <= bit_lo) return cudaSuccess;
     if (n >= (1ull << 32)) return cudaErrorInvalidValue;
     {
-        static bool attr_set = false;                                      // 48 KB staging + 9 KB static shared memory > the 48 KB default
-        if (!attr_set) {
+        // 48 KB staging + 9 KB static shared memory > the 48 KB default.  Set on every call: the attribute belongs to the device the
+        // caller is on, and one process may drive several devices (one host thread each).
+        {
             cudaError_t e = cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
             if (e != cudaSuccess) return e;
-            attr_set = true;
         }
     }
     const uint32_t nb = (uint32_t)((n + RS_B - 1) / RS_B);
@@ -344,11 +344,9 @@ cudaError_t radix_sort_u32(uint32_t *keys_a, uint32_t *keys_b, uint32_t *vals_a,
     if (n <= 1 || bits <= 0) return cudaSuccess;
     if (n >= (1ull << 32) || bits > 32) return cudaErrorInvalidValue;
     {
-        static bool attr_set = false;
-        if (!attr_set) {
+        {
             cudaError_t e = cudaFuncSetAttribute(radix32_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R32_SMEM);
             if (e != cudaSuccess) return e;
-            attr_set = true;
         }
     }
     const int passes = (bits + 10) / 11;                                   // digits of at most 11 bits, as even as possible

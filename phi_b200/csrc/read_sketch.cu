@@ -84,6 +84,15 @@ read_sketch_kernel(ReadSketchArgs A)
         }
     }
 
+    // the first staging load of every thread is issued here, ahead of the boundary pass: its latency and the boundary pass's chain
+    // (tile directory -> read offsets) overlap instead of queueing up
+    uint64_t v_first = 0;
+    const bool have_first = !bulk;
+    if (have_first && tid < L.nchunks) {
+        const long long g = t.g0 + 8ll * tid;
+        if (g + 8 > 0 && g < t.seq_len) v_first = load8_unaligned(A.read_bases + g);
+    }
+
     // ---- read boundaries -> window masks.  A read starting at local base b makes the windows e with b inside their bases
     // (e-w+1, e+k-1], i.e. e in [b-k+1, b+w-2], invalid, and e = b+w-1 the first window of that read.
     const int nwords = (L.M + 31) / 32 + 2;
@@ -129,7 +138,7 @@ read_sketch_kernel(ReadSketchArgs A)
         long long g = t.g0 + 8ll * c;
         uint64_t v = 0;
         if (g + 8 > 0 && g < t.seq_len) {
-            v = bulk ? load8_unaligned(raw + (g - a0)) : load8_unaligned(A.read_bases + g);   // front padding covers g in [-7, -1]
+            v = bulk ? load8_unaligned(raw + (g - a0)) : (have_first && c == tid) ? v_first : load8_unaligned(A.read_bases + g);   // front padding covers g in [-7, -1]
             if (g < 0) v &= ~0ull << (8 * (int)(-g));
             long long nvalid = t.seq_len - g;                        // bytes [0, nvalid) of the chunk are real
             if (nvalid < 8) v &= (1ull << (8 * nvalid)) - 1;

@@ -143,8 +143,7 @@ __device__ __forceinline__ void walk_sketch_body(const WalkSketchArgs &A)
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t tile = blockIdx.x;
     const TileRec tr = A.tiles[tile];
-    const uint32_t h = tr.walk;
-    const long long len = A.walk_len[h];
+    const long long len = tr.walk_len;
     const TileLayout &L = A.layout;
     Tile t = carve(smem, L, A.k, A.w);
     // the tile owns the window end positions [e0, e1) of walk h (at most TILE_W); everything below is sized by what it really holds
@@ -158,8 +157,7 @@ __device__ __forceinline__ void walk_sketch_body(const WalkSketchArgs &A)
     // ---- steps overlapping the tile's bases [base_lo, base_hi)
     const long long base_lo = t.g0 < 0 ? 0 : t.g0;
     const long long base_hi = min(len, t.g0 + (long long)t.NB);
-    const uint64_t wbeg = A.walk_off[h], wend = A.walk_off[h + 1];
-    const uint64_t s0 = wbeg + tr.first_step;
+    const uint64_t wend = tr.step_end, s0 = tr.step0;
     int n_steps = 0;
     for (uint64_t c0 = s0;; c0 += NT) {
         uint64_t s = c0 + tid; int ok = 0;

@@ -49,6 +49,28 @@ class SynthGraph:
             return self.alleles[h]
         return self.fa[self.pick[h][self.block], np.arange(self.n_sites)].astype(np.uint8)
 
+    def walk_of_hap_sites(self, h, s_lo, s_hi):
+        """The part of haplotype h's walk that runs through the sites [s_lo, s_hi) (from the backbone piece in front of site s_lo to the
+        one behind site s_hi - 1): what a GPU that owns a region of the graph needs, without spelling the whole walk."""
+        s_lo, s_hi = max(0, int(s_lo)), min(self.n_sites, int(s_hi))
+        cols = np.arange(s_lo, s_hi)
+        if self.alleles is not None:
+            row = self.alleles[h, s_lo:s_hi]
+        else:
+            row = self.fa[self.pick[h][self.block[s_lo:s_hi]], cols].astype(np.uint8)
+        n = s_hi - s_lo
+        sel = np.ones(3 * n + 1, dtype=bool)
+        sel[1:3 * n:3] = row == 0
+        sel[2:3 * n:3] = row == 1
+        p = 3 * s_lo + np.nonzero(sel)[0]
+        return expand_ranges(self.piece_first_node[p], self.piece_n_nodes[p]).astype(np.uint32)
+
+    def hap_length(self, h):
+        """Bases of haplotype h's whole walk (no vertex list is spelled)."""
+        row = self.allele_row(h)
+        n = self.n_sites
+        return int(self.piece_len[0:3 * n + 1:3].sum() + self.piece_len[1:3 * n:3][row == 0].sum() + self.piece_len[2:3 * n:3][row == 1].sum())
+
     def mosaic_row(self, src_of_site):
         """Allele vector of a mosaic: site s takes the allele of haplotype src_of_site[s]."""
         cols = np.arange(self.n_sites)
