@@ -76,6 +76,7 @@ def parse_args():
     ap.add_argument("--partition", default="region", choices=["region", "walk"], help="how the walks are sharded over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip digest / parity_n / no-sharing extras (profiling runs)")
+    ap.add_argument("--no-digest", action="store_true", help="skip the merged-result digest (the parts of a c5 run are several GB)")
     ap.add_argument("--cpu-walks", type=int, default=0, help="walks in the reference slice of c4/c5 (0: min(nproc, 16))")
     a = ap.parse_args()
     c = CONFIGS[a.config]
@@ -262,9 +263,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU reference
-def run_reference(g, rd, k, w, threads):
+def run_reference(g, rd, k, w, threads, files=None):
     """Times the reference's own front end (log-stamp deltas) on the given graph and reads.  Kills the process once
-    the front end is done (model construction is not timed)."""
+    the front end is done (model construction is not timed).  files: (gfa, fasta) already written for this input."""
     from phi_b200 import synth
     exe = os.path.join(ROOT, "oracle", "_ref", "PHI_ref")
     P = positions(g.walk_lengths(), k, w)
@@ -278,9 +279,12 @@ def run_reference(g, rd, k, w, threads):
         dt = time.time() - t0
         return dict(kind="port", P=P, Q=Q, t_index=dt, t_reads=None, t_paths=None)
     with tempfile.TemporaryDirectory() as tmp:
-        gfa, fa = os.path.join(tmp, "g.gfa"), os.path.join(tmp, "r.fa")
-        synth.write_gfa(g, gfa)
-        synth.write_fasta(rd, fa)
+        if files is None:
+            gfa, fa = os.path.join(tmp, "g.gfa"), os.path.join(tmp, "r.fa")
+            synth.write_gfa(g, gfa)
+            synth.write_fasta(rd, fa)
+        else:
+            gfa, fa = files
         env = dict(os.environ, PHI_STUB_DUMP=os.path.join(tmp, "dump.txt"))
         p = subprocess.Popen([exe, "-g", gfa, "-r", fa, "-o", os.path.join(tmp, "o.fa"), "-t", str(threads), "-k", str(k),
                               "-w", str(w)], env=env, stderr=subprocess.PIPE, stdout=subprocess.DEVNULL, text=True)
@@ -314,11 +318,16 @@ def main_reference(args):
     threads = os.cpu_count() or 1
     g, rd, desc, full = wl.reference_input(threads)
     vals, times, r = [], [], None
-    for i in range(args.warmup + args.steps):
-        r = run_reference(g, rd, args.k, args.w, threads)
-        if i >= args.warmup:
-            vals.append((r["P"] + r["Q"]) / r["t_index"])
-            times.append(r["t_index"])
+    from phi_b200 import synth
+    with tempfile.TemporaryDirectory() as tmp:                    # the input files are written once, every step is one run of the reference CLI
+        files = (os.path.join(tmp, "g.gfa"), os.path.join(tmp, "r.fa"))
+        synth.write_gfa(g, files[0])
+        synth.write_fasta(rd, files[1])
+        for i in range(args.warmup + args.steps):
+            r = run_reference(g, rd, args.k, args.w, threads, files)
+            if i >= args.warmup:
+                vals.append((r["P"] + r["Q"]) / r["t_index"])
+                times.append(r["t_index"])
     v = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True,
@@ -367,11 +376,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def kernel_profile(name):
-    """ncu numbers of the current build (profiles/kernel_traffic.json; re-captured per round, version inside)."""
+def kernel_profile(name, config):
+    """ncu numbers of the current build for this config (profiles/kernel_traffic.json: written by profiles/make_kernel_traffic.py from
+    an `ncu --set full` capture of the same bench command; re-captured per round, version inside)."""
     tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     try:
-        j = json.load(open(tp))
+        j = json.load(open(tp)).get(config, {})
         return j.get(name, {}), j.get("source")
     except Exception:
         return {}, None
@@ -563,8 +573,8 @@ def main_gpu(args):
     if not args.no_extras:
         # ---- the merged result and its digest (the same at every N), the N-rank parity case
         t0 = time.time()
-        parts = D.gather_results(full, "digest")
-        if rank == 0:
+        parts = D.gather_results(full, "digest") if not args.no_digest else None
+        if rank == 0 and parts is not None:
             from phi_b200 import multi
             t1 = time.time()
             merged = multi.merge_results(parts, expand=False) if world > 1 else full
@@ -610,7 +620,7 @@ def main_gpu(args):
         kernels = {}
         for name, ms, alg, nunits in (("walk_sketch_kernel", tm["walk_kernel_ms"], walk_alg, share["unique_windows"]),
                                       ("read_sketch_kernel", tm["read_kernel_ms"], read_alg, res.read_kmer_positions)):
-            prof, _ = kernel_profile(name)
+            prof, _ = kernel_profile(name, args.config)
             ach = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             kernels[name] = {"kernel_ms": ms, "units_per_launch": int(nunits), "algorithmic_bytes_per_launch": alg, "achieved": ach, "frac": ach / peak,
                              "traffic": prof.get("dram_bytes_per_launch"), "issue_slot_util": prof.get("issue_slot_util"),
@@ -619,7 +629,7 @@ def main_gpu(args):
             "achieved": walk_eff / (tm["walk_kernel_ms"] * 1e-3) / 1e9 if tm["walk_kernel_ms"] > 0 else 0.0,
             "note": "bytes of ALL path k-mer positions the launch accounts for (identical chunks are sketched once): not a roofline figure"}
         dom = max(kernels, key=lambda n: kernels[n]["kernel_ms"])
-        _, prof_src = kernel_profile(dom)
+        _, prof_src = kernel_profile(dom, args.config)
         line = {"metric": METRIC, "value": units * args.steps / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u8/u64", "data": "synthetic" if args.config != "readme" else "README test files", "config": config_dict(wl, world),

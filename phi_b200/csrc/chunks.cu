@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) step_pass_kernel(const uint32_t *walk_vtx
 // decoupled look-back over one 64-bit word per tile; nothing but walk_vtx is read and nothing but step_base (and the few
 // per-chunk / per-walk values) is written.  The scanned value: bits [0,35) bases since the last walk start, [35,61) chunk
 // starts, bit 61 "a walk started" (the bases of the left operand are discarded); bits 62-63 of a tile word: 1 = aggregate, 2 = prefix.
-constexpr int FS_THREADS = 256;   // every thread owns FS_ITEMS consecutive steps (template parameter: 4, 8 or 16; PHI_GPU_FS_ITEMS picks, default 8)
+// every thread owns FS_ITEMS consecutive steps (4, 8 or 16; PHI_GPU_FS_ITEMS), a tile has FS_THREADS threads (128 or 256; PHI_GPU_FS_THREADS)
 constexpr uint64_t FS_BASES = (1ull << 35) - 1, FS_CHUNKS = ((1ull << 26) - 1) << 35, FS_RESET = 1ull << 61, FS_VALUE = (1ull << 62) - 1;
 __device__ __forceinline__ uint64_t fs_comb(uint64_t a, uint64_t b)           // a, then b
 {
@@ -150,8 +150,8 @@ __device__ __forceinline__ uint64_t fs_comb(uint64_t a, uint64_t b)           //
     if (b & FS_RESET) return (b & FS_BASES) | chunks | FS_RESET;
     return (((a & FS_BASES) + (b & FS_BASES)) & FS_BASES) | chunks | (a & FS_RESET);
 }
-template <int FS_ITEMS>
-__global__ void __launch_bounds__(FS_THREADS, FS_ITEMS >= 16 ? 2 : 4) fused_steps_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
+template <int FS_ITEMS, int FS_THREADS>
+__global__ void __launch_bounds__(FS_THREADS, (FS_ITEMS >= 16 ? 2 : 4) * (256 / FS_THREADS)) fused_steps_kernel(const uint32_t *walk_vtx, const uint64_t *walk_off, uint32_t n_walks, uint64_t n_steps,
                                                                     const uint4 *vinfo, uint32_t n_vtx, unsigned long long *tile_state, uint32_t *ticket, uint32_t *step_base,
                                                                     uint32_t *chunk_step, uint32_t *c_walk, uint64_t *walk_len, unsigned long long *ctr)
 {
@@ -590,6 +590,12 @@ cudaError_t walk_step_pass(const uint32_t *walk_vtx, const uint64_t *walk_off, u
     return cudaSuccess;
 }
 
+static int fs_threads()
+{
+    static int v = 0;
+    if (!v) { const char *e = getenv("PHI_GPU_FS_THREADS"); v = e ? atoi(e) : 256; if (v != 128 && v != 256) v = 256; }
+    return v;
+}
 static int fs_items()
 {
     static int v = 0;
@@ -614,15 +620,14 @@ cudaError_t walk_steps_fused(const uint32_t *walk_vtx, const uint64_t *walk_off,
     }
     if (tile_last <= tile_first) return cudaSuccess;
     const unsigned grid = (unsigned)(tile_last - tile_first);
-    switch (fs_items()) {
-        case 4: fused_steps_kernel<4><<<grid, FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr); break;
-        case 16: fused_steps_kernel<16><<<grid, FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr); break;
-        default: fused_steps_kernel<8><<<grid, FS_THREADS, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr); break;
-    }
+#define PHI_FS_LAUNCH(I, T) fused_steps_kernel<I, T><<<grid, T, 0, st>>>(walk_vtx, walk_off, n_walks, n_steps, vinfo, n_vtx, tile_state, ticket, step_base, chunk_step, c_walk, walk_len, ctr)
+    if (fs_threads() == 128) { switch (fs_items()) { case 4: PHI_FS_LAUNCH(4, 128); break; case 16: PHI_FS_LAUNCH(16, 128); break; default: PHI_FS_LAUNCH(8, 128); break; } }
+    else { switch (fs_items()) { case 4: PHI_FS_LAUNCH(4, 256); break; case 16: PHI_FS_LAUNCH(16, 256); break; default: PHI_FS_LAUNCH(8, 256); break; } }
+#undef PHI_FS_LAUNCH
     PHI_LAUNCH_CHECK();
     return cudaSuccess;
 }
-uint64_t walk_steps_fused_tile_steps() { return (uint64_t)FS_THREADS * fs_items(); }
+uint64_t walk_steps_fused_tile_steps() { return (uint64_t)fs_threads() * fs_items(); }
 uint64_t walk_steps_fused_tiles(uint64_t n_steps) { const uint64_t t = walk_steps_fused_tile_steps(); return (n_steps + t - 1) / t; }
 
 cudaError_t walk_step_finalize(const ChunkTable &C, const PackedStep *packed, const uint64_t *scanned, const uint64_t *walk_off, uint32_t n_walks,

@@ -94,13 +94,16 @@ extern "C" int phi_index_result_merge(const phi_index_result *const *parts, int 
         }
         if (live.empty()) continue;
         if (live.size() == 1) {                                           // the usual case: all groups of this rank come from one GPU
+            // block copies: the groups, their vertex lists and their member walks lie back to back in the part
             const int p = live[0]; const phi_index_result *r = parts[p];
-            for (uint32_t g = cur[p]; g < end[p]; ++g) {
-                o_len[ng] = r->group_len[g]; o_moff[ng] = (uint32_t)nm;
-                memcpy(o_vtx + nv, r->group_vtx + gvoff[p][g], (size_t)r->group_len[g] * 4); nv += r->group_len[g];
-                for (uint32_t i = r->group_member_off[g]; i < r->group_member_off[g + 1]; ++i) put_member(member(r, i));
-                ++ng;
-            }
+            const uint32_t g0 = cur[p], g1 = end[p];
+            const uint32_t m0 = r->group_member_off[g0], m1 = r->group_member_off[g1];
+            memcpy(o_len + ng, r->group_len + g0, (size_t)(g1 - g0));
+            memcpy(o_vtx + nv, r->group_vtx + gvoff[p][g0], (size_t)(gvoff[p][g1] - gvoff[p][g0]) * 4); nv += gvoff[p][g1] - gvoff[p][g0];
+            for (uint32_t g = g0; g < g1; ++g) o_moff[ng++] = (uint32_t)(nm + (r->group_member_off[g] - m0));
+            if (w16 && r->member_walk16) { memcpy(o_w16 + nm, r->member_walk16 + m0, (size_t)(m1 - m0) * 2); nm += m1 - m0; }
+            else if (!w16 && r->member_walk32) { memcpy(o_w32 + nm, r->member_walk32 + m0, (size_t)(m1 - m0) * 4); nm += m1 - m0; }
+            else for (uint32_t i = m0; i < m1; ++i) put_member(member(r, i));
             continue;
         }
         for (int p : live) keys[p] = key_of(parts[p]->group_vtx + gvoff[p][cur[p]], parts[p]->group_len[cur[p]]);
