@@ -259,6 +259,10 @@ const phi_graph_view *phi_host_graph_view(const phi_host_graph *g);
 const char *phi_host_graph_walk_name(const phi_host_graph *g, uint32_t walk);       /* sample + "." + haplotype index */
 const char *phi_host_graph_segment_name(const phi_host_graph *g, uint32_t vtx);
 uint64_t phi_host_graph_n_links(const phi_host_graph *g);
+/* walk steps (u -> v consecutive in a walk) that no L-line backs.  0 for graphs written by pangenome builders; only then is the order
+ * of the vertices inside an anchor independent of how ties between equally valid topological orders are broken (the reference's
+ * Kahn order, /root/reference/src/ILP_index.cpp:116-147, and this loader's may break them differently). */
+uint64_t phi_host_graph_unlinked_steps(const phi_host_graph *g);
 void phi_host_graph_free(phi_host_graph *g);
 int phi_host_reads_load(const char *path, phi_host_reads **out, char *err, size_t errlen);
 const phi_reads_view *phi_host_reads_view(const phi_host_reads *r);

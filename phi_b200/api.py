@@ -75,6 +75,8 @@ def load_library():
     lib.phi_host_graph_segment_name.argtypes = [C.c_void_p, C.c_uint32]
     lib.phi_host_graph_n_links.restype = C.c_uint64
     lib.phi_host_graph_n_links.argtypes = [C.c_void_p]
+    lib.phi_host_graph_unlinked_steps.restype = C.c_uint64
+    lib.phi_host_graph_unlinked_steps.argtypes = [C.c_void_p]
     lib.phi_host_graph_free.argtypes = [C.c_void_p]
     lib.phi_host_reads_load.restype = C.c_int
     lib.phi_host_reads_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
@@ -117,6 +119,7 @@ def load_gfa(path):
                        [lib.phi_host_graph_walk_name(h, i).decode() for i in range(nw)])
         g.segment_names = [lib.phi_host_graph_segment_name(h, i).decode() for i in range(nv)]
         g.n_links = int(lib.phi_host_graph_n_links(h))
+        g.n_unlinked_steps = int(lib.phi_host_graph_unlinked_steps(h))
         return g
     finally:
         lib.phi_host_graph_free(h)

@@ -17,7 +17,8 @@
 //     arc, gfa-base.cpp:421-430), strands dropped (ILP_index.cpp:77-86); Kahn order with a FIFO queue seeded in vertex
 //     order (:116-147).  The order of a vertex's arcs (which only breaks ties between equally valid topological orders;
 //     the reference's comes out of gfatools' in-place radix sort) is L-line order here: top_order_map may differ from the
-//     reference's in such ties, the front end's results cannot (SURVEY.md §9 rule 8).
+//     reference's in such ties, the front end's results cannot (SURVEY.md §9 rule 8) as long as every walk step follows an
+//     L-line: phi_host_graph_unlinked_steps() counts the steps that do not (0 for every graph a pangenome builder writes).
 //   * reads: kseq_read — header at the next '>' or '@', name up to the first white space, sequence lines concatenated
 //     with one trailing '\r' stripped, FASTQ quality skipped and length-checked; parsing stops at the first malformed
 //     record (kseq returns -2 and read_ip_reads' loop ends)
@@ -88,6 +89,7 @@ struct phi_host_graph {
     std::string seg_bases;
     std::vector<uint32_t> walk_vtx;
     std::vector<int32_t> top_order_map;
+    uint64_t n_unlinked_steps = 0;
     std::vector<std::string> walk_names, seg_names;
     uint64_t n_links = 0;
 };
@@ -225,14 +227,15 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
                 wk.sample.assign(f[0].first, f[0].second); wk.hap = atoi(std::string(f[1].first, f[1].second).c_str());
                 const char *c = f[5].first, *send = f[5].second;
                 wk.v.reserve((size_t)(send - c) / 4);
+                // tokens as gfa_parse_W cuts them (gfa-io.cpp:395-408): a token runs from one '>' / '<' to the next, and the FIRST
+                // token starts at the first byte of the field whatever that byte is (it takes the orientation marker's place:
+                // the name is what follows it); names that are no segment are dropped
                 while (c < send) {
-                    if (*c == '>' || *c == '<') {
-                        const char *d = c + 1;
-                        while (d < send && *d != '>' && *d != '<') ++d;
-                        const uint32_t id = name2id.find(c + 1, (uint32_t)(d - c - 1), false);
-                        if (id != 0xFFFFFFFFu) wk.v.push_back(id << 1 | (*c == '<' ? 1u : 0u));
-                        c = d;
-                    } else ++c;
+                    const char *d = c + 1;
+                    while (d < send && *d != '>' && *d != '<') ++d;
+                    const uint32_t id = name2id.find(c + 1, (uint32_t)(d - c - 1), false);
+                    if (id != 0xFFFFFFFFu) wk.v.push_back(id << 1 | (*c == '<' ? 1u : 0u));
+                    c = d;
                 }
                 walks.push_back(std::move(wk));
             }
@@ -297,6 +300,17 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
             G->top_order_map[u] = next++;
             for (uint32_t w : adj[u]) if (--indeg[w >> 1] == 0) q.push(w >> 1);
         }
+        // walk steps that no L-line backs: where there are none (the rule for real graphs) the order of an anchor's vertices is walk
+        // order under ANY valid topological order, so the Kahn tie-breaks above cannot show; where there are some, the reference's own
+        // tie-breaks (gfatools' arc sort) would decide the order of those two vertices inside an anchor, and ours may differ
+        G->n_unlinked_steps = 0;
+        for (size_t h = 0; h + 1 < G->walk_off.size(); ++h)
+            for (uint64_t s = G->walk_off[h]; s + 1 < G->walk_off[h + 1]; ++s) {
+                const uint32_t a = G->walk_vtx[s], b = G->walk_vtx[s + 1] << 1;
+                bool linked = false;
+                for (uint32_t x : adj[a]) linked |= x == b;
+                G->n_unlinked_steps += linked ? 0 : 1;
+            }
     }
     pt.lap("adjacency + Kahn order");
     G->view.n_vtx = V; G->view.seg_off = G->seg_off.data(); G->view.seg_bases = (const uint8_t *)G->seg_bases.data();
@@ -310,6 +324,7 @@ extern "C" const phi_graph_view *phi_host_graph_view(const phi_host_graph *g) { 
 extern "C" const char *phi_host_graph_walk_name(const phi_host_graph *g, uint32_t h) { return g && h < g->walk_names.size() ? g->walk_names[h].c_str() : ""; }
 extern "C" const char *phi_host_graph_segment_name(const phi_host_graph *g, uint32_t v) { return g && v < g->seg_names.size() ? g->seg_names[v].c_str() : ""; }
 extern "C" uint64_t phi_host_graph_n_links(const phi_host_graph *g) { return g ? g->n_links : 0; }
+extern "C" uint64_t phi_host_graph_unlinked_steps(const phi_host_graph *g) { return g ? g->n_unlinked_steps : 0; }
 extern "C" void phi_host_graph_free(phi_host_graph *g) { delete g; }
 
 extern "C" int phi_host_reads_load(const char *path, phi_host_reads **out, char *err, size_t errlen)

@@ -88,6 +88,9 @@ GFA_EDGE = "\n".join([
     "W\ts1\t0\tchr\t0\t0\t>a>zz>b>c",
     "W\ts1\t1\tchr\t0\t0\t<c<b<a",                 # reversed walk: flipped to >a>b>c
     "W\ts2\t7\tchr\t0\t0\t>a>nosuch>b",            # unknown segment dropped
+    "W\ts3\t0\tchr\t0\t0\tXa>b",                   # gfa_parse_W takes the first token whatever its first byte is: name "a", forward
+    "W\ts4\t0\tchr\t0\t0\tb>c",                    # ... here the first token's name is empty: dropped, the walk is >c
+    "W\ts5\t0\tchr\t0\t0\t>a>c",                   # a -> c is backed by no L-line
     "W\tshort\t0\tchr",                            # too few fields: ignored
     "S\tlate\tAC",                                 # defined after the W-lines
     ""]) + "\n"
@@ -104,7 +107,8 @@ def test_gfa_edge_cases_match_the_reference_parser(tmp_path, crlf, gz):
     ref = phi_io.graph_from_arrays(d)
     g = phi_b200.load_gfa(path)
     assert_same_graph(g, ref, ref.walk_names)
-    assert g.segment_names[:2] == ["a", "zz"] and g.walk_names == ["s1.0", "s1.1", "s2.7"]
+    assert g.segment_names[:2] == ["a", "zz"] and g.walk_names == ["s1.0", "s1.1", "s2.7", "s3.0", "s4.0", "s5.0"]
+    assert g.n_unlinked_steps == 1                                  # only s5's a -> c
     wo = g.walk_off.astype(int)
     assert g.walk_vtx[wo[1]:wo[2]].tolist() == [0, 2, 3]           # the reversed walk came out forward
 
