@@ -434,20 +434,29 @@ class Dist:
         if self.world == 1:
             return [part]
         import pickle
-        d = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(), f"phi_bench_{os.environ.get('MASTER_PORT', '0')}_{tag}")
-        os.makedirs(d, exist_ok=True)
-        with open(os.path.join(d, f"part{self.rank}.pkl"), "wb") as f:
-            pickle.dump(part, f, protocol=4)
-        self.dist.barrier()
+        import shutil
+        need = 2 * self.world * (part.wire_bytes() + (1 << 20))
+        base = next((b for b in ("/dev/shm", tempfile.gettempdir()) if os.path.isdir(b) and shutil.disk_usage(b).free > need), tempfile.gettempdir())
+        d = os.path.join(base, f"phi_bench_{os.environ.get('MASTER_PORT', '0')}_{tag}")
+        ok = 1.0
+        try:
+            os.makedirs(d, exist_ok=True)
+            with open(os.path.join(d, f"part{self.rank}.pkl"), "wb") as f:
+                pickle.dump(part, f, protocol=4)
+        except Exception:
+            ok = 0.0
+        ok = min(self.reduce([ok], "sum")[0] / self.world, ok)       # every rank takes the same path (the reduce is the barrier)
         parts = None
-        if self.rank == 0:
-            parts = []
-            for r in range(self.world):
-                with open(os.path.join(d, f"part{r}.pkl"), "rb") as f:
-                    parts.append(pickle.load(f))
-                os.remove(os.path.join(d, f"part{r}.pkl"))
-            os.rmdir(d)
+        if self.rank == 0 and ok == 1.0:
+            try:
+                parts = []
+                for r in range(self.world):
+                    with open(os.path.join(d, f"part{r}.pkl"), "rb") as f:
+                        parts.append(pickle.load(f))
+            except Exception:
+                parts = None
         self.dist.barrier()
+        shutil.rmtree(d, ignore_errors=True) if self.rank == 0 else None
         return parts
 
     def close(self):
@@ -483,7 +492,9 @@ def parity_case(rank, world, local, D, partition):
     ix.close()
     parts = D.gather_results(part, "parity")
     verdict = None
-    if rank == 0:
+    if rank == 0 and parts is None:
+        verdict = "not checked (no scratch space for the parts)"
+    elif rank == 0:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import phi_io
         got = multi.merge_results(parts)
@@ -574,6 +585,8 @@ def main_gpu(args):
         # ---- the merged result and its digest (the same at every N), the N-rank parity case
         t0 = time.time()
         parts = D.gather_results(full, "digest") if not args.no_digest else None
+        if rank == 0 and parts is None and not args.no_digest:
+            extras["result_digest"] = None                   # (the parts could not be handed to rank 0: no scratch space)
         if rank == 0 and parts is not None:
             from phi_b200 import multi
             t1 = time.time()

@@ -110,11 +110,11 @@ __global__ void __launch_bounds__(256) group_flags_kernel(FilterArgs A, FilterWo
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint32_t f = 0; unsigned long long members = 0, vtx = 0;
     if (i < A.n_hits) {
-        const uint32_t slot = W.hit_slot[i];
-        const uint2 gs = W.g_slot[slot];
-        if (gs.x == (uint32_t)i) {
-            if (!W.rank_drop[A.hit_rank[i]]) { f = 1; members = gs.y; vtx = A.hit_nv[i]; }
-            else W.g_slot[slot].x = G_DROPPED;                           // the other hits of the slot only ever compare it with their own id
+        // most hits belong to dropped ranks (minimizers every walk carries): the drop flags (one byte per rank, L2-resident) are looked
+        // at first, the scattered slot of the group table only for the hits that survive
+        if (!W.rank_drop[A.hit_rank[i]]) {
+            const uint2 gs = W.g_slot[W.hit_slot[i]];
+            if (gs.x == (uint32_t)i) { f = 1; members = gs.y; vtx = A.hit_nv[i]; }
         }
         flags[i] = f;
     }
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(256) group_fill_kernel(FilterArgs A, FilterWor
     const uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 2;
     const uint32_t sub = threadIdx.x & 3;
     if (i >= A.n_hits) return;
+    if (W.rank_drop[A.hit_rank[i]]) return;                               // (before the scattered read below: most hits stop here)
     const uint32_t j = W.g_slot[W.hit_slot[i]].x;                         // output index of the hit's group
-    if (j == G_DROPPED) return;
     const uint32_t c = A.hit_walk[i];                                     // hits of representatives: the chunk takes the place of the walk
     const uint32_t s0 = G.cm_off[c], n = G.cm_off[c + 1] - s0;
     const uint32_t hs = W.hit_sub[i];

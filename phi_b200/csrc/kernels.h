@@ -123,6 +123,7 @@ struct WalkSketchArgs {
     // hits of the representative chunks: hit_chunk = chunk id, hit_pos = p + w - (first base of the chunk)
     uint32_t *hit_rank, *hit_chunk, *hit_pos; uint64_t *hit_voff; uint8_t *hit_nv; uint64_t *hit_hash;
     int32_t *vtx_pool;
+    uint4 *probe;                                             // optional [2 * hit_cap]: the group table's 32-byte probe record of every hit (filter.cu)
     uint64_t hit_cap, vtx_cap;
     unsigned long long *ctr;
 };

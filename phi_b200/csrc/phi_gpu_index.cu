@@ -895,7 +895,7 @@ static int reads_sketch_launch(phi_gpu_index_ctx *ctx, int k, int w, const Reads
     A.read_bases = ctx->read_bases.as<uint8_t>() + 16; A.read_off = ctx->read_off.as<uint64_t>();
     A.n_reads = ctx->n_reads; A.total_bases = ctx->read_total; A.tile_first_read = ctx->tile_first_read.as<uint64_t>();
     A.k = k; A.w = w; A.table = ctx->table.as<uint64_t>(); A.table_mult = rs.cap; A.table_limit = limit; A.ctr = d_ctr;
-    { static int bulk = -1; if (bulk < 0) { const char *e = getenv("PHI_GPU_READ_BULK"); bulk = e ? atoi(e) : 0; } A.bulk = bulk; }
+    { static int bulk = -1; if (bulk < 0) { const char *e = getenv("PHI_GPU_READ_BULK"); bulk = e ? atoi(e) : 1; } A.bulk = bulk; }
     CU(cudaEventRecord(ctx->ev[EV_RK0], ctx->st));
     if (ctx->n_pieces > 1 && !rs.relaunch) {
         // the reads are still arriving: sketch the tiles whose bases are complete after every piece
@@ -1037,6 +1037,7 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
         CU(ctx->hit_voff.reserve(hit_cap * 8)); CU(ctx->hit_nv.reserve(hit_cap));
         if (mode == WALK_MODE_ALL) CU(ctx->hit_hash.reserve(hit_cap * 8));
         CU(ctx->vtx_pool.reserve(vtx_cap * 4));
+        if (mode == WALK_MODE_PROBE) CU(ctx->probe.reserve(hit_cap * 32 + 32));
         CU(cudaMemsetAsync(d_ctr + CTR_HITS, 0, 2 * 8, ctx->st));
         CU(cudaMemsetAsync(ctx->hseg_cnt.p, 0, (size_t)NT_ * SEG_PER_TILE * 4, ctx->st));
         CU(cudaMemsetAsync(ctx->c_emitted.p, 0, (size_t)NC * 4, ctx->st));
@@ -1054,6 +1055,7 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
         A.hit_voff = ctx->hit_voff.as<uint64_t>(); A.hit_nv = ctx->hit_nv.as<uint8_t>();
         A.hit_hash = mode == WALK_MODE_ALL ? ctx->hit_hash.as<uint64_t>() : nullptr;
         A.vtx_pool = ctx->vtx_pool.as<int32_t>(); A.hit_cap = hit_cap; A.vtx_cap = vtx_cap; A.ctr = d_ctr;
+        A.probe = mode == WALK_MODE_PROBE ? ctx->probe.as<uint4>() : nullptr;
         CU(cudaEventRecord(ctx->ev[EV_WK0], ctx->st));
         CU(launch_walk_sketch(A, NT_, ctx->st)); ctx->launches++;
         CU(cudaEventRecord(ctx->ev[EV_WK1], ctx->st));
@@ -1102,8 +1104,10 @@ static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, Fi
     W.hit_sub = nullptr;
     if (!owner_side) { CU(ctx->hit_sub.reserve(n * 4 + 4)); W.hit_sub = ctx->hit_sub.as<uint32_t>(); }
     W.weight = weight; W.chunk_weight = chunk_weight;
-    CU(probeb.reserve(n * 32 + 32));
-    CU(filter_build_probe(A, probeb.as<uint4>(), ctx->st, &ctx->launches));
+    if (owner_side) {                                                     // received summaries: probe records from their SoA arrays
+        CU(probeb.reserve(n * 32 + 32));
+        CU(filter_build_probe(A, probeb.as<uint4>(), ctx->st, &ctx->launches));
+    }                                                                     // (the walk kernel wrote the probe records of its own hits)
     W.probe = probeb.as<uint4>();
     for (;;) {
         CU(tabb.reserve(gcap * 8));

@@ -131,6 +131,13 @@ __device__ __forceinline__ void walk_tile_body(Tile &t, const WalkSketchArgs &A,
                 if (A.hit_hash) A.hit_hash[hi_idx] = hv;
                 if (!slow) for (int i = 0; i < nv; ++i) A.vtx_pool[vo + i] = (int32_t)t.stepv[j0 + i];
                 else anchor_slow(t, j0, n_raw, A.top_order_map, A.vtx_pool + vo);
+                if (A.probe) {                                       // (rank, vertices, first 6 vertices): what the group table compares
+                    uint32_t v[6];
+                    #pragma unroll
+                    for (int q = 0; q < 6; ++q) v[q] = q < nv ? (slow ? (uint32_t)A.vtx_pool[vo + q] : t.stepv[j0 + q]) : 0u;
+                    A.probe[2 * hi_idx] = make_uint4((uint32_t)rank, (uint32_t)nv, v[0], v[1]);
+                    A.probe[2 * hi_idx + 1] = make_uint4(v[2], v[3], v[4], v[5]);
+                }
             }
         }
         __syncthreads();

@@ -21,13 +21,15 @@ import phi_b200
 
 
 def stamps(exe, gfa, fa, tmp, env=None, threads=None):
-    e = dict(os.environ, PHI_STUB_DUMP=os.path.join(tmp, "dump.txt"))
+    e = dict(os.environ, PHI_STUB_DUMP=os.path.join(tmp, "dump.txt"), PHI_ADAPTER_TIMES="1")
     e.update(env or {})
     t0 = time.time()
     p = subprocess.Popen([exe, "-g", gfa, "-r", fa, "-o", os.path.join(tmp, "o.fa"), "-t", str(threads or os.cpu_count())], env=e,
                          stderr=subprocess.PIPE, stdout=subprocess.DEVNULL, text=True)
     st = {}
     for line in p.stderr:
+        if line.startswith("[phi_adapter]"):
+            st["adapter"] = line.strip()                   # flat views / wait for the CUDA context / run
         m = re.match(r"\[M::ILP_function::([\d.]+)\*", line)
         if m:
             for key in ("Graph has", "Haplotypes sketched", "Indexed reads", "Filtered/Retained"):
@@ -42,6 +44,14 @@ def stamps(exe, gfa, fa, tmp, env=None, threads=None):
 
 c = Case("mhc4")
 out = {"config": "BASELINE configs[0]: README test (MHC_4.gfa.gz + CHM13_reads.fq.gz), -k31 -w25", "host_threads": os.cpu_count()}
+try:
+    out["gpu_persistence_mode"] = subprocess.run(["nvidia-smi", "--query-gpu=persistence_mode", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+    # what a fresh process pays before it can launch anything: phi_gpu_index_create = CUDA context creation + a few small allocations
+    code = ("import ctypes, time; lib = ctypes.CDLL(%r); ctx = ctypes.c_void_p(); t = time.time(); "
+            "rc = lib.phi_gpu_index_create(0, ctypes.byref(ctx)); print(rc, time.time() - t)") % os.path.join(ROOT, "phi_b200", "libphi_gpu_index.so")
+    out["ctx_create_s_fresh_process"] = [float(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True).stdout.split()[1]) for _ in range(3)]
+except Exception:
+    pass
 with tempfile.TemporaryDirectory() as tmp:
     gfa, fa = os.path.join(tmp, "g.gfa"), os.path.join(tmp, "r.fa")
     synth.write_gfa(c.graph, gfa)
