@@ -227,31 +227,16 @@ __global__ void __launch_bounds__(FS_THREADS, (FS_ITEMS >= 16 ? 2 : 4) * (256 / 
         else {
             if (lane == 0) ((volatile unsigned long long *)tile_state)[tile] = (1ull << 62) | total;
             uint64_t run = 0;                                              // aggregate of the tiles already folded in (nearer than the window)
-            // All resident tiles move in step, so the nearest tile whose prefix is known lies a few hundred tiles back: every lane
-            // looks at LB_K predecessors per round (independent loads: one latency for 32 * LB_K tiles), nearest in lane 0, slot 0.
-            constexpr int LB_K = 8;
-            for (int64_t top = (int64_t)tile - 1;; top -= 32 * LB_K) {
-                unsigned long long w[LB_K];
-                bool ready;
-                do {
-                    ready = true;
-                    #pragma unroll
-                    for (int i = 0; i < LB_K; ++i) {
-                        const int64_t j = top - ((int64_t)lane * LB_K + i);
-                        w[i] = j >= 0 ? ((volatile unsigned long long *)tile_state)[j] : (2ull << 62);   // before tile 0: an empty prefix
-                        ready &= (w[i] >> 62) != 0;
-                    }
-                } while (!ready);
-                // inside the lane: fold slot 0 .. the first slot with a known prefix (farther tiles come first in the combination)
-                uint64_t mine = 0; bool found = false;
-                #pragma unroll
-                for (int i = 0; i < LB_K; ++i) {
-                    if (!found) mine = fs_comb(w[i] & FS_VALUE, mine);
-                    found |= (w[i] >> 62) == 2;
-                }
-                const uint32_t pref = __ballot_sync(0xFFFFFFFFu, found);
+            // 32 predecessors per round, nearest in lane 0.  (Looking at 8 predecessors per lane per round was tried — one latency for 256
+            // tiles — and measured SLOWER, 8.7 ms instead of 6.4 ms on c4: a round then waits for the aggregate of every one of 256
+            // concurrently running tiles instead of 32.)
+            for (int64_t top = (int64_t)tile - 1;; top -= 32) {
+                const int64_t j = top - lane;
+                unsigned long long w = 2ull << 62;                          // before tile 0: an empty prefix
+                if (j >= 0) { do { w = ((volatile unsigned long long *)tile_state)[j]; } while (!(w >> 62)); }
+                const uint32_t pref = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 2);
                 const int stop = pref ? __ffs(pref) - 1 : 31;                // lanes 0..stop take part
-                uint64_t v2 = lane <= stop ? mine : 0ull;
+                uint64_t v2 = lane <= stop ? (w & FS_VALUE) : 0ull;
                 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_down_sync(0xFFFFFFFFu, v2, d); if (lane + d < 32) v2 = fs_comb(o, v2); }
                 run = fs_comb(__shfl_sync(0xFFFFFFFFu, v2, 0), run);

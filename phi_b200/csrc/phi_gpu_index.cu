@@ -101,6 +101,7 @@ struct phi_gpu_index_ctx {
     uint64_t *h_words = nullptr; size_t h_words_cap = 0;   // pinned: gathered words of the small collectives
     uint64_t *h_route = nullptr;         // pinned [512]: small host -> device parameter blocks of the record exchange
 
+    size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting L2 set aside at create (0: not available)
     std::string err2;                      // error text of the graph-preparation thread (moved into err when its failure is reported)
     uint64_t launches2 = 0;                // kernels launched by that thread
     int fail(int code, const std::string &m) { err = m; return code; }
@@ -140,6 +141,11 @@ extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
     }
     phi_gpu_index_ctx *ctx = new phi_gpu_index_ctx();
     ctx->device = device;
+    if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {      // L2 set-aside for the vertex records of the step kernel
+        const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)prop.l2CacheSize / 2);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) { ctx->l2_persist_bytes = want; ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize; }
+        else cudaGetLastError();
+    }
     if (const char *e_shift = getenv("PHI_GPU_CHUNK_SHIFT")) { int v = atoi(e_shift); if (v >= 4 && v <= 24) ctx->chunk_shift = v; }   // tuning only: results never depend on it
     if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return PHI_ERR_CUDA; }
     // (a higher priority for this stream was tried: the preparation then finishes earlier but the read kernel, which fills every SM,
@@ -397,6 +403,17 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     CUP(ctx->chunk_step.reserve((S + 2) * 4)); CUP(ctx->c_walk.reserve((S + 2) * 4));       // at most one chunk per step
     CUP(ctx->fs_state.reserve(walk_steps_fused_tiles(S) * 8 + 16));
     CUP(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, st)); CUP(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, st));
+    // the step kernel gathers one 16-byte vertex record per step while it streams the steps through L2: keep the records resident
+    // (persisting access window on this stream; measured: profiles/r2_variants_ab.txt)
+    const bool l2_pin = ctx->l2_persist_bytes > 0 && !getenv("PHI_GPU_NO_L2_PIN");
+    if (l2_pin) {
+        cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+        av.accessPolicyWindow.base_ptr = ctx->coord.p;
+        av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)V * 16, ctx->l2_window_max);
+        av.accessPolicyWindow.hitRatio = std::min(1.0f, (float)ctx->l2_persist_bytes / (float)std::max<size_t>(av.accessPolicyWindow.num_bytes, 1));
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CUP(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     if (ctx->n_pieces && ctx->n_wpieces > 1) {
         // phi_gpu_index_run: the walk steps are still arriving; every piece is scanned as soon as it is there
         const uint64_t tile = walk_steps_fused_tile_steps();
@@ -416,7 +433,12 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
                             ctx->step_base.as<uint32_t>(), ctx->chunk_step.as<uint32_t>(), ctx->c_walk.as<uint32_t>(), ctx->walk_len.as<uint64_t>(), d_ctr,
                             st, launches));
     }
+    if (l2_pin) {
+        cudaStreamAttrValue av; memset(&av, 0, sizeof av);                 // window off again (num_bytes 0)
+        CUP(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     CUP(read_counters_on(ctx, st, ctr, h_ctr));                                             // wait 1
+    if (l2_pin) cudaCtxResetPersistingL2Cache();                          // the step kernel is done: its persisting lines become ordinary ones again
     if (h_ctr[CTR_BAD_VTX]) return ctx->fail2(PHI_ERR_ARG, "graph view: a walk step names a vertex id >= n_vtx");
     if (h_ctr[CTR_SEG_TOO_LONG]) return ctx->fail2(PHI_ERR_UNSUPPORTED, "segment of 2^31 bases or more");
     const bool fused = h_ctr[CTR_ZERO_STEPS] == 0;
@@ -1056,10 +1078,26 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
         A.hit_hash = mode == WALK_MODE_ALL ? ctx->hit_hash.as<uint64_t>() : nullptr;
         A.vtx_pool = ctx->vtx_pool.as<int32_t>(); A.hit_cap = hit_cap; A.vtx_cap = vtx_cap; A.ctr = d_ctr;
         A.probe = mode == WALK_MODE_PROBE ? ctx->probe.as<uint4>() : nullptr;
+        // every emitted minimizer looks up one bucket of the radix directory and then the spectrum: with the directory resident in L2
+        // (persisting access window) a probe costs one scattered DRAM access instead of two dependent ones
+        const bool l2_pin = ctx->l2_persist_bytes > 0 && mode == WALK_MODE_PROBE && !getenv("PHI_GPU_NO_L2_PIN");
+        if (l2_pin) {
+            cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+            av.accessPolicyWindow.base_ptr = ctx->dir.p;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(((size_t)1 << dbits) * 4 + 4, ctx->l2_window_max);
+            av.accessPolicyWindow.hitRatio = std::min(1.0f, (float)ctx->l2_persist_bytes / (float)std::max<size_t>(av.accessPolicyWindow.num_bytes, 1));
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CU(cudaStreamSetAttribute(ctx->st, cudaStreamAttributeAccessPolicyWindow, &av));
+        }
         CU(cudaEventRecord(ctx->ev[EV_WK0], ctx->st));
         CU(launch_walk_sketch(A, NT_, ctx->st)); ctx->launches++;
         CU(cudaEventRecord(ctx->ev[EV_WK1], ctx->st));
+        if (l2_pin) {
+            cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+            CU(cudaStreamSetAttribute(ctx->st, cudaStreamAttributeAccessPolicyWindow, &av));
+        }
         CU(read_counters(ctx));
+        if (l2_pin) cudaCtxResetPersistingL2Cache();
         o.n_hits = ctx->h_ctr[CTR_HITS]; o.n_hit_vtx = ctx->h_ctr[CTR_HIT_VTX];
         if (o.n_hits <= hit_cap && o.n_hit_vtx <= vtx_cap) break;
         if (attempt) return ctx->fail(PHI_ERR_CUDA, "walk hit buffers overflowed twice (internal error)");
@@ -1094,7 +1132,9 @@ static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, Fi
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
     const uint64_t n = A.n_hits;
     // distinct (rank, vertex list) groups are usually fewer than records, so start small and grow on overflow
-    uint64_t gcap = 1024; while (gcap < n / 2) gcap <<= 1;
+    // (load <= 50 % even if every record were its own group: on chromosome-scale inputs the table misses L2 and every extra probe is
+    // two more scattered DRAM sectors)
+    uint64_t gcap = 1024; while (gcap < n) gcap <<= 1;
     uint64_t &hint = owner_side ? ctx->gcap_hint2 : ctx->gcap_hint;
     if (owner_side) { gcap = 1024; while (gcap < 2 * n) gcap <<= 1; }     // at most n groups: the 80 % load limit is out of reach, no host wait needed
     else if (hint > gcap) gcap = hint;
