@@ -141,7 +141,10 @@ extern "C" int phi_gpu_index_create(int device, phi_gpu_index_ctx **out)
     }
     phi_gpu_index_ctx *ctx = new phi_gpu_index_ctx();
     ctx->device = device;
-    if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {      // L2 set-aside for the vertex records of the step kernel
+    // Opt-in (PHI_GPU_L2_PIN=1): an L2 set-aside with persisting access windows over the vertex records (step kernel) and the radix
+    // directory (walk kernel).  Measured on B200 (profiles/r2_variants_ab.txt): 48.94 vs 49.19 ms on c4, 2.13 vs 2.08 ms on c2 — the
+    // set-aside takes L2 away from everything else, so it stays off.
+    if (getenv("PHI_GPU_L2_PIN") && atoi(getenv("PHI_GPU_L2_PIN")) && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
         const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)prop.l2CacheSize / 2);
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) { ctx->l2_persist_bytes = want; ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize; }
         else cudaGetLastError();
@@ -403,9 +406,9 @@ static int stage_graph_prep(phi_gpu_index_ctx *ctx, int k, int w, std::vector<ui
     CUP(ctx->chunk_step.reserve((S + 2) * 4)); CUP(ctx->c_walk.reserve((S + 2) * 4));       // at most one chunk per step
     CUP(ctx->fs_state.reserve(walk_steps_fused_tiles(S) * 8 + 16));
     CUP(cudaMemsetAsync(d_ctr + CTR_ZERO_STEPS, 0, 8, st)); CUP(cudaMemsetAsync(d_ctr + CTR_CHUNK_FLAGS, 0, 8, st));
-    // the step kernel gathers one 16-byte vertex record per step while it streams the steps through L2: keep the records resident
-    // (persisting access window on this stream; measured: profiles/r2_variants_ab.txt)
-    const bool l2_pin = ctx->l2_persist_bytes > 0 && !getenv("PHI_GPU_NO_L2_PIN");
+    // the step kernel gathers one 16-byte vertex record per step while it streams the steps through L2: optionally keep the records
+    // resident (persisting access window on this stream; opt-in, see phi_gpu_index_create)
+    const bool l2_pin = ctx->l2_persist_bytes > 0;
     if (l2_pin) {
         cudaStreamAttrValue av; memset(&av, 0, sizeof av);
         av.accessPolicyWindow.base_ptr = ctx->coord.p;
@@ -1080,7 +1083,7 @@ static int stage_walks(phi_gpu_index_ctx *ctx, int k, int w, int mode, int dbits
         A.probe = mode == WALK_MODE_PROBE ? ctx->probe.as<uint4>() : nullptr;
         // every emitted minimizer looks up one bucket of the radix directory and then the spectrum: with the directory resident in L2
         // (persisting access window) a probe costs one scattered DRAM access instead of two dependent ones
-        const bool l2_pin = ctx->l2_persist_bytes > 0 && mode == WALK_MODE_PROBE && !getenv("PHI_GPU_NO_L2_PIN");
+        const bool l2_pin = ctx->l2_persist_bytes > 0 && mode == WALK_MODE_PROBE;
         if (l2_pin) {
             cudaStreamAttrValue av; memset(&av, 0, sizeof av);
             av.accessPolicyWindow.base_ptr = ctx->dir.p;
@@ -1132,9 +1135,9 @@ static int count_groups_adaptive(phi_gpu_index_ctx *ctx, const FilterArgs &A, Fi
     unsigned long long *d_ctr = ctx->ctr.as<unsigned long long>();
     const uint64_t n = A.n_hits;
     // distinct (rank, vertex list) groups are usually fewer than records, so start small and grow on overflow
-    // (load <= 50 % even if every record were its own group: on chromosome-scale inputs the table misses L2 and every extra probe is
-    // two more scattered DRAM sectors)
-    uint64_t gcap = 1024; while (gcap < n) gcap <<= 1;
+    // (a table twice this size, load <= 50 % whatever the data, was measured on c4: the filter stage went from 11.6 to 14.4 ms —
+    // the fill and the wider scatter cost more than the saved probes)
+    uint64_t gcap = 1024; while (gcap < n / 2) gcap <<= 1;
     uint64_t &hint = owner_side ? ctx->gcap_hint2 : ctx->gcap_hint;
     if (owner_side) { gcap = 1024; while (gcap < 2 * n) gcap <<= 1; }     // at most n groups: the 80 % load limit is out of reach, no host wait needed
     else if (hint > gcap) gcap = hint;

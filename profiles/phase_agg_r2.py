@@ -24,18 +24,19 @@ tot = sum(o[2] for o in out); tots = sum(o[3] for o in out); tott = sum(o[4] for
 print(f"total warp instructions {tot:.0f}, thread instructions {tott:.0f} (avg active lanes {tott / tot:.1f}), stall samples {tots:.0f}")
 T = "sketch_tile.cuh"; D = "device_common.cuh"; C = "sketch_common.cuh"
 K = "walk_sketch.cu" if kind == "walk" else "read_sketch.cu"
-phases = [("carve / layout / bounds", T, 76, 110), ("upcase + stage_chunk (pack, dirty mask)", T, 111, 142), ("extract_kmer / extract8", T, 144, 158),
-          ("general (shared-memory) core", T, 159, 378), ("window_minima (cross-lane combine)", T, 391, 424), ("fast_runs: geometry", T, 429, 441),
-          ("fast_runs: canonical k-mers rolled", T, 442, 458), ("fast_runs: in-lane prefix / suffix minima", T, 459, 474), ("fast_runs: dispatch on r", T, 475, 488),
-          ("fast_runs: validity, changed, starts", T, 489, 511), ("fast_runs: compaction of run starts", T, 512, 540),
-          ("murmur + fmix", D, 1, 56), ("toupper/is_acgt/code2/comp", D, 57, 110), ("rev2 / revcomp2", D, 111, 125), ("ascii expansion + hash_packed_kmer", D, 126, 160),
+phases = [("carve / layout / bounds", T, 76, 113), ("upcase + stage_chunk (pack, dirty mask)", T, 114, 146), ("extract_kmer / extract8", T, 147, 161),
+          ("general (shared-memory) core", T, 162, 400), ("window_minima (cross-lane combine)", T, 401, 436), ("fast_runs: geometry", T, 437, 452),
+          ("fast_runs: canonical k-mers rolled", T, 453, 469), ("fast_runs: in-lane prefix / suffix minima", T, 470, 485), ("fast_runs: dispatch on r", T, 486, 499),
+          ("fast_runs: validity, changed, starts", T, 500, 522), ("fast_runs: compaction of run starts", T, 523, 560),
+          ("murmur + fmix", D, 1, 87), ("toupper / is_acgt / code2 / comp_byte", D, 88, 99), ("rev2 / revcomp2", D, 100, 111), ("ascii expansion + hash_packed_kmer", D, 112, 136),
           ("block_scan2 / table_insert / load8", C, 1, 100)]
 if kind == "walk":
-    phases += [("spectrum_probe", K, 14, 28), ("anchor_slow / step_of", K, 29, 56), ("tile body: runs -> hash -> emit flags", K, 57, 92), ("tile body: probe + anchor size", K, 93, 111),
-               ("tile body: scan + segment + hit write", K, 112, 140), ("kernel: tile record, step table", K, 141, 184), ("kernel: gather bases through the steps", K, 185, 216),
-               ("kernel: dispatch", K, 217, 235)]
+    phases += [("spectrum_probe", K, 14, 30), ("anchor_slow / step_of", K, 31, 57), ("tile body: runs -> hash -> emit flags", K, 58, 92), ("tile body: probe + anchor size", K, 93, 110),
+               ("tile body: scan + segment + hit / probe record write", K, 111, 147), ("kernel: tile record, step table", K, 148, 187), ("kernel: gather bases through the steps", K, 188, 218),
+               ("kernel: dispatch", K, 219, 235)]
 else:
-    phases += [("tile body: runs -> hash -> insert", K, 13, 52), ("kernel: boundaries -> window masks", K, 53, 97), ("kernel: stage bases", K, 98, 112), ("kernel: dispatch", K, 113, 120)]
+    phases += [("tile body: runs -> hash -> insert", K, 13, 53), ("kernel: set-up + bulk copy issue + first load", K, 54, 95), ("kernel: boundaries -> window masks", K, 96, 127),
+               ("kernel: wait for the bulk copy + stage bases", K, 128, 150), ("kernel: dispatch", K, 151, 160)]
 acc = 0
 for name, f, a, b in phases:
     i = sum(o[2] for o in out if o[0] == f and a <= o[1] <= b)
