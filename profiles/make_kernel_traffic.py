@@ -14,12 +14,12 @@ if "walk_sketch_kernel" in out:
     out = {}                                             # round-1 layout (not keyed by config)
 for arg in sys.argv[1:]:
     cfg, rest = arg.split("=", 1)
-    summ_p, bench_p = rest.split(":", 1)
-    summ = json.load(open(summ_p))
+    summ_ps, bench_p = rest.split(":", 1)
     bench = json.loads([l for l in open(bench_p) if l.startswith("{")][-1])
     units = {"walk_sketch_kernel": bench["sharing"]["unique_windows"], "read_sketch_kernel": bench["units_per_step"]["read_kmer_positions"]}
-    ent = {"source": f"ncu --set full --clock-control none, profiles/{os.path.basename(summ_p)} ({summ['version']})"}
-    for k in summ["kernels"]:
+    summs = [json.load(open(q)) for q in summ_ps.split("+")]          # later summaries override earlier ones kernel by kernel
+    ent = {"source": "ncu --set full --clock-control none, " + " + ".join(f"profiles/{os.path.basename(q)}" for q in summ_ps.split("+")) + f" ({summs[-1]['version']})"}
+    for k in [k for sm in summs for k in sm["kernels"]]:
         name = k["name"].split("(")[0].split("<")[0].replace("void ", "").replace("phi::", "")
         for suffix in ("_r64", "_r72"):                      # register-budget variants of the walk kernel
             if name.endswith(suffix):
@@ -30,7 +30,7 @@ for arg in sys.argv[1:]:
                 return None
             x = float(v[0].replace(",", ""))
             u = v[1]
-            return x * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
+            return x * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}.get(u, 1.0)
         rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
         e = {"dram_bytes_per_launch": (rd or 0) + (wr or 0), "dram_read": rd, "dram_write": wr,
              "gpu_time_us": val("gpu__time_duration.sum"), "issue_slot_util": (val("smsp__issue_active.avg.pct_of_peak_sustained_active") or 0) / 100.0,
