@@ -591,7 +591,8 @@ def main_gpu(args):
             from phi_b200 import multi
             t1 = time.time()
             merged = multi.merge_results(parts, expand=False) if world > 1 else full
-            extras["merge_ms"] = (time.time() - t1) * 1e3
+            extras["merge_ms"] = getattr(multi.merge_results, "last_call_ms", 0.0) if world > 1 else 0.0   # phi_index_result_merge alone
+            extras["merge_with_numpy_conversions_ms"] = (time.time() - t1) * 1e3
             extras["result_digest"] = result_digest(merged)
             extras["result"] = {"spectrum": merged.count_sp_r, "groups": merged.n_groups, "anchors": int(len(merged.member_walk)),
                                 "group_vertices": int(len(merged.group_vtx)), "filtered_ranks": merged.n_filtered}

@@ -78,7 +78,10 @@ def merge_results(parts, expand=True):
     cs = [_abi.py_to_c_result(p) for p in parts]
     arr = (C.POINTER(_abi.IndexResult) * len(parts))(*[C.pointer(c[0]) for c in cs])
     out = C.POINTER(_abi.IndexResult)()
+    import time
+    t0 = time.perf_counter()
     rc = lib.phi_index_result_merge(arr, len(parts), C.byref(out))
+    merge_results.last_call_ms = (time.perf_counter() - t0) * 1e3       # the library call alone (the numpy conversions around it are test / bench plumbing)
     assert rc == 0, rc
     res = _abi.result_to_py(out.contents, expand)
     lib.phi_gpu_index_result_free(out)
