@@ -405,6 +405,10 @@ class Dist:
     def __init__(self, rank, world, local):
         self.rank, self.world = rank, world
         if world > 1:
+            # (the library sets these before it creates its communicator; here torch's process group initialises NCCL first and NCCL
+            # reads its environment once per process)
+            os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "8")
+            os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
             import torch
             import torch.distributed as dist
             torch.cuda.set_device(local)

@@ -598,6 +598,10 @@ extern "C" int phi_gpu_index_comm_init(phi_gpu_index_ctx *ctx, int rank, int wor
     NcclApi *nc = nccl_api(err);
     if (!nc) return ctx->fail(PHI_ERR_COMM, err);
     CU(cudaSetDevice(ctx->device));
+    // the exchanges are point-to-point (grouped send / recv by owner): give NCCL more than its default couple of channels per peer,
+    // unless the caller has set the knobs (tens of MB per peer move at a fraction of NVLink speed otherwise)
+    setenv("NCCL_MIN_P2P_NCHANNELS", "8", 0);
+    setenv("NCCL_MAX_P2P_NCHANNELS", "32", 0);
     ncclUniqueId u; memcpy(u.internal, id, PHI_COMM_ID_BYTES);
     ncclComm_t comm;
     NC(nc->CommInitRank(&comm, world, u, rank));
@@ -685,7 +689,11 @@ static int exchange_spectrum(phi_gpu_index_ctx *ctx, uint64_t n_local, uint64_t 
     }
     // from here on a failure of this rank alone would leave the peers inside a collective: the communicator is aborted then
     struct AbortGuard { phi_gpu_index_ctx *c; bool armed; ~AbortGuard() { if (armed) comm_release(c, true); } } guard = {ctx, true};
-    CU(ctx->xk_a.reserve((rtot + 1) * 8)); CU(ctx->xk_b.reserve((rtot + 2) * 8));
+    // xk_b will hold this owner's slice and is read up to the LARGEST owner's slice size by the all-gather below: no owner can
+    // end up with more distinct keys than it was sent, so the largest receive count of any owner bounds them all
+    uint64_t rtot_max = 0;
+    for (int o = 0; o < W; ++o) { uint64_t t = 0; for (int p = 0; p < W; ++p) t += all[(size_t)p * (W + 2) + o + 1] - all[(size_t)p * (W + 2) + o]; rtot_max = std::max(rtot_max, t); }
+    CU(ctx->xk_a.reserve((rtot + 1) * 8)); CU(ctx->xk_b.reserve((rtot_max + 2) * 8));
     for (uint64_t cap_mul = 2;; cap_mul <<= 1) {
         NC(nc->GroupStart());
         for (int p = 0; p < W; ++p) {
@@ -730,17 +738,19 @@ static int exchange_spectrum(phi_gpu_index_ctx *ctx, uint64_t n_local, uint64_t 
     for (int o = 0; o < W; ++o) ctx->own_off[o + 1] = ctx->own_off[o] + all[(size_t)o * 3];
     n_spec = ctx->own_off[W];
     CU(ctx->spec_a.reserve((n_spec + 1) * 8));
-    // every owner's sorted slice to everybody: concatenation of range slices is the sorted spectrum
-    const uint64_t mine_n = ctx->own_off[me + 1] - ctx->own_off[me];
-    NC(nc->GroupStart());
-    for (int p = 0; p < W; ++p) {
-        if (p == me) continue;
-        if (mine_n) NC(nc->Send(ctx->xk_b.p, mine_n, ncclUint64, p, comm, ctx->st));
-        const uint64_t cnt = ctx->own_off[p + 1] - ctx->own_off[p];
-        if (cnt) NC(nc->Recv(ctx->spec_a.as<uint64_t>() + ctx->own_off[p], cnt, ncclUint64, p, comm, ctx->st));
+    // every owner's sorted slice to everybody: concatenation of range slices is the sorted spectrum.  ONE all-gather of slices padded
+    // to the largest one (Murmur hashes are uniform: the owners' slices differ by a fraction of a per cent) — a collective NCCL runs
+    // at full NVLink / NVSwitch bandwidth, unlike W - 1 point-to-point pairs — then the slices are moved next to each other.
+    uint64_t maxn = 0;
+    for (int o = 0; o < W; ++o) maxn = std::max(maxn, ctx->own_off[o + 1] - ctx->own_off[o]);
+    if (maxn) {
+        CU(ctx->xk_a.reserve((size_t)W * maxn * 8 + 8));                  // (the keys received above are not needed any more)
+        NC(nc->AllGather(ctx->xk_b.p, ctx->xk_a.p, maxn, ncclUint64, comm, ctx->st));
+        for (int o = 0; o < W; ++o) {
+            const uint64_t cnt = ctx->own_off[o + 1] - ctx->own_off[o];
+            if (cnt) CU(cudaMemcpyAsync(ctx->spec_a.as<uint64_t>() + ctx->own_off[o], ctx->xk_a.as<uint64_t>() + (size_t)o * maxn, cnt * 8, cudaMemcpyDeviceToDevice, ctx->st));
+        }
     }
-    NC(nc->GroupEnd());
-    if (mine_n) CU(cudaMemcpyAsync(ctx->spec_a.as<uint64_t>() + ctx->own_off[me], ctx->xk_b.p, mine_n * 8, cudaMemcpyDeviceToDevice, ctx->st));
     guard.armed = false;
     return PHI_OK;
 }
