@@ -229,14 +229,21 @@ int phi_gpu_hash128_to_64(phi_gpu_index_ctx *ctx, const uint8_t *keys, uint64_t 
  * id comes from phi_gpu_index_comm_unique_id() on rank 0 and is distributed by
  * the caller (torch.distributed store, MPI, a file ...).  After comm_init,
  * phi_gpu_index_run / _run_resident treat `reads` and the walks of `graph` as
- * THIS RANK'S SHARD (segments and top_order_map replicated), exchange read
- * minimizer hashes by hash range (all-to-all), all-gather the spectrum, route
- * one (rank, count, vertex list) summary per local group to the owner of the
- * rank (which applies the threshold; the drop flags are shared), and return on
- * every rank the surviving groups of ITS walks for all ranks (spectrum: rank 0
- * only, NULL elsewhere - it is the same everywhere; n_filtered: the
- * dropped ranks this rank owns; sum over the ranks).  phi_shard_* below describe
- * the partition.  walk ids in the result are global: walk_id_base + local index.
+ * THIS RANK'S SHARD (segments and top_order_map replicated): whole walks
+ * (walk_id_base = id of the first one) or, with phi_gpu_index_set_walk_region,
+ * all walks cut to this rank's region of the graph (walk_id_base 0).  The ranks
+ * exchange read minimizer hashes by hash range (all-to-all), all-gather the
+ * owners' sorted slices, route one (rank, count, vertex list) summary per local
+ * group to the owner of the rank (which applies the threshold; the drop flags
+ * are all-reduced), and every rank returns the surviving groups of ITS walks /
+ * region for all ranks (spectrum: rank 0 only, NULL elsewhere - it is the same
+ * everywhere; n_filtered: the dropped ranks this rank owns; sum over the ranks);
+ * phi_index_result_merge makes one result of the parts.  params.debug and every
+ * k <= 255 work as on one GPU.  A stage that fails on one rank is reported to
+ * all ranks through the next exchange (PHI_ERR_COMM on the others); a failure in
+ * the middle of an exchange aborts the communicator (comm_init again to go on).
+ * phi_gpu_index_destroy and a repeated comm_init release the communicator.
+ * walk ids in the result are global: walk_id_base + local index.
  */
 #define PHI_COMM_ID_BYTES 128
 int phi_gpu_index_comm_unique_id(uint8_t id[PHI_COMM_ID_BYTES]);

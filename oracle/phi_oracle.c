@@ -86,9 +86,10 @@ static void reverse_strand(const uint8_t *s, int k, uint8_t *out)
 /*
  * The minimizer scan shared by index_kmers (ILP_index.cpp:383-442) and
  * compute_hashes (:455-490).  `seq` is already upper-cased, length n.
- * Calls emit(ctx, hash, best_start_idx) for every emitted minimizer in order.
+ * Calls emit(ctx, hash, best_start_idx, i) for every emitted minimizer in order; i is the start of the LAST k-mer of the
+ * window that emitted it (the loop variable of :388 at :413).
  */
-typedef void (*emit_fn)(void *ctx, uint64_t hash, int64_t pos);
+typedef void (*emit_fn)(void *ctx, uint64_t hash, int64_t pos, int64_t win_end);
 
 static void minimizer_scan(const uint8_t *seq, int64_t n, int k, int w, emit_fn emit, void *ctx)
 {
@@ -113,7 +114,7 @@ static void minimizer_scan(const uint8_t *seq, int64_t n, int k, int w, emit_fn 
         if (size > 0 && dq_pos[head] <= i - w) { head = (head + 1) % cap; --size; }  /* :405-407 */
         if (i >= w - 1) {                                       /* :410 */
             uint64_t h = phi_oracle_hash128_to_64(dq_str + (size_t)head * k, k);      /* :412 */
-            if (h != prev_hash) { prev_hash = h; emit(ctx, h, dq_pos[head]); }        /* :413-414 */
+            if (h != prev_hash) { prev_hash = h; emit(ctx, h, dq_pos[head], i); }     /* :413-414 */
         }
     }
     free(dq_str); free(dq_pos); free(rev);
@@ -139,7 +140,7 @@ static int cmp_u64(const void *a, const void *b)
 }
 
 /* ------------------------------------------------------------------- reads */
-static void emit_hash_only(void *ctx, uint64_t h, int64_t pos) { (void)pos; push_u64((vec_u64 *)ctx, h); }
+static void emit_hash_only(void *ctx, uint64_t h, int64_t pos, int64_t win_end) { (void)pos; (void)win_end; push_u64((vec_u64 *)ctx, h); }
 
 /* compute_hashes, ILP_index.cpp:447-493 */
 int64_t phi_oracle_read_hashes(const uint8_t *read, uint64_t len, int32_t k, int32_t w, uint64_t **out)
@@ -161,15 +162,17 @@ typedef struct {
     vec_u64 hash;      /* per minimizer */
     vec_u64 voff;      /* per minimizer + 1 */
     vec_i32 vtx;
+    vec_i32 own;       /* per minimizer: the vertex under the start of the last k-mer of the window that emitted it */
     const int32_t *idx_vtx_map;
     const int32_t *top_order_map;
     int k;
 } walk_sketch;
 
 /* anchor construction, ILP_index.cpp:416-439 */
-static void emit_walk_min(void *ctx, uint64_t h, int64_t pos)
+static void emit_walk_min(void *ctx, uint64_t h, int64_t pos, int64_t win_end)
 {
     walk_sketch *ws = (walk_sketch *)ctx;
+    push_i32(&ws->own, ws->idx_vtx_map[win_end]);
     int32_t uniq[256]; int nu = 0;
     for (int j = 0; j < ws->k; ++j) {                            /* :424-430 distinct, first-seen order */
         int32_t v = ws->idx_vtx_map[pos + j];
@@ -242,6 +245,12 @@ static void to_compact(phi_oracle_result *r, int32_t *arank, uint64_t *aoff, int
 int phi_oracle_sketch_walks(const phi_graph_view *g, const phi_index_params *prm, int n_threads,
                             phi_oracle_result **out, uint64_t **hashes_out)
 {
+    return phi_oracle_sketch_walks_owner(g, prm, n_threads, out, hashes_out, NULL);
+}
+
+int phi_oracle_sketch_walks_owner(const phi_graph_view *g, const phi_index_params *prm, int n_threads,
+                                  phi_oracle_result **out, uint64_t **hashes_out, int32_t **owner_vtx_out)
+{
     if (!g || !out || !hashes_out || !check_params(prm)) return PHI_ERR_ARG;
     uint32_t H = g->n_walks;
     walk_sketch *ws = (walk_sketch *)calloc(H ? H : 1, sizeof(walk_sketch));
@@ -255,6 +264,7 @@ int phi_oracle_sketch_walks(const phi_graph_view *g, const phi_index_params *prm
     uint64_t na = 0, nv = 0;
     for (uint32_t h = 0; h < H; ++h) { na += ws[h].hash.n; nv += ws[h].vtx.n; }
     uint64_t *hashes = (uint64_t *)malloc((na ? na : 1) * 8);
+    int32_t *owner = owner_vtx_out ? (int32_t *)malloc((na ? na : 1) * 4) : NULL;
     int32_t *arank = (int32_t *)calloc(na ? na : 1, 4), *awalk = (int32_t *)malloc((na ? na : 1) * 4);
     uint64_t *aoff = (uint64_t *)malloc((na + 1) * 8);
     int32_t *avtx = (int32_t *)malloc((nv ? nv : 1) * 4);
@@ -264,6 +274,7 @@ int phi_oracle_sketch_walks(const phi_graph_view *g, const phi_index_params *prm
     for (uint32_t h = 0; h < H; ++h) {
         for (size_t i = 0; i < ws[h].hash.n; ++i) {
             hashes[a] = ws[h].hash.a[i]; awalk[a] = (int32_t)h;
+            if (owner) owner[a] = ws[h].own.a[i];
             for (uint64_t q = ws[h].voff.a[i]; q < ws[h].voff.a[i + 1]; ++q) avtx[vo++] = ws[h].vtx.a[q];
             aoff[++a] = vo;
         }
@@ -271,9 +282,10 @@ int phi_oracle_sketch_walks(const phi_graph_view *g, const phi_index_params *prm
         uint64_t len = 0;
         for (uint64_t s = g->walk_off[h]; s < g->walk_off[h + 1]; ++s) len += g->seg_off[g->walk_vtx[s] + 1] - g->seg_off[g->walk_vtx[s]];
         r->path_kmer_positions += kmer_positions(len, prm->k, prm->w);
-        free(ws[h].hash.a); free(ws[h].voff.a); free(ws[h].vtx.a);
+        free(ws[h].hash.a); free(ws[h].voff.a); free(ws[h].vtx.a); free(ws[h].own.a);
     }
     free(ws);
+    if (owner_vtx_out) *owner_vtx_out = owner;
     r->n_walks = H; r->n_anchors = na; r->n_anchor_vtx = nv;
     r->anchor_walk = awalk; r->anchor_vtx = avtx;
     to_compact(r, arank, aoff, 0);

@@ -55,6 +55,11 @@ int phi_oracle_index_run(const phi_graph_view *graph, const phi_reads_view *read
 int phi_oracle_sketch_walks(const phi_graph_view *graph, const phi_index_params *params, int n_threads,
                             phi_oracle_result **out, uint64_t **hashes_out);
 
+/* The same, plus for every emitted minimizer the vertex under the start of the LAST k-mer of the window that emitted it (the
+ * loop variable i of ILP_index.cpp:388 at :413): what the multi-GPU region partition decides ownership by.  Free with phi_oracle_free. */
+int phi_oracle_sketch_walks_owner(const phi_graph_view *graph, const phi_index_params *params, int n_threads,
+                                  phi_oracle_result **out, uint64_t **hashes_out, int32_t **owner_vtx_out);
+
 /* compute_hashes for one read (ILP_index.cpp:447-493): sorted distinct hashes; returns count, fills *out (malloc). */
 int64_t phi_oracle_read_hashes(const uint8_t *read, uint64_t len, int32_t k, int32_t w, uint64_t **out);
 

@@ -2,10 +2,11 @@
 
 gpu : every rank drives one B200 through the C ABI (NCCL exchange inside the library), rank 0 merges and checks
       against the oracle on the unsharded input.
-cpu : gloo, no GPU — the same partition functions (phi_shard_*) and merge code, with the per-rank compute done by the
-      oracle and the exchanges done with torch.distributed object collectives: a check of the sharded ALGORITHM
-      (hash-range ownership, rank offsets, group summaries to the owner, owner-side threshold, shared drop flags,
-      local ordering, merge), not of the kernels.
+cpu : gloo, no GPU — the same partition functions (phi_shard_*: whole walks, or every walk cut to a region of the graph) and
+      the library's merge (phi_index_result_merge), with the per-rank compute done by the oracle and the exchanges done with
+      torch.distributed object collectives: a check of the sharded ALGORITHM (hash-range ownership, rank offsets, which rank
+      owns which window of a sliced walk, group summaries to the owner, owner-side threshold, shared drop flags, local
+      ordering, merge), not of the kernels.
 """
 import os
 import sys
@@ -90,11 +91,11 @@ def py_filter(hits, n_walks_global, T):
     return out, filtered
 
 
-def main_cpu(name):
+def main_cpu(name, mode="walk"):
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo")
     g, rd, k, w, T = load(name)
-    gs, rs, base, _ = multi.shard_inputs(g, rd, rank, world, k, w, "walk")
+    gs, rs, base, region = multi.shard_inputs(g, rd, rank, world, k, w, mode)
     empty = _abi.Graph(g.seg_off, g.seg_bases, np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint32), g.top_order_map)
     local = phi_io.oracle_index(empty, rs, k, w, T).spectrum            # this rank's distinct read-minimizer hashes
     owner = np.array([multi.owner_of_hash(h, world) for h in local], dtype=np.int64)
@@ -108,10 +109,24 @@ def main_cpu(name):
     spectrum = np.concatenate(slices)                                   # concatenation of range slices is globally sorted
     own_off = np.concatenate([[0], np.cumsum([len(s) for s in slices])])
     assert np.all(spectrum[1:] > spectrum[:-1])
-    sk, hashes = phi_io.oracle_sketch_walks(gs, k, w)
+    if region is None:
+        sk, hashes = phi_io.oracle_sketch_walks(gs, k, w)
+        mpw_local = sk.minimizers_per_walk
+    else:
+        # region partition: this rank holds every walk cut to its region plus context; of what the slices emit it owns the minimizers
+        # whose emitting window ends (last k-mer starts) on a vertex inside the region — exactly what the library's chunks own
+        sk, hashes, owner = phi_io.oracle_sketch_walks_owner(gs, k, w)
+        seg_len = np.diff(g.seg_off.astype(np.int64))
+        order = np.argsort(g.top_order_map, kind="stable")
+        coord = np.zeros(g.n_vtx, dtype=np.float64)
+        coord[order] = np.concatenate([[0], np.cumsum(seg_len[order])])[:-1]
+        own = (coord[owner] >= float(region[0])) & (coord[owner] < float(region[1]))
+        mpw_local = np.bincount(sk.anchor_walk[own], minlength=gs.n_walks).astype(np.uint64)
     idx = np.searchsorted(spectrum, hashes)
     idx[idx == len(spectrum)] = 0
     hit = spectrum[idx] == hashes if len(spectrum) else np.zeros(len(hashes), dtype=bool)
+    if region is not None:
+        hit &= own
     off = sk.anchor_off.astype(np.int64)
     hits = [(int(idx[a]), int(sk.anchor_walk[a]) + base, int(a), sk.anchor_vtx[off[a]:off[a + 1]].tolist()) for a in np.nonzero(hit)[0]]
     # group summaries (rank, vertex-list key) -> count travel to the owner of the rank; the owner adds them up and decides
@@ -135,7 +150,7 @@ def main_cpu(name):
     kept, none_dropped = py_filter([h for h in hits if h[0] not in dropped], 1 << 30, 1.0)   # local order of the local walks' anchors
     assert none_dropped == 0
     mpw = np.zeros(g.n_walks, dtype=np.uint64)
-    mpw[base:base + gs.n_walks] = sk.minimizers_per_walk
+    mpw[base:base + gs.n_walks] = mpw_local
     apw = np.bincount([h[1] for h in kept], minlength=g.n_walks).astype(np.uint64)
     voff = np.concatenate([[0], np.cumsum([len(h[3]) for h in kept])]).astype(np.uint64)
     part = _abi.IndexResultPy(
@@ -156,7 +171,7 @@ def main_cpu(name):
         for f in ("spectrum", "anchor_rank", "anchor_walk", "anchor_off", "anchor_vtx", "minimizers_per_walk", "anchors_per_walk"):
             assert np.array_equal(getattr(got, f), getattr(want, f)), f
         assert got.n_filtered == want.n_filtered and got.count_sp_r == want.count_sp_r
-        print(f"MULTI_OK cpu world={world} case={name} spectrum={got.count_sp_r} anchors={got.n_anchors}")
+        print(f"MULTI_OK cpu world={world} case={name} mode={mode} spectrum={got.count_sp_r} anchors={got.n_anchors}")
     dist.barrier()
 
 
@@ -164,4 +179,4 @@ if __name__ == "__main__":
     if sys.argv[1] == "gpu":
         main_gpu(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "region")
     else:
-        main_cpu(sys.argv[2])
+        main_cpu(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "walk")

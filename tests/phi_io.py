@@ -153,6 +153,9 @@ def oracle_lib():
         lib.phi_oracle_sketch_walks.restype = C.c_int
         lib.phi_oracle_sketch_walks.argtypes = [C.POINTER(_abi.GraphView), C.POINTER(_abi.IndexParams), C.c_int,
                                                 C.POINTER(C.POINTER(OracleResult)), C.POINTER(_abi.u64p)]
+        lib.phi_oracle_sketch_walks_owner.restype = C.c_int
+        lib.phi_oracle_sketch_walks_owner.argtypes = [C.POINTER(_abi.GraphView), C.POINTER(_abi.IndexParams), C.c_int,
+                                                      C.POINTER(C.POINTER(OracleResult)), C.POINTER(_abi.u64p), C.POINTER(_abi.i32p)]
         lib.phi_oracle_read_hashes.restype = C.c_int64
         lib.phi_oracle_read_hashes.argtypes = [C.c_char_p, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(_abi.u64p)]
         lib.phi_oracle_result_free.argtypes = [C.POINTER(OracleResult)]
@@ -190,6 +193,24 @@ def oracle_sketch_walks(graph, k=31, w=25, threads=0):
     lib.phi_oracle_result_free(out)
     lib.phi_oracle_free(hp)
     return res, hashes
+
+
+def oracle_sketch_walks_owner(graph, k=31, w=25, threads=0):
+    """oracle_sketch_walks + for every emitted minimizer the vertex under the start of the last k-mer of the window that emitted it."""
+    lib = oracle_lib()
+    gv = graph.view()
+    prm = _abi.IndexParams(k, w, 1.0, 0)
+    out = C.POINTER(OracleResult)()
+    hp, op = _abi.u64p(), _abi.i32p()
+    rc = lib.phi_oracle_sketch_walks_owner(C.byref(gv), C.byref(prm), threads, C.byref(out), C.byref(hp), C.byref(op))
+    assert rc == 0, rc
+    res = oracle_result_to_py(out.contents)
+    hashes = _abi._np_from(hp, res.n_anchors, np.uint64)
+    owner = _abi._np_from(op, res.n_anchors, np.int32)
+    lib.phi_oracle_result_free(out)
+    lib.phi_oracle_free(hp)
+    lib.phi_oracle_free(op)
+    return res, hashes, owner
 
 
 def oracle_read_hashes(seq: bytes, k=31, w=25):

@@ -27,9 +27,10 @@ def launch(mode, case, world, partition="region"):
     return p.stdout
 
 
-@pytest.mark.parametrize("case,world", [("synth_small", 2), ("synth_repeats", 2), ("synth_dirty", 3)])
-def test_sharded_algorithm_cpu_gloo(case, world):
-    launch("cpu", case, world)
+@pytest.mark.parametrize("case,world,partition", [("synth_small", 2, "walk"), ("synth_repeats", 2, "walk"), ("synth_dirty", 3, "walk"),
+                                                  ("synth_small", 2, "region"), ("synth_repeats", 3, "region"), ("synth_dirty", 2, "region")])
+def test_sharded_algorithm_cpu_gloo(case, world, partition):
+    launch("cpu", case, world, partition)
 
 
 @pytest.mark.gpu
