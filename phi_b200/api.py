@@ -143,7 +143,7 @@ def load_reads(path):
 
 
 class PhiGpuIndex:
-    """One ctx == one GPU == one CUDA stream.  Mirrors the C ABI one to one."""
+    """One ctx == one GPU.  Mirrors the C ABI one to one."""
 
     def __init__(self, device=-1):
         self.lib = load_library()

@@ -1,7 +1,9 @@
 // Host side of libphi_gpu_index.so: the C ABI declared in include/phi_gpu_index.h and the stage
 // pipeline that replaces /root/reference/src/ILP_index.cpp:543-743.  C++ only (no PyTorch); one ctx
-// drives one GPU through one CUDA stream.  There is no CPU fallback: without a usable device
-// phi_gpu_index_create() fails and nothing else can be called.
+// drives one GPU: the calling thread owns the main stream (reads, spectrum, walk sketch, filter, result), a second
+// thread it starts per run owns the second stream (graph preparation), a copy stream carries the uploads and the early
+// part of the download.  There is no CPU fallback: without a usable device phi_gpu_index_create() fails and nothing
+// else can be called.
 #include "../../include/phi_gpu_index.h"
 #include "kernels.h"
 #include "result_box.h"
@@ -87,7 +89,7 @@ struct phi_gpu_index_ctx {
     DevBuf fs_state;                       // ticket + one look-back word per tile of the fused step kernel
     DevBuf cm_off, cm_cursor, cm_tmp, cm_walk, hit_slot, hit_sub, hit_slot2, g_slot2, probe2, grp_cnt, grp_moff, grp_voff, members_tmp;
     unsigned long long *h_ctr = nullptr;   // pinned mirror of the counter block
-    // what the second stream uses instead of ctr / h_ctr / scan_scr / flags / flags64 / nv_out (swapped in by PrepScope)
+    // what the graph-preparation thread (second stream) uses instead of ctr / h_ctr / scan_scr / flags / flags64
     DevBuf ctr2, scan_scr2, flags2, flags64_2, nv_out2; unsigned long long *h_ctr2 = nullptr;
     std::vector<PinnedBuf> pinned_pool;    // free pinned buffers (returned by phi_gpu_index_result_free)
 

@@ -106,3 +106,33 @@ def test_region_cut_refuses_walks_against_the_order(case):
     assert multi.region_bounds(_abi.Graph(g.seg_off, g.seg_bases, g.walk_off, g.walk_vtx, np.zeros(g.n_vtx, dtype=np.int32)), 2) is None
     gs, rs, base, region = multi.shard_inputs(bad, case[1], 1, 2, 31, 25, "region")    # falls back to whole walks
     assert region is None and base > 0
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_bench_generates_the_same_shards_it_would_cut_from_the_whole_input(monkeypatch, world):
+    """bench.py never spells the whole walk set of the chromosome-scale configs: a rank generates only the part of every walk that
+    runs through its region, and only its batch range of the reads.  On a small instance of the same generator that must be exactly
+    what phi_shard_walk_regions / phi_shard_slice_walks cut from the whole graph, and the read shards must tile the global read set."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--config", "c4", "--haps", "11", "--backbone", "300000", "--coverage", "2"])
+    a = bench.parse_args()
+    whole_g, whole_rd, _, _, _, units = bench.Workload(a).shard(0, 1)
+    assert units[0] == bench.positions(whole_g.walk_lengths(), a.k, a.w)
+    # the region bounds bench derives from 4 sample walks
+    sample = [h for h in range(0, a.haps, max(1, a.haps // 4))][:4]
+    wo = whole_g.walk_off.astype(np.int64)
+    gsample = _abi.Graph(whole_g.seg_off, whole_g.seg_bases, np.concatenate([[0], np.cumsum([wo[h + 1] - wo[h] for h in sample])]),
+                         np.concatenate([whole_g.walk_vtx[wo[h]:wo[h + 1]] for h in sample]), whole_g.top_order_map)
+    bounds = multi.region_bounds(gsample, world)
+    reads = []
+    for r in range(world):
+        g, rd, base, n_walks, region, units_r = bench.Workload(a).shard(r, world)
+        assert (base, n_walks, units_r) == (0, a.haps, units) and region == (int(bounds[r]), int(bounds[r + 1]))
+        want = multi.slice_walks(whole_g, a.k, a.w, bounds[r], bounds[r + 1])
+        assert np.array_equal(g.walk_off, want.walk_off) and np.array_equal(g.walk_vtx, want.walk_vtx)
+        reads.append(rd)
+    assert sum(r.n_reads for r in reads) == whole_rd.n_reads
+    assert np.array_equal(np.concatenate([r.read_bases for r in reads]), whole_rd.read_bases)
