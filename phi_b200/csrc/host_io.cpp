@@ -28,11 +28,16 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <queue>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -81,6 +86,106 @@ bool slurp(const char *path, std::string &out, std::string &err)
     return true;
 }
 
+// Inflated text that becomes available while it is being parsed: a reader thread inflates (zlib is the slowest stage of the read
+// ingest and cannot be split for a plain gzip stream) into a buffer of fixed capacity — the size the gzip trailer promises —
+// and the parser, written against `more()` / `line_end()` instead of a fixed end pointer, follows right behind it.  If the trailer
+// lied (multi-member or > 4 GB streams) the buffer overflows, `overflow` is set and the caller falls back to slurp().
+struct TextStream {
+    std::vector<char> buf;
+    std::atomic<size_t> avail{0};
+    std::atomic<bool> done{false};
+    bool failed = false, overflow = false;
+    std::mutex mu; std::condition_variable cv;
+    std::thread th;
+
+    explicit TextStream(std::string &&whole) : buf(whole.begin(), whole.end()) { avail = buf.size(); done = true; }   // complete text: nothing to wait for
+    TextStream(const char *path, size_t capacity) : buf(capacity)
+    {
+        th = std::thread([this, path]() {
+            gzFile fp = gzopen(path, "rb");
+            if (!fp) { failed = true; finish(); return; }
+            gzbuffer(fp, 1 << 20);
+            size_t have = 0;
+            for (;;) {
+                if (have == buf.size()) {                               // more text than promised?
+                    char probe;
+                    if (gzread(fp, &probe, 1) > 0) overflow = true;
+                    break;
+                }
+                const int n = gzread(fp, buf.data() + have, (unsigned)std::min<size_t>(buf.size() - have, (size_t)4 << 20));
+                if (n < 0) { failed = true; break; }
+                if (n == 0) break;
+                have += (size_t)n;
+                { std::lock_guard<std::mutex> lk(mu); avail = have; }
+                cv.notify_one();
+            }
+            gzclose(fp);
+            finish();
+        });
+    }
+    ~TextStream() { if (th.joinable()) th.join(); }
+    void finish() { { std::lock_guard<std::mutex> lk(mu); done = true; } cv.notify_one(); }
+    const char *begin() const { return buf.data(); }
+    // is there a byte at p?  (waits for the reader when p is at the current end)
+    bool more(const char *p)
+    {
+        const size_t off = (size_t)(p - buf.data());
+        if (off < avail.load(std::memory_order_acquire)) return true;
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return off < avail.load() || done.load(); });
+        return off < avail.load();
+    }
+    // the '\n' that ends the line s lies in, or the end of the text
+    const char *line_end(const char *s)
+    {
+        size_t searched = (size_t)(s - buf.data());                      // no '\n' in [s, searched)
+        for (;;) {
+            const bool fin = done.load(std::memory_order_acquire);       // (read before avail: once done is seen, avail is final)
+            const size_t a = avail.load(std::memory_order_acquire);
+            if (searched < a) {
+                const char *nl = (const char *)memchr(buf.data() + searched, '\n', a - searched);
+                if (nl) return nl;
+                searched = a;
+            }
+            if (fin) return buf.data() + a;
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&]() { return avail.load() > a || done.load(); });
+        }
+    }
+    const char *end_now() { return buf.data() + avail.load(std::memory_order_acquire); }
+};
+
+// capacity for a TextStream: what slurp() uses as its size hint, exact for single-member gzip files below 4 GB and for plain files
+size_t text_size_hint(const char *path)
+{
+    size_t hint = 0;
+    if (FILE *raw = fopen(path, "rb")) {
+        unsigned char magic[2] = {0, 0}, tail[4];
+        if (fread(magic, 1, 2, raw) == 2 && fseek(raw, 0, SEEK_END) == 0) {
+            const long fsz = ftell(raw);
+            if (magic[0] == 0x1f && magic[1] == 0x8b) {
+                if (fsz >= 18 && fseek(raw, -4, SEEK_END) == 0 && fread(tail, 1, 4, raw) == 4)
+                    hint = (size_t)tail[0] | (size_t)tail[1] << 8 | (size_t)tail[2] << 16 | (size_t)tail[3] << 24;
+                if (hint < (size_t)fsz) hint = 0;                        // wrapped or multi-member: no usable promise
+            } else if (fsz > 0) hint = (size_t)fsz;
+        }
+        fclose(raw);
+    }
+    return hint;
+}
+
+// f(i) for i in [0, n) on up to 16 host threads (items are handed out one by one: walks differ in length)
+template <class F>
+void parallel_for(size_t n, F f)
+{
+    const unsigned T = (unsigned)std::min<size_t>(std::min<size_t>(n, 16), std::max(1u, std::thread::hardware_concurrency()));
+    if (T <= 1) { for (size_t i = 0; i < n; ++i) f(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t) th.emplace_back([&]() { for (;;) { const size_t i = next.fetch_add(1); if (i >= n) break; f(i); } });
+    for (auto &x : th) x.join();
+}
+
 }  // namespace
 
 struct phi_host_graph {
@@ -98,7 +203,8 @@ struct phi_host_reads {
     phi_reads_view view;
     std::vector<uint64_t> read_off;
     std::string read_bases;
-    std::vector<std::string> names;
+    std::string name_arena;              // the names back to back, each followed by a NUL
+    std::vector<uint64_t> name_off;
 };
 
 static void set_err(char *err, size_t errlen, const std::string &m)
@@ -110,10 +216,7 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
 {
     if (!gfa_path || !out) return PHI_ERR_ARG;
     *out = nullptr;
-    std::string text, e;
     PhaseTimer pt;
-    if (!slurp(gfa_path, text, e)) { set_err(err, errlen, e); return PHI_ERR_ARG; }
-    pt.lap("inflate");
     phi_host_graph *G = new phi_host_graph();
     // Names and sequences are views into `text` while parsing: no per-field std::string, one open-addressing table keyed by the
     // bytes of the name (the reference goes through a khash of strdup'ed names, gfa-base.cpp:75-96).
@@ -143,7 +246,7 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
         // table: the number indexes `direct`.  The prefix is the one of the first such name; a number with a leading zero, more
         // than 8 digits or another prefix is an ordinary name (hash table), so equal strings always take the same route.
         std::vector<uint32_t> direct; const char *prefix = nullptr; uint32_t prefix_len = 0; bool have_prefix = false; size_t hashed = 0;
-        bool numeric(const char *p, uint32_t n, uint32_t &num)
+        bool numeric(const char *p, uint32_t n, uint32_t &num, bool establish = true)
         {
             uint32_t i = 0;
             while (i < n && (p[i] < '0' || p[i] > '9')) ++i;
@@ -152,12 +255,24 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
             uint32_t v = 0;
             for (uint32_t q = i; q < n; ++q) { if (p[q] < '0' || p[q] > '9') return false; v = v * 10 + (uint32_t)(p[q] - '0'); }
             if (v >= (1u << 24)) return false;
-            if (!have_prefix) { have_prefix = true; prefix = p; prefix_len = i; }
+            if (!have_prefix) { if (!establish) return false; have_prefix = true; prefix = p; prefix_len = i; }   // (a lookup never fixes the prefix: no name is in `direct` yet)
             else if (i != prefix_len || memcmp(p, prefix, i) != 0) return false;
             num = v;
             return true;
         }
         // id of the name, or 0xFFFFFFFF; with add: the name gets the next id
+        // read-only (safe from several threads): id of the name if it is known, else 0xFFFFFFFF
+        uint32_t lookup(const char *p, uint32_t n) const
+        {
+            uint32_t num;
+            if (const_cast<NameTable *>(this)->numeric(p, n, num, false)) return num < direct.size() ? direct[num] : 0xFFFFFFFFu;
+            if (slot.empty()) return 0xFFFFFFFFu;
+            for (size_t s = hash(p, n) & mask;; s = (s + 1) & mask) {
+                const uint32_t id = slot[s];
+                if (id == 0xFFFFFFFFu) return id;
+                if ((*names)[id].n == n && memcmp((*names)[id].p, p, n) == 0) return id;
+            }
+        }
         uint32_t find(const char *p, uint32_t n, bool add)
         {
             uint32_t num;
@@ -186,7 +301,10 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
     std::vector<View> seqs;                                          // per segment (n == 0: no sequence)
     NameTable name2id; name2id.names = &seg_name; name2id.mask = 0;
     std::vector<std::pair<uint32_t, uint32_t>> arcs;                // oriented vertices (seg << 1 | reverse)
-    struct Walk { std::string sample; int hap; std::vector<uint32_t> v; };
+    // a W-line is only cut into fields during the scan; its steps are looked up afterwards, all walks in parallel.  The reference drops
+    // steps that name a segment not defined SO FAR (gfa-io.cpp:399-405): ids are handed out in order of first appearance, so "known
+    // at that line" is "id < number of segments at that line".
+    struct Walk { std::string sample; int hap; std::vector<uint32_t> v; const char *c, *send; uint32_t known; };
     std::vector<Walk> walks;
     auto add_seg = [&](const char *b, const char *e) -> uint32_t {
         const uint32_t id = name2id.find(b, (uint32_t)(e - b), true);
@@ -194,11 +312,16 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
         return id;
     };
     std::vector<std::pair<const char *, const char *>> f;            // tab-separated fields of the current line
-    const char *p = text.data(), *tend = p + text.size();
-    while (p < tend) {
-        const char *nl = (const char *)memchr(p, '\n', (size_t)(tend - p));
-        const char *lend = nl ? nl : tend;
-        const char *next_line = nl ? nl + 1 : tend;
+    // The text arrives while it is scanned: a reader thread inflates into a buffer sized by the gzip trailer (TextStream); if that
+    // promise does not hold the scan is repeated over the text inflated the plain way.  Names and sequences stay views into the text.
+    std::unique_ptr<TextStream> text;
+    auto scan = [&](TextStream &T) {
+    seg_name.clear(); seqs.clear(); arcs.clear(); walks.clear(); G->n_links = 0;
+    name2id = NameTable(); name2id.names = &seg_name; name2id.mask = 0;
+    const char *p = T.begin();
+    while (T.more(p)) {
+        const char *lend = T.line_end(p);
+        const char *next_line = T.more(lend) ? lend + 1 : lend;
         if (lend - p > 1 && lend[-1] == '\r') --lend;                    // kstream strips one trailing CR
         if (lend - p >= 3 && p[1] == '\t' && (p[0] == 'S' || p[0] == 'L' || p[0] == 'W')) {
             f.clear();
@@ -225,24 +348,47 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
             } else if (p[0] == 'W' && f.size() >= 6) {                   // sample, haplotype, contig, start, end, walk
                 Walk wk;
                 wk.sample.assign(f[0].first, f[0].second); wk.hap = atoi(std::string(f[1].first, f[1].second).c_str());
-                const char *c = f[5].first, *send = f[5].second;
-                wk.v.reserve((size_t)(send - c) / 4);
-                // tokens as gfa_parse_W cuts them (gfa-io.cpp:395-408): a token runs from one '>' / '<' to the next, and the FIRST
-                // token starts at the first byte of the field whatever that byte is (it takes the orientation marker's place:
-                // the name is what follows it); names that are no segment are dropped
-                while (c < send) {
-                    const char *d = c + 1;
-                    while (d < send && *d != '>' && *d != '<') ++d;
-                    const uint32_t id = name2id.find(c + 1, (uint32_t)(d - c - 1), false);
-                    if (id != 0xFFFFFFFFu) wk.v.push_back(id << 1 | (*c == '<' ? 1u : 0u));
-                    c = d;
-                }
+                wk.c = f[5].first; wk.send = f[5].second; wk.known = (uint32_t)seg_name.size();
                 walks.push_back(std::move(wk));
             }
         }
         p = next_line;
     }
-    pt.lap("parse lines");
+    };
+    const size_t hint = text_size_hint(gfa_path);
+    bool scanned = false;
+    if (hint) {
+        text.reset(new TextStream(gfa_path, hint));
+        scan(*text);
+        if (text->th.joinable()) text->th.join();
+        if (text->failed && text->avail.load() == 0 && !text->overflow) { delete G; set_err(err, errlen, std::string("cannot open ") + gfa_path); return PHI_ERR_ARG; }
+        scanned = !text->failed && !text->overflow;
+        pt.lap(scanned ? "inflate || scan lines" : "streamed scan (discarded)");
+    }
+    if (!scanned) {
+        std::string whole, e;
+        if (!slurp(gfa_path, whole, e)) { delete G; set_err(err, errlen, e); return PHI_ERR_ARG; }
+        pt.lap("inflate");
+        text.reset(new TextStream(std::move(whole)));
+        scan(*text);
+        pt.lap("scan lines");
+    }
+    // tokens as gfa_parse_W cuts them (gfa-io.cpp:395-408): a token runs from one '>' / '<' to the next, and the FIRST token starts at
+    // the first byte of the field whatever that byte is (it takes the orientation marker's place: the name is what follows it);
+    // names that are no segment (yet, at that line) are dropped
+    parallel_for(walks.size(), [&](size_t h) {
+        Walk &wk = walks[h];
+        const char *c = wk.c, *send = wk.send;
+        wk.v.reserve((size_t)(send - c) / 4);
+        while (c < send) {
+            const char *d = c + 1;
+            while (d < send && *d != '>' && *d != '<') ++d;
+            const uint32_t id = name2id.lookup(c + 1, (uint32_t)(d - c - 1));
+            if (id < wk.known) wk.v.push_back(id << 1 | (*c == '<' ? 1u : 0u));
+            c = d;
+        }
+    });
+    pt.lap("walk steps (parallel)");
     G->seg_names.reserve(seg_name.size());
     for (const View &v : seg_name) G->seg_names.emplace_back(v.p, v.n);
     pt.lap("segment names");
@@ -267,17 +413,22 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
     for (uint32_t v = 0; v < V; ++v) if (seqs[v].n) memcpy(&G->seg_bases[G->seg_off[v]], seqs[v].p, seqs[v].n);
     G->walk_off.assign(1, 0);
     for (size_t h = 0; h < walks.size(); ++h) {
-        for (uint32_t v : walks[h].v) {
-            if (v & 1) {                                                       // ILP_index.cpp:104-107
-                set_err(err, errlen, "Error: Walk " + std::to_string(h) + " has reverse strand vertices " + std::to_string(v));
-                delete G;
-                return PHI_ERR_UNSUPPORTED;
-            }
-            G->walk_vtx.push_back(v >> 1);
-        }
-        G->walk_off.push_back(G->walk_vtx.size());
+        G->walk_off.push_back(G->walk_off.back() + walks[h].v.size());
         G->walk_names.push_back(walks[h].sample + "." + std::to_string(walks[h].hap));
     }
+    G->walk_vtx.resize(G->walk_off.back());
+    std::vector<int64_t> bad(walks.size(), -1);                                // first reverse-strand step of every walk
+    parallel_for(walks.size(), [&](size_t h) {
+        uint32_t *dst = G->walk_vtx.data() + G->walk_off[h];
+        const std::vector<uint32_t> &v = walks[h].v;
+        for (size_t j = 0; j < v.size(); ++j) { if ((v[j] & 1) && bad[h] < 0) bad[h] = (int64_t)v[j]; dst[j] = v[j] >> 1; }
+    });
+    for (size_t h = 0; h < walks.size(); ++h)
+        if (bad[h] >= 0) {                                                     // ILP_index.cpp:104-107
+            set_err(err, errlen, "Error: Walk " + std::to_string(h) + " has reverse strand vertices " + std::to_string(bad[h]));
+            delete G;
+            return PHI_ERR_UNSUPPORTED;
+        }
     pt.lap("walk flip + flat views");
     // ---- adjacency of the forward vertices after symmetrisation, Kahn order (ILP_index.cpp:77-154)
     {
@@ -327,60 +478,88 @@ extern "C" uint64_t phi_host_graph_n_links(const phi_host_graph *g) { return g ?
 extern "C" uint64_t phi_host_graph_unlinked_steps(const phi_host_graph *g) { return g ? g->n_unlinked_steps : 0; }
 extern "C" void phi_host_graph_free(phi_host_graph *g) { delete g; }
 
+// kseq_read over a TextStream (kseq.h:192-232): the parser never looks past what the reader thread has delivered
+static void parse_reads(TextStream &T, phi_host_reads *R)
+{
+    R->read_off.assign(1, 0);
+    const char *p = T.begin();
+    int last_char = 0;
+    for (;;) {
+        if (!last_char) { while (T.more(p) && *p != '>' && *p != '@') ++p; if (!T.more(p)) break; last_char = *p++; }
+        if (!T.more(p)) break;                                                  // header char at the very end: ks_getuntil returns -1
+        const char *q = p;
+        while (T.more(q) && !isspace((unsigned char)*q)) ++q;                   // name
+        const size_t name_at = R->name_arena.size();
+        R->name_arena.append(p, q); R->name_arena.push_back('\0');
+        if (T.more(q) && *q != '\n') q = T.line_end(q);                         // comment
+        p = T.more(q) ? q + 1 : q;
+        const size_t seq_at = R->read_bases.size();                             // the sequence goes straight to its final place
+        int c = -1;
+        while (T.more(p)) {
+            c = (unsigned char)*p++;
+            if (c == '>' || c == '+' || c == '@') break;
+            if (c == '\n') { c = -1; continue; }
+            R->read_bases.push_back((char)c);
+            const char *le = T.line_end(p);
+            R->read_bases.append(p, le);
+            p = T.more(le) ? le + 1 : le;
+            if (R->read_bases.size() - seq_at > 1 && R->read_bases.back() == '\r') R->read_bases.pop_back();
+            c = -1;
+        }
+        const size_t seq_len = R->read_bases.size() - seq_at;
+        last_char = (c == '>' || c == '@') ? c : 0;
+        bool keep = true;
+        if (c == '+') {                                                         // FASTQ: skip the '+' line, read >= |seq| quality bytes
+            const char *le = T.line_end(p);
+            if (!T.more(le)) keep = false;                                      // -2: no quality string
+            else {
+                p = le + 1;
+                size_t ql = 0; bool got = false;
+                while (T.more(p) || !got) {
+                    if (!T.more(p)) break;
+                    const char *l2 = T.line_end(p);
+                    size_t n = (size_t)(l2 - p);
+                    ql += n;
+                    if (ql > 1 && n && l2[-1] == '\r') --ql;
+                    p = T.more(l2) ? l2 + 1 : l2;
+                    got = true;
+                    if (ql >= seq_len) break;
+                }
+                last_char = 0;
+                if (ql != seq_len) keep = false;                                // -2: truncated quality: the reference stops here
+            }
+        }
+        if (!keep) { R->read_bases.resize(seq_at); R->name_arena.resize(name_at); break; }
+        R->name_off.push_back(name_at);
+        R->read_off.push_back(R->read_bases.size());
+    }
+}
+
 extern "C" int phi_host_reads_load(const char *path, phi_host_reads **out, char *err, size_t errlen)
 {
     if (!path || !out) return PHI_ERR_ARG;
     *out = nullptr;
-    std::string text, e;
-    if (!slurp(path, text, e)) { set_err(err, errlen, e); return PHI_ERR_ARG; }
+    PhaseTimer pt;
     phi_host_reads *R = new phi_host_reads();
-    R->read_off.assign(1, 0);
-    const char *p = text.data(), *end = p + text.size();
-    auto line_end = [&](const char *s) { const char *nl = (const char *)memchr(s, '\n', (size_t)(end - s)); return nl ? nl : end; };
-    int last_char = 0;
-    for (;;) {                                                                  // kseq_read (kseq.h:192-232)
-        if (!last_char) { while (p < end && *p != '>' && *p != '@') ++p; if (p >= end) break; last_char = *p++; }
-        if (p >= end) break;                                                    // header char at the very end: ks_getuntil returns -1
-        const char *q = p;
-        while (q < end && !isspace((unsigned char)*q)) ++q;                     // name
-        std::string name(p, q);
-        if (q < end && *q != '\n') q = line_end(q);                             // comment
-        p = q < end ? q + 1 : end;
-        std::string seq;
-        int c = -1;
-        while (p < end) {
-            c = (unsigned char)*p++;
-            if (c == '>' || c == '+' || c == '@') break;
-            if (c == '\n') { c = -1; continue; }
-            seq.push_back((char)c);
-            const char *le = line_end(p);
-            seq.append(p, le);
-            p = le < end ? le + 1 : end;
-            if (seq.size() > 1 && seq.back() == '\r') seq.pop_back();
-            c = -1;
-        }
-        last_char = (c == '>' || c == '@') ? c : 0;
-        if (c == '+') {                                                         // FASTQ: skip the '+' line, read >= |seq| quality bytes
-            const char *le = line_end(p);
-            if (le >= end) break;                                               // -2: no quality string
-            p = le + 1;
-            size_t ql = 0; bool got = false;
-            while (p < end || !got) {
-                if (p >= end) break;
-                const char *l2 = line_end(p);
-                size_t n = (size_t)(l2 - p);
-                ql += n;
-                if (ql > 1 && n && l2[-1] == '\r') --ql;
-                p = l2 < end ? l2 + 1 : end;
-                got = true;
-                if (ql >= seq.size()) break;
-            }
-            last_char = 0;
-            if (ql != seq.size()) break;                                        // -2: truncated quality: the reference stops here
-        }
-        R->names.push_back(name);
-        R->read_bases += seq;
-        R->read_off.push_back(R->read_bases.size());
+    bool parsed = false;
+    const size_t hint = text_size_hint(path);
+    if (hint) {                                                                 // streamed: the parser runs while the reader thread inflates
+        TextStream T(path, hint);
+        R->read_bases.reserve(hint / 2 + 1024);
+        parse_reads(T, R);
+        if (T.th.joinable()) T.th.join();
+        if (T.failed && T.avail.load() == 0 && !T.overflow) { delete R; set_err(err, errlen, std::string("cannot open ") + path); return PHI_ERR_ARG; }
+        parsed = !T.failed && !T.overflow;
+        pt.lap(parsed ? "inflate || parse" : "streamed pass (discarded)");
+    }
+    if (!parsed) {                                                              // no usable size promise: inflate everything, then parse
+        delete R; R = new phi_host_reads();
+        std::string text, e;
+        if (!slurp(path, text, e)) { delete R; set_err(err, errlen, e); return PHI_ERR_ARG; }
+        pt.lap("inflate");
+        TextStream T(std::move(text));
+        parse_reads(T, R);
+        pt.lap("parse");
     }
     R->view.n_reads = R->read_off.size() - 1; R->view.read_off = R->read_off.data(); R->view.read_bases = (const uint8_t *)R->read_bases.data();
     *out = R;
@@ -388,5 +567,5 @@ extern "C" int phi_host_reads_load(const char *path, phi_host_reads **out, char 
 }
 
 extern "C" const phi_reads_view *phi_host_reads_view(const phi_host_reads *r) { return r ? &r->view : nullptr; }
-extern "C" const char *phi_host_reads_name(const phi_host_reads *r, uint64_t i) { return r && i < r->names.size() ? r->names[i].c_str() : ""; }
+extern "C" const char *phi_host_reads_name(const phi_host_reads *r, uint64_t i) { return r && i < r->name_off.size() ? r->name_arena.c_str() + r->name_off[i] : ""; }
 extern "C" void phi_host_reads_free(phi_host_reads *r) { delete r; }

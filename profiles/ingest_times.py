@@ -59,4 +59,4 @@ if __name__ == "__main__":
     print(json.dumps({"fixture": "test/MHC_4.gfa.gz (3.4 MB gz, 14 MB text, 111,805 S / 151,740 L / 5 W lines) + test/CHM13_reads.fq.gz (16,401 reads)",
                       "reference_s": {"gfa_read ('Loaded graph' stamp)": rl, "gfa_read + read_gfa + reads ('Graph has' stamp, includes process start)": rt},
                       "phi_b200_s": {"phi_host_graph_load": round(g, 4), "phi_host_reads_load": round(r, 4), "sum": round(g + r, 4)},
-                      "note": "single thread both; zlib inflate of the GFA alone is ~0.07 s"}, indent=1))
+                      "note": "reference: single thread; phi_b200 (round 2): a reader thread inflates while the caller's thread parses, W-line steps are resolved on up to 16 threads; zlib inflate of the GFA alone is ~0.07 s"}, indent=1))

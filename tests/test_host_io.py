@@ -74,6 +74,7 @@ def test_loaders_match_the_reference_parsers_on_its_fixtures(tmp_path, gfa, read
 
 GFA_EDGE = "\n".join([
     "H\tVN:Z:1.1",
+    "W\tearly\t3\tchr\t0\t0\t>a>b",                 # in front of the S-lines: neither step names a segment yet, both are dropped
     "S\ta\tACGTACGTAC",
     "L\ta\t+\tzz\t+\t0M",                         # zz first appears on an L-line: it gets id 1 before its S-line
     "S\tb\tGGGTTT\tLN:i:6\txx:Z:tag",
@@ -107,10 +108,11 @@ def test_gfa_edge_cases_match_the_reference_parser(tmp_path, crlf, gz):
     ref = phi_io.graph_from_arrays(d)
     g = phi_b200.load_gfa(path)
     assert_same_graph(g, ref, ref.walk_names)
-    assert g.segment_names[:2] == ["a", "zz"] and g.walk_names == ["s1.0", "s1.1", "s2.7", "s3.0", "s4.0", "s5.0"]
+    assert g.segment_names[:2] == ["a", "zz"] and g.walk_names == ["early.3", "s1.0", "s1.1", "s2.7", "s3.0", "s4.0", "s5.0"]
     assert g.n_unlinked_steps == 1                                  # only s5's a -> c
     wo = g.walk_off.astype(int)
-    assert g.walk_vtx[wo[1]:wo[2]].tolist() == [0, 2, 3]           # the reversed walk came out forward
+    assert wo[1] == 0                                               # the early walk is empty
+    assert g.walk_vtx[wo[2]:wo[3]].tolist() == [0, 2, 3]           # the reversed walk came out forward
 
 
 GFA_NAMES = "\n".join([
@@ -250,3 +252,55 @@ def test_random_gfas_match_the_reference_parser(tmp_path, seed):
     g = phi_b200.load_gfa(path)
     assert_same_graph(g, ref, ref.walk_names)
     assert_valid_topological_order(g)
+
+
+def test_read_loader_streams_and_falls_back(tmp_path):
+    """The read loader parses while a reader thread inflates, into a buffer sized by the gzip trailer.  A multi-member gzip file
+    promises only its last member's size: the streamed pass overflows and the loader must fall back to inflate-then-parse, with the
+    same result as on the plain file (and as on a single-member file, where the promise holds)."""
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(4000):
+        seq = "".join(rng.choice(list("ACGTN"), size=int(rng.integers(1, 400))))
+        recs.append(f"@r{i} comment {i}\n{seq}\n+\n{'I' * len(seq)}\n" if i % 3 else f">f{i}\n{seq[:len(seq) // 2]}\n{seq[len(seq) // 2:]}\n")
+    text = "".join(recs).encode()
+    plain, single, multi = str(tmp_path / "r.fx"), str(tmp_path / "single.gz"), str(tmp_path / "multi.gz")
+    open(plain, "wb").write(text)
+    with gzip.open(single, "wb") as f:
+        f.write(text)
+    cut = len(text) * 3 // 4
+    cut = text.index(b"\n", cut) + 1
+    with open(multi, "wb") as f:                                   # two members: the trailer of the file describes the second one only
+        f.write(gzip.compress(text[:cut]))
+        f.write(gzip.compress(text[cut:]))
+    want, want_names = phi_b200.load_reads(plain)
+    assert want.n_reads == 4000
+    for path in (single, multi):
+        got, names = phi_b200.load_reads(path)
+        assert np.array_equal(got.read_off, want.read_off) and np.array_equal(got.read_bases, want.read_bases) and names == want_names
+
+
+def test_gfa_loader_streams_and_falls_back(tmp_path):
+    """The same for the GFA loader: a two-member gzip file overflows the streamed pass, the scan is repeated over the text inflated
+    the plain way, and W-lines (cut during the scan, resolved afterwards in parallel) still only see the segments defined above them."""
+    c = Case("synth_small")
+    plain = str(tmp_path / "g.gfa")
+    synth.write_gfa(c.graph, plain)
+    text = open(plain, "rb").read()
+    # a W-line in front of every S-line: all its steps are unknown at that point and must be dropped (gfa-io.cpp:399-405)
+    early = b"W\tearly\t0\tchr\t0\t0\t>s1>s2>s3\n"
+    text = text.replace(b"S\ts1\t", early + b"S\ts1\t", 1)
+    open(plain, "wb").write(text)
+    cut = text.index(b"\n", len(text) // 2) + 1
+    multi_gz, single_gz = str(tmp_path / "multi.gfa.gz"), str(tmp_path / "single.gfa.gz")
+    with open(multi_gz, "wb") as f:
+        f.write(gzip.compress(text[:cut]))
+        f.write(gzip.compress(text[cut:]))
+    with gzip.open(single_gz, "wb") as f:
+        f.write(text)
+    want = phi_b200.load_gfa(plain)
+    wo = want.walk_off.astype(int)
+    assert want.walk_names[0] == "early.0" and wo[1] == 0            # known at its line: nothing
+    for path in (single_gz, multi_gz):
+        got = phi_b200.load_gfa(path)
+        assert_same_graph(got, want, want.walk_names)
