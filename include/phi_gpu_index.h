@@ -35,7 +35,7 @@ extern "C" {
 enum {
     PHI_OK = 0,
     PHI_ERR_ARG = 1,          /* bad argument / inconsistent view */
-    PHI_ERR_UNSUPPORTED = 2,  /* legal for the reference but not implemented here (e.g. k > 32): hard error, never a silent divergence */
+    PHI_ERR_UNSUPPORTED = 2,  /* legal for the reference but not implemented here (e.g. k > 255, w > 256): hard error, never a silent divergence */
     PHI_ERR_CUDA = 3,         /* CUDA runtime / no device */
     PHI_ERR_NOMEM = 4,
     PHI_ERR_COMM = 5          /* NCCL / multi-GPU exchange */
@@ -70,6 +70,8 @@ typedef struct {
  * Parameters = the ILP_index members the replaced range reads
  * (/root/reference/src/ILP_index.h:72-81; set in /root/reference/src/main.cpp:118-131):
  * k_mer (-k, 31), window (-w, 25), threshold (-T, 1.0f), debug (-d).
+ * Accepted: 1 <= k <= 255 (k-mers of up to 32 bases are packed two bits per base; longer ones are compared and
+ * hashed from their spelling, like k-mers with non-ACGT bytes), 1 <= w <= 256.
  */
 typedef struct {
     int32_t k;
@@ -102,7 +104,7 @@ typedef struct {
  * n_filtered          : filtered_kmers, ILP_index.cpp:719-721 (log :738-743).
  * n_walk_kmers / shared_kmer_hist : the -d1 statistic, ILP_index.cpp:565-606 — number of distinct walk-minimizer hashes
  *     (uniqe_kmers.size()) and, for i in [0, n_walks], how many of them occur in exactly i walks (kmer_hist_count[i]).
- *     Only computed when params.debug != 0 (shared_kmer_hist == NULL otherwise); single GPU only.
+ *     Only computed when params.debug != 0 (shared_kmer_hist == NULL otherwise); with several GPUs every rank returns the same, global statistic.
  */
 typedef struct {
     int32_t count_sp_r;
