@@ -295,6 +295,9 @@ void phi_host_reads_free(phi_host_reads *r);
  *                              (/root/reference/src/ILP_index.cpp:680-709), member lists of a group that occurs in several parts
  *                              united, per-walk counters / n_filtered / work counters summed, spectrum from the part that has it.
  *                              Works for parts of a by-walk partition (walk_id_base) as well.  Free with phi_gpu_index_result_free.
+ *                              Big merges cut the hash ranks into blocks and run them on up to 16 host threads
+ *                              (PHI_MERGE_THREADS overrides; count pass, prefix sum, write pass), output arrays are 2 MB aligned
+ *                              and marked for transparent huge pages.
  * PHI_ERR_UNSUPPORTED: top_order_map is not a permutation, or a walk does not follow it (use the by-walk partition then).
  */
 int phi_shard_walk_regions(const phi_graph_view *g, int world, uint64_t *coord_bounds /* [world + 1] */);

@@ -30,11 +30,14 @@ def case():
     return sg.graph, rd, phi_io.oracle_index(sg.graph, rd, 31, 25, 1.0)
 
 
-@pytest.mark.parametrize("n_parts,seed", [(1, 0), (2, 1), (3, 2), (8, 3)])
-def test_merge_of_arbitrary_parts_is_the_whole(case, n_parts, seed):
+@pytest.mark.parametrize("n_parts,seed,threads", [(1, 0, 1), (2, 1, 1), (3, 2, 1), (8, 3, 1), (1, 4, 3), (3, 5, 5), (8, 6, 16)])
+def test_merge_of_arbitrary_parts_is_the_whole(case, n_parts, seed, threads, monkeypatch):
     """Anchors dealt to the parts at random: the same (rank, vertex list) group then lives in several parts with different member
-    walks, the groups of one rank are spread over the parts — the merge must restore key order and unite the members."""
+    walks, the groups of one rank are spread over the parts — the merge must restore key order and unite the members.  Big merges
+    cut the hash ranks into blocks and run them on several threads (count pass, prefix, write pass): PHI_MERGE_THREADS forces that
+    path on this small case too."""
     g, rd, want = case
+    monkeypatch.setenv("PHI_MERGE_THREADS", str(threads))
     rng = np.random.default_rng(seed)
     assign = rng.integers(0, n_parts, want.n_anchors)
     parts = []
