@@ -304,3 +304,65 @@ def test_gfa_loader_streams_and_falls_back(tmp_path):
     for path in (single_gz, multi_gz):
         got = phi_b200.load_gfa(path)
         assert_same_graph(got, want, want.walk_names)
+
+
+MALFORMED_GFA = {
+    "empty": b"", "no_newline": b"S\t1\tACGT", "s_one_field": b"S\n", "s_two_fields": b"S\t1\n", "s_empty_seq": b"S\t1\t\n",
+    "l_short": b"S\t1\tACGT\nL\t1\n", "w_short": b"S\t1\tACGT\nW\tx\n", "w_unknown_segments": b"S\t1\tACGT\nW\ts\t0\tc\t0\t4\t>7>8\n",
+    "w_empty": b"S\t1\tACGT\nW\ts\t0\tc\t0\t4\t\n", "w_star": b"S\t1\tACGT\nW\ts\t0\tc\t0\t4\t*\n", "w_bad_hap": b"S\t1\tACGT\nW\ts\tzz\tc\t0\t4\t>1\n",
+    "cycle": b"S\t1\tACGT\nS\t2\tAC\nL\t1\t+\t2\t+\t0M\nL\t2\t+\t1\t+\t0M\nW\ts\t0\tc\t0\t4\t>1>2\n", "duplicate_s": b"S\t1\tACGT\nS\t1\tAC\n",
+    "only_tabs": b"\t\t\t\n\t\nS\t\t\n", "long_line": b"S\t1\t" + b"A" * 3000000 + b"\n",
+    "binary": bytes(np.random.default_rng(1).integers(0, 256, 5000, dtype=np.uint8)),
+}
+MALFORMED_READS = {
+    "no_newline.fa": b">r\nACGT", "no_name.fa": b"ACGT\nACGT\n", "fq_cut_in_quality.fq": b"@r\nACGT\n+\nII", "fq_no_plus.fq": b"@r\nACGT\nIIII\n",
+    "fq_short_quality.fq": b"@r\nACGT\n+\nI\n@r2\nAC\n+\nII\n", "blank_lines.fa": b">r\nAC\nGT\n\n>s\n\n>t\nA\n", "headers_only.fa": b">\n>\n>\n",
+    "binary.fa": bytes(np.random.default_rng(2).integers(0, 256, 5000, dtype=np.uint8)),
+}
+
+
+@needs_probe
+@pytest.mark.parametrize("name", sorted(MALFORMED_GFA))
+def test_malformed_gfa_is_read_like_the_reference_reads_it(tmp_path, name):
+    """Broken or degenerate GFA text: whatever the reference's parser makes of it (gfa-io.cpp skips what it cannot use), this one
+    makes the same of it — and never crashes."""
+    path = str(tmp_path / "m.gfa")
+    with open(path, "wb") as f:
+        f.write(MALFORMED_GFA[name])
+    d = probe(path, None, str(tmp_path / "p.phiarr"))
+    g = phi_b200.load_gfa(path)
+    assert (g.n_vtx, g.n_walks) == (len(d["seg_off"]) - 1, len(d["walk_off"]) - 1)
+    assert g.seg_off.tolist() == d["seg_off"].tolist() and bytes(g.seg_bases) == bytes(d["seg_bases"])
+    assert g.walk_off.tolist() == d["walk_off"].tolist() and g.walk_vtx.tolist() == d["walk_vtx"].tolist()
+
+
+@needs_probe
+@pytest.mark.parametrize("fname", sorted(MALFORMED_READS))
+def test_malformed_reads_are_read_like_kseq_reads_them(tmp_path, fname):
+    gfa = str(tmp_path / "g.gfa")
+    with open(gfa, "w") as f:
+        f.write("S\ta\tACGT\n")
+    path = str(tmp_path / fname)
+    with open(path, "wb") as f:
+        f.write(MALFORMED_READS[fname])
+    d = probe(gfa, path, str(tmp_path / "p.phiarr"))
+    rd, names = phi_b200.load_reads(path)
+    assert rd.read_off.tolist() == d["read_off"].tolist() and bytes(rd.read_bases) == bytes(d["read_bases"])
+
+
+@pytest.mark.parametrize("cut", [150, 1000])
+def test_truncated_gzip_yields_what_could_be_inflated(tmp_path, cut):
+    """A gzip file cut short: gzread (the reference's reader) hands out what inflates and then stops; so does this loader."""
+    import gzip
+    body = b"".join(b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(5000))
+    path = str(tmp_path / "t.fq.gz")
+    with open(path, "wb") as f:
+        f.write(gzip.compress(body)[:cut])
+    rd, names = phi_b200.load_reads(path)
+    assert 0 < rd.n_reads < 5000 and np.all(np.diff(rd.read_off.astype(np.int64))[:-1] == 10)
+    if os.path.exists(PROBE):
+        gfa = str(tmp_path / "g.gfa")
+        with open(gfa, "w") as f:
+            f.write("S\ta\tACGT\n")
+        d = probe(gfa, path, str(tmp_path / "p.phiarr"))
+        assert rd.read_off.tolist() == d["read_off"].tolist() and bytes(rd.read_bases) == bytes(d["read_bases"])
