@@ -287,6 +287,9 @@ void phi_host_reads_free(phi_host_reads *r);
  *   phi_shard_slice_walks    : for every walk of `g` the slice [slice_first[h], slice_first[h] + slice_len[h]) of g->walk_vtx
  *                              (absolute step indices) that the GPU owning [coord_lo, coord_hi) needs; the caller builds that GPU's
  *                              graph view from the slices (same walk order, walk_id_base 0, n_walks_global = n_walks);
+ *   phi_shard_slice_walks_all : the same for all `world` regions of coord_bounds at once (slice_first / slice_len are [world][n_walks],
+ *                              region r at r * n_walks): the O(steps) check that the walks follow the order runs once, on several
+ *                              host threads, instead of once per region;
  *   phi_gpu_index_set_walk_region : tells the ctx which coordinate range it owns: of the walks (slices) it is given, only the
  *                              windows whose last k-mer starts on a vertex inside the range are produced (path_kmer_positions,
  *                              minimizers_per_walk and the groups then cover the owned part only; sum / merge over the GPUs).
@@ -303,6 +306,8 @@ void phi_host_reads_free(phi_host_reads *r);
 int phi_shard_walk_regions(const phi_graph_view *g, int world, uint64_t *coord_bounds /* [world + 1] */);
 int phi_shard_slice_walks(const phi_graph_view *g, int k, int w, uint64_t coord_lo, uint64_t coord_hi,
                           uint64_t *slice_first /* [n_walks] */, uint64_t *slice_len /* [n_walks] */);
+int phi_shard_slice_walks_all(const phi_graph_view *g, int k, int w, int world, const uint64_t *coord_bounds /* [world + 1] */,
+                              uint64_t *slice_first /* [world * n_walks] */, uint64_t *slice_len /* [world * n_walks] */);
 int phi_gpu_index_set_walk_region(phi_gpu_index_ctx *ctx, uint64_t coord_lo, uint64_t coord_hi);
 int phi_index_result_merge(const phi_index_result *const *parts, int n_parts, phi_index_result **out);
 

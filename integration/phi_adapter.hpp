@@ -17,6 +17,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <thread>
 #include <utility>
@@ -156,19 +157,24 @@ inline FrontEnd run_front_end_result(ILP_index &ix, std::vector<std::pair<std::s
         uint8_t id[PHI_COMM_ID_BYTES];
         if (W > 1 && phi_gpu_index_comm_unique_id(id) != PHI_OK) { fprintf(stderr, "Error: %s\n", phi_gpu_last_error(0)); exit(1); }
         std::vector<detail::Shard> shards(W);
-        std::vector<uint64_t> sl_first(ix.num_walks), sl_len(ix.num_walks);
+        const size_t NWK = (size_t)ix.num_walks;
+        std::vector<uint64_t> sl_first((size_t)W * NWK), sl_len((size_t)W * NWK);
+        if (by_region) by_region = phi_shard_slice_walks_all(&gfull, prm.k, prm.w, W, cb.data(), sl_first.data(), sl_len.data()) == PHI_OK;
         if (by_region) {
-            for (int r = 0; r < W && by_region; ++r) {
+            // every GPU's copy of its slices: offsets first, then the (walk, GPU) copies in parallel
+            for (int r = 0; r < W; ++r) {
                 detail::Shard &s = shards[r];
-                if (phi_shard_slice_walks(&gfull, prm.k, prm.w, cb[r], cb[r + 1], sl_first.data(), sl_len.data()) != PHI_OK) { by_region = false; break; }
-                s.walk_off.assign(1, 0);
-                for (uint32_t h = 0; h < ix.num_walks; ++h) {
-                    s.walk_vtx.insert(s.walk_vtx.end(), walk_vtx.begin() + sl_first[h], walk_vtx.begin() + sl_first[h] + sl_len[h]);
-                    s.walk_off.push_back(s.walk_vtx.size());
-                }
+                s.walk_off.assign(NWK + 1, 0);
+                for (size_t h = 0; h < NWK; ++h) s.walk_off[h + 1] = s.walk_off[h] + sl_len[(size_t)r * NWK + h];
+                s.walk_vtx.resize(s.walk_off[NWK]);
                 s.region = true; s.coord_lo = cb[r]; s.coord_hi = cb[r + 1]; s.walk_id_base = 0;
-                s.g = gfull; s.g.walk_off = s.walk_off.data(); s.g.walk_vtx = s.walk_vtx.data();
             }
+#pragma omp parallel for schedule(dynamic, 1)
+            for (long long t = 0; t < (long long)((size_t)W * NWK); ++t) {
+                const size_t r = (size_t)t / NWK, h = (size_t)t % NWK;
+                if (sl_len[t]) memcpy(shards[r].walk_vtx.data() + shards[r].walk_off[h], walk_vtx.data() + sl_first[t], (size_t)sl_len[t] * sizeof(uint32_t));
+            }
+            for (int r = 0; r < W; ++r) { detail::Shard &s = shards[r]; s.g = gfull; s.g.walk_off = s.walk_off.data(); s.g.walk_vtx = s.walk_vtx.data(); }
         }
         if (!by_region) {
             if (W > 1) phi_shard_split_by_weight(walk_off.data(), ix.num_walks, W, wb.data());

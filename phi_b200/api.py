@@ -93,6 +93,8 @@ def load_library():
     lib.phi_shard_walk_regions.argtypes = [C.POINTER(_abi.GraphView), C.c_int, _abi.u64p]
     lib.phi_shard_slice_walks.restype = C.c_int
     lib.phi_shard_slice_walks.argtypes = [C.POINTER(_abi.GraphView), C.c_int, C.c_int, C.c_uint64, C.c_uint64, _abi.u64p, _abi.u64p]
+    lib.phi_shard_slice_walks_all.restype = C.c_int
+    lib.phi_shard_slice_walks_all.argtypes = [C.POINTER(_abi.GraphView), C.c_int, C.c_int, C.c_int, _abi.u64p, _abi.u64p, _abi.u64p]
     lib.phi_gpu_index_set_walk_region.restype = C.c_int
     lib.phi_gpu_index_set_walk_region.argtypes = [ctxp, C.c_uint64, C.c_uint64]
     lib.phi_index_result_merge.restype = C.c_int

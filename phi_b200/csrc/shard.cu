@@ -19,10 +19,11 @@ extern "C" int phi_shard_split_by_weight(const uint64_t *off, uint64_t n, int wo
     bounds[0] = 0;
     uint64_t i = 0;
     for (int r = 1; r < world; ++r) {
-        // first item whose start offset reaches r/world of the total weight
-        unsigned __int128 target = (unsigned __int128)total * (unsigned)r / (unsigned)world;
-        while (i < n && (unsigned __int128)(off[i] - base) < target) ++i;
-        bounds[r] = i;
+        // first item whose start offset reaches r/world of the total weight (offsets ascend: binary search from the last cut on)
+        const unsigned __int128 target = (unsigned __int128)total * (unsigned)r / (unsigned)world;
+        uint64_t lo = i, hi = n;
+        while (lo < hi) { const uint64_t m = lo + ((hi - lo) >> 1); if ((unsigned __int128)(off[m] - base) < target) lo = m + 1; else hi = m; }
+        bounds[r] = i = lo;
     }
     bounds[world] = n;
     return PHI_OK;
@@ -38,6 +39,9 @@ extern "C" int phi_shard_split_by_weight(const uint64_t *off, uint64_t n, int wo
 // of every walk is owned by exactly one GPU, and the union of the per-GPU results is the reference's result
 // (phi_index_result_merge).
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -61,6 +65,74 @@ bool topo_coordinates(const phi_graph_view *g, std::vector<uint64_t> &coord)
     return true;
 }
 
+// fn(task) for task in [0, n) on up to 16 host threads (PHI_SHARD_THREADS overrides); `work` = items behind the tasks, small jobs stay
+// on the calling thread.
+template <class F> void shard_parallel(size_t n, uint64_t work, F fn)
+{
+    int threads = 1;
+    if (const char *e = getenv("PHI_SHARD_THREADS")) threads = std::max(1, std::min(64, atoi(e)));
+    else if (work >= (1u << 20)) threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    threads = (int)std::min<size_t>((size_t)threads, n);
+    if (threads <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<size_t> next(0);
+    auto body = [&]() { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(body);
+    body();
+    for (std::thread &t : pool) t.join();
+}
+
+// the walk steps cut into pieces of at most PIECE steps (a piece never spans two walks): the unit of the parallel passes
+struct StepPiece { uint32_t walk; uint64_t s0, s1; };
+std::vector<StepPiece> step_pieces(const phi_graph_view *g)
+{
+    uint64_t PIECE = 1u << 21;
+    if (const char *e = getenv("PHI_SHARD_PIECE")) PIECE = std::max<uint64_t>(1, strtoull(e, nullptr, 10));   // tests: piece borders everywhere
+    std::vector<StepPiece> out;
+    for (uint32_t h = 0; h < g->n_walks; ++h)
+        for (uint64_t s = g->walk_off[h]; s < g->walk_off[h + 1]; s += PIECE) out.push_back({h, s, std::min<uint64_t>(s + PIECE, g->walk_off[h + 1])});
+    return out;
+}
+
+// every walk follows the topological order (non-decreasing coordinate from step to step)?
+bool walks_follow_order(const phi_graph_view *g, const std::vector<uint64_t> &coord)
+{
+    const std::vector<StepPiece> pieces = step_pieces(g);
+    const uint32_t *wv = g->walk_vtx;
+    std::atomic<int> bad(0);
+    shard_parallel(pieces.size(), g->n_walks ? g->walk_off[g->n_walks] : 0, [&](size_t i) {
+        if (bad.load(std::memory_order_relaxed)) return;
+        const StepPiece &pc = pieces[i];
+        const uint64_t end = std::min<uint64_t>(pc.s1 + 1, g->walk_off[pc.walk + 1]);     // the pair across the piece border belongs to this piece
+        if (pc.s0 >= end) return;
+        uint64_t prev = coord[wv[pc.s0]];
+        for (uint64_t s = pc.s0 + 1; s < end; ++s) { const uint64_t c = coord[wv[s]]; if (c < prev) { bad.store(1); return; } prev = c; }
+    });
+    return !bad.load();
+}
+
+// slices of all walks for the region [lo, hi): see phi_shard_slice_walks
+void slice_region(const phi_graph_view *g, const std::vector<uint64_t> &coord, int k, int w, uint64_t coord_lo, uint64_t coord_hi,
+                  uint64_t *slice_first, uint64_t *slice_len)
+{
+    const uint32_t *wv = g->walk_vtx;
+    for (uint32_t h = 0; h < g->n_walks; ++h) {
+        const uint64_t s0 = g->walk_off[h], s1 = g->walk_off[h + 1];
+        // a = first step with coordinate >= lo, b = first step with coordinate >= hi
+        uint64_t a = s0, b = s1, x = s0, y = s1;
+        while (x < y) { const uint64_t m = (x + y) >> 1; if (coord[wv[m]] < coord_lo) x = m + 1; else y = m; }
+        a = x; y = s1;
+        while (x < y) { const uint64_t m = (x + y) >> 1; if (coord[wv[m]] < coord_hi) x = m + 1; else y = m; }
+        b = x;
+        if (a >= b) { slice_first[h] = a; slice_len[h] = 0; continue; }
+        uint64_t L = a, have = 0;
+        while (L > s0 && have < (uint64_t)w) { --L; have += g->seg_off[wv[L] + 1] - g->seg_off[wv[L]]; }
+        uint64_t R = b; have = 0;
+        while (R < s1 && have < (uint64_t)(k - 1)) { have += g->seg_off[wv[R] + 1] - g->seg_off[wv[R]]; ++R; }
+        slice_first[h] = L; slice_len[h] = R - L;
+    }
+}
+
 }  // namespace
 
 extern "C" int phi_shard_walk_regions(const phi_graph_view *g, int world, uint64_t *coord_bounds)
@@ -72,12 +144,26 @@ extern "C" int phi_shard_walk_regions(const phi_graph_view *g, int world, uint64
     std::vector<uint64_t> coord;
     if (!topo_coordinates(g, coord)) return PHI_ERR_UNSUPPORTED;
     const uint64_t total = g->seg_off[g->n_vtx];
-    // steps per coordinate bin over the given walks (a sample of the walks is enough), equal-weight cuts
+    // steps per coordinate bin over the given walks, equal-weight cuts.  The bin of a vertex is computed once per vertex; big walk
+    // sets are sampled (every stride-th step, at most ~8 M samples: the cuts move by a fraction of a bin) piece by piece on
+    // several threads.
     const int BINS = 1 << 14;
-    std::vector<uint64_t> hist(BINS + 1, 0);
-    const uint64_t S = g->n_walks ? g->walk_off[g->n_walks] : 0;
     const unsigned __int128 scale = total ? total : 1;
-    for (uint64_t s = 0; s < S; ++s) hist[(size_t)(((unsigned __int128)coord[g->walk_vtx[s]] * BINS) / scale)]++;
+    std::vector<uint16_t> bin_of(g->n_vtx);
+    for (uint32_t v = 0; v < g->n_vtx; ++v) bin_of[v] = (uint16_t)std::min<uint64_t>(BINS - 1, (uint64_t)(((unsigned __int128)coord[v] * BINS) / scale));
+    const uint64_t S = g->n_walks ? g->walk_off[g->n_walks] : 0;
+    const uint64_t stride = std::max<uint64_t>(1, S >> 23);
+    const std::vector<StepPiece> pieces = step_pieces(g);
+    std::vector<std::vector<uint64_t>> part(pieces.size());
+    const uint32_t *wv = g->walk_vtx;
+    shard_parallel(pieces.size(), S / stride, [&](size_t i) {
+        std::vector<uint64_t> &hist = part[i];
+        hist.assign(BINS, 0);
+        const uint64_t first = (pieces[i].s0 + stride - 1) / stride * stride;               // the sample is every stride-th step of the whole step array
+        for (uint64_t s = first; s < pieces[i].s1; s += stride) hist[bin_of[wv[s]]]++;
+    });
+    std::vector<uint64_t> hist(BINS + 1, 0);
+    for (const std::vector<uint64_t> &h : part) for (int b = 0; b < BINS; ++b) hist[b] += h[b];
     if (!S) for (int b = 0; b < BINS; ++b) hist[b] = 1;
     uint64_t sum = 0; for (int b = 0; b < BINS; ++b) sum += hist[b];
     uint64_t run = 0; int b = 0;
@@ -96,23 +182,19 @@ extern "C" int phi_shard_slice_walks(const phi_graph_view *g, int k, int w, uint
     if (!g || !slice_first || !slice_len || k < 1 || w < 1) return PHI_ERR_ARG;
     std::vector<uint64_t> coord;
     if (!topo_coordinates(g, coord)) return PHI_ERR_UNSUPPORTED;
-    for (uint32_t h = 0; h < g->n_walks; ++h) {
-        const uint64_t s0 = g->walk_off[h], s1 = g->walk_off[h + 1];
-        const uint32_t *wv = g->walk_vtx;
-        for (uint64_t s = s0; s + 1 < s1; ++s)
-            if (coord[wv[s]] > coord[wv[s + 1]]) return PHI_ERR_UNSUPPORTED;     // a walk that does not follow the topological order: no region cut
-        // a = first step with coordinate >= lo, b = first step with coordinate >= hi
-        uint64_t a = s0, b = s1, x = s0, y = s1;
-        while (x < y) { const uint64_t m = (x + y) >> 1; if (coord[wv[m]] < coord_lo) x = m + 1; else y = m; }
-        a = x; y = s1;
-        while (x < y) { const uint64_t m = (x + y) >> 1; if (coord[wv[m]] < coord_hi) x = m + 1; else y = m; }
-        b = x;
-        if (a >= b) { slice_first[h] = a; slice_len[h] = 0; continue; }
-        uint64_t L = a, have = 0;
-        while (L > s0 && have < (uint64_t)w) { --L; have += g->seg_off[wv[L] + 1] - g->seg_off[wv[L]]; }
-        uint64_t R = b; have = 0;
-        while (R < s1 && have < (uint64_t)(k - 1)) { have += g->seg_off[wv[R] + 1] - g->seg_off[wv[R]]; ++R; }
-        slice_first[h] = L; slice_len[h] = R - L;
-    }
+    if (!walks_follow_order(g, coord)) return PHI_ERR_UNSUPPORTED;                           // no region cut for such walks
+    slice_region(g, coord, k, w, coord_lo, coord_hi, slice_first, slice_len);
+    return PHI_OK;
+}
+
+extern "C" int phi_shard_slice_walks_all(const phi_graph_view *g, int k, int w, int world, const uint64_t *coord_bounds,
+                                         uint64_t *slice_first, uint64_t *slice_len)
+{
+    if (!g || !coord_bounds || !slice_first || !slice_len || k < 1 || w < 1 || world < 1) return PHI_ERR_ARG;
+    std::vector<uint64_t> coord;
+    if (!topo_coordinates(g, coord)) return PHI_ERR_UNSUPPORTED;
+    if (!walks_follow_order(g, coord)) return PHI_ERR_UNSUPPORTED;                           // checked once for all regions
+    for (int r = 0; r < world; ++r)
+        slice_region(g, coord, k, w, coord_bounds[r], coord_bounds[r + 1], slice_first + (size_t)r * g->n_walks, slice_len + (size_t)r * g->n_walks);
     return PHI_OK;
 }

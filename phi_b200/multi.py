@@ -53,6 +53,22 @@ def slice_walks(graph, k, w, coord_lo, coord_hi):
     return _abi.Graph(graph.seg_off, graph.seg_bases, off, vtx, graph.top_order_map, graph.walk_names)
 
 
+def slice_walks_all(graph, k, w, bounds):
+    """phi_shard_slice_walks_all: (slice_first, slice_len), each [world][n_walks], for all regions of `bounds` at once (the order
+    check of the walks runs once).  None when a walk does not follow the topological order."""
+    lib = load_library()
+    world = len(bounds) - 1
+    first = np.zeros((world, graph.n_walks), dtype=np.uint64)
+    length = np.zeros((world, graph.n_walks), dtype=np.uint64)
+    b = np.ascontiguousarray(bounds, dtype=np.uint64)
+    gv = graph.view()
+    rc = lib.phi_shard_slice_walks_all(C.byref(gv), k, w, world, b.ctypes.data_as(_abi.u64p), first.ctypes.data_as(_abi.u64p), length.ctypes.data_as(_abi.u64p))
+    if rc == _abi.PHI_ERR_UNSUPPORTED:
+        return None
+    assert rc == 0, rc
+    return first, length
+
+
 def shard_inputs(graph, reads, rank, world, k=31, w=25, mode="region"):
     """This rank's shard.  Reads: contiguous, balanced by bases.  Walks, mode "region" (default): ALL walks cut to this rank's range
     of the topological base coordinate (walk sharing keeps working: identical chunks of different walks meet on one GPU);

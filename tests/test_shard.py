@@ -102,6 +102,53 @@ def test_region_slices_cover_the_walks_with_context(case, world, k, w):
         assert np.all(owned[h] == 1)                       # every step is owned by exactly one region
 
 
+@pytest.mark.parametrize("threads", [1, 4])
+def test_all_regions_at_once_equal_region_by_region(case, threads, monkeypatch):
+    """phi_shard_slice_walks_all (one order check for all regions, pieces of the walks on several host threads) against one
+    phi_shard_slice_walks call per region; the bounds do not depend on the number of threads either."""
+    g = case[0]
+    monkeypatch.setenv("PHI_SHARD_THREADS", "1")
+    b1 = multi.region_bounds(g, 5)
+    monkeypatch.setenv("PHI_SHARD_THREADS", str(threads))
+    b = multi.region_bounds(g, 5)
+    assert np.array_equal(b, b1)
+    first, length = multi.slice_walks_all(g, 31, 25, b)
+    wo = g.walk_off.astype(np.int64)
+    for r in range(5):
+        gs = multi.slice_walks(g, 31, 25, b[r], b[r + 1])
+        assert np.array_equal(np.diff(gs.walk_off.astype(np.int64)), length[r].astype(np.int64))
+        for h in range(g.n_walks):
+            f, n = int(first[r, h]), int(length[r, h])
+            assert wo[h] <= f and f + n <= wo[h + 1]
+            assert np.array_equal(g.walk_vtx[f:f + n], gs.walk_vtx[int(gs.walk_off[h]):int(gs.walk_off[h + 1])])
+    # one pair of steps out of order anywhere refuses the cut — also when the pair lies across a border of the pieces the parallel
+    # check works on (PHI_SHARD_PIECE=4: borders every 4 steps), or at the very end of a walk
+    monkeypatch.setenv("PHI_SHARD_PIECE", "4")
+    assert np.array_equal(multi.region_bounds(g, 5), b1)
+    f4, l4 = multi.slice_walks_all(g, 31, 25, b)
+    assert np.array_equal(f4, first) and np.array_equal(l4, length)
+    for s in [int(wo[3]) + d for d in (0, 2, 3, 4, 7, 8)] + [int(wo[4]) - 2, int(wo[g.n_walks]) - 2]:
+        bad_vtx = g.walk_vtx.copy()
+        bad_vtx[s], bad_vtx[s + 1] = bad_vtx[s + 1], bad_vtx[s]
+        bad = _abi.Graph(g.seg_off, g.seg_bases, g.walk_off, bad_vtx, g.top_order_map)
+        assert multi.slice_walks_all(bad, 31, 25, b) is None and multi.slice_walks(bad, 31, 25, b[0], b[1]) is None, s
+    # the last step of one walk and the first of the next are not a pair
+    ok_vtx = g.walk_vtx.copy()
+    assert multi.slice_walks_all(_abi.Graph(g.seg_off, g.seg_bases, g.walk_off, ok_vtx, g.top_order_map), 31, 25, b) is not None
+
+
+def test_split_by_weight_cuts():
+    off = np.concatenate([[0], np.cumsum(np.array([5, 0, 0, 7, 1, 1, 1, 30, 2, 0], dtype=np.uint64))]).astype(np.uint64)
+    for world in (1, 2, 3, 4, 7, 12):
+        b = multi.split_by_weight(off, world)
+        assert b[0] == 0 and b[-1] == len(off) - 1 and np.all(np.diff(b.astype(np.int64)) >= 0)
+        total = int(off[-1])
+        for r in range(1, world):                      # first item whose start offset reaches r/world of the total weight
+            target = total * r // world
+            want = next(i for i in range(len(off)) if int(off[i]) >= target)
+            assert int(b[r]) == min(want, len(off) - 1), (world, r)
+
+
 def test_region_cut_refuses_walks_against_the_order(case):
     g = case[0]
     bad = _abi.Graph(g.seg_off, g.seg_bases, g.walk_off, g.walk_vtx[::-1].copy(), g.top_order_map)
