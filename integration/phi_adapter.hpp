@@ -14,6 +14,7 @@
 #define PHI_ADAPTER_HPP
 
 #include "phi_gpu_index.h"
+#include "phi_shards.hpp"     // detail::Shard, detail::build_shards: the per-GPU views of a multi-GPU run
 
 #include <cstdio>
 #include <cstdlib>
@@ -46,13 +47,6 @@ inline int32_t member_walk(const phi_index_result *res, uint64_t m)
 }
 
 namespace detail {
-struct Shard {                                     // the views of one GPU: its walks (whole walks or region slices) and reads, offsets rebased to 0
-    std::vector<uint64_t> walk_off, read_off;
-    std::vector<uint32_t> walk_vtx;                // region slices only (by-walk shards point into the caller's array)
-    phi_graph_view g; phi_reads_view rd;
-    uint32_t walk_id_base;
-    bool region; uint64_t coord_lo, coord_hi;
-};
 struct Job { phi_gpu_index_ctx *ctx; int rank, world; const uint8_t *id; uint32_t n_walks_global; Shard *sh; const phi_index_params *prm; phi_index_result *res; int rc; std::string err; };
 inline void run_job(Job *j)
 {
@@ -147,52 +141,17 @@ inline FrontEnd run_front_end_result(ILP_index &ix, std::vector<std::pair<std::s
         phi_graph_view gfull;
         gfull.n_vtx = ix.n_vtx; gfull.seg_off = seg_off.data(); gfull.seg_bases = (const uint8_t *)seg_bases.data();
         gfull.n_walks = ix.num_walks; gfull.walk_off = walk_off.data(); gfull.walk_vtx = walk_vtx.data(); gfull.top_order_map = ix.top_order_map.data();
-        std::vector<uint64_t> wb(W + 1, 0), rb(W + 1, 0), cb(W + 1, 0);
-        wb[W] = ix.num_walks; rb[W] = ip_reads.size();
-        bool by_region = false;
-        if (W > 1) {
-            phi_shard_split_by_weight(read_off.data(), ip_reads.size(), W, rb.data());
-            by_region = phi_shard_walk_regions(&gfull, W, cb.data()) == PHI_OK;
-        }
+        phi_reads_view rfull;
+        rfull.n_reads = ip_reads.size(); rfull.read_off = read_off.data(); rfull.read_bases = (const uint8_t *)read_bases.data();
         uint8_t id[PHI_COMM_ID_BYTES];
         if (W > 1 && phi_gpu_index_comm_unique_id(id) != PHI_OK) { fprintf(stderr, "Error: %s\n", phi_gpu_last_error(0)); exit(1); }
-        std::vector<detail::Shard> shards(W);
-        const size_t NWK = (size_t)ix.num_walks;
-        std::vector<uint64_t> sl_first((size_t)W * NWK), sl_len((size_t)W * NWK);
-        if (by_region) by_region = phi_shard_slice_walks_all(&gfull, prm.k, prm.w, W, cb.data(), sl_first.data(), sl_len.data()) == PHI_OK;
-        if (by_region) {
-            // every GPU's copy of its slices: offsets first, then the (walk, GPU) copies in parallel
-            for (int r = 0; r < W; ++r) {
-                detail::Shard &s = shards[r];
-                s.walk_off.assign(NWK + 1, 0);
-                for (size_t h = 0; h < NWK; ++h) s.walk_off[h + 1] = s.walk_off[h] + sl_len[(size_t)r * NWK + h];
-                s.walk_vtx.resize(s.walk_off[NWK]);
-                s.region = true; s.coord_lo = cb[r]; s.coord_hi = cb[r + 1]; s.walk_id_base = 0;
-            }
-#pragma omp parallel for schedule(dynamic, 1)
-            for (long long t = 0; t < (long long)((size_t)W * NWK); ++t) {
-                const size_t r = (size_t)t / NWK, h = (size_t)t % NWK;
-                if (sl_len[t]) memcpy(shards[r].walk_vtx.data() + shards[r].walk_off[h], walk_vtx.data() + sl_first[t], (size_t)sl_len[t] * sizeof(uint32_t));
-            }
-            for (int r = 0; r < W; ++r) { detail::Shard &s = shards[r]; s.g = gfull; s.g.walk_off = s.walk_off.data(); s.g.walk_vtx = s.walk_vtx.data(); }
-        }
-        if (!by_region) {
-            if (W > 1) phi_shard_split_by_weight(walk_off.data(), ix.num_walks, W, wb.data());
-            for (int r = 0; r < W; ++r) {
-                detail::Shard &s = shards[r];
-                s.walk_off.clear(); s.walk_vtx.clear();
-                for (uint64_t h = wb[r]; h <= wb[r + 1]; ++h) s.walk_off.push_back(walk_off[h] - walk_off[wb[r]]);
-                s.region = false; s.coord_lo = 0; s.coord_hi = ~0ull; s.walk_id_base = (uint32_t)wb[r];
-                s.g = gfull; s.g.n_walks = (uint32_t)(wb[r + 1] - wb[r]); s.g.walk_off = s.walk_off.data(); s.g.walk_vtx = walk_vtx.data() + walk_off[wb[r]];
-            }
-        }
+        std::vector<detail::Shard> shards;
+        detail::build_shards(gfull, rfull, W, prm.k, prm.w, shards);
+        const double t_shard = realtime();
         std::vector<detail::Job> jobs(W);
         for (int r = 0; r < W; ++r) {
-            detail::Shard &s = shards[r];
-            for (uint64_t q = rb[r]; q <= rb[r + 1]; ++q) s.read_off.push_back(read_off[q] - read_off[rb[r]]);
-            s.rd.n_reads = rb[r + 1] - rb[r]; s.rd.read_off = s.read_off.data(); s.rd.read_bases = (const uint8_t *)read_bases.data() + read_off[rb[r]];
             detail::Job &j = jobs[r];
-            j.ctx = P.ctx[r]; j.rank = r; j.world = W; j.id = id; j.n_walks_global = ix.num_walks; j.sh = &s; j.prm = &prm; j.res = 0; j.rc = PHI_OK;
+            j.ctx = P.ctx[r]; j.rank = r; j.world = W; j.id = id; j.n_walks_global = ix.num_walks; j.sh = &shards[r]; j.prm = &prm; j.res = 0; j.rc = PHI_OK;
         }
         if (W == 1) detail::run_job(&jobs[0]);
         else {
@@ -209,8 +168,8 @@ inline FrontEnd run_front_end_result(ILP_index &ix, std::vector<std::pair<std::s
             parts.push_back(jobs[r].res);
         }
         if (getenv("PHI_ADAPTER_TIMES"))          // where the front end's wall time goes (stderr, one line)
-            fprintf(stderr, "[phi_adapter] flat views %.4f s, wait for the CUDA context(s) %.4f s, shard + run on %d GPU(s) %.4f s\n",
-                    t_flat - t_enter, t_ctx - t_flat, W, realtime() - t_ctx);
+            fprintf(stderr, "[phi_adapter] flat views %.4f s, wait for the CUDA context(s) %.4f s, shards %.4f s, run on %d GPU(s) %.4f s\n",
+                    t_flat - t_enter, t_ctx - t_flat, t_shard - t_ctx, W, realtime() - t_shard);
         if (W == 1) fe.parts = parts;
         else {                                    // one result in the reference's order
             phi_index_result *merged = 0;
