@@ -2,6 +2,8 @@
 // What the reference does with gfatools + read_gfa + kseq (serial text I/O into nested std::vector / std::string
 // containers, /root/reference/src/gfa-io.cpp:462-508, src/ILP_index.cpp:20-155, :313-328, src/kseq.h:192-232) is done here
 // straight into the buffers include/phi_gpu_index.h describes, so nothing has to be re-flattened before the upload.
+// Text arrives while it is parsed: single-member gzip through a reader thread, bgzip (BGZF) files through parallel inflate of the
+// members (TextStream).
 //
 // Semantics kept (SURVEY.md §9 rule 11):
 //   * only S, L and W records are looked at (gfa-io.cpp:493-495); lines shorter than 3 bytes or without a tab in column 2
@@ -26,6 +28,10 @@
 
 #include <zlib.h>
 #include <time.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -86,33 +92,99 @@ bool slurp(const char *path, std::string &out, std::string &err)
     return true;
 }
 
-// Inflated text that becomes available while it is being parsed: a reader thread inflates (zlib is the slowest stage of the read
-// ingest and cannot be split for a plain gzip stream) into a buffer of fixed capacity — the size the gzip trailer promises —
-// and the parser, written against `more()` / `line_end()` instead of a fixed end pointer, follows right behind it.  If the trailer
-// lied (multi-member or > 4 GB streams) the buffer overflows, `overflow` is set and the caller falls back to slurp().
+// A BGZF file (bgzip: what pangenome graphs, VCFs and many read sets are compressed with) is a chain of independent gzip members of
+// at most 64 KB of text each, every member header carrying the member's compressed size ("BC" extra subfield) and every trailer its
+// text size — so the members can be found by hopping from header to header and inflated in parallel straight to their final places.
+struct BgzfIndex {
+    struct Block { size_t in_off, in_len, out_off; uint32_t out_len, crc; };   // in_off / in_len: the raw deflate data of the member
+    std::vector<Block> blocks;
+    size_t total = 0;                                                           // text bytes
+    const unsigned char *map = nullptr; size_t map_len = 0;                     // the compressed file (mmap)
+    BgzfIndex() = default;
+    BgzfIndex(const BgzfIndex &) = delete; BgzfIndex &operator=(const BgzfIndex &) = delete;
+    BgzfIndex(BgzfIndex &&o) noexcept : blocks(std::move(o.blocks)), total(o.total), map(o.map), map_len(o.map_len) { o.map = nullptr; o.map_len = 0; }
+    ~BgzfIndex() { if (map) munmap((void *)map, map_len); }
+};
+
+// true iff the WHOLE file is a well-formed chain of BGZF members (anything else — plain gzip, a cut file, trailing bytes — is left
+// to the serial gzread path, which treats it the way the reference's reader does)
+bool bgzf_index(const char *path, BgzfIndex &ix)
+{
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 28) { close(fd); return false; }
+    const size_t n = (size_t)st.st_size;
+    void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return false;
+    ix.map = (const unsigned char *)m; ix.map_len = n;
+    const unsigned char *b = ix.map;
+    auto le16 = [&](size_t o) { return (size_t)b[o] | (size_t)b[o + 1] << 8; };
+    auto le32 = [&](size_t o) { return (uint32_t)b[o] | (uint32_t)b[o + 1] << 8 | (uint32_t)b[o + 2] << 16 | (uint32_t)b[o + 3] << 24; };
+    size_t o = 0, out = 0;
+    while (o < n) {
+        if (n - o < 28 || b[o] != 0x1f || b[o + 1] != 0x8b || b[o + 2] != 8 || b[o + 3] != 4) return false;   // FLG: FEXTRA and nothing else
+        const size_t xlen = le16(o + 10);
+        if (o + 12 + xlen + 8 > n) return false;
+        size_t bsize = 0;
+        for (size_t f = o + 12; f + 4 <= o + 12 + xlen;) {
+            const size_t slen = le16(f + 2);
+            if (b[f] == 'B' && b[f + 1] == 'C' && slen == 2 && f + 6 <= o + 12 + xlen) bsize = le16(f + 4) + 1;
+            f += 4 + slen;
+        }
+        if (!bsize || bsize < 12 + xlen + 8 || o + bsize > n) return false;
+        BgzfIndex::Block k;
+        k.in_off = o + 12 + xlen; k.in_len = bsize - 12 - xlen - 8;
+        k.crc = le32(o + bsize - 8); k.out_len = le32(o + bsize - 4); k.out_off = out;
+        ix.blocks.push_back(k);
+        out += k.out_len; o += bsize;
+    }
+    ix.total = out;
+    return true;
+}
+
+// Inflated text that becomes available while it is being parsed.  Plain gzip: a reader thread inflates (one deflate stream cannot be
+// split) into a buffer of fixed capacity — the size the gzip trailer promises — and the parser, written against `more()` /
+// `line_end()` instead of a fixed end pointer, follows right behind it; if the trailer lied (multi-member or > 4 GB streams) the
+// buffer overflows, `overflow` is set and the caller falls back to slurp().  BGZF: up to 16 threads inflate the members in file
+// order, each to its final place, and the text is released to the parser as the finished prefix grows.
 struct TextStream {
-    std::vector<char> buf;
+    std::string owned;                                                   // complete text handed in by the caller
+    char *base = nullptr; size_t cap = 0; bool heap = false;
     std::atomic<size_t> avail{0};
     std::atomic<bool> done{false};
     bool failed = false, overflow = false;
     std::mutex mu; std::condition_variable cv;
     std::thread th;
+    BgzfIndex bz; std::vector<std::thread> workers; std::vector<uint8_t> block_done; size_t frontier = 0; std::atomic<size_t> next_block{0};
+    std::atomic<bool> stop{false};
 
-    explicit TextStream(std::string &&whole) : buf(whole.begin(), whole.end()) { avail = buf.size(); done = true; }   // complete text: nothing to wait for
-    TextStream(const char *path, size_t capacity) : buf(capacity)
+    void alloc(size_t n)
     {
+        cap = n; heap = true;
+        // no zero fill (every byte is written before it is released); big buffers on huge pages: one fault per 2 MB instead of per 4 KB
+        void *q = nullptr;
+        if (n >= ((size_t)4 << 20) && !getenv("PHI_HOST_NO_THP") && posix_memalign(&q, (size_t)2 << 20, n) == 0) { base = (char *)q; madvise(q, n, MADV_HUGEPAGE); }
+        else base = (char *)malloc(n ? n : 1);
+    }
+    explicit TextStream(std::string &&whole) : owned(std::move(whole)) { base = &owned[0]; cap = owned.size(); avail = cap; done = true; }   // nothing to wait for
+    TextStream(const char *path, size_t capacity)
+    {
+        alloc(capacity);
+        if (!base) { failed = true; done = true; return; }
         th = std::thread([this, path]() {
             gzFile fp = gzopen(path, "rb");
             if (!fp) { failed = true; finish(); return; }
             gzbuffer(fp, 1 << 20);
             size_t have = 0;
             for (;;) {
-                if (have == buf.size()) {                               // more text than promised?
+                if (have == cap) {                                      // more text than promised?
                     char probe;
                     if (gzread(fp, &probe, 1) > 0) overflow = true;
                     break;
                 }
-                const int n = gzread(fp, buf.data() + have, (unsigned)std::min<size_t>(buf.size() - have, (size_t)4 << 20));
+                const int n = gzread(fp, base + have, (unsigned)std::min<size_t>(cap - have, (size_t)4 << 20));
                 if (n < 0) { failed = true; break; }
                 if (n == 0) break;
                 have += (size_t)n;
@@ -123,13 +195,54 @@ struct TextStream {
             finish();
         });
     }
-    ~TextStream() { if (th.joinable()) th.join(); }
+    explicit TextStream(BgzfIndex &&index) : bz(std::move(index))
+    {
+        alloc(bz.total);
+        if (!base) { failed = true; done = true; return; }
+        const size_t nb = bz.blocks.size();
+        block_done.assign(nb, 0);
+        if (!nb) { done = true; return; }
+        unsigned T = (unsigned)std::min<size_t>(std::min<size_t>(nb, 16), std::max(1u, std::thread::hardware_concurrency()));
+        if (const char *e = getenv("PHI_HOST_INFLATE_THREADS")) T = (unsigned)std::max(1, std::min(64, atoi(e)));
+        for (unsigned t = 0; t < T; ++t) workers.emplace_back([this, nb]() {
+            z_stream zs; memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) { fail_block(); return; }
+            for (;;) {
+                const size_t i = next_block.fetch_add(1);
+                if (i >= nb || stop.load(std::memory_order_relaxed)) break;
+                const BgzfIndex::Block &k = bz.blocks[i];
+                bool ok = inflateReset(&zs) == Z_OK;
+                if (ok) {
+                    zs.next_in = const_cast<Bytef *>(bz.map + k.in_off); zs.avail_in = (uInt)k.in_len;
+                    zs.next_out = (Bytef *)(base + k.out_off); zs.avail_out = k.out_len;
+                    const int rc = inflate(&zs, Z_FINISH);
+                    ok = rc == Z_STREAM_END && zs.avail_out == 0 && zs.avail_in == 0 &&
+                         (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)(base + k.out_off), k.out_len) == k.crc;
+                }
+                if (!ok) { fail_block(); break; }
+                bool fin = false;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    block_done[i] = 1;
+                    while (frontier < nb && block_done[frontier]) ++frontier;
+                    avail = frontier < nb ? bz.blocks[frontier].out_off : bz.total;
+                    if (frontier == nb) { done = true; fin = true; }
+                }
+                cv.notify_all();
+                if (fin) break;
+            }
+            inflateEnd(&zs);
+        });
+    }
+    void fail_block() { stop = true; { std::lock_guard<std::mutex> lk(mu); failed = true; done = true; } cv.notify_all(); }
+    void join() { if (th.joinable()) th.join(); for (std::thread &w : workers) if (w.joinable()) w.join(); }
+    ~TextStream() { join(); if (heap) free(base); }
     void finish() { { std::lock_guard<std::mutex> lk(mu); done = true; } cv.notify_one(); }
-    const char *begin() const { return buf.data(); }
+    const char *begin() const { return base; }
     // is there a byte at p?  (waits for the reader when p is at the current end)
     bool more(const char *p)
     {
-        const size_t off = (size_t)(p - buf.data());
+        const size_t off = (size_t)(p - base);
         if (off < avail.load(std::memory_order_acquire)) return true;
         std::unique_lock<std::mutex> lk(mu);
         cv.wait(lk, [&]() { return off < avail.load() || done.load(); });
@@ -138,21 +251,21 @@ struct TextStream {
     // the '\n' that ends the line s lies in, or the end of the text
     const char *line_end(const char *s)
     {
-        size_t searched = (size_t)(s - buf.data());                      // no '\n' in [s, searched)
+        size_t searched = (size_t)(s - base);                            // no '\n' in [s, searched)
         for (;;) {
             const bool fin = done.load(std::memory_order_acquire);       // (read before avail: once done is seen, avail is final)
             const size_t a = avail.load(std::memory_order_acquire);
             if (searched < a) {
-                const char *nl = (const char *)memchr(buf.data() + searched, '\n', a - searched);
+                const char *nl = (const char *)memchr(base + searched, '\n', a - searched);
                 if (nl) return nl;
                 searched = a;
             }
-            if (fin) return buf.data() + a;
+            if (fin) return base + a;
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&]() { return avail.load() > a || done.load(); });
         }
     }
-    const char *end_now() { return buf.data() + avail.load(std::memory_order_acquire); }
+    const char *end_now() { return base + avail.load(std::memory_order_acquire); }
 };
 
 // capacity for a TextStream: what slurp() uses as its size hint, exact for single-member gzip files below 4 GB and for plain files
@@ -355,12 +468,22 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
         p = next_line;
     }
     };
-    const size_t hint = text_size_hint(gfa_path);
     bool scanned = false;
+    {
+        BgzfIndex bz;
+        if (bgzf_index(gfa_path, bz)) {                                         // bgzip: members inflated in parallel, scanned as they land
+            text.reset(new TextStream(std::move(bz)));
+            scan(*text);
+            text->join();
+            scanned = !text->failed;
+            pt.lap(scanned ? "inflate (bgzf) || scan" : "bgzf scan (discarded)");
+        }
+    }
+    const size_t hint = scanned ? 0 : text_size_hint(gfa_path);
     if (hint) {
         text.reset(new TextStream(gfa_path, hint));
         scan(*text);
-        if (text->th.joinable()) text->th.join();
+        text->join();
         if (text->failed && text->avail.load() == 0 && !text->overflow) { delete G; set_err(err, errlen, std::string("cannot open ") + gfa_path); return PHI_ERR_ARG; }
         scanned = !text->failed && !text->overflow;
         pt.lap(scanned ? "inflate || scan lines" : "streamed scan (discarded)");
@@ -542,12 +665,24 @@ extern "C" int phi_host_reads_load(const char *path, phi_host_reads **out, char 
     PhaseTimer pt;
     phi_host_reads *R = new phi_host_reads();
     bool parsed = false;
-    const size_t hint = text_size_hint(path);
+    {
+        BgzfIndex bz;
+        if (bgzf_index(path, bz)) {                                             // bgzip: members inflated in parallel, parsed as they land
+            TextStream T(std::move(bz));
+            R->read_bases.reserve(T.cap / 2 + 1024);
+            parse_reads(T, R);
+            T.join();
+            parsed = !T.failed;
+            pt.lap(parsed ? "inflate (bgzf) || parse" : "bgzf pass (discarded)");
+            if (!parsed) { delete R; R = new phi_host_reads(); }
+        }
+    }
+    const size_t hint = parsed ? 0 : text_size_hint(path);
     if (hint) {                                                                 // streamed: the parser runs while the reader thread inflates
         TextStream T(path, hint);
         R->read_bases.reserve(hint / 2 + 1024);
         parse_reads(T, R);
-        if (T.th.joinable()) T.th.join();
+        T.join();
         if (T.failed && T.avail.load() == 0 && !T.overflow) { delete R; set_err(err, errlen, std::string("cannot open ") + path); return PHI_ERR_ARG; }
         parsed = !T.failed && !T.overflow;
         pt.lap(parsed ? "inflate || parse" : "streamed pass (discarded)");

@@ -366,3 +366,78 @@ def test_truncated_gzip_yields_what_could_be_inflated(tmp_path, cut):
             f.write("S\ta\tACGT\n")
         d = probe(gfa, path, str(tmp_path / "p.phiarr"))
         assert rd.read_off.tolist() == d["read_off"].tolist() and bytes(rd.read_bases) == bytes(d["read_bases"])
+
+
+def bgzf_bytes(data, block=65280, level=6, eof=True):
+    """bgzip's container: independent gzip members of <= 64 KB of text, each header carrying the member's size in a 'BC' extra subfield."""
+    import struct
+    import zlib
+    out = bytearray()
+
+    def member(chunk):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        d = c.compress(chunk) + c.flush()
+        out.extend(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(d) + 25) + d
+                   + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+    for i in range(0, len(data), block):
+        member(data[i:i + block])
+    if eof:
+        member(b"")
+    return bytes(out)
+
+
+@pytest.mark.parametrize("threads,block,eof", [(1, 65280, True), (5, 4096, True), (16, 700, False)])
+def test_bgzf_files_are_inflated_in_parallel_to_the_same_text(tmp_path, monkeypatch, threads, block, eof):
+    """bgzip-compressed GFA and FASTQ (the reference's own MHC_4.gfa.gz is one): the members are inflated by several threads while the
+    parser follows the finished prefix — the outcome is the plain file's."""
+    monkeypatch.setenv("PHI_HOST_INFLATE_THREADS", str(threads))
+    c = Case("synth_small")
+    gfa, fq = str(tmp_path / "g.gfa"), str(tmp_path / "r.fq")
+    synth.write_gfa(c.graph, gfa)
+    ro = c.reads.read_off.astype(np.int64)
+    with open(fq, "wb") as f:
+        for i in range(c.reads.n_reads):
+            s = bytes(c.reads.read_bases[ro[i]:ro[i + 1]])
+            f.write(b"@r%d some comment\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    for path in (gfa, fq):
+        with open(path + ".gz", "wb") as f:
+            f.write(bgzf_bytes(open(path, "rb").read(), block, 6, eof))
+        assert gzip.decompress(open(path + ".gz", "rb").read()) == open(path, "rb").read()
+    a, b = phi_b200.load_gfa(gfa), phi_b200.load_gfa(gfa + ".gz")
+    for fld in ("seg_off", "seg_bases", "walk_off", "walk_vtx", "top_order_map"):
+        assert np.array_equal(getattr(a, fld), getattr(b, fld)), fld
+    assert a.walk_names == b.walk_names and a.segment_names == b.segment_names
+    (ra, na), (rb, nb) = phi_b200.load_reads(fq), phi_b200.load_reads(fq + ".gz")
+    assert np.array_equal(ra.read_off, rb.read_off) and np.array_equal(ra.read_bases, rb.read_bases) and na == nb
+    assert np.array_equal(ra.read_bases, c.reads.read_bases)
+
+
+def test_bgzf_look_alikes_take_the_serial_path(tmp_path):
+    """Whatever is not a well-formed chain of BGZF members from the first to the last byte is read the way gzread reads it: a
+    BGZF chain followed by an ordinary gzip member (concatenation = concatenated text), a member whose checksum is wrong (error,
+    as before), a chain cut inside a member (what inflates is used)."""
+    body = b"".join(b">r%d\n%s\n" % (i, b"ACGT" * 30) for i in range(3000))
+    good = bgzf_bytes(body, 5000)
+    mixed = str(tmp_path / "mixed.fa.gz")
+    with open(mixed, "wb") as f:
+        f.write(bgzf_bytes(body, 5000, eof=False) + gzip.compress(b">last\nGGGG\n"))
+    rd, names = phi_b200.load_reads(mixed)
+    assert rd.n_reads == 3001 and names[-1] == "last" and bytes(rd.read_bases[-4:]) == b"GGGG"
+    bad = bytearray(good)
+    bad[len(good) // 2] ^= 0x55                                              # somewhere inside a member's deflate data
+    broken = str(tmp_path / "broken.fa.gz")
+    with open(broken, "wb") as f:
+        f.write(bytes(bad))
+    with pytest.raises(phi_b200.PhiGpuError):
+        phi_b200.load_reads(broken)
+    cut = str(tmp_path / "cut.fa.gz")
+    with open(cut, "wb") as f:
+        f.write(good[:len(good) // 2])
+    rd, names = phi_b200.load_reads(cut)
+    assert 0 < rd.n_reads < 3000 and np.all(np.diff(rd.read_off.astype(np.int64))[:-1] == 120)
+    if os.path.exists(PROBE):                                                # ... exactly what kseq over gzread makes of the cut file
+        gfa = str(tmp_path / "g.gfa")
+        with open(gfa, "w") as f:
+            f.write("S\ta\tACGT\n")
+        d = probe(gfa, cut, str(tmp_path / "p.phiarr"))
+        assert rd.read_off.tolist() == d["read_off"].tolist() and bytes(rd.read_bases) == bytes(d["read_bases"])
