@@ -517,7 +517,11 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
     pt.lap("segment names");
     const uint32_t V = (uint32_t)seqs.size();
     // ---- walk flip (gfa-io.cpp:64-115)
-    {
+    // (no step of any walk is spelled '<' in the graphs pangenome builders write: then every segment's first orientation is forward,
+    // nothing is against it and nothing flips — found out per walk in parallel, and the two serial passes below are skipped)
+    std::vector<uint8_t> has_rev(walks.size(), 0);
+    parallel_for(walks.size(), [&](size_t h) { uint32_t any = 0; for (uint32_t v : walks[h].v) any |= v; has_rev[h] = (uint8_t)(any & 1); });
+    if (std::any_of(has_rev.begin(), has_rev.end(), [](uint8_t x) { return x != 0; })) {
         std::vector<int8_t> strand(V, 0);
         for (auto &wk : walks) for (uint32_t v : wk.v) if (!strand[v >> 1]) strand[v >> 1] = (v & 1) ? -1 : 1;
         for (auto &wk : walks) {
@@ -577,14 +581,20 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
         // walk steps that no L-line backs: where there are none (the rule for real graphs) the order of an anchor's vertices is walk
         // order under ANY valid topological order, so the Kahn tie-breaks above cannot show; where there are some, the reference's own
         // tie-breaks (gfatools' arc sort) would decide the order of those two vertices inside an anchor, and ours may differ
-        G->n_unlinked_steps = 0;
-        for (size_t h = 0; h + 1 < G->walk_off.size(); ++h)
+        const size_t NWALK = G->walk_off.size() - 1;
+        std::vector<uint64_t> unlinked(NWALK, 0);
+        parallel_for(NWALK, [&](size_t h) {
+            uint64_t n = 0;
             for (uint64_t s = G->walk_off[h]; s + 1 < G->walk_off[h + 1]; ++s) {
                 const uint32_t a = G->walk_vtx[s], b = G->walk_vtx[s + 1] << 1;
                 bool linked = false;
                 for (uint32_t x : adj[a]) linked |= x == b;
-                G->n_unlinked_steps += linked ? 0 : 1;
+                n += linked ? 0 : 1;
             }
+            unlinked[h] = n;
+        });
+        G->n_unlinked_steps = 0;
+        for (uint64_t n : unlinked) G->n_unlinked_steps += n;
     }
     pt.lap("adjacency + Kahn order");
     G->view.n_vtx = V; G->view.seg_off = G->seg_off.data(); G->view.seg_bases = (const uint8_t *)G->seg_bases.data();
