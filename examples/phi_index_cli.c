@@ -6,10 +6,11 @@
  *
  * -o writes the result in the "PHIRES3" layout integration/phi_adapter_testhook.hpp reads (header of seven u64, then the arrays
  * of phi_index_result in declaration order, each padded to 8 bytes).  Plain C99: the same calls work from cgo / JNI / ctypes.
- * Build: gcc -std=c99 -O2 -Iinclude examples/phi_index_cli.c -o phi_index_cli -Lphi_b200 -lphi_gpu_index -Wl,-rpath,$PWD/phi_b200
+ * Build: gcc -std=c99 -O2 -pthread -Iinclude examples/phi_index_cli.c -o phi_index_cli -Lphi_b200 -lphi_gpu_index -Wl,-rpath,$PWD/phi_b200
  */
 #include "phi_gpu_index.h"
 
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -20,6 +21,18 @@ static void put(FILE *f, const void *p, size_t bytes)
     if (bytes) fwrite(p, 1, bytes, f);
     if (bytes & 7) fwrite(zero, 1, 8 - (bytes & 7), f);
 }
+
+struct ctx_job { phi_gpu_index_ctx *ctx; int rc; char err[512]; };
+static void *create_ctx(void *p)
+{
+    struct ctx_job *j = (struct ctx_job *)p;
+    j->rc = phi_gpu_index_create(-1, &j->ctx);
+    /* without a ctx the library keeps the message per thread: fetch it on the thread that made the call */
+    if (j->rc != PHI_OK) { strncpy(j->err, phi_gpu_last_error(NULL), sizeof j->err - 1); j->err[sizeof j->err - 1] = 0; }
+    return NULL;
+}
+struct reads_job { const char *path; phi_host_reads *hr; int rc; char err[512]; };
+static void *load_reads(void *p) { struct reads_job *j = (struct reads_job *)p; j->rc = phi_host_reads_load(j->path, &j->hr, j->err, sizeof j->err); return NULL; }
 
 int main(int argc, char **argv)
 {
@@ -37,17 +50,32 @@ int main(int argc, char **argv)
     }
     if (!gfa || !reads) { fprintf(stderr, "usage: phi_index_cli -g graph.gfa -r reads.fq [-k 31] [-w 25] [-T 1.0] [-d 0] [-o result.bin]\n"); return 1; }
 
+    /* three things that do not depend on each other run side by side: the CUDA context (a few hundred ms in a fresh process), the
+     * read file and — on this thread — the graph file */
+    struct ctx_job cj; cj.ctx = NULL; cj.rc = PHI_OK; cj.err[0] = 0;
+    struct reads_job rj; rj.path = reads; rj.hr = NULL; rj.rc = PHI_OK; rj.err[0] = 0;
+    pthread_t t_ctx, t_reads;
+    const int have_ctx_thread = pthread_create(&t_ctx, NULL, create_ctx, &cj) == 0;
+    const int have_reads_thread = pthread_create(&t_reads, NULL, load_reads, &rj) == 0;
     char err[512];
-    phi_host_graph *hg = NULL; phi_host_reads *hr = NULL;
-    if (phi_host_graph_load(gfa, &hg, err, sizeof err) != PHI_OK) { fprintf(stderr, "Error: %s\n", err); return 1; }
-    if (phi_host_reads_load(reads, &hr, err, sizeof err) != PHI_OK) { fprintf(stderr, "Error: %s\n", err); return 1; }
+    phi_host_graph *hg = NULL;
+    const int grc = phi_host_graph_load(gfa, &hg, err, sizeof err);
+    if (have_reads_thread) pthread_join(t_reads, NULL); else load_reads(&rj);
+    if (grc != PHI_OK || rj.rc != PHI_OK) {
+        fprintf(stderr, "Error: %s\n", grc != PHI_OK ? err : rj.err);
+        if (have_ctx_thread) pthread_join(t_ctx, NULL);
+        return 1;
+    }
+    phi_host_reads *hr = rj.hr;
     const phi_graph_view *g = phi_host_graph_view(hg);
     const phi_reads_view *rd = phi_host_reads_view(hr);
     fprintf(stderr, "Graph has %u vertices, %u walks and read has %llu reads\n", g->n_vtx, g->n_walks, (unsigned long long)rd->n_reads);
 
-    phi_gpu_index_ctx *ctx = NULL; phi_index_result *res = NULL;
-    int rc = phi_gpu_index_create(-1, &ctx);
-    if (rc == PHI_OK) rc = phi_gpu_index_run(ctx, g, rd, &prm, &res);
+    if (have_ctx_thread) pthread_join(t_ctx, NULL); else create_ctx(&cj);
+    phi_gpu_index_ctx *ctx = cj.ctx; phi_index_result *res = NULL;
+    int rc = cj.rc;
+    if (rc != PHI_OK) { fprintf(stderr, "Error: GPU ILP_index front end failed (%d): %s\n", rc, cj.err); return 1; }
+    rc = phi_gpu_index_run(ctx, g, rd, &prm, &res);
     if (rc != PHI_OK) { fprintf(stderr, "Error: GPU ILP_index front end failed (%d): %s\n", rc, phi_gpu_last_error(ctx)); return 1; }
 
     fprintf(stderr, "Number of Minimizers\n");

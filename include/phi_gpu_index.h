@@ -158,7 +158,8 @@ typedef struct phi_gpu_index_ctx phi_gpu_index_ctx;
 /* device < 0 selects the current device.  Fails (PHI_ERR_CUDA) without a GPU. */
 int phi_gpu_index_create(int device, phi_gpu_index_ctx **out);
 void phi_gpu_index_destroy(phi_gpu_index_ctx *ctx);
-/* Last error text of this ctx (or of create() when ctx == NULL). Never NULL. */
+/* Last error text of this ctx, or with ctx == NULL of the last failed create / comm_unique_id ON THE CALLING THREAD (the text is
+ * kept per thread: fetch it on the thread that made the call). Never NULL. */
 const char *phi_gpu_last_error(const phi_gpu_index_ctx *ctx);
 int phi_gpu_index_abi_version(void);
 

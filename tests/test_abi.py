@@ -62,7 +62,7 @@ def test_c_example_builds_against_the_header_and_fails_loudly_without_a_gpu(tmp_
     from phi_b200 import synth
     from golden_cases import Case
     exe = str(tmp_path / "phi_index_cli")
-    subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "phi_index_cli.c"),
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-pthread", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "phi_index_cli.c"),
                            "-o", exe, "-L", os.path.join(ROOT, "phi_b200"), "-lphi_gpu_index", "-Wl,-rpath," + os.path.join(ROOT, "phi_b200")])
     c = Case("synth_small")
     gfa, fa = str(tmp_path / "g.gfa"), str(tmp_path / "r.fa")
