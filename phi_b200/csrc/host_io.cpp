@@ -611,14 +611,56 @@ extern "C" uint64_t phi_host_graph_n_links(const phi_host_graph *g) { return g ?
 extern "C" uint64_t phi_host_graph_unlinked_steps(const phi_host_graph *g) { return g ? g->n_unlinked_steps : 0; }
 extern "C" void phi_host_graph_free(phi_host_graph *g) { delete g; }
 
-// kseq_read over a TextStream (kseq.h:192-232): the parser never looks past what the reader thread has delivered
-static void parse_reads(TextStream &T, phi_host_reads *R)
+// An uncompressed file, mapped (false: not there, empty, or it starts with the gzip magic).
+struct PlainFile {
+    const unsigned char *map = nullptr; size_t len = 0;
+    bool open(const char *path)
+    {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size <= 0) { close(fd); return false; }
+        void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        close(fd);
+        if (m == MAP_FAILED) return false;
+        map = (const unsigned char *)m; len = (size_t)st.st_size;
+        if (len >= 2 && map[0] == 0x1f && map[1] == 0x8b) { munmap(m, len); map = nullptr; len = 0; return false; }
+        return true;
+    }
+    ~PlainFile() { if (map) munmap((void *)map, len); }
+};
+
+// A complete text in memory behind the interface the record parser is written against (TextStream: text that is still arriving).
+struct FixedText {
+    const char *b, *e;
+    const char *begin() const { return b; }
+    bool more(const char *p) const { return p < e; }
+    const char *line_end(const char *s) const { const char *nl = (const char *)memchr(s, '\n', (size_t)(e - s)); return nl ? nl : e; }
+};
+
+// What a parse produces; phi_host_reads holds one, the parallel parse one per chunk of the text.
+struct ReadSink {
+    std::vector<uint64_t> read_off;      // cumulative bases, starts with 0
+    std::string read_bases, name_arena;
+    std::vector<uint64_t> name_off;
+};
+
+// kseq_read in a loop (kseq.h:192-232) over a text that may still be arriving: the parser never looks past what `more` grants.
+// The loop's state between two records is a position and `last_char` (0, or the header byte '>' / '@' that the sequence loop of the
+// previous record already consumed).  A parse can start in the middle of the text from such a state (hp: the header byte of its
+// first record; NULL: at `from`, looking for one) and stops BEFORE the first record whose header byte lies at or behind `limit`
+// (NULL: no limit), returning that header byte's position — NULL when the text, or a malformed record (-2: the reference's loop
+// ends there), ended the parse.
+template <class Text>
+static const char *parse_reads_range(Text &T, const char *from, const char *hp, const char *limit, ReadSink *R, bool *malformed)
 {
-    R->read_off.assign(1, 0);
-    const char *p = T.begin();
-    int last_char = 0;
+    if (R->read_off.empty()) R->read_off.assign(1, 0);
+    const char *p = hp ? hp + 1 : from;
+    int last_char = hp ? (unsigned char)*hp : 0;
+    if (malformed) *malformed = false;
     for (;;) {
         if (!last_char) { while (T.more(p) && *p != '>' && *p != '@') ++p; if (!T.more(p)) break; last_char = *p++; }
+        if (limit && p - 1 >= limit) return p - 1;
         if (!T.more(p)) break;                                                  // header char at the very end: ks_getuntil returns -1
         const char *q = p;
         while (T.more(q) && !isspace((unsigned char)*q)) ++q;                   // name
@@ -662,10 +704,90 @@ static void parse_reads(TextStream &T, phi_host_reads *R)
                 if (ql != seq_len) keep = false;                                // -2: truncated quality: the reference stops here
             }
         }
-        if (!keep) { R->read_bases.resize(seq_at); R->name_arena.resize(name_at); break; }
+        if (!keep) { R->read_bases.resize(seq_at); R->name_arena.resize(name_at); if (malformed) *malformed = true; break; }
         R->name_off.push_back(name_at);
         R->read_off.push_back(R->read_bases.size());
     }
+    return nullptr;
+}
+
+static void sink_to_reads(ReadSink &S, phi_host_reads *R)
+{
+    R->read_off.swap(S.read_off); R->read_bases.swap(S.read_bases); R->name_arena.swap(S.name_arena); R->name_off.swap(S.name_off);
+    if (R->read_off.empty()) R->read_off.assign(1, 0);
+}
+
+static void parse_reads(TextStream &T, phi_host_reads *R)
+{
+    ReadSink S;
+    S.read_bases.swap(R->read_bases);                                           // (keeps the caller's reserve)
+    parse_reads_range(T, T.begin(), nullptr, nullptr, &S, nullptr);
+    sink_to_reads(S, R);
+}
+
+// The same over a complete text, cut into chunks that are parsed side by side.  Where a record starts cannot be told from the
+// middle of a FASTQ file (quality lines may begin with '@' or '>'), so every chunk GUESSES its first header — a line that begins
+// with '>' , or with '@' when the line after next begins with '+' — and parses from there; afterwards the chain is checked: the
+// parse of chunk i-1 must have stopped exactly at the header chunk i started from, in which case the two states are identical and
+// the concatenation is what the serial loop produces.  The first link that does not hold (a wrong guess; a malformed record, after
+// which the reference reads nothing) ends the chain, and the rest of the text is parsed serially from the true state.
+static void parse_reads_parallel(const char *b, const char *e, phi_host_reads *R)
+{
+    FixedText T = {b, e};
+    size_t chunk = 0;
+    if (const char *env = getenv("PHI_HOST_PARSE_CHUNK")) chunk = (size_t)strtoull(env, nullptr, 10);    // tests: chunk borders everywhere
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (!chunk) chunk = std::max<size_t>((size_t)(e - b) / (hw * 4) + 1, (size_t)1 << 20);
+    std::vector<const char *> starts;                                           // starts[0] = b (no guess), then one guessed header per chunk that has one
+    starts.push_back(b);
+    for (const char *c = b + chunk; c < e; c += chunk) {
+        const char *lim = c + chunk < e ? c + chunk : e;
+        const char *l = (const char *)memchr(c, '\n', (size_t)(e - c));
+        for (l = l ? l + 1 : e; l < lim; ) {
+            const char *nl = (const char *)memchr(l, '\n', (size_t)(e - l));
+            if (*l == '>') break;
+            if (*l == '@' && nl) {
+                const char *nl2 = (const char *)memchr(nl + 1, '\n', (size_t)(e - nl - 1));
+                if (nl2 && nl2 + 1 < e && nl2[1] == '+') break;
+            }
+            l = nl ? nl + 1 : e;
+        }
+        if (l < lim && l > starts.back()) starts.push_back(l);
+    }
+    const size_t n = starts.size();
+    if (n == 1) { ReadSink S; parse_reads_range(T, b, nullptr, nullptr, &S, nullptr); sink_to_reads(S, R); return; }
+    std::vector<ReadSink> part(n);
+    std::vector<const char *> stop(n, nullptr);
+    parallel_for(n, [&](size_t i) {
+        part[i].read_bases.reserve((size_t)((i + 1 < n ? starts[i + 1] : e) - starts[i]) / 2 + 64);
+        stop[i] = parse_reads_range(T, starts[i], i ? starts[i] : nullptr, i + 1 < n ? starts[i + 1] : nullptr, &part[i], nullptr);
+    });
+    size_t good = 1;                                                            // parts [0, good) are what the serial loop produces
+    while (good < n && stop[good - 1] == starts[good]) ++good;
+    ReadSink tail;
+    if (good < n && stop[good - 1]) parse_reads_range(T, nullptr, stop[good - 1], nullptr, &tail, nullptr);   // the true state, serially to the end
+    // (stop == NULL: the text or a malformed record ended the serial loop inside part good-1: nothing follows)
+    std::vector<ReadSink *> seq;
+    for (size_t i = 0; i < good; ++i) seq.push_back(&part[i]);
+    if (good < n) seq.push_back(&tail);
+    std::vector<uint64_t> base_at(seq.size() + 1, 0), name_at(seq.size() + 1, 0), read_at(seq.size() + 1, 0);
+    for (size_t i = 0; i < seq.size(); ++i) {
+        if (seq[i]->read_off.empty()) seq[i]->read_off.assign(1, 0);
+        base_at[i + 1] = base_at[i] + seq[i]->read_bases.size(); name_at[i + 1] = name_at[i] + seq[i]->name_arena.size();
+        read_at[i + 1] = read_at[i] + (seq[i]->read_off.size() - 1);
+    }
+    R->read_bases.resize(base_at.back()); R->name_arena.resize(name_at.back());
+    R->read_off.resize(read_at.back() + 1); R->name_off.resize(read_at.back());
+    R->read_off[0] = 0;
+    parallel_for(seq.size(), [&](size_t i) {
+        const ReadSink &S = *seq[i];
+        if (!S.read_bases.empty()) memcpy(&R->read_bases[base_at[i]], S.read_bases.data(), S.read_bases.size());
+        if (!S.name_arena.empty()) memcpy(&R->name_arena[name_at[i]], S.name_arena.data(), S.name_arena.size());
+        for (size_t r = 0; r + 1 < S.read_off.size(); ++r) {
+            R->read_off[read_at[i] + r + 1] = base_at[i] + S.read_off[r + 1];
+            R->name_off[read_at[i] + r] = name_at[i] + S.name_off[r];
+        }
+    });
 }
 
 extern "C" int phi_host_reads_load(const char *path, phi_host_reads **out, char *err, size_t errlen)
@@ -677,14 +799,28 @@ extern "C" int phi_host_reads_load(const char *path, phi_host_reads **out, char 
     bool parsed = false;
     {
         BgzfIndex bz;
-        if (bgzf_index(path, bz)) {                                             // bgzip: members inflated in parallel, parsed as they land
+        if (bgzf_index(path, bz)) {                                             // bgzip: members inflated in parallel ...
             TextStream T(std::move(bz));
-            R->read_bases.reserve(T.cap / 2 + 1024);
-            parse_reads(T, R);
-            T.join();
+            if (T.cap >= ((size_t)8 << 20) || getenv("PHI_HOST_PARSE_CHUNK")) {   // ... then parsed in parallel chunks,
+                T.join();
+                pt.lap("inflate (bgzf)");
+                if (!T.failed) { parse_reads_parallel(T.base, T.base + T.cap, R); pt.lap("parse (parallel chunks)"); }
+            } else {                                                            // or, small files, parsed as they land
+                R->read_bases.reserve(T.cap / 2 + 1024);
+                parse_reads(T, R);
+                T.join();
+                pt.lap("inflate (bgzf) || parse");
+            }
             parsed = !T.failed;
-            pt.lap(parsed ? "inflate (bgzf) || parse" : "bgzf pass (discarded)");
             if (!parsed) { delete R; R = new phi_host_reads(); }
+        }
+    }
+    if (!parsed) {                                                              // not compressed: the file itself is the text
+        PlainFile pf;
+        if (pf.open(path)) {
+            parse_reads_parallel((const char *)pf.map, (const char *)pf.map + pf.len, R);
+            parsed = true;
+            pt.lap("parse (mapped file, parallel chunks)");
         }
     }
     const size_t hint = parsed ? 0 : text_size_hint(path);

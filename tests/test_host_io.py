@@ -441,3 +441,52 @@ def test_bgzf_look_alikes_take_the_serial_path(tmp_path):
             f.write("S\ta\tACGT\n")
         d = probe(gfa, cut, str(tmp_path / "p.phiarr"))
         assert rd.read_off.tolist() == d["read_off"].tolist() and bytes(rd.read_bases) == bytes(d["read_bases"])
+
+
+@pytest.mark.parametrize("chunk", [1, 5, 33, 257, 4096])
+def test_reads_parsed_in_parallel_chunks_equal_the_serial_parse(tmp_path, monkeypatch, chunk):
+    """Big uncompressed / bgzip read files are cut into chunks that guess their first header and are parsed side by side; the chain
+    of guesses is checked afterwards and whatever does not fit is parsed again serially.  PHI_HOST_PARSE_CHUNK puts chunk borders
+    everywhere in small files: every edge case of this file, plus FASTQ whose quality lines begin with '@', '>' and '+', multi-line
+    FASTQ and a malformed record in the middle, must come out as the serial loop (= kseq) reads them."""
+    rng = np.random.default_rng(chunk)
+    recs = []
+    for i in range(400):
+        n = int(rng.integers(1, 90))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTNacgt", dtype=np.uint8), n))
+        qual = bytes(rng.choice(np.frombuffer(b"@>+I#5", dtype=np.uint8), n))
+        style = int(rng.integers(0, 4))
+        if style == 0:
+            recs.append(b"@q%d c\n" % i + seq + b"\n+\n" + qual + b"\n")
+        elif style == 1:                                       # two-line sequence and quality
+            h = n // 2
+            recs.append(b"@m%d\n" % i + seq[:h] + b"\n" + seq[h:] + b"\n+m%d\n" % i + qual[:h] + b"\n" + qual[h:] + b"\n")
+        elif style == 2:
+            recs.append(b">f%d\n" % i + seq + b"\n")
+        else:
+            recs.append(b">g%d x y\n" % i + seq[:n // 3] + b"\r\n" + seq[n // 3:] + b"\n\n")
+    corpus = dict(READS_EDGE)
+    corpus = {k: v.encode() for k, v in corpus.items()}
+    corpus.update(MALFORMED_READS)
+    corpus["random.fq"] = b"".join(recs)
+    corpus["random_then_malformed.fq"] = b"".join(recs[:200]) + b"@bad\nACGTACGT\n+\nIII\n" + b"".join(recs[200:])
+    for fname, data in sorted(corpus.items()):
+        path = str(tmp_path / fname)
+        with open(path, "wb") as f:
+            f.write(data)
+        with open(path + ".bgzf.gz", "wb") as f:
+            f.write(bgzf_bytes(data, 300))
+        monkeypatch.delenv("PHI_HOST_PARSE_CHUNK", raising=False)
+        want, want_names = phi_b200.load_reads(path)                            # small file, no chunks: the serial loop
+        monkeypatch.setenv("PHI_HOST_PARSE_CHUNK", str(chunk))
+        for p in (path, path + ".bgzf.gz"):
+            got, names = phi_b200.load_reads(p)
+            assert got.read_off.tolist() == want.read_off.tolist() and bytes(got.read_bases) == bytes(want.read_bases) and names == want_names, (fname, p)
+    if os.path.exists(PROBE):                                                   # and the serial loop is kseq's
+        gfa = str(tmp_path / "g.gfa")
+        with open(gfa, "w") as f:
+            f.write("S\ta\tACGT\n")
+        for fname in ("random.fq", "random_then_malformed.fq"):
+            d = probe(gfa, str(tmp_path / fname), str(tmp_path / "p.phiarr"))
+            got, _ = phi_b200.load_reads(str(tmp_path / fname))
+            assert got.read_off.tolist() == d["read_off"].tolist() and bytes(got.read_bases) == bytes(d["read_bases"]), fname
