@@ -8,12 +8,14 @@
  * of phi_index_result in declaration order, each padded to 8 bytes).  Plain C99: the same calls work from cgo / JNI / ctypes.
  * Build: gcc -std=c99 -O2 -pthread -Iinclude examples/phi_index_cli.c -o phi_index_cli -Lphi_b200 -lphi_gpu_index -Wl,-rpath,$PWD/phi_b200
  */
+#define _POSIX_C_SOURCE 200809L
 #include "phi_gpu_index.h"
 
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 static void put(FILE *f, const void *p, size_t bytes)
 {
@@ -22,17 +24,26 @@ static void put(FILE *f, const void *p, size_t bytes)
     if (bytes & 7) fwrite(zero, 1, 8 - (bytes & 7), f);
 }
 
-struct ctx_job { phi_gpu_index_ctx *ctx; int rc; char err[512]; };
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
+
+struct ctx_job { phi_gpu_index_ctx *ctx; int rc; char err[512]; double t_done; };
 static void *create_ctx(void *p)
 {
     struct ctx_job *j = (struct ctx_job *)p;
     j->rc = phi_gpu_index_create(-1, &j->ctx);
     /* without a ctx the library keeps the message per thread: fetch it on the thread that made the call */
     if (j->rc != PHI_OK) { strncpy(j->err, phi_gpu_last_error(NULL), sizeof j->err - 1); j->err[sizeof j->err - 1] = 0; }
+    j->t_done = now_s();
     return NULL;
 }
-struct reads_job { const char *path; phi_host_reads *hr; int rc; char err[512]; };
-static void *load_reads(void *p) { struct reads_job *j = (struct reads_job *)p; j->rc = phi_host_reads_load(j->path, &j->hr, j->err, sizeof j->err); return NULL; }
+struct reads_job { const char *path; phi_host_reads *hr; int rc; char err[512]; double t_done; };
+static void *load_reads(void *p)
+{
+    struct reads_job *j = (struct reads_job *)p;
+    j->rc = phi_host_reads_load(j->path, &j->hr, j->err, sizeof j->err);
+    j->t_done = now_s();
+    return NULL;
+}
 
 int main(int argc, char **argv)
 {
@@ -52,14 +63,16 @@ int main(int argc, char **argv)
 
     /* three things that do not depend on each other run side by side: the CUDA context (a few hundred ms in a fresh process), the
      * read file and — on this thread — the graph file */
-    struct ctx_job cj; cj.ctx = NULL; cj.rc = PHI_OK; cj.err[0] = 0;
-    struct reads_job rj; rj.path = reads; rj.hr = NULL; rj.rc = PHI_OK; rj.err[0] = 0;
+    const double t0 = now_s();
+    struct ctx_job cj; cj.ctx = NULL; cj.rc = PHI_OK; cj.err[0] = 0; cj.t_done = t0;
+    struct reads_job rj; rj.path = reads; rj.hr = NULL; rj.rc = PHI_OK; rj.err[0] = 0; rj.t_done = t0;
     pthread_t t_ctx, t_reads;
     const int have_ctx_thread = pthread_create(&t_ctx, NULL, create_ctx, &cj) == 0;
     const int have_reads_thread = pthread_create(&t_reads, NULL, load_reads, &rj) == 0;
     char err[512];
     phi_host_graph *hg = NULL;
     const int grc = phi_host_graph_load(gfa, &hg, err, sizeof err);
+    const double t_graph = now_s();
     if (have_reads_thread) pthread_join(t_reads, NULL); else load_reads(&rj);
     if (grc != PHI_OK || rj.rc != PHI_OK) {
         fprintf(stderr, "Error: %s\n", grc != PHI_OK ? err : rj.err);
@@ -75,7 +88,9 @@ int main(int argc, char **argv)
     phi_gpu_index_ctx *ctx = cj.ctx; phi_index_result *res = NULL;
     int rc = cj.rc;
     if (rc != PHI_OK) { fprintf(stderr, "Error: GPU ILP_index front end failed (%d): %s\n", rc, cj.err); return 1; }
+    const double t_ready = now_s();
     rc = phi_gpu_index_run(ctx, g, rd, &prm, &res);
+    const double t_run = now_s();
     if (rc != PHI_OK) { fprintf(stderr, "Error: GPU ILP_index front end failed (%d): %s\n", rc, phi_gpu_last_error(ctx)); return 1; }
 
     fprintf(stderr, "Number of Minimizers\n");
@@ -89,6 +104,10 @@ int main(int argc, char **argv)
     if (phi_gpu_index_last_times(ctx, &t) == PHI_OK)
         fprintf(stderr, "GPU front end: %.3f ms (copies in %.3f ms, out %.3f ms; %llu kernel launches); %llu groups, %llu anchors\n", t.total_ms, t.h2d_ms,
                 t.d2h_ms, (unsigned long long)t.kernel_launches, (unsigned long long)res->n_groups, (unsigned long long)res->n_anchors);
+
+    if (getenv("PHI_CLI_TIMES"))                     /* wall clock from program start: what ran side by side, and what the result waited for */
+        fprintf(stderr, "[phi_index_cli] graph loaded %.3f s, reads loaded %.3f s, CUDA context ready %.3f s | all three ready %.3f s, front end done %.3f s "
+                        "(phi_gpu_index_run %.3f s)\n", t_graph - t0, rj.t_done - t0, cj.t_done - t0, t_ready - t0, t_run - t0, t_run - t_ready);
 
     if (out) {
         FILE *f = fopen(out, "wb");
