@@ -301,11 +301,32 @@ void parallel_for(size_t n, F f)
 
 }  // namespace
 
+// A big array that is written completely before it is read: no zero fill (std::vector::resize would run one serial pass over
+// gigabytes on chromosome-scale inputs), 2 MB aligned and marked for transparent huge pages.
+template <class T> struct RawArray {
+    T *p = nullptr; size_t n = 0;
+    RawArray() = default;
+    RawArray(const RawArray &) = delete; RawArray &operator=(const RawArray &) = delete;
+    ~RawArray() { free(p); }
+    bool alloc(size_t count)
+    {
+        free(p); p = nullptr; n = count;
+        const size_t bytes = std::max<size_t>(count * sizeof(T), 1);
+        void *q = nullptr;
+        if (bytes >= ((size_t)4 << 20) && posix_memalign(&q, (size_t)2 << 20, bytes) == 0) { p = (T *)q; madvise(q, bytes, MADV_HUGEPAGE); }
+        else p = (T *)malloc(bytes);
+        return p != nullptr;
+    }
+    T *data() { return p; } const T *data() const { return p; }
+    size_t size() const { return n; }
+    T &operator[](size_t i) { return p[i]; } const T &operator[](size_t i) const { return p[i]; }
+};
+
 struct phi_host_graph {
     phi_graph_view view;
     std::vector<uint64_t> seg_off, walk_off;
-    std::string seg_bases;
-    std::vector<uint32_t> walk_vtx;
+    RawArray<char> seg_bases;
+    RawArray<uint32_t> walk_vtx;
     std::vector<int32_t> top_order_map;
     uint64_t n_unlinked_steps = 0;
     std::vector<std::string> walk_names, seg_names;
@@ -318,6 +339,10 @@ struct phi_host_reads {
     std::string read_bases;
     std::string name_arena;              // the names back to back, each followed by a NUL
     std::vector<uint64_t> name_off;
+    bool raw = false;                    // the parallel parse stitches its parts into these instead (no zero fill of gigabytes)
+    RawArray<char> bases_raw, names_raw;
+    const char *bases() const { return raw ? bases_raw.data() : read_bases.data(); }
+    const char *names() const { return raw ? names_raw.data() : name_arena.c_str(); }
 };
 
 static void set_err(char *err, size_t errlen, const std::string &m)
@@ -536,14 +561,14 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
     // ---- flat views
     G->seg_off.assign((size_t)V + 1, 0);
     for (uint32_t v = 0; v < V; ++v) G->seg_off[v + 1] = G->seg_off[v] + seqs[v].n;
-    G->seg_bases.resize(G->seg_off[V]);
+    if (!G->seg_bases.alloc(G->seg_off[V])) { set_err(err, errlen, "out of memory"); delete G; return PHI_ERR_NOMEM; }
     for (uint32_t v = 0; v < V; ++v) if (seqs[v].n) memcpy(&G->seg_bases[G->seg_off[v]], seqs[v].p, seqs[v].n);
     G->walk_off.assign(1, 0);
     for (size_t h = 0; h < walks.size(); ++h) {
         G->walk_off.push_back(G->walk_off.back() + walks[h].v.size());
         G->walk_names.push_back(walks[h].sample + "." + std::to_string(walks[h].hap));
     }
-    G->walk_vtx.resize(G->walk_off.back());
+    if (!G->walk_vtx.alloc(G->walk_off.back())) { set_err(err, errlen, "out of memory"); delete G; return PHI_ERR_NOMEM; }
     std::vector<int64_t> bad(walks.size(), -1);                                // first reverse-strand step of every walk
     parallel_for(walks.size(), [&](size_t h) {
         uint32_t *dst = G->walk_vtx.data() + G->walk_off[h];
@@ -776,13 +801,16 @@ static void parse_reads_parallel(const char *b, const char *e, phi_host_reads *R
         base_at[i + 1] = base_at[i] + seq[i]->read_bases.size(); name_at[i + 1] = name_at[i] + seq[i]->name_arena.size();
         read_at[i + 1] = read_at[i] + (seq[i]->read_off.size() - 1);
     }
-    R->read_bases.resize(base_at.back()); R->name_arena.resize(name_at.back());
+    R->raw = R->bases_raw.alloc(base_at.back()) && R->names_raw.alloc(name_at.back() + 1);
+    if (!R->raw) { R->read_bases.resize(base_at.back()); R->name_arena.resize(name_at.back()); }
+    else R->names_raw[name_at.back()] = 0;
+    char *bases_out = R->raw ? R->bases_raw.data() : &R->read_bases[0], *names_out = R->raw ? R->names_raw.data() : &R->name_arena[0];
     R->read_off.resize(read_at.back() + 1); R->name_off.resize(read_at.back());
     R->read_off[0] = 0;
     parallel_for(seq.size(), [&](size_t i) {
         const ReadSink &S = *seq[i];
-        if (!S.read_bases.empty()) memcpy(&R->read_bases[base_at[i]], S.read_bases.data(), S.read_bases.size());
-        if (!S.name_arena.empty()) memcpy(&R->name_arena[name_at[i]], S.name_arena.data(), S.name_arena.size());
+        if (!S.read_bases.empty()) memcpy(bases_out + base_at[i], S.read_bases.data(), S.read_bases.size());
+        if (!S.name_arena.empty()) memcpy(names_out + name_at[i], S.name_arena.data(), S.name_arena.size());
         for (size_t r = 0; r + 1 < S.read_off.size(); ++r) {
             R->read_off[read_at[i] + r + 1] = base_at[i] + S.read_off[r + 1];
             R->name_off[read_at[i] + r] = name_at[i] + S.name_off[r];
@@ -842,11 +870,11 @@ extern "C" int phi_host_reads_load(const char *path, phi_host_reads **out, char 
         parse_reads(T, R);
         pt.lap("parse");
     }
-    R->view.n_reads = R->read_off.size() - 1; R->view.read_off = R->read_off.data(); R->view.read_bases = (const uint8_t *)R->read_bases.data();
+    R->view.n_reads = R->read_off.size() - 1; R->view.read_off = R->read_off.data(); R->view.read_bases = (const uint8_t *)R->bases();
     *out = R;
     return PHI_OK;
 }
 
 extern "C" const phi_reads_view *phi_host_reads_view(const phi_host_reads *r) { return r ? &r->view : nullptr; }
-extern "C" const char *phi_host_reads_name(const phi_host_reads *r, uint64_t i) { return r && i < r->name_off.size() ? r->name_arena.c_str() + r->name_off[i] : ""; }
+extern "C" const char *phi_host_reads_name(const phi_host_reads *r, uint64_t i) { return r && i < r->name_off.size() ? r->names() + r->name_off[i] : ""; }
 extern "C" void phi_host_reads_free(phi_host_reads *r) { delete r; }
