@@ -138,6 +138,15 @@ def synth_case(name, seed, backbone, haps, cov, k=31, w=25, T=1.0, read_len=150,
 
 if __name__ == "__main__":
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    ONLY = set(sys.argv[1:])                                   # `make_golden.py name ...` regenerates the named cases only
+    if ONLY:
+        _make_case, _synth_case = make_case, synth_case
+        make_case = lambda name, *a, **k: _make_case(name, *a, **k) if name in ONLY else None      # noqa: E731
+        synth_case = lambda name, *a, **k: _synth_case(name, *a, **k) if name in ONLY else None    # noqa: E731
+    # k > 32 (round 2: the library's byte-wise compare-and-hash path; the reference's string code takes any k, ILP_index.cpp:390-394)
+    synth_case("synth_k33", 21, 40000, 5, 3.0, k=33, w=25)
+    synth_case("synth_k64_dirty", 22, 40000, 4, 3.0, k=64, w=11, T=0.8, lower_frac=0.02, n_frac=0.0008, r_lower_frac=0.02, r_n_frac=0.0008)
+    synth_case("synth_k101_w9", 23, 50000, 4, 4.0, k=101, w=9, read_len=400, T=0.75)
     make_case("toy_k3_w2", f"{REF}/test.gfa", f"{REF}/read.fa", k=3, w=2)
     make_case("toy_defaults", f"{REF}/test.gfa", f"{REF}/read.fa")                       # all walks < 55 bp: nothing
     synth_case("synth_small", 11, 60000, 5, 3.0)

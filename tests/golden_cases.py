@@ -13,6 +13,9 @@ MHC = ["mhc4", "mhc4_N75", "mhc4_lower"]
 # shapes of BASELINE.json configs[2] (15 kb reads) and configs[3] (200 haplotypes, fractional threshold): they pin the oracle on those
 # shapes against the unmodified reference (the GPU parity tests of the same shapes compare with the oracle)
 SHAPES = ["shape_long_reads_15kb", "shape_200_haplotypes"]
+# k > 32 (the library's byte-wise path, round 2): pins the ORACLE against the unmodified reference for long k-mers, dirty bytes included;
+# the GPU parity tests of k = 33 / 64 / 101 compare with the oracle (tests/test_gpu_parity.py)
+LONG_K = ["synth_k33", "synth_k64_dirty", "synth_k101_w9"]
 
 
 class Case:

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import phi_io
-from golden_cases import Case, SMALL, MHC, SHAPES, check_against_golden
+from golden_cases import Case, SMALL, MHC, SHAPES, LONG_K, check_against_golden
 
 # hash128_to_64 known answers produced by the reference's own MurmurHash3.cpp
 KAT = {b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA": 0xc76d5c1cf7227aee, b"ACGTACGTACGTACGTACGTACGTACGTACG": 0x8f3c55213ed8e5fb,
@@ -17,7 +17,7 @@ def test_murmur_known_answers():
         assert phi_io.oracle_hash(key) == want
 
 
-@pytest.mark.parametrize("name", SMALL + SHAPES + MHC)
+@pytest.mark.parametrize("name", SMALL + SHAPES + LONG_K + MHC)
 def test_oracle_matches_reference(name):
     c = Case(name)
     res = phi_io.oracle_index(c.graph, c.reads, c.k, c.w, c.T)
