@@ -5,6 +5,7 @@
 // of one rank are merged in key order; a group that occurs in several parts (its occurrences were owned by several GPUs) gets
 // the union of the member lists.  Per-walk counters and n_filtered are sums over the parts; the spectrum comes from the part
 // that carries it (rank 0).  With one part this is a copy.
+// Big merges run on several host threads over blocks of hash ranks (count pass, prefix sum, write pass): PHI_MERGE_THREADS.
 #include "result_box.h"
 
 #include <algorithm>
