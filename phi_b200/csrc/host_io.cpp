@@ -584,24 +584,35 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
     pt.lap("walk flip + flat views");
     // ---- adjacency of the forward vertices after symmetrisation, Kahn order (ILP_index.cpp:77-154)
     {
-        std::vector<std::vector<uint32_t>> adj(V);
-        auto add = [&](uint32_t a, uint32_t b) {
-            if (a & 1) return;                                                 // only arcs leaving a forward vertex count
-            auto &l = adj[a >> 1];
-            for (uint32_t x : l) if (x == b) return;                           // multi-arcs are removed by gfa_cleanup
-            l.push_back(b);
+        // CSR over the forward source vertices, a vertex's arcs in L-line order (counting sort by source: stable), multi-arcs removed
+        // (gfa_cleanup) by a scan of the vertex's own short list
+        std::vector<uint64_t> adj_off((size_t)V + 1, 0);
+        auto each_arc = [&](auto &&f) {
+            for (auto &ab : arcs) {
+                if (!(ab.first & 1)) f(ab.first >> 1, ab.second);               // only arcs leaving a forward vertex count
+                if (!((ab.second ^ 1) & 1)) f((ab.second ^ 1) >> 1, ab.first ^ 1);   // the reverse-complement arc of the same L-line
+            }
         };
-        for (auto &ab : arcs) { add(ab.first, ab.second); add(ab.second ^ 1, ab.first ^ 1); }
+        each_arc([&](uint32_t a, uint32_t) { adj_off[a + 1]++; });
+        for (uint32_t v = 0; v < V; ++v) adj_off[v + 1] += adj_off[v];
+        std::vector<uint32_t> adj_to(adj_off[V]);
+        std::vector<uint64_t> adj_end(adj_off.begin(), adj_off.end() - 1);      // v's list is adj_to[adj_off[v] .. adj_end[v])
+        each_arc([&](uint32_t a, uint32_t b) {
+            for (uint64_t i = adj_off[a]; i < adj_end[a]; ++i) if (adj_to[i] == b) return;
+            adj_to[adj_end[a]++] = b;
+        });
+        struct Adj { const std::vector<uint64_t> &b, &e; const std::vector<uint32_t> &to; };
+        const Adj adj = {adj_off, adj_end, adj_to};
         std::vector<int32_t> indeg(V, 0);
-        for (uint32_t v = 0; v < V; ++v) for (uint32_t w : adj[v]) indeg[w >> 1]++;
-        std::queue<uint32_t> q;
-        for (uint32_t v = 0; v < V; ++v) if (!indeg[v]) q.push(v);
+        for (uint32_t v = 0; v < V; ++v) for (uint64_t i = adj.b[v]; i < adj.e[v]; ++i) indeg[adj.to[i] >> 1]++;
+        std::vector<uint32_t> q; q.reserve(V);                                  // FIFO: the order vertices enter is the order they leave
+        for (uint32_t v = 0; v < V; ++v) if (!indeg[v]) q.push_back(v);
         G->top_order_map.assign(V, 0);
         int32_t next = 0;
-        while (!q.empty()) {
-            uint32_t u = q.front(); q.pop();
+        for (size_t head = 0; head < q.size(); ++head) {
+            const uint32_t u = q[head];
             G->top_order_map[u] = next++;
-            for (uint32_t w : adj[u]) if (--indeg[w >> 1] == 0) q.push(w >> 1);
+            for (uint64_t i = adj.b[u]; i < adj.e[u]; ++i) if (--indeg[adj.to[i] >> 1] == 0) q.push_back(adj.to[i] >> 1);
         }
         // walk steps that no L-line backs: where there are none (the rule for real graphs) the order of an anchor's vertices is walk
         // order under ANY valid topological order, so the Kahn tie-breaks above cannot show; where there are some, the reference's own
@@ -613,7 +624,7 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
             for (uint64_t s = G->walk_off[h]; s + 1 < G->walk_off[h + 1]; ++s) {
                 const uint32_t a = G->walk_vtx[s], b = G->walk_vtx[s + 1] << 1;
                 bool linked = false;
-                for (uint32_t x : adj[a]) linked |= x == b;
+                for (uint64_t i = adj.b[a]; i < adj.e[a]; ++i) linked |= adj.to[i] == b;
                 n += linked ? 0 : 1;
             }
             unlinked[h] = n;
