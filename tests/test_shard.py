@@ -186,3 +186,21 @@ def test_bench_generates_the_same_shards_it_would_cut_from_the_whole_input(monke
         reads.append(rd)
     assert sum(r.n_reads for r in reads) == whole_rd.n_reads
     assert np.array_equal(np.concatenate([r.read_bases for r in reads]), whole_rd.read_bases)
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_merge_of_empty_parts(monkeypatch, threads):
+    """No reads (count_sp_r == 0) on every GPU: the merge is a result without ranks whose per-walk counters are still the sums."""
+    monkeypatch.setenv("PHI_MERGE_THREADS", str(threads))
+    z = np.zeros(0)
+
+    def empty(nw):
+        return _abi.IndexResultPy(count_sp_r=0, n_walks=nw, n_filtered=0, spectrum=z.astype(np.uint64), anchor_rank=z.astype(np.int32),
+                                  anchor_walk=z.astype(np.int32), anchor_off=np.zeros(1, dtype=np.uint64), anchor_vtx=z.astype(np.int32),
+                                  minimizers_per_walk=np.arange(nw, dtype=np.uint64), anchors_per_walk=np.zeros(nw, dtype=np.uint64),
+                                  n_groups=0, group_len=z.astype(np.uint8), group_vtx=z.astype(np.int32),
+                                  group_member_off=np.zeros(1, dtype=np.uint32), member_walk=z.astype(np.int32), rank_off=np.zeros(1, dtype=np.uint32))
+    for n_parts in (1, 3):
+        got = multi.merge_results([empty(4) for _ in range(n_parts)])
+        assert got.count_sp_r == 0 and got.n_groups == 0 and got.n_anchors == 0
+        assert got.minimizers_per_walk.tolist() == [0, n_parts, 2 * n_parts, 3 * n_parts]
