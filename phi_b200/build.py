@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libphi_gpu_index.so")
 SOURCES = ["read_sketch.cu", "walk_sketch.cu", "chunks.cu", "primitives.cu", "filter.cu", "groups.cu", "phi_gpu_index.cu", "shard.cu", "host_io.cpp", "merge.cpp"]
-HEADERS = ["kernels.h", "device_common.cuh", "sketch_tile.cuh", "sketch_common.cuh", "result_box.h", os.path.join(ROOT, "include", "phi_gpu_index.h")]
+HEADERS = ["kernels.h", "device_common.cuh", "sketch_tile.cuh", "sketch_common.cuh", "result_box.h", "fast_inflate.h", os.path.join(ROOT, "include", "phi_gpu_index.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xptxas", "-v"]
 

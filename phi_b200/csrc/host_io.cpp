@@ -25,6 +25,7 @@
 //     with one trailing '\r' stripped, FASTQ quality skipped and length-checked; parsing stops at the first malformed
 //     record (kseq returns -2 and read_ip_reads' loop ends)
 #include "../../include/phi_gpu_index.h"
+#include "fast_inflate.h"
 
 #include <zlib.h>
 #include <time.h>
@@ -90,6 +91,18 @@ bool slurp(const char *path, std::string &out, std::string &err)
     gzclose(fp);
     out.resize(have);
     return true;
+}
+
+// f(i) for i in [0, n) on up to 16 host threads (items are handed out one by one: walks differ in length)
+template <class F>
+void parallel_for(size_t n, F f)
+{
+    const unsigned T = (unsigned)std::min<size_t>(std::min<size_t>(n, 16), std::max(1u, std::thread::hardware_concurrency()));
+    if (T <= 1) { for (size_t i = 0; i < n; ++i) f(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t) th.emplace_back([&]() { for (;;) { const size_t i = next.fetch_add(1); if (i >= n) break; f(i); } });
+    for (auto &x : th) x.join();
 }
 
 // A BGZF file (bgzip: what pangenome graphs, VCFs and many read sets are compressed with) is a chain of independent gzip members of
@@ -174,6 +187,8 @@ struct TextStream {
         alloc(capacity);
         if (!base) { failed = true; done = true; return; }
         th = std::thread([this, path]() {
+            if (fast_single_member(path)) { finish(); return; }
+            if (overflow) { finish(); return; }                          // the fast decoder gave up after text had been released: the caller repeats with zlib
             gzFile fp = gzopen(path, "rb");
             if (!fp) { failed = true; finish(); return; }
             gzbuffer(fp, 1 << 20);
@@ -195,6 +210,49 @@ struct TextStream {
             finish();
         });
     }
+    // A file that is exactly ONE gzip member whose trailer promises `cap` bytes: decoded from the mapped file by the whole-buffer
+    // decoder (fast_inflate.h), block by block straight to its final place, then checked against the trailer's CRC-32 (in parallel
+    // pieces).  false + nothing released: not such a file (the zlib loop takes over); false + overflow: it looked like one but the
+    // decoder or the check failed after text had been released — the caller discards what it parsed and lets zlib decide.
+    bool fast_single_member(const char *path)
+    {
+        if (getenv("PHI_HOST_ZLIB_ONLY")) return false;
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 18) { close(fd); return false; }
+        const size_t n = (size_t)st.st_size;
+        void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        close(fd);
+        if (m == MAP_FAILED) return false;
+        const unsigned char *b = (const unsigned char *)m;
+        struct Unmap { void *m; size_t n; ~Unmap() { munmap(m, n); } } unmap = {m, n};
+        (void)unmap;
+        const size_t off = phi_inflate::gzip_header_size(b, n);
+        if (!off) return false;
+        size_t out_len = 0, used = 0;
+        const int rc = phi_inflate::inflate_raw(b + off, n - off - 8, (unsigned char *)base, cap, &out_len, &used, [this](size_t have) {
+            if (have > avail.load(std::memory_order_relaxed)) { { std::lock_guard<std::mutex> lk(mu); avail = have; } cv.notify_one(); }
+        });
+        auto le32 = [&](size_t o) { return (uint32_t)b[o] | (uint32_t)b[o + 1] << 8 | (uint32_t)b[o + 2] << 16 | (uint32_t)b[o + 3] << 24; };
+        bool ok = rc == 0 && off + used + 8 == n && out_len == cap && le32(n - 4) == (uint32_t)out_len;
+        if (ok) {                                                        // CRC-32 of the text in parallel pieces, combined
+            const size_t P = std::max<size_t>(1, std::min<size_t>(16, out_len >> 20));
+            std::vector<uLong> part(P);
+            parallel_for(P, [&](size_t i) {
+                const size_t a = out_len * i / P, z = out_len * (i + 1) / P;
+                uLong c = crc32(0L, Z_NULL, 0);
+                for (size_t p = a; p < z;) { const size_t step = std::min<size_t>(z - p, (size_t)1 << 30); c = crc32(c, (const Bytef *)base + p, (uInt)step); p += step; }
+                part[i] = c;
+            });
+            uLong c = part[0];
+            for (size_t i = 1; i < P; ++i) c = crc32_combine(c, part[i], (z_off_t)(out_len * (i + 1) / P - out_len * i / P));
+            ok = (uint32_t)c == le32(n - 8);
+        }
+        if (!ok) { if (avail.load() > 0) overflow = true; return false; }
+        { std::lock_guard<std::mutex> lk(mu); avail = out_len; }
+        return true;
+    }
     explicit TextStream(BgzfIndex &&index) : bz(std::move(index))
     {
         alloc(bz.total);
@@ -204,15 +262,20 @@ struct TextStream {
         if (!nb) { done = true; return; }
         unsigned T = (unsigned)std::min<size_t>(std::min<size_t>(nb, 16), std::max(1u, std::thread::hardware_concurrency()));
         if (const char *e = getenv("PHI_HOST_INFLATE_THREADS")) T = (unsigned)std::max(1, std::min(64, atoi(e)));
-        for (unsigned t = 0; t < T; ++t) workers.emplace_back([this, nb]() {
+        const bool zlib_only = getenv("PHI_HOST_ZLIB_ONLY") != nullptr;
+        for (unsigned t = 0; t < T; ++t) workers.emplace_back([this, nb, zlib_only]() {
             z_stream zs; memset(&zs, 0, sizeof zs);
             if (inflateInit2(&zs, -15) != Z_OK) { fail_block(); return; }
             for (;;) {
                 const size_t i = next_block.fetch_add(1);
                 if (i >= nb || stop.load(std::memory_order_relaxed)) break;
                 const BgzfIndex::Block &k = bz.blocks[i];
-                bool ok = inflateReset(&zs) == Z_OK;
-                if (ok) {
+                // the whole-buffer decoder first (fast_inflate.h); zlib decides when it does not produce exactly what the trailer promises
+                size_t got = 0, used = 0;
+                bool ok = !zlib_only && phi_inflate::inflate_raw(bz.map + k.in_off, k.in_len, (unsigned char *)base + k.out_off, k.out_len, &got, &used, [](size_t) {}) == 0 &&
+                          got == k.out_len && used == k.in_len &&
+                          (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)(base + k.out_off), k.out_len) == k.crc;
+                if (!ok && (ok = inflateReset(&zs) == Z_OK)) {
                     zs.next_in = const_cast<Bytef *>(bz.map + k.in_off); zs.avail_in = (uInt)k.in_len;
                     zs.next_out = (Bytef *)(base + k.out_off); zs.avail_out = k.out_len;
                     const int rc = inflate(&zs, Z_FINISH);
@@ -285,18 +348,6 @@ size_t text_size_hint(const char *path)
         fclose(raw);
     }
     return hint;
-}
-
-// f(i) for i in [0, n) on up to 16 host threads (items are handed out one by one: walks differ in length)
-template <class F>
-void parallel_for(size_t n, F f)
-{
-    const unsigned T = (unsigned)std::min<size_t>(std::min<size_t>(n, 16), std::max(1u, std::thread::hardware_concurrency()));
-    if (T <= 1) { for (size_t i = 0; i < n; ++i) f(i); return; }
-    std::atomic<size_t> next{0};
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < T; ++t) th.emplace_back([&]() { for (;;) { const size_t i = next.fetch_add(1); if (i >= n) break; f(i); } });
-    for (auto &x : th) x.join();
 }
 
 }  // namespace

@@ -490,3 +490,50 @@ def test_reads_parsed_in_parallel_chunks_equal_the_serial_parse(tmp_path, monkey
             d = probe(gfa, str(tmp_path / fname), str(tmp_path / "p.phiarr"))
             got, _ = phi_b200.load_reads(str(tmp_path / fname))
             assert got.read_off.tolist() == d["read_off"].tolist() and bytes(got.read_bases) == bytes(d["read_bases"]), fname
+
+
+def test_whole_buffer_inflate_and_zlib_read_the_same(tmp_path, monkeypatch):
+    """Single-member gzip and bgzip files go through the library's own whole-buffer deflate decoder (fast_inflate.h; the gzip trailer's
+    CRC-32 and size are verified, zlib takes over on any doubt); PHI_HOST_ZLIB_ONLY=1 forces zlib.  Same graph, same reads — for every
+    compression level, stored blocks (level 0) included."""
+    import zlib
+    c = Case("synth_small")
+    gfa = str(tmp_path / "g.gfa")
+    synth.write_gfa(c.graph, gfa)
+    text = open(gfa, "rb").read()
+    ro = c.reads.read_off.astype(np.int64)
+    fq = b"".join(b"@r%d\n" % i + bytes(c.reads.read_bases[ro[i]:ro[i + 1]]) + b"\n+\n" + b"I" * int(ro[i + 1] - ro[i]) + b"\n" for i in range(c.reads.n_reads))
+    want_g = phi_b200.load_gfa(gfa)
+    for level in (0, 1, 6, 9):
+        for kind in ("gz", "bgzf"):
+            pg, pr = str(tmp_path / f"g{level}.{kind}.gfa.gz"), str(tmp_path / f"r{level}.{kind}.fq.gz")
+            for path, data in ((pg, text), (pr, fq)):
+                with open(path, "wb") as f:
+                    f.write(gzip.compress(data, level) if kind == "gz" else bgzf_bytes(data, 20000, level))
+            for zlib_only in (False, True):
+                if zlib_only:
+                    monkeypatch.setenv("PHI_HOST_ZLIB_ONLY", "1")
+                else:
+                    monkeypatch.delenv("PHI_HOST_ZLIB_ONLY", raising=False)
+                g = phi_b200.load_gfa(pg)
+                for fld in ("seg_off", "seg_bases", "walk_off", "walk_vtx", "top_order_map"):
+                    assert np.array_equal(getattr(g, fld), getattr(want_g, fld)), (level, kind, zlib_only, fld)
+                rd, names = phi_b200.load_reads(pr)
+                assert np.array_equal(rd.read_off, c.reads.read_off) and np.array_equal(rd.read_bases, c.reads.read_bases), (level, kind, zlib_only)
+    # a member with a header name and comment (gzip -N style) and one whose CRC is wrong: the first is read, the second is zlib's to judge
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = co.compress(fq) + co.flush()
+    import struct
+    named = b"\x1f\x8b\x08\x18\x00\x00\x00\x00\x00\x03" + b"reads.fq\x00" + b"a comment\x00" + body + struct.pack("<II", zlib.crc32(fq) & 0xffffffff, len(fq))
+    p = str(tmp_path / "named.fq.gz")
+    with open(p, "wb") as f:
+        f.write(named)
+    monkeypatch.delenv("PHI_HOST_ZLIB_ONLY", raising=False)
+    rd, _ = phi_b200.load_reads(p)
+    assert np.array_equal(rd.read_bases, c.reads.read_bases)
+    bad = bytearray(named)
+    bad[-8] ^= 0xFF                                                          # CRC-32 field
+    with open(p, "wb") as f:
+        f.write(bytes(bad))
+    with pytest.raises(phi_b200.PhiGpuError):                                # gzread reports the data error at the end: so does this loader
+        phi_b200.load_reads(p)

@@ -84,3 +84,16 @@ def test_threaded_loaders_and_partition_helpers_are_clean(drivers, san, tmp_path
                 {"PHI_HOST_PARSE_CHUNK": "301", "PHI_HOST_INFLATE_THREADS": "3", "PHI_SHARD_THREADS": "16"}):
         assert run_clean(drivers[san], ["load"] + files, env) == ref          # and the same counts whatever the threading
     assert "reads.fq reads rc=0 n=%d bases=%d" % (c.reads.n_reads, int(ro[-1])) in ref
+
+
+def test_whole_buffer_inflate_against_zlib_under_asan(tmp_path):
+    """phi_b200/csrc/fast_inflate.h: every zlib level and strategy on nine kinds of text decodes to the same bytes with the same
+    consumed length; cut and bit-flipped streams are rejected or decoded inside the buffers (ASan + UBSan watch the bounds)."""
+    exe = str(tmp_path / "inflate_fuzz")
+    p = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                        os.path.join(ROOT, "tests", "inflate_fuzz.cpp"), "-o", exe, "-lz"], capture_output=True, text=True)
+    if p.returncode != 0 and ("cannot find" in p.stderr or "not supported" in p.stderr):
+        pytest.skip("no -fsanitize=address runtime")
+    assert p.returncode == 0, p.stderr[-3000:]
+    out = run_clean(exe, ["6"])
+    assert "inflate_raw == zlib on" in out
