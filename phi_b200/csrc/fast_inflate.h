@@ -185,19 +185,19 @@ static int inflate_raw(const uint8_t *in, size_t n, uint8_t *out, size_t cap, si
             if (!build_table(lens, type == 1 ? 288 : hlit, LIT_ROOT, *lit, litlen_entry)) return 2;
             if (!build_table(lens + 288, hdist, DIST_ROOT, *dist, dist_entry)) return 2;
             for (;;) {
-                if (r.pos + 8 <= n && op + 280 <= cap) {
-                    // fast iteration: the refill leaves >= 56 bits (a length + distance pair takes <= 48) and there is room for three
-                    // literals or the longest match plus the eight-byte copy slack, so nothing below checks input or output bounds
+                if (r.pos + 8 <= n && op + 336 <= cap) {
+                    // fast iteration: the refill leaves >= 56 bits (a length + distance pair takes <= 48) and there is room for a run of
+                    // literals (<= 63: one per bit) or the longest match plus the eight-byte copy slack, so nothing below checks input
+                    // or output bounds
                     r.refill();
                     uint32_t e = lit->e[r.peek(LIT_ROOT)];
-                    if (!(e & 0x300)) {                                  // up to three literals per refill (<= 45 bits)
+                    if (!(e & 0x300)) {                                  // a run of literals from one refill: while a whole code (<= 15 bits) is there
                         if (!(e & 255)) return 2;
-                        r.drop(e & 255); out[op++] = (uint8_t)(e >> 16);
-                        e = lit->e[r.peek(LIT_ROOT)];
-                        if (!(e & 0x300) && (e & 255)) {
+                        for (;;) {
                             r.drop(e & 255); out[op++] = (uint8_t)(e >> 16);
+                            if (r.cnt < MAX_BITS) break;
                             e = lit->e[r.peek(LIT_ROOT)];
-                            if (!(e & 0x300) && (e & 255)) { r.drop(e & 255); out[op++] = (uint8_t)(e >> 16); }
+                            if ((e & 0x300) || !(e & 255)) break;
                         }
                         continue;
                     }
