@@ -193,13 +193,14 @@ static int inflate_raw(const uint8_t *in, size_t n, uint8_t *out, size_t cap, si
                     uint32_t e = lit->e[r.peek(LIT_ROOT)];
                     if (!(e & 0x300)) {                                  // a run of literals from one refill: while a whole code (<= 15 bits) is there
                         if (!(e & 255)) return 2;
+                        bool more = false;
                         for (;;) {
                             r.drop(e & 255); out[op++] = (uint8_t)(e >> 16);
                             if (r.cnt < MAX_BITS) break;
                             e = lit->e[r.peek(LIT_ROOT)];
-                            if ((e & 0x300) || !(e & 255)) break;
+                            if ((e & 0x300) || !(e & 255)) { more = r.cnt >= 48 && (e & 255); break; }
                         }
-                        continue;
+                        if (!more) continue;                             // (else: the length / end code that ended the run is decoded from the same bits)
                     }
                     if (((e >> 8) & 3) == K_SUB) { r.drop(LIT_ROOT); e = lit->e[(e >> 16) + r.peek((e >> 10) & 63)]; }
                     if (!(e & 255)) return 2;
