@@ -638,10 +638,10 @@ extern "C" int phi_host_graph_load(const char *gfa_path, phi_host_graph **out, c
         // CSR over the forward source vertices, a vertex's arcs in L-line order (counting sort by source: stable), multi-arcs removed
         // (gfa_cleanup) by a scan of the vertex's own short list
         std::vector<uint64_t> adj_off((size_t)V + 1, 0);
-        auto each_arc = [&](auto &&f) {
+        auto each_arc = [&](auto &&fn) {
             for (auto &ab : arcs) {
-                if (!(ab.first & 1)) f(ab.first >> 1, ab.second);               // only arcs leaving a forward vertex count
-                if (!((ab.second ^ 1) & 1)) f((ab.second ^ 1) >> 1, ab.first ^ 1);   // the reverse-complement arc of the same L-line
+                if (!(ab.first & 1)) fn(ab.first >> 1, ab.second);              // only arcs leaving a forward vertex count
+                if (!((ab.second ^ 1) & 1)) fn((ab.second ^ 1) >> 1, ab.first ^ 1);  // the reverse-complement arc of the same L-line
             }
         };
         each_arc([&](uint32_t a, uint32_t) { adj_off[a + 1]++; });
