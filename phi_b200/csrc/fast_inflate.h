@@ -285,7 +285,7 @@ static int inflate_raw(const uint8_t *in, size_t n, uint8_t *out, size_t cap, si
 }
 
 // gzip member header (RFC 1952) at b[0, n): offset of the deflate data, or 0 when this is not a plain gzip header.
-static size_t gzip_header_size(const uint8_t *b, size_t n)
+static inline size_t gzip_header_size(const uint8_t *b, size_t n)
 {
     if (n < 18 || b[0] != 0x1f || b[1] != 0x8b || b[2] != 8 || (b[3] & 0xE0)) return 0;
     const uint8_t flg = b[3];

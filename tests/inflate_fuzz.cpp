@@ -37,9 +37,16 @@ int main(int argc, char **argv)
             switch (kind) {
             case 0: for (auto &c : t) c = (char)rng(); break;                                        // incompressible
             case 1: for (auto &c : t) c = "ACGT"[rng() & 3]; break;                                  // DNA
-            case 2: { size_t i = 0; while (i < n) { std::string rec = "@read" + std::to_string(rng() % 100000) + "\n"; std::string s(150, 'A');
-                      for (auto &c : s) c = "ACGTN"[rng() % 5 == 0 ? 4 : rng() & 3]; rec += s + "\n+\n" + std::string(150, (char)('!' + rng() % 40)) + "\n";
-                      for (size_t j = 0; j < rec.size() && i < n; ++j) t[i++] = rec[j]; } break; }    // FASTQ-like
+            case 2: {                                                                                // FASTQ-like
+                size_t i = 0;
+                while (i < n) {
+                    std::string rec = "@read" + std::to_string(rng() % 100000) + "\n", s(150, 'A');
+                    for (auto &c : s) c = "ACGTN"[rng() % 5 == 0 ? 4 : rng() & 3];
+                    rec += s + "\n+\n" + std::string(150, (char)('!' + rng() % 40)) + "\n";
+                    for (size_t j = 0; j < rec.size() && i < n; ++j) t[i++] = rec[j];
+                }
+                break;
+            }
             case 3: { size_t i = 0; unsigned v = 1; while (i < n) { std::string tok = ">s" + std::to_string(v); v += 1 + rng() % 3;
                       for (size_t j = 0; j < tok.size() && i < n; ++j) t[i++] = tok[j]; } break; }   // W-line-like
             case 4: { char c = 'A'; size_t i = 0; while (i < n) { size_t run = 1 + rng() % 3000; for (size_t j = 0; j < run && i < n; ++j) t[i++] = c; c = (char)('A' + rng() % 26); } break; }   // long runs (distance 1 matches)
